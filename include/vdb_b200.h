@@ -1,0 +1,173 @@
+/*
+ * vdb_b200.h — C ABI of the B200-native search backend for lab-1806-vec-db.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. A Rust
+ * `extern "C"` block binds these 1:1 (rust_shim/ and INTEGRATION.md show the binding a
+ * maintainer of the reference would add). The reference has no FFI seam of its own; each
+ * entry point names the reference trait method / function it replaces (paths relative to the
+ * reference repository, v0.8.1).
+ *
+ * Conventions
+ *  - every function returns 0 (VDB_OK) or a VDB_E* code; vdb_last_error() gives the message of
+ *    the last failure on the calling thread. The reference panics on misuse (assert!), so the
+ *    Rust shim panics on non-zero. CUDA errors are never swallowed and there is NO CPU fallback.
+ *  - host-pointer entry points copy inputs to the GPU and results back; the `_dev` variants
+ *    take device pointers plus a cudaStream_t (as void*) and are fully asynchronous.
+ *  - rows/queries are row-major `dim`-element vectors of `dtype` (VecSet<T>, src/vec_set.rs:15-30).
+ *  - results are SoA: ids[nq*k] (u64), dist[nq*k] (f32), counts[nq] = valid entries per query
+ *    (min(k, n)); entries are ascending by (distance, id) exactly like
+ *    ResultSet::into_sorted_vec (src/index_algorithm/candidate_pair.rs:36-40, 76-78).
+ *    Unused tail entries are id = UINT64_MAX, dist = NaN.
+ *  - search calls are re-entrant on one handle (the reference calls knn from rayon workers and
+ *    Python threads under a read lock: src/database/mod.rs:255, examples/bench.rs:415).
+ */
+#ifndef VDB_B200_H
+#define VDB_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VDB_OK = 0, VDB_EINVAL = 1, VDB_ECUDA = 2, VDB_ENOMEM = 3, VDB_EUNSUPPORTED = 4 };
+enum { VDB_L2SQR = 0, VDB_COSINE = 1 }; /* DistanceAlgorithm, src/distance/mod.rs:18-28 */
+enum { VDB_F32 = 0, VDB_U8 = 1 };       /* Scalar, src/scalar.rs:117-119 */
+
+typedef struct vdb_dataset vdb_dataset; /* device mirror of one VecSet<T> (or one row shard of it) */
+typedef struct vdb_pq vdb_pq;           /* device mirror of a PQTable<T> (src/distance/pq_table.rs:116-137) */
+typedef struct vdb_ivf vdb_ivf;         /* device mirror of an IVFIndex<T> (src/index_algorithm/ivf_index.rs:34-47) */
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+const char* vdb_last_error(void);
+int vdb_version(void);
+int vdb_device_count(int* out);
+/* Selects the CUDA device used by handles created afterwards on this thread. */
+int vdb_set_device(int device);
+
+/* ---- VecSet mirror -------------------------------------------------------------------------- */
+/* Replaces the storage side of FlatIndex::from_vec_set (src/index_algorithm/flat_index.rs:59-70):
+ * uploads `n` rows to HBM (rows padded to a 16-byte multiple so every row starts 128-bit aligned).
+ * `id_base` is added to local row numbers in results (row-sharding across GPUs: shard r holds
+ * rows [id_base, id_base+n)); id_base + n must be < 2^32. Host memory stays authoritative. */
+int vdb_dataset_create(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
+                       uint64_t id_base, vdb_dataset** out);
+/* Same, but adopts rows already resident on the device (row pitch in elements; pitch*sizeof(T)
+ * must be a multiple of 16 and pad columns must be zero). The memory is NOT owned by the handle. */
+int vdb_dataset_create_dev(const void* d_rows, uint64_t n, uint32_t dim, uint32_t pitch, int dtype,
+                           int metric, uint64_t id_base, vdb_dataset** out);
+/* VecSet::push / DynamicIndex::batch_add (src/vec_set.rs:113-118, src/database/dynamic_index.rs:49-56) */
+int vdb_dataset_append(vdb_dataset* ds, const void* rows, uint64_t n);
+/* VecSet::swap_remove (src/vec_set.rs:131-137): row `idx` is overwritten by the last row. */
+int vdb_dataset_swap_remove(vdb_dataset* ds, uint64_t idx);
+int vdb_dataset_len(const vdb_dataset* ds, uint64_t* n);
+int vdb_dataset_dim(const vdb_dataset* ds, uint32_t* dim);
+int vdb_dataset_destroy(vdb_dataset* ds);
+
+/* ---- distance primitives -------------------------------------------------------------------- */
+/* DistanceAdapter<[T],[T]>::distance for `count` independent pairs a[i], b[i]
+ * (src/distance/mod.rs:106-113; pyo3 calc_dist src/pyo3/mod.rs:43-48 is count == 1).
+ * metric may also be VDB_DOT (the trait primitive dot_product, src/distance/mod.rs:43). */
+enum { VDB_DOT = 2 };
+int vdb_calc_dist(const void* a, const void* b, uint64_t count, uint32_t dim, int dtype, int metric,
+                  float* out);
+/* DistanceAlgorithm::dist_cache for every row (src/distance/mod.rs:31-36; HNSW push_init
+ * src/index_algorithm/hnsw_index.rs:251-254, 371-379): L2Sqr -> ||v||^2, Cosine -> ||v||. */
+int vdb_row_cache(const vdb_dataset* ds, float* out);
+/* Batched HNSW candidate evaluation, cached form (src/index_algorithm/hnsw_index.rs:351-358,
+ * src/distance/mod.rs:54-57, 67-69). Query j is compared with rows cand_ids[cand_off[j]..cand_off[j+1]);
+ * out has cand_off[nq] entries. cand_ids are LOCAL row numbers of `ds`. */
+int vdb_gather_dist(const vdb_dataset* ds, const void* queries, uint32_t nq, const uint32_t* cand_ids,
+                    const uint64_t* cand_off, float* out);
+
+/* ---- Flat ------------------------------------------------------------------------------------ */
+/* IndexKNN::knn for FlatIndex (src/index_algorithm/flat_index.rs:48-57), batched over nq queries
+ * (nq == 1 is the unchanged trait call; nq > 1 is the additive batch entry used by bench drivers,
+ * examples/bench.rs:414-418, src/bin/gen_gnd.rs:65-68). Exact: the k smallest by (distance, id),
+ * distances in the difference form sum((q-x)^2) / the 3-dot cosine form. */
+int vdb_flat_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32_t k, uint64_t* ids,
+                 float* dist, uint32_t* counts);
+int vdb_flat_knn_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
+                     uint64_t* d_ids, float* d_dist, uint32_t* d_counts, void* stream);
+/* Row-sharded search, step 1: this shard's k best per query as packed sortable keys
+ * (high 32 bits = order-preserving distance bits, low 32 bits = global id), [nq, k], ascending,
+ * padded with UINT64_MAX. Step 2 (after an NCCL all-gather of the shards' keys):
+ * vdb_merge_keys_dev merges `nlists` such lists per query: keys is [nlists, nq, k]. */
+int vdb_flat_knn_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
+                          uint64_t* d_keys, void* stream);
+int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t k,
+                       uint64_t* d_ids, float* d_dist, uint32_t* d_counts, void* stream);
+/* Selects the Flat implementation: 0 = auto, 1 = FP32 streaming scan (K1), 2 = tensor-core
+ * contraction + FP32 rerank (K2, batched L2Sqr f32 only). Results are identical either way. */
+int vdb_flat_set_path(int path);
+
+/* ---- k-means (IVF / PQ training) ---------------------------------------------------------- */
+/* find_nearest for n rows (src/distance/k_means.rs:40-57, 117-120, 166-170;
+ * src/index_algorithm/ivf_index.rs:89-93): out[i] = argmin_c d(rows[i][sel_lo..sel_hi], centroids[c])
+ * by (distance, c). centroids is [k, sel_hi-sel_lo] of the rows' dtype. */
+int vdb_kmeans_assign(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
+                      const void* centroids, uint32_t k, uint32_t sel_lo, uint32_t sel_hi,
+                      uint32_t* out);
+int vdb_kmeans_assign_ds(const vdb_dataset* ds, const void* centroids, uint32_t k, uint32_t sel_lo,
+                         uint32_t sel_hi, uint32_t* out);
+/* Lloyd iterations of KMeans::from_vec_set from given initial centroids
+ * (src/distance/k_means.rs:108-161): assignment, per-centroid mean summed in ascending member
+ * order in f32, empty clusters keep their centroid, stop when max squared shift < tol.
+ * centroids: in = initial (k-means++ draws stay on the host side because they consume the
+ * caller's RNG, k_means.rs:61-87), out = trained. *iters = iterations executed. */
+int vdb_kmeans_train(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
+                     void* centroids, uint32_t k, uint32_t sel_lo, uint32_t sel_hi, uint32_t max_iter,
+                     float tol, uint32_t* iters);
+/* k-means++ weight update w[i] = min(w[i], d(c, rows[i][sel])) (src/distance/k_means.rs:75-77). */
+int vdb_kmeans_pp_weights(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
+                          const void* centroid, uint32_t sel_lo, uint32_t sel_hi, float* weights);
+
+/* ---- PQ ------------------------------------------------------------------------------------- */
+/* pq_groups (src/distance/pq_table.rs:38-53): out is [m, 2] (start, end). */
+int vdb_pq_groups(uint32_t dim, uint32_t m, uint32_t* out);
+/* Builds the device PQ table from trained codebooks (group g = [2^n_bits, len_g], concatenated)
+ * and encodes every row of `ds` (pq_encode + the encode loop, src/distance/pq_table.rs:66-91,
+ * 178-181). If `codes` is non-NULL it receives the reference-layout codes [n, encoded_dim]. */
+int vdb_pq_create(const vdb_dataset* ds, const void* codebooks, uint32_t m, uint32_t n_bits,
+                  uint8_t* codes, vdb_pq** out);
+/* Same, from codes computed earlier (PQTable::load, src/distance/pq_table.rs:232-237). */
+int vdb_pq_create_from_codes(const vdb_dataset* ds, const void* codebooks, uint32_t m, uint32_t n_bits,
+                             const uint8_t* codes, vdb_pq** out);
+int vdb_pq_destroy(vdb_pq* pq);
+/* PQTable::create_lookup (src/distance/pq_table.rs:195-224): lut is [nq, m*2^n_bits], qcache [nq]. */
+int vdb_pq_lut(const vdb_pq* pq, const void* queries, uint32_t nq, float* lut, float* qcache);
+/* ADC distance of every code against query LUTs (src/distance/pq_table.rs:239-301): out [nq, n]. */
+int vdb_pq_adc_all(const vdb_pq* pq, const void* queries, uint32_t nq, float* out);
+/* IndexPQ::knn_pq for FlatIndex (src/index_algorithm/flat_index.rs:84-104): ADC scan into the
+ * max(ef,k) best by (adc, id), then exact rerank (candidate_pair.rs:102-108). */
+int vdb_pq_knn(const vdb_dataset* ds, const vdb_pq* pq, const void* queries, uint32_t nq, uint32_t k,
+               uint32_t ef, uint64_t* ids, float* dist, uint32_t* counts);
+int vdb_pq_knn_dev(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq,
+                   uint32_t k, uint32_t ef, uint64_t* d_ids, float* d_dist, uint32_t* d_counts,
+                   void* stream);
+
+/* ---- IVF ------------------------------------------------------------------------------------ */
+/* IVFIndex::from_vec_set after training (src/index_algorithm/ivf_index.rs:88-106): assigns every
+ * row to its nearest centroid and builds the inverted lists (members ascending). `assign_out`
+ * (may be NULL) receives the per-row list id. */
+int vdb_ivf_create(const vdb_dataset* ds, const void* centroids, uint32_t nlist, uint32_t* assign_out,
+                   vdb_ivf** out);
+int vdb_ivf_destroy(vdb_ivf* ivf);
+/* Copies the lists out: offsets [nlist+1], members [n] (local row ids). */
+int vdb_ivf_lists(const vdb_ivf* ivf, uint64_t* offsets, uint32_t* members);
+/* IndexKNNWithEf::knn_with_ef for IVFIndex (src/index_algorithm/ivf_index.rs:143-154):
+ * find_n_nearest centroids (src/distance/k_means.rs:174-191) then scan the probed lists. */
+int vdb_ivf_knn(const vdb_dataset* ds, const vdb_ivf* ivf, const void* queries, uint32_t nq, uint32_t k,
+                uint32_t n_probes, uint64_t* ids, float* dist, uint32_t* counts);
+int vdb_ivf_knn_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq,
+                    uint32_t k, uint32_t n_probes, uint64_t* d_ids, float* d_dist, uint32_t* d_counts,
+                    void* stream);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* Number of kernels this library has launched on the calling process since load. */
+uint64_t vdb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDB_B200_H */

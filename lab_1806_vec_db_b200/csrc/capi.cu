@@ -1,0 +1,326 @@
+// capi.cu — the extern "C" boundary declared in include/vdb_b200.h.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "dataset.cuh"
+#include "index.cuh"
+#include "topk.cuh"
+
+namespace {
+thread_local std::string t_error;
+thread_local int t_device = -1;
+
+template <class F> int guarded(F f) {
+    try {
+        f();
+        return VDB_OK;
+    } catch (const vdb::Error& e) {
+        t_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        t_error = "host out of memory";
+        return VDB_ENOMEM;
+    } catch (const std::exception& e) {
+        t_error = e.what();
+        return VDB_ECUDA;
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        VDB_CUDA(cudaGetDevice(&prev));
+        if (dev != prev) VDB_CUDA(cudaSetDevice(dev));
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// per-call stream for the host-pointer entry points: re-entrant, no cross-call serialisation
+struct CallStream {
+    cudaStream_t s = nullptr;
+    CallStream() { VDB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+    ~CallStream() {
+        if (s) cudaStreamDestroy(s);
+    }
+    void sync() { VDB_CUDA(cudaStreamSynchronize(s)); }
+};
+
+int current_device() {
+    if (t_device >= 0) return t_device;
+    int d = 0;
+    VDB_CUDA(cudaGetDevice(&d));
+    return d;
+}
+
+void check_dtype_metric(int dtype, int metric) {
+    VDB_REQUIRE(dtype == VDB_F32 || dtype == VDB_U8, "dtype must be VDB_F32 or VDB_U8");
+    VDB_REQUIRE(metric == VDB_L2SQR || metric == VDB_COSINE, "metric must be VDB_L2SQR or VDB_COSINE");
+}
+
+void upload_rows(vdb_dataset* ds, uint64_t at, const void* rows, uint64_t n, cudaStream_t st) {
+    if (n == 0) return;
+    const size_t es = ds->elem_size();
+    uint8_t* dst = (uint8_t*)ds->d_rows + at * ds->pitch_bytes();
+    if (ds->pitch == ds->dim) {
+        VDB_CUDA(cudaMemcpyAsync(dst, rows, n * ds->pitch_bytes(), cudaMemcpyHostToDevice, st));
+    } else {
+        VDB_CUDA(cudaMemsetAsync(dst, 0, n * ds->pitch_bytes(), st));
+        VDB_CUDA(cudaMemcpy2DAsync(dst, ds->pitch_bytes(), rows, ds->dim * es, ds->dim * es, n,
+                                   cudaMemcpyHostToDevice, st));
+    }
+}
+
+void drop_side_arrays(vdb_dataset* ds) {
+    if (ds->d_lo) cudaFree(ds->d_lo);
+    if (ds->d_sqnorm) cudaFree(ds->d_sqnorm);
+    ds->d_lo = nullptr;
+    ds->d_sqnorm = nullptr;
+    ds->side_n = 0;
+}
+
+// copies nq query rows to the device, runs `body(d_queries, d_ids, d_dist, d_counts, stream)`, copies back
+template <class Body>
+void host_search(int device, const void* queries, uint32_t nq, size_t qbytes_per, uint32_t k, uint64_t* ids,
+                 float* dist, uint32_t* counts, Body body) {
+    DeviceGuard g(device);
+    CallStream cs;
+    vdb::DevBuf dq((size_t)nq * qbytes_per, cs.s);
+    vdb::DevBuf dids((size_t)nq * k * 8, cs.s), ddist((size_t)nq * k * 4, cs.s), dcnt((size_t)nq * 4, cs.s);
+    if (nq) VDB_CUDA(cudaMemcpyAsync(dq.p, queries, (size_t)nq * qbytes_per, cudaMemcpyHostToDevice, cs.s));
+    body(dq.p, dids.as<uint64_t>(), ddist.as<float>(), dcnt.as<uint32_t>(), cs.s);
+    if (nq && k) {
+        VDB_CUDA(cudaMemcpyAsync(ids, dids.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, cs.s));
+        VDB_CUDA(cudaMemcpyAsync(dist, ddist.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, cs.s));
+    }
+    if (nq) VDB_CUDA(cudaMemcpyAsync(counts, dcnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs.s));
+    cs.sync();
+    dq.release();
+    dids.release();
+    ddist.release();
+    dcnt.release();
+    cs.sync();
+}
+}  // namespace
+
+extern "C" {
+
+const char* vdb_last_error(void) { return t_error.c_str(); }
+int vdb_version(void) { return 801; /* tracks reference v0.8.1 */ }
+uint64_t vdb_launch_count(void) { return vdb::g_launches.load(); }
+
+int vdb_device_count(int* out) {
+    return guarded([&] {
+        VDB_REQUIRE(out, "out is NULL");
+        VDB_CUDA(cudaGetDeviceCount(out));
+    });
+}
+int vdb_set_device(int device) {
+    return guarded([&] {
+        int n = 0;
+        VDB_CUDA(cudaGetDeviceCount(&n));
+        VDB_REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+        VDB_CUDA(cudaSetDevice(device));
+        t_device = device;
+    });
+}
+
+// ---- dataset -------------------------------------------------------------------------------------
+int vdb_dataset_create(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric, uint64_t id_base,
+                       vdb_dataset** out) {
+    return guarded([&] {
+        VDB_REQUIRE(out, "out is NULL");
+        VDB_REQUIRE(dim > 0, "dim must be > 0");
+        VDB_REQUIRE(rows || n == 0, "rows is NULL");
+        check_dtype_metric(dtype, metric);
+        VDB_REQUIRE(id_base + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
+        auto ds = new vdb_dataset();
+        ds->device = current_device();
+        DeviceGuard g(ds->device);
+        ds->dim = dim;
+        ds->dtype = dtype;
+        ds->metric = metric;
+        ds->id_base = id_base;
+        ds->pitch = vdb::round_up(dim, vdb::vec_elems(dtype));
+        ds->n = n;
+        ds->cap = std::max<uint64_t>(n, 1);
+        try {
+            VDB_CUDA(cudaMalloc(&ds->d_rows, ds->cap * ds->pitch_bytes()));
+            CallStream cs;
+            upload_rows(ds, 0, rows, n, cs.s);
+            cs.sync();
+        } catch (...) {
+            if (ds->d_rows) cudaFree(ds->d_rows);
+            delete ds;
+            throw;
+        }
+        *out = ds;
+    });
+}
+
+int vdb_dataset_create_dev(const void* d_rows, uint64_t n, uint32_t dim, uint32_t pitch, int dtype, int metric,
+                           uint64_t id_base, vdb_dataset** out) {
+    return guarded([&] {
+        VDB_REQUIRE(out && (d_rows || n == 0), "NULL argument");
+        VDB_REQUIRE(dim > 0 && pitch >= dim, "need 0 < dim <= pitch");
+        check_dtype_metric(dtype, metric);
+        VDB_REQUIRE(pitch % vdb::vec_elems(dtype) == 0, "row pitch must be a multiple of 16 bytes");
+        VDB_REQUIRE(((uintptr_t)d_rows & 15) == 0, "device rows must be 16-byte aligned");
+        VDB_REQUIRE(id_base + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
+        auto ds = new vdb_dataset();
+        ds->device = current_device();
+        ds->d_rows = const_cast<void*>(d_rows);
+        ds->owned = false;
+        ds->n = ds->cap = n;
+        ds->dim = dim;
+        ds->pitch = pitch;
+        ds->dtype = dtype;
+        ds->metric = metric;
+        ds->id_base = id_base;
+        *out = ds;
+    });
+}
+
+int vdb_dataset_append(vdb_dataset* ds, const void* rows, uint64_t n) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && (rows || n == 0), "NULL argument");
+        VDB_REQUIRE(ds->owned, "cannot append to an adopted device dataset");
+        VDB_REQUIRE(ds->id_base + ds->n + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
+        DeviceGuard g(ds->device);
+        drop_side_arrays(ds);
+        CallStream cs;
+        if (ds->n + n > ds->cap) {  // amortised growth, like Vec::push
+            uint64_t cap = std::max<uint64_t>(ds->n + n, ds->cap + ds->cap / 2);
+            void* p = nullptr;
+            VDB_CUDA(cudaMalloc(&p, cap * ds->pitch_bytes()));
+            VDB_CUDA(cudaMemcpyAsync(p, ds->d_rows, ds->n * ds->pitch_bytes(), cudaMemcpyDeviceToDevice, cs.s));
+            cs.sync();
+            cudaFree(ds->d_rows);
+            ds->d_rows = p;
+            ds->cap = cap;
+        }
+        upload_rows(ds, ds->n, rows, n, cs.s);
+        cs.sync();
+        ds->n += n;
+    });
+}
+
+int vdb_dataset_swap_remove(vdb_dataset* ds, uint64_t idx) {
+    return guarded([&] {
+        VDB_REQUIRE(ds, "NULL dataset");
+        VDB_REQUIRE(ds->owned, "cannot mutate an adopted device dataset");
+        VDB_REQUIRE(idx < ds->n, "swap_remove index %llu out of range (len %llu)", (unsigned long long)idx,
+                    (unsigned long long)ds->n);
+        DeviceGuard g(ds->device);
+        drop_side_arrays(ds);
+        if (idx != ds->n - 1) {
+            uint8_t* base = (uint8_t*)ds->d_rows;
+            VDB_CUDA(cudaMemcpy(base + idx * ds->pitch_bytes(), base + (ds->n - 1) * ds->pitch_bytes(),
+                                ds->pitch_bytes(), cudaMemcpyDeviceToDevice));
+        }
+        ds->n -= 1;
+    });
+}
+int vdb_dataset_len(const vdb_dataset* ds, uint64_t* n) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && n, "NULL argument");
+        *n = ds->n;
+    });
+}
+int vdb_dataset_dim(const vdb_dataset* ds, uint32_t* dim) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && dim, "NULL argument");
+        *dim = ds->dim;
+    });
+}
+int vdb_dataset_destroy(vdb_dataset* ds) {
+    return guarded([&] {
+        if (!ds) return;
+        DeviceGuard g(ds->device);
+        drop_side_arrays(ds);
+        if (ds->owned && ds->d_rows) cudaFree(ds->d_rows);
+        delete ds;
+    });
+}
+
+// ---- Flat ------------------------------------------------------------------------------------------
+int vdb_flat_set_path(int path) {
+    return guarded([&] {
+        VDB_REQUIRE(path >= 0 && path <= 2, "path must be 0 (auto), 1 (scan) or 2 (tensor)");
+        vdb::g_flat_path = path;
+    });
+}
+
+static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                               cudaStream_t st) {
+    const int path = vdb::g_flat_path;
+    bool tensor = false;
+    if (path == 2) {
+        VDB_REQUIRE(vdb::flat_gemm_supported(ds, nq, k),
+                    "tensor-core Flat path needs f32 L2Sqr rows, dim %% 4 == 0 and k <= 1024");
+        tensor = true;
+    } else if (path == 0) {
+        tensor = nq >= 256 && vdb::flat_gemm_supported(ds, nq, k);
+    }
+    if (tensor) vdb::flat_gemm_keys(ds, d_q, nq, k, d_keys, st);
+    else vdb::flat_scan_keys(ds, d_q, nq, k, d_keys, st);
+}
+
+int vdb_flat_knn_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                          void* stream) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && (d_queries || nq == 0) && (d_keys || nq * (uint64_t)k == 0), "NULL argument");
+        DeviceGuard g(ds->device);
+        flat_keys_dispatch(ds, d_queries, nq, k, d_keys, (cudaStream_t)stream);
+    });
+}
+
+int vdb_flat_knn_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_ids,
+                     float* d_dist, uint32_t* d_counts, void* stream) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && (d_queries || nq == 0), "NULL argument");
+        VDB_REQUIRE(nq == 0 || d_counts, "d_counts is NULL");
+        VDB_REQUIRE(nq * (uint64_t)k == 0 || (d_ids && d_dist), "NULL result arrays");
+        DeviceGuard g(ds->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        vdb::DevBuf keys((size_t)nq * k * 8, st);
+        flat_keys_dispatch(ds, d_queries, nq, k, keys.as<uint64_t>(), st);
+        vdb::decode_keys(keys.as<uint64_t>(), nq, k, d_ids, d_dist, d_counts, st);
+    });
+}
+
+int vdb_flat_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32_t k, uint64_t* ids, float* dist,
+                 uint32_t* counts) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && (queries || nq == 0), "NULL argument");
+        VDB_REQUIRE(nq == 0 || counts, "counts is NULL");
+        VDB_REQUIRE(nq * (uint64_t)k == 0 || (ids && dist), "NULL result arrays");
+        host_search(ds->device, queries, nq, (size_t)ds->dim * ds->elem_size(), k, ids, dist, counts,
+                    [&](void* dq, uint64_t* dids, float* dd, uint32_t* dc, cudaStream_t st) {
+                        vdb::DevBuf keys((size_t)nq * k * 8, st);
+                        flat_keys_dispatch(ds, dq, nq, k, keys.as<uint64_t>(), st);
+                        vdb::decode_keys(keys.as<uint64_t>(), nq, k, dids, dd, dc, st);
+                    });
+    });
+}
+
+int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t k, uint64_t* d_ids,
+                       float* d_dist, uint32_t* d_counts, void* stream) {
+    return guarded([&] {
+        VDB_REQUIRE(nq * (uint64_t)k == 0 || (d_keys && d_ids && d_dist), "NULL argument");
+        VDB_REQUIRE(nlists > 0, "nlists must be > 0");
+        cudaStream_t st = (cudaStream_t)stream;
+        if (k == 0) {
+            if (nq && d_counts) VDB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, st));
+            return;
+        }
+        vdb::launch_merge_keys(d_keys, nlists, nq, k, true, k, nullptr, d_ids, d_dist, d_counts, st);
+    });
+}
+
+#include "capi_index.inc"
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// dataset.cuh — device mirror of a VecSet<T> (reference src/vec_set.rs:15-30) and internal launchers.
+#pragma once
+#include "common.cuh"
+
+struct vdb_dataset {
+    int device = 0;
+    void* d_rows = nullptr;   // [cap][pitch] of dtype, pad columns are zero
+    bool owned = true;
+    uint64_t n = 0, cap = 0;
+    uint32_t dim = 0;
+    uint32_t pitch = 0;       // row pitch in ELEMENTS; pitch * elem_size is a multiple of 16 bytes
+    int dtype = VDB_F32;
+    int metric = VDB_L2SQR;
+    uint64_t id_base = 0;
+    // lazily built side arrays for the tensor-core path (K2); invalidated on mutation
+    float* d_lo = nullptr;    // tf32 residual x - tf32(x), [n][pitch]
+    float* d_sqnorm = nullptr;  // ||x||^2 (fp32), [n]
+    uint64_t side_n = 0;      // number of rows the side arrays cover
+    uint32_t elem_size() const { return dtype == VDB_F32 ? 4u : 1u; }
+    size_t pitch_bytes() const { return (size_t)pitch * elem_size(); }
+};
+
+namespace vdb {
+
+inline uint32_t vec_elems(int dtype) { return dtype == VDB_F32 ? 4u : 16u; }  // elements per 16-byte load
+
+// ---- query preparation: T[nq][dim] -> f32 tile layout used by the scan kernels --------------
+// layout per query: [planes][nit*32] float4, where element e of the (zero padded) row lives in
+// plane (e % VEC) / 4, float4 index e / VEC, component e % 4  (VEC = 4 -> 1 plane, VEC = 16 -> 4).
+struct QueryTile {
+    DevBuf q;        // [nq][qstride] f32
+    DevBuf qcache;   // [nq] f32: ||q|| (cosine) / ||q||^2 (l2) in plain f32
+    uint32_t qstride = 0;  // floats per query
+    uint32_t nvec = 0, nit = 0;
+};
+QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st);
+
+// ---- Flat exact scan (K1) ---------------------------------------------------------------------
+// keys out: [nq][k] ascending, KEY_NONE padded. If `d_members` != nullptr the scan visits only the
+// rows listed per query (IVF probe scan): see ivf.cu.
+void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
+                    uint64_t* d_keys, cudaStream_t st);
+// decode [nq][k] keys into the SoA result arrays
+void decode_keys(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
+                 uint32_t* d_counts, cudaStream_t st);
+
+// ---- Flat tensor-core path (K2) ----------------------------------------------------------------
+bool flat_gemm_supported(const vdb_dataset* ds, uint32_t nq, uint32_t k);
+void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
+                    uint64_t* d_keys, cudaStream_t st);
+
+// exact distances of listed rows: out[j] for pairs (query qidx[j], local row rid[j]); difference
+// form / 3-dot cosine (mode 0) or the cached form of hnsw_index.rs:351-358 (mode 1)
+void pair_distances(const vdb_dataset* ds, const float* d_qtile, uint32_t qstride, const float* d_qcache,
+                    const float* d_rowcache, const uint32_t* d_qidx, const uint32_t* d_rid, uint64_t npairs,
+                    int mode, float* d_out, cudaStream_t st);
+
+extern int g_flat_path;
+
+}  // namespace vdb

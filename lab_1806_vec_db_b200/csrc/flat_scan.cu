@@ -1,0 +1,413 @@
+// flat_scan.cu — K1: exact Flat kNN as one streaming pass over the row shard.
+//
+// Replaces FlatIndex::knn (reference src/index_algorithm/flat_index.rs:48-57): for every row the
+// difference-form L2 sum((q-x)^2) (src/distance/mod.rs:75-77) or the 3-dot cosine
+// (src/distance/mod.rs:60-69), then the k smallest by (distance, id)
+// (src/index_algorithm/candidate_pair.rs:36-40, 61-74).
+//
+// HBM-bound design: each warp streams R consecutive rows with 128-bit L1-bypassing loads
+// (double-buffered in registers), up to NQ=8 queries are resident in shared memory and share every
+// row byte, partial sums are reduced with a V-1 shuffle reduce-scatter, and candidates that beat the
+// CTA's current k-th best go to a shared-memory buffer that is bitonic-sorted only when it fills.
+// Algorithmic bytes per pass: n * pitch * sizeof(T) (+ the query tile and G*k keys).
+#include "dataset.cuh"
+#include "topk.cuh"
+
+namespace vdb {
+
+std::atomic<uint64_t> g_launches{0};
+int g_flat_path = 0;
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+
+struct ScanParams {
+    const uint8_t* rows;
+    uint64_t n;
+    uint64_t pitch_bytes;
+    uint32_t nvec, nit;
+    const float* q;        // query tile (see prepare_queries), first query of this pass
+    uint32_t qstride;      // floats per query
+    const float* qcache;   // per query ||q|| (cosine)
+    uint32_t nq_valid;
+    uint32_t K, P, limit, sync_every;
+    uint32_t id_base;
+    uint32_t iters;        // row-group iterations per warp
+    uint64_t* partial;     // [NQ][gridDim.x][K]
+};
+
+__device__ __forceinline__ float4 u4_as_f4(const uint4& u) {
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
+                       __uint_as_float(u.w));
+}
+__device__ __forceinline__ float4 bytes_as_f4(uint32_t w) {
+    return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu),
+                       (float)(w >> 24));
+}
+__device__ __forceinline__ uint32_t u4_comp(const uint4& u, int i) {
+    return i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w));
+}
+
+// PL = 1: f32 rows (4 elements per 16-byte load); PL = 4: u8 rows (16 elements per load)
+template <int NQ, int R, int METRIC, int PL>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int V = NQ * R;
+    constexpr int SH = 5 - Log2<V>::value;
+    constexpr int SHR = 5 - Log2<R>::value;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qs4 = p.qstride >> 2;  // float4 per query
+    const uint32_t plane4 = p.nit * 32;   // float4 per plane
+    float4* qs = reinterpret_cast<float4*>(smem);
+    uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)NQ * p.qstride * 4);
+    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
+
+    for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x)
+        qs[i] = (i / qs4 < p.nq_valid) ? reinterpret_cast<const float4*>(p.q)[i]
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    topk.init();
+
+    const int pidx = lane >> SH;
+    const int my_r = pidx / NQ, my_q = pidx % NQ;
+    const bool emitter = (lane & ((1 << SH) - 1)) == 0 && my_q < (int)p.nq_valid;
+    float qn = 0.f;
+    if (METRIC == VDB_COSINE && my_q < (int)p.nq_valid) qn = p.qcache[my_q];
+
+    const uint64_t total_warps = (uint64_t)gridDim.x * SCAN_WARPS;
+    uint64_t g = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
+    const uint64_t last_row = p.n - 1;
+
+    uint4 nxt[R], cur[R];
+    auto prefetch = [&](uint64_t gg, uint32_t it) {
+        const uint32_t c = it * 32 + lane;
+        const bool in = c < p.nvec;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            uint64_t row = gg * R + r;
+            row = row < last_row ? row : last_row;
+            nxt[r] = in ? ldg_stream_u4(p.rows + row * p.pitch_bytes + (size_t)c * 16)
+                        : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+
+    bool want = false;
+    prefetch(g, 0);
+    for (uint32_t gi = 0; gi < p.iters; ++gi, g += total_warps) {
+        float acc[V];
+        float xx[R];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) xx[r] = 0.f;
+
+        for (uint32_t it = 0; it < p.nit; ++it) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) cur[r] = nxt[r];
+            if (it + 1 < p.nit) prefetch(g, it + 1);
+            else if (gi + 1 < p.iters) prefetch(g + total_warps, 0);
+            const uint32_t c = it * 32 + lane;
+#pragma unroll
+            for (int pl = 0; pl < PL; ++pl) {
+                float4 x[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    {
+                    if constexpr (PL == 1) x[r] = u4_as_f4(cur[r]);
+                    else x[r] = bytes_as_f4(u4_comp(cur[r], pl));
+                }
+                if (METRIC == VDB_COSINE) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        xx[r] = fmaf(x[r].x, x[r].x, xx[r]);
+                        xx[r] = fmaf(x[r].y, x[r].y, xx[r]);
+                        xx[r] = fmaf(x[r].z, x[r].z, xx[r]);
+                        xx[r] = fmaf(x[r].w, x[r].w, xx[r]);
+                    }
+                }
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) {
+                    const float4 q = qs[(size_t)qi * qs4 + (size_t)pl * plane4 + c];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float a = acc[r * NQ + qi];
+                        if (METRIC == VDB_L2SQR) {
+                            const float d0 = x[r].x - q.x, d1 = x[r].y - q.y, d2 = x[r].z - q.z,
+                                        d3 = x[r].w - q.w;
+                            a = fmaf(d0, d0, a);
+                            a = fmaf(d1, d1, a);
+                            a = fmaf(d2, d2, a);
+                            a = fmaf(d3, d3, a);
+                        } else {
+                            a = fmaf(x[r].x, q.x, a);
+                            a = fmaf(x[r].y, q.y, a);
+                            a = fmaf(x[r].z, q.z, a);
+                            a = fmaf(x[r].w, q.w, a);
+                        }
+                        acc[r * NQ + qi] = a;
+                    }
+                }
+            }
+        }
+
+        // cross-lane reduction: lane L now holds the total of (row my_r, query my_q)
+        float tot = warp_reduce_scatter<V>(acc, lane);
+        if (METRIC == VDB_COSINE) {
+            const float xs = warp_reduce_scatter<R>(xx, lane);
+            const float xr = __shfl_sync(0xffffffffu, xs, my_r << SHR);
+            tot = 1.0f - tot / fmaxf(sqrtf(xr) * qn, 1e-10f);
+        }
+        const uint64_t row = g * R + my_r;
+        if (emitter && row < p.n) {
+            const uint64_t key = make_key(tot, p.id_base + (uint32_t)row);
+            if (key < topk.tau(my_q)) want |= topk.push(my_q, key);
+        }
+        if ((gi + 1) % p.sync_every == 0) {
+            topk.maybe_flush(want);
+            want = false;
+        }
+    }
+    topk.final_flush();
+    for (uint32_t i = threadIdx.x; i < p.nq_valid * p.K; i += blockDim.x) {
+        const uint32_t qi = i / p.K, j = i - qi * p.K;
+        p.partial[((size_t)qi * gridDim.x + blockIdx.x) * p.K + j] = topk.seg(qi)[j];
+    }
+}
+
+// ---- merge of key lists ------------------------------------------------------------------------
+constexpr int MERGE_THREADS = 256;
+__global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
+    const uint64_t* __restrict__ keys, uint32_t nlists, uint32_t nq, uint32_t len, int list_major,
+    uint32_t K, uint32_t P, uint32_t limit, uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids,
+    float* __restrict__ dist, uint32_t* __restrict__ counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* tk = reinterpret_cast<uint64_t*>(smem);
+    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + P), K, P, 1, limit};
+    topk.init();
+    const uint32_t q = blockIdx.x;
+    const uint64_t total = (uint64_t)nlists * len;
+    const uint64_t rounds = (total + blockDim.x - 1) / blockDim.x;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t i = r * blockDim.x + threadIdx.x;
+        bool want = false;
+        if (i < total) {
+            const uint64_t l = i / len, j = i - l * len;
+            const uint64_t src = list_major ? ((l * nq + q) * len + j) : (((uint64_t)q * nlists + l) * len + j);
+            const uint64_t key = keys[src];
+            if (key < topk.tau(0)) want = topk.push(0, key);
+        }
+        topk.maybe_flush(want);
+    }
+    topk.final_flush();
+    uint32_t valid = 0;
+    for (uint32_t j = threadIdx.x; j < K; j += blockDim.x) {
+        const uint64_t key = topk.seg(0)[j];
+        const bool ok = key != KEY_NONE;
+        valid += ok;
+        if (out_keys) out_keys[(size_t)q * K + j] = key;
+        if (ids) ids[(size_t)q * K + j] = ok ? (uint64_t)key_id(key) : KEY_NONE;
+        if (dist) dist[(size_t)q * K + j] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+    }
+    __shared__ uint32_t total_valid;
+    if (threadIdx.x == 0) total_valid = 0;
+    __syncthreads();
+    if (valid) atomicAdd(&total_valid, valid);
+    __syncthreads();
+    if (threadIdx.x == 0 && counts) counts[q] = total_valid;
+}
+
+void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
+                       uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
+                       uint32_t* d_counts, cudaStream_t stream) {
+    if (nq == 0 || k == 0) return;
+    const uint32_t P = topk_segment_size(k, MERGE_THREADS);
+    const size_t smem = TopkSmem::bytes(1, P);
+    VDB_REQUIRE(smem <= 200 * 1024, "k=%u too large for the fused top-k (max %u)", k, 20000u);
+    if (smem > 48 * 1024)
+        VDB_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, k,
+                                                           P, P - k - MERGE_THREADS, d_out_keys, d_ids,
+                                                           d_dist, d_counts);
+    VDB_LAUNCHED();
+}
+
+__global__ void decode_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k,
+                                   uint64_t* __restrict__ ids, float* __restrict__ dist,
+                                   uint32_t* __restrict__ counts) {
+    const uint32_t q = blockIdx.x;
+    uint32_t valid = 0;
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint64_t key = keys[(size_t)q * k + j];
+        const bool ok = key != KEY_NONE;
+        valid += ok;
+        ids[(size_t)q * k + j] = ok ? (uint64_t)key_id(key) : KEY_NONE;
+        dist[(size_t)q * k + j] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+    }
+    __shared__ uint32_t total_valid;
+    if (threadIdx.x == 0) total_valid = 0;
+    __syncthreads();
+    if (valid) atomicAdd(&total_valid, valid);
+    __syncthreads();
+    if (threadIdx.x == 0 && counts) counts[q] = total_valid;
+}
+
+void decode_keys(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
+                 uint32_t* d_counts, cudaStream_t st) {
+    if (nq == 0) return;
+    if (k == 0) {
+        if (d_counts) VDB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, st));
+        return;
+    }
+    decode_keys_kernel<<<nq, 128, 0, st>>>(d_keys, nq, k, d_ids, d_dist, d_counts);
+    VDB_LAUNCHED();
+}
+
+// ---- query tile preparation ---------------------------------------------------------------------
+template <typename T>
+__global__ void prepare_queries_kernel(const T* __restrict__ src, uint32_t dim, uint32_t vec, uint32_t nit,
+                                       uint32_t qstride, int metric, float* __restrict__ tile,
+                                       float* __restrict__ qcache) {
+    const uint32_t q = blockIdx.x;
+    const uint32_t plane = nit * 32 * 4;  // floats per plane
+    float ss = 0.f;
+    for (uint32_t i = threadIdx.x; i < qstride; i += blockDim.x) {
+        const uint32_t pl = i / plane, rem = i - pl * plane;
+        const uint32_t c = rem >> 2, comp = rem & 3;
+        const uint32_t e = c * vec + pl * 4 + comp;
+        const float v = e < dim ? (float)src[(size_t)q * dim + e] : 0.f;
+        tile[(size_t)q * qstride + i] = v;
+        ss = fmaf(v, v, ss);
+    }
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += red[w];
+        qcache[q] = metric == VDB_COSINE ? sqrtf(t) : t;
+    }
+}
+
+QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st) {
+    QueryTile t;
+    const uint32_t vec = vec_elems(ds->dtype);
+    t.nvec = ds->pitch / vec;
+    t.nit = ceil_div(t.nvec, 32u);
+    t.qstride = t.nit * 32 * vec;
+    t.q = DevBuf((size_t)nq * t.qstride * 4, st);
+    t.qcache = DevBuf((size_t)nq * 4, st);
+    if (nq == 0) return t;
+    if (ds->dtype == VDB_F32)
+        prepare_queries_kernel<float><<<nq, 256, 0, st>>>((const float*)d_queries, ds->dim, vec, t.nit,
+                                                         t.qstride, ds->metric, t.q.as<float>(),
+                                                         t.qcache.as<float>());
+    else
+        prepare_queries_kernel<uint8_t><<<nq, 256, 0, st>>>((const uint8_t*)d_queries, ds->dim, vec, t.nit,
+                                                           t.qstride, ds->metric, t.q.as<float>(),
+                                                           t.qcache.as<float>());
+    VDB_LAUNCHED();
+    return t;
+}
+
+// ---- host launcher ------------------------------------------------------------------------------
+template <int NQ, int R, int METRIC, int PL>
+static void launch_scan(const ScanParams& p, uint32_t grid, size_t smem, cudaStream_t st) {
+    auto kern = flat_scan_kernel<NQ, R, METRIC, PL>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    kern<<<grid, SCAN_THREADS, smem, st>>>(p);
+    VDB_LAUNCHED();
+}
+
+template <int METRIC, int PL>
+static void dispatch_scan(int nqt, const ScanParams& p, uint32_t grid, size_t smem, cudaStream_t st) {
+    switch (nqt) {
+        case 1: launch_scan<1, 8, METRIC, PL>(p, grid, smem, st); break;
+        case 2: launch_scan<2, 8, METRIC, PL>(p, grid, smem, st); break;
+        case 4: launch_scan<4, 4, METRIC, PL>(p, grid, smem, st); break;
+        default: launch_scan<8, 4, METRIC, PL>(p, grid, smem, st); break;
+    }
+}
+static int rows_per_group(int nqt) { return nqt <= 2 ? 8 : 4; }
+
+constexpr size_t SCAN_SMEM_MAX = 200 * 1024;
+
+void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
+                    uint64_t* d_keys, cudaStream_t st) {
+    if (nq == 0 || k == 0) return;
+    if (ds->n == 0) {
+        VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
+        return;
+    }
+    QueryTile qt = prepare_queries(ds, d_queries, nq, st);
+
+    // queries per pass: as many as fit (<= 8) next to the top-k segments in shared memory
+    const uint32_t period = 64;
+    const uint32_t P = topk_segment_size(k, period);
+    int nqt = 8;
+    auto smem_for = [&](int t) { return (size_t)t * qt.qstride * 4 + TopkSmem::bytes(t, P); };
+    while (nqt > 1 && smem_for(nqt) > SCAN_SMEM_MAX) nqt >>= 1;
+    VDB_REQUIRE(smem_for(nqt) <= SCAN_SMEM_MAX,
+                "flat scan: dim=%u with k=%u does not fit in shared memory", ds->dim, k);
+
+    const int sms = sm_count();
+    ScanParams p{};
+    p.rows = (const uint8_t*)ds->d_rows;
+    p.n = ds->n;
+    p.pitch_bytes = ds->pitch_bytes();
+    p.nvec = qt.nvec;
+    p.nit = qt.nit;
+    p.qstride = qt.qstride;
+    p.K = k;
+    p.P = P;
+    p.limit = P - k - period;
+    p.id_base = (uint32_t)ds->id_base;
+
+    // passes are grouped in chunks so the partial lists stay small
+    const uint32_t max_grid = 2 * sms;
+    const size_t partial_per_query = (size_t)max_grid * k * 8;
+    uint32_t chunk = (uint32_t)std::max<size_t>(8, (size_t)(64u << 20) / partial_per_query);
+    chunk = std::min(round_up(chunk, 8u), round_up(nq, 8u));
+    DevBuf partial(partial_per_query * chunk, st);
+
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t qn = std::min(chunk, nq - q0);
+        uint32_t grid_used = 0;
+        for (uint32_t qq = 0; qq < qn;) {
+            const uint32_t left = qn - qq;
+            int t = nqt;
+            while (t > 1 && (uint32_t)(t >> 1) >= left) t >>= 1;  // smallest template that covers `left`
+            const uint32_t now = std::min<uint32_t>(left, t);
+            const int R = rows_per_group(t);
+            const uint64_t ngroups = ceil_div<uint64_t>(ds->n, R);
+            const uint32_t grid = (uint32_t)std::max<uint64_t>(
+                1, std::min<uint64_t>(max_grid, ceil_div<uint64_t>(ngroups, SCAN_WARPS)));
+            // every pass of a chunk must use the same grid so the partial layout is uniform
+            if (grid_used == 0) grid_used = grid;
+            p.iters = (uint32_t)ceil_div<uint64_t>(ngroups, (uint64_t)grid_used * SCAN_WARPS);
+            p.sync_every = std::max(1u, period / (SCAN_WARPS * R));
+            p.q = qt.q.as<float>() + (size_t)(q0 + qq) * qt.qstride;
+            p.qcache = qt.qcache.as<float>() + (q0 + qq);
+            p.nq_valid = now;
+            p.partial = partial.as<uint64_t>() + (size_t)qq * grid_used * k;
+            const size_t smem = smem_for(t);
+            if (ds->dtype == VDB_F32) {
+                if (ds->metric == VDB_L2SQR) dispatch_scan<VDB_L2SQR, 1>(t, p, grid_used, smem, st);
+                else dispatch_scan<VDB_COSINE, 1>(t, p, grid_used, smem, st);
+            } else {
+                if (ds->metric == VDB_L2SQR) dispatch_scan<VDB_L2SQR, 4>(t, p, grid_used, smem, st);
+                else dispatch_scan<VDB_COSINE, 4>(t, p, grid_used, smem, st);
+            }
+            qq += now;
+        }
+        launch_merge_keys(partial.as<uint64_t>(), grid_used, qn, k, false, k, d_keys + (size_t)q0 * k,
+                          nullptr, nullptr, nullptr, st);
+    }
+}
+
+}  // namespace vdb

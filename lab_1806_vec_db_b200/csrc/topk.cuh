@@ -1,0 +1,73 @@
+// topk.cuh — CTA-level bounded top-k over sortable u64 keys (see make_key in common.cuh).
+//
+// This is the GPU counterpart of ResultSet (reference src/index_algorithm/candidate_pair.rs:43-82)
+// for scans whose visiting order is ascending id: the k smallest keys by (distance, id).
+//
+// Layout per query segment in shared memory: P = 2^p u64 slots.
+//   [0, K)        current best, ascending (KEY_NONE padded)
+//   [K, K+ncand)  unsorted candidates that beat the current threshold tau = slot[K-1]
+//   rest          KEY_NONE
+// Threads append candidates with one shared-memory atomic; when a segment may overflow within the
+// next `period` appends the CTA sorts all segments (bitonic, all segments per barrier) and the
+// first K slots become the new best. Because tau only ever decreases, filtering against a stale
+// tau is always safe (it only admits extra candidates).
+#pragma once
+#include "common.cuh"
+
+namespace vdb {
+
+struct TopkSmem {
+    uint64_t* keys;    // [nseg][P]
+    uint32_t* ncand;   // [nseg]
+    uint32_t K, P, nseg;
+    uint32_t limit;    // flush when ncand > limit  (limit = P - K - period)
+
+    __device__ __forceinline__ uint64_t* seg(uint32_t s) const { return keys + (size_t)s * P; }
+    __device__ __forceinline__ uint64_t tau(uint32_t s) const { return seg(s)[K - 1]; }
+
+    // all threads
+    __device__ __forceinline__ void init() {
+        for (uint32_t i = threadIdx.x; i < nseg * P; i += blockDim.x) keys[i] = KEY_NONE;
+        for (uint32_t i = threadIdx.x; i < nseg; i += blockDim.x) ncand[i] = 0;
+        __syncthreads();
+    }
+    // any thread; returns true if the segment is now past its flush limit.
+    // The caller guarantees at most `period` appends per segment between two maybe_flush() calls.
+    __device__ __forceinline__ bool push(uint32_t s, uint64_t key) {
+        const uint32_t pos = atomicAdd(&ncand[s], 1u);
+        seg(s)[K + pos] = key;
+        return pos + 1 > limit;
+    }
+    // all threads (contains barriers). `want` = this thread saw push() return true.
+    __device__ __forceinline__ void maybe_flush(bool want) {
+        if (__syncthreads_or(want)) flush_nosync_entry();
+    }
+    // all threads; must be preceded by a barrier that orders all pushes
+    __device__ __forceinline__ void flush_nosync_entry() {
+        cta_bitonic_sort(keys, P, nseg, P);  // ends with __syncthreads()
+        for (uint32_t i = threadIdx.x; i < nseg * (P - K); i += blockDim.x) {
+            const uint32_t s = i / (P - K), j = i - s * (P - K);
+            seg(s)[K + j] = KEY_NONE;
+        }
+        for (uint32_t i = threadIdx.x; i < nseg; i += blockDim.x) ncand[i] = 0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void final_flush() {
+        __syncthreads();
+        flush_nosync_entry();
+    }
+    static __host__ __device__ size_t bytes(uint32_t nseg, uint32_t P) {
+        return (size_t)nseg * P * 8 + (size_t)nseg * 4;
+    }
+};
+
+// Smallest power-of-two segment that holds K best + two periods of candidates.
+inline uint32_t topk_segment_size(uint32_t K, uint32_t period) { return next_pow2(K + 2 * period); }
+
+// merges `nlists` ascending (or unsorted) key lists of length `len` per query into the k best.
+// in: keys[list][query][len] when list_major, else keys[query][list][len].
+void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
+                       uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
+                       uint32_t* d_counts, cudaStream_t stream);
+
+}  // namespace vdb

@@ -1,0 +1,147 @@
+"""Parity of the CUDA Flat path (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import assert_knn_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _flat(base, dist):
+    import lab_1806_vec_db_b200 as V
+    return V.FlatIndex.from_vec_set(base, dist)
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_c1_gist1000_k10_all_queries(fixtures, golden, oracle, metric):
+    """Config C1: gist_1000 x gist_test, k=10 (src/bin/gen_gnd.rs:54-68 protocol), vs golden + oracle."""
+    base, test = fixtures["base"], fixtures["test"]
+    idx = _flat(base, metric)
+    got = idx.knn_batch(test, 10)
+    want = (golden[f"flat_{metric}_ids"], golden[f"flat_{metric}_dist"], np.full(1000, 10))
+    rate = assert_knn_parity(base, test, metric, got, want, oracle)
+    assert rate > 0.999, f"exact-id rate {rate}"
+    # the duplicate pair (rows 50 and 444) must come out lower id first (candidate_pair.rs:36-40)
+    if metric == "l2sqr":
+        assert got[0][19, :2].tolist() == [50, 444]
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_reference_unit_shape_dim12(fixtures, golden, oracle, metric):
+    """flat_index.rs:117-170: 1000x12, query = row 200, k = 4/6: self first, distance ~0, ascending."""
+    base = np.ascontiguousarray(fixtures["base"][:, :12])
+    idx = _flat(base, metric)
+    res = idx.knn(base[200], 6)
+    assert [p.index for p in res] == golden[f"unit12_{metric}_ids"][0].tolist()
+    assert res[0].index == 200 and abs(res[0].distance) < 1e-6
+    assert all(a.distance <= b.distance for a, b in zip(res, res[1:]))
+    np.testing.assert_allclose([p.distance for p in res], golden[f"unit12_{metric}_dist"][0], rtol=1e-5, atol=1e-6)
+    assert len(idx.knn(base[200], 4)) == 4
+
+
+@pytest.mark.parametrize("nq", [1, 2, 3, 5, 8, 9, 17])
+def test_query_batch_shapes(fixtures, oracle, nq):
+    base, test = fixtures["base"], fixtures["test"]
+    idx = _flat(base, "l2sqr")
+    got = idx.knn_batch(test[:nq], 10)
+    want = oracle.flat_knn(base, test[:nq], 10, "l2sqr")
+    assert_knn_parity(base, test[:nq], "l2sqr", got, want, oracle)
+
+
+@pytest.mark.parametrize("k", [1, 2, 10, 100, 128, 129, 600, 1000])
+def test_k_sweep(fixtures, oracle, k):
+    base, test = fixtures["base"], fixtures["test"]
+    idx = _flat(base, "l2sqr")
+    got = idx.knn_batch(test[:4], k)
+    want = oracle.flat_knn(base, test[:4], k, "l2sqr", 4)
+    assert_knn_parity(base, test[:4], "l2sqr", got, want, oracle)
+
+
+def test_k_larger_than_n_and_k0(fixtures, oracle):
+    """k > N returns N results; k = 0 returns none (candidate_pair.rs:61-74)."""
+    base, test = fixtures["base"][:37], fixtures["test"][:3]
+    idx = _flat(base, "l2sqr")
+    ids, dist, counts = idx.knn_batch(test, 50)
+    assert counts.tolist() == [37, 37, 37]
+    want = oracle.flat_knn(base, test, 50, "l2sqr")
+    assert_knn_parity(base, test, "l2sqr", (ids, dist, counts), want, oracle)
+    assert (ids[:, 37:] == np.iinfo(np.uint64).max).all() and np.isnan(dist[:, 37:]).all()
+    assert idx.knn(test[0], 0) == []
+
+
+@pytest.mark.parametrize("n,dim", [(1, 960), (7, 5), (33, 13), (257, 4), (1000, 127), (300, 1024), (64, 2050)])
+def test_ragged_shapes(oracle, n, dim):
+    rng = np.random.default_rng(n * 1000 + dim)
+    base = rng.random((n, dim), dtype=np.float32)
+    q = rng.random((5, dim), dtype=np.float32)
+    for metric in ("l2sqr", "cosine"):
+        idx = _flat(base, metric)
+        k = min(n, 10)
+        got = idx.knn_batch(q, k)
+        want = oracle.flat_knn(base, q, k, metric)
+        assert_knn_parity(base, q, metric, got, want, oracle)
+
+
+def test_exact_ties_lower_id_first(oracle):
+    """Many exact duplicates: order must be (distance, id)."""
+    rng = np.random.default_rng(5)
+    proto = rng.random((8, 64), dtype=np.float32)
+    base = np.ascontiguousarray(proto[rng.integers(0, 8, 5000)])
+    q = proto[:3] + np.float32(0.01)
+    idx = _flat(base, "l2sqr")
+    got = idx.knn_batch(q, 50)
+    want = oracle.flat_knn(base, q, 50, "l2sqr")
+    assert (got[0].astype(np.int64) == want[0].astype(np.int64)).all()
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_u8_rows(oracle, metric):
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, (2000, 100), dtype=np.uint8)
+    q = rng.integers(0, 256, (9, 100), dtype=np.uint8)
+    idx = _flat(base, metric)
+    got = idx.knn_batch(q, 10)
+    want = oracle.flat_knn(base, q, 10, metric)
+    assert_knn_parity(base, q, metric, got, want, oracle)
+
+
+def test_push_and_swap_remove(fixtures, oracle):
+    """VecSet::push / swap_remove keep the mirror in sync (vec_set.rs:113-137)."""
+    import lab_1806_vec_db_b200 as V
+    base, test = fixtures["base"], fixtures["test"][:4]
+    vs = V.DeviceVecSet(base[:500], "l2sqr")
+    vs.push(base[500:800])
+    vs.push(base[800])
+    assert len(vs) == 801
+    idx = V.FlatIndex(vs)
+    host = base[:801].copy()
+    assert_knn_parity(host, test, "l2sqr", idx.knn_batch(test, 10), oracle.flat_knn(host, test, 10, "l2sqr"), oracle)
+    vs.swap_remove(3)
+    host[3] = host[800]
+    host = host[:800]
+    assert_knn_parity(host, test, "l2sqr", idx.knn_batch(test, 10), oracle.flat_knn(host, test, 10, "l2sqr"), oracle)
+
+
+def test_dimension_mismatch_raises(fixtures):
+    idx = _flat(fixtures["base"], "l2sqr")
+    with pytest.raises(ValueError):
+        idx.knn(np.zeros(12, np.float32), 3)
+    with pytest.raises(TypeError):
+        idx.knn(np.zeros(960, np.float64), 3)
+
+
+def test_synthetic_large_properties(oracle):
+    """Size-independent properties at a size the oracle cannot cover fully: a planted exact copy of
+    each query must be rank 0 with distance 0, results ascending, and a 200k subsample oracle check."""
+    rng = np.random.default_rng(3)
+    n, dim = 200_000, 960
+    base = rng.random((n, dim), dtype=np.float32)
+    q = rng.random((8, dim), dtype=np.float32)
+    planted = rng.integers(0, n, 8)
+    base[planted] = q
+    idx = _flat(base, "l2sqr")
+    ids, dist, counts = idx.knn_batch(q, 100)
+    assert (ids[:, 0] == planted).all() and (dist[:, 0] == 0).all()
+    assert (np.diff(dist, axis=1) >= 0).all()
+    want = oracle.flat_knn(base, q, 100, "l2sqr", 8)
+    assert_knn_parity(base, q, "l2sqr", (ids, dist, counts), want, oracle)
