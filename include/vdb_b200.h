@@ -166,6 +166,14 @@ int vdb_ivf_knn_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_que
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the calling process since load. */
 uint64_t vdb_launch_count(void);
+/* Per-kernel device timing for the roofline report: when enabled, the library brackets its hot
+ * kernels with CUDA events on the launching stream. vdb_prof_read synchronises the device, then
+ * returns the accumulated milliseconds and launch count of kernel `name` since the last reset
+ * (names: "flat_scan", "flat_gemm", "rerank", "merge", "pq_adc", "pq_encode", "ivf_scan",
+ * "kmeans_assign"). */
+int vdb_prof_enable(int on);
+int vdb_prof_reset(void);
+int vdb_prof_read(const char* name, double* ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,9 @@ SIGNATURES = {
     "vdb_ivf_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
     "vdb_ivf_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     "vdb_launch_count": (u64, []),
+    "vdb_prof_enable": (i32, [i32]),
+    "vdb_prof_reset": (i32, []),
+    "vdb_prof_read": (i32, [C.c_char_p, vp, vp]),
 }
 
 

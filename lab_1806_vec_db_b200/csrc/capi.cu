@@ -7,6 +7,36 @@
 #include "index.cuh"
 #include "topk.cuh"
 
+#include <map>
+#include <mutex>
+
+namespace vdb {
+bool g_prof_on = false;
+namespace {
+struct ProfEntry {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    cudaEvent_t open = nullptr;
+};
+std::mutex g_prof_mu;
+std::map<std::string, ProfEntry> g_prof;
+}  // namespace
+void prof_record(const char* name, cudaStream_t st, bool begin) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfEntry& e = g_prof[name];
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    if (begin) {
+        e.open = ev;
+    } else if (e.open) {
+        e.spans.emplace_back(e.open, ev);
+        e.open = nullptr;
+    } else {
+        cudaEventDestroy(ev);
+    }
+}
+}  // namespace vdb
+
 namespace {
 thread_local std::string t_error;
 thread_local int t_device = -1;
@@ -318,6 +348,41 @@ int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
             return;
         }
         vdb::launch_merge_keys(d_keys, nlists, nq, k, true, k, nullptr, d_ids, d_dist, d_counts, st);
+    });
+}
+
+int vdb_prof_enable(int on) {
+    vdb::g_prof_on = on != 0;
+    return VDB_OK;
+}
+int vdb_prof_reset(void) {
+    return guarded([&] {
+        std::lock_guard<std::mutex> lk(vdb::g_prof_mu);
+        for (auto& kv : vdb::g_prof) {
+            for (auto& sp : kv.second.spans) {
+                cudaEventDestroy(sp.first);
+                cudaEventDestroy(sp.second);
+            }
+            if (kv.second.open) cudaEventDestroy(kv.second.open);
+        }
+        vdb::g_prof.clear();
+    });
+}
+int vdb_prof_read(const char* name, double* ms, uint64_t* launches) {
+    return guarded([&] {
+        VDB_REQUIRE(name && ms && launches, "NULL argument");
+        VDB_CUDA(cudaDeviceSynchronize());
+        std::lock_guard<std::mutex> lk(vdb::g_prof_mu);
+        *ms = 0;
+        *launches = 0;
+        auto it = vdb::g_prof.find(name);
+        if (it == vdb::g_prof.end()) return;
+        for (auto& sp : it->second.spans) {
+            float t = 0;
+            VDB_CUDA(cudaEventElapsedTime(&t, sp.first, sp.second));
+            *ms += t;
+            *launches += 1;
+        }
     });
 }
 

@@ -51,12 +51,41 @@ extern std::atomic<uint64_t> g_launches;
         VDB_CUDA(cudaGetLastError());       \
     } while (0)
 
+// ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----
+void prof_record(const char* name, cudaStream_t st, bool begin);
+extern bool g_prof_on;
+struct ProfScope {
+    const char* name;
+    cudaStream_t st;
+    ProfScope(const char* n, cudaStream_t s) : name(n), st(s) {
+        if (g_prof_on) prof_record(name, st, true);
+    }
+    ~ProfScope() {
+        if (g_prof_on) prof_record(name, st, false);
+    }
+};
+
+// keep freed scratch memory in the stream-ordered pool instead of returning it to the driver on
+// every synchronisation (the default release threshold is 0)
+inline void pool_init() {
+    static thread_local int done_dev = -1;
+    int dev;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_dev = dev;
+}
+
 // stream-ordered scratch allocation (re-entrant: every call owns its workspace)
 struct DevBuf {
     void* p = nullptr;
     cudaStream_t s = nullptr;
     DevBuf() = default;
     DevBuf(size_t bytes, cudaStream_t st) : s(st) {
+        pool_init();
         if (bytes) VDB_CUDA(cudaMallocAsync(&p, bytes, st));
     }
     DevBuf(const DevBuf&) = delete;

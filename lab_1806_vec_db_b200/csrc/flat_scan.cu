@@ -225,6 +225,7 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     if (smem > 48 * 1024)
         VDB_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
+    ProfScope prof("merge", stream);
     merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, k,
                                                            P, P - k - MERGE_THREADS, d_out_keys, d_ids,
                                                            d_dist, d_counts);
@@ -320,6 +321,7 @@ static void launch_scan(const ScanParams& p, uint32_t grid, size_t smem, cudaStr
         VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    ProfScope prof("flat_scan", st);
     kern<<<grid, SCAN_THREADS, smem, st>>>(p);
     VDB_LAUNCHED();
 }

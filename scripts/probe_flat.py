@@ -1,0 +1,36 @@
+"""Quick device-side timing of the Flat scan (K1) at several batch sizes. Not the bench."""
+import ctypes as C
+import sys, os
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lab_1806_vec_db_b200 as V
+from lab_1806_vec_db_b200 import _lib as L
+
+n = int(os.environ.get("N", 1_000_000)); dim = int(os.environ.get("DIM", 960))
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev); g.manual_seed(42)
+base = torch.rand((n, dim), device=dev, generator=g, dtype=torch.float32)
+ds = V.DeviceVecSet.from_device(base.data_ptr(), n, dim, dim, np.float32, os.environ.get("METRIC", "l2sqr"), keepalive=base)
+lib = L.lib()
+L.check(lib.vdb_flat_set_path(1))
+stream = torch.cuda.current_stream().cuda_stream
+for nq, k in [(1, 10), (2, 10), (4, 10), (8, 10), (8, 100), (1, 100), (16, 10), (64, 100)]:
+    q = torch.rand((nq, dim), device=dev, generator=g)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev); dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    def run():
+        L.check(lib.vdb_flat_knn_dev(ds._h, C.c_void_p(q.data_ptr()), nq, k, C.c_void_p(ids.data_ptr()),
+                                     C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), C.c_void_p(stream)))
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps): run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    passes = (nq + 7) // 8
+    gbs = passes * n * dim * 4 / ms / 1e6
+    print(f"nq={nq:3d} k={k:4d}: {ms:8.3f} ms/call  {nq/ms*1e3:9.1f} QPS  {gbs:7.1f} GB/s ({gbs/6551.4*100:5.1f}% of measured HBM peak)", flush=True)

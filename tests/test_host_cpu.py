@@ -1,0 +1,125 @@
+"""`not gpu`: host logic, the C-ABI library (load + symbols, no compute), and the world_size-2 shard/merge path."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in os.listdir(inc):
+        if fn.endswith(".h"):
+            src = open(os.path.join(inc, fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            names |= set(re.findall(r"\b(vdb_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from lab_1806_vec_db_b200 import _lib as L
+    lib = C.CDLL(L.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 35
+    for name in decl:
+        assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
+    assert set(L.SIGNATURES) == decl, set(L.SIGNATURES) ^ decl
+    assert L.lib().vdb_version() == 801
+
+
+def test_no_cpu_fallback_on_a_box_without_gpu():
+    """The product path must fail loudly, never compute on the CPU."""
+    import lab_1806_vec_db_b200 as V
+    from conftest import have_gpu
+    if have_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(V.VdbError):
+        V.FlatIndex.from_vec_set(np.zeros((4, 8), np.float32), "l2sqr")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "lab_1806_vec_db_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "liboracle" not in src and "orc_" not in src, fn
+
+
+def test_metric_names_follow_pyo3():
+    from lab_1806_vec_db_b200 import _lib as L
+    assert L.metric_code("l2sqr") == 0 and L.metric_code("cosine") == 1
+    with pytest.raises(ValueError):
+        L.metric_code("dot")  # no such DistanceAlgorithm variant (distance/mod.rs:18-28)
+
+
+def test_key_packing_orders_like_candidate_pair():
+    from lab_1806_vec_db_b200.sharded import pack_keys, unpack_keys
+    d = np.array([0.0, -0.0, 1.5, -1e-7, np.inf, np.nan, 1.5, 3e-39], np.float32)
+    i = np.array([7, 3, 2, 9, 1, 0, 1, 4], np.uint64)
+    keys = pack_keys(d, i)
+    order = np.argsort(keys, kind="stable")
+    # expected: (-1e-7,9) (-0.0,3) (0.0,7) (3e-39,4) (1.5,1) (1.5,2) (inf,1) (nan,0): -0 == +0, NaN greatest
+    assert order.tolist() == [3, 1, 0, 7, 6, 2, 4, 5]
+    dd, ii = unpack_keys(keys)
+    assert (ii == i).all() and np.isnan(dd[5]) and dd[2] == np.float32(1.5) and dd[3] == np.float32(-1e-7)
+
+
+def test_shard_bounds_cover_everything():
+    from lab_1806_vec_db_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 1000, 1_000_000):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from lab_1806_vec_db_b200.sharded import shard_bounds, pack_keys, unpack_keys
+import oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+fx = np.load(os.path.join({root!r}, "tests", "golden", "fixtures.npz"))
+dec = lambda u: (u.astype(np.float64) / 1e4).astype(np.float32)
+base, test = dec(fx["base_u16"]), dec(fx["test_u16"])[:32]
+k = 10
+lo, hi = shard_bounds(len(base), world, rank)
+ids, dd, cnt = O.flat_knn(base[lo:hi], test, k, "l2sqr")           # this rank's shard (oracle stands in for the GPU)
+keys = torch.from_numpy(pack_keys(dd, ids + np.uint64(lo)).astype(np.int64))
+allk = [torch.empty_like(keys) for _ in range(world)]
+dist.all_gather(allk, keys)                                          # the path's one exchange step
+merged = np.sort(np.concatenate([a.numpy().astype(np.uint64) for a in allk], axis=1), axis=1)[:, :k]
+md, mi = unpack_keys(merged)
+wi, wd, _ = O.flat_knn(base, test, k, "l2sqr")
+assert (mi == wi).all() and (md.view(np.uint32) == wd.view(np.uint32)).all()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_world_size_2_shard_and_merge_gloo(tmp_path):
+    """Row sharding + all-gather + (distance, id) merge reproduce the unsharded result (CPU, gloo)."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("ok") == 2
