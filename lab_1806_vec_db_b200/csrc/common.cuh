@@ -122,8 +122,8 @@ inline uint32_t next_pow2(uint32_t v) {
     while (p < v) p <<= 1;
     return p;
 }
-template <class T> inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
-template <class T> inline T round_up(T a, T b) { return ceil_div(a, b) * b; }
+template <class T> __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+template <class T> __host__ __device__ inline T round_up(T a, T b) { return ceil_div(a, b) * b; }
 
 // ---------------------------------------------------------------------------------------------
 // sortable keys: (distance, id) -> u64 whose integer order equals CandidatePair's order

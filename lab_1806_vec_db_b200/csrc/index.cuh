@@ -1,5 +1,84 @@
-// index.cuh — device mirrors of PQTable / IVFIndex and the k-means launchers.
+// index.cuh — device mirrors of PQTable / IVFIndex and the k-means / pair-distance launchers.
 #pragma once
+#include <vector>
+
 #include "dataset.cuh"
 
-namespace vdb {}  // filled in by kmeans.cu / pq.cu / ivf.cu
+// device mirror of PQTable<T> (reference src/distance/pq_table.rs:116-137)
+struct vdb_pq {
+    int device = 0;
+    uint32_t dim = 0, m = 0, n_bits = 0, kc = 0, enc = 0;  // enc = encoded_dim (bytes per row)
+    int dtype = VDB_F32, metric = VDB_L2SQR;
+    uint64_t n = 0;
+    uint32_t words = 0;             // u32 words per row in the transposed layout
+    std::vector<uint32_t> g_lo, g_len, g_off;  // per group: first dim, length, codebook element offset
+    uint32_t max_len = 0;
+    void* d_codebooks = nullptr;    // groups concatenated, group g = [kc][len_g] of dtype
+    uint32_t* d_groups = nullptr;   // [m][3] (lo, len, off)
+    float* d_dist_cache = nullptr;  // [m*kc] 0 (L2) / dot(c,c) (cosine), pq_table.rs:165-170
+    float* d_cb_norm = nullptr;     // [m*kc] ||c|| for cosine encoding
+    uint8_t* d_codes = nullptr;     // [n][enc] reference layout
+    uint32_t* d_codes_t = nullptr;  // [ceil(n/32)][words][32] transposed for the ADC scan
+};
+
+// device mirror of IVFIndex<T> (reference src/index_algorithm/ivf_index.rs:34-47)
+struct vdb_ivf {
+    int device = 0;
+    uint32_t nlist = 0, dim = 0;
+    int dtype = VDB_F32, metric = VDB_L2SQR;
+    uint64_t n = 0;
+    void* d_centroids = nullptr;    // [nlist][dim] of dtype
+    uint64_t* d_offsets = nullptr;  // [nlist+1]
+    uint32_t* d_members = nullptr;  // [n] local row ids, ascending inside a list
+    uint32_t max_list = 0;
+};
+
+namespace vdb {
+
+// kmeans.cu
+void kmeans_assign_exact(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, int metric, uint32_t lo,
+                         uint32_t d, const void* d_cent, uint32_t k, uint64_t* d_best, uint32_t* d_assign,
+                         float* d_all_dist, cudaStream_t st);
+void build_lists(const uint32_t* d_assign, uint64_t n, uint32_t k, uint64_t* d_offsets, uint32_t* d_members,
+                 cudaStream_t st);
+uint32_t kmeans_lloyd(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, int metric, uint32_t lo,
+                      uint32_t d, void* d_cent, uint32_t k, uint32_t max_iter, float tol, cudaStream_t st);
+void kmeans_pp_weights(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, int metric, uint32_t lo,
+                       uint32_t d, const void* d_c, float* d_w, cudaStream_t st);
+
+// pairs.cu
+void row_cache(const vdb_dataset* ds, float* d_out, cudaStream_t st);
+void exact_pair_distances(const vdb_dataset* ds, const void* d_queries, const uint32_t* d_qidx,
+                          const uint32_t* d_rid, uint64_t npairs, float* d_out, cudaStream_t st);
+void cached_pair_distances(const vdb_dataset* ds, const void* d_queries, const float* d_qcache,
+                           const float* d_rowcache, const uint32_t* d_qidx, const uint32_t* d_rid,
+                           uint64_t npairs, float* d_out, cudaStream_t st);
+void raw_pair_distances(const void* d_a, const void* d_b, uint64_t count, uint32_t dim, int dtype, int metric,
+                        float* d_out, cudaStream_t st);
+void expand_offsets(const uint64_t* d_off, uint32_t nq, uint32_t* d_qidx, cudaStream_t st);
+
+// pq.cu
+void pq_groups_host(uint32_t dim, uint32_t m, std::vector<uint32_t>& lo, std::vector<uint32_t>& len);
+vdb_pq* pq_create(const vdb_dataset* ds, const void* h_codebooks, uint32_t m, uint32_t n_bits,
+                  const uint8_t* h_codes_in, uint8_t* h_codes_out);
+void pq_destroy(vdb_pq* pq);
+void pq_lut(const vdb_pq* pq, const void* d_queries, uint32_t nq, float* d_lut, float* d_qcache, cudaStream_t st);
+void pq_adc_all(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, float* d_out,
+                cudaStream_t st);
+void pq_knn_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,
+                 uint32_t ef, uint64_t* d_keys, cudaStream_t st);
+
+void rerank_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, const uint64_t* d_cand, uint32_t kk,
+                 uint32_t k, uint64_t* d_keys, cudaStream_t st);
+
+// ivf.cu
+vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nlist, uint32_t* h_assign_out);
+void ivf_destroy(vdb_ivf* ivf);
+void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
+                  uint32_t n_probes, uint64_t* d_keys, cudaStream_t st);
+
+// rebuilds (distance, id) keys: key[j] = valid[j] ? make_key(dist[j], id[j]) : KEY_NONE
+void rekey(const float* d_dist, const uint32_t* d_ids, const uint8_t* d_valid, uint64_t count, uint64_t* d_keys,
+           cudaStream_t st);
+
+}  // namespace vdb

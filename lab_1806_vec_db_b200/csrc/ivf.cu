@@ -1,0 +1,283 @@
+// ivf.cu — K9: IVF list construction and probe scan.
+//
+// Replaces (reference paths):
+//   IVFIndex::from_vec_set (assignment + lists)   src/index_algorithm/ivf_index.rs:88-106
+//   KMeans::find_n_nearest                        src/distance/k_means.rs:174-191
+//   IVFIndex::knn_with_ef                         src/index_algorithm/ivf_index.rs:143-154
+//
+// Assignment and probe selection use the exact sequential arithmetic of kmeans.cu (bit-exact lists and
+// probe order). The list scan gathers whole rows by id (a 960-d f32 row is 30 full 128-byte lines, so a
+// gather at row granularity wastes no HBM traffic), one CTA per (query, slice of its visit sequence), warps
+// stream 8 rows at a time, partial top-k lists are merged per query. Ties at the k-th distance are resolved
+// by (distance, id) instead of the reference's visit order (documented in DESIGN.md; within the parity rule).
+#include "index.cuh"
+#include "topk.cuh"
+
+namespace vdb {
+
+constexpr int IVF_THREADS = 256;
+constexpr int IVF_WARPS = IVF_THREADS / 32;
+constexpr int IVF_R = 8;
+
+struct IvfScanParams {
+    const uint8_t* rows;
+    uint64_t pitch_bytes;
+    uint32_t nvec, nit;
+    const float* q;          // query tiles [nq][qstride]
+    uint32_t qstride;
+    const float* qcache;     // [nq]
+    const uint64_t* probes;  // [nq][nprobe] keys (distance, list id), KEY_NONE padded
+    uint32_t nprobe;
+    const uint64_t* offsets; // [nlist+1]
+    const uint32_t* members;
+    uint32_t splits;         // CTAs per query
+    uint32_t K, P, limit;
+    uint32_t id_base;
+    uint64_t* partial;       // [nq][splits][K]
+};
+
+__device__ __forceinline__ float4 ivf_u4_as_f4(const uint4& u) {
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
+__device__ __forceinline__ float4 ivf_bytes_as_f4(uint32_t w) {
+    return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu), (float)(w >> 24));
+}
+
+template <int METRIC, int PL>
+__global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int R = IVF_R;
+    const uint32_t q = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qs4 = p.qstride >> 2, plane4 = p.nit * 32;
+    float4* qs = reinterpret_cast<float4*>(smem);
+    uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)p.qstride * 4);
+    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + p.P), p.K, p.P, 1, p.limit};
+    uint32_t* pre = reinterpret_cast<uint32_t*>(tk + p.P) + 4;  // [nprobe+1] prefix of probed list lengths
+    uint64_t* lbase = reinterpret_cast<uint64_t*>(pre + round_up(p.nprobe + 1, 2u));  // [nprobe] list starts
+
+    for (uint32_t i = threadIdx.x; i < qs4; i += blockDim.x)
+        qs[i] = reinterpret_cast<const float4*>(p.q + (size_t)q * p.qstride)[i];
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (uint32_t j = 0; j < p.nprobe; ++j) {
+            const uint64_t pk = p.probes[(size_t)q * p.nprobe + j];
+            pre[j] = s;
+            if (pk != KEY_NONE) {
+                const uint32_t c = key_id(pk);
+                lbase[j] = p.offsets[c];
+                s += (uint32_t)(p.offsets[c + 1] - p.offsets[c]);
+            } else {
+                lbase[j] = 0;
+            }
+        }
+        pre[p.nprobe] = s;
+    }
+    topk.init();
+    const uint32_t total = pre[p.nprobe];
+    const float qn = METRIC == VDB_COSINE ? p.qcache[q] : 0.f;
+    // this CTA's slice of the visit sequence, in groups of R positions
+    const uint32_t groups = ceil_div<uint32_t>(total, R);
+    const uint32_t gper = ceil_div<uint32_t>(groups, p.splits);
+    const uint32_t g_lo = split * gper, g_hi = min(groups, g_lo + gper);
+    const uint32_t steps = ceil_div<uint32_t>(g_hi > g_lo ? g_hi - g_lo : 0, IVF_WARPS);
+
+    for (uint32_t s = 0; s < steps; ++s) {
+        const uint32_t g = g_lo + s * IVF_WARPS + warp;
+        const bool active = g < g_hi;
+        uint32_t rid[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t pos = g * R + r;
+            uint32_t id = 0xffffffffu;
+            if (active && pos < total) {
+                uint32_t j = 0;
+                while (pre[j + 1] <= pos) ++j;  // nprobe is small
+                id = p.members[lbase[j] + (pos - pre[j])];
+            }
+            rid[r] = id;
+        }
+        float acc[R], xx[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f, xx[r] = 0.f;
+        if (active) {
+            for (uint32_t it = 0; it < p.nit; ++it) {
+                const uint32_t c = it * 32 + lane;
+                uint4 v[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    v[r] = (c < p.nvec && rid[r] != 0xffffffffu)
+                               ? ldg_stream_u4(p.rows + (uint64_t)rid[r] * p.pitch_bytes + (size_t)c * 16)
+                               : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int pl = 0; pl < PL; ++pl) {
+                    const float4 qv = qs[(size_t)pl * plane4 + c];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float4 x;
+                        if constexpr (PL == 1) x = ivf_u4_as_f4(v[r]);
+                        else x = ivf_bytes_as_f4(pl == 0 ? v[r].x : (pl == 1 ? v[r].y : (pl == 2 ? v[r].z : v[r].w)));
+                        if (METRIC == VDB_L2SQR) {
+                            const float d0 = x.x - qv.x, d1 = x.y - qv.y, d2 = x.z - qv.z, d3 = x.w - qv.w;
+                            acc[r] = fmaf(d0, d0, acc[r]);
+                            acc[r] = fmaf(d1, d1, acc[r]);
+                            acc[r] = fmaf(d2, d2, acc[r]);
+                            acc[r] = fmaf(d3, d3, acc[r]);
+                        } else {
+                            acc[r] = fmaf(x.x, qv.x, acc[r]);
+                            acc[r] = fmaf(x.y, qv.y, acc[r]);
+                            acc[r] = fmaf(x.z, qv.z, acc[r]);
+                            acc[r] = fmaf(x.w, qv.w, acc[r]);
+                            xx[r] = fmaf(x.x, x.x, xx[r]);
+                            xx[r] = fmaf(x.y, x.y, xx[r]);
+                            xx[r] = fmaf(x.z, x.z, xx[r]);
+                            xx[r] = fmaf(x.w, x.w, xx[r]);
+                        }
+                    }
+                }
+            }
+        }
+        float tot = warp_reduce_scatter<R>(acc, lane);  // lane L holds row L >> 2
+        if (METRIC == VDB_COSINE) {
+            const float xs = warp_reduce_scatter<R>(xx, lane);
+            tot = 1.0f - tot / fmaxf(sqrtf(xs) * qn, 1e-10f);
+        }
+        const int my_r = lane >> 2;
+        uint32_t my_id = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r == my_r) my_id = rid[r];
+        bool want = false;
+        if ((lane & 3) == 0 && my_id != 0xffffffffu) {
+            const uint64_t key = make_key(tot, p.id_base + my_id);
+            if (key < topk.tau(0)) want = topk.push(0, key);
+        }
+        topk.maybe_flush(want);
+    }
+    topk.final_flush();
+    for (uint32_t j = threadIdx.x; j < p.K; j += blockDim.x)
+        p.partial[((size_t)q * p.splits + split) * p.K + j] = topk.seg(0)[j];
+}
+
+// [nq][nlist] exact distances -> keys (distance, list id)
+__global__ void probe_keys_kernel(const float* __restrict__ dist, uint64_t count, uint32_t nlist,
+                                  uint64_t* __restrict__ keys) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x)
+        keys[j] = make_key(dist[j], (uint32_t)(j % nlist));
+}
+
+vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nlist, uint32_t* h_assign_out) {
+    VDB_REQUIRE(nlist > 0, "The number of clusters should be greater than 0.");
+    VDB_REQUIRE(h_centroids, "centroids is NULL");
+    auto ivf = new vdb_ivf();
+    cudaStream_t st = nullptr;
+    try {
+        ivf->device = ds->device;
+        ivf->nlist = nlist;
+        ivf->dim = ds->dim;
+        ivf->dtype = ds->dtype;
+        ivf->metric = ds->metric;
+        ivf->n = ds->n;
+        const size_t cbytes = (size_t)nlist * ds->dim * ds->elem_size();
+        VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        VDB_CUDA(cudaMalloc(&ivf->d_centroids, cbytes));
+        VDB_CUDA(cudaMalloc(&ivf->d_offsets, (size_t)(nlist + 1) * 8));
+        VDB_CUDA(cudaMalloc(&ivf->d_members, std::max<size_t>(4, ds->n * 4)));
+        VDB_CUDA(cudaMemcpyAsync(ivf->d_centroids, h_centroids, cbytes, cudaMemcpyHostToDevice, st));
+        {
+            DevBuf best(ds->n * 8, st), assign(std::max<size_t>(4, ds->n * 4), st);
+            kmeans_assign_exact(ds->d_rows, ds->n, ds->pitch, ds->dtype, ds->metric, 0, ds->dim, ivf->d_centroids,
+                                nlist, best.as<uint64_t>(), assign.as<uint32_t>(), nullptr, st);
+            build_lists(assign.as<uint32_t>(), ds->n, nlist, ivf->d_offsets, ivf->d_members, st);
+            if (h_assign_out && ds->n)
+                VDB_CUDA(cudaMemcpyAsync(h_assign_out, assign.p, ds->n * 4, cudaMemcpyDeviceToHost, st));
+            VDB_CUDA(cudaStreamSynchronize(st));
+        }
+        std::vector<uint64_t> off(nlist + 1);
+        VDB_CUDA(cudaMemcpy(off.data(), ivf->d_offsets, off.size() * 8, cudaMemcpyDeviceToHost));
+        for (uint32_t c = 0; c < nlist; ++c) ivf->max_list = std::max<uint32_t>(ivf->max_list, (uint32_t)(off[c + 1] - off[c]));
+        VDB_CUDA(cudaStreamSynchronize(st));
+        cudaStreamDestroy(st);
+    } catch (...) {
+        if (st) cudaStreamDestroy(st);
+        ivf_destroy(ivf);
+        throw;
+    }
+    return ivf;
+}
+
+void ivf_destroy(vdb_ivf* ivf) {
+    if (!ivf) return;
+    cudaFree(ivf->d_centroids);
+    cudaFree(ivf->d_offsets);
+    cudaFree(ivf->d_members);
+    delete ivf;
+}
+
+void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
+                  uint32_t n_probes, uint64_t* d_keys, cudaStream_t st) {
+    VDB_REQUIRE(n_probes > 0, "The number of probes should be greater than 0.");
+    VDB_REQUIRE(ds->n == ivf->n && ds->dim == ivf->dim && ds->dtype == ivf->dtype && ds->metric == ivf->metric,
+                "IVF index was built for a different vector set");
+    if (nq == 0 || k == 0) return;
+    const uint32_t nprobe = std::min(n_probes, ivf->nlist);
+    // 1. exact query-centroid distances, probe order = find_n_nearest (k_means.rs:174-191)
+    DevBuf cdist((size_t)nq * ivf->nlist * 4, st), best((size_t)nq * 8, st), ckeys((size_t)nq * ivf->nlist * 8, st),
+        probes((size_t)nq * nprobe * 8, st);
+    kmeans_assign_exact(d_queries, nq, ds->dim, ds->dtype, ds->metric, 0, ds->dim, ivf->d_centroids, ivf->nlist,
+                        best.as<uint64_t>(), nullptr, cdist.as<float>(), st);
+    const uint64_t cnt = (uint64_t)nq * ivf->nlist;
+    probe_keys_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(cnt, 256), 4096), 256, 0, st>>>(
+        cdist.as<float>(), cnt, ivf->nlist, ckeys.as<uint64_t>());
+    VDB_LAUNCHED();
+    launch_merge_keys(ckeys.as<uint64_t>(), 1, nq, ivf->nlist, false, nprobe, probes.as<uint64_t>(), nullptr, nullptr,
+                      nullptr, st);
+    // 2. list scan
+    QueryTile qt = prepare_queries(ds, d_queries, nq, st);
+    const uint32_t period = IVF_WARPS * IVF_R;
+    const uint32_t P = topk_segment_size(k, period);
+    const size_t smem = (size_t)qt.qstride * 4 + TopkSmem::bytes(1, P) + 16 + (size_t)round_up(nprobe + 1, 2u) * 4 +
+                        (size_t)nprobe * 8;
+    VDB_REQUIRE(smem <= 200 * 1024, "IVF scan: dim=%u / k=%u / n_probes=%u do not fit in shared memory", ds->dim, k,
+                nprobe);
+    const uint32_t target = (uint32_t)sm_count() * 4;
+    uint32_t splits = std::max(1u, ceil_div(target, nq));
+    const uint64_t max_visit = (uint64_t)ivf->max_list * nprobe;
+    splits = (uint32_t)std::min<uint64_t>(splits, std::max<uint64_t>(1, max_visit / (IVF_WARPS * IVF_R)));
+    DevBuf partial((size_t)nq * splits * k * 8, st);
+    IvfScanParams p{};
+    p.rows = (const uint8_t*)ds->d_rows;
+    p.pitch_bytes = ds->pitch_bytes();
+    p.nvec = qt.nvec;
+    p.nit = qt.nit;
+    p.q = qt.q.as<float>();
+    p.qstride = qt.qstride;
+    p.qcache = qt.qcache.as<float>();
+    p.probes = probes.as<uint64_t>();
+    p.nprobe = nprobe;
+    p.offsets = ivf->d_offsets;
+    p.members = ivf->d_members;
+    p.splits = splits;
+    p.K = k;
+    p.P = P;
+    p.limit = P - k - period;
+    p.id_base = (uint32_t)ds->id_base;
+    p.partial = partial.as<uint64_t>();
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024)
+            VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ProfScope prof("ivf_scan", st);
+        kern<<<nq * splits, IVF_THREADS, smem, st>>>(p);
+        VDB_LAUNCHED();
+    };
+    if (ds->dtype == VDB_F32) {
+        if (ds->metric == VDB_L2SQR) go(ivf_scan_kernel<VDB_L2SQR, 1>);
+        else go(ivf_scan_kernel<VDB_COSINE, 1>);
+    } else {
+        if (ds->metric == VDB_L2SQR) go(ivf_scan_kernel<VDB_L2SQR, 4>);
+        else go(ivf_scan_kernel<VDB_COSINE, 4>);
+    }
+    launch_merge_keys(partial.as<uint64_t>(), splits, nq, k, false, k, d_keys, nullptr, nullptr, nullptr, st);
+}
+
+}  // namespace vdb

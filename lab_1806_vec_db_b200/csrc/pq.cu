@@ -1,0 +1,545 @@
+// pq.cu — K6/K7/K8: product-quantisation encode, lookup tables and the ADC scan with top-ef + rerank.
+//
+// Replaces (reference paths):
+//   pq_groups                         src/distance/pq_table.rs:38-53
+//   pq_encode + encode loop           src/distance/pq_table.rs:66-91, 178-181 (serial over N in the reference)
+//   PQTable::create_lookup            src/distance/pq_table.rs:195-224
+//   ADC DistanceAdapter<[u8], LUT>    src/distance/pq_table.rs:239-301
+//   FlatIndex::knn_pq + pq_resort     src/index_algorithm/flat_index.rs:84-104, candidate_pair.rs:102-108
+//
+// Codes, lookup tables and ADC distances are bit-exact: every sum is one thread's sequential f32 chain
+// in the reference's order (group order, low nibble = even group first) with unfused multiply/add.
+// HBM layout of the codes for the scan: blocks of 32 rows, word-major ([block][word][lane]) so a warp's
+// load of one code word for its 32 rows is a single coalesced 128-byte request; one lane owns one row, all
+// lanes look up the SAME group at the same time, so the 16-entry LUT row is read conflict free.
+#include <cstring>
+
+#include "index.cuh"
+#include "topk.cuh"
+
+namespace vdb {
+
+void pq_groups_host(uint32_t dim, uint32_t m, std::vector<uint32_t>& lo, std::vector<uint32_t>& len) {
+    VDB_REQUIRE(dim > 0, "dim must be greater than 0 in PQTable.");
+    VDB_REQUIRE(m > 0, "m must be greater than 0 in PQTable.");
+    VDB_REQUIRE(dim >= m, "dim must be greater than or equal to m in PQTable.");
+    lo.clear();
+    len.clear();
+    uint32_t cur = 0;
+    while (cur < dim) {
+        const uint32_t rem = m - (uint32_t)lo.size();
+        const uint32_t gs = (dim - cur + rem - 1) / rem;
+        lo.push_back(cur);
+        len.push_back(gs);
+        cur += gs;
+    }
+}
+
+template <typename T> __device__ __forceinline__ float pq_f32(T v) { return (float)v; }
+
+// exact (reference-order) distance of a sub-vector against one centroid
+template <typename T, int METRIC>
+__device__ __forceinline__ float sub_distance(const T* __restrict__ v, const T* __restrict__ c, uint32_t len,
+                                              float cnorm) {
+    float s = 0.f, svv = 0.f;
+    for (uint32_t j = 0; j < len; ++j) {
+        const float x = pq_f32(v[j]), y = pq_f32(c[j]);
+        if (METRIC == VDB_L2SQR) {
+            const float df = __fsub_rn(x, y);
+            s = __fadd_rn(s, __fmul_rn(df, df));
+        } else {
+            s = __fadd_rn(s, __fmul_rn(x, y));
+            svv = __fadd_rn(svv, __fmul_rn(x, x));
+        }
+    }
+    if (METRIC == VDB_L2SQR) return s;
+    const float den = fmaxf(__fmul_rn(sqrtf(svv), cnorm), 1e-10f);
+    return __fsub_rn(1.0f, __fdiv_rn(s, den));
+}
+
+// per centroid: dot(c,c) (dist_cache for cosine) and ||c||
+template <typename T>
+__global__ void pq_centroid_norms_kernel(const T* __restrict__ cb, const uint32_t* __restrict__ groups, uint32_t m,
+                                         uint32_t kc, int metric, float* __restrict__ dist_cache,
+                                         float* __restrict__ cb_norm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m * kc) return;
+    const uint32_t g = i / kc, c = i - g * kc;
+    const uint32_t len = groups[3 * g + 1], off = groups[3 * g + 2];
+    const T* cc = cb + off + (size_t)c * len;
+    float s = 0.f;
+    for (uint32_t j = 0; j < len; ++j) {
+        const float y = pq_f32(cc[j]);
+        s = __fadd_rn(s, __fmul_rn(y, y));
+    }
+    dist_cache[i] = metric == VDB_COSINE ? s : 0.f;
+    cb_norm[i] = sqrtf(s);
+}
+
+// K6: one thread per (row, code byte)
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256) pq_encode_kernel(const T* __restrict__ rows, uint64_t n, uint64_t pitch,
+                                                        const T* __restrict__ cb, const uint32_t* __restrict__ groups,
+                                                        const float* __restrict__ cb_norm, uint32_t m, uint32_t n_bits,
+                                                        uint32_t kc, uint32_t enc, uint8_t* __restrict__ codes) {
+    const uint64_t total = n * enc;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = t / enc;
+        const uint32_t b = (uint32_t)(t - row * enc);
+        const uint32_t per = n_bits == 4 ? 2u : 1u;
+        uint32_t byte = 0;
+        for (uint32_t h = 0; h < per; ++h) {
+            const uint32_t g = b * per + h;
+            if (g >= m) break;
+            const uint32_t lo = groups[3 * g], len = groups[3 * g + 1], off = groups[3 * g + 2];
+            const T* v = rows + row * pitch + lo;
+            unsigned long long best = KEY_NONE;
+            for (uint32_t c = 0; c < kc; ++c) {
+                const float d = sub_distance<T, METRIC>(v, cb + off + (size_t)c * len, len, cb_norm[g * kc + c]);
+                const unsigned long long key = make_key(d, c);
+                best = key < best ? key : best;
+            }
+            byte |= key_id(best) << (4 * h);
+        }
+        codes[t] = (uint8_t)byte;
+    }
+}
+
+// reference layout [n][enc] -> [ceil(n/32)][words][32] u32 (zero padded)
+__global__ void pq_transpose_kernel(const uint8_t* __restrict__ codes, uint64_t n, uint32_t enc, uint32_t words,
+                                    uint32_t* __restrict__ out) {
+    const uint64_t total = ceil_div<uint64_t>(n, 32) * words * 32;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t lane = t & 31;
+        const uint64_t bw = t >> 5;
+        const uint64_t blk = bw / words;
+        const uint32_t w = (uint32_t)(bw - blk * words);
+        const uint64_t row = blk * 32 + lane;
+        uint32_t v = 0;
+        if (row < n)
+            for (uint32_t i = 0; i < 4; ++i) {
+                const uint32_t byte = w * 4 + i;
+                if (byte < enc) v |= (uint32_t)codes[row * enc + byte] << (8 * i);
+            }
+        out[t] = v;
+    }
+}
+
+// K7: one thread per (query, group, centroid); qcache by one thread per query (sequential dot)
+template <typename T>
+__global__ void pq_lut_kernel(const T* __restrict__ q, uint32_t nq, uint32_t dim, const T* __restrict__ cb,
+                              const uint32_t* __restrict__ groups, uint32_t m, uint32_t kc, int metric,
+                              float* __restrict__ lut, float* __restrict__ qcache) {
+    const uint64_t total = (uint64_t)nq * m * kc;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) {
+        const uint32_t qi = (uint32_t)(t / (m * kc));
+        const uint32_t r = (uint32_t)(t - (uint64_t)qi * m * kc);
+        const uint32_t g = r / kc, c = r - g * kc;
+        const uint32_t lo = groups[3 * g], len = groups[3 * g + 1], off = groups[3 * g + 2];
+        const T* v = q + (size_t)qi * dim + lo;
+        const T* cc = cb + off + (size_t)c * len;
+        float s = 0.f;
+        for (uint32_t j = 0; j < len; ++j) {
+            const float x = pq_f32(v[j]), y = pq_f32(cc[j]);
+            if (metric == VDB_L2SQR) {
+                const float df = __fsub_rn(x, y);
+                s = __fadd_rn(s, __fmul_rn(df, df));
+            } else {
+                s = __fadd_rn(s, __fmul_rn(x, y));
+            }
+        }
+        lut[t] = s;
+    }
+    if (t < nq) {
+        float s = 0.f;
+        if (metric == VDB_COSINE) {
+            const T* v = q + (size_t)t * dim;
+            for (uint32_t j = 0; j < dim; ++j) {
+                const float x = pq_f32(v[j]);
+                s = __fadd_rn(s, __fmul_rn(x, x));
+            }
+            s = sqrtf(s);
+        }
+        qcache[t] = s;
+    }
+}
+
+// ---- K8: ADC scan ----------------------------------------------------------------------------------
+constexpr int ADC_THREADS = 512;
+
+struct AdcParams {
+    const uint32_t* codes_t;
+    uint64_t n;
+    uint32_t words, m, kc;
+    const float* lut;         // [nq_pass][m*kc]
+    const float* dist_cache;  // [m*kc]
+    const float* qcache;      // [nq_pass]
+    uint32_t nq_valid;
+    uint32_t K, P, limit;
+    uint32_t id_base;
+    uint32_t iters;           // row tiles per CTA
+    uint64_t* partial;        // [NQ][gridDim.x][K]
+    float* all_out;           // optional: [nq_pass][n] every ADC distance (no top-k)
+};
+
+// LUT_SMEM: lookup tables staged in shared memory (4-bit codes); otherwise read through L1 (8-bit codes)
+template <int NQ, int NBITS, int METRIC, bool LUT_SMEM>
+__global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tab = p.m * p.kc;
+    float* s_lut = reinterpret_cast<float*>(smem);
+    float* s_dc = s_lut + (LUT_SMEM ? (size_t)NQ * tab : 0);
+    uint8_t* after = reinterpret_cast<uint8_t*>(s_dc + ((LUT_SMEM && METRIC == VDB_COSINE) ? tab : 0));
+    uint64_t* tk = reinterpret_cast<uint64_t*>(after);
+    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
+    if (LUT_SMEM) {
+        for (uint32_t i = threadIdx.x; i < NQ * tab; i += blockDim.x)
+            s_lut[i] = (i / tab < p.nq_valid) ? p.lut[i] : 0.f;
+        if (METRIC == VDB_COSINE)
+            for (uint32_t i = threadIdx.x; i < tab; i += blockDim.x) s_dc[i] = p.dist_cache[i];
+    }
+    const bool do_topk = p.all_out == nullptr;
+    if (do_topk) topk.init();
+    else __syncthreads();
+    const float* lut = LUT_SMEM ? s_lut : p.lut;
+    const float* dc = (LUT_SMEM && METRIC == VDB_COSINE) ? s_dc : p.dist_cache;
+    const int lane = threadIdx.x & 31;
+    float qn[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) qn[q] = (METRIC == VDB_COSINE && q < (int)p.nq_valid) ? p.qcache[q] : 0.f;
+
+    for (uint32_t it = 0; it < p.iters; ++it) {
+        const uint64_t tile = (uint64_t)it * gridDim.x + blockIdx.x;
+        const uint64_t row = tile * ADC_THREADS + threadIdx.x;
+        const uint64_t blk = row >> 5;
+        float sum[NQ];
+        float cdp = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) sum[q] = 0.f;
+        const bool in = row < p.n;
+        if (in) {
+            const uint32_t* cw = p.codes_t + blk * p.words * 32 + lane;
+            uint32_t g = 0;
+            for (uint32_t w = 0; w < p.words; ++w) {
+                const uint32_t word = cw[(size_t)w * 32];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t byte = (word >> (8 * b)) & 0xffu;
+                    if (NBITS == 4) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h, ++g) {
+                            if (g < p.m) {
+                                const uint32_t e = g * 16 + ((byte >> (4 * h)) & 0xfu);
+#pragma unroll
+                                for (int q = 0; q < NQ; ++q) sum[q] = __fadd_rn(sum[q], lut[(size_t)q * tab + e]);
+                                if (METRIC == VDB_COSINE) cdp = __fadd_rn(cdp, dc[e]);
+                            }
+                        }
+                    } else {
+                        if (g < p.m) {
+                            const uint32_t e = g * 256 + byte;
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q) sum[q] = __fadd_rn(sum[q], lut[(size_t)q * tab + e]);
+                            if (METRIC == VDB_COSINE) cdp = __fadd_rn(cdp, dc[e]);
+                        }
+                        ++g;
+                    }
+                }
+            }
+        }
+        bool want = false;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (q < (int)p.nq_valid && in) {
+                float d = sum[q];
+                if (METRIC == VDB_COSINE) {
+                    const float den = fmaxf(__fmul_rn(sqrtf(cdp), qn[q]), 1e-10f);
+                    d = __fsub_rn(1.0f, __fdiv_rn(sum[q], den));
+                }
+                if (do_topk) {
+                    const uint64_t key = make_key(d, p.id_base + (uint32_t)row);
+                    if (key < topk.tau(q)) want |= topk.push(q, key);
+                } else {
+                    p.all_out[(size_t)q * p.n + row] = d;
+                }
+            }
+        }
+        if (do_topk) topk.maybe_flush(want);
+    }
+    if (do_topk) {
+        topk.final_flush();
+        for (uint32_t i = threadIdx.x; i < p.nq_valid * p.K; i += blockDim.x) {
+            const uint32_t qi = i / p.K, j = i - qi * p.K;
+            p.partial[((size_t)qi * gridDim.x + blockIdx.x) * p.K + j] = topk.seg(qi)[j];
+        }
+    }
+}
+
+constexpr size_t ADC_SMEM_MAX = 200 * 1024;
+
+template <int NQ>
+static void adc_launch(const vdb_pq* pq, const AdcParams& p, bool lut_smem, uint32_t grid, size_t smem,
+                       cudaStream_t st) {
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024)
+            VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADC_SMEM_MAX));
+        ProfScope prof("pq_adc", st);
+        kern<<<grid, ADC_THREADS, smem, st>>>(p);
+        VDB_LAUNCHED();
+    };
+    const bool cosine = pq->metric == VDB_COSINE;
+    if (pq->n_bits == 4) {
+        if (lut_smem) {
+            if (cosine) go(pq_adc_scan_kernel<NQ, 4, VDB_COSINE, true>);
+            else go(pq_adc_scan_kernel<NQ, 4, VDB_L2SQR, true>);
+        } else {
+            if (cosine) go(pq_adc_scan_kernel<NQ, 4, VDB_COSINE, false>);
+            else go(pq_adc_scan_kernel<NQ, 4, VDB_L2SQR, false>);
+        }
+    } else {
+        if (lut_smem) {
+            if (cosine) go(pq_adc_scan_kernel<NQ, 8, VDB_COSINE, true>);
+            else go(pq_adc_scan_kernel<NQ, 8, VDB_L2SQR, true>);
+        } else {
+            if (cosine) go(pq_adc_scan_kernel<NQ, 8, VDB_COSINE, false>);
+            else go(pq_adc_scan_kernel<NQ, 8, VDB_L2SQR, false>);
+        }
+    }
+}
+
+// runs the scan for `nq` queries whose LUTs are in d_lut; either top-K keys ([nq][K]) or all distances
+static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K,
+                     uint32_t id_base, uint64_t* d_keys, float* d_all, cudaStream_t st) {
+    if (nq == 0) return;
+    const uint32_t tab = pq->m * pq->kc;
+    const bool topk = d_all == nullptr;
+    const uint32_t P = topk ? topk_segment_size(K, ADC_THREADS) : 0;
+    auto smem_for = [&](int t, bool ls) {
+        size_t s = ls ? ((size_t)t * tab + (pq->metric == VDB_COSINE ? tab : 0)) * 4 : 0;
+        if (topk) s += TopkSmem::bytes(t, P);
+        return s;
+    };
+    int nqt = 4;
+    bool lut_smem = true;
+    while (nqt > 1 && smem_for(nqt, true) > ADC_SMEM_MAX) nqt >>= 1;
+    if (smem_for(nqt, true) > ADC_SMEM_MAX) lut_smem = false;
+    VDB_REQUIRE(smem_for(nqt, lut_smem) <= ADC_SMEM_MAX, "ADC scan: ef=%u too large for the fused top-k", K);
+    const uint64_t tiles = ceil_div<uint64_t>(pq->n, ADC_THREADS);
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sm_count() * 2));
+    AdcParams p{};
+    p.codes_t = pq->d_codes_t;
+    p.n = pq->n;
+    p.words = pq->words;
+    p.m = pq->m;
+    p.kc = pq->kc;
+    p.dist_cache = pq->d_dist_cache;
+    p.K = K;
+    p.P = P;
+    p.limit = topk ? P - K - ADC_THREADS : 0;
+    p.id_base = id_base;
+    p.iters = (uint32_t)ceil_div<uint64_t>(tiles, grid);
+    const size_t per_q = (size_t)grid * K * 8;
+    uint32_t chunk = topk ? (uint32_t)std::max<size_t>(4, (size_t)(64u << 20) / std::max<size_t>(per_q, 1)) : nq;
+    chunk = std::min(round_up(chunk, 4u), round_up(nq, 4u));
+    DevBuf partial(topk ? per_q * chunk : 0, st);
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t qn = std::min(chunk, nq - q0);
+        for (uint32_t qq = 0; qq < qn;) {
+            const uint32_t left = qn - qq;
+            int t = nqt;
+            while (t > 1 && (uint32_t)(t >> 1) >= left) t >>= 1;
+            const uint32_t now = std::min<uint32_t>(left, t);
+            p.lut = d_lut + (size_t)(q0 + qq) * tab;
+            p.qcache = d_qcache + (q0 + qq);
+            p.nq_valid = now;
+            p.partial = topk ? partial.as<uint64_t>() + (size_t)qq * grid * K : nullptr;
+            p.all_out = topk ? nullptr : d_all + (size_t)(q0 + qq) * pq->n;
+            const size_t smem = smem_for(t, lut_smem);
+            switch (t) {
+                case 1: adc_launch<1>(pq, p, lut_smem, grid, smem, st); break;
+                case 2: adc_launch<2>(pq, p, lut_smem, grid, smem, st); break;
+                default: adc_launch<4>(pq, p, lut_smem, grid, smem, st); break;
+            }
+            qq += now;
+        }
+        if (topk)
+            launch_merge_keys(partial.as<uint64_t>(), grid, qn, K, false, K, d_keys + (size_t)q0 * K, nullptr,
+                              nullptr, nullptr, st);
+    }
+}
+
+// ---- table construction -------------------------------------------------------------------------------
+vdb_pq* pq_create(const vdb_dataset* ds, const void* h_codebooks, uint32_t m, uint32_t n_bits,
+                  const uint8_t* h_codes_in, uint8_t* h_codes_out) {
+    VDB_REQUIRE(n_bits == 4 || n_bits == 8, "n_bits must be 4 or 8 in PQTable.");
+    VDB_REQUIRE(h_codebooks, "codebooks is NULL");
+    auto pq = new vdb_pq();
+    cudaStream_t st = nullptr;
+    try {
+        pq->device = ds->device;
+        pq->dim = ds->dim;
+        pq->m = m;
+        pq->n_bits = n_bits;
+        pq->kc = 1u << n_bits;
+        pq->enc = n_bits == 4 ? (m + 1) / 2 : m;
+        pq->dtype = ds->dtype;
+        pq->metric = ds->metric;
+        pq->n = ds->n;
+        pq->words = ceil_div(pq->enc, 4u);
+        pq_groups_host(ds->dim, m, pq->g_lo, pq->g_len);
+        VDB_REQUIRE(pq->g_lo.size() == m, "pq_groups produced %zu groups for m=%u", pq->g_lo.size(), m);
+        std::vector<uint32_t> groups(3 * m);
+        uint32_t off = 0;
+        for (uint32_t g = 0; g < m; ++g) {
+            pq->g_off.push_back(off);
+            groups[3 * g] = pq->g_lo[g];
+            groups[3 * g + 1] = pq->g_len[g];
+            groups[3 * g + 2] = off;
+            off += pq->kc * pq->g_len[g];
+            pq->max_len = std::max(pq->max_len, pq->g_len[g]);
+        }
+        const size_t es = ds->elem_size();
+        VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        VDB_CUDA(cudaMalloc(&pq->d_codebooks, (size_t)off * es));
+        VDB_CUDA(cudaMalloc(&pq->d_groups, groups.size() * 4));
+        VDB_CUDA(cudaMalloc(&pq->d_dist_cache, (size_t)m * pq->kc * 4));
+        VDB_CUDA(cudaMalloc(&pq->d_cb_norm, (size_t)m * pq->kc * 4));
+        VDB_CUDA(cudaMalloc(&pq->d_codes, std::max<size_t>(1, pq->n * pq->enc)));
+        VDB_CUDA(cudaMalloc(&pq->d_codes_t, std::max<size_t>(1, ceil_div<uint64_t>(pq->n, 32) * pq->words * 32 * 4)));
+        VDB_CUDA(cudaMemcpyAsync(pq->d_codebooks, h_codebooks, (size_t)off * es, cudaMemcpyHostToDevice, st));
+        VDB_CUDA(cudaMemcpyAsync(pq->d_groups, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice, st));
+        const uint32_t tab = m * pq->kc;
+        if (ds->dtype == VDB_F32)
+            pq_centroid_norms_kernel<float><<<ceil_div(tab, 256u), 256, 0, st>>>(
+                (const float*)pq->d_codebooks, pq->d_groups, m, pq->kc, pq->metric, pq->d_dist_cache, pq->d_cb_norm);
+        else
+            pq_centroid_norms_kernel<uint8_t><<<ceil_div(tab, 256u), 256, 0, st>>>(
+                (const uint8_t*)pq->d_codebooks, pq->d_groups, m, pq->kc, pq->metric, pq->d_dist_cache, pq->d_cb_norm);
+        VDB_LAUNCHED();
+        if (pq->n) {
+            if (h_codes_in) {
+                VDB_CUDA(cudaMemcpyAsync(pq->d_codes, h_codes_in, pq->n * pq->enc, cudaMemcpyHostToDevice, st));
+            } else {
+                const uint64_t total = pq->n * pq->enc;
+                const uint32_t grid = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(total, 256), (uint64_t)sm_count() * 32);
+                ProfScope prof("pq_encode", st);
+                auto go = [&](auto kern, auto* tag) {
+                    using T = std::remove_pointer_t<decltype(tag)>;
+                    kern<<<grid, 256, 0, st>>>((const T*)ds->d_rows, ds->n, (uint64_t)ds->pitch, (const T*)pq->d_codebooks,
+                                               pq->d_groups, pq->d_cb_norm, m, n_bits, pq->kc, pq->enc, pq->d_codes);
+                };
+                if (ds->dtype == VDB_F32) {
+                    if (pq->metric == VDB_L2SQR) go(pq_encode_kernel<float, VDB_L2SQR>, (float*)nullptr);
+                    else go(pq_encode_kernel<float, VDB_COSINE>, (float*)nullptr);
+                } else {
+                    if (pq->metric == VDB_L2SQR) go(pq_encode_kernel<uint8_t, VDB_L2SQR>, (uint8_t*)nullptr);
+                    else go(pq_encode_kernel<uint8_t, VDB_COSINE>, (uint8_t*)nullptr);
+                }
+                VDB_LAUNCHED();
+            }
+            const uint64_t tt = ceil_div<uint64_t>(pq->n, 32) * pq->words * 32;
+            pq_transpose_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(tt, 256), 1u << 20), 256, 0, st>>>(
+                pq->d_codes, pq->n, pq->enc, pq->words, pq->d_codes_t);
+            VDB_LAUNCHED();
+            if (h_codes_out)
+                VDB_CUDA(cudaMemcpyAsync(h_codes_out, pq->d_codes, pq->n * pq->enc, cudaMemcpyDeviceToHost, st));
+        }
+        VDB_CUDA(cudaStreamSynchronize(st));
+        cudaStreamDestroy(st);
+    } catch (...) {
+        if (st) cudaStreamDestroy(st);
+        pq_destroy(pq);
+        throw;
+    }
+    return pq;
+}
+
+void pq_destroy(vdb_pq* pq) {
+    if (!pq) return;
+    cudaFree(pq->d_codebooks);
+    cudaFree(pq->d_groups);
+    cudaFree(pq->d_dist_cache);
+    cudaFree(pq->d_cb_norm);
+    cudaFree(pq->d_codes);
+    cudaFree(pq->d_codes_t);
+    delete pq;
+}
+
+void pq_lut(const vdb_pq* pq, const void* d_queries, uint32_t nq, float* d_lut, float* d_qcache, cudaStream_t st) {
+    if (nq == 0) return;
+    const uint64_t total = (uint64_t)nq * pq->m * pq->kc;
+    const uint32_t grid = (uint32_t)ceil_div<uint64_t>(std::max<uint64_t>(total, nq), 256);
+    if (pq->dtype == VDB_F32)
+        pq_lut_kernel<float><<<grid, 256, 0, st>>>((const float*)d_queries, nq, pq->dim, (const float*)pq->d_codebooks,
+                                                  pq->d_groups, pq->m, pq->kc, pq->metric, d_lut, d_qcache);
+    else
+        pq_lut_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)d_queries, nq, pq->dim,
+                                                    (const uint8_t*)pq->d_codebooks, pq->d_groups, pq->m, pq->kc,
+                                                    pq->metric, d_lut, d_qcache);
+    VDB_LAUNCHED();
+}
+
+void pq_adc_all(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, float* d_out,
+                cudaStream_t st) {
+    adc_scan(pq, d_lut, d_qcache, nq, 0, 0, nullptr, d_out, st);
+}
+
+// keys -> (query index, local row, valid) for the rerank
+__global__ void keys_to_pairs_kernel(const uint64_t* __restrict__ keys, uint64_t count, uint32_t per_q, uint32_t id_base,
+                                     uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid, uint8_t* __restrict__ valid) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[j];
+        const bool ok = k != KEY_NONE;
+        qidx[j] = (uint32_t)(j / per_q);
+        rid[j] = ok ? key_id(k) - id_base : 0u;
+        valid[j] = ok;
+    }
+}
+__global__ void rekey_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ ids, uint32_t id_base,
+                             const uint8_t* __restrict__ valid, uint64_t count, uint64_t* __restrict__ keys) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x)
+        keys[j] = (!valid || valid[j]) ? make_key(dist[j], ids[j] + id_base) : KEY_NONE;
+}
+void rekey(const float* d_dist, const uint32_t* d_ids, const uint8_t* d_valid, uint64_t count, uint64_t* d_keys,
+           cudaStream_t st) {
+    if (count == 0) return;
+    rekey_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), 4096), 256, 0, st>>>(d_dist, d_ids, 0,
+                                                                                                  d_valid, count, d_keys);
+    VDB_LAUNCHED();
+}
+
+// exact rerank of [nq][kk] candidate keys -> [nq][k] keys ordered by (exact distance, id)
+void rerank_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, const uint64_t* d_cand, uint32_t kk,
+                 uint32_t k, uint64_t* d_keys, cudaStream_t st) {
+    const uint64_t count = (uint64_t)nq * kk;
+    if (count == 0 || k == 0) return;
+    DevBuf qidx(count * 4, st), rid(count * 4, st), valid(count, st), dist(count * 4, st), keys2(count * 8, st);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), 4096);
+    keys_to_pairs_kernel<<<grid, 256, 0, st>>>(d_cand, count, kk, (uint32_t)ds->id_base, qidx.as<uint32_t>(),
+                                               rid.as<uint32_t>(), valid.as<uint8_t>());
+    VDB_LAUNCHED();
+    exact_pair_distances(ds, d_queries, qidx.as<uint32_t>(), rid.as<uint32_t>(), count, dist.as<float>(), st);
+    rekey_kernel<<<grid, 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(), (uint32_t)ds->id_base,
+                                       valid.as<uint8_t>(), count, keys2.as<uint64_t>());
+    VDB_LAUNCHED();
+    launch_merge_keys(keys2.as<uint64_t>(), 1, nq, kk, false, k, d_keys, nullptr, nullptr, nullptr, st);
+}
+
+void pq_knn_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,
+                 uint32_t ef, uint64_t* d_keys, cudaStream_t st) {
+    VDB_REQUIRE(ds->metric == pq->metric, "Distance algorithm mismatch.");
+    VDB_REQUIRE(ds->n == pq->n && ds->dim == pq->dim && ds->dtype == pq->dtype,
+                "PQ table was built for a different vector set (it must be rebuilt after add/delete)");
+    if (nq == 0 || k == 0) return;
+    const uint32_t kk = std::max(ef, k);
+    const uint32_t tab = pq->m * pq->kc;
+    DevBuf lut((size_t)nq * tab * 4, st), qcache((size_t)nq * 4, st), cand((size_t)nq * kk * 8, st);
+    pq_lut(pq, d_queries, nq, lut.as<float>(), qcache.as<float>(), st);
+    adc_scan(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, cand.as<uint64_t>(), nullptr, st);
+    rerank_keys(ds, d_queries, nq, cand.as<uint64_t>(), kk, k, d_keys, st);
+}
+
+}  // namespace vdb

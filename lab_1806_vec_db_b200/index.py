@@ -141,3 +141,302 @@ def calc_dist(a, b, dist="cosine"):
     out = np.zeros(1, np.float32)
     L.check(L.lib().vdb_calc_dist(L.ptr(a), L.ptr(b), 1, a.size, L.F32, L.metric_code(dist), L.ptr(out)))
     return float(out[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# distance primitives
+# ---------------------------------------------------------------------------------------------------
+def calc_dist_batch(a, b, dist="l2sqr"):
+    """DistanceAdapter<[T],[T]>::distance for row pairs (a[i], b[i]); dist may also be "dot"."""
+    a, b = _as_rows(a), _as_rows(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("The dimension of the vectors doesn't match.")
+    code = L.DOT if (isinstance(dist, str) and dist.lower() == "dot") else L.metric_code(dist)
+    out = np.zeros(a.shape[0], np.float32)
+    L.check(L.lib().vdb_calc_dist(L.ptr(a), L.ptr(b), a.shape[0], a.shape[1], L.dtype_code(a), code, L.ptr(out)))
+    return out
+
+
+def dist_cache(vec_set: DeviceVecSet):
+    """DistanceAlgorithm::dist_cache for every row (distance/mod.rs:31-36)."""
+    out = np.zeros(len(vec_set), np.float32)
+    L.check(L.lib().vdb_row_cache(vec_set._h, L.ptr(out)))
+    return out
+
+
+def gather_dist(vec_set: DeviceVecSet, queries, cand_lists):
+    """Batched cached-form distances for HNSW frontier expansion (hnsw_index.rs:351-358).
+    cand_lists[j] = local row ids to compare with queries[j]. Returns a list of f32 arrays."""
+    q = _as_rows(queries, vec_set.dtype)
+    off = np.zeros(len(cand_lists) + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in cand_lists])
+    ids = (np.concatenate([np.asarray(c, np.uint32) for c in cand_lists]) if len(cand_lists) and off[-1]
+           else np.zeros(0, np.uint32))
+    out = np.zeros(int(off[-1]), np.float32)
+    L.check(L.lib().vdb_gather_dist(vec_set._h, L.ptr(q), q.shape[0], L.ptr(ids) if ids.size else None,
+                                    L.ptr(off), L.ptr(out) if out.size else None))
+    return [out[int(off[j]):int(off[j + 1])] for j in range(len(cand_lists))]
+
+
+# ---------------------------------------------------------------------------------------------------
+# k-means (reference src/distance/k_means.rs)
+# ---------------------------------------------------------------------------------------------------
+class KMeansConfig(NamedTuple):
+    """KMeansConfig (k_means.rs:15-31)."""
+    k: int
+    max_iter: int = 20
+    tol: float = 1e-6
+    dist: str = "l2sqr"
+    selected: tuple = None
+
+
+def k_means_init(rows, config: KMeansConfig, rng):
+    """k-means++ (k_means.rs:61-87). The draws consume the CALLER's rng (numpy Generator here; the
+    reference's ChaCha12 stream cannot be reproduced), the weight update runs on the GPU."""
+    rows = np.ascontiguousarray(rows)
+    n, dim = rows.shape
+    lo, hi = config.selected if config.selected is not None else (0, dim)
+    first = int(rng.integers(0, n))
+    cents = [rows[first, lo:hi].copy()]
+    w = np.full(n, np.inf, np.float32)
+    lib = L.lib()
+    for _ in range(1, config.k):
+        c = np.ascontiguousarray(cents[-1])
+        L.check(lib.vdb_kmeans_pp_weights(L.ptr(rows), n, dim, L.dtype_code(rows), L.metric_code(config.dist),
+                                          L.ptr(c), lo, hi, L.ptr(w)))
+        fallback = int(rng.integers(0, n))  # eager unwrap_or argument (k_means.rs:80-82)
+        ww = w.astype(np.float64)
+        ok = np.isfinite(ww).all() and (ww >= 0).all() and ww.sum() > 0
+        pick = int(rng.choice(n, p=ww / ww.sum())) if ok else fallback
+        cents.append(rows[pick, lo:hi].copy())
+    return np.ascontiguousarray(np.stack(cents))
+
+
+class KMeans:
+    """KMeans<T> (k_means.rs:34-37, 95-191)."""
+
+    def __init__(self, config: KMeansConfig, centroids):
+        self.config = config
+        self.centroids = np.ascontiguousarray(centroids)
+
+    @classmethod
+    def from_vec_set(cls, rows, config: KMeansConfig, rng=None, init_centroids=None):
+        rows = np.ascontiguousarray(rows)
+        if config.k <= 0:
+            raise ValueError("The number of clusters should be greater than 0.")
+        n, dim = rows.shape
+        lo, hi = config.selected if config.selected is not None else (0, dim)
+        if hi > dim:
+            raise ValueError("The selected range should be in the range [0, vec_set.dim())")
+        if init_centroids is None:
+            init_centroids = k_means_init(rows, config, rng if rng is not None else np.random.default_rng())
+        cent = np.array(init_centroids, dtype=rows.dtype, order="C", copy=True)
+        iters = C.c_uint32(0)
+        L.check(L.lib().vdb_kmeans_train(L.ptr(rows), n, dim, L.dtype_code(rows), L.metric_code(config.dist),
+                                         L.ptr(cent), config.k, lo, hi, config.max_iter, config.tol, C.byref(iters)))
+        self = cls(config, cent)
+        self.iterations = int(iters.value)
+        return self
+
+    def find_nearest_batch(self, rows):
+        rows = _as_rows(rows, self.centroids.dtype)
+        n, dim = rows.shape
+        lo, hi = self.config.selected if self.config.selected is not None else (0, dim)
+        out = np.zeros(n, np.uint32)
+        L.check(L.lib().vdb_kmeans_assign(L.ptr(rows), n, dim, L.dtype_code(rows), L.metric_code(self.config.dist),
+                                          L.ptr(self.centroids), self.centroids.shape[0], lo, hi, L.ptr(out)))
+        return out
+
+    def find_nearest(self, v):
+        """KMeans::find_nearest (k_means.rs:166-170)."""
+        return int(self.find_nearest_batch(np.asarray(v).reshape(1, -1))[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# PQ (reference src/distance/pq_table.rs)
+# ---------------------------------------------------------------------------------------------------
+def pq_groups(dim, m):
+    """pq_groups (pq_table.rs:38-53)."""
+    out = np.zeros((max(m, 1), 2), np.uint32)
+    L.check(L.lib().vdb_pq_groups(dim, m, L.ptr(out)))
+    return [(int(a), int(b)) for a, b in out[:m]]
+
+
+class PQConfig(NamedTuple):
+    """PQConfig (pq_table.rs:19-34)."""
+    n_bits: int
+    m: int
+    dist: str = "l2sqr"
+    k_means_size: int = None
+    k_means_max_iter: int = 20
+    k_means_tol: float = 1e-6
+
+
+class PQTable:
+    """PQTable<T> (pq_table.rs:116-137): codebooks + codes, device resident."""
+
+    def __init__(self, vec_set: DeviceVecSet, config: PQConfig, codebooks, codes=None):
+        if config.n_bits not in (4, 8):
+            raise ValueError("n_bits must be 4 or 8 in PQTable.")
+        self.config = config
+        self.vec_set = vec_set
+        self.dim = vec_set.dim
+        self.k = 1 << config.n_bits
+        self.encoded_dim = (config.m + 1) // 2 if config.n_bits == 4 else config.m
+        self.codebooks = np.ascontiguousarray(codebooks, dtype=vec_set.dtype).reshape(-1)
+        self._h = C.c_void_p()
+        n = len(vec_set)
+        if codes is None:
+            self.encoded_vec_set = np.zeros((n, self.encoded_dim), np.uint8)
+            L.check(L.lib().vdb_pq_create(vec_set._h, L.ptr(self.codebooks), config.m, config.n_bits,
+                                          L.ptr(self.encoded_vec_set), C.byref(self._h)))
+        else:
+            self.encoded_vec_set = np.ascontiguousarray(codes, np.uint8)
+            L.check(L.lib().vdb_pq_create_from_codes(vec_set._h, L.ptr(self.codebooks), config.m, config.n_bits,
+                                                     L.ptr(self.encoded_vec_set), C.byref(self._h)))
+
+    @classmethod
+    def from_vec_set(cls, vec_set, rows_host, config: PQConfig, rng=None):
+        """PQTable::from_vec_set (pq_table.rs:141-191): sample, per-group k-means, encode."""
+        rng = rng if rng is not None else np.random.default_rng()
+        rows_host = np.ascontiguousarray(rows_host)
+        train = rows_host
+        if config.k_means_size is not None:
+            perm = rng.permutation(len(rows_host))[:config.k_means_size]  # VecSet::random_sample (vec_set.rs:154-163)
+            train = np.ascontiguousarray(rows_host[perm])
+        books = []
+        for lo, hi in pq_groups(rows_host.shape[1], config.m):
+            km = KMeans.from_vec_set(train, KMeansConfig(1 << config.n_bits, config.k_means_max_iter,
+                                                         config.k_means_tol, config.dist, (lo, hi)), rng)
+            books.append(km.centroids.reshape(-1))
+        return cls(vec_set, config, np.concatenate(books))
+
+    def create_lookup(self, queries):
+        """PQTable::create_lookup (pq_table.rs:195-224) -> (lookup [nq, m*k], dist_cache [nq])."""
+        q = _as_rows(queries, self.vec_set.dtype)
+        lut = np.zeros((q.shape[0], self.config.m * self.k), np.float32)
+        qc = np.zeros(q.shape[0], np.float32)
+        L.check(L.lib().vdb_pq_lut(self._h, L.ptr(q), q.shape[0], L.ptr(lut), L.ptr(qc)))
+        return lut, qc
+
+    def adc_distances(self, queries):
+        """ADC distance of every code (pq_table.rs:239-301) -> [nq, n]."""
+        q = _as_rows(queries, self.vec_set.dtype)
+        out = np.zeros((q.shape[0], len(self.vec_set)), np.float32)
+        L.check(L.lib().vdb_pq_adc_all(self._h, L.ptr(q), q.shape[0], L.ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            L.lib().vdb_pq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _knn_pq_batch(self, queries, k, ef, pq_table):
+    vs = self.vec_set
+    q = _as_rows(queries, vs.dtype)
+    if q.shape[1] != vs.dim:
+        raise ValueError("The dimension of the query doesn't match.")
+    if L.metric_code(pq_table.config.dist) != vs.metric:
+        raise ValueError("Distance algorithm mismatch.")
+    nq = q.shape[0]
+    ids = np.full((nq, k), np.iinfo(np.uint64).max, np.uint64)
+    dist = np.full((nq, k), np.nan, np.float32)
+    counts = np.zeros(nq, np.uint32)
+    L.check(L.lib().vdb_pq_knn(vs._h, pq_table._h, L.ptr(q), nq, k, ef, L.ptr(ids), L.ptr(dist), L.ptr(counts)))
+    return ids, dist, counts
+
+
+def _knn_pq(self, query, k, ef, pq_table):
+    """IndexPQ::knn_pq (flat_index.rs:84-104)."""
+    return _pairs(*_knn_pq_batch(self, np.asarray(query).reshape(1, -1), k, ef, pq_table))[0]
+
+
+FlatIndex.knn_pq_batch = _knn_pq_batch
+FlatIndex.knn_pq = _knn_pq
+
+
+# ---------------------------------------------------------------------------------------------------
+# IVF (reference src/index_algorithm/ivf_index.rs)
+# ---------------------------------------------------------------------------------------------------
+class IVFConfig(NamedTuple):
+    """IVFConfig (ivf_index.rs:20-31)."""
+    k: int
+    k_means_size: int = None
+    k_means_max_iter: int = 20
+    k_means_tol: float = 1e-6
+
+
+class IVFIndex:
+    """IVFIndex<T> (ivf_index.rs:34-47)."""
+
+    def __init__(self, vec_set: DeviceVecSet, centroids, config: IVFConfig = None):
+        self.vec_set = vec_set
+        self.config = config
+        self.default_n_probes = 4  # ivf_index.rs:97
+        self.centroids = np.ascontiguousarray(centroids, dtype=vec_set.dtype)
+        self._h = C.c_void_p()
+        self.assignment = np.zeros(len(vec_set), np.uint32)
+        L.check(L.lib().vdb_ivf_create(vec_set._h, L.ptr(self.centroids), self.centroids.shape[0],
+                                       L.ptr(self.assignment), C.byref(self._h)))
+
+    @classmethod
+    def from_vec_set(cls, vec_set, rows_host, dist, config: IVFConfig, rng=None):
+        """IndexFromVecSet::from_vec_set (ivf_index.rs:67-107)."""
+        rng = rng if rng is not None else np.random.default_rng()
+        rows_host = np.ascontiguousarray(rows_host)
+        train = rows_host
+        if config.k_means_size is not None:
+            train = np.ascontiguousarray(rows_host[rng.permutation(len(rows_host))[:config.k_means_size]])
+        km = KMeans.from_vec_set(train, KMeansConfig(config.k, config.k_means_max_iter, config.k_means_tol, dist), rng)
+        if not isinstance(vec_set, DeviceVecSet):
+            vec_set = DeviceVecSet(rows_host, dist)
+        return cls(vec_set, km.centroids, config)
+
+    @property
+    def clusters(self):
+        off = np.zeros(self.centroids.shape[0] + 1, np.uint64)
+        mem = np.zeros(len(self.vec_set), np.uint32)
+        L.check(L.lib().vdb_ivf_lists(self._h, L.ptr(off), L.ptr(mem)))
+        return [mem[int(off[c]):int(off[c + 1])] for c in range(self.centroids.shape[0])]
+
+    def set_default_ef(self, n_probes):
+        self.default_n_probes = n_probes
+
+    def knn_with_ef_batch(self, queries, k, n_probes):
+        vs = self.vec_set
+        q = _as_rows(queries, vs.dtype)
+        if q.shape[1] != vs.dim:
+            raise ValueError("The dimension of the query doesn't match.")
+        if n_probes <= 0:
+            raise ValueError("The number of probes should be greater than 0.")
+        nq = q.shape[0]
+        ids = np.full((nq, k), np.iinfo(np.uint64).max, np.uint64)
+        dist = np.full((nq, k), np.nan, np.float32)
+        counts = np.zeros(nq, np.uint32)
+        L.check(L.lib().vdb_ivf_knn(vs._h, self._h, L.ptr(q), nq, k, n_probes, L.ptr(ids), L.ptr(dist), L.ptr(counts)))
+        return ids, dist, counts
+
+    def knn_with_ef(self, query, k, n_probes):
+        """IndexKNNWithEf::knn_with_ef (ivf_index.rs:143-154); ef = number of probes."""
+        return _pairs(*self.knn_with_ef_batch(np.asarray(query).reshape(1, -1), k, n_probes))[0]
+
+    def knn(self, query, k):
+        return self.knn_with_ef(query, k, self.default_n_probes)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            L.lib().vdb_ivf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

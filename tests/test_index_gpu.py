@@ -1,0 +1,261 @@
+"""Parity of the CUDA k-means / PQ / IVF / distance paths (through the C ABI) against the CPU oracle.
+
+Index-valued results (assignments, codes, lists, probe order) and the quantities they are derived from
+(lookup tables, ADC sums) must be BIT-EXACT; reranked distances follow the 1e-5 rule."""
+import numpy as np
+import pytest
+
+from conftest import ATOL, RTOL, assert_knn_parity, close
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def V():
+    import lab_1806_vec_db_b200 as V
+    return V
+
+
+# ---- distance primitives ------------------------------------------------------------------------------
+def test_calc_dist_known_answers(V):
+    """distance/mod.rs:138-150 and the pyo3 calc_dist default (cosine)."""
+    assert abs(V.calc_dist([1, 2, 3], [4, 5, 6], "l2sqr") - 27.0) < 1e-6
+    assert abs(V.calc_dist([1, 2, 3], [2, 4, 6]) - 0.0) < 1e-6
+    a8, b8 = np.array([[1, 2, 3]], np.uint8), np.array([[2, 4, 6]], np.uint8)
+    assert abs(V.calc_dist_batch(a8, b8, "cosine")[0]) < 1e-6
+    with pytest.raises(ValueError):
+        V.calc_dist([1, 2], [1, 2, 3])
+    with pytest.raises(ValueError):
+        V.calc_dist([1, 2], [1, 2], "manhattan")
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine", "dot"])
+def test_calc_dist_batch_vs_oracle(V, fixtures, oracle, metric):
+    a, b = fixtures["base"][:300], fixtures["test"][:300]
+    got = V.calc_dist_batch(a, b, metric)
+    want = np.array([oracle.dot(x, y) if metric == "dot" else oracle.distance(x, y, metric) for x, y in zip(a, b)])
+    assert close(got, want).all()
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_row_cache_and_gather_dist(V, fixtures, golden, oracle, metric):
+    """K3/K10: dist_cache per row and cached-form candidate distances (hnsw_index.rs:351-358)."""
+    base, test = fixtures["base"], fixtures["test"]
+    vs = V.DeviceVecSet(base, metric)
+    cache = V.dist_cache(vs)
+    assert close(cache, golden[f"cached_{metric}_rowcache"]).all()
+    cand = np.arange(0, 1000, 7)
+    got = V.gather_dist(vs, test[3:5], [cand, cand[:5]])
+    assert close(got[0], golden[f"cached_{metric}_dist"], RTOL, 2e-6).all()
+    want1 = oracle.gather_dist(base, golden[f"cached_{metric}_rowcache"], test[4], oracle.dist_cache(test[4], metric),
+                               cand[:5], metric)
+    assert close(got[1], want1, RTOL, 2e-6).all()
+    assert [len(g) for g in V.gather_dist(vs, test[:2], [[], [1]])] == [0, 1]
+    with pytest.raises(V.VdbError):
+        V.gather_dist(vs, test[:1], [[1000]])
+
+
+# ---- k-means -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_assign_bit_exact_golden(V, fixtures, golden, metric):
+    base = fixtures["base"]
+    km = V.KMeans(V.KMeansConfig(16, dist=metric), base[7:23])
+    assert (km.find_nearest_batch(base) == golden[f"assign16_{metric}"]).all()
+
+
+def test_assign_selected_range_golden(V, fixtures, golden):
+    base = fixtures["base"]
+    km = V.KMeans(V.KMeansConfig(16, dist="l2sqr", selected=(100, 113)), np.ascontiguousarray(base[7:23, 100:113]))
+    assert (km.find_nearest_batch(base) == golden["assign16_sel_l2sqr"]).all()
+    assert km.find_nearest(base[5]) == golden["assign16_sel_l2sqr"][5]
+
+
+@pytest.mark.parametrize("k,d", [(1, 7), (3, 5), (16, 4), (33, 12), (128, 960), (200, 64), (5, 1500)])
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_assign_bit_exact_shapes(V, oracle, k, d, metric):
+    rng = np.random.default_rng(k * 7 + d)
+    n = 700 if d >= 960 else 3000
+    rows = rng.random((n, d + 3), dtype=np.float32)
+    cent = rng.random((k, d), dtype=np.float32)
+    cent[k // 2] = cent[0]  # an exact duplicate centroid: ties must go to the lowest id
+    km = V.KMeans(V.KMeansConfig(k, dist=metric, selected=(2, 2 + d)), cent)
+    want = oracle.kmeans_assign(rows, cent, metric, sel=(2, 2 + d), nthreads=8)
+    assert (km.find_nearest_batch(rows) == want).all()
+
+
+def test_assign_u8_bit_exact(V, oracle):
+    rng = np.random.default_rng(2)
+    rows = rng.integers(0, 256, (2000, 48), dtype=np.uint8)
+    cent = rng.integers(0, 256, (20, 48), dtype=np.uint8)
+    for metric in ("l2sqr", "cosine"):
+        km = V.KMeans(V.KMeansConfig(20, dist=metric), cent)
+        assert (km.find_nearest_batch(rows) == oracle.kmeans_assign(rows, cent, metric)).all()
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_lloyd_bit_exact_given_initial_centroids(V, fixtures, oracle, metric):
+    """k_means.rs:108-161 from identical initial centroids: centroids and iteration count bit-exact."""
+    rows = np.ascontiguousarray(fixtures["base"][:400])
+    for sel, k in (((0, 5), 3), ((100, 104), 16), (None, 7)):
+        init = oracle.kmeans_pp_init(rows, k, metric, seed=42, sel=sel)
+        want, it_want = oracle.kmeans_lloyd(rows, init, metric, 20, 1e-6, sel=sel)
+        km = V.KMeans.from_vec_set(rows, V.KMeansConfig(k, 20, 1e-6, metric, sel), init_centroids=init)
+        assert km.iterations == it_want
+        assert (bits(km.centroids) == bits(want)).all()
+
+
+def test_lloyd_u8_and_empty_cluster(V, oracle):
+    rows = np.array([[0, 0], [2, 0], [0, 2], [2, 2]], np.uint8)
+    init = np.array([[1, 1], [200, 200]], np.uint8)
+    km = V.KMeans.from_vec_set(rows, V.KMeansConfig(2, 5, 1e-6, "l2sqr"), init_centroids=init)
+    assert km.centroids.tolist() == [[1, 1], [200, 200]] and km.iterations == 1
+    rng = np.random.default_rng(9)
+    rows = rng.integers(0, 256, (500, 6), dtype=np.uint8)
+    init = rows[:4].copy()
+    want, it_want = oracle.kmeans_lloyd(rows, init, "l2sqr", 10, 1e-6)
+    km = V.KMeans.from_vec_set(rows, V.KMeansConfig(4, 10, 1e-6, "l2sqr"), init_centroids=init)
+    assert (km.centroids == want).all() and km.iterations == it_want
+
+
+def test_kmeans_on_real_set_property(V, fixtures):
+    """k_means.rs:241-277 through the GPU path with k-means++ on the GPU weights."""
+    rows = np.ascontiguousarray(fixtures["base"][:400])
+    km = V.KMeans.from_vec_set(rows, V.KMeansConfig(3, 20, 1e-6, "l2sqr", (0, 5)), np.random.default_rng(42))
+    assert km.centroids.shape == (3, 5)
+    v = np.zeros(960, np.float32)
+    v[:5] = km.centroids[1]
+    assert km.find_nearest(v) == 1
+
+
+# ---- PQ ---------------------------------------------------------------------------------------------------
+def test_pq_groups_known_answers(V):
+    assert V.pq_groups(6, 2) == [(0, 3), (3, 6)]
+    assert V.pq_groups(7, 3) == [(0, 3), (3, 5), (5, 7)]
+    with pytest.raises(V.VdbError):
+        V.pq_groups(3, 5)
+
+
+@pytest.mark.parametrize("tag,m,n_bits,dimclip", [("pq240", 240, 4, 960), ("pq7", 7, 4, 13), ("pq5b8", 5, 8, 13)])
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_pq_golden_bit_exact(V, fixtures, golden, oracle, tag, m, n_bits, dimclip, metric):
+    """Codes, lookup tables and ADC distances bit-exact vs the golden vectors; knn_pq by the parity rule."""
+    rows = np.ascontiguousarray(fixtures["base"][:200, :dimclip])
+    queries = np.ascontiguousarray(fixtures["test"][:5, :dimclip])
+    vs = V.DeviceVecSet(rows, metric)
+    pq = V.PQTable(vs, V.PQConfig(n_bits, m, metric), golden[f"{tag}_codebooks"])
+    assert (pq.encoded_vec_set == golden[f"{tag}_{metric}_codes"]).all()
+    lut, qc = pq.create_lookup(queries)
+    assert (bits(lut) == bits(golden[f"{tag}_{metric}_lut"])).all()
+    assert (bits(qc) == bits(golden[f"{tag}_{metric}_qcache"])).all()
+    adc = pq.adc_distances(queries)
+    assert (bits(adc) == bits(golden[f"{tag}_{metric}_adc"])).all()
+    got = V.FlatIndex(vs).knn_pq_batch(queries, 10, 40, pq)
+    want = (golden[f"{tag}_{metric}_knn_ids"], golden[f"{tag}_{metric}_knn_dist"], np.full(5, 10))
+    assert_knn_parity(rows, queries, metric, got, want, oracle)
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_pq_precise_when_points_fewer_than_centroids(V, oracle, metric):
+    """pq_table.rs:324-372 (ADC == exact distance when every point is its own centroid)."""
+    rng = np.random.default_rng(42)
+    rows = rng.random((5, 8), dtype=np.float32)
+    cbs = []
+    for lo, hi in V.pq_groups(8, 2):
+        c = np.zeros((16, hi - lo), np.float32)
+        c[:5] = rows[:, lo:hi]
+        c[5:] = 1e3 + np.arange(11)[:, None]
+        cbs.append(c.reshape(-1))
+    vs = V.DeviceVecSet(rows, metric)
+    pq = V.PQTable(vs, V.PQConfig(4, 2, metric), np.concatenate(cbs))
+    adc = pq.adc_distances(rows)
+    for i in range(5):
+        for j in range(5):
+            assert abs(adc[i, j] - oracle.distance(rows[i], rows[j], metric)) < 1e-6
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_pq_knn_end_to_end_vs_oracle(V, fixtures, oracle, metric):
+    """C4 shape on gist_1000: m=240 4-bit, trained on the GPU; then encode/scan/rerank vs the oracle run on the
+    SAME codebooks; ef sweep incl. ef < k and ef > n."""
+    base, test = fixtures["base"], fixtures["test"][:16]
+    vs = V.DeviceVecSet(base, metric)
+    pq = V.PQTable.from_vec_set(vs, base, V.PQConfig(4, 240, metric, 300, 5, 1e-6), np.random.default_rng(42))
+    codes = oracle.pq_encode(base, pq.codebooks, 240, 4, metric, nthreads=8)
+    assert (pq.encoded_vec_set == codes).all()
+    idx = V.FlatIndex(vs)
+    for k, ef in ((10, 240), (10, 4), (3, 2000)):
+        got = idx.knn_pq_batch(test, k, ef, pq)
+        want = oracle.flat_knn_pq(base, codes, pq.codebooks, 240, 4, test, k, ef, metric, nthreads=8)
+        assert_knn_parity(base, test, metric, got, want, oracle)
+    # statistical property of pq_table.rs:407-411: p90 relative ADC error < 0.2
+    adc = pq.adc_distances(test[:4])
+    exact = np.array([[oracle.distance(q, r, metric) for r in base[:50]] for q in test[:4]])
+    rel = np.abs(adc[:, :50] - exact) / np.maximum(np.abs(exact), 1e-6)
+    assert np.quantile(rel, 0.9) < 0.2
+
+
+def test_pq_mismatch_errors(V, fixtures):
+    base = np.ascontiguousarray(fixtures["base"][:100, :16])
+    vs = V.DeviceVecSet(base, "l2sqr")
+    with pytest.raises(ValueError):
+        V.PQTable(vs, V.PQConfig(5, 4), np.zeros(16 * 16, np.float32))
+    pq = V.PQTable(vs, V.PQConfig(4, 4, "l2sqr"), np.ascontiguousarray(base[:16]).reshape(-1))
+    vs.push(base[:3])  # the reference drops the PQ table on every write (metadata_vec_table.rs:65)
+    with pytest.raises(V.VdbError):
+        V.FlatIndex(vs).knn_pq(base[0], 3, 10, pq)
+
+
+# ---- IVF --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_ivf_golden(V, fixtures, golden, oracle, metric):
+    base, test = fixtures["base"], fixtures["test"][:50]
+    vs = V.DeviceVecSet(base, metric)
+    ivf = V.IVFIndex(vs, base[7:23])
+    assert (ivf.assignment == golden[f"assign16_{metric}"]).all()
+    off, mem = oracle.ivf_lists(golden[f"assign16_{metric}"], 16)
+    for c, lst in enumerate(ivf.clusters):
+        assert (lst == mem[int(off[c]):int(off[c + 1])]).all()
+    got = ivf.knn_with_ef_batch(test, 10, 4)
+    want = (golden[f"ivf_{metric}_ids"], golden[f"ivf_{metric}_dist"], np.full(50, 10))
+    assert_knn_parity(base, test, metric, got, want, oracle)
+
+
+def test_ivf_reference_unit_shape(V, fixtures, oracle):
+    """ivf_index.rs:166-235: 1000x12, nlist=7 trained on a 100-row sample, default nprobe 4, k=6 -> same ids as Flat."""
+    base = np.ascontiguousarray(fixtures["base"][:, :12])
+    ivf = V.IVFIndex.from_vec_set(None, base, "l2sqr", V.IVFConfig(7, 100, 20, 1e-6), np.random.default_rng(42))
+    flat = V.FlatIndex(ivf.vec_set)
+    a = [p.index for p in ivf.knn(base[200], 6)]
+    b = [p.index for p in flat.knn(base[200], 6)]
+    assert a == b
+    # and against the oracle on the same centroids, several probe counts incl. nprobe > nlist
+    off, mem = oracle.ivf_lists(oracle.kmeans_assign(base, ivf.centroids, "l2sqr"), 7)
+    q = np.ascontiguousarray(fixtures["test"][:20, :12])
+    for nprobe in (1, 2, 4, 7, 50):
+        got = ivf.knn_with_ef_batch(q, 6, nprobe)
+        want = oracle.ivf_knn(base, ivf.centroids, off, mem, q, 6, nprobe, "l2sqr")
+        assert_knn_parity(base, q, "l2sqr", got, want, oracle)
+    with pytest.raises(ValueError):
+        ivf.knn_with_ef(base[0], 3, 0)
+
+
+def test_ivf_c3_shape_small(V, oracle):
+    """C3 shape scaled down: nlist=128, nprobe sweep 8..24, k=10, 960-d; counts < k when lists are short."""
+    rng = np.random.default_rng(1)
+    proto = rng.random((40, 960), dtype=np.float32)
+    base = (proto[rng.integers(0, 40, 6000)] + 0.05 * rng.standard_normal((6000, 960))).astype(np.float32)
+    q = (proto[rng.integers(0, 40, 12)] + 0.05 * rng.standard_normal((12, 960))).astype(np.float32)
+    cent = np.ascontiguousarray(base[rng.permutation(6000)[:128]])
+    vs = V.DeviceVecSet(base, "l2sqr")
+    ivf = V.IVFIndex(vs, cent)
+    a = oracle.kmeans_assign(base, cent, "l2sqr", nthreads=8)
+    assert (ivf.assignment == a).all()
+    off, mem = oracle.ivf_lists(a, 128)
+    for nprobe in (1, 8, 16, 24):
+        got = ivf.knn_with_ef_batch(q, 10, nprobe)
+        want = oracle.ivf_knn(base, cent, off, mem, q, 10, nprobe, "l2sqr", nthreads=8)
+        assert_knn_parity(base, q, "l2sqr", got, want, oracle)
