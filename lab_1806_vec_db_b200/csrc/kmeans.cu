@@ -40,6 +40,7 @@ struct AssignParams {
     uint32_t k;
     uint32_t c_base, kc;   // this launch handles centroids [c_base, c_base+kc), kc <= cpw
     uint32_t cpw;          // lanes per row (power of two <= 32)
+    uint32_t rps;          // rows per warp step (<= 32 / cpw; fewer when shared memory is tight)
     uint64_t* best;        // [n] running best key (in/out)
     uint32_t* out_assign;  // optional: written when non-null
     float* all_dist;       // optional [n][k]: every exact distance
@@ -49,7 +50,7 @@ struct AssignParams {
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(ASG_THREADS) assign_exact_kernel(const AssignParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t cpw = p.cpw, rps = 32 / cpw;  // rows per warp step
+    const uint32_t cpw = p.cpw, rps = p.rps;
     float* centT = reinterpret_cast<float*>(smem);            // [d][cpw]
     float* cnorm = centT + (size_t)p.d * cpw;                  // [cpw]  ||c|| (cosine)
     float* rowbuf = cnorm + 32;                                // [ASG_WARPS][rps][d]
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(ASG_THREADS) assign_exact_kernel(const AssignP
             myrows[i] = row < p.n ? to_f32(rows[row * p.pitch + p.lo + j]) : 0.f;
         }
         __syncwarp();
-        const float* x = myrows + (size_t)sub * p.d;
+        const float* x = myrows + (size_t)(sub < rps ? sub : 0) * p.d;
         float s = 0.f, svv = 0.f;
         for (uint32_t j = 0; j < p.d; ++j) {
             const float xv = x[j];
@@ -103,14 +104,14 @@ __global__ void __launch_bounds__(ASG_THREADS) assign_exact_kernel(const AssignP
             dist = __fsub_rn(1.0f, __fdiv_rn(s, den));
         }
         const uint64_t row = row0 + sub;
-        const bool valid = row < p.n && ci < p.kc;
+        const bool valid = row < p.n && ci < p.kc && sub < rps;
         if (valid && p.all_dist) p.all_dist[row * p.k + p.c_base + ci] = dist;
         unsigned long long key = valid ? make_key(dist, p.c_base + ci) : KEY_NONE;
         for (uint32_t o = cpw >> 1; o > 0; o >>= 1) {
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
             key = other < key ? other : key;
         }
-        if (ci == 0 && row < p.n) {
+        if (ci == 0 && row < p.n && sub < rps) {
             const uint64_t prev = p.best[row];
             const uint64_t b = key < prev ? key : prev;
             p.best[row] = b;
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(ASG_THREADS) assign_exact_kernel(const AssignP
 }
 
 constexpr size_t ASG_SMEM_MAX = 200 * 1024;
-static size_t assign_smem(uint32_t d, uint32_t cpw) {
-    return ((size_t)d * cpw + 32 + (size_t)ASG_WARPS * (32 / cpw) * d) * 4;
+static size_t assign_smem(uint32_t d, uint32_t cpw, uint32_t rps) {
+    return ((size_t)d * cpw + 32 + (size_t)ASG_WARPS * rps * d) * 4;
 }
 
 // rows: device pointer to the first row (dataset dtype), pitch in elements
@@ -131,15 +132,14 @@ void kmeans_assign_exact(const void* d_rows, uint64_t n, uint64_t pitch, int dty
     VDB_REQUIRE(k > 0, "The number of centroids should be greater than 0.");
     VDB_REQUIRE(d > 0, "empty dimension range");
     if (n == 0) return;
-    // widest centroid chunk (lanes per row) whose transposed centroids + row staging fit in shared memory
-    uint32_t cpw = 0;
+    // lanes = (rows per warp step) x (centroid chunk); pick the combination with the most busy lanes whose
+    // transposed centroid chunk + row staging fit in shared memory (ties -> wider centroid chunk)
+    uint32_t cpw = 0, rps = 0;
     for (uint32_t c = std::min(32u, next_pow2(k)); c >= 1; c >>= 1)
-        if (assign_smem(d, c) <= ASG_SMEM_MAX) {
-            cpw = c;
-            break;
-        }
+        for (uint32_t r = 32 / c; r >= 1; r >>= 1)
+            if (assign_smem(d, c, r) <= ASG_SMEM_MAX && c * r > cpw * rps) cpw = c, rps = r;
     VDB_REQUIRE(cpw > 0, "k-means assignment: dimension range %u too large for shared memory", d);
-    const size_t smem = assign_smem(d, cpw);
+    const size_t smem = assign_smem(d, cpw, rps);
     VDB_CUDA(cudaMemsetAsync(d_best, 0xff, n * 8, st));
     AssignParams p{};
     p.rows = d_rows;
@@ -150,9 +150,9 @@ void kmeans_assign_exact(const void* d_rows, uint64_t n, uint64_t pitch, int dty
     p.cent = d_cent;
     p.k = k;
     p.cpw = cpw;
+    p.rps = rps;
     p.best = d_best;
     p.all_dist = d_all_dist;
-    const uint32_t rps = 32 / cpw;
     const uint64_t steps = ceil_div<uint64_t>(n, rps);
     const int occ = std::max<int>(1, (int)(ASG_SMEM_MAX / std::max<size_t>(smem, 16 * 1024)));
     const uint32_t grid = (uint32_t)std::max<uint64_t>(

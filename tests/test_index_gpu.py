@@ -191,11 +191,24 @@ def test_pq_knn_end_to_end_vs_oracle(V, fixtures, oracle, metric):
         got = idx.knn_pq_batch(test, k, ef, pq)
         want = oracle.flat_knn_pq(base, codes, pq.codebooks, 240, 4, test, k, ef, metric, nthreads=8)
         assert_knn_parity(base, test, metric, got, want, oracle)
-    # statistical property of pq_table.rs:407-411: p90 relative ADC error < 0.2
-    adc = pq.adc_distances(test[:4])
-    exact = np.array([[oracle.distance(q, r, metric) for r in base[:50]] for q in test[:4]])
-    rel = np.abs(adc[:, :50] - exact) / np.maximum(np.abs(exact), 1e-6)
-    assert np.quantile(rel, 0.9) < 0.2
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_pq_table_test_replica(V, fixtures, oracle, metric):
+    """pq_table.rs:374-438: 64 rows x 13 dims, m = ceil(13/3) = 5 (uneven groups), 4 bits, trained on all rows;
+    p90 of |adc - exact| / max(exact, 1) over 20 random pairs < 0.2."""
+    rows = np.ascontiguousarray(fixtures["base"][:64, :13])
+    rng = np.random.default_rng(42)
+    vs = V.DeviceVecSet(rows, metric)
+    pq = V.PQTable.from_vec_set(vs, rows, V.PQConfig(4, 5, metric, None, 20, 1e-6), rng)
+    adc = pq.adc_distances(rows)
+    errs = []
+    for _ in range(20):
+        i0, i1 = int(rng.integers(0, 64)), int(rng.integers(0, 64))
+        expected = oracle.distance(rows[i0], rows[i1], metric)
+        errs.append(abs(adc[i1, i0] - expected) / max(expected, 1.0))
+    errs.sort()
+    assert errs[int(np.ceil(20 * 0.9)) - 1] < 0.2
 
 
 def test_pq_mismatch_errors(V, fixtures):
