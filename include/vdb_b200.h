@@ -163,6 +163,15 @@ int vdb_ivf_knn_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_que
                     uint32_t k, uint32_t n_probes, uint64_t* d_ids, float* d_dist, uint32_t* d_counts,
                     void* stream);
 
+/* ---- tensor-core path internals (tests / tuning) ---------------------------------------------- */
+/* Pruning scores of the tensor-core Flat path: out_keys[q * ns + i] = key(S'(q, row i*row_stride), i) for the
+ * ns = n / row_stride sampled rows, S' = ||x||^2 - 2 q.x - c ||q|| ||x|| evaluated with TF32 tensor cores.
+ * d_queries: device [nq, dim] f32. */
+int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride,
+                              float c, uint64_t* d_out_keys, void* stream);
+/* Queries that failed the tensor path's completeness check and were re-run through the exact scan. */
+uint64_t vdb_flat_gemm_fallbacks(void);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the calling process since load. */
 uint64_t vdb_launch_count(void);

@@ -351,6 +351,16 @@ int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     });
 }
 
+int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
+                              uint64_t* d_out_keys, void* stream) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && d_queries && d_out_keys, "NULL argument");
+        DeviceGuard g(ds->device);
+        vdb::flat_gemm_store(ds, d_queries, nq, row_stride, c, d_out_keys, (cudaStream_t)stream);
+    });
+}
+uint64_t vdb_flat_gemm_fallbacks(void) { return vdb::g_gemm_redo; }
+
 int vdb_prof_enable(int on) {
     vdb::g_prof_on = on != 0;
     return VDB_OK;

@@ -1,8 +1,560 @@
-// flat_gemm.cu — K2 placeholder (tensor-core batched Flat); see DESIGN.md
-#include "dataset.cuh"
+// flat_gemm.cu — K2: batched Flat L2 kNN as a tensor-core contraction + exact FP32 rerank.
+//
+// Replaces FlatIndex::knn (reference src/index_algorithm/flat_index.rs:48-57) for large query batches
+// (the additive batch entry; the reference batches with rayon, examples/bench.rs:414-418).
+//
+// Pipeline (all on the caller's stream):
+//   1. side arrays per dataset: ||x||^2 and ||x|| (fp32), built once and cached on the handle
+//   2. SAMPLE pass  : S' over a strided row sample, per query the j-th smallest S' becomes tau_q
+//   3. FILTER pass  : for every (query, row): S' = ||x||^2 - 2 q.x - c ||q|| ||x||  (a LOWER bound of
+//                     d(q,x) - ||q||^2: c bounds the TF32 rounding of the contraction);
+//                     rows with S' < tau_q are appended to the query's candidate list
+//   4. RERANK       : exact difference-form distances of the candidates (pairs.cu), top-k by (d, id)
+//   5. CHECK        : the candidate set is provably complete iff  d_k - ||q||^2 < tau_q  (every excluded
+//                     row has d - ||q||^2 >= S' >= tau_q); queries that fail (or overflowed their list)
+//                     are re-run through the exact streaming scan (K1) — still on the GPU.
+// Results are therefore identical to the exact scan: the tensor cores only PRUNE.
+//
+// The contraction kernel is hand-written for sm_100a: TMA (cp.async.bulk.tensor, 128B swizzle) feeds a
+// 4-stage shared-memory ring, one elected thread issues tcgen05.mma.kind::tf32 (M=128 queries x N=256 rows,
+// K=8 per instruction) into double-buffered TMEM accumulators, four epilogue warps read them back with
+// tcgen05.ld (thread = query, registers = rows) and apply the per-query threshold in registers.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "index.cuh"
+#include "topk.cuh"
+
 namespace vdb {
-bool flat_gemm_supported(const vdb_dataset*, uint32_t, uint32_t) { return false; }
-void flat_gemm_keys(const vdb_dataset*, const void*, uint32_t, uint32_t, uint64_t*, cudaStream_t) {
-    fail(VDB_EUNSUPPORTED, "tensor-core Flat path not built");
+
+// ---- tile configuration ---------------------------------------------------------------------------------
+constexpr int GM = 128;              // queries per tile (TMEM lanes)
+constexpr int GN = 256;              // database rows per tile (TMEM columns per accumulator)
+constexpr int GK = 32;               // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int G_STAGES = 4;
+constexpr int G_A_BYTES = GM * GK * 4;   // 16 KB
+constexpr int G_B_BYTES = GN * GK * 4;   // 32 KB
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_THREADS = 192;       // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int G_TMEM_COLS = 512;     // 2 accumulators x 256 columns
+constexpr uint32_t G_SMEM = 1024 /*align*/ + G_STAGES * G_STAGE_BYTES + 2 * 2 * GN * 4 /*norm tiles*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded wait: a protocol bug must trap (a reportable error), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (global_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO=1 (<<16) | SBO=1024B>>4 (<<32) | version=1 (<<46) | layout SWIZZLE_128B=2 (<<61)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
+constexpr uint32_t G_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+
+// ---- kernel ----------------------------------------------------------------------------------------------------
+struct GemmParams {
+    uint32_t nq;            // queries
+    uint64_t nrows;         // rows addressed by the B tensor map (sample rows or all rows)
+    uint32_t row_stride;    // database row of B row i is i * row_stride
+    uint32_t kblocks;       // ceil(dim / 32)
+    uint32_t ntiles;        // ceil(nrows / GN)
+    uint32_t nqt;           // ceil(nq / GM)
+    uint32_t tiles_per_slab;
+    uint32_t nslabs;
+    const float* sqnorm;    // [n] ||x||^2
+    const float* rnorm;     // [n] ||x||
+    const float* qcm;       // [nq] c * ||q||   (error-bound coefficient times the query norm)
+    // mode 0: store keys (S', sample index) to out_keys[nq][nrows]
+    uint64_t* out_keys;
+    // mode 1: filter
+    const float* tau;       // [nq]
+    uint32_t* cand_cnt;     // [nq]
+    uint64_t* cand;         // [nq][cap]  (S' bits << 32 | local row)
+    uint32_t cap;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(G_THREADS, 1)
+flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    float* norm_tiles = reinterpret_cast<float*>(smem + G_STAGES * G_STAGE_BYTES);  // [2 acc][2 arrays][GN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(norm_tiles + 2 * 2 * GN);
+    uint64_t* full_bar = bars;                 // [G_STAGES]
+    uint64_t* empty_bar = bars + G_STAGES;     // [G_STAGES]
+    uint64_t* tfull_bar = bars + 2 * G_STAGES; // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, G_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t items = p.nqt * p.nslabs;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const uint32_t slab = item / p.nqt, qt = item - slab * p.nqt;
+                const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], G_STAGE_BYTES);
+                        const uint32_t sa = smem_u32(stage_base + stage * G_STAGE_BYTES);
+                        tma_load_2d(sa, &map_q, (int)(kb * GK), (int)(qt * GM), &full_bar[stage]);
+                        tma_load_2d(sa + G_A_BYTES, &map_x, (int)(kb * GK), (int)(t * GN), &full_bar[stage]);
+                        if (++stage == G_STAGES) stage = 0, phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer (one elected thread) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const uint32_t slab = item / p.nqt;
+                const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * GN;
+                    for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * G_STAGE_BYTES);
+                        const uint64_t da = umma_desc(sa), db = umma_desc(sa + G_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GK / 8; ++k)  // advance 32 bytes (2 x 16B units) per K=8 step
+                            umma_tf32(d_tmem, da + 2 * k, db + 2 * k, G_IDESC, (kb | k) != 0);
+                        umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                        if (++stage == G_STAGES) stage = 0, phase ^= 1;
+                    }
+                    umma_commit(&tfull_bar[acc]);        // accumulator ready for the epilogue
+                    if (++acc == 2) acc = 0, acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 0-3, thread = query (TMEM lane), registers = database rows =====
+        uint32_t acc = 0, acc_phase = 0;
+        const uint32_t lane_base = (uint32_t)warp * 32;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const uint32_t slab = item / p.nqt, qt = item - slab * p.nqt;
+            const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
+            const uint32_t q = qt * GM + threadIdx.x;
+            const bool qok = q < p.nq;
+            const float cq = qok ? p.qcm[q] : 0.f;
+            float tau = 0.f;
+            if (MODE == 1) tau = qok ? p.tau[q] : __uint_as_float(0xff800000u);  // -inf: nothing passes
+            for (uint32_t t = t0; t < t1; ++t) {
+                // stage the row-norm tiles of this N-tile (2 x GN floats) while the MMAs run
+                float* sq = norm_tiles + acc * 2 * GN;
+                float* rn = sq + GN;
+                for (uint32_t c = threadIdx.x; c < GN; c += 128) {
+                    const uint64_t brow = (uint64_t)t * GN + c;
+                    const bool ok = brow < p.nrows;
+                    const uint64_t row = brow * p.row_stride;
+                    sq[c] = ok ? p.sqnorm[row] : __uint_as_float(0x7f800000u);  // +inf: never a candidate
+                    rn[c] = ok ? p.rnorm[row] : 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (lane_base << 16) + acc * GN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < GN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (qok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float dot = __uint_as_float(v[j]);
+                            // S' = ||x||^2 - c||q|| ||x|| - 2 q.x
+                            const float s = fmaf(-2.0f, dot, fmaf(-cq, rn[c0 + j], sq[c0 + j]));
+                            if (MODE == 0) {
+                                const uint64_t brow = (uint64_t)t * GN + c0 + j;
+                                if (brow < p.nrows) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(s, (uint32_t)brow);
+                            } else if (s < tau) {
+                                const uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
+                                if (pos < p.cap)
+                                    p.cand[(uint64_t)q * p.cap + pos] =
+                                        ((uint64_t)__float_as_uint(s) << 32) | (uint32_t)((uint64_t)t * GN + c0 + j);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) acc = 0, acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, G_TMEM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    if (!fn) fail(VDB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    return fn;
+}
+
+// 2-D fp32 tensor map over rows of `pitch_bytes`: dims {dim, nrows}, box {32, box_rows}, 128B swizzle, zero OOB fill
+static CUtensorMap make_map(const void* base, uint32_t dim, uint64_t nrows, uint64_t pitch_bytes, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {dim, nrows};
+    cuuint64_t gstride[1] = {pitch_bytes};
+    cuuint32_t box[2] = {GK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(VDB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return m;
+}
+
+static std::mutex g_side_mu;
+// ||x||^2 and ||x|| per row, cached on the (logically const) dataset handle
+static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
+    vdb_dataset* ds = const_cast<vdb_dataset*>(cds);
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    if (ds->d_sqnorm && ds->side_n == ds->n) return;
+    if (ds->d_sqnorm) cudaFree(ds->d_sqnorm);
+    if (ds->d_lo) cudaFree(ds->d_lo);
+    ds->d_sqnorm = ds->d_lo = nullptr;
+    VDB_CUDA(cudaMalloc(&ds->d_sqnorm, ds->n * 4));
+    VDB_CUDA(cudaMalloc(&ds->d_lo, ds->n * 4));  // d_lo holds ||x|| for this path
+    vdb_dataset tmp = *ds;
+    tmp.metric = VDB_L2SQR;
+    row_cache(&tmp, ds->d_sqnorm, st);
+    tmp.metric = VDB_COSINE;
+    row_cache(&tmp, ds->d_lo, st);
+    VDB_CUDA(cudaStreamSynchronize(st));
+    ds->side_n = ds->n;
+}
+
+static void launch_gemm(int mode, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st) {
+    static thread_local bool configured = false;
+    if (!configured) {
+        VDB_CUDA(cudaFuncSetAttribute(flat_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+        VDB_CUDA(cudaFuncSetAttribute(flat_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+        configured = true;
+    }
+    const uint32_t sms = (uint32_t)sm_count();
+    p.ntiles = (uint32_t)ceil_div<uint64_t>(p.nrows, GN);
+    p.nqt = ceil_div<uint32_t>(p.nq, GM);
+    // slabs of ~16 row tiles; query tile fastest so concurrently running CTAs share the same slab in L2
+    p.tiles_per_slab = std::max(1u, std::min(16u, ceil_div(p.ntiles * p.nqt, sms)));
+    p.nslabs = ceil_div(p.ntiles, p.tiles_per_slab);
+    const uint32_t grid = std::min(sms, p.nqt * p.nslabs);
+    ProfScope prof("flat_gemm", st);
+    if (mode == 0) flat_gemm_kernel<0><<<grid, G_THREADS, G_SMEM, st>>>(mq, mx, p);
+    else flat_gemm_kernel<1><<<grid, G_THREADS, G_SMEM, st>>>(mq, mx, p);
+    VDB_LAUNCHED();
+}
+
+// c * ||q|| per query; c bounds |S'_tf32 - S'_exact| / (||q|| ||x||): two TF32 operand roundings (2^-10 each,
+// truncation) + their product + K fp32 accumulation steps (K * 2^-23), times 2 for the -2 q.x term.
+__global__ void qcm_kernel(const float* __restrict__ qsq, uint32_t nq, float c, float* __restrict__ qcm) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) qcm[q] = c * sqrtf(qsq[q]);
+}
+__global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, float* __restrict__ tau) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) tau[q] = key_dist(keys[(size_t)q * j + (j - 1)]);
+}
+// candidate (S', local row) lists -> rerank inputs
+__global__ void cand_to_pairs_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t nq,
+                                     uint32_t cap, uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid,
+                                     uint8_t* __restrict__ valid) {
+    const uint64_t total = (uint64_t)nq * cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t q = (uint32_t)(i / cap), j = (uint32_t)(i - (uint64_t)q * cap);
+        const bool ok = j < min(cnt[q], cap);
+        qidx[i] = q;
+        rid[i] = ok ? (uint32_t)cand[i] : 0u;
+        valid[i] = ok;
+    }
+}
+// completeness check; failing queries are appended to redo[]
+__global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, uint64_t n,
+                             const uint32_t* __restrict__ cnt, uint32_t cap, const float* __restrict__ tau,
+                             const float* __restrict__ qsq, uint32_t* __restrict__ redo, uint32_t* __restrict__ nredo) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t need = (uint32_t)((uint64_t)k < n ? (uint64_t)k : n);
+    bool ok = cnt[q] <= cap && cnt[q] >= need;
+    if (ok) {
+        const float dk = key_dist(keys[(size_t)q * k + (need - 1)]);
+        const float slack = 2e-5f * (fabsf(dk) + qsq[q] + fabsf(tau[q]));
+        ok = (dk - qsq[q]) < tau[q] - slack;
+    }
+    if (!ok) redo[atomicAdd(nredo, 1u)] = q;
+}
+__global__ void gather_rows_kernel(const float* __restrict__ src, uint32_t dim, const uint32_t* __restrict__ idx,
+                                   uint32_t cnt, float* __restrict__ dst) {
+    const uint32_t i = blockIdx.x;
+    if (i >= cnt) return;
+    for (uint32_t e = threadIdx.x; e < dim; e += blockDim.x) dst[(size_t)i * dim + e] = src[(size_t)idx[i] * dim + e];
+}
+__global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, uint32_t k, const uint32_t* __restrict__ idx,
+                                    uint32_t cnt, uint64_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x;
+    if (i >= cnt) return;
+    for (uint32_t e = threadIdx.x; e < k; e += blockDim.x) dst[(size_t)idx[i] * k + e] = src[(size_t)i * k + e];
+}
+
+constexpr uint32_t G_SAMPLE = 8192;   // sampled rows for the thresholds
+constexpr uint32_t G_MAX_K = 1024;
+
+bool flat_gemm_supported(const vdb_dataset* ds, uint32_t nq, uint32_t k) {
+    return ds->dtype == VDB_F32 && ds->metric == VDB_L2SQR && k >= 1 && k <= G_MAX_K && ds->n >= 16ull * G_SAMPLE &&
+           nq >= 1 && ((uintptr_t)ds->d_rows & 15) == 0;
+}
+
+uint64_t g_gemm_redo = 0;  // queries that needed the exact fallback (instrumentation)
+
+void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                    cudaStream_t st) {
+    VDB_REQUIRE(flat_gemm_supported(ds, nq, k), "tensor-core Flat path: unsupported dataset/k");
+    ensure_side_arrays(ds, st);
+    const float* sqnorm = ds->d_sqnorm;
+    const float* rnorm = ds->d_lo;
+    const uint32_t dim = ds->dim;
+    const float c = 2.0f * (ldexpf(1.0f, -9) + (float)dim * ldexpf(1.0f, -23));
+
+    // queries: contiguous [nq][dim] f32 (TMA needs a 16-byte aligned base and row pitch)
+    DevBuf qcopy;
+    const float* dq = (const float*)d_queries;
+    const uint32_t qpitch = round_up(dim, 4u);
+    if (dim % 4 != 0 || ((uintptr_t)d_queries & 15)) {
+        qcopy = DevBuf((size_t)nq * qpitch * 4, st);
+        VDB_CUDA(cudaMemsetAsync(qcopy.p, 0, (size_t)nq * qpitch * 4, st));
+        VDB_CUDA(cudaMemcpy2DAsync(qcopy.p, (size_t)qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
+                                   cudaMemcpyDeviceToDevice, st));
+        dq = qcopy.as<float>();
+    }
+    DevBuf qsq((size_t)nq * 4, st), qcm((size_t)nq * 4, st), tau((size_t)nq * 4, st);
+    {
+        vdb_dataset qd = *ds;
+        qd.d_rows = const_cast<float*>(dq);
+        qd.n = nq;
+        qd.pitch = qpitch;
+        qd.metric = VDB_L2SQR;
+        row_cache(&qd, qsq.as<float>(), st);
+        qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(qsq.as<float>(), nq, c, qcm.as<float>());
+        VDB_LAUNCHED();
+    }
+    const CUtensorMap mq = make_map(dq, dim, nq, (uint64_t)qpitch * 4, GM);
+
+    // ---- thresholds from a strided sample ----
+    const uint32_t stride = (uint32_t)(ds->n / G_SAMPLE);
+    const uint64_t ns = ds->n / stride;
+    // expected candidates per query = j * n / ns; aim at max(8k, 768) so the k-th exact distance sits well
+    // inside the threshold
+    const uint32_t want = std::max(8 * k, 768u);
+    const uint32_t j = (uint32_t)std::min<uint64_t>(ns, std::max<uint64_t>(6, ceil_div<uint64_t>((uint64_t)want * ns, ds->n)));
+    const uint32_t cap = (uint32_t)next_pow2((uint32_t)std::min<uint64_t>(ds->n, 4ull * j * stride + 1024));
+    GemmParams p{};
+    p.nq = nq;
+    p.kblocks = ceil_div(dim, (uint32_t)GK);
+    p.sqnorm = sqnorm;
+    p.rnorm = rnorm;
+    p.qcm = qcm.as<float>();
+    {
+        DevBuf skeys((size_t)nq * ns * 8, st), jkeys((size_t)nq * j * 8, st);
+        const CUtensorMap ms = make_map(ds->d_rows, dim, ns, ds->pitch_bytes() * stride, GN);
+        GemmParams ps = p;
+        ps.nrows = ns;
+        ps.row_stride = stride;
+        ps.out_keys = skeys.as<uint64_t>();
+        launch_gemm(0, mq, ms, ps, st);
+        launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j, jkeys.as<uint64_t>(), nullptr, nullptr,
+                          nullptr, st);
+        tau_from_keys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j, tau.as<float>());
+        VDB_LAUNCHED();
+    }
+    // ---- filter pass over the whole shard ----
+    DevBuf cnt((size_t)nq * 4, st), cand((size_t)nq * cap * 8, st);
+    VDB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * 4, st));
+    {
+        const CUtensorMap mx = make_map(ds->d_rows, dim, ds->n, ds->pitch_bytes(), GN);
+        GemmParams pf = p;
+        pf.nrows = ds->n;
+        pf.row_stride = 1;
+        pf.tau = tau.as<float>();
+        pf.cand_cnt = cnt.as<uint32_t>();
+        pf.cand = cand.as<uint64_t>();
+        pf.cap = cap;
+        launch_gemm(1, mq, mx, pf, st);
+    }
+    // ---- exact rerank of the candidates ----
+    const uint64_t total = (uint64_t)nq * cap;
+    {
+        DevBuf qidx(total * 4, st), rid(total * 4, st), valid(total, st), dist(total * 4, st), keys2(total * 8, st);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(total, 256), 8192);
+        cand_to_pairs_kernel<<<grid, 256, 0, st>>>(cand.as<uint64_t>(), cnt.as<uint32_t>(), nq, cap, qidx.as<uint32_t>(),
+                                                   rid.as<uint32_t>(), valid.as<uint8_t>());
+        VDB_LAUNCHED();
+        exact_pair_distances_masked(ds, dq, qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), valid.as<uint8_t>(), total,
+                                    dist.as<float>(), st);
+        rekey_based(dist.as<float>(), rid.as<uint32_t>(), (uint32_t)ds->id_base, valid.as<uint8_t>(), total,
+                    keys2.as<uint64_t>(), st);
+        launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st);
+    }
+    // ---- completeness check + exact fallback ----
+    DevBuf redo((size_t)nq * 4, st), nredo(4, st);
+    VDB_CUDA(cudaMemsetAsync(nredo.p, 0, 4, st));
+    check_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(d_keys, nq, k, ds->n, cnt.as<uint32_t>(), cap, tau.as<float>(),
+                                                     qsq.as<float>(), redo.as<uint32_t>(), nredo.as<uint32_t>());
+    VDB_LAUNCHED();
+    uint32_t h_redo = 0;
+    VDB_CUDA(cudaMemcpyAsync(&h_redo, nredo.p, 4, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaStreamSynchronize(st));
+    g_gemm_redo += h_redo;
+    if (h_redo) {
+        DevBuf rq((size_t)h_redo * dim * 4, st), rkeys((size_t)h_redo * k * 8, st);
+        gather_rows_kernel<<<h_redo, 128, 0, st>>>((const float*)d_queries, dim, redo.as<uint32_t>(), h_redo, rq.as<float>());
+        VDB_LAUNCHED();
+        flat_scan_keys(ds, rq.p, h_redo, k, rkeys.as<uint64_t>(), st);
+        scatter_keys_kernel<<<h_redo, 128, 0, st>>>(rkeys.as<uint64_t>(), k, redo.as<uint32_t>(), h_redo, d_keys);
+        VDB_LAUNCHED();
+    }
+}
+
+// debug / test entry: S' keys of every (query, sampled row) pair, [nq][nrows] (mode 0 of the kernel)
+void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
+                     uint64_t* d_out_keys, cudaStream_t st) {
+    VDB_REQUIRE(ds->dtype == VDB_F32 && ds->dim % 4 == 0 && ((uintptr_t)d_queries & 15) == 0 && row_stride >= 1,
+                "flat_gemm_store: f32 rows, dim %% 4 == 0 and aligned queries only");
+    ensure_side_arrays(ds, st);
+    const uint64_t ns = ds->n / row_stride;
+    DevBuf qsq((size_t)nq * 4, st), qcm((size_t)nq * 4, st);
+    vdb_dataset qd = *ds;
+    qd.d_rows = const_cast<void*>(d_queries);
+    qd.n = nq;
+    qd.pitch = ds->dim;
+    qd.metric = VDB_L2SQR;
+    row_cache(&qd, qsq.as<float>(), st);
+    qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(qsq.as<float>(), nq, c, qcm.as<float>());
+    VDB_LAUNCHED();
+    GemmParams p{};
+    p.nq = nq;
+    p.kblocks = ceil_div(ds->dim, (uint32_t)GK);
+    p.sqnorm = ds->d_sqnorm;
+    p.rnorm = ds->d_lo;
+    p.qcm = qcm.as<float>();
+    p.nrows = ns;
+    p.row_stride = row_stride;
+    p.out_keys = d_out_keys;
+    const CUtensorMap mq = make_map(d_queries, ds->dim, nq, (uint64_t)ds->dim * 4, GM);
+    const CUtensorMap ms = make_map(ds->d_rows, ds->dim, ns, ds->pitch_bytes() * row_stride, GN);
+    launch_gemm(0, mq, ms, p, st);
+}
+
 }  // namespace vdb

@@ -50,6 +50,9 @@ void kmeans_pp_weights(const void* d_rows, uint64_t n, uint64_t pitch, int dtype
 void row_cache(const vdb_dataset* ds, float* d_out, cudaStream_t st);
 void exact_pair_distances(const vdb_dataset* ds, const void* d_queries, const uint32_t* d_qidx,
                           const uint32_t* d_rid, uint64_t npairs, float* d_out, cudaStream_t st);
+void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, uint32_t qpitch, const uint32_t* d_qidx,
+                                 const uint32_t* d_rid, const uint8_t* d_valid, uint64_t npairs, float* d_out,
+                                 cudaStream_t st);
 void cached_pair_distances(const vdb_dataset* ds, const void* d_queries, const float* d_qcache,
                            const float* d_rowcache, const uint32_t* d_qidx, const uint32_t* d_rid,
                            uint64_t npairs, float* d_out, cudaStream_t st);
@@ -80,5 +83,13 @@ void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queri
 // rebuilds (distance, id) keys: key[j] = valid[j] ? make_key(dist[j], id[j]) : KEY_NONE
 void rekey(const float* d_dist, const uint32_t* d_ids, const uint8_t* d_valid, uint64_t count, uint64_t* d_keys,
            cudaStream_t st);
+
+void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, const uint8_t* d_valid, uint64_t count,
+                 uint64_t* d_keys, cudaStream_t st);
+
+// flat_gemm.cu
+void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
+                     uint64_t* d_out_keys, cudaStream_t st);
+extern uint64_t g_gemm_redo;
 
 }  // namespace vdb

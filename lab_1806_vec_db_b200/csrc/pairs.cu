@@ -20,6 +20,7 @@ struct PairParams {
     const uint32_t* idxB;
     const float* cacheA;     // per A-row cache (cached modes), indexed like A rows
     const float* cacheB;
+    const uint8_t* valid;    // optional per-pair mask (invalid pairs are skipped, out = 0)
     uint32_t dim;
     uint64_t npairs;
     float* out;
@@ -31,6 +32,10 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t j = warp; j < p.npairs; j += nwarps) {
+        if (p.valid && !p.valid[j]) {
+            if (lane == 0) p.out[j] = 0.f;
+            continue;
+        }
         const uint64_t ia = p.idxA ? p.idxA[j] : j;
         const uint64_t ib = p.idxB ? p.idxB[j] : j;
         const TA* a = (const TA*)p.A + ia * p.strideA;
@@ -121,6 +126,24 @@ void exact_pair_distances(const vdb_dataset* ds, const void* d_queries, const ui
     p.B = ds->d_rows;
     p.strideB = ds->pitch;
     p.idxB = d_rid;
+    p.dim = ds->dim;
+    p.npairs = npairs;
+    p.out = d_out;
+    launch_pairs(ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE, false, ds->dtype, p, st);
+}
+
+// same with an explicit query pitch and a validity mask (K2 rerank)
+void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, uint32_t qpitch, const uint32_t* d_qidx,
+                                 const uint32_t* d_rid, const uint8_t* d_valid, uint64_t npairs, float* d_out,
+                                 cudaStream_t st) {
+    PairParams p{};
+    p.A = d_queries;
+    p.strideA = qpitch;
+    p.idxA = d_qidx;
+    p.B = ds->d_rows;
+    p.strideB = ds->pitch;
+    p.idxB = d_rid;
+    p.valid = d_valid;
     p.dim = ds->dim;
     p.npairs = npairs;
     p.out = d_out;

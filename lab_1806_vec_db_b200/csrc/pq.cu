@@ -511,6 +511,14 @@ void rekey(const float* d_dist, const uint32_t* d_ids, const uint8_t* d_valid, u
     VDB_LAUNCHED();
 }
 
+void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, const uint8_t* d_valid, uint64_t count,
+                 uint64_t* d_keys, cudaStream_t st) {
+    if (count == 0) return;
+    rekey_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), 8192), 256, 0, st>>>(
+        d_dist, d_ids, id_base, d_valid, count, d_keys);
+    VDB_LAUNCHED();
+}
+
 // exact rerank of [nq][kk] candidate keys -> [nq][k] keys ordered by (exact distance, id)
 void rerank_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, const uint64_t* d_cand, uint32_t kk,
                  uint32_t k, uint64_t* d_keys, cudaStream_t st) {

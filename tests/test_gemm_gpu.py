@@ -1,0 +1,104 @@
+"""Tensor-core Flat path (K2): contraction scores vs numpy, then end-to-end identity with the exact scan."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_knn_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _scores(V, base, q, stride, c):
+    import torch
+    from lab_1806_vec_db_b200 import _lib as L
+    from lab_1806_vec_db_b200.sharded import unpack_keys
+    vs = V.DeviceVecSet(base, "l2sqr")
+    dq = torch.from_numpy(q).cuda()
+    ns = base.shape[0] // stride
+    out = torch.empty((q.shape[0], ns), dtype=torch.int64, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(L.lib().vdb_debug_gemm_scores_dev(vs._h, C.c_void_p(dq.data_ptr()), q.shape[0], stride, c,
+                                              C.c_void_p(out.data_ptr()), st))
+    torch.cuda.synchronize()
+    s, idx = unpack_keys(out.cpu().numpy().astype(np.uint64))
+    return s, idx
+
+
+@pytest.mark.parametrize("n,dim,nq,stride", [(1024, 960, 128, 1), (5000, 960, 300, 1), (5000, 960, 130, 3),
+                                             (777, 100, 5, 1), (4096, 32, 256, 2), (3000, 2052, 64, 1)])
+def test_contraction_scores_match_numpy(n, dim, nq, stride):
+    import lab_1806_vec_db_b200 as V
+    rng = np.random.default_rng(n + dim)
+    base = rng.random((n, dim), dtype=np.float32)
+    q = rng.random((nq, dim), dtype=np.float32)
+    for c in (0.0, 4.1e-3):
+        s, idx = _scores(V, base, q, stride, c)
+        rows = base[::stride][: n // stride].astype(np.float64)
+        qq = q.astype(np.float64)
+        xn2 = (rows * rows).sum(1)
+        want = xn2[None, :] - 2.0 * qq @ rows.T - c * np.sqrt((qq * qq).sum(1))[:, None] * np.sqrt(xn2)[None, :]
+        assert (idx == np.arange(n // stride)[None, :]).all()
+        # TF32 operand rounding: |error| <= 2 * 2^-9 * ||q|| ||x|| (+ fp32 accumulation)
+        bound = 4.2e-3 * np.sqrt((qq * qq).sum(1))[:, None] * np.sqrt(xn2)[None, :] + 1e-4
+        err = np.abs(s.astype(np.float64) - want)
+        assert (err <= bound).all(), float((err / bound).max())
+        # and the scores are genuinely tensor-core results, not the exact fp32 values
+        assert err.max() > 0
+
+
+def _synthetic(n, nq, seed=0):
+    rng = np.random.default_rng(seed)
+    proto = rng.random((256, 960), dtype=np.float32) * 0.15
+    base = (proto[rng.integers(0, 256, n)] + 0.02 * rng.standard_normal((n, 960), dtype=np.float32)).clip(0, 1)
+    q = (proto[rng.integers(0, 256, nq)] + 0.02 * rng.standard_normal((nq, 960), dtype=np.float32)).clip(0, 1)
+    return np.ascontiguousarray(base, np.float32), np.ascontiguousarray(q, np.float32)
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_tensor_path_identical_to_exact_scan(oracle, k):
+    """The tensor cores only prune: ids and distances must equal the exact scan's (and the oracle's)."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    n, nq = 140_000, 300
+    base, q = _synthetic(n, nq)
+    idx = V.FlatIndex.from_vec_set(base, "l2sqr")
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, k)
+        L.check(lib.vdb_flat_set_path(2))
+        fb0 = lib.vdb_flat_gemm_fallbacks()
+        tens = idx.knn_batch(q, k)
+        fallbacks = lib.vdb_flat_gemm_fallbacks() - fb0
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (tens[2] == scan[2]).all()
+    assert (tens[0] == scan[0]).all(), float((tens[0] == scan[0]).mean())
+    assert (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    want = oracle.flat_knn(base, q[:16], k, "l2sqr", 8)
+    assert_knn_parity(base, q[:16], "l2sqr", tuple(a[:16] for a in tens), want, oracle)
+    assert fallbacks < nq // 2, f"{fallbacks} of {nq} queries fell back to the exact scan"
+
+
+def test_tensor_path_adversarial_ties_and_duplicates(oracle):
+    """Exact duplicates and a uniform cloud (no neighbourhood structure): still identical to the scan."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(7)
+    n, nq, k = 131_072 + 77, 140, 20
+    base = rng.random((n, 960), dtype=np.float32)
+    base[1000:1040] = base[5]          # 40 exact copies
+    q = rng.random((nq, 960), dtype=np.float32)
+    q[0] = base[5]
+    idx = V.FlatIndex.from_vec_set(base, "l2sqr")
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, k)
+        L.check(lib.vdb_flat_set_path(2))
+        tens = idx.knn_batch(q, k)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    assert tens[0][0, :3].tolist() == [5, 1000, 1001]
