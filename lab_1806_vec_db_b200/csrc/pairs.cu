@@ -9,7 +9,7 @@
 
 namespace vdb {
 
-enum PairMode { PM_L2 = 0, PM_COSINE = 1, PM_DOT = 2, PM_L2_CACHED = 3, PM_COSINE_CACHED = 4, PM_SQNORM = 5, PM_NORM = 6 };
+enum PairMode { PM_L2 = 0, PM_COSINE = 1, PM_DOT = 2, PM_L2_CACHED = 3, PM_COSINE_CACHED = 4, PM_SQNORM = 5, PM_NORM = 6, PM_L2_SCANORDER = 7 };
 
 struct PairParams {
     const void* A;           // rows of A
@@ -41,6 +41,20 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
         const TA* a = (const TA*)p.A + ia * p.strideA;
         const TB* b = (const TB*)p.B + ib * p.strideB;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        if (MODE == PM_L2_SCANORDER) {
+            // same per-lane element order (float4 chunk c = it*32 + lane) and the same xor-butterfly as the
+            // streaming scan kernel (flat_scan.cu), so both Flat paths return bit-identical distances
+            for (uint32_t c = lane; c * 4 < p.dim; c += 32) {
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i) {
+                    const uint32_t e = c * 4 + i;
+                    if (e < p.dim) {
+                        const float d = (float)b[e] - (float)a[e];
+                        s0 = fmaf(d, d, s0);
+                    }
+                }
+            }
+        } else
         for (uint32_t e = lane; e < p.dim; e += 32) {
             const float x = (float)a[e];
             const float y = (MODE == PM_SQNORM || MODE == PM_NORM) ? x : (float)b[e];
@@ -85,6 +99,7 @@ static void launch_pairs_t(int mode, const PairParams& p, cudaStream_t st) {
         case PM_L2_CACHED: pair_dist_kernel<TA, TB, PM_L2_CACHED><<<grid, 256, 0, st>>>(p); break;
         case PM_COSINE_CACHED: pair_dist_kernel<TA, TB, PM_COSINE_CACHED><<<grid, 256, 0, st>>>(p); break;
         case PM_SQNORM: pair_dist_kernel<TA, TB, PM_SQNORM><<<grid, 256, 0, st>>>(p); break;
+        case PM_L2_SCANORDER: pair_dist_kernel<TA, TB, PM_L2_SCANORDER><<<grid, 256, 0, st>>>(p); break;
         default: pair_dist_kernel<TA, TB, PM_NORM><<<grid, 256, 0, st>>>(p); break;
     }
     VDB_LAUNCHED();
@@ -147,7 +162,8 @@ void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, u
     p.dim = ds->dim;
     p.npairs = npairs;
     p.out = d_out;
-    launch_pairs(ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE, false, ds->dtype, p, st);
+    const bool scan_order = ds->metric == VDB_L2SQR && ds->dtype == VDB_F32;
+    launch_pairs(scan_order ? PM_L2_SCANORDER : (ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE), false, ds->dtype, p, st);
 }
 
 void cached_pair_distances(const vdb_dataset* ds, const void* d_queries, const float* d_qcache,

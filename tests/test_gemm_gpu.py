@@ -75,7 +75,7 @@ def test_tensor_path_identical_to_exact_scan(oracle, k):
         L.check(lib.vdb_flat_set_path(0))
     assert (tens[2] == scan[2]).all()
     assert (tens[0] == scan[0]).all(), float((tens[0] == scan[0]).mean())
-    assert (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    assert (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()  # rerank uses the scan's summation order
     want = oracle.flat_knn(base, q[:16], k, "l2sqr", 8)
     assert_knn_parity(base, q[:16], "l2sqr", tuple(a[:16] for a in tens), want, oracle)
     assert fallbacks < nq // 2, f"{fallbacks} of {nq} queries fell back to the exact scan"
