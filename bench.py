@@ -133,6 +133,14 @@ def cpu_arm(base_host, q_host, k, cores, steps, warmup, gpu_check=None):
     return len(q_host) / dt, dt, res
 
 
+def tensor_stats(lib):
+    q, c, f = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    lib.vdb_flat_gemm_stats(C.byref(q), C.byref(c), C.byref(f))
+    if q.value == 0:
+        return None
+    return {"queries": q.value, "candidates_per_query": c.value / q.value, "exact_fallback_queries": f.value}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port) on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -322,6 +330,7 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "kernel_ms": {k_: {"ms": v[0], "launches": v[1]} for k_, v in prof.items()},
+        "tensor_path": tensor_stats(lib),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -171,6 +171,8 @@ int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint
                               float c, uint64_t* d_out_keys, void* stream);
 /* Queries that failed the tensor path's completeness check and were re-run through the exact scan. */
 uint64_t vdb_flat_gemm_fallbacks(void);
+/* Cumulative counters of the tensor path: queries served, candidates reranked, queries re-run exactly. */
+int vdb_flat_gemm_stats(uint64_t* queries, uint64_t* candidates, uint64_t* fallbacks);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the calling process since load. */

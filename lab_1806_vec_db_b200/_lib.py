@@ -65,6 +65,7 @@ SIGNATURES = {
     "vdb_ivf_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     "vdb_debug_gemm_scores_dev": (i32, [vp, vp, u32, u32, f32, vp, vp]),
     "vdb_flat_gemm_fallbacks": (u64, []),
+    "vdb_flat_gemm_stats": (i32, [vp, vp, vp]),
     "vdb_launch_count": (u64, []),
     "vdb_prof_enable": (i32, [i32]),
     "vdb_prof_reset": (i32, []),

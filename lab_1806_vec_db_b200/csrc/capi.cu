@@ -360,6 +360,12 @@ int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint
     });
 }
 uint64_t vdb_flat_gemm_fallbacks(void) { return vdb::g_gemm_redo; }
+int vdb_flat_gemm_stats(uint64_t* queries, uint64_t* candidates, uint64_t* fallbacks) {
+    if (queries) *queries = vdb::g_gemm_queries;
+    if (candidates) *candidates = vdb::g_gemm_cands;
+    if (fallbacks) *fallbacks = vdb::g_gemm_redo;
+    return VDB_OK;
+}
 
 int vdb_prof_enable(int on) {
     vdb::g_prof_on = on != 0;

@@ -16,6 +16,7 @@ struct vdb_dataset {
     float* d_lo = nullptr;    // tf32 residual x - tf32(x), [n][pitch]
     float* d_sqnorm = nullptr;  // ||x||^2 (fp32), [n]
     uint64_t side_n = 0;      // number of rows the side arrays cover
+    float mean_norm = 0.f;    // mean ||x|| over a row sample (threshold margin of the tensor path)
     uint32_t elem_size() const { return dtype == VDB_F32 ? 4u : 1u; }
     size_t pitch_bytes() const { return (size_t)pitch * elem_size(); }
 };

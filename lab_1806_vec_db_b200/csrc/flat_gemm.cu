@@ -318,6 +318,26 @@ static CUtensorMap make_map(const void* base, uint32_t dim, uint64_t nrows, uint
     return m;
 }
 
+__global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v, uint64_t n, uint64_t stride, float* out) {
+    __shared__ float red[32];
+    float s = 0.f;
+    uint32_t cnt = 0;
+    for (uint64_t i = (uint64_t)threadIdx.x * stride; i < n; i += (uint64_t)blockDim.x * stride) s += v[i], ++cnt;
+    __shared__ uint32_t total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    atomicAdd(&total, cnt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 32; ++w) t += red[w];
+        *out = t / (float)max(total, 1u);
+    }
+}
+
 static std::mutex g_side_mu;
 // ||x||^2 and ||x|| per row, cached on the (logically const) dataset handle
 static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
@@ -334,7 +354,13 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
     row_cache(&tmp, ds->d_sqnorm, st);
     tmp.metric = VDB_COSINE;
     row_cache(&tmp, ds->d_lo, st);
-    VDB_CUDA(cudaStreamSynchronize(st));
+    {
+        DevBuf m(4, st);
+        mean_kernel<<<1, 1024, 0, st>>>(ds->d_lo, ds->n, std::max<uint64_t>(1, ds->n / 65536), m.as<float>());
+        VDB_LAUNCHED();
+        VDB_CUDA(cudaMemcpyAsync(&ds->mean_norm, m.p, 4, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaStreamSynchronize(st));
+    }
     ds->side_n = ds->n;
 }
 
@@ -364,22 +390,69 @@ __global__ void qcm_kernel(const float* __restrict__ qsq, uint32_t nq, float c, 
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) qcm[q] = c * sqrtf(qsq[q]);
 }
-__global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, float* __restrict__ tau) {
+// tau_q = max(j-th smallest sampled S', smallest sampled S' + margin): the j-th value fixes the expected number
+// of candidates; the margin (2.5 x the pruning bound at the mean row norm) keeps the k-th exact distance inside
+// the threshold for queries whose neighbours are densely spaced (S <= S' + 2 c||q|| ||x||).
+__global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j,
+                                     const float* __restrict__ qcm, float mean_norm, float* __restrict__ tau) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) tau[q] = key_dist(keys[(size_t)q * j + (j - 1)]);
+    if (q < nq)
+        tau[q] = fmaxf(key_dist(keys[(size_t)q * j + (j - 1)]), key_dist(keys[(size_t)q * j]) + 2.5f * qcm[q] * mean_norm);
 }
-// candidate (S', local row) lists -> rerank inputs
-__global__ void cand_to_pairs_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t nq,
-                                     uint32_t cap, uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid,
-                                     uint8_t* __restrict__ valid) {
-    const uint64_t total = (uint64_t)nq * cap;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t q = (uint32_t)(i / cap), j = (uint32_t)(i - (uint64_t)q * cap);
-        const bool ok = j < min(cnt[q], cap);
-        qidx[i] = q;
-        rid[i] = ok ? (uint32_t)cand[i] : 0u;
-        valid[i] = ok;
+// exclusive scan of min(cnt, cap) over the queries (one block; nq is at most a few 100k)
+__global__ void __launch_bounds__(1024) cand_offsets_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
+                                                            uint64_t* __restrict__ off) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nq; base += blockDim.x) {
+        const uint32_t q = base + threadIdx.x;
+        const uint64_t v = q < nq ? min(cnt[q], cap) : 0u;
+        uint64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t before = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
+        if (q < nq) off[q] = before;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + v;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) off[nq] = carry;
+}
+// candidate (S', local row) lists -> dense rerank inputs at off[q]
+__global__ void cand_to_pairs_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap,
+                                     const uint64_t* __restrict__ off, uint32_t* __restrict__ qidx,
+                                     uint32_t* __restrict__ rid) {
+    const uint32_t q = blockIdx.x;
+    const uint32_t c = min(cnt[q], cap);
+    const uint64_t o = off[q];
+    for (uint32_t j = threadIdx.x; j < c; j += blockDim.x) {
+        qidx[o + j] = q;
+        rid[o + j] = (uint32_t)cand[(uint64_t)q * cap + j];
+    }
+}
+__global__ void rekey_dev_count_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ ids, uint32_t id_base,
+                                       const uint64_t* __restrict__ count, uint64_t* __restrict__ keys) {
+    const uint64_t n = *count;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
+        keys[j] = make_key(dist[j], ids[j] + id_base);
 }
 // completeness check; failing queries are appended to redo[]
 __global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, uint64_t n,
@@ -418,6 +491,8 @@ bool flat_gemm_supported(const vdb_dataset* ds, uint32_t nq, uint32_t k) {
 }
 
 uint64_t g_gemm_redo = 0;  // queries that needed the exact fallback (instrumentation)
+uint64_t g_gemm_cands = 0; // candidates reranked (instrumentation)
+uint64_t g_gemm_queries = 0;
 
 void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
                     cudaStream_t st) {
@@ -476,7 +551,8 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
         launch_gemm(0, mq, ms, ps, st);
         launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j, jkeys.as<uint64_t>(), nullptr, nullptr,
                           nullptr, st);
-        tau_from_keys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j, tau.as<float>());
+        tau_from_keys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j, qcm.as<float>(), ds->mean_norm,
+                                                                tau.as<float>());
         VDB_LAUNCHED();
     }
     // ---- filter pass over the whole shard ----
@@ -493,19 +569,26 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
         pf.cap = cap;
         launch_gemm(1, mq, mx, pf, st);
     }
-    // ---- exact rerank of the candidates ----
-    const uint64_t total = (uint64_t)nq * cap;
+    // ---- exact rerank of the candidates (compacted: only the valid pairs are touched) ----
+    const uint64_t total = (uint64_t)nq * cap;  // capacity bound; the live count stays on the device
+    DevBuf off((size_t)(nq + 1) * 8, st);
     {
-        DevBuf qidx(total * 4, st), rid(total * 4, st), valid(total, st), dist(total * 4, st), keys2(total * 8, st);
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(total, 256), 8192);
-        cand_to_pairs_kernel<<<grid, 256, 0, st>>>(cand.as<uint64_t>(), cnt.as<uint32_t>(), nq, cap, qidx.as<uint32_t>(),
-                                                   rid.as<uint32_t>(), valid.as<uint8_t>());
+        DevBuf qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st),
+            keys2(total * 8, st);
+        cand_offsets_kernel<<<1, 1024, 0, st>>>(cnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
         VDB_LAUNCHED();
-        exact_pair_distances_masked(ds, dq, qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), valid.as<uint8_t>(), total,
-                                    dist.as<float>(), st);
-        rekey_based(dist.as<float>(), rid.as<uint32_t>(), (uint32_t)ds->id_base, valid.as<uint8_t>(), total,
-                    keys2.as<uint64_t>(), st);
-        launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st);
+        cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, off.as<uint64_t>(),
+                                                 qidx.as<uint32_t>(), rid.as<uint32_t>());
+        VDB_LAUNCHED();
+        const uint64_t* d_total = off.as<uint64_t>() + nq;
+        exact_pair_distances_masked(ds, dq, qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
+                                    dist.as<float>(), st, d_total);
+        rekey_dev_count_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(),
+                                                                        (uint32_t)ds->id_base, d_total,
+                                                                        keys2.as<uint64_t>());
+        VDB_LAUNCHED();
+        launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st,
+                          off.as<uint64_t>());
     }
     // ---- completeness check + exact fallback ----
     DevBuf redo((size_t)nq * 4, st), nredo(4, st);
@@ -514,9 +597,13 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
                                                      qsq.as<float>(), redo.as<uint32_t>(), nredo.as<uint32_t>());
     VDB_LAUNCHED();
     uint32_t h_redo = 0;
+    uint64_t h_cands = 0;
     VDB_CUDA(cudaMemcpyAsync(&h_redo, nredo.p, 4, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaMemcpyAsync(&h_cands, off.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToHost, st));
     VDB_CUDA(cudaStreamSynchronize(st));
     g_gemm_redo += h_redo;
+    g_gemm_cands += h_cands;
+    g_gemm_queries += nq;
     if (h_redo) {
         DevBuf rq((size_t)h_redo * dim * 4, st), rkeys((size_t)h_redo * k * 8, st);
         gather_rows_kernel<<<h_redo, 128, 0, st>>>((const float*)d_queries, dim, redo.as<uint32_t>(), h_redo, rq.as<float>());

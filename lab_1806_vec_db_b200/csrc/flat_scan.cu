@@ -177,21 +177,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
 constexpr int MERGE_THREADS = 256;
 __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
     const uint64_t* __restrict__ keys, uint32_t nlists, uint32_t nq, uint32_t len, int list_major,
-    uint32_t K, uint32_t P, uint32_t limit, uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids,
+    const uint64_t* __restrict__ seg_off, uint32_t K, uint32_t P, uint32_t limit, uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids,
     float* __restrict__ dist, uint32_t* __restrict__ counts) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem);
     TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + P), K, P, 1, limit};
     topk.init();
     const uint32_t q = blockIdx.x;
-    const uint64_t total = (uint64_t)nlists * len;
+    // seg_off != nullptr: one variable-length list per query, keys[seg_off[q] .. seg_off[q+1])
+    const uint64_t seg_base = seg_off ? seg_off[q] : 0;
+    const uint64_t total = seg_off ? seg_off[q + 1] - seg_base : (uint64_t)nlists * len;
     const uint64_t rounds = (total + blockDim.x - 1) / blockDim.x;
     for (uint64_t r = 0; r < rounds; ++r) {
         const uint64_t i = r * blockDim.x + threadIdx.x;
         bool want = false;
         if (i < total) {
-            const uint64_t l = i / len, j = i - l * len;
-            const uint64_t src = list_major ? ((l * nq + q) * len + j) : (((uint64_t)q * nlists + l) * len + j);
+            const uint64_t l = seg_off ? 0 : i / len, j = seg_off ? 0 : i - l * len;
+            const uint64_t src = seg_off ? seg_base + i
+                                         : (list_major ? ((l * nq + q) * len + j) : (((uint64_t)q * nlists + l) * len + j));
             const uint64_t key = keys[src];
             if (key < topk.tau(0)) want = topk.push(0, key);
         }
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
 
 void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
-                       uint32_t* d_counts, cudaStream_t stream) {
+                       uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off) {
     if (nq == 0 || k == 0) return;
     const uint32_t P = topk_segment_size(k, MERGE_THREADS);
     const size_t smem = TopkSmem::bytes(1, P);
@@ -226,8 +229,8 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
         VDB_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     ProfScope prof("merge", stream);
-    merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, k,
-                                                           P, P - k - MERGE_THREADS, d_out_keys, d_ids,
+    merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off,
+                                                           k, P, P - k - MERGE_THREADS, d_out_keys, d_ids,
                                                            d_dist, d_counts);
     VDB_LAUNCHED();
 }

@@ -52,7 +52,7 @@ void exact_pair_distances(const vdb_dataset* ds, const void* d_queries, const ui
                           const uint32_t* d_rid, uint64_t npairs, float* d_out, cudaStream_t st);
 void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, uint32_t qpitch, const uint32_t* d_qidx,
                                  const uint32_t* d_rid, const uint8_t* d_valid, uint64_t npairs, float* d_out,
-                                 cudaStream_t st);
+                                 cudaStream_t st, const uint64_t* d_npairs = nullptr);
 void cached_pair_distances(const vdb_dataset* ds, const void* d_queries, const float* d_qcache,
                            const float* d_rowcache, const uint32_t* d_qidx, const uint32_t* d_rid,
                            uint64_t npairs, float* d_out, cudaStream_t st);
@@ -90,6 +90,6 @@ void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, c
 // flat_gemm.cu
 void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
                      uint64_t* d_out_keys, cudaStream_t st);
-extern uint64_t g_gemm_redo;
+extern uint64_t g_gemm_redo, g_gemm_cands, g_gemm_queries;
 
 }  // namespace vdb

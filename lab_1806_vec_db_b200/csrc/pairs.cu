@@ -21,8 +21,10 @@ struct PairParams {
     const float* cacheA;     // per A-row cache (cached modes), indexed like A rows
     const float* cacheB;
     const uint8_t* valid;    // optional per-pair mask (invalid pairs are skipped, out = 0)
+    bool vec4;               // f32 rows, dim % 4 == 0, 16-byte aligned bases and strides: use 128-bit loads
     uint32_t dim;
     uint64_t npairs;
+    const uint64_t* npairs_dev;  // optional: the pair count lives on the device (npairs is then the grid bound)
     float* out;
 };
 
@@ -31,7 +33,8 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t j = warp; j < p.npairs; j += nwarps) {
+    const uint64_t npairs = p.npairs_dev ? *p.npairs_dev : p.npairs;
+    for (uint64_t j = warp; j < npairs; j += nwarps) {
         if (p.valid && !p.valid[j]) {
             if (lane == 0) p.out[j] = 0.f;
             continue;
@@ -44,6 +47,32 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
         if (MODE == PM_L2_SCANORDER) {
             // same per-lane element order (float4 chunk c = it*32 + lane) and the same xor-butterfly as the
             // streaming scan kernel (flat_scan.cu), so both Flat paths return bit-identical distances
+            if (p.vec4) {
+                // 128-bit loads, 8 row chunks in flight per lane before the first use
+                const uint32_t nvec = p.dim >> 2;
+                const float4* a4 = reinterpret_cast<const float4*>(a);
+                const float4* b4 = reinterpret_cast<const float4*>(b);
+                for (uint32_t c0 = 0; c0 < nvec; c0 += 256) {
+                    float4 xb[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t c = c0 + u * 32 + lane;
+                        xb[u] = c < nvec ? ldg_stream_f4(b4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t c = c0 + u * 32 + lane;
+                        if (c < nvec) {
+                            const float4 q = __ldg(a4 + c);
+                            const float d0 = xb[u].x - q.x, d1 = xb[u].y - q.y, d2 = xb[u].z - q.z, d3 = xb[u].w - q.w;
+                            s0 = fmaf(d0, d0, s0);
+                            s0 = fmaf(d1, d1, s0);
+                            s0 = fmaf(d2, d2, s0);
+                            s0 = fmaf(d3, d3, s0);
+                        }
+                    }
+                }
+            } else
             for (uint32_t c = lane; c * 4 < p.dim; c += 32) {
 #pragma unroll
                 for (uint32_t i = 0; i < 4; ++i) {
@@ -150,7 +179,7 @@ void exact_pair_distances(const vdb_dataset* ds, const void* d_queries, const ui
 // same with an explicit query pitch and a validity mask (K2 rerank)
 void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, uint32_t qpitch, const uint32_t* d_qidx,
                                  const uint32_t* d_rid, const uint8_t* d_valid, uint64_t npairs, float* d_out,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const uint64_t* d_npairs) {
     PairParams p{};
     p.A = d_queries;
     p.strideA = qpitch;
@@ -161,8 +190,11 @@ void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, u
     p.valid = d_valid;
     p.dim = ds->dim;
     p.npairs = npairs;
+    p.npairs_dev = d_npairs;
     p.out = d_out;
     const bool scan_order = ds->metric == VDB_L2SQR && ds->dtype == VDB_F32;
+    p.vec4 = scan_order && ds->dim % 4 == 0 && qpitch % 4 == 0 && ds->pitch % 4 == 0 &&
+             ((uintptr_t)d_queries & 15) == 0 && ((uintptr_t)ds->d_rows & 15) == 0;
     launch_pairs(scan_order ? PM_L2_SCANORDER : (ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE), false, ds->dtype, p, st);
 }
 
