@@ -21,6 +21,7 @@
 // tcgen05.ld (thread = query, registers = rows) and apply the per-query threshold in registers.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "index.cuh"
@@ -32,13 +33,23 @@ namespace vdb {
 constexpr int GM = 128;              // queries per tile (TMEM lanes)
 constexpr int GN = 256;              // database rows per tile (TMEM columns per accumulator)
 constexpr int GK = 32;               // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int G_STAGES = 4;
-constexpr int G_A_BYTES = GM * GK * 4;   // 16 KB
-constexpr int G_B_BYTES = GN * GK * 4;   // 32 KB
-constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_A_BYTES = GM * GK * 4;   // 16 KB: 128 queries x 128 B
 constexpr int G_THREADS = 192;       // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
 constexpr int G_TMEM_COLS = 512;     // 2 accumulators x 256 columns
-constexpr uint32_t G_SMEM = 1024 /*align*/ + G_STAGES * G_STAGE_BYTES + 2 * 2 * GN * 4 /*norm tiles*/ + 256 /*barriers*/;
+constexpr int G_MAX_STAGES = 6;
+// CTAS = 1: one CTA computes a 128 x 256 tile. CTAS = 2: a CTA pair (cta_group::2) computes 256 x 256, each CTA
+// loads its own 128 queries and HALF of the 256 database rows, so the shared-memory fill per MMA cycle drops 1.5x.
+template <int CTAS> struct GemmCfg {
+    static constexpr int B_ROWS = GN / CTAS;                    // database rows loaded per CTA and k-block
+    static constexpr int B_BYTES = B_ROWS * GK * 4;
+    static constexpr int STAGE_BYTES = G_A_BYTES + B_BYTES;     // 48 KB / 32 KB
+    static constexpr int STAGES = CTAS == 1 ? 4 : 6;            // 192 KB either way
+    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 2 * GN * 4 /*norm tiles*/ + 256 /*barriers*/;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) |
+                                      ((uint32_t)((GM * CTAS) >> 4) << 24);
+};
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-pair peer bit of a shared::cluster address (-> even CTA)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +92,44 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar_addr)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair when the MMAs retire
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -119,8 +168,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
-constexpr uint32_t G_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
 
 // ---- kernel ----------------------------------------------------------------------------------------------------
 struct GemmParams {
@@ -129,7 +176,7 @@ struct GemmParams {
     uint32_t row_stride;    // database row of B row i is i * row_stride
     uint32_t kblocks;       // ceil(dim / 32)
     uint32_t ntiles;        // ceil(nrows / GN)
-    uint32_t nqt;           // ceil(nq / GM)
+    uint32_t nqt;           // query-tile UNITS: ceil(nq / (GM * CTAS))
     uint32_t tiles_per_slab;
     uint32_t nslabs;
     const float* sqnorm;    // [n] ||x||^2
@@ -144,65 +191,83 @@ struct GemmParams {
     uint32_t cap;
 };
 
-template <int MODE>
+template <int MODE, int CTAS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
+    using Cfg = GemmCfg<CTAS>;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stage_base = smem;
-    float* norm_tiles = reinterpret_cast<float*>(smem + G_STAGES * G_STAGE_BYTES);  // [2 acc][2 arrays][GN]
+    float* norm_tiles = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2 acc][2 arrays][GN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(norm_tiles + 2 * 2 * GN);
-    uint64_t* full_bar = bars;                 // [G_STAGES]
-    uint64_t* empty_bar = bars + G_STAGES;     // [G_STAGES]
-    uint64_t* tfull_bar = bars + 2 * G_STAGES; // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+    uint64_t* full_bar = bars;                       // [STAGES]  (pair mode: the leader's copy is the live one)
+    uint64_t* empty_bar = bars + G_MAX_STAGES;       // [STAGES]  per CTA
+    uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES;   // [2]       per CTA
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]       (pair mode: the leader's copy is the live one)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 128);
+            mbar_init(&tempty_bar[a], 4 * CTAS);  // one arrive per epilogue warp of every CTA in the group
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(tmem_slot, G_TMEM_COLS);
+    if (warp == 5) {
+        if (CTAS == 2) tmem_alloc2(tmem_slot, G_TMEM_COLS);
+        else tmem_alloc(tmem_slot, G_TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / TMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const uint32_t items = p.nqt * p.nslabs;
+    const uint32_t unit = blockIdx.x / CTAS, nunits = gridDim.x / CTAS;
 
     if (warp == 4) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA loads its own queries and its share of the database rows) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
-                const uint32_t slab = item / p.nqt, qt = item - slab * p.nqt;
+            for (uint32_t item = unit; item < items; item += nunits) {
+                const uint32_t slab = item / p.nqt, qt = (item - slab * p.nqt) * CTAS + cta_rank;
                 const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
                 for (uint32_t t = t0; t < t1; ++t) {
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], G_STAGE_BYTES);
-                        const uint32_t sa = smem_u32(stage_base + stage * G_STAGE_BYTES);
-                        tma_load_2d(sa, &map_q, (int)(kb * GK), (int)(qt * GM), &full_bar[stage]);
-                        tma_load_2d(sa + G_A_BYTES, &map_x, (int)(kb * GK), (int)(t * GN), &full_bar[stage]);
-                        if (++stage == G_STAGES) stage = 0, phase ^= 1;
+                        const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+                        if (CTAS == 1) {
+                            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                            tma_load_2d(sa, &map_q, (int)(kb * GK), (int)(qt * GM), &full_bar[stage]);
+                            tma_load_2d(sa + G_A_BYTES, &map_x, (int)(kb * GK), (int)(t * GN), &full_bar[stage]);
+                        } else {
+                            // both CTAs' bytes are accounted on the LEADER's barrier
+                            if (leader) mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * CTAS);
+                            const uint32_t lbar = smem_u32(&full_bar[stage]) & PEER_MASK;
+                            tma_load_2d_2sm(sa, &map_q, (int)(kb * GK), (int)(qt * GM), lbar);
+                            tma_load_2d_2sm(sa + G_A_BYTES, &map_x, (int)(kb * GK),
+                                            (int)(t * GN + cta_rank * Cfg::B_ROWS), lbar);
+                        }
+                        if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 5) {
-        // ===== MMA issuer (one elected thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer (one elected thread of the leader CTA) =====
+        if (lane == 0 && leader) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            for (uint32_t item = unit; item < items; item += nunits) {
                 const uint32_t slab = item / p.nqt;
                 const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
                 for (uint32_t t = t0; t < t1; ++t) {
@@ -212,15 +277,21 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(stage_base + stage * G_STAGE_BYTES);
+                        const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
                         const uint64_t da = umma_desc(sa), db = umma_desc(sa + G_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < GK / 8; ++k)  // advance 32 bytes (2 x 16B units) per K=8 step
-                            umma_tf32(d_tmem, da + 2 * k, db + 2 * k, G_IDESC, (kb | k) != 0);
-                        umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-                        if (++stage == G_STAGES) stage = 0, phase ^= 1;
+                        for (int k = 0; k < GK / 8; ++k) {  // advance 32 bytes (2 x 16B units) per K=8 step
+                            if (CTAS == 1) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                            else umma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                        }
+                        // frees the smem stage (in both CTAs) when these MMAs retire
+                        if (CTAS == 1) umma_commit(&empty_bar[stage]);
+                        else umma_commit_2sm(&empty_bar[stage]);
+                        if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
-                    umma_commit(&tfull_bar[acc]);        // accumulator ready for the epilogue
+                    // accumulator ready for the epilogue warps (of both CTAs)
+                    if (CTAS == 1) umma_commit(&tfull_bar[acc]);
+                    else umma_commit_2sm(&tfull_bar[acc]);
                     if (++acc == 2) acc = 0, acc_phase ^= 1;
                 }
             }
@@ -229,8 +300,8 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== epilogue: warps 0-3, thread = query (TMEM lane), registers = database rows =====
         uint32_t acc = 0, acc_phase = 0;
         const uint32_t lane_base = (uint32_t)warp * 32;
-        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
-            const uint32_t slab = item / p.nqt, qt = item - slab * p.nqt;
+        for (uint32_t item = unit; item < items; item += nunits) {
+            const uint32_t slab = item / p.nqt, qt = (item - slab * p.nqt) * CTAS + cta_rank;
             const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
             const uint32_t q = qt * GM + threadIdx.x;
             const bool qok = q < p.nq;
@@ -274,15 +345,24 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         }
                     }
                 }
+                // hand the accumulator back to the MMA issuer: one arrive per warp, on the leader's barrier
                 tc_fence_before();
-                mbar_arrive(&tempty_bar[acc]);
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTAS == 1) mbar_arrive(&tempty_bar[acc]);
+                    else mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_MASK);
+                }
                 if (++acc == 2) acc = 0, acc_phase ^= 1;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, G_TMEM_COLS);
+    if (CTAS == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still uses it
+    if (warp == 5) {
+        if (CTAS == 2) tmem_dealloc2(tmem_base, G_TMEM_COLS);
+        else tmem_dealloc(tmem_base, G_TMEM_COLS);
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -364,24 +444,54 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
     ds->side_n = ds->n;
 }
 
-static void launch_gemm(int mode, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st) {
+static int gemm_ctas() {
+    static const int v = getenv("VDB_GEMM_CTAS") ? atoi(getenv("VDB_GEMM_CTAS")) : 2;
+    return v == 1 ? 1 : 2;
+}
+
+template <int MODE, int CTAS>
+static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st) {
+    using Cfg = GemmCfg<CTAS>;
+    auto kern = flat_gemm_kernel<MODE, CTAS>;
     static thread_local bool configured = false;
     if (!configured) {
-        VDB_CUDA(cudaFuncSetAttribute(flat_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
-        VDB_CUDA(cudaFuncSetAttribute(flat_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
     const uint32_t sms = (uint32_t)sm_count();
     p.ntiles = (uint32_t)ceil_div<uint64_t>(p.nrows, GN);
-    p.nqt = ceil_div<uint32_t>(p.nq, GM);
-    // slabs of ~16 row tiles; query tile fastest so concurrently running CTAs share the same slab in L2
-    p.tiles_per_slab = std::max(1u, std::min(16u, ceil_div(p.ntiles * p.nqt, sms)));
+    p.nqt = ceil_div<uint32_t>(p.nq, GM * CTAS);
+    // small slabs, query tile fastest: concurrently running CTAs share a few row tiles (and all query tiles) in L2
+    static const uint32_t tps_env = getenv("VDB_GEMM_TPS") ? (uint32_t)atoi(getenv("VDB_GEMM_TPS")) : 0;
+    const uint32_t tps = tps_env ? tps_env : 4u;
+    p.tiles_per_slab = std::max(1u, std::min(tps, ceil_div(p.ntiles * p.nqt, sms / CTAS)));
     p.nslabs = ceil_div(p.ntiles, p.tiles_per_slab);
-    const uint32_t grid = std::min(sms, p.nqt * p.nslabs);
+    const uint32_t units = std::min(sms / CTAS, p.nqt * p.nslabs);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(units * CTAS);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     ProfScope prof("flat_gemm", st);
-    if (mode == 0) flat_gemm_kernel<0><<<grid, G_THREADS, G_SMEM, st>>>(mq, mx, p);
-    else flat_gemm_kernel<1><<<grid, G_THREADS, G_SMEM, st>>>(mq, mx, p);
+    VDB_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, p));
     VDB_LAUNCHED();
+}
+
+static void launch_gemm(int mode, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st) {
+    if (gemm_ctas() == 2) {
+        if (mode == 0) launch_gemm_t<0, 2>(mq, mx, p, st);
+        else launch_gemm_t<1, 2>(mq, mx, p, st);
+    } else {
+        if (mode == 0) launch_gemm_t<0, 1>(mq, mx, p, st);
+        else launch_gemm_t<1, 1>(mq, mx, p, st);
+    }
 }
 
 // c * ||q|| per query; c bounds |S'_tf32 - S'_exact| / (||q|| ||x||): two TF32 operand roundings (2^-10 each,
@@ -543,7 +653,7 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     p.qcm = qcm.as<float>();
     {
         DevBuf skeys((size_t)nq * ns * 8, st), jkeys((size_t)nq * j * 8, st);
-        const CUtensorMap ms = make_map(ds->d_rows, dim, ns, ds->pitch_bytes() * stride, GN);
+        const CUtensorMap ms = make_map(ds->d_rows, dim, ns, ds->pitch_bytes() * stride, GN / gemm_ctas());
         GemmParams ps = p;
         ps.nrows = ns;
         ps.row_stride = stride;
@@ -559,7 +669,7 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     DevBuf cnt((size_t)nq * 4, st), cand((size_t)nq * cap * 8, st);
     VDB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * 4, st));
     {
-        const CUtensorMap mx = make_map(ds->d_rows, dim, ds->n, ds->pitch_bytes(), GN);
+        const CUtensorMap mx = make_map(ds->d_rows, dim, ds->n, ds->pitch_bytes(), GN / gemm_ctas());
         GemmParams pf = p;
         pf.nrows = ds->n;
         pf.row_stride = 1;
@@ -640,7 +750,7 @@ void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
     p.row_stride = row_stride;
     p.out_keys = d_out_keys;
     const CUtensorMap mq = make_map(d_queries, ds->dim, nq, (uint64_t)ds->dim * 4, GM);
-    const CUtensorMap ms = make_map(ds->d_rows, ds->dim, ns, ds->pitch_bytes() * row_stride, GN);
+    const CUtensorMap ms = make_map(ds->d_rows, ds->dim, ns, ds->pitch_bytes() * row_stride, GN / gemm_ctas());
     launch_gemm(0, mq, ms, p, st);
 }
 
