@@ -107,6 +107,13 @@ void upload_rows(vdb_dataset* ds, uint64_t at, const void* rows, uint64_t n, cud
 void drop_side_arrays(vdb_dataset* ds) {
     if (ds->d_lo) cudaFree(ds->d_lo);
     if (ds->d_sqnorm) cudaFree(ds->d_sqnorm);
+    if (ds->d_tf32) cudaFree(ds->d_tf32);
+    if (ds->d_sample) cudaFree(ds->d_sample);
+    if (ds->d_sample_sq) cudaFree(ds->d_sample_sq);
+    if (ds->d_sample_rn) cudaFree(ds->d_sample_rn);
+    ds->d_sample = ds->d_sample_sq = ds->d_sample_rn = nullptr;
+    ds->sample_n = 0;
+    ds->d_tf32 = nullptr;
     ds->d_lo = nullptr;
     ds->d_sqnorm = nullptr;
     ds->side_n = 0;

@@ -13,8 +13,12 @@ struct vdb_dataset {
     int metric = VDB_L2SQR;
     uint64_t id_base = 0;
     // lazily built side arrays for the tensor-core path (K2); invalidated on mutation
-    float* d_lo = nullptr;    // tf32 residual x - tf32(x), [n][pitch]
+    float* d_lo = nullptr;    // ||x|| (fp32), [n]
+    float* d_tf32 = nullptr;  // rows rounded to TF32 (round-to-nearest), [n][pitch]: the tensor-core operand
     float* d_sqnorm = nullptr;  // ||x||^2 (fp32), [n]
+    float* d_sample = nullptr;  // stratified random row sample (TF32-rounded), [sample_n][pitch]
+    float* d_sample_sq = nullptr, *d_sample_rn = nullptr;  // its ||x||^2 and ||x||
+    uint32_t sample_n = 0;
     uint64_t side_n = 0;      // number of rows the side arrays cover
     float mean_norm = 0.f;    // mean ||x|| over a row sample (threshold margin of the tensor path)
     uint32_t elem_size() const { return dtype == VDB_F32 ? 4u : 1u; }

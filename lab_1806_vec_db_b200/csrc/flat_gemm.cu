@@ -21,6 +21,7 @@
 // tcgen05.ld (thread = query, registers = rows) and apply the per-query threshold in registers.
 #include <cuda.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -44,11 +45,14 @@ template <int CTAS> struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * GK * 4;
     static constexpr int STAGE_BYTES = G_A_BYTES + B_BYTES;     // 48 KB / 32 KB
     static constexpr int STAGES = CTAS == 1 ? 4 : 6;            // 192 KB either way
-    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 2 * GN * 4 /*norm tiles*/ + 256 /*barriers*/;
+    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 2 * GN * 4 /*norm tiles*/ + 512 /*barriers*/;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) |
                                       ((uint32_t)((GM * CTAS) >> 4) << 24);
 };
+constexpr uint32_t G_SAMPLE = 32768;  // sampled rows for the thresholds
+constexpr int G_ITEMQ = 4;              // depth of the dynamic-scheduler item queue
+constexpr uint32_t G_NO_ITEM = 0xFFFFFFFFu;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-pair peer bit of a shared::cluster address (-> even CTA)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -100,6 +104,35 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
         "l"(map), "r"(c0), "r"(c1), "r"(bar_addr)
         : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const uint64_t t0 = global_ns();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (global_ns() - t0 > 4000000000ull) __trap();
+    }
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -189,6 +222,7 @@ struct GemmParams {
     uint32_t* cand_cnt;     // [nq]
     uint64_t* cand;         // [nq][cap]  (S' bits << 32 | local row)
     uint32_t cap;
+    uint32_t* work_counter; // dynamic item scheduler (zeroed before the launch)
 };
 
 template <int MODE, int CTAS>
@@ -205,7 +239,10 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t* empty_bar = bars + G_MAX_STAGES;       // [STAGES]  per CTA
     uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES;   // [2]       per CTA
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]       (pair mode: the leader's copy is the live one)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* iq_full = tempty_bar + 2;              // [G_ITEMQ] per CTA: an item id has been published
+    uint64_t* iq_empty = iq_full + G_ITEMQ;          // [G_ITEMQ] (leader's copy is live): every reader took it
+    uint32_t* item_ring = reinterpret_cast<uint32_t*>(iq_empty + G_ITEMQ);  // [G_ITEMQ]
+    uint32_t* tmem_slot = item_ring + G_ITEMQ;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
@@ -220,6 +257,11 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], 4 * CTAS);  // one arrive per epilogue warp of every CTA in the group
         }
+        for (int i = 0; i < G_ITEMQ; ++i) {
+            mbar_init(&iq_full[i], 1);
+            // readers of a published item: MMA thread + 4 epilogue warps (+ the peer's producer and 4 epilogue warps)
+            mbar_init(&iq_empty[i], CTAS == 1 ? 5 : 10);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -233,13 +275,41 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     const uint32_t items = p.nqt * p.nslabs;
-    const uint32_t unit = blockIdx.x / CTAS, nunits = gridDim.x / CTAS;
+    // ---- dynamic scheduler: the leader's producer draws item ids from a global counter and publishes them to
+    // every role of the CTA (pair) through a small shared-memory queue. Items are taken in global order, so the
+    // CTAs in flight always work on neighbouring slabs (shared in L2) no matter how their speeds drift apart.
+    const uint32_t leader_empty_base = CTAS == 2 ? mapa_cluster(smem_u32(iq_empty), 0) : smem_u32(iq_empty);
+    auto take_item = [&](uint32_t n) -> uint32_t {  // called by ONE thread of a reader role, n = 0, 1, 2, ...
+        const uint32_t slot = n % G_ITEMQ, ph = (n / G_ITEMQ) & 1;
+        if (CTAS == 2) mbar_wait_cluster(&iq_full[slot], ph);
+        else mbar_wait(&iq_full[slot], ph);
+        const uint32_t item = ((volatile uint32_t*)item_ring)[slot];
+        if (CTAS == 2) mbar_arrive_cluster_release(leader_empty_base + slot * 8);
+        else mbar_arrive(&iq_empty[slot]);
+        return item;
+    };
 
     if (warp == 4) {
         // ===== TMA producer (every CTA loads its own queries and its share of the database rows) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t item = unit; item < items; item += nunits) {
+            for (uint32_t n = 0;; ++n) {
+                uint32_t item;
+                if (leader) {
+                    const uint32_t slot = n % G_ITEMQ, ph = (n / G_ITEMQ) & 1;
+                    mbar_wait_cluster(&iq_empty[slot], ph ^ 1);
+                    item = atomicAdd(p.work_counter, 1u);
+                    if (item >= items) item = G_NO_ITEM;
+                    item_ring[slot] = item;
+                    mbar_arrive(&iq_full[slot]);
+                    if (CTAS == 2) {
+                        st_cluster_u32(mapa_cluster(smem_u32(&item_ring[slot]), 1), item);
+                        mbar_arrive_cluster_release(mapa_cluster(smem_u32(&iq_full[slot]), 1));
+                    }
+                } else {
+                    item = take_item(n);
+                }
+                if (item == G_NO_ITEM) break;
                 const uint32_t slab = item / p.nqt, qt = (item - slab * p.nqt) * CTAS + cta_rank;
                 const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
                 for (uint32_t t = t0; t < t1; ++t) {
@@ -267,7 +337,9 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== MMA issuer (one elected thread of the leader CTA) =====
         if (lane == 0 && leader) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t item = unit; item < items; item += nunits) {
+            for (uint32_t n = 0;; ++n) {
+                const uint32_t item = take_item(n);
+                if (item == G_NO_ITEM) break;
                 const uint32_t slab = item / p.nqt;
                 const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
                 for (uint32_t t = t0; t < t1; ++t) {
@@ -300,7 +372,11 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== epilogue: warps 0-3, thread = query (TMEM lane), registers = database rows =====
         uint32_t acc = 0, acc_phase = 0;
         const uint32_t lane_base = (uint32_t)warp * 32;
-        for (uint32_t item = unit; item < items; item += nunits) {
+        for (uint32_t n = 0;; ++n) {
+            uint32_t item = 0;
+            if (lane == 0) item = take_item(n);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item == G_NO_ITEM) break;
             const uint32_t slab = item / p.nqt, qt = (item - slab * p.nqt) * CTAS + cta_rank;
             const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
             const uint32_t q = qt * GM + threadIdx.x;
@@ -418,6 +494,41 @@ __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v,
     }
 }
 
+// round-to-nearest TF32 copy: the tensor core then consumes exactly representable operands, so the only operand
+// error is this rounding (2^-11 relative) instead of the hardware's truncation (2^-10)
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, uint64_t count) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
+        dst[i] = __uint_as_float(r);
+    }
+}
+static void round_tf32(const float* src, float* dst, uint64_t count, cudaStream_t st) {
+    if (count == 0) return;
+    round_tf32_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), (uint64_t)sm_count() * 32), 256, 0, st>>>(src, dst, count);
+    VDB_LAUNCHED();
+}
+
+// stratified random sample: one row per bucket of n/ns consecutive rows, at a hashed offset inside the bucket
+// (a plain stride would alias with periodic data)
+__global__ void gather_sample_kernel(const float* __restrict__ rows_tf32, const float* __restrict__ sqnorm,
+                                     const float* __restrict__ rnorm, uint64_t n, uint32_t pitch, uint32_t ns,
+                                     float* __restrict__ out, float* __restrict__ out_sq, float* __restrict__ out_rn) {
+    const uint32_t i = blockIdx.x;
+    if (i >= ns) return;
+    const uint64_t lo = (uint64_t)i * n / ns, hi = (uint64_t)(i + 1) * n / ns;
+    uint64_t h = (i + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 29;
+    const uint64_t row = lo + h % (hi > lo ? hi - lo : 1);
+    for (uint32_t e = threadIdx.x; e < pitch; e += blockDim.x) out[(size_t)i * pitch + e] = rows_tf32[row * pitch + e];
+    if (threadIdx.x == 0) {
+        out_sq[i] = sqnorm[row];
+        out_rn[i] = rnorm[row];
+    }
+}
+
 static std::mutex g_side_mu;
 // ||x||^2 and ||x|| per row, cached on the (logically const) dataset handle
 static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
@@ -426,14 +537,27 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
     if (ds->d_sqnorm && ds->side_n == ds->n) return;
     if (ds->d_sqnorm) cudaFree(ds->d_sqnorm);
     if (ds->d_lo) cudaFree(ds->d_lo);
-    ds->d_sqnorm = ds->d_lo = nullptr;
+    if (ds->d_tf32) cudaFree(ds->d_tf32);
+    if (ds->d_sample) cudaFree(ds->d_sample);
+    if (ds->d_sample_sq) cudaFree(ds->d_sample_sq);
+    if (ds->d_sample_rn) cudaFree(ds->d_sample_rn);
+    ds->d_sqnorm = ds->d_lo = ds->d_tf32 = ds->d_sample = ds->d_sample_sq = ds->d_sample_rn = nullptr;
     VDB_CUDA(cudaMalloc(&ds->d_sqnorm, ds->n * 4));
-    VDB_CUDA(cudaMalloc(&ds->d_lo, ds->n * 4));  // d_lo holds ||x|| for this path
+    VDB_CUDA(cudaMalloc(&ds->d_lo, ds->n * 4));
+    VDB_CUDA(cudaMalloc(&ds->d_tf32, ds->n * ds->pitch_bytes()));
+    round_tf32((const float*)ds->d_rows, ds->d_tf32, ds->n * ds->pitch, st);
+    ds->sample_n = (uint32_t)std::min<uint64_t>(G_SAMPLE, ds->n / 2);
+    VDB_CUDA(cudaMalloc(&ds->d_sample, (size_t)ds->sample_n * ds->pitch_bytes()));
+    VDB_CUDA(cudaMalloc(&ds->d_sample_sq, (size_t)ds->sample_n * 4));
+    VDB_CUDA(cudaMalloc(&ds->d_sample_rn, (size_t)ds->sample_n * 4));
     vdb_dataset tmp = *ds;
     tmp.metric = VDB_L2SQR;
     row_cache(&tmp, ds->d_sqnorm, st);
     tmp.metric = VDB_COSINE;
     row_cache(&tmp, ds->d_lo, st);
+    gather_sample_kernel<<<ds->sample_n, 256, 0, st>>>(ds->d_tf32, ds->d_sqnorm, ds->d_lo, ds->n, ds->pitch, ds->sample_n,
+                                                       ds->d_sample, ds->d_sample_sq, ds->d_sample_rn);
+    VDB_LAUNCHED();
     {
         DevBuf m(4, st);
         mean_kernel<<<1, 1024, 0, st>>>(ds->d_lo, ds->n, std::max<uint64_t>(1, ds->n / 65536), m.as<float>());
@@ -479,6 +603,9 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    DevBuf counter(4, st);
+    VDB_CUDA(cudaMemsetAsync(counter.p, 0, 4, st));
+    p.work_counter = counter.as<uint32_t>();
     ProfScope prof("flat_gemm", st);
     VDB_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, p));
     VDB_LAUNCHED();
@@ -500,14 +627,13 @@ __global__ void qcm_kernel(const float* __restrict__ qsq, uint32_t nq, float c, 
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) qcm[q] = c * sqrtf(qsq[q]);
 }
-// tau_q = max(j-th smallest sampled S', smallest sampled S' + margin): the j-th value fixes the expected number
-// of candidates; the margin (2.5 x the pruning bound at the mean row norm) keeps the k-th exact distance inside
-// the threshold for queries whose neighbours are densely spaced (S <= S' + 2 c||q|| ||x||).
-__global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j,
+// tau_q = (j0-th smallest sampled S') + margin. j0 is chosen so that the k-th best S' of the shard is <= S'_(j0)
+// with high probability; because S <= S' + 2 c||q|| ||x||, the margin (2.5 x the pruning bound at the mean row
+// norm) keeps the k-th EXACT distance inside the threshold. The check kernel verifies it per query afterwards.
+__global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, uint32_t j0,
                                      const float* __restrict__ qcm, float mean_norm, float* __restrict__ tau) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq)
-        tau[q] = fmaxf(key_dist(keys[(size_t)q * j + (j - 1)]), key_dist(keys[(size_t)q * j]) + 2.5f * qcm[q] * mean_norm);
+    if (q < nq) tau[q] = key_dist(keys[(size_t)q * j + (j0 - 1)]) + 2.5f * qcm[q] * mean_norm;
 }
 // exclusive scan of min(cnt, cap) over the queries (one block; nq is at most a few 100k)
 __global__ void __launch_bounds__(1024) cand_offsets_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
@@ -592,11 +718,10 @@ __global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, uint32_t k
     for (uint32_t e = threadIdx.x; e < k; e += blockDim.x) dst[(size_t)idx[i] * k + e] = src[(size_t)i * k + e];
 }
 
-constexpr uint32_t G_SAMPLE = 8192;   // sampled rows for the thresholds
 constexpr uint32_t G_MAX_K = 1024;
 
 bool flat_gemm_supported(const vdb_dataset* ds, uint32_t nq, uint32_t k) {
-    return ds->dtype == VDB_F32 && ds->metric == VDB_L2SQR && k >= 1 && k <= G_MAX_K && ds->n >= 16ull * G_SAMPLE &&
+    return ds->dtype == VDB_F32 && ds->metric == VDB_L2SQR && k >= 1 && k <= G_MAX_K && ds->n >= 65536 &&
            nq >= 1 && ((uintptr_t)ds->d_rows & 15) == 0;
 }
 
@@ -611,19 +736,19 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     const float* sqnorm = ds->d_sqnorm;
     const float* rnorm = ds->d_lo;
     const uint32_t dim = ds->dim;
-    const float c = 2.0f * (ldexpf(1.0f, -9) + (float)dim * ldexpf(1.0f, -23));
+    // pruning-bound coefficient: both operands rounded to TF32 (2^-11 each, products then exact in fp32) plus
+    // dim fp32 accumulation steps, times 2 for the -2 q.x term
+    const float c = 2.0f * (ldexpf(1.0f, -10) * 1.001f + (float)dim * ldexpf(1.0f, -23));
 
     // queries: contiguous [nq][dim] f32 (TMA needs a 16-byte aligned base and row pitch)
-    DevBuf qcopy;
-    const float* dq = (const float*)d_queries;
+    // dq: padded fp32 copy (exact rerank + norms); dq_tf32: the same rounded to TF32 (tensor-core operand)
     const uint32_t qpitch = round_up(dim, 4u);
-    if (dim % 4 != 0 || ((uintptr_t)d_queries & 15)) {
-        qcopy = DevBuf((size_t)nq * qpitch * 4, st);
-        VDB_CUDA(cudaMemsetAsync(qcopy.p, 0, (size_t)nq * qpitch * 4, st));
-        VDB_CUDA(cudaMemcpy2DAsync(qcopy.p, (size_t)qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
-                                   cudaMemcpyDeviceToDevice, st));
-        dq = qcopy.as<float>();
-    }
+    DevBuf qcopy((size_t)nq * qpitch * 4, st), qround((size_t)nq * qpitch * 4, st);
+    if (qpitch != dim) VDB_CUDA(cudaMemsetAsync(qcopy.p, 0, (size_t)nq * qpitch * 4, st));
+    VDB_CUDA(cudaMemcpy2DAsync(qcopy.p, (size_t)qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
+                               cudaMemcpyDeviceToDevice, st));
+    const float* dq = qcopy.as<float>();
+    round_tf32(dq, qround.as<float>(), (uint64_t)nq * qpitch, st);
     DevBuf qsq((size_t)nq * 4, st), qcm((size_t)nq * 4, st), tau((size_t)nq * 4, st);
     {
         vdb_dataset qd = *ds;
@@ -635,16 +760,25 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
         qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(qsq.as<float>(), nq, c, qcm.as<float>());
         VDB_LAUNCHED();
     }
-    const CUtensorMap mq = make_map(dq, dim, nq, (uint64_t)qpitch * 4, GM);
+    const CUtensorMap mq = make_map(qround.as<float>(), dim, nq, (uint64_t)qpitch * 4, GM);
 
     // ---- thresholds from a strided sample ----
-    const uint32_t stride = (uint32_t)(ds->n / G_SAMPLE);
-    const uint64_t ns = ds->n / stride;
-    // expected candidates per query = j * n / ns; aim at max(8k, 768) so the k-th exact distance sits well
-    // inside the threshold
-    const uint32_t want = std::max(8 * k, 768u);
-    const uint32_t j = (uint32_t)std::min<uint64_t>(ns, std::max<uint64_t>(6, ceil_div<uint64_t>((uint64_t)want * ns, ds->n)));
-    const uint32_t cap = (uint32_t)next_pow2((uint32_t)std::min<uint64_t>(ds->n, 4ull * j * stride + 1024));
+    const uint64_t ns = ds->sample_n;
+    // j0: smallest order statistic of the sample whose rank in the shard is >= k with high probability:
+    // P(rank < k) = P(Poisson(k*ns/n) >= j0) < 2e-3
+    uint32_t j0 = 1;
+    {
+        const double x = (double)k * (double)ns / (double)ds->n;
+        double term = exp(-x), cdf = term;
+        while (1.0 - cdf >= 2e-3 && j0 < 4096) {
+            term *= x / j0;
+            cdf += term;
+            ++j0;
+        }
+    }
+    j0 = (uint32_t)std::min<uint64_t>(j0, ns);
+    const uint32_t j = j0;
+    const uint32_t cap = (uint32_t)next_pow2((uint32_t)std::min<uint64_t>(ds->n, std::max<uint64_t>(8ull * j * (ds->n / ns), 8192)));
     GemmParams p{};
     p.nq = nq;
     p.kblocks = ceil_div(dim, (uint32_t)GK);
@@ -653,15 +787,17 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     p.qcm = qcm.as<float>();
     {
         DevBuf skeys((size_t)nq * ns * 8, st), jkeys((size_t)nq * j * 8, st);
-        const CUtensorMap ms = make_map(ds->d_rows, dim, ns, ds->pitch_bytes() * stride, GN / gemm_ctas());
+        const CUtensorMap ms = make_map(ds->d_sample, dim, ns, ds->pitch_bytes(), GN / gemm_ctas());
         GemmParams ps = p;
         ps.nrows = ns;
-        ps.row_stride = stride;
+        ps.row_stride = 1;
+        ps.sqnorm = ds->d_sample_sq;
+        ps.rnorm = ds->d_sample_rn;
         ps.out_keys = skeys.as<uint64_t>();
         launch_gemm(0, mq, ms, ps, st);
         launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j, jkeys.as<uint64_t>(), nullptr, nullptr,
                           nullptr, st);
-        tau_from_keys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j, qcm.as<float>(), ds->mean_norm,
+        tau_from_keys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j, j0, qcm.as<float>(), ds->mean_norm,
                                                                 tau.as<float>());
         VDB_LAUNCHED();
     }
@@ -669,7 +805,7 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     DevBuf cnt((size_t)nq * 4, st), cand((size_t)nq * cap * 8, st);
     VDB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * 4, st));
     {
-        const CUtensorMap mx = make_map(ds->d_rows, dim, ds->n, ds->pitch_bytes(), GN / gemm_ctas());
+        const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, ds->pitch_bytes(), GN / gemm_ctas());
         GemmParams pf = p;
         pf.nrows = ds->n;
         pf.row_stride = 1;
