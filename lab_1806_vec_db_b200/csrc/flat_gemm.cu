@@ -546,7 +546,8 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
     VDB_CUDA(cudaMalloc(&ds->d_lo, ds->n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_tf32, ds->n * ds->pitch_bytes()));
     round_tf32((const float*)ds->d_rows, ds->d_tf32, ds->n * ds->pitch, st);
-    ds->sample_n = (uint32_t)std::min<uint64_t>(G_SAMPLE, ds->n / 2);
+    // ~3 % of the shard, so the sample pass stays a small fixed fraction of the filter pass on every shard size
+    ds->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(G_SAMPLE, ds->n / 2), std::max<uint64_t>(2048, ds->n / 30));
     VDB_CUDA(cudaMalloc(&ds->d_sample, (size_t)ds->sample_n * ds->pitch_bytes()));
     VDB_CUDA(cudaMalloc(&ds->d_sample_sq, (size_t)ds->sample_n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_sample_rn, (size_t)ds->sample_n * 4));

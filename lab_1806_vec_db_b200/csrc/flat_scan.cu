@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
 
 // ---- merge of key lists ------------------------------------------------------------------------
 constexpr int MERGE_THREADS = 256;
+constexpr int MERGE_UNROLL = 1;
 __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
     const uint64_t* __restrict__ keys, uint32_t nlists, uint32_t nq, uint32_t len, int list_major,
     const uint64_t* __restrict__ seg_off, uint32_t K, uint32_t P, uint32_t limit, uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids,
@@ -187,17 +188,23 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
     // seg_off != nullptr: one variable-length list per query, keys[seg_off[q] .. seg_off[q+1])
     const uint64_t seg_base = seg_off ? seg_off[q] : 0;
     const uint64_t total = seg_off ? seg_off[q + 1] - seg_base : (uint64_t)nlists * len;
+    // one key per thread and round; the next round's key is loaded before this round's CTA-wide flush test so
+    // the load latency overlaps the barrier
     const uint64_t rounds = (total + blockDim.x - 1) / blockDim.x;
-    for (uint64_t r = 0; r < rounds; ++r) {
+    auto load_key = [&](uint64_t r) -> uint64_t {
         const uint64_t i = r * blockDim.x + threadIdx.x;
+        if (i >= total) return KEY_NONE;
+        const uint64_t l = seg_off ? 0 : i / len, j = seg_off ? 0 : i - l * len;
+        const uint64_t src = seg_off ? seg_base + i
+                                     : (list_major ? ((l * nq + q) * len + j) : (((uint64_t)q * nlists + l) * len + j));
+        return keys[src];
+    };
+    uint64_t next = rounds ? load_key(0) : KEY_NONE;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t key = next;
+        if (r + 1 < rounds) next = load_key(r + 1);
         bool want = false;
-        if (i < total) {
-            const uint64_t l = seg_off ? 0 : i / len, j = seg_off ? 0 : i - l * len;
-            const uint64_t src = seg_off ? seg_base + i
-                                         : (list_major ? ((l * nq + q) * len + j) : (((uint64_t)q * nlists + l) * len + j));
-            const uint64_t key = keys[src];
-            if (key < topk.tau(0)) want = topk.push(0, key);
-        }
+        if (key < topk.tau(0)) want = topk.push(0, key);
         topk.maybe_flush(want);
     }
     topk.final_flush();
@@ -222,7 +229,7 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
                        uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off) {
     if (nq == 0 || k == 0) return;
-    const uint32_t P = topk_segment_size(k, MERGE_THREADS);
+    const uint32_t P = topk_segment_size(k, MERGE_THREADS * MERGE_UNROLL);
     const size_t smem = TopkSmem::bytes(1, P);
     VDB_REQUIRE(smem <= 200 * 1024, "k=%u too large for the fused top-k (max %u)", k, 20000u);
     if (smem > 48 * 1024)
@@ -230,7 +237,7 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
                                       (int)smem));
     ProfScope prof("merge", stream);
     merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off,
-                                                           k, P, P - k - MERGE_THREADS, d_out_keys, d_ids,
+                                                           k, P, P - k - MERGE_THREADS * MERGE_UNROLL, d_out_keys, d_ids,
                                                            d_dist, d_counts);
     VDB_LAUNCHED();
 }
