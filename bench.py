@@ -360,6 +360,37 @@ def run_ours(args):
                "id_mismatches_are_ties_within_1e-5": bool(ties_ok)}
         del base_host
 
+    # ---- the HBM-bound regime of the same path: the trait's small-batch call through the streaming scan (K1) ----
+    hbm_scan = None
+    if world == 1:
+        peak_hbm = peaks.get("hbm_gbs") or 6650.0
+        hbm_scan = {"kernel": "flat_scan_kernel", "peak_gbs": peak_hbm,
+                    "peak_source": "measured" if peaks.get("hbm_gbs") else "fallback", "k": 10, "cases": []}
+        L.check(lib.vdb_flat_set_path(1))
+        for nq1 in (1, 2, 4, 8):
+            qs = q_dev[:nq1].contiguous()
+            for _ in range(3):
+                idx.knn_batch_dev(qs, 10)
+            L.check(lib.vdb_prof_reset())
+            L.check(lib.vdb_prof_enable(1))
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            a0.record()
+            for _ in range(reps):
+                idx.knn_batch_dev(qs, 10)
+            a1.record()
+            torch.cuda.synchronize()
+            L.check(lib.vdb_prof_enable(0))
+            t, c = C.c_double(0), C.c_uint64(0)
+            L.check(lib.vdb_prof_read(b"flat_scan", C.byref(t), C.byref(c)))
+            call_ms = a0.elapsed_time(a1) / reps
+            kern_ms = t.value / max(int(c.value), 1)
+            gbs = n_local * DIM * 4 / (kern_ms * 1e-3) / 1e9
+            hbm_scan["cases"].append({"nq": nq1, "qps": nq1 / (call_ms * 1e-3), "call_ms": call_ms,
+                                      "scan_kernel_ms": kern_ms, "achieved_gbs": gbs, "frac": gbs / peak_hbm,
+                                      "frac_whole_call": n_local * DIM * 4 / (call_ms * 1e-3) / 1e9 / peak_hbm})
+        L.check(lib.vdb_flat_set_path({"auto": 0, "scan": 1, "tensor": 2}[args.path]))
+
     qps = args.nq / (ms * 1e-3)
     line = {
         "metric": "QPS, exact Flat L2 kNN", "value": qps, "unit": "queries/s", "n_gpus": world,
@@ -378,6 +409,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "kernel_ms": {k_: {"ms": v[0], "launches": v[1]} for k_, v in prof.items()},
         "tensor_path": tensor_stats(lib),
+        "hbm_scan": hbm_scan,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
