@@ -12,6 +12,7 @@
 // HBM layout of the codes for the scan: blocks of 32 rows, word-major ([block][word][lane]) so a warp's
 // load of one code word for its 32 rows is a single coalesced 128-byte request; one lane owns one row, all
 // lanes look up the SAME group at the same time, so the 16-entry LUT row is read conflict free.
+#include <cstdlib>
 #include <cstring>
 
 #include "index.cuh"
@@ -204,12 +205,25 @@ __global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParam
     const bool do_topk = p.all_out == nullptr;
     if (do_topk) topk.init();
     else __syncthreads();
-    const float* lut = LUT_SMEM ? s_lut : p.lut;
-    const float* dc = (LUT_SMEM && METRIC == VDB_COSINE) ? s_dc : p.dist_cache;
     const int lane = threadIdx.x & 31;
     float qn[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) qn[q] = (METRIC == VDB_COSINE && q < (int)p.nq_valid) ? p.qcache[q] : 0.f;
+    constexpr int KC = NBITS == 4 ? 16 : 256;
+
+    // one table lookup for all NQ queries; the branch on LUT_SMEM is compile-time so the shared-memory path
+    // compiles to LDS (32-bit shared addressing), never to generic loads
+    auto lookup = [&](uint32_t e, float (&sum)[NQ], float& cdp) {
+        if constexpr (LUT_SMEM) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) sum[q] = __fadd_rn(sum[q], s_lut[q * tab + e]);
+            if (METRIC == VDB_COSINE) cdp = __fadd_rn(cdp, s_dc[e]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) sum[q] = __fadd_rn(sum[q], __ldg(p.lut + (size_t)q * tab + e));
+            if (METRIC == VDB_COSINE) cdp = __fadd_rn(cdp, __ldg(p.dist_cache + e));
+        }
+    };
 
     for (uint32_t it = 0; it < p.iters; ++it) {
         const uint64_t tile = (uint64_t)it * gridDim.x + blockIdx.x;
@@ -223,30 +237,38 @@ __global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParam
         if (in) {
             const uint32_t* cw = p.codes_t + blk * p.words * 32 + lane;
             uint32_t g = 0;
+            uint32_t next = cw[0];
             for (uint32_t w = 0; w < p.words; ++w) {
-                const uint32_t word = cw[(size_t)w * 32];
+                const uint32_t word = next;
+                if (w + 1 < p.words) next = cw[(size_t)(w + 1) * 32];  // prefetch the next code word
+                if (NBITS == 4) {
+                    if (LUT_SMEM && METRIC == VDB_L2SQR && g + 8 <= p.m) {
+                        // full word: issue all 8 x NQ table reads first, then add in the reference's group order
+                        float v[8][NQ];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t byte = (word >> (8 * b)) & 0xffu;
-                    if (NBITS == 4) {
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t e = (g + i) * KC + ((word >> (4 * i)) & 0xfu);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h, ++g) {
-                            if (g < p.m) {
-                                const uint32_t e = g * 16 + ((byte >> (4 * h)) & 0xfu);
-#pragma unroll
-                                for (int q = 0; q < NQ; ++q) sum[q] = __fadd_rn(sum[q], lut[(size_t)q * tab + e]);
-                                if (METRIC == VDB_COSINE) cdp = __fadd_rn(cdp, dc[e]);
-                            }
+                            for (int q = 0; q < NQ; ++q) v[i][q] = s_lut[q * tab + e];
                         }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q) sum[q] = __fadd_rn(sum[q], v[i][q]);
+                    } else if (g + 8 <= p.m) {  // full word: 8 groups, no per-nibble bound checks
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) lookup((g + i) * KC + ((word >> (4 * i)) & 0xfu), sum, cdp);
                     } else {
-                        if (g < p.m) {
-                            const uint32_t e = g * 256 + byte;
 #pragma unroll
-                            for (int q = 0; q < NQ; ++q) sum[q] = __fadd_rn(sum[q], lut[(size_t)q * tab + e]);
-                            if (METRIC == VDB_COSINE) cdp = __fadd_rn(cdp, dc[e]);
-                        }
-                        ++g;
+                        for (int i = 0; i < 8; ++i)
+                            if (g + i < p.m) lookup((g + i) * KC + ((word >> (4 * i)) & 0xfu), sum, cdp);
                     }
+                    g += 8;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (g + i < p.m) lookup((g + i) * KC + ((word >> (8 * i)) & 0xffu), sum, cdp);
+                    g += 4;
                 }
             }
         }
@@ -322,13 +344,16 @@ static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache
         if (topk) s += TopkSmem::bytes(t, P);
         return s;
     };
-    int nqt = 4;
+    static const int nqt_env = getenv("VDB_ADC_NQ") ? atoi(getenv("VDB_ADC_NQ")) : 0;
+    int nqt = (nqt_env == 1 || nqt_env == 2 || nqt_env == 4) ? nqt_env : 4;
     bool lut_smem = true;
     while (nqt > 1 && smem_for(nqt, true) > ADC_SMEM_MAX) nqt >>= 1;
     if (smem_for(nqt, true) > ADC_SMEM_MAX) lut_smem = false;
     VDB_REQUIRE(smem_for(nqt, lut_smem) <= ADC_SMEM_MAX, "ADC scan: ef=%u too large for the fused top-k", K);
     const uint64_t tiles = ceil_div<uint64_t>(pq->n, ADC_THREADS);
-    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sm_count() * 2));
+    // one wave: resident CTAs per SM is limited by shared memory (LUTs + top-k segments)
+    const uint32_t occ = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem_for(nqt, lut_smem), 1)));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sm_count() * occ));
     AdcParams p{};
     p.codes_t = pq->d_codes_t;
     p.n = pq->n;
