@@ -163,6 +163,40 @@ int vdb_ivf_knn_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_que
                     uint32_t k, uint32_t n_probes, uint64_t* d_ids, float* d_dist, uint32_t* d_counts,
                     void* stream);
 
+/* ---- tensor-core Flat path, phase by phase (row-sharded search: lab_1806_vec_db_b200/sharded.py) ---------
+ * The single-GPU vdb_flat_knn runs these phases internally. Across shards the thresholds must be GLOBAL (else
+ * every shard reranks its own ~750 candidates per query), so the phases are exported and the host inserts the
+ * collectives:  begin -> sample -> [all-gather] -> tau -> filter -> [all-gather keys, all-reduce overflow] ->
+ * vdb_merge_keys_dev -> check -> (rare) exact re-scan of the flagged queries -> end.  All pointers are device
+ * pointers; everything runs on the stream given to begin. */
+typedef struct vdb_tq vdb_tq;
+/* n, sample size and mean row norm of this shard (builds the side arrays on first use). */
+int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm);
+/* Smallest sample order statistic whose rank among n_total rows is >= k with probability > 1 - 2e-3. */
+uint32_t vdb_tq_j0(uint32_t k, uint64_t sample_total, uint64_t n_total);
+int vdb_tq_begin_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, void* stream, vdb_tq** out);
+/* this shard's j smallest sampled pruning scores per query: d_keys [nq, j] ascending */
+int vdb_tq_sample_dev(vdb_tq* tq, uint32_t j, uint64_t* d_keys);
+/* merges nlists shards' sample keys ([nlists, nq, j]) and writes tau[q] = score_(j0) + margin(mean_norm) */
+int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0,
+                   float mean_norm, float* d_tau);
+/* filter pass + exact rerank: this shard's k best keys per query ([nq, k], KEY_NONE padded) and per-query
+ * overflow flags (candidate list overflowed: the result for that query is not provably complete) */
+int vdb_tq_filter_dev(vdb_tq* tq, uint32_t k, const float* d_tau, uint64_t* d_keys, uint32_t* d_overflow);
+/* completeness check of the MERGED keys: d_redo receives the queries that must be re-run exactly, *d_nredo their count */
+int vdb_tq_check_dev(vdb_tq* tq, const uint64_t* d_merged_keys, uint32_t k, uint64_t n_total, const float* d_tau,
+                     const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo);
+int vdb_tq_end(vdb_tq* tq);
+/* Exact streaming scan (K1) regardless of the selected Flat path: d_keys [nq, k]. */
+int vdb_flat_scan_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                           void* stream);
+/* Merge that returns packed keys instead of SoA results (keys [nlists, nq, k] -> d_out_keys [nq, k]). */
+int vdb_merge_keys_to_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t k, uint64_t* d_out_keys,
+                               void* stream);
+/* Decodes packed keys into ids / distances / counts. */
+int vdb_decode_keys_dev(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
+                        uint32_t* d_counts, void* stream);
+
 /* ---- tensor-core path internals (tests / tuning) ---------------------------------------------- */
 /* Pruning scores of the tensor-core Flat path: out_keys[q * ns + i] = key(S'(q, row i*row_stride), i) for the
  * ns = n / row_stride sampled rows, S' = ||x||^2 - 2 q.x - c ||q|| ||x|| evaluated with TF32 tensor cores.

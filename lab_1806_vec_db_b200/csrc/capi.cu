@@ -358,6 +358,79 @@ int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     });
 }
 
+int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm) {
+    return guarded([&] {
+        VDB_REQUIRE(ds, "NULL dataset");
+        DeviceGuard g(ds->device);
+        CallStream cs;
+        vdb::tensor_info(ds, n, sample_n, mean_norm, cs.s);
+        cs.sync();
+    });
+}
+uint32_t vdb_tq_j0(uint32_t k, uint64_t sample_total, uint64_t n_total) {
+    if (n_total == 0 || sample_total == 0) return 1;
+    return vdb::tensor_j0(k, sample_total, n_total);
+}
+int vdb_tq_begin_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, void* stream, vdb_tq** out) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && d_queries && out && nq > 0, "NULL argument");
+        DeviceGuard g(ds->device);
+        *out = vdb::tensor_begin(ds, d_queries, nq, (cudaStream_t)stream);
+    });
+}
+int vdb_tq_sample_dev(vdb_tq* tq, uint32_t j, uint64_t* d_keys) {
+    return guarded([&] {
+        VDB_REQUIRE(tq && d_keys, "NULL argument");
+        vdb::tensor_sample_keys(tq, j, d_keys);
+    });
+}
+int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm,
+                   float* d_tau) {
+    return guarded([&] {
+        VDB_REQUIRE(tq && d_keys_lists && d_tau && nlists > 0, "NULL argument");
+        vdb::tensor_tau(tq, d_keys_lists, nlists, j, j0, mean_norm, d_tau);
+    });
+}
+int vdb_tq_filter_dev(vdb_tq* tq, uint32_t k, const float* d_tau, uint64_t* d_keys, uint32_t* d_overflow) {
+    return guarded([&] {
+        VDB_REQUIRE(tq && d_tau && d_keys && d_overflow && k > 0, "NULL argument");
+        vdb::tensor_filter_keys(tq, k, 0, d_tau, d_keys, d_overflow, nullptr);
+    });
+}
+int vdb_tq_check_dev(vdb_tq* tq, const uint64_t* d_merged_keys, uint32_t k, uint64_t n_total, const float* d_tau,
+                     const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo) {
+    return guarded([&] {
+        VDB_REQUIRE(tq && d_merged_keys && d_tau && d_redo && d_nredo, "NULL argument");
+        vdb::tensor_check(tq, d_merged_keys, k, n_total, d_tau, d_overflow, d_redo, d_nredo);
+    });
+}
+int vdb_tq_end(vdb_tq* tq) {
+    return guarded([&] { vdb::tensor_end(tq); });
+}
+int vdb_flat_scan_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                           void* stream) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && (d_queries || nq == 0) && (d_keys || nq * (uint64_t)k == 0), "NULL argument");
+        DeviceGuard g(ds->device);
+        vdb::flat_scan_keys(ds, d_queries, nq, k, d_keys, (cudaStream_t)stream);
+    });
+}
+int vdb_merge_keys_to_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t k, uint64_t* d_out_keys,
+                               void* stream) {
+    return guarded([&] {
+        VDB_REQUIRE(nq * (uint64_t)k == 0 || (d_keys && d_out_keys), "NULL argument");
+        VDB_REQUIRE(nlists > 0, "nlists must be > 0");
+        vdb::launch_merge_keys(d_keys, nlists, nq, k, true, k, d_out_keys, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    });
+}
+int vdb_decode_keys_dev(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
+                        uint32_t* d_counts, void* stream) {
+    return guarded([&] {
+        VDB_REQUIRE(nq * (uint64_t)k == 0 || (d_keys && d_ids && d_dist), "NULL argument");
+        vdb::decode_keys(d_keys, nq, k, d_ids, d_dist, d_counts, (cudaStream_t)stream);
+    });
+}
+
 int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
                               uint64_t* d_out_keys, void* stream) {
     return guarded([&] {

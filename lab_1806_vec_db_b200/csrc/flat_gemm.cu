@@ -691,18 +691,26 @@ __global__ void rekey_dev_count_kernel(const float* __restrict__ dist, const uin
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
         keys[j] = make_key(dist[j], ids[j] + id_base);
 }
+__global__ void overflow_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap, uint32_t* __restrict__ flag) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) flag[q] = cnt[q] > cap ? 1u : 0u;
+}
 // completeness check; failing queries are appended to redo[]
 __global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, uint64_t n,
-                             const uint32_t* __restrict__ cnt, uint32_t cap, const float* __restrict__ tau,
+                             const uint32_t* __restrict__ overflow, const float* __restrict__ tau,
                              const float* __restrict__ qsq, uint32_t* __restrict__ redo, uint32_t* __restrict__ nredo) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint32_t need = (uint32_t)((uint64_t)k < n ? (uint64_t)k : n);
-    bool ok = cnt[q] <= cap && cnt[q] >= need;
-    if (ok) {
-        const float dk = key_dist(keys[(size_t)q * k + (need - 1)]);
-        const float slack = 2e-5f * (fabsf(dk) + qsq[q] + fabsf(tau[q]));
-        ok = (dk - qsq[q]) < tau[q] - slack;
+    bool ok = !(overflow && overflow[q]);
+    if (ok && need) {
+        const uint64_t kk = keys[(size_t)q * k + (need - 1)];
+        ok = kk != KEY_NONE;  // fewer than `need` candidates survived the filter
+        if (ok) {
+            const float dk = key_dist(kk);
+            const float slack = 2e-5f * (fabsf(dk) + qsq[q] + fabsf(tau[q]));
+            ok = (dk - qsq[q]) < tau[q] - slack;
+        }
     }
     if (!ok) redo[atomicAdd(nredo, 1u)] = q;
 }
@@ -730,135 +738,216 @@ uint64_t g_gemm_redo = 0;  // queries that needed the exact fallback (instrument
 uint64_t g_gemm_cands = 0; // candidates reranked (instrumentation)
 uint64_t g_gemm_queries = 0;
 
-void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
-                    cudaStream_t st) {
-    VDB_REQUIRE(flat_gemm_supported(ds, nq, k), "tensor-core Flat path: unsupported dataset/k");
+// ---- phases (also exported one by one for the row-sharded search, sharded.py) -------------------------------
+// j0: smallest order statistic of an `ns`-row uniform sample whose rank among the `n` rows is >= k with high
+// probability: P(rank < k) = P(Poisson(k*ns/n) >= j0) < 2e-3
+uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n) {
+    uint32_t j0 = 1;
+    const double x = (double)k * (double)ns / (double)n;
+    double term = exp(-x), cdf = term;
+    while (1.0 - cdf >= 2e-3 && j0 < 4096) {
+        term *= x / j0;
+        cdf += term;
+        ++j0;
+    }
+    return (uint32_t)std::min<uint64_t>(j0, ns);
+}
+
+}  // namespace vdb
+
+// per-call query context of the tensor path: padded fp32 copy (exact rerank), TF32-rounded copy (MMA operand),
+// ||q||^2, c||q|| and the TMA descriptor of the rounded copy
+struct vdb_tq {
+    const vdb_dataset* ds = nullptr;
+    const void* d_queries = nullptr;
+    uint32_t nq = 0, qpitch = 0;
+    cudaStream_t st = nullptr;
+    vdb::DevBuf qcopy, qround, qsq, qcm, cnt;
+    CUtensorMap mq;
+    uint32_t cap = 0;
+};
+
+namespace vdb {
+
+vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st) {
+    VDB_REQUIRE(flat_gemm_supported(ds, nq, 1), "tensor-core Flat path: unsupported dataset");
     ensure_side_arrays(ds, st);
-    const float* sqnorm = ds->d_sqnorm;
-    const float* rnorm = ds->d_lo;
     const uint32_t dim = ds->dim;
     // pruning-bound coefficient: both operands rounded to TF32 (2^-11 each, products then exact in fp32) plus
     // dim fp32 accumulation steps, times 2 for the -2 q.x term
     const float c = 2.0f * (ldexpf(1.0f, -10) * 1.001f + (float)dim * ldexpf(1.0f, -23));
-
-    // queries: contiguous [nq][dim] f32 (TMA needs a 16-byte aligned base and row pitch)
-    // dq: padded fp32 copy (exact rerank + norms); dq_tf32: the same rounded to TF32 (tensor-core operand)
-    const uint32_t qpitch = round_up(dim, 4u);
-    DevBuf qcopy((size_t)nq * qpitch * 4, st), qround((size_t)nq * qpitch * 4, st);
-    if (qpitch != dim) VDB_CUDA(cudaMemsetAsync(qcopy.p, 0, (size_t)nq * qpitch * 4, st));
-    VDB_CUDA(cudaMemcpy2DAsync(qcopy.p, (size_t)qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
-                               cudaMemcpyDeviceToDevice, st));
-    const float* dq = qcopy.as<float>();
-    round_tf32(dq, qround.as<float>(), (uint64_t)nq * qpitch, st);
-    DevBuf qsq((size_t)nq * 4, st), qcm((size_t)nq * 4, st), tau((size_t)nq * 4, st);
-    {
+    auto tq = new vdb_tq();
+    try {
+        tq->ds = ds;
+        tq->d_queries = d_queries;
+        tq->nq = nq;
+        tq->st = st;
+        tq->qpitch = round_up(dim, 4u);
+        const size_t qbytes = (size_t)nq * tq->qpitch * 4;
+        tq->qcopy = DevBuf(qbytes, st);
+        tq->qround = DevBuf(qbytes, st);
+        tq->qsq = DevBuf((size_t)nq * 4, st);
+        tq->qcm = DevBuf((size_t)nq * 4, st);
+        tq->cnt = DevBuf((size_t)nq * 4, st);
+        if (tq->qpitch != dim) VDB_CUDA(cudaMemsetAsync(tq->qcopy.p, 0, qbytes, st));
+        VDB_CUDA(cudaMemcpy2DAsync(tq->qcopy.p, (size_t)tq->qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
+                                   cudaMemcpyDeviceToDevice, st));
+        round_tf32(tq->qcopy.as<float>(), tq->qround.as<float>(), (uint64_t)nq * tq->qpitch, st);
         vdb_dataset qd = *ds;
-        qd.d_rows = const_cast<float*>(dq);
+        qd.d_rows = tq->qcopy.p;
         qd.n = nq;
-        qd.pitch = qpitch;
+        qd.pitch = tq->qpitch;
         qd.metric = VDB_L2SQR;
-        row_cache(&qd, qsq.as<float>(), st);
-        qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(qsq.as<float>(), nq, c, qcm.as<float>());
+        row_cache(&qd, tq->qsq.as<float>(), st);
+        qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qsq.as<float>(), nq, c, tq->qcm.as<float>());
         VDB_LAUNCHED();
+        tq->mq = make_map(tq->qround.as<float>(), dim, nq, (uint64_t)tq->qpitch * 4, GM);
+    } catch (...) {
+        delete tq;
+        throw;
     }
-    const CUtensorMap mq = make_map(qround.as<float>(), dim, nq, (uint64_t)qpitch * 4, GM);
+    return tq;
+}
+void tensor_end(vdb_tq* tq) { delete tq; }
+void tensor_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, cudaStream_t st) {
+    VDB_REQUIRE(flat_gemm_supported(ds, 1, 1), "tensor-core Flat path: unsupported dataset");
+    ensure_side_arrays(ds, st);
+    if (n) *n = ds->n;
+    if (sample_n) *sample_n = ds->sample_n;
+    if (mean_norm) *mean_norm = ds->mean_norm;
+}
 
-    // ---- thresholds from a strided sample ----
-    const uint64_t ns = ds->sample_n;
-    // j0: smallest order statistic of the sample whose rank in the shard is >= k with high probability:
-    // P(rank < k) = P(Poisson(k*ns/n) >= j0) < 2e-3
-    uint32_t j0 = 1;
-    {
-        const double x = (double)k * (double)ns / (double)ds->n;
-        double term = exp(-x), cdf = term;
-        while (1.0 - cdf >= 2e-3 && j0 < 4096) {
-            term *= x / j0;
-            cdf += term;
-            ++j0;
-        }
-    }
-    j0 = (uint32_t)std::min<uint64_t>(j0, ns);
-    const uint32_t j = j0;
-    const uint32_t cap = (uint32_t)next_pow2((uint32_t)std::min<uint64_t>(ds->n, std::max<uint64_t>(8ull * j * (ds->n / ns), 8192)));
+static GemmParams base_params(const vdb_tq* tq) {
     GemmParams p{};
-    p.nq = nq;
-    p.kblocks = ceil_div(dim, (uint32_t)GK);
-    p.sqnorm = sqnorm;
-    p.rnorm = rnorm;
-    p.qcm = qcm.as<float>();
-    {
-        DevBuf skeys((size_t)nq * ns * 8, st), jkeys((size_t)nq * j * 8, st);
-        const CUtensorMap ms = make_map(ds->d_sample, dim, ns, ds->pitch_bytes(), GN / gemm_ctas());
-        GemmParams ps = p;
-        ps.nrows = ns;
-        ps.row_stride = 1;
-        ps.sqnorm = ds->d_sample_sq;
-        ps.rnorm = ds->d_sample_rn;
-        ps.out_keys = skeys.as<uint64_t>();
-        launch_gemm(0, mq, ms, ps, st);
-        launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j, jkeys.as<uint64_t>(), nullptr, nullptr,
-                          nullptr, st);
-        tau_from_keys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j, j0, qcm.as<float>(), ds->mean_norm,
-                                                                tau.as<float>());
-        VDB_LAUNCHED();
-    }
-    // ---- filter pass over the whole shard ----
-    DevBuf cnt((size_t)nq * 4, st), cand((size_t)nq * cap * 8, st);
-    VDB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * 4, st));
+    p.nq = tq->nq;
+    p.kblocks = ceil_div(tq->ds->dim, (uint32_t)GK);
+    p.qcm = tq->qcm.as<float>();
+    return p;
+}
+
+// SAMPLE: this shard's j smallest sampled S' keys per query, [nq][j] ascending
+void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
+    const vdb_dataset* ds = tq->ds;
+    cudaStream_t st = tq->st;
+    const uint64_t ns = ds->sample_n;
+    VDB_REQUIRE(j >= 1 && j <= ns, "sample order statistic %u out of range (sample %llu)", j, (unsigned long long)ns);
+    DevBuf skeys((size_t)tq->nq * ns * 8, st);
+    const CUtensorMap ms = make_map(ds->d_sample, ds->dim, ns, ds->pitch_bytes(), GN / gemm_ctas());
+    GemmParams ps = base_params(tq);
+    ps.nrows = ns;
+    ps.row_stride = 1;
+    ps.sqnorm = ds->d_sample_sq;
+    ps.rnorm = ds->d_sample_rn;
+    ps.out_keys = skeys.as<uint64_t>();
+    launch_gemm(0, tq->mq, ms, ps, st);
+    launch_merge_keys(skeys.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
+}
+
+// TAU: merge `nlists` shards' [nq][j] sample keys (list-major) and set tau_q = S'_(j0) + margin
+void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm,
+                float* d_tau) {
+    cudaStream_t st = tq->st;
+    VDB_REQUIRE(j0 >= 1 && j0 <= (uint64_t)j * nlists, "j0 out of range");
+    const uint32_t jj = std::min<uint64_t>(j0, (uint64_t)j * nlists);
+    DevBuf merged((size_t)tq->nq * jj * 8, st);
+    launch_merge_keys(d_lists, nlists, tq->nq, j, true, jj, merged.as<uint64_t>(), nullptr, nullptr, nullptr, st);
+    tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj, tq->qcm.as<float>(),
+                                                                  mean_norm, d_tau);
+    VDB_LAUNCHED();
+}
+
+// FILTER + RERANK: rows with S' < tau_q -> exact distances -> this shard's k best keys per query.
+// d_overflow[q] = 1 when the candidate list of q overflowed (its result is then incomplete).
+void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
+                        uint32_t* d_overflow, uint64_t* d_cand_total) {
+    const vdb_dataset* ds = tq->ds;
+    cudaStream_t st = tq->st;
+    const uint32_t nq = tq->nq, dim = ds->dim;
+    const uint64_t ns = ds->sample_n;
+    const uint32_t cap = (uint32_t)next_pow2((uint32_t)std::min<uint64_t>(
+        ds->n, std::max<uint64_t>(8ull * std::max(j0_local_hint, 1u) * (ds->n / ns), 8192)));
+    tq->cap = cap;
+    DevBuf cand((size_t)nq * cap * 8, st);
+    VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
     {
         const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, ds->pitch_bytes(), GN / gemm_ctas());
-        GemmParams pf = p;
+        GemmParams pf = base_params(tq);
+        pf.sqnorm = ds->d_sqnorm;
+        pf.rnorm = ds->d_lo;
         pf.nrows = ds->n;
         pf.row_stride = 1;
-        pf.tau = tau.as<float>();
-        pf.cand_cnt = cnt.as<uint32_t>();
+        pf.tau = d_tau;
+        pf.cand_cnt = tq->cnt.as<uint32_t>();
         pf.cand = cand.as<uint64_t>();
         pf.cap = cap;
-        launch_gemm(1, mq, mx, pf, st);
+        launch_gemm(1, tq->mq, mx, pf, st);
     }
-    // ---- exact rerank of the candidates (compacted: only the valid pairs are touched) ----
+    // exact rerank of the candidates (compacted: only the valid pairs are touched)
     const uint64_t total = (uint64_t)nq * cap;  // capacity bound; the live count stays on the device
-    DevBuf off((size_t)(nq + 1) * 8, st);
-    {
-        DevBuf qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st),
-            keys2(total * 8, st);
-        cand_offsets_kernel<<<1, 1024, 0, st>>>(cnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
-        VDB_LAUNCHED();
-        cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, off.as<uint64_t>(),
-                                                 qidx.as<uint32_t>(), rid.as<uint32_t>());
-        VDB_LAUNCHED();
-        const uint64_t* d_total = off.as<uint64_t>() + nq;
-        exact_pair_distances_masked(ds, dq, qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
-                                    dist.as<float>(), st, d_total);
-        rekey_dev_count_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(),
-                                                                        (uint32_t)ds->id_base, d_total,
-                                                                        keys2.as<uint64_t>());
-        VDB_LAUNCHED();
-        launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st,
-                          off.as<uint64_t>());
-    }
-    // ---- completeness check + exact fallback ----
-    DevBuf redo((size_t)nq * 4, st), nredo(4, st);
-    VDB_CUDA(cudaMemsetAsync(nredo.p, 0, 4, st));
-    check_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(d_keys, nq, k, ds->n, cnt.as<uint32_t>(), cap, tau.as<float>(),
-                                                     qsq.as<float>(), redo.as<uint32_t>(), nredo.as<uint32_t>());
+    DevBuf off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st), keys2(total * 8, st);
+    cand_offsets_kernel<<<1, 1024, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
     VDB_LAUNCHED();
-    uint32_t h_redo = 0;
-    uint64_t h_cands = 0;
-    VDB_CUDA(cudaMemcpyAsync(&h_redo, nredo.p, 4, cudaMemcpyDeviceToHost, st));
-    VDB_CUDA(cudaMemcpyAsync(&h_cands, off.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToHost, st));
-    VDB_CUDA(cudaStreamSynchronize(st));
-    g_gemm_redo += h_redo;
-    g_gemm_cands += h_cands;
-    g_gemm_queries += nq;
-    if (h_redo) {
-        DevBuf rq((size_t)h_redo * dim * 4, st), rkeys((size_t)h_redo * k * 8, st);
-        gather_rows_kernel<<<h_redo, 128, 0, st>>>((const float*)d_queries, dim, redo.as<uint32_t>(), h_redo, rq.as<float>());
-        VDB_LAUNCHED();
-        flat_scan_keys(ds, rq.p, h_redo, k, rkeys.as<uint64_t>(), st);
-        scatter_keys_kernel<<<h_redo, 128, 0, st>>>(rkeys.as<uint64_t>(), k, redo.as<uint32_t>(), h_redo, d_keys);
+    cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, off.as<uint64_t>(),
+                                             qidx.as<uint32_t>(), rid.as<uint32_t>());
+    VDB_LAUNCHED();
+    const uint64_t* d_total = off.as<uint64_t>() + nq;
+    exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
+                                dist.as<float>(), st, d_total);
+    rekey_dev_count_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(),
+                                                                    (uint32_t)ds->id_base, d_total, keys2.as<uint64_t>());
+    VDB_LAUNCHED();
+    launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, off.as<uint64_t>());
+    if (d_overflow) {
+        overflow_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, d_overflow);
         VDB_LAUNCHED();
     }
+    if (d_cand_total) VDB_CUDA(cudaMemcpyAsync(d_cand_total, d_total, 8, cudaMemcpyDeviceToDevice, st));
+}
+
+// CHECK: the (merged) result of q is provably exact iff no shard overflowed and d_k - ||q||^2 < tau_q
+void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,
+                  const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo) {
+    VDB_CUDA(cudaMemsetAsync(d_nredo, 0, 4, tq->st));
+    check_kernel<<<ceil_div(tq->nq, 256u), 256, 0, tq->st>>>(d_keys, tq->nq, k, n_total, d_overflow, d_tau,
+                                                             tq->qsq.as<float>(), d_redo, d_nredo);
+    VDB_LAUNCHED();
+}
+
+void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                    cudaStream_t st) {
+    VDB_REQUIRE(flat_gemm_supported(ds, nq, k), "tensor-core Flat path: unsupported dataset/k");
+    vdb_tq* tq = tensor_begin(ds, d_queries, nq, st);
+    try {
+        const uint32_t j0 = tensor_j0(k, ds->sample_n, ds->n);
+        DevBuf jkeys((size_t)nq * j0 * 8, st), tau((size_t)nq * 4, st), overflow((size_t)nq * 4, st),
+            redo((size_t)nq * 4, st), nredo(4, st), ctotal(8, st);
+        tensor_sample_keys(tq, j0, jkeys.as<uint64_t>());
+        tensor_tau(tq, jkeys.as<uint64_t>(), 1, j0, j0, ds->mean_norm, tau.as<float>());
+        tensor_filter_keys(tq, k, j0, tau.as<float>(), d_keys, overflow.as<uint32_t>(), ctotal.as<uint64_t>());
+        tensor_check(tq, d_keys, k, ds->n, tau.as<float>(), overflow.as<uint32_t>(), redo.as<uint32_t>(),
+                     nredo.as<uint32_t>());
+        uint32_t h_redo = 0;
+        uint64_t h_cands = 0;
+        VDB_CUDA(cudaMemcpyAsync(&h_redo, nredo.p, 4, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaMemcpyAsync(&h_cands, ctotal.p, 8, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaStreamSynchronize(st));
+        g_gemm_redo += h_redo;
+        g_gemm_cands += h_cands;
+        g_gemm_queries += nq;
+        if (h_redo) {  // exact streaming scan for the queries whose candidate set could not be proven complete
+            DevBuf rq((size_t)h_redo * ds->dim * 4, st), rkeys((size_t)h_redo * k * 8, st);
+            gather_rows_kernel<<<h_redo, 128, 0, st>>>((const float*)d_queries, ds->dim, redo.as<uint32_t>(), h_redo,
+                                                       rq.as<float>());
+            VDB_LAUNCHED();
+            flat_scan_keys(ds, rq.p, h_redo, k, rkeys.as<uint64_t>(), st);
+            scatter_keys_kernel<<<h_redo, 128, 0, st>>>(rkeys.as<uint64_t>(), k, redo.as<uint32_t>(), h_redo, d_keys);
+            VDB_LAUNCHED();
+        }
+    } catch (...) {
+        tensor_end(tq);
+        throw;
+    }
+    tensor_end(tq);
 }
 
 // debug / test entry: S' keys of every (query, sampled row) pair, [nq][nrows] (mode 0 of the kernel)

@@ -22,6 +22,8 @@ struct vdb_pq {
 };
 
 // device mirror of IVFIndex<T> (reference src/index_algorithm/ivf_index.rs:34-47)
+struct vdb_tq;  // per-call query context of the tensor path (flat_gemm.cu)
+
 struct vdb_ivf {
     int device = 0;
     uint32_t nlist = 0, dim = 0;
@@ -91,5 +93,15 @@ void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, c
 void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
                      uint64_t* d_out_keys, cudaStream_t st);
 extern uint64_t g_gemm_redo, g_gemm_cands, g_gemm_queries;
+uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n);
+vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st);
+void tensor_end(vdb_tq* tq);
+void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys);
+void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm, float* d_tau);
+void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
+                        uint32_t* d_overflow, uint64_t* d_cand_total);
+void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,
+                  const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo);
+void tensor_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, cudaStream_t st);
 
 }  // namespace vdb

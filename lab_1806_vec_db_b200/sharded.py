@@ -38,34 +38,130 @@ def unpack_keys(keys):
 
 
 class ShardedFlatIndex:
-    """Flat index over this rank's row block; search results are global and identical on all ranks."""
+    """Flat index over this rank's row block; search results are global and identical on all ranks.
+
+    Large L2Sqr/f32 batches use the tensor-core phases of the library with GLOBAL thresholds: the shards'
+    sample scores are all-gathered so that every shard filters against the same tau_q and reranks only its share
+    of the ~k candidates (instead of its own ~750 per query); small batches use the exact streaming scan.
+    Collectives per batch: all-gather of [nq, j0] sample keys, all-gather of [nq, k] result keys, all-reduce of
+    the per-query overflow flags (tensor path only)."""
+
+    TENSOR_MIN_NQ = 256
 
     def __init__(self, vec_set, rank=0, world=1):
         self.vec_set = vec_set
         self.rank, self.world = rank, world
+        self._tensor = None  # (n_total, sample_total, mean_norm) once known; False if unsupported
 
+    # ---- helpers -------------------------------------------------------------------------------------------
+    def _tensor_info(self, dev):
+        if self._tensor is None:
+            import torch
+            lib = L.lib()
+            n, ns, mn = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
+            ok = (self.vec_set.dtype == np.float32 and self.vec_set.metric == L.L2SQR and
+                  lib.vdb_tq_info(self.vec_set._h, C.byref(n), C.byref(ns), C.byref(mn)) == L.OK)
+            t = torch.tensor([float(n.value), float(ns.value), 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+            m = torch.tensor([mn.value], dtype=torch.float32, device=dev)
+            if self.world > 1:
+                import torch.distributed as dist
+                okmin = t[2:3].clone()
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                dist.all_reduce(okmin, op=dist.ReduceOp.MIN)
+                dist.all_reduce(m, op=dist.ReduceOp.MAX)
+                ok = bool(okmin.item() > 0)
+            self._tensor = (int(t[0].item()), int(t[1].item()), float(m.item())) if ok else False
+        return self._tensor
+
+    def _gather(self, t):
+        import torch
+        if self.world == 1:
+            return t.unsqueeze(0)
+        import torch.distributed as dist
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    def _scan_keys(self, q, k, st):
+        import torch
+        keys = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+        L.check(L.lib().vdb_flat_scan_keys_dev(self.vec_set._h, C.c_void_p(q.data_ptr()), q.shape[0], k,
+                                               C.c_void_p(keys.data_ptr()), st))
+        return keys
+
+    def _merge_to_keys(self, allk, nq, k, st):
+        import torch
+        out = torch.empty((nq, k), dtype=torch.int64, device=allk.device)
+        L.check(L.lib().vdb_merge_keys_to_keys_dev(C.c_void_p(allk.data_ptr()), allk.shape[0], nq, k,
+                                                   C.c_void_p(out.data_ptr()), st))
+        return out
+
+    def _tensor_keys(self, q, k, st, info):
+        """Global [nq, k] keys through the tensor-core phases (identical on every rank)."""
+        import torch
+        lib = L.lib()
+        n_total, ns_total, mean_norm = info
+        nq, dev = q.shape[0], q.device
+        j0 = int(lib.vdb_tq_j0(k, ns_total, n_total))
+        j = max(1, min(j0, ns_total // self.world))
+        tq = C.c_void_p()
+        L.check(lib.vdb_tq_begin_dev(self.vec_set._h, C.c_void_p(q.data_ptr()), nq, st, C.byref(tq)))
+        try:
+            jkeys = torch.empty((nq, j), dtype=torch.int64, device=dev)
+            L.check(lib.vdb_tq_sample_dev(tq, j, C.c_void_p(jkeys.data_ptr())))
+            allj = self._gather(jkeys)
+            tau = torch.empty((nq,), dtype=torch.float32, device=dev)
+            L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(allj.data_ptr()), self.world, j, min(j0, j * self.world),
+                                       mean_norm, C.c_void_p(tau.data_ptr())))
+            keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            ovf = torch.empty((nq,), dtype=torch.int32, device=dev)
+            L.check(lib.vdb_tq_filter_dev(tq, k, C.c_void_p(tau.data_ptr()), C.c_void_p(keys.data_ptr()),
+                                          C.c_void_p(ovf.data_ptr())))
+            allk = self._gather(keys)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+            merged = self._merge_to_keys(allk, nq, k, st) if self.world > 1 else keys
+            redo = torch.empty((nq,), dtype=torch.int32, device=dev)
+            nredo = torch.zeros((1,), dtype=torch.int32, device=dev)
+            L.check(lib.vdb_tq_check_dev(tq, C.c_void_p(merged.data_ptr()), k, n_total, C.c_void_p(tau.data_ptr()),
+                                         C.c_void_p(ovf.data_ptr()), C.c_void_p(redo.data_ptr()),
+                                         C.c_void_p(nredo.data_ptr())))
+            nr = int(nredo.item())  # identical on every rank (same merged keys, same tau, reduced flags)
+            self.last_fallbacks = nr
+            if nr:
+                sel = torch.sort(redo[:nr].long()).values
+                rq = q.index_select(0, sel).contiguous()
+                rk = self._scan_keys(rq, k, st)
+                rall = self._gather(rk)
+                rmerged = self._merge_to_keys(rall, nr, k, st) if self.world > 1 else rk
+                merged.index_copy_(0, sel, rmerged)
+            return merged
+        finally:
+            lib.vdb_tq_end(tq)
+
+    # ---- search --------------------------------------------------------------------------------------------
     def knn_batch_dev(self, q, k):
         """q: torch CUDA tensor [nq, dim] (dataset dtype). Returns torch tensors (ids i64, dist f32, counts i32)."""
         import torch
         nq = q.shape[0]
         dev = q.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
         lib = L.lib()
-        L.check(lib.vdb_flat_knn_keys_dev(self.vec_set._h, C.c_void_p(q.data_ptr()), nq, k,
-                                          C.c_void_p(keys.data_ptr()), st))
-        if self.world > 1:
-            import torch.distributed as dist
-            allk = torch.empty((self.world, nq, k), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allk, keys)
-            nlists = self.world
-        else:
-            allk, nlists = keys, 1
         ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
         cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
-        L.check(lib.vdb_merge_keys_dev(C.c_void_p(allk.data_ptr()), nlists, nq, k, C.c_void_p(ids.data_ptr()),
-                                       C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), st))
+        if self.world == 1:
+            L.check(lib.vdb_flat_knn_dev(self.vec_set._h, C.c_void_p(q.data_ptr()), nq, k, C.c_void_p(ids.data_ptr()),
+                                         C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), st))
+            return ids, dd, cnt
+        info = self._tensor_info(dev) if (nq >= self.TENSOR_MIN_NQ and 1 <= k <= 1024) else False
+        if info:
+            merged = self._tensor_keys(q, k, st, info)
+        else:
+            merged = self._merge_to_keys(self._gather(self._scan_keys(q, k, st)), nq, k, st)
+        L.check(lib.vdb_decode_keys_dev(C.c_void_p(merged.data_ptr()), nq, k, C.c_void_p(ids.data_ptr()),
+                                        C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), st))
         return ids, dd, cnt
 
     def knn_batch(self, queries_pinned, k, out=None):
