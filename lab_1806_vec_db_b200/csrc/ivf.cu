@@ -10,6 +10,9 @@
 // gather at row granularity wastes no HBM traffic), one CTA per (query, slice of its visit sequence), warps
 // stream 8 rows at a time, partial top-k lists are merged per query. Ties at the k-th distance are resolved
 // by (distance, id) instead of the reference's visit order (documented in DESIGN.md; within the parity rule).
+#include <algorithm>
+#include <vector>
+
 #include "index.cuh"
 #include "topk.cuh"
 
@@ -159,6 +162,184 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
         p.partial[((size_t)q * p.splits + split) * p.K + j] = topk.seg(0)[j];
 }
 
+// ---- list-major batched scan -----------------------------------------------------------------------------------
+// For a batch of queries the same list is probed by many queries. Work items are (list, group of <= LQ queries probing
+// it, row range): the item's rows are streamed ONCE for all its queries (the K1 inner loop with gathered row ids), so
+// the HBM traffic drops from sum_q(rows visited by q) to sum_lists(ceil(Q_list / 8) * list rows). Every item writes a
+// k-best list per query slot; a per-query index of those partial lists drives the final merge.
+constexpr int LQ = 8;   // queries per item
+constexpr int LR = 4;   // rows per warp step
+
+struct IvfItem {
+    uint64_t row_begin;   // offset into members[]
+    uint32_t nrows;
+    uint32_t nq_valid;
+    uint32_t qid[LQ];
+};
+
+struct IvfListParams {
+    const uint8_t* rows;
+    uint64_t pitch_bytes;
+    uint32_t nvec, nit;
+    const float* q;          // query tiles [nq][qstride]
+    uint32_t qstride;
+    const float* qcache;
+    const IvfItem* items;
+    const uint32_t* members;
+    uint32_t K, P, limit, sync_every;
+    uint32_t id_base;
+    uint64_t* partial;       // [nitems][LQ][K]
+};
+
+template <int METRIC, int PL>
+__global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const IvfListParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int NQ = LQ, R = LR, V = NQ * R;
+    constexpr int SH = 5 - Log2<V>::value, SHR = 5 - Log2<R>::value;
+    const IvfItem item = p.items[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qs4 = p.qstride >> 2, plane4 = p.nit * 32;
+    float4* qs = reinterpret_cast<float4*>(smem);
+    uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)NQ * p.qstride * 4);
+    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
+    for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x) {
+        const uint32_t qi = i / qs4, e = i - qi * qs4;
+        qs[i] = qi < item.nq_valid ? reinterpret_cast<const float4*>(p.q + (size_t)item.qid[qi] * p.qstride)[e]
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    topk.init();
+    const int pidx = lane >> SH;
+    const int my_r = pidx / NQ, my_q = pidx % NQ;
+    const bool emitter = (lane & ((1 << SH) - 1)) == 0 && my_q < (int)item.nq_valid;
+    float qn = 0.f;
+    if (METRIC == VDB_COSINE && my_q < (int)item.nq_valid) qn = p.qcache[item.qid[my_q]];
+    const uint32_t groups = ceil_div<uint32_t>(item.nrows, R);
+    const uint32_t iters = ceil_div<uint32_t>(groups, IVF_WARPS);
+    const uint32_t* mem = p.members + item.row_begin;
+
+    bool want = false;
+    for (uint32_t gi = 0; gi < iters; ++gi) {
+        const uint32_t g = gi * IVF_WARPS + warp;
+        uint32_t rid[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t pos = g * R + r;
+            rid[r] = pos < item.nrows ? mem[pos] : 0xffffffffu;
+        }
+        float acc[V], xx[R];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) xx[r] = 0.f;
+        if (g < groups) {
+            uint4 nxt[R], cur[R];
+            auto load = [&](uint32_t it) {
+                const uint32_t c = it * 32 + lane;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    nxt[r] = (c < p.nvec && rid[r] != 0xffffffffu)
+                                 ? ldg_stream_u4(p.rows + (uint64_t)rid[r] * p.pitch_bytes + (size_t)c * 16)
+                                 : make_uint4(0u, 0u, 0u, 0u);
+            };
+            load(0);
+            for (uint32_t it = 0; it < p.nit; ++it) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) cur[r] = nxt[r];
+                if (it + 1 < p.nit) load(it + 1);
+                const uint32_t c = it * 32 + lane;
+#pragma unroll
+                for (int pl = 0; pl < PL; ++pl) {
+                    float4 x[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if constexpr (PL == 1) x[r] = ivf_u4_as_f4(cur[r]);
+                        else x[r] = ivf_bytes_as_f4(pl == 0 ? cur[r].x : (pl == 1 ? cur[r].y : (pl == 2 ? cur[r].z : cur[r].w)));
+                    }
+                    if (METRIC == VDB_COSINE) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            xx[r] = fmaf(x[r].x, x[r].x, xx[r]);
+                            xx[r] = fmaf(x[r].y, x[r].y, xx[r]);
+                            xx[r] = fmaf(x[r].z, x[r].z, xx[r]);
+                            xx[r] = fmaf(x[r].w, x[r].w, xx[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int qi = 0; qi < NQ; ++qi) {
+                        const float4 qv = qs[(size_t)qi * qs4 + (size_t)pl * plane4 + c];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            float a = acc[r * NQ + qi];
+                            if (METRIC == VDB_L2SQR) {
+                                const float d0 = x[r].x - qv.x, d1 = x[r].y - qv.y, d2 = x[r].z - qv.z, d3 = x[r].w - qv.w;
+                                a = fmaf(d0, d0, a);
+                                a = fmaf(d1, d1, a);
+                                a = fmaf(d2, d2, a);
+                                a = fmaf(d3, d3, a);
+                            } else {
+                                a = fmaf(x[r].x, qv.x, a);
+                                a = fmaf(x[r].y, qv.y, a);
+                                a = fmaf(x[r].z, qv.z, a);
+                                a = fmaf(x[r].w, qv.w, a);
+                            }
+                            acc[r * NQ + qi] = a;
+                        }
+                    }
+                }
+            }
+        }
+        float tot = warp_reduce_scatter<V>(acc, lane);
+        if (METRIC == VDB_COSINE) {
+            const float xs = warp_reduce_scatter<R>(xx, lane);
+            const float xr = __shfl_sync(0xffffffffu, xs, my_r << SHR);
+            tot = 1.0f - tot / fmaxf(sqrtf(xr) * qn, 1e-10f);
+        }
+        uint32_t my_id = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r == my_r) my_id = rid[r];
+        if (emitter && my_id != 0xffffffffu) {
+            const uint64_t key = make_key(tot, p.id_base + my_id);
+            if (key < topk.tau(my_q)) want |= topk.push(my_q, key);
+        }
+        if ((gi + 1) % p.sync_every == 0) {
+            topk.maybe_flush(want);
+            want = false;
+        }
+    }
+    topk.final_flush();
+    for (uint32_t i = threadIdx.x; i < NQ * p.K; i += blockDim.x) {
+        const uint32_t qi = i / p.K, j = i - qi * p.K;
+        p.partial[((size_t)blockIdx.x * NQ + qi) * p.K + j] = qi < item.nq_valid ? topk.seg(qi)[j] : KEY_NONE;
+    }
+}
+
+// final merge: query q owns the partial lists plist[poff[q] .. poff[q+1]) (each K keys)
+__global__ void __launch_bounds__(256) ivf_merge_kernel(const uint64_t* __restrict__ partial, const uint64_t* __restrict__ poff,
+                                                        const uint32_t* __restrict__ plist, uint32_t K, uint32_t P,
+                                                        uint32_t limit, uint64_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* tk = reinterpret_cast<uint64_t*>(smem);
+    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + P), K, P, 1, limit};
+    topk.init();
+    const uint32_t q = blockIdx.x;
+    const uint64_t b = poff[q], e = poff[q + 1];
+    const uint64_t total = (e - b) * K;
+    const uint64_t rounds = (total + blockDim.x - 1) / blockDim.x;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t i = r * blockDim.x + threadIdx.x;
+        bool want = false;
+        if (i < total) {
+            const uint64_t l = i / K, j = i - l * K;
+            const uint64_t key = partial[(uint64_t)plist[b + l] * K + j];
+            if (key < topk.tau(0)) want = topk.push(0, key);
+        }
+        topk.maybe_flush(want);
+    }
+    topk.final_flush();
+    for (uint32_t j = threadIdx.x; j < K; j += blockDim.x) out[(size_t)q * K + j] = topk.seg(0)[j];
+}
+
 // [nq][nlist] exact distances -> keys (distance, list id)
 __global__ void probe_keys_kernel(const float* __restrict__ dist, uint64_t count, uint32_t nlist,
                                   uint64_t* __restrict__ keys) {
@@ -214,6 +395,103 @@ void ivf_destroy(vdb_ivf* ivf) {
     delete ivf;
 }
 
+static void ivf_list_major(const vdb_dataset* ds, const vdb_ivf* ivf, const QueryTile& qt, const uint64_t* d_probes,
+                           uint32_t nq, uint32_t nprobe, uint32_t k, uint64_t* d_keys, cudaStream_t st) {
+    // probe table to the host (nq * nprobe keys), grouping on the host, item table back to the device
+    std::vector<uint64_t> probes((size_t)nq * nprobe);
+    VDB_CUDA(cudaMemcpyAsync(probes.data(), d_probes, probes.size() * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<uint64_t> off(ivf->nlist + 1);
+    VDB_CUDA(cudaMemcpyAsync(off.data(), ivf->d_offsets, off.size() * 8, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaStreamSynchronize(st));
+    std::vector<std::vector<uint32_t>> by_list(ivf->nlist);
+    for (uint32_t q = 0; q < nq; ++q)
+        for (uint32_t j = 0; j < nprobe; ++j) {
+            const uint64_t pk = probes[(size_t)q * nprobe + j];
+            if (pk != KEY_NONE) by_list[key_id(pk)].push_back(q);
+        }
+    // row-range size: enough items to fill the GPU a few times, rows per item a multiple of the warp tile
+    uint64_t work = 0;  // sum over (list, query group) of rows
+    for (uint32_t l = 0; l < ivf->nlist; ++l) work += ceil_div<uint64_t>(by_list[l].size(), LQ) * (off[l + 1] - off[l]);
+    const uint64_t target_items = (uint64_t)sm_count() * 16;
+    uint32_t range = (uint32_t)std::max<uint64_t>(IVF_WARPS * LR * 4, round_up<uint64_t>(ceil_div<uint64_t>(work, target_items), IVF_WARPS * LR));
+    std::vector<IvfItem> items;
+    std::vector<std::vector<uint32_t>> qlists(nq);  // partial-list indices per query
+    for (uint32_t l = 0; l < ivf->nlist; ++l) {
+        const uint64_t len = off[l + 1] - off[l];
+        if (len == 0) continue;
+        const auto& qv = by_list[l];
+        for (size_t c = 0; c < qv.size(); c += LQ) {
+            const uint32_t nv = (uint32_t)std::min<size_t>(LQ, qv.size() - c);
+            for (uint64_t r0 = 0; r0 < len; r0 += range) {
+                IvfItem it{};
+                it.row_begin = off[l] + r0;
+                it.nrows = (uint32_t)std::min<uint64_t>(range, len - r0);
+                it.nq_valid = nv;
+                for (uint32_t s = 0; s < nv; ++s) {
+                    it.qid[s] = qv[c + s];
+                    qlists[qv[c + s]].push_back((uint32_t)(items.size() * LQ + s));
+                }
+                items.push_back(it);
+            }
+        }
+    }
+    std::vector<uint64_t> poff(nq + 1, 0);
+    for (uint32_t q = 0; q < nq; ++q) poff[q + 1] = poff[q] + qlists[q].size();
+    std::vector<uint32_t> plist(poff[nq]);
+    for (uint32_t q = 0; q < nq; ++q) std::copy(qlists[q].begin(), qlists[q].end(), plist.begin() + poff[q]);
+    if (items.empty()) {
+        VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
+        return;
+    }
+    DevBuf d_items(items.size() * sizeof(IvfItem), st), d_poff(poff.size() * 8, st), d_plist(std::max<size_t>(4, plist.size() * 4), st),
+        partial(items.size() * LQ * (size_t)k * 8, st);
+    VDB_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(IvfItem), cudaMemcpyHostToDevice, st));
+    VDB_CUDA(cudaMemcpyAsync(d_poff.p, poff.data(), poff.size() * 8, cudaMemcpyHostToDevice, st));
+    if (!plist.empty()) VDB_CUDA(cudaMemcpyAsync(d_plist.p, plist.data(), plist.size() * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t period = 64;
+    const uint32_t P = topk_segment_size(k, period);
+    const size_t smem = (size_t)LQ * qt.qstride * 4 + TopkSmem::bytes(LQ, P);
+    VDB_REQUIRE(smem <= 200 * 1024, "IVF scan: dim=%u / k=%u do not fit in shared memory", ds->dim, k);
+    IvfListParams p{};
+    p.rows = (const uint8_t*)ds->d_rows;
+    p.pitch_bytes = ds->pitch_bytes();
+    p.nvec = qt.nvec;
+    p.nit = qt.nit;
+    p.q = qt.q.as<float>();
+    p.qstride = qt.qstride;
+    p.qcache = qt.qcache.as<float>();
+    p.items = d_items.as<IvfItem>();
+    p.members = ivf->d_members;
+    p.K = k;
+    p.P = P;
+    p.limit = P - k - period;
+    p.sync_every = std::max(1u, period / (IVF_WARPS * LR));
+    p.id_base = (uint32_t)ds->id_base;
+    p.partial = partial.as<uint64_t>();
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024)
+            VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ProfScope prof("ivf_scan", st);
+        kern<<<(uint32_t)items.size(), IVF_THREADS, smem, st>>>(p);
+        VDB_LAUNCHED();
+    };
+    if (ds->dtype == VDB_F32) {
+        if (ds->metric == VDB_L2SQR) go(ivf_list_scan_kernel<VDB_L2SQR, 1>);
+        else go(ivf_list_scan_kernel<VDB_COSINE, 1>);
+    } else {
+        if (ds->metric == VDB_L2SQR) go(ivf_list_scan_kernel<VDB_L2SQR, 4>);
+        else go(ivf_list_scan_kernel<VDB_COSINE, 4>);
+    }
+    const uint32_t PM = topk_segment_size(k, 256);
+    const size_t smem_m = TopkSmem::bytes(1, PM);
+    VDB_REQUIRE(smem_m <= 200 * 1024, "IVF merge: k=%u too large", k);
+    if (smem_m > 48 * 1024)
+        VDB_CUDA(cudaFuncSetAttribute(ivf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+    ivf_merge_kernel<<<nq, 256, smem_m, st>>>(partial.as<uint64_t>(), d_poff.as<uint64_t>(), d_plist.as<uint32_t>(), k, PM,
+                                              PM - k - 256, d_keys);
+    VDB_LAUNCHED();
+}
+
 void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
                   uint32_t n_probes, uint64_t* d_keys, cudaStream_t st) {
     VDB_REQUIRE(n_probes > 0, "The number of probes should be greater than 0.");
@@ -234,6 +512,10 @@ void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queri
                       nullptr, st);
     // 2. list scan
     QueryTile qt = prepare_queries(ds, d_queries, nq, st);
+    if (nq >= 4) {
+        ivf_list_major(ds, ivf, qt, probes.as<uint64_t>(), nq, nprobe, k, d_keys, st);
+        return;
+    }
     const uint32_t period = IVF_WARPS * IVF_R;
     const uint32_t P = topk_segment_size(k, period);
     const size_t smem = (size_t)qt.qstride * 4 + TopkSmem::bytes(1, P) + 16 + (size_t)round_up(nprobe + 1, 2u) * 4 +
