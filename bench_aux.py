@@ -124,9 +124,11 @@ def main():
         cfg = V.PQConfig(4, 240, "l2sqr", 10_000, 20, 1e-6)
         train = np.ascontiguousarray(base_host[rng.permutation(args.n)[:10_000]])
         books = []
+        train_dev = V.DeviceVecSet(train, "l2sqr")
         for lo, hi in V.pq_groups(DIM, 240):
-            km = V.KMeans.from_vec_set(train, V.KMeansConfig(16, 20, 1e-6, "l2sqr", (lo, hi)), rng)
+            km = V.KMeans.from_vec_set(train_dev, V.KMeansConfig(16, 20, 1e-6, "l2sqr", (lo, hi)), rng)
             books.append(km.centroids.reshape(-1))
+        train_dev.close()
         books = np.concatenate(books)
         t_train = time.perf_counter() - t0
         t0 = time.perf_counter()

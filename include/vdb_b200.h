@@ -118,6 +118,17 @@ int vdb_kmeans_assign_ds(const vdb_dataset* ds, const void* centroids, uint32_t 
 int vdb_kmeans_train(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
                      void* centroids, uint32_t k, uint32_t sel_lo, uint32_t sel_hi, uint32_t max_iter,
                      float tol, uint32_t* iters);
+/* Same as vdb_kmeans_train with the training rows already resident in a dataset handle (PQ trains one k-means
+ * per group on the same sample: pq_table.rs:154-172). */
+int vdb_kmeans_train_ds(const vdb_dataset* ds, void* centroids, uint32_t k, uint32_t sel_lo, uint32_t sel_hi,
+                        uint32_t max_iter, float tol, uint32_t* iters);
+/* k-means++ initialisation (src/distance/k_means.rs:61-87) on device-resident rows. The random draws stay with the
+ * caller: uniforms[0] picks the first row (index = floor(u * n)); round r = 1..k-1 uses uniforms[2r-1] for the
+ * weighted pick (probability proportional to w[i] = min over chosen c of d(c, v_i)) and uniforms[2r] for the
+ * uniform fallback the reference draws eagerly (k_means.rs:80-82; used when the weights are all zero/invalid).
+ * uniforms has 2k-1 entries in [0,1). centroids receives [k, sel_hi-sel_lo] rows of the dataset dtype. */
+int vdb_kmeans_pp_init_ds(const vdb_dataset* ds, uint32_t k, uint32_t sel_lo, uint32_t sel_hi, const double* uniforms,
+                          void* centroids);
 /* k-means++ weight update w[i] = min(w[i], d(c, rows[i][sel])) (src/distance/k_means.rs:75-77). */
 int vdb_kmeans_pp_weights(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
                           const void* centroid, uint32_t sel_lo, uint32_t sel_hi, float* weights);

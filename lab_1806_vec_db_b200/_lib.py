@@ -49,6 +49,8 @@ SIGNATURES = {
     "vdb_kmeans_assign": (i32, [vp, u64, u32, i32, i32, vp, u32, u32, u32, vp]),
     "vdb_kmeans_assign_ds": (i32, [vp, vp, u32, u32, u32, vp]),
     "vdb_kmeans_train": (i32, [vp, u64, u32, i32, i32, vp, u32, u32, u32, u32, f32, vp]),
+    "vdb_kmeans_train_ds": (i32, [vp, vp, u32, u32, u32, u32, f32, vp]),
+    "vdb_kmeans_pp_init_ds": (i32, [vp, u32, u32, u32, vp, vp]),
     "vdb_kmeans_pp_weights": (i32, [vp, u64, u32, i32, i32, vp, u32, u32, vp]),
     "vdb_pq_groups": (i32, [u32, u32, vp]),
     "vdb_pq_create": (i32, [vp, vp, u32, u32, vp, vp]),

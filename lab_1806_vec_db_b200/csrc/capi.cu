@@ -1,6 +1,8 @@
 // capi.cu — the extern "C" boundary declared in include/vdb_b200.h.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include "dataset.cuh"

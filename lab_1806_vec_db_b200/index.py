@@ -190,26 +190,23 @@ class KMeansConfig(NamedTuple):
     selected: tuple = None
 
 
+def _as_device_rows(rows, dist):
+    """Training rows as a DeviceVecSet (uploaded once; PQ trains one k-means per group on the same sample)."""
+    if isinstance(rows, DeviceVecSet):
+        return rows
+    return DeviceVecSet(np.ascontiguousarray(rows), dist)
+
+
 def k_means_init(rows, config: KMeansConfig, rng):
-    """k-means++ (k_means.rs:61-87). The draws consume the CALLER's rng (numpy Generator here; the
-    reference's ChaCha12 stream cannot be reproduced), the weight update runs on the GPU."""
-    rows = np.ascontiguousarray(rows)
-    n, dim = rows.shape
-    lo, hi = config.selected if config.selected is not None else (0, dim)
-    first = int(rng.integers(0, n))
-    cents = [rows[first, lo:hi].copy()]
-    w = np.full(n, np.inf, np.float32)
-    lib = L.lib()
-    for _ in range(1, config.k):
-        c = np.ascontiguousarray(cents[-1])
-        L.check(lib.vdb_kmeans_pp_weights(L.ptr(rows), n, dim, L.dtype_code(rows), L.metric_code(config.dist),
-                                          L.ptr(c), lo, hi, L.ptr(w)))
-        fallback = int(rng.integers(0, n))  # eager unwrap_or argument (k_means.rs:80-82)
-        ww = w.astype(np.float64)
-        ok = np.isfinite(ww).all() and (ww >= 0).all() and ww.sum() > 0
-        pick = int(rng.choice(n, p=ww / ww.sum())) if ok else fallback
-        cents.append(rows[pick, lo:hi].copy())
-    return np.ascontiguousarray(np.stack(cents))
+    """k-means++ (k_means.rs:61-87). The draws consume the CALLER's rng (numpy Generator here; the reference's
+    ChaCha12 stream cannot be reproduced): 2k-1 uniforms drive the first pick, the weighted picks and the eagerly
+    drawn fallbacks; the weight updates run on the GPU over device-resident rows."""
+    vs = _as_device_rows(rows, config.dist)
+    lo, hi = config.selected if config.selected is not None else (0, vs.dim)
+    u = np.ascontiguousarray(rng.random(2 * config.k - 1), dtype=np.float64)
+    cent = np.zeros((config.k, hi - lo), vs.dtype)
+    L.check(L.lib().vdb_kmeans_pp_init_ds(vs._h, config.k, lo, hi, L.ptr(u), L.ptr(cent)))
+    return cent
 
 
 class KMeans:
@@ -221,19 +218,20 @@ class KMeans:
 
     @classmethod
     def from_vec_set(cls, rows, config: KMeansConfig, rng=None, init_centroids=None):
-        rows = np.ascontiguousarray(rows)
+        """KMeans::from_vec_set (k_means.rs:95-162). `rows` may be a host array or a DeviceVecSet."""
         if config.k <= 0:
             raise ValueError("The number of clusters should be greater than 0.")
-        n, dim = rows.shape
+        vs = _as_device_rows(rows, config.dist)
+        dim = vs.dim
         lo, hi = config.selected if config.selected is not None else (0, dim)
         if hi > dim:
             raise ValueError("The selected range should be in the range [0, vec_set.dim())")
         if init_centroids is None:
-            init_centroids = k_means_init(rows, config, rng if rng is not None else np.random.default_rng())
-        cent = np.array(init_centroids, dtype=rows.dtype, order="C", copy=True)
+            init_centroids = k_means_init(vs, config, rng if rng is not None else np.random.default_rng())
+        cent = np.array(init_centroids, dtype=vs.dtype, order="C", copy=True)
         iters = C.c_uint32(0)
-        L.check(L.lib().vdb_kmeans_train(L.ptr(rows), n, dim, L.dtype_code(rows), L.metric_code(config.dist),
-                                         L.ptr(cent), config.k, lo, hi, config.max_iter, config.tol, C.byref(iters)))
+        L.check(L.lib().vdb_kmeans_train_ds(vs._h, L.ptr(cent), config.k, lo, hi, config.max_iter, config.tol,
+                                            C.byref(iters)))
         self = cls(config, cent)
         self.iterations = int(iters.value)
         return self
@@ -305,10 +303,12 @@ class PQTable:
             perm = rng.permutation(len(rows_host))[:config.k_means_size]  # VecSet::random_sample (vec_set.rs:154-163)
             train = np.ascontiguousarray(rows_host[perm])
         books = []
+        train_dev = DeviceVecSet(train, config.dist)  # the sample is uploaded once for all m groups
         for lo, hi in pq_groups(rows_host.shape[1], config.m):
-            km = KMeans.from_vec_set(train, KMeansConfig(1 << config.n_bits, config.k_means_max_iter,
-                                                         config.k_means_tol, config.dist, (lo, hi)), rng)
+            km = KMeans.from_vec_set(train_dev, KMeansConfig(1 << config.n_bits, config.k_means_max_iter,
+                                                             config.k_means_tol, config.dist, (lo, hi)), rng)
             books.append(km.centroids.reshape(-1))
+        train_dev.close()
         return cls(vec_set, config, np.concatenate(books))
 
     def create_lookup(self, queries):
