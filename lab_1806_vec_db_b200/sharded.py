@@ -46,7 +46,7 @@ class ShardedFlatIndex:
     Collectives per batch: all-gather of [nq, j0] sample keys, all-gather of [nq, k] result keys, all-reduce of
     the per-query overflow flags (tensor path only)."""
 
-    TENSOR_MIN_NQ = 256
+    TENSOR_MIN_NQ = 12
 
     def __init__(self, vec_set, rank=0, world=1):
         self.vec_set = vec_set
