@@ -102,3 +102,50 @@ def test_tensor_path_adversarial_ties_and_duplicates(oracle):
         L.check(lib.vdb_flat_set_path(0))
     assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
     assert tens[0][0, :3].tolist() == [5, 1000, 1001]
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(70_000, 12, 40, 6), (66_000, 13, 13, 1), (80_000, 100, 300, 1024),
+                                        (65_536, 960, 12, 10), (100_000, 36, 1000, 50)])
+def test_auto_path_edge_shapes_match_scan(n, dim, nq, k):
+    """Auto path (tensor pruning from 12 queries up) on odd shapes: tiny / ragged dims (zero-filled TMA boxes),
+    k = 1 and k = 1024, the smallest supported shard. Must be bit-identical to the forced exact scan."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(n + dim)
+    base = rng.random((n, dim), dtype=np.float32)
+    q = rng.random((nq, dim), dtype=np.float32)
+    q[0] = base[17]
+    idx = V.FlatIndex.from_vec_set(base, "l2sqr")
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, k)
+        L.check(lib.vdb_flat_set_path(0))
+        q0 = C.c_uint64(0)
+        lib.vdb_flat_gemm_stats(C.byref(q0), None, None)
+        auto = idx.knn_batch(q, k)
+        q1 = C.c_uint64(0)
+        lib.vdb_flat_gemm_stats(C.byref(q1), None, None)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert q1.value - q0.value == nq, "the auto path did not take the tensor route"
+    assert (auto[2] == scan[2]).all()
+    assert (auto[0] == scan[0]).all(), float((auto[0] == scan[0]).mean())
+    assert (auto[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    assert auto[0][0, 0] == 17 and auto[1][0, 0] == 0.0
+
+
+def test_auto_path_keeps_scan_for_unsupported_cases(oracle):
+    """cosine and u8 rows have no tensor route: the auto path must silently use the exact scan (same results)."""
+    import lab_1806_vec_db_b200 as V
+    rng = np.random.default_rng(3)
+    base = rng.random((70_000, 64), dtype=np.float32)
+    q = rng.random((20, 64), dtype=np.float32)
+    got = V.FlatIndex.from_vec_set(base, "cosine").knn_batch(q, 5)
+    want = oracle.flat_knn(base, q, 5, "cosine", 8)
+    assert_knn_parity(base, q, "cosine", got, want, oracle)
+    b8 = rng.integers(0, 256, (70_000, 32), dtype=np.uint8)
+    q8 = rng.integers(0, 256, (20, 32), dtype=np.uint8)
+    got = V.FlatIndex.from_vec_set(b8, "l2sqr").knn_batch(q8, 5)
+    want = oracle.flat_knn(b8, q8, 5, "l2sqr", 8)
+    assert_knn_parity(b8, q8, "l2sqr", got, want, oracle)
