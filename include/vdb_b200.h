@@ -157,6 +157,14 @@ int vdb_pq_knn_dev(const vdb_dataset* ds, const vdb_pq* pq, const void* d_querie
                    uint32_t k, uint32_t ef, uint64_t* d_ids, float* d_dist, uint32_t* d_counts,
                    void* stream);
 
+/* Row-sharded knn_pq: (1) every shard's max(ef,k) best codes by (ADC, global id) as packed keys
+ * [nq, kk]; (2) after an all-gather + vdb_merge_keys_to_keys_dev to the GLOBAL top-kk, every shard reranks the
+ * candidates it owns (others become KEY_NONE) into [nq, k] keys; (3) all-gather + merge gives the reference result. */
+int vdb_pq_adc_keys_dev(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t kk,
+                        uint64_t* d_keys, void* stream);
+int vdb_pq_rerank_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, const uint64_t* d_cand_keys,
+                           uint32_t kk, uint32_t k, uint64_t* d_keys, void* stream);
+
 /* ---- IVF ------------------------------------------------------------------------------------ */
 /* IVFIndex::from_vec_set after training (src/index_algorithm/ivf_index.rs:88-106): assigns every
  * row to its nearest centroid and builds the inverted lists (members ascending). `assign_out`
@@ -218,6 +226,10 @@ int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint
 uint64_t vdb_flat_gemm_fallbacks(void);
 /* Cumulative counters of the tensor path: queries served, candidates reranked, queries re-run exactly. */
 int vdb_flat_gemm_stats(uint64_t* queries, uint64_t* candidates, uint64_t* fallbacks);
+
+/* Row-sharded IVF: this shard's [nq, k] packed keys (merge the shards' lists with vdb_merge_keys_dev). */
+int vdb_ivf_knn_keys_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
+                         uint32_t n_probes, uint64_t* d_keys, void* stream);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the calling process since load. */

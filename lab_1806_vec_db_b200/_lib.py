@@ -60,6 +60,9 @@ SIGNATURES = {
     "vdb_pq_adc_all": (i32, [vp, vp, u32, vp]),
     "vdb_pq_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
     "vdb_pq_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
+    "vdb_pq_adc_keys_dev": (i32, [vp, vp, vp, u32, u32, vp, vp]),
+    "vdb_pq_rerank_keys_dev": (i32, [vp, vp, u32, vp, u32, u32, vp, vp]),
+    "vdb_ivf_knn_keys_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
     "vdb_ivf_create": (i32, [vp, vp, u32, vp, vp]),
     "vdb_ivf_destroy": (i32, [vp]),
     "vdb_ivf_lists": (i32, [vp, vp, vp]),

@@ -514,10 +514,12 @@ void pq_adc_all(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uin
 
 // keys -> (query index, local row, valid) for the rerank
 __global__ void keys_to_pairs_kernel(const uint64_t* __restrict__ keys, uint64_t count, uint32_t per_q, uint32_t id_base,
-                                     uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid, uint8_t* __restrict__ valid) {
+                                     uint64_t n, uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid,
+                                     uint8_t* __restrict__ valid) {
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[j];
-        const bool ok = k != KEY_NONE;
+        // candidates owned by another row shard (ids outside [id_base, id_base + n)) are skipped here
+        const bool ok = k != KEY_NONE && key_id(k) >= id_base && (uint64_t)(key_id(k) - id_base) < n;
         qidx[j] = (uint32_t)(j / per_q);
         rid[j] = ok ? key_id(k) - id_base : 0u;
         valid[j] = ok;
@@ -551,7 +553,7 @@ void rerank_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cons
     if (count == 0 || k == 0) return;
     DevBuf qidx(count * 4, st), rid(count * 4, st), valid(count, st), dist(count * 4, st), keys2(count * 8, st);
     const uint32_t grid = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), 4096);
-    keys_to_pairs_kernel<<<grid, 256, 0, st>>>(d_cand, count, kk, (uint32_t)ds->id_base, qidx.as<uint32_t>(),
+    keys_to_pairs_kernel<<<grid, 256, 0, st>>>(d_cand, count, kk, (uint32_t)ds->id_base, ds->n, qidx.as<uint32_t>(),
                                                rid.as<uint32_t>(), valid.as<uint8_t>());
     VDB_LAUNCHED();
     exact_pair_distances(ds, d_queries, qidx.as<uint32_t>(), rid.as<uint32_t>(), count, dist.as<float>(), st);
@@ -559,6 +561,19 @@ void rerank_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cons
                                        valid.as<uint8_t>(), count, keys2.as<uint64_t>());
     VDB_LAUNCHED();
     launch_merge_keys(keys2.as<uint64_t>(), 1, nq, kk, false, k, d_keys, nullptr, nullptr, nullptr, st);
+}
+
+// this shard's max(ef,k) best codes per query by (ADC distance, global id): [nq][kk]
+void pq_adc_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t kk, uint64_t* d_keys,
+                 cudaStream_t st) {
+    VDB_REQUIRE(ds->metric == pq->metric, "Distance algorithm mismatch.");
+    VDB_REQUIRE(ds->n == pq->n && ds->dim == pq->dim && ds->dtype == pq->dtype,
+                "PQ table was built for a different vector set (it must be rebuilt after add/delete)");
+    if (nq == 0 || kk == 0) return;
+    const uint32_t tab = pq->m * pq->kc;
+    DevBuf lut((size_t)nq * tab * 4, st), qcache((size_t)nq * 4, st);
+    pq_lut(pq, d_queries, nq, lut.as<float>(), qcache.as<float>(), st);
+    adc_scan(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, d_keys, nullptr, st);
 }
 
 void pq_knn_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,

@@ -179,3 +179,76 @@ class ShardedFlatIndex:
         out[2].copy_(cnt, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return out
+
+
+class ShardedIVFIndex:
+    """IVF over row shards: centroids replicated, every rank holds its slice of every list (members ascending),
+    per-rank probe scans are merged by (distance, global id) after one all-gather."""
+
+    def __init__(self, ivf_index, rank=0, world=1):
+        self.ivf, self.rank, self.world = ivf_index, rank, world
+
+    def knn_with_ef_batch_dev(self, q, k, n_probes):
+        import torch
+        nq, dev = q.shape[0], q.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        lib = L.lib()
+        keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        L.check(lib.vdb_ivf_knn_keys_dev(self.ivf.vec_set._h, self.ivf._h, C.c_void_p(q.data_ptr()), nq, k, n_probes,
+                                         C.c_void_p(keys.data_ptr()), st))
+        return _gather_merge_decode(keys, nq, k, self.world, st)
+
+
+class ShardedPQFlatIndex:
+    """FlatIndex::knn_pq over row shards, identical to the unsharded call: the GLOBAL max(ef,k) best codes by ADC
+    distance are selected first (all-gather + merge), then every rank reranks the candidates it owns."""
+
+    def __init__(self, vec_set, pq_table, rank=0, world=1):
+        self.vec_set, self.pq, self.rank, self.world = vec_set, pq_table, rank, world
+
+    def knn_pq_batch_dev(self, q, k, ef):
+        import torch
+        nq, dev = q.shape[0], q.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        lib = L.lib()
+        kk = max(ef, k)
+        adc = torch.empty((nq, kk), dtype=torch.int64, device=dev)
+        L.check(lib.vdb_pq_adc_keys_dev(self.vec_set._h, self.pq._h, C.c_void_p(q.data_ptr()), nq, kk,
+                                        C.c_void_p(adc.data_ptr()), st))
+        cand = _gather_merge_keys(adc, nq, kk, self.world, st)
+        keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        L.check(lib.vdb_pq_rerank_keys_dev(self.vec_set._h, C.c_void_p(q.data_ptr()), nq, C.c_void_p(cand.data_ptr()), kk,
+                                           k, C.c_void_p(keys.data_ptr()), st))
+        return _gather_merge_decode(keys, nq, k, self.world, st)
+
+
+def _gather(t, world):
+    import torch
+    if world == 1:
+        return t.unsqueeze(0)
+    import torch.distributed as dist
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous())
+    return out
+
+
+def _gather_merge_keys(keys, nq, k, world, st):
+    import torch
+    if world == 1:
+        return keys
+    allk = _gather(keys, world)
+    out = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
+    L.check(L.lib().vdb_merge_keys_to_keys_dev(C.c_void_p(allk.data_ptr()), world, nq, k, C.c_void_p(out.data_ptr()), st))
+    return out
+
+
+def _gather_merge_decode(keys, nq, k, world, st):
+    import torch
+    dev = keys.device
+    allk = _gather(keys, world)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    L.check(L.lib().vdb_merge_keys_dev(C.c_void_p(allk.data_ptr()), world, nq, k, C.c_void_p(ids.data_ptr()),
+                                       C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), st))
+    return ids, dd, cnt

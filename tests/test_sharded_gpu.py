@@ -44,6 +44,26 @@ for k in (10, 100):
     ids, dd, cnt = idx.knn_batch_dev(qd[:5].contiguous(), k)   # small batch: sharded exact scan
     assert (ids.cpu().numpy() == want[0][:5].astype(np.int64)).all(), ("scan", k, rank)
     assert (dd.cpu().numpy().view(np.uint32) == want[1][:5].view(np.uint32)).all()
+# ---- sharded IVF and PQ: identical to the unsharded calls ----
+from lab_1806_vec_db_b200.sharded import ShardedIVFIndex, ShardedPQFlatIndex
+L.check(L.lib().vdb_flat_set_path(0))
+cent = np.ascontiguousarray(base[np.random.default_rng(1).permutation(n)[:32]])
+ivf_full = V.IVFIndex(full.vec_set, cent)
+sivf = ShardedIVFIndex(V.IVFIndex(vs, cent), rank, world)
+for nprobe in (1, 4, 32):
+    want = ivf_full.knn_with_ef_batch(q[:64], 10, nprobe)
+    ids, dd, cnt = sivf.knn_with_ef_batch_dev(qd[:64].contiguous(), 10, nprobe)
+    assert (ids.cpu().numpy() == want[0].astype(np.int64)).all(), ("ivf", nprobe, rank)
+    assert (dd.cpu().numpy().view(np.uint32) == want[1].view(np.uint32)).all()
+books = np.concatenate([np.ascontiguousarray(base[100:116, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(dim, 240)])
+cfg = V.PQConfig(4, 240, "l2sqr")
+pq_full = V.PQTable(full.vec_set, cfg, books)
+spq = ShardedPQFlatIndex(vs, V.PQTable(vs, cfg, books), rank, world)
+for k, ef in ((10, 240), (10, 5), (3, 600)):
+    want = full.knn_pq_batch(q[:32], k, ef, pq_full)
+    ids, dd, cnt = spq.knn_pq_batch_dev(qd[:32].contiguous(), k, ef)
+    assert (ids.cpu().numpy() == want[0].astype(np.int64)).all(), ("pq", k, ef, rank)
+    assert (dd.cpu().numpy().view(np.uint32) == want[1].view(np.uint32)).all()
 pin = torch.from_numpy(q).pin_memory()
 out = idx.knn_batch(pin, 10)
 assert (out[0].numpy() == full.knn_batch(q, 10)[0].astype(np.int64)).all()
