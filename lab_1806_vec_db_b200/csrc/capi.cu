@@ -299,7 +299,7 @@ static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t 
     bool tensor = false;
     if (path == 2) {
         VDB_REQUIRE(vdb::flat_gemm_supported(ds, nq, k),
-                    "tensor-core Flat path needs f32 L2Sqr rows, dim %% 4 == 0 and k <= 1024");
+                    "tensor-core Flat path needs f32 rows, at least 65536 of them, and k <= 1024");
         tensor = true;
     } else if (path == 0) {
         tensor = nq >= 12 && vdb::flat_gemm_supported(ds, nq, k);  // measured crossover: one tensor pass (any nq <= 256) costs ~1.1 ms, one 8-query scan pass ~0.95 ms

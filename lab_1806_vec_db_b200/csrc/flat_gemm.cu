@@ -214,7 +214,9 @@ struct GemmParams {
     uint32_t nslabs;
     const float* sqnorm;    // [n] ||x||^2
     const float* rnorm;     // [n] ||x||
-    const float* qcm;       // [nq] c * ||q||   (error-bound coefficient times the query norm)
+    const float* qcm;       // [nq] L2Sqr: c * ||q|| (pruning-bound coefficient times the query norm); cosine: 1/||q||
+    const float* qnorm;     // [nq] cosine: ||q||
+    float kc;               // cosine: 1 - (bound on the cosine-distance error)
     // mode 0: store keys (S', sample index) to out_keys[nq][nrows]
     uint64_t* out_keys;
     // mode 1: filter
@@ -225,7 +227,7 @@ struct GemmParams {
     uint32_t* work_counter; // dynamic item scheduler (zeroed before the launch)
 };
 
-template <int MODE, int CTAS>
+template <int MODE, int CTAS, int METRIC>
 __global__ void __launch_bounds__(G_THREADS, 1)
 flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
     using Cfg = GemmCfg<CTAS>;
@@ -382,6 +384,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint32_t q = qt * GM + threadIdx.x;
             const bool qok = q < p.nq;
             const float cq = qok ? p.qcm[q] : 0.f;
+            const float qn = (METRIC == VDB_COSINE && qok) ? p.qnorm[q] : 0.f;
             float tau = 0.f;
             if (MODE == 1) tau = qok ? p.tau[q] : __uint_as_float(0xff800000u);  // -inf: nothing passes
             for (uint32_t t = t0; t < t1; ++t) {
@@ -407,8 +410,16 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float dot = __uint_as_float(v[j]);
-                            // S' = ||x||^2 - c||q|| ||x|| - 2 q.x
-                            const float s = fmaf(-2.0f, dot, fmaf(-cq, rn[c0 + j], sq[c0 + j]));
+                            float s;
+                            if (METRIC == VDB_L2SQR) {
+                                // S' = ||x||^2 - c||q|| ||x|| - 2 q.x   (lower bound of d - ||q||^2)
+                                s = fmaf(-2.0f, dot, fmaf(-cq, rn[c0 + j], sq[c0 + j]));
+                            } else {
+                                // S' = (1 - bound) - q.x / (||q|| ||x||)  (lower bound of the cosine distance); rows whose
+                                // norm product falls under the reference's 1e-10 clamp are always kept (sq = 1/||x||)
+                                s = fmaf(-(cq * sq[c0 + j]), dot, p.kc);
+                                if (qn * rn[c0 + j] < 2e-10f) s = __uint_as_float(0xff800000u);
+                            }
                             if (MODE == 0) {
                                 const uint64_t brow = (uint64_t)t * GN + c0 + j;
                                 if (brow < p.nrows) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(s, (uint32_t)brow);
@@ -529,6 +540,11 @@ __global__ void gather_sample_kernel(const float* __restrict__ rows_tf32, const 
     }
 }
 
+__global__ void rinv_kernel(const float* __restrict__ rn, uint64_t n, float* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = rn[i] > 0.f ? 1.0f / rn[i] : 0.f;
+}
+
 static std::mutex g_side_mu;
 // ||x||^2 and ||x|| per row, cached on the (logically const) dataset handle
 static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
@@ -552,10 +568,15 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
     VDB_CUDA(cudaMalloc(&ds->d_sample_sq, (size_t)ds->sample_n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_sample_rn, (size_t)ds->sample_n * 4));
     vdb_dataset tmp = *ds;
-    tmp.metric = VDB_L2SQR;
-    row_cache(&tmp, ds->d_sqnorm, st);
     tmp.metric = VDB_COSINE;
-    row_cache(&tmp, ds->d_lo, st);
+    row_cache(&tmp, ds->d_lo, st);  // ||x||
+    if (ds->metric == VDB_L2SQR) {
+        tmp.metric = VDB_L2SQR;
+        row_cache(&tmp, ds->d_sqnorm, st);  // ||x||^2
+    } else {
+        rinv_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(ds->n, 256), 65535), 256, 0, st>>>(ds->d_lo, ds->n, ds->d_sqnorm);
+        VDB_LAUNCHED();  // 1/||x|| (0 for zero rows)
+    }
     gather_sample_kernel<<<ds->sample_n, 256, 0, st>>>(ds->d_tf32, ds->d_sqnorm, ds->d_lo, ds->n, ds->pitch, ds->sample_n,
                                                        ds->d_sample, ds->d_sample_sq, ds->d_sample_rn);
     VDB_LAUNCHED();
@@ -574,10 +595,10 @@ static int gemm_ctas() {
     return v == 1 ? 1 : 2;
 }
 
-template <int MODE, int CTAS>
+template <int MODE, int CTAS, int METRIC>
 static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st) {
     using Cfg = GemmCfg<CTAS>;
-    auto kern = flat_gemm_kernel<MODE, CTAS>;
+    auto kern = flat_gemm_kernel<MODE, CTAS, METRIC>;
     static thread_local bool configured = false;
     if (!configured) {
         VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -612,13 +633,18 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
     VDB_LAUNCHED();
 }
 
-static void launch_gemm(int mode, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st) {
-    if (gemm_ctas() == 2) {
-        if (mode == 0) launch_gemm_t<0, 2>(mq, mx, p, st);
-        else launch_gemm_t<1, 2>(mq, mx, p, st);
-    } else {
-        if (mode == 0) launch_gemm_t<0, 1>(mq, mx, p, st);
-        else launch_gemm_t<1, 1>(mq, mx, p, st);
+static void launch_gemm(int mode, int metric, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p,
+                        cudaStream_t st) {
+    const int sel = (gemm_ctas() == 2 ? 4 : 0) | (mode ? 2 : 0) | (metric == VDB_COSINE ? 1 : 0);
+    switch (sel) {
+        case 0: launch_gemm_t<0, 1, VDB_L2SQR>(mq, mx, p, st); break;
+        case 1: launch_gemm_t<0, 1, VDB_COSINE>(mq, mx, p, st); break;
+        case 2: launch_gemm_t<1, 1, VDB_L2SQR>(mq, mx, p, st); break;
+        case 3: launch_gemm_t<1, 1, VDB_COSINE>(mq, mx, p, st); break;
+        case 4: launch_gemm_t<0, 2, VDB_L2SQR>(mq, mx, p, st); break;
+        case 5: launch_gemm_t<0, 2, VDB_COSINE>(mq, mx, p, st); break;
+        case 6: launch_gemm_t<1, 2, VDB_L2SQR>(mq, mx, p, st); break;
+        default: launch_gemm_t<1, 2, VDB_COSINE>(mq, mx, p, st); break;
     }
 }
 
@@ -628,13 +654,18 @@ __global__ void qcm_kernel(const float* __restrict__ qsq, uint32_t nq, float c, 
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) qcm[q] = c * sqrtf(qsq[q]);
 }
+// cosine: qcm = 1/||q|| with ||q|| exactly as the streaming scan computes it (prepare_queries)
+__global__ void qinv_kernel(const float* __restrict__ qn, uint32_t nq, float* __restrict__ qinv) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) qinv[q] = qn[q] > 0.f ? 1.0f / qn[q] : 0.f;
+}
 // tau_q = (j0-th smallest sampled S') + margin. j0 is chosen so that the k-th best S' of the shard is <= S'_(j0)
 // with high probability; because S <= S' + 2 c||q|| ||x||, the margin (2.5 x the pruning bound at the mean row
 // norm) keeps the k-th EXACT distance inside the threshold. The check kernel verifies it per query afterwards.
 __global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, uint32_t j0,
                                      const float* __restrict__ qcm, float mean_norm, float* __restrict__ tau) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) tau[q] = key_dist(keys[(size_t)q * j + (j0 - 1)]) + 2.5f * qcm[q] * mean_norm;
+    if (q < nq) tau[q] = key_dist(keys[(size_t)q * j + (j0 - 1)]) + 2.5f * (qcm ? qcm[q] * mean_norm : mean_norm);
 }
 // exclusive scan of min(cnt, cap) over the queries (one block; nq is at most a few 100k)
 __global__ void __launch_bounds__(1024) cand_offsets_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
@@ -699,6 +730,7 @@ __global__ void overflow_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, u
 __global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, uint64_t n,
                              const uint32_t* __restrict__ overflow, const float* __restrict__ tau,
                              const float* __restrict__ qsq, uint32_t* __restrict__ redo, uint32_t* __restrict__ nredo) {
+    // qsq == nullptr: cosine (scores bound the distance itself); else L2Sqr (scores bound d - ||q||^2)
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint32_t need = (uint32_t)((uint64_t)k < n ? (uint64_t)k : n);
@@ -708,8 +740,9 @@ __global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uin
         ok = kk != KEY_NONE;  // fewer than `need` candidates survived the filter
         if (ok) {
             const float dk = key_dist(kk);
-            const float slack = 2e-5f * (fabsf(dk) + qsq[q] + fabsf(tau[q]));
-            ok = (dk - qsq[q]) < tau[q] - slack;
+            const float shift = qsq ? qsq[q] : 0.f;
+            const float slack = 2e-5f * (fabsf(dk) + shift + fabsf(tau[q]));
+            ok = (dk - shift) < tau[q] - slack;
         }
     }
     if (!ok) redo[atomicAdd(nredo, 1u)] = q;
@@ -730,7 +763,7 @@ __global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, uint32_t k
 constexpr uint32_t G_MAX_K = 1024;
 
 bool flat_gemm_supported(const vdb_dataset* ds, uint32_t nq, uint32_t k) {
-    return ds->dtype == VDB_F32 && ds->metric == VDB_L2SQR && k >= 1 && k <= G_MAX_K && ds->n >= 65536 &&
+    return ds->dtype == VDB_F32 && k >= 1 && k <= G_MAX_K && ds->n >= 65536 &&
            nq >= 1 && ((uintptr_t)ds->d_rows & 15) == 0;
 }
 
@@ -763,6 +796,8 @@ struct vdb_tq {
     uint32_t nq = 0, qpitch = 0;
     cudaStream_t st = nullptr;
     vdb::DevBuf qcopy, qround, qsq, qcm, cnt;
+    vdb::QueryTile qtile;   // cosine: ||q|| exactly as the streaming scan computes it
+    float kc = 0.f, cbound = 0.f;
     CUtensorMap mq;
     uint32_t cap = 0;
 };
@@ -793,14 +828,23 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
         VDB_CUDA(cudaMemcpy2DAsync(tq->qcopy.p, (size_t)tq->qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
                                    cudaMemcpyDeviceToDevice, st));
         round_tf32(tq->qcopy.as<float>(), tq->qround.as<float>(), (uint64_t)nq * tq->qpitch, st);
-        vdb_dataset qd = *ds;
-        qd.d_rows = tq->qcopy.p;
-        qd.n = nq;
-        qd.pitch = tq->qpitch;
-        qd.metric = VDB_L2SQR;
-        row_cache(&qd, tq->qsq.as<float>(), st);
-        qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qsq.as<float>(), nq, c, tq->qcm.as<float>());
-        VDB_LAUNCHED();
+        if (ds->metric == VDB_L2SQR) {
+            vdb_dataset qd = *ds;
+            qd.d_rows = tq->qcopy.p;
+            qd.n = nq;
+            qd.pitch = tq->qpitch;
+            qd.metric = VDB_L2SQR;
+            row_cache(&qd, tq->qsq.as<float>(), st);
+            qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qsq.as<float>(), nq, c, tq->qcm.as<float>());
+            VDB_LAUNCHED();
+        } else {
+            // cosine distance error <= (c/2) from the contraction + the reciprocal products of the epilogue
+            tq->cbound = 0.5f * c + 1e-6f;
+            tq->kc = 1.0f - tq->cbound;
+            tq->qtile = prepare_queries(ds, d_queries, nq, st);
+            qinv_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qtile.qcache.as<float>(), nq, tq->qcm.as<float>());
+            VDB_LAUNCHED();
+        }
         tq->mq = make_map(tq->qround.as<float>(), dim, nq, (uint64_t)tq->qpitch * 4, GM);
     } catch (...) {
         delete tq;
@@ -822,6 +866,8 @@ static GemmParams base_params(const vdb_tq* tq) {
     p.nq = tq->nq;
     p.kblocks = ceil_div(tq->ds->dim, (uint32_t)GK);
     p.qcm = tq->qcm.as<float>();
+    p.qnorm = tq->ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr;
+    p.kc = tq->kc;
     return p;
 }
 
@@ -839,7 +885,7 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     ps.sqnorm = ds->d_sample_sq;
     ps.rnorm = ds->d_sample_rn;
     ps.out_keys = skeys.as<uint64_t>();
-    launch_gemm(0, tq->mq, ms, ps, st);
+    launch_gemm(0, ds->metric, tq->mq, ms, ps, st);
     launch_merge_keys(skeys.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
 }
 
@@ -851,8 +897,10 @@ void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j
     const uint32_t jj = std::min<uint64_t>(j0, (uint64_t)j * nlists);
     DevBuf merged((size_t)tq->nq * jj * 8, st);
     launch_merge_keys(d_lists, nlists, tq->nq, j, true, jj, merged.as<uint64_t>(), nullptr, nullptr, nullptr, st);
-    tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj, tq->qcm.as<float>(),
-                                                                  mean_norm, d_tau);
+    const bool cosine = tq->ds->metric == VDB_COSINE;
+    tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj,
+                                                                  cosine ? nullptr : tq->qcm.as<float>(),
+                                                                  cosine ? tq->cbound : mean_norm, d_tau);
     VDB_LAUNCHED();
 }
 
@@ -880,7 +928,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         pf.cand_cnt = tq->cnt.as<uint32_t>();
         pf.cand = cand.as<uint64_t>();
         pf.cap = cap;
-        launch_gemm(1, tq->mq, mx, pf, st);
+        launch_gemm(1, ds->metric, tq->mq, mx, pf, st);
     }
     // exact rerank of the candidates (compacted: only the valid pairs are touched)
     const uint64_t total = (uint64_t)nq * cap;  // capacity bound; the live count stays on the device
@@ -892,7 +940,8 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     VDB_LAUNCHED();
     const uint64_t* d_total = off.as<uint64_t>() + nq;
     exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
-                                dist.as<float>(), st, d_total);
+                                dist.as<float>(), st, d_total,
+                                ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr);
     rekey_dev_count_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(),
                                                                     (uint32_t)ds->id_base, d_total, keys2.as<uint64_t>());
     VDB_LAUNCHED();
@@ -909,7 +958,8 @@ void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_tot
                   const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo) {
     VDB_CUDA(cudaMemsetAsync(d_nredo, 0, 4, tq->st));
     check_kernel<<<ceil_div(tq->nq, 256u), 256, 0, tq->st>>>(d_keys, tq->nq, k, n_total, d_overflow, d_tau,
-                                                             tq->qsq.as<float>(), d_redo, d_nredo);
+                                                             tq->ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(),
+                                                             d_redo, d_nredo);
     VDB_LAUNCHED();
 }
 
@@ -953,8 +1003,9 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
 // debug / test entry: S' keys of every (query, sampled row) pair, [nq][nrows] (mode 0 of the kernel)
 void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
                      uint64_t* d_out_keys, cudaStream_t st) {
-    VDB_REQUIRE(ds->dtype == VDB_F32 && ds->dim % 4 == 0 && ((uintptr_t)d_queries & 15) == 0 && row_stride >= 1,
-                "flat_gemm_store: f32 rows, dim %% 4 == 0 and aligned queries only");
+    VDB_REQUIRE(ds->dtype == VDB_F32 && ds->metric == VDB_L2SQR && ds->dim % 4 == 0 && ((uintptr_t)d_queries & 15) == 0 &&
+                    row_stride >= 1,
+                "flat_gemm_store: f32 L2Sqr rows, dim %% 4 == 0 and aligned queries only");
     ensure_side_arrays(ds, st);
     const uint64_t ns = ds->n / row_stride;
     DevBuf qsq((size_t)nq * 4, st), qcm((size_t)nq * 4, st);
@@ -977,7 +1028,7 @@ void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
     p.out_keys = d_out_keys;
     const CUtensorMap mq = make_map(d_queries, ds->dim, nq, (uint64_t)ds->dim * 4, GM);
     const CUtensorMap ms = make_map(ds->d_rows, ds->dim, ns, ds->pitch_bytes() * row_stride, GN / gemm_ctas());
-    launch_gemm(0, mq, ms, p, st);
+    launch_gemm(0, VDB_L2SQR, mq, ms, p, st);
 }
 
 }  // namespace vdb

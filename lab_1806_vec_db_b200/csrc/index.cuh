@@ -54,7 +54,7 @@ void exact_pair_distances(const vdb_dataset* ds, const void* d_queries, const ui
                           const uint32_t* d_rid, uint64_t npairs, float* d_out, cudaStream_t st);
 void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, uint32_t qpitch, const uint32_t* d_qidx,
                                  const uint32_t* d_rid, const uint8_t* d_valid, uint64_t npairs, float* d_out,
-                                 cudaStream_t st, const uint64_t* d_npairs = nullptr);
+                                 cudaStream_t st, const uint64_t* d_npairs = nullptr, const float* d_qnorm = nullptr);
 void cached_pair_distances(const vdb_dataset* ds, const void* d_queries, const float* d_qcache,
                            const float* d_rowcache, const uint32_t* d_qidx, const uint32_t* d_rid,
                            uint64_t npairs, float* d_out, cudaStream_t st);

@@ -9,7 +9,7 @@
 
 namespace vdb {
 
-enum PairMode { PM_L2 = 0, PM_COSINE = 1, PM_DOT = 2, PM_L2_CACHED = 3, PM_COSINE_CACHED = 4, PM_SQNORM = 5, PM_NORM = 6, PM_L2_SCANORDER = 7 };
+enum PairMode { PM_L2 = 0, PM_COSINE = 1, PM_DOT = 2, PM_L2_CACHED = 3, PM_COSINE_CACHED = 4, PM_SQNORM = 5, PM_NORM = 6, PM_L2_SCANORDER = 7, PM_COS_SCANORDER = 8 };
 
 struct PairParams {
     const void* A;           // rows of A
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
         const TA* a = (const TA*)p.A + ia * p.strideA;
         const TB* b = (const TB*)p.B + ib * p.strideB;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        if (MODE == PM_L2_SCANORDER) {
+        if (MODE == PM_L2_SCANORDER || MODE == PM_COS_SCANORDER) {
             // same per-lane element order (float4 chunk c = it*32 + lane) and the same xor-butterfly as the
             // streaming scan kernel (flat_scan.cu), so both Flat paths return bit-identical distances
             if (p.vec4) {
@@ -64,11 +64,22 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
                         const uint32_t c = c0 + u * 32 + lane;
                         if (c < nvec) {
                             const float4 q = __ldg(a4 + c);
-                            const float d0 = xb[u].x - q.x, d1 = xb[u].y - q.y, d2 = xb[u].z - q.z, d3 = xb[u].w - q.w;
-                            s0 = fmaf(d0, d0, s0);
-                            s0 = fmaf(d1, d1, s0);
-                            s0 = fmaf(d2, d2, s0);
-                            s0 = fmaf(d3, d3, s0);
+                            if (MODE == PM_L2_SCANORDER) {
+                                const float d0 = xb[u].x - q.x, d1 = xb[u].y - q.y, d2 = xb[u].z - q.z, d3 = xb[u].w - q.w;
+                                s0 = fmaf(d0, d0, s0);
+                                s0 = fmaf(d1, d1, s0);
+                                s0 = fmaf(d2, d2, s0);
+                                s0 = fmaf(d3, d3, s0);
+                            } else {
+                                s0 = fmaf(xb[u].x, q.x, s0);
+                                s0 = fmaf(xb[u].y, q.y, s0);
+                                s0 = fmaf(xb[u].z, q.z, s0);
+                                s0 = fmaf(xb[u].w, q.w, s0);
+                                s1 = fmaf(xb[u].x, xb[u].x, s1);
+                                s1 = fmaf(xb[u].y, xb[u].y, s1);
+                                s1 = fmaf(xb[u].z, xb[u].z, s1);
+                                s1 = fmaf(xb[u].w, xb[u].w, s1);
+                            }
                         }
                     }
                 }
@@ -78,8 +89,14 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
                 for (uint32_t i = 0; i < 4; ++i) {
                     const uint32_t e = c * 4 + i;
                     if (e < p.dim) {
-                        const float d = (float)b[e] - (float)a[e];
-                        s0 = fmaf(d, d, s0);
+                        const float xv = (float)b[e], qv = (float)a[e];
+                        if (MODE == PM_L2_SCANORDER) {
+                            const float d = xv - qv;
+                            s0 = fmaf(d, d, s0);
+                        } else {
+                            s0 = fmaf(xv, qv, s0);
+                            s1 = fmaf(xv, xv, s1);
+                        }
                     }
                 }
             }
@@ -105,6 +122,7 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
                 s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                 s2 += __shfl_xor_sync(0xffffffffu, s2, o);
             }
+            if (MODE == PM_COS_SCANORDER) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         }
         if (lane == 0) {
             float r = s0;
@@ -112,6 +130,8 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
             if (MODE == PM_L2_CACHED) r = (p.cacheA[ia] + p.cacheB[ib]) - 2.0f * s0;
             if (MODE == PM_COSINE_CACHED) r = 1.0f - s0 / fmaxf(p.cacheA[ia] * p.cacheB[ib], 1e-10f);
             if (MODE == PM_NORM) r = sqrtf(s0);
+            // the streaming scan's cosine: 1 - dot / max(sqrt(x.x) * ||q||, 1e-10) with ||q|| from prepare_queries
+            if (MODE == PM_COS_SCANORDER) r = 1.0f - s0 / fmaxf(sqrtf(s1) * p.cacheA[ia], 1e-10f);
             p.out[j] = r;
         }
     }
@@ -129,6 +149,7 @@ static void launch_pairs_t(int mode, const PairParams& p, cudaStream_t st) {
         case PM_COSINE_CACHED: pair_dist_kernel<TA, TB, PM_COSINE_CACHED><<<grid, 256, 0, st>>>(p); break;
         case PM_SQNORM: pair_dist_kernel<TA, TB, PM_SQNORM><<<grid, 256, 0, st>>>(p); break;
         case PM_L2_SCANORDER: pair_dist_kernel<TA, TB, PM_L2_SCANORDER><<<grid, 256, 0, st>>>(p); break;
+        case PM_COS_SCANORDER: pair_dist_kernel<TA, TB, PM_COS_SCANORDER><<<grid, 256, 0, st>>>(p); break;
         default: pair_dist_kernel<TA, TB, PM_NORM><<<grid, 256, 0, st>>>(p); break;
     }
     VDB_LAUNCHED();
@@ -179,7 +200,7 @@ void exact_pair_distances(const vdb_dataset* ds, const void* d_queries, const ui
 // same with an explicit query pitch and a validity mask (K2 rerank)
 void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, uint32_t qpitch, const uint32_t* d_qidx,
                                  const uint32_t* d_rid, const uint8_t* d_valid, uint64_t npairs, float* d_out,
-                                 cudaStream_t st, const uint64_t* d_npairs) {
+                                 cudaStream_t st, const uint64_t* d_npairs, const float* d_qnorm) {
     PairParams p{};
     p.A = d_queries;
     p.strideA = qpitch;
@@ -192,10 +213,12 @@ void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, u
     p.npairs = npairs;
     p.npairs_dev = d_npairs;
     p.out = d_out;
-    const bool scan_order = ds->metric == VDB_L2SQR && ds->dtype == VDB_F32;
+    const bool scan_order = ds->dtype == VDB_F32 && (ds->metric == VDB_L2SQR || d_qnorm != nullptr);
+    p.cacheA = d_qnorm;
     p.vec4 = scan_order && ds->dim % 4 == 0 && qpitch % 4 == 0 && ds->pitch % 4 == 0 &&
              ((uintptr_t)d_queries & 15) == 0 && ((uintptr_t)ds->d_rows & 15) == 0;
-    launch_pairs(scan_order ? PM_L2_SCANORDER : (ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE), false, ds->dtype, p, st);
+    const int so_mode = ds->metric == VDB_L2SQR ? PM_L2_SCANORDER : PM_COS_SCANORDER;
+    launch_pairs(scan_order ? so_mode : (ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE), false, ds->dtype, p, st);
 }
 
 void cached_pair_distances(const vdb_dataset* ds, const void* d_queries, const float* d_qcache,

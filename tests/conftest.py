@@ -11,6 +11,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 RTOL = 1e-5      # north star: distances within 1e-5 relative, ids exact except ties within 1e-5
 ATOL = 1e-6      # absolute floor near zero (the reference's own tests use abs 1e-6, distance/mod.rs:136)
+# Cosine distance is 1 - cos: the subtraction cancels, so the 1e-5 relative bar is applied to the O(1) cosine term,
+# i.e. as an ABSOLUTE 1e-5 ("for cosine use an absolute floor"). The reference's own
+# sequential-f32 cosine is only accurate to ~3e-6 absolute on 960-d data, so no summation order can do better.
+ATOL_COSINE = 1e-5
 
 
 def pytest_configure(config):
@@ -51,6 +55,8 @@ def assert_knn_parity(base, queries, metric, got, want, oracle, rtol=RTOL, atol=
     """got/want = (ids [nq,k], dist [nq,k], counts [nq]). Parity rule of BASELINE.json:
     counts equal; distances within rtol; ids identical except where the oracle's own distance of
     the returned id ties the oracle's distance at that rank within rtol. Returns the exact-id rate."""
+    if metric in ("cosine", 1) and atol == ATOL:
+        atol = ATOL_COSINE
     gi, gd, gc = got
     wi, wd, wc = want
     assert gi.shape == wi.shape and gd.shape == wd.shape

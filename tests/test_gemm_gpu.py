@@ -56,13 +56,14 @@ def _synthetic(n, nq, seed=0):
 
 
 @pytest.mark.parametrize("k", [10, 100])
-def test_tensor_path_identical_to_exact_scan(oracle, k):
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_tensor_path_identical_to_exact_scan(oracle, k, metric):
     """The tensor cores only prune: ids and distances must equal the exact scan's (and the oracle's)."""
     import lab_1806_vec_db_b200 as V
     from lab_1806_vec_db_b200 import _lib as L
     n, nq = 140_000, 300
     base, q = _synthetic(n, nq)
-    idx = V.FlatIndex.from_vec_set(base, "l2sqr")
+    idx = V.FlatIndex.from_vec_set(base, metric)
     lib = L.lib()
     try:
         L.check(lib.vdb_flat_set_path(1))
@@ -76,8 +77,8 @@ def test_tensor_path_identical_to_exact_scan(oracle, k):
     assert (tens[2] == scan[2]).all()
     assert (tens[0] == scan[0]).all(), float((tens[0] == scan[0]).mean())
     assert (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()  # rerank uses the scan's summation order
-    want = oracle.flat_knn(base, q[:16], k, "l2sqr", 8)
-    assert_knn_parity(base, q[:16], "l2sqr", tuple(a[:16] for a in tens), want, oracle)
+    want = oracle.flat_knn(base, q[:16], k, metric, 8)
+    assert_knn_parity(base, q[:16], metric, tuple(a[:16] for a in tens), want, oracle)
     assert fallbacks < nq // 2, f"{fallbacks} of {nq} queries fell back to the exact scan"
 
 
@@ -135,15 +136,37 @@ def test_auto_path_edge_shapes_match_scan(n, dim, nq, k):
     assert auto[0][0, 0] == 17 and auto[1][0, 0] == 0.0
 
 
+def test_cosine_tensor_path_zero_vectors_and_signs(oracle):
+    """Cosine through the tensor route with signed data, exact zero rows and a zero query (the reference clamps the
+    norm product at 1e-10, distance/mod.rs:67-69): identical to the forced scan and to the oracle."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((70_000, 64)).astype(np.float32)
+    base[100:110] = 0.0
+    base[500] *= 1e-7
+    q = rng.standard_normal((20, 64)).astype(np.float32)
+    q[3] = 0.0
+    q[4] = base[1234] * 3.0
+    idx = V.FlatIndex.from_vec_set(base, "cosine")
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, 12)
+        L.check(lib.vdb_flat_set_path(2))
+        tens = idx.knn_batch(q, 12)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    want = oracle.flat_knn(base, q, 12, "cosine", 8)
+    assert_knn_parity(base, q, "cosine", tens, want, oracle)
+    assert tens[0][4, 0] == 1234
+
+
 def test_auto_path_keeps_scan_for_unsupported_cases(oracle):
-    """cosine and u8 rows have no tensor route: the auto path must silently use the exact scan (same results)."""
+    """u8 rows have no tensor route: the auto path must silently use the exact scan (same results)."""
     import lab_1806_vec_db_b200 as V
     rng = np.random.default_rng(3)
-    base = rng.random((70_000, 64), dtype=np.float32)
-    q = rng.random((20, 64), dtype=np.float32)
-    got = V.FlatIndex.from_vec_set(base, "cosine").knn_batch(q, 5)
-    want = oracle.flat_knn(base, q, 5, "cosine", 8)
-    assert_knn_parity(base, q, "cosine", got, want, oracle)
     b8 = rng.integers(0, 256, (70_000, 32), dtype=np.uint8)
     q8 = rng.integers(0, 256, (20, 32), dtype=np.uint8)
     got = V.FlatIndex.from_vec_set(b8, "l2sqr").knn_batch(q8, 5)
