@@ -1,0 +1,72 @@
+"""VecDB / MetadataVecTable surface on the GPU backend: the reference's own API smoke tests."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_examples_test_pyo3_script():
+    """examples/test_pyo3.py:1-37, statement for statement."""
+    from lab_1806_vec_db_b200.table import VecDB
+    db = VecDB("./tmp/vec_db")
+    for key in db.get_all_keys():
+        db.delete_table(key)
+    assert len(db.get_all_keys()) == 0
+    db.create_table_if_not_exists("table_1", 4)
+    db.add("table_1", [1.0, 0.0, 0.0, 0.0], {"content": "a"})
+    db.add("table_1", [0.0, 1.0, 0.0, 0.0], {"content": "b"})
+    db.build_hnsw_index("table_1")
+    db.add("table_1", [0.0, 0.0, 1.0, 0.0], {"content": "c"})
+    db.add("table_1", [0.0, 0.0, 1.0, 1.0], {"content": "d", "type": "oops"})
+    assert db.has_hnsw_index("table_1"), "Add operation should not clear HNSW index"
+    db.delete("table_1", {"type": "oops"})
+    assert db.get_len("table_1") == 3
+    assert not db.has_hnsw_index("table_1"), "HNSW index should be cleared when a vector is deleted"
+    db.build_hnsw_index("table_1")
+    db.build_pq_table("table_1")
+    result = db.search("table_1", [1.0, 0.0, 0.0, 0.0], 3, None, 0.5)
+    assert len(result) == 1 and result[0][0]["content"] == "a"
+
+
+def test_database_mod_rs_scenario():
+    """database/mod.rs:543-610: PQ + HNSW search with upper_bound = 0.5 returns exactly ["c"]."""
+    from lab_1806_vec_db_b200.table import VecDB
+    db = VecDB()
+    assert db.create_table_if_not_exists("t", 4, "cosine") and not db.create_table_if_not_exists("t", 4, "cosine")
+    db.batch_add("t", [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], [{"content": c} for c in "abc"])
+    assert db.get_len("t") == 3 and db.get_dim("t") == 4 and db.get_dist("t") == "cosine"
+    db.build_pq_table("t")
+    assert db.has_pq_table("t")
+    db.add("t", [0, 0, 0, 1], {"content": "d"})
+    assert not db.has_pq_table("t")            # the PQ table is dropped on every write
+    db.build_pq_table("t")
+    db.build_hnsw_index("t")
+    res = db.search("t", [0.0, 0.0, 1.0, 0.0], 3, 10, 0.5)
+    assert [m["content"] for m, _ in res] == ["c"] and abs(res[0][1]) < 1e-6
+    db.delete("t", {"content": "a"})           # swap_remove: "d" takes slot 0
+    assert not db.has_pq_table("t") and not db.has_hnsw_index("t")
+    assert [m["content"] for _, m in db.extract_data("t")] == ["d", "b", "c"]
+    res = db.search("t", [0, 0, 0, 1.0], 1)
+    assert res[0][0]["content"] == "d"
+    with pytest.raises(ValueError):
+        db.create_table_if_not_exists("x", 4, "manhattan")
+    with pytest.raises(RuntimeError):
+        db.search("missing", [0, 0, 0, 0], 1)
+
+
+def test_search_variants_against_oracle(fixtures, oracle):
+    from lab_1806_vec_db_b200.table import MetadataVecTable
+    base = fixtures["base"][:300]
+    t = MetadataVecTable(960, "l2sqr", np.random.default_rng(42))
+    t.batch_add(base, [{"i": str(i)} for i in range(300)])
+    q = fixtures["test"][0]
+    want = oracle.flat_knn(base, q.reshape(1, -1), 5, "l2sqr")
+    got = t.search(q, 5)
+    assert [int(m["i"]) for m, _ in got] == want[0][0].tolist()
+    assert [int(m["i"]) for m, _ in t.search(q, 5, ef=50)] == want[0][0].tolist()   # no PQ: ef ignored
+    ub = float(want[1][0][2])
+    assert len(t.search(q, 5, upper_bound=ub)) == 3                                   # distance <= upper_bound
+    t.build_pq_table(0.5, 8, 240)                                                     # n_bits is forced to 4
+    assert t.pq_table.config.n_bits == 4 and t.pq_table.config.k_means_size == 150
+    got = t.search(q, 5, ef=300)                                                      # ef >= n: rerank of everything
+    assert [int(m["i"]) for m, _ in got] == want[0][0].tolist()
