@@ -214,11 +214,12 @@ template <> struct Log2<1> { static constexpr int value = 0; };
 __device__ __forceinline__ void cta_bitonic_sort(uint64_t* base, uint32_t n, uint32_t nseg,
                                                  uint32_t stride) {
     const uint32_t half = n >> 1;
+    const uint32_t hshift = 31 - __clz(half);  // n is a power of two: divisions become shifts
     const uint32_t total = half * nseg;
     for (uint32_t size = 2; size <= n; size <<= 1) {
         for (uint32_t j = size >> 1; j > 0; j >>= 1) {
             for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
-                const uint32_t seg = t / half, p = t - seg * half;
+                const uint32_t seg = t >> hshift, p = t & (half - 1);
                 const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1));  // insert a 0 bit at position log2(j)
                 const uint32_t l = i | j;
                 uint64_t* a = base + (size_t)seg * stride;

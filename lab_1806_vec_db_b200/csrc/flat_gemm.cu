@@ -51,6 +51,7 @@ template <int CTAS> struct GemmCfg {
                                       ((uint32_t)((GM * CTAS) >> 4) << 24);
 };
 constexpr uint32_t G_SAMPLE = 32768;  // sampled rows for the thresholds
+constexpr int G_TOPJ = 16;             // order statistics kept in registers by the sample pass (mode 2)
 constexpr int G_ITEMQ = 4;              // depth of the dynamic-scheduler item queue
 constexpr uint32_t G_NO_ITEM = 0xFFFFFFFFu;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-pair peer bit of a shared::cluster address (-> even CTA)
@@ -218,6 +219,7 @@ struct GemmParams {
     const float* qnorm;     // [nq] cosine: ||q||
     float kc;               // cosine: 1 - (bound on the cosine-distance error)
     // mode 0: store keys (S', sample index) to out_keys[nq][nrows]
+    // mode 2: per (query, slab) the G_TOPJ smallest S' as keys to out_keys[nq][nslabs][G_TOPJ]
     uint64_t* out_keys;
     // mode 1: filter
     const float* tau;       // [nq]
@@ -387,6 +389,11 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const float qn = (METRIC == VDB_COSINE && qok) ? p.qnorm[q] : 0.f;
             float tau = 0.f;
             if (MODE == 1) tau = qok ? p.tau[q] : __uint_as_float(0xff800000u);  // -inf: nothing passes
+            float best[MODE == 2 ? G_TOPJ : 1];  // mode 2: this query's smallest scores of the slab, ascending
+            if (MODE == 2) {
+#pragma unroll
+                for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) best[i] = __uint_as_float(0x7f800000u);
+            }
             for (uint32_t t = t0; t < t1; ++t) {
                 // stage the row-norm tiles of this N-tile (2 x GN floats) while the MMAs run
                 float* sq = norm_tiles + acc * 2 * GN;
@@ -419,10 +426,21 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                 // norm product falls under the reference's 1e-10 clamp are always kept (sq = 1/||x||)
                                 s = fmaf(-(cq * sq[c0 + j]), dot, p.kc);
                                 if (qn * rn[c0 + j] < 2e-10f) s = __uint_as_float(0xff800000u);
+                                if ((uint64_t)t * GN + c0 + j >= p.nrows) s = __uint_as_float(0x7f800000u);  // padding row
                             }
                             if (MODE == 0) {
                                 const uint64_t brow = (uint64_t)t * GN + c0 + j;
                                 if (brow < p.nrows) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(s, (uint32_t)brow);
+                            } else if (MODE == 2) {
+                                if (s < best[G_TOPJ - 1]) {  // rare after the first few hundred rows: bubble s into place
+                                    float v = s;
+#pragma unroll
+                                    for (int i = 0; i < G_TOPJ; ++i) {
+                                        const float lo = fminf(best[i], v);
+                                        v = fmaxf(best[i], v);
+                                        best[i] = lo;
+                                    }
+                                }
                             } else if (s < tau) {
                                 const uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
                                 if (pos < p.cap)
@@ -440,6 +458,11 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     else mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_MASK);
                 }
                 if (++acc == 2) acc = 0, acc_phase ^= 1;
+            }
+            if (MODE == 2 && qok) {
+#pragma unroll
+                for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i)
+                    p.out_keys[((uint64_t)q * p.nslabs + slab) * G_TOPJ + i] = make_key(best[i], slab * G_TOPJ + i);
             }
         }
     }
@@ -590,6 +613,20 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
     ds->side_n = ds->n;
 }
 
+static int gemm_ctas();
+// tiling of one pass: query-tile units x row slabs (small slabs, query tile fastest: the CTAs in flight share a few
+// row tiles and all query tiles in L2)
+static void plan_gemm(GemmParams& p) {
+    const uint32_t ctas = (uint32_t)gemm_ctas();
+    const uint32_t sms = (uint32_t)sm_count();
+    p.ntiles = (uint32_t)ceil_div<uint64_t>(p.nrows, GN);
+    p.nqt = ceil_div<uint32_t>(p.nq, GM * ctas);
+    static const uint32_t tps_env = getenv("VDB_GEMM_TPS") ? (uint32_t)atoi(getenv("VDB_GEMM_TPS")) : 0;
+    const uint32_t tps = tps_env ? tps_env : 4u;
+    p.tiles_per_slab = std::max(1u, std::min(tps, ceil_div(p.ntiles * p.nqt, sms / ctas)));
+    p.nslabs = ceil_div(p.ntiles, p.tiles_per_slab);
+}
+
 static int gemm_ctas() {
     static const int v = getenv("VDB_GEMM_CTAS") ? atoi(getenv("VDB_GEMM_CTAS")) : 2;
     return v == 1 ? 1 : 2;
@@ -605,13 +642,6 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
         configured = true;
     }
     const uint32_t sms = (uint32_t)sm_count();
-    p.ntiles = (uint32_t)ceil_div<uint64_t>(p.nrows, GN);
-    p.nqt = ceil_div<uint32_t>(p.nq, GM * CTAS);
-    // small slabs, query tile fastest: concurrently running CTAs share a few row tiles (and all query tiles) in L2
-    static const uint32_t tps_env = getenv("VDB_GEMM_TPS") ? (uint32_t)atoi(getenv("VDB_GEMM_TPS")) : 0;
-    const uint32_t tps = tps_env ? tps_env : 4u;
-    p.tiles_per_slab = std::max(1u, std::min(tps, ceil_div(p.ntiles * p.nqt, sms / CTAS)));
-    p.nslabs = ceil_div(p.ntiles, p.tiles_per_slab);
     const uint32_t units = std::min(sms / CTAS, p.nqt * p.nslabs);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units * CTAS);
@@ -633,18 +663,23 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
     VDB_LAUNCHED();
 }
 
+// mode 0 = store every score, 1 = filter, 2 = per-slab smallest scores; `p` must have been planned (plan_gemm)
 static void launch_gemm(int mode, int metric, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p,
                         cudaStream_t st) {
-    const int sel = (gemm_ctas() == 2 ? 4 : 0) | (mode ? 2 : 0) | (metric == VDB_COSINE ? 1 : 0);
+    const int sel = (gemm_ctas() == 2 ? 6 : 0) + mode * 2 + (metric == VDB_COSINE ? 1 : 0);
     switch (sel) {
         case 0: launch_gemm_t<0, 1, VDB_L2SQR>(mq, mx, p, st); break;
         case 1: launch_gemm_t<0, 1, VDB_COSINE>(mq, mx, p, st); break;
         case 2: launch_gemm_t<1, 1, VDB_L2SQR>(mq, mx, p, st); break;
         case 3: launch_gemm_t<1, 1, VDB_COSINE>(mq, mx, p, st); break;
-        case 4: launch_gemm_t<0, 2, VDB_L2SQR>(mq, mx, p, st); break;
-        case 5: launch_gemm_t<0, 2, VDB_COSINE>(mq, mx, p, st); break;
-        case 6: launch_gemm_t<1, 2, VDB_L2SQR>(mq, mx, p, st); break;
-        default: launch_gemm_t<1, 2, VDB_COSINE>(mq, mx, p, st); break;
+        case 4: launch_gemm_t<2, 1, VDB_L2SQR>(mq, mx, p, st); break;
+        case 5: launch_gemm_t<2, 1, VDB_COSINE>(mq, mx, p, st); break;
+        case 6: launch_gemm_t<0, 2, VDB_L2SQR>(mq, mx, p, st); break;
+        case 7: launch_gemm_t<0, 2, VDB_COSINE>(mq, mx, p, st); break;
+        case 8: launch_gemm_t<1, 2, VDB_L2SQR>(mq, mx, p, st); break;
+        case 9: launch_gemm_t<1, 2, VDB_COSINE>(mq, mx, p, st); break;
+        case 10: launch_gemm_t<2, 2, VDB_L2SQR>(mq, mx, p, st); break;
+        default: launch_gemm_t<2, 2, VDB_COSINE>(mq, mx, p, st); break;
     }
 }
 
@@ -877,16 +912,26 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     cudaStream_t st = tq->st;
     const uint64_t ns = ds->sample_n;
     VDB_REQUIRE(j >= 1 && j <= ns, "sample order statistic %u out of range (sample %llu)", j, (unsigned long long)ns);
-    DevBuf skeys((size_t)tq->nq * ns * 8, st);
     const CUtensorMap ms = make_map(ds->d_sample, ds->dim, ns, ds->pitch_bytes(), GN / gemm_ctas());
     GemmParams ps = base_params(tq);
     ps.nrows = ns;
     ps.row_stride = 1;
     ps.sqnorm = ds->d_sample_sq;
     ps.rnorm = ds->d_sample_rn;
-    ps.out_keys = skeys.as<uint64_t>();
-    launch_gemm(0, ds->metric, tq->mq, ms, ps, st);
-    launch_merge_keys(skeys.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
+    plan_gemm(ps);
+    if (j <= (uint32_t)G_TOPJ) {
+        // the epilogue keeps each query's G_TOPJ smallest scores per slab in registers: nothing but
+        // nq * nslabs * G_TOPJ keys ever reaches HBM
+        DevBuf part((size_t)tq->nq * ps.nslabs * G_TOPJ * 8, st);
+        ps.out_keys = part.as<uint64_t>();
+        launch_gemm(2, ds->metric, tq->mq, ms, ps, st);
+        launch_merge_keys(part.as<uint64_t>(), ps.nslabs, tq->nq, G_TOPJ, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
+    } else {
+        DevBuf skeys((size_t)tq->nq * ns * 8, st);
+        ps.out_keys = skeys.as<uint64_t>();
+        launch_gemm(0, ds->metric, tq->mq, ms, ps, st);
+        launch_merge_keys(skeys.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
+    }
 }
 
 // TAU: merge `nlists` shards' [nq][j] sample keys (list-major) and set tau_q = S'_(j0) + margin
@@ -928,6 +973,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         pf.cand_cnt = tq->cnt.as<uint32_t>();
         pf.cand = cand.as<uint64_t>();
         pf.cap = cap;
+        plan_gemm(pf);
         launch_gemm(1, ds->metric, tq->mq, mx, pf, st);
     }
     // exact rerank of the candidates (compacted: only the valid pairs are touched)
@@ -1028,6 +1074,7 @@ void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
     p.out_keys = d_out_keys;
     const CUtensorMap mq = make_map(d_queries, ds->dim, nq, (uint64_t)ds->dim * 4, GM);
     const CUtensorMap ms = make_map(ds->d_rows, ds->dim, ns, ds->pitch_bytes() * row_stride, GN / gemm_ctas());
+    plan_gemm(p);
     launch_gemm(0, VDB_L2SQR, mq, ms, p, st);
 }
 

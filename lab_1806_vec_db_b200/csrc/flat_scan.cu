@@ -229,7 +229,17 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
                        uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off) {
     if (nq == 0 || k == 0) return;
-    const uint32_t P = topk_segment_size(k, MERGE_THREADS * MERGE_UNROLL);
+    // segment size: small inputs (K + all keys of a query fit in 1024 slots) are loaded completely and sorted once
+    // in the smallest power-of-two segment; larger inputs stream through a K + 2 * 256 slot segment
+    const uint64_t total_max = (uint64_t)nlists * len;  // per query (an upper bound when segment offsets are used)
+    uint32_t P, limit;
+    if (total_max + k <= 1024) {
+        P = std::max(64u, next_pow2((uint32_t)total_max + k));
+        limit = P - k;  // never reached: no intermediate flush
+    } else {
+        P = topk_segment_size(k, MERGE_THREADS);
+        limit = P - k - MERGE_THREADS;
+    }
     const size_t smem = TopkSmem::bytes(1, P);
     VDB_REQUIRE(smem <= 200 * 1024, "k=%u too large for the fused top-k (max %u)", k, 20000u);
     if (smem > 48 * 1024)
@@ -237,7 +247,7 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
                                       (int)smem));
     ProfScope prof("merge", stream);
     merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off,
-                                                           k, P, P - k - MERGE_THREADS * MERGE_UNROLL, d_out_keys, d_ids,
+                                                           k, P, limit, d_out_keys, d_ids,
                                                            d_dist, d_counts);
     VDB_LAUNCHED();
 }
