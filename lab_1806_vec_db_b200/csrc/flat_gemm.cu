@@ -1009,9 +1009,8 @@ void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_tot
     VDB_LAUNCHED();
 }
 
-void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
-                    cudaStream_t st) {
-    VDB_REQUIRE(flat_gemm_supported(ds, nq, k), "tensor-core Flat path: unsupported dataset/k");
+static void flat_gemm_keys_chunk(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                                 cudaStream_t st) {
     vdb_tq* tq = tensor_begin(ds, d_queries, nq, st);
     try {
         const uint32_t j0 = tensor_j0(k, ds->sample_n, ds->n);
@@ -1044,6 +1043,18 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
         throw;
     }
     tensor_end(tq);
+}
+
+// query batches are processed in chunks so the candidate / rerank scratch stays bounded (~5 GB per chunk)
+constexpr uint32_t G_QUERY_CHUNK = 16384;
+
+void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                    cudaStream_t st) {
+    VDB_REQUIRE(flat_gemm_supported(ds, nq, k), "tensor-core Flat path: unsupported dataset/k");
+    for (uint32_t q0 = 0; q0 < nq; q0 += G_QUERY_CHUNK) {
+        const uint32_t cn = std::min(G_QUERY_CHUNK, nq - q0);
+        flat_gemm_keys_chunk(ds, (const float*)d_queries + (size_t)q0 * ds->dim, cn, k, d_keys + (size_t)q0 * k, st);
+    }
 }
 
 // debug / test entry: S' keys of every (query, sampled row) pair, [nq][nrows] (mode 0 of the kernel)

@@ -47,6 +47,7 @@ class ShardedFlatIndex:
     the per-query overflow flags (tensor path only)."""
 
     TENSOR_MIN_NQ = 12
+    QUERY_CHUNK = 16384
 
     def __init__(self, vec_set, rank=0, world=1):
         self.vec_set = vec_set
@@ -157,7 +158,10 @@ class ShardedFlatIndex:
             return ids, dd, cnt
         info = self._tensor_info(dev) if (nq >= self.TENSOR_MIN_NQ and 1 <= k <= 1024) else False
         if info:
-            merged = self._tensor_keys(q, k, st, info)
+            # chunks bound the candidate / rerank scratch of the filter phase
+            parts = [self._tensor_keys(q[c0:c0 + self.QUERY_CHUNK].contiguous(), k, st, info)
+                     for c0 in range(0, nq, self.QUERY_CHUNK)]
+            merged = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
         else:
             merged = self._merge_to_keys(self._gather(self._scan_keys(q, k, st)), nq, k, st)
         L.check(lib.vdb_decode_keys_dev(C.c_void_p(merged.data_ptr()), nq, k, C.c_void_p(ids.data_ptr()),

@@ -172,3 +172,22 @@ def test_auto_path_keeps_scan_for_unsupported_cases(oracle):
     got = V.FlatIndex.from_vec_set(b8, "l2sqr").knn_batch(q8, 5)
     want = oracle.flat_knn(b8, q8, 5, "l2sqr", 8)
     assert_knn_parity(b8, q8, "l2sqr", got, want, oracle)
+
+
+def test_tensor_path_large_query_batch_is_chunked():
+    """40 000 queries (three chunks of the tensor path) against a small shard: identical to the scan on a subsample."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(11)
+    base = rng.random((66_000, 32), dtype=np.float32)
+    q = rng.random((40_000, 32), dtype=np.float32)
+    idx = V.FlatIndex.from_vec_set(base, "l2sqr")
+    auto = idx.knn_batch(q, 5)
+    sel = np.r_[0:50, 16380:16390, 32760:32780, 39990:40000]
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q[sel], 5)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (auto[0][sel] == scan[0]).all() and (auto[1][sel].view(np.uint32) == scan[1].view(np.uint32)).all()
