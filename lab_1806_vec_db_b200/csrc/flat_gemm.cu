@@ -809,11 +809,11 @@ uint64_t g_gemm_queries = 0;
 // ---- phases (also exported one by one for the row-sharded search, sharded.py) -------------------------------
 // j0: smallest order statistic of an `ns`-row uniform sample whose rank among the `n` rows is >= k with high
 // probability: P(rank < k) = P(Poisson(k*ns/n) >= j0) < 2e-3
-uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n) {
+uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps) {
     uint32_t j0 = 1;
     const double x = (double)k * (double)ns / (double)n;
     double term = exp(-x), cdf = term;
-    while (1.0 - cdf >= 2e-3 && j0 < 4096) {
+    while (1.0 - cdf >= eps && j0 < 4096) {
         term *= x / j0;
         cdf += term;
         ++j0;

@@ -19,6 +19,8 @@ struct vdb_pq {
     float* d_cb_norm = nullptr;     // [m*kc] ||c|| for cosine encoding
     uint8_t* d_codes = nullptr;     // [n][enc] reference layout
     uint32_t* d_codes_t = nullptr;  // [ceil(n/32)][words][32] transposed for the ADC scan
+    uint32_t* d_sample_t = nullptr; // the same layout for a stratified random row sample (thresholds of the scan)
+    uint32_t sample_n = 0;
 };
 
 // device mirror of IVFIndex<T> (reference src/index_algorithm/ivf_index.rs:34-47)
@@ -95,7 +97,7 @@ void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, c
 void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
                      uint64_t* d_out_keys, cudaStream_t st);
 extern uint64_t g_gemm_redo, g_gemm_cands, g_gemm_queries;
-uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n);
+uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps = 2e-3);
 vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st);
 void tensor_end(vdb_tq* tq);
 void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys);

@@ -300,6 +300,141 @@ __global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParam
     }
 }
 
+// ---- global-threshold ADC scan (4-bit codes, batches) --------------------------------------------------------
+// The per-CTA top-k of pq_adc_scan_kernel costs as much as the lookups when ef is large (every CTA sorts its own
+// ef-best of ~7 k rows). Here the threshold is GLOBAL: the ADC distances of a stratified ~3 % row sample give, per
+// query, a value tau_q that at least max(ef,k) rows of the shard undercut with probability > 1 - 1e-5 (ADC values
+// are exact, so no margin is needed); the scan then only appends rows with adc <= tau_q to a per-query list and the
+// exact top-max(ef,k) by (adc, id) is selected from that short list. Queries whose list turns out too short or
+// overflows are re-run through the per-CTA kernel. The LUTs of the 4 queries of a pass are interleaved
+// ([entry][query] as float4) so one LDS.128 serves all four.
+constexpr int GQ = 4;
+struct AdcGlobalParams {
+    const uint32_t* codes_t;
+    uint64_t n;
+    uint32_t words, m;
+    const float* lut;         // [GQ][m*16] of this pass (rows beyond nq_valid are ignored)
+    const float* dist_cache;  // [m*16] (cosine)
+    const float* qcache;      // [GQ]
+    uint32_t nq_valid;
+    uint32_t id_base;
+    uint32_t iters;
+    float* all_out;           // MODE 0: [GQ][n] every ADC distance
+    const float* tau;         // MODE 1: [GQ]
+    uint32_t* cnt;            // MODE 1: [GQ]
+    uint64_t* cand;           // MODE 1: [GQ][cap]
+    uint32_t cap;
+};
+
+template <int METRIC, int MODE>
+__global__ void __launch_bounds__(ADC_THREADS) pq_adc_global_kernel(const AdcGlobalParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tab = p.m * 16;
+    float4* s_lut = reinterpret_cast<float4*>(smem);           // [tab] (q0, q1, q2, q3)
+    float* s_dc = reinterpret_cast<float*>(s_lut + tab);        // [tab] (cosine)
+    for (uint32_t e = threadIdx.x; e < tab; e += blockDim.x) {
+        float4 v;
+        v.x = p.lut[e];
+        v.y = p.nq_valid > 1 ? p.lut[(size_t)tab + e] : 0.f;
+        v.z = p.nq_valid > 2 ? p.lut[(size_t)2 * tab + e] : 0.f;
+        v.w = p.nq_valid > 3 ? p.lut[(size_t)3 * tab + e] : 0.f;
+        s_lut[e] = v;
+        if (METRIC == VDB_COSINE) s_dc[e] = p.dist_cache[e];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    float tau[GQ], qn[GQ];
+#pragma unroll
+    for (int q = 0; q < GQ; ++q) {
+        tau[q] = (MODE == 1 && q < (int)p.nq_valid) ? p.tau[q] : __uint_as_float(0xff800000u);
+        qn[q] = (METRIC == VDB_COSINE && q < (int)p.nq_valid) ? p.qcache[q] : 0.f;
+    }
+    for (uint32_t it = 0; it < p.iters; ++it) {
+        const uint64_t tile = (uint64_t)it * gridDim.x + blockIdx.x;
+        const uint64_t row = tile * ADC_THREADS + threadIdx.x;
+        if (row >= p.n) continue;
+        const uint32_t* cw = p.codes_t + (row >> 5) * p.words * 32 + lane;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, cdp = 0.f;
+        uint32_t g = 0;
+        uint32_t next = cw[0];
+        for (uint32_t w = 0; w < p.words; ++w) {
+            const uint32_t word = next;
+            if (w + 1 < p.words) next = cw[(size_t)(w + 1) * 32];
+            const uint32_t ng = min(8u, p.m - g);
+            if (ng == 8) {
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = s_lut[(g + i) * 16 + ((word >> (4 * i)) & 0xfu)];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {  // the reference's group order, one sequential chain per query
+                    s0 = __fadd_rn(s0, v[i].x);
+                    s1 = __fadd_rn(s1, v[i].y);
+                    s2 = __fadd_rn(s2, v[i].z);
+                    s3 = __fadd_rn(s3, v[i].w);
+                }
+                if (METRIC == VDB_COSINE) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cdp = __fadd_rn(cdp, s_dc[(g + i) * 16 + ((word >> (4 * i)) & 0xfu)]);
+                }
+            } else {
+                for (uint32_t i = 0; i < ng; ++i) {
+                    const uint32_t e = (g + i) * 16 + ((word >> (4 * i)) & 0xfu);
+                    const float4 v = s_lut[e];
+                    s0 = __fadd_rn(s0, v.x);
+                    s1 = __fadd_rn(s1, v.y);
+                    s2 = __fadd_rn(s2, v.z);
+                    s3 = __fadd_rn(s3, v.w);
+                    if (METRIC == VDB_COSINE) cdp = __fadd_rn(cdp, s_dc[e]);
+                }
+            }
+            g += 8;
+        }
+        float d[GQ] = {s0, s1, s2, s3};
+#pragma unroll
+        for (int q = 0; q < GQ; ++q) {
+            if (q >= (int)p.nq_valid) continue;
+            float dd = d[q];
+            if (METRIC == VDB_COSINE) {
+                const float den = fmaxf(__fmul_rn(sqrtf(cdp), qn[q]), 1e-10f);
+                dd = __fsub_rn(1.0f, __fdiv_rn(d[q], den));
+            }
+            if (MODE == 0) {
+                p.all_out[(size_t)q * p.n + row] = dd;
+            } else if (!(dd > tau[q])) {  // adc <= tau (NaN is kept: it orders last and is dropped by the selection)
+                const uint32_t pos = atomicAdd(&p.cnt[q], 1u);
+                if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = make_key(dd, p.id_base + (uint32_t)row);
+            }
+        }
+    }
+}
+
+__global__ void floats_to_keys_kernel(const float* __restrict__ v, uint64_t count, uint64_t per_q, uint64_t* __restrict__ keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        keys[i] = make_key(v[i], (uint32_t)(i % per_q));
+}
+__global__ void tau_from_jkeys_kernel(const uint64_t* __restrict__ jkeys, uint32_t nq, uint32_t j, float* __restrict__ tau) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) tau[q] = key_dist(jkeys[(size_t)q * j + (j - 1)]);
+}
+// queries whose candidate list is too short (the threshold was too tight) or overflowed must be redone
+__global__ void adc_check_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t need, uint32_t cap,
+                                 uint32_t* __restrict__ redo, uint32_t* __restrict__ nredo) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq && (cnt[q] < need || cnt[q] > cap)) redo[atomicAdd(nredo, 1u)] = q;
+}
+__global__ void gather_f32_rows_kernel(const float* __restrict__ src, uint32_t width, const uint32_t* __restrict__ idx,
+                                       uint32_t cnt, float* __restrict__ dst) {
+    const uint32_t i = blockIdx.x;
+    if (i >= cnt) return;
+    for (uint32_t e = threadIdx.x; e < width; e += blockDim.x) dst[(size_t)i * width + e] = src[(size_t)idx[i] * width + e];
+}
+__global__ void scatter_u64_rows_kernel(const uint64_t* __restrict__ src, uint32_t width, const uint32_t* __restrict__ idx,
+                                        uint32_t cnt, uint64_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x;
+    if (i >= cnt) return;
+    for (uint32_t e = threadIdx.x; e < width; e += blockDim.x) dst[(size_t)idx[i] * width + e] = src[(size_t)i * width + e];
+}
+
 constexpr size_t ADC_SMEM_MAX = 200 * 1024;
 
 template <int NQ>
@@ -396,6 +531,122 @@ static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache
     }
 }
 
+static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K,
+                     uint32_t id_base, uint64_t* d_keys, float* d_all, cudaStream_t st);
+
+template <int MODE>
+static void launch_adc_global(const vdb_pq* pq, AdcGlobalParams p, const uint32_t* codes_t, uint64_t n, cudaStream_t st) {
+    const uint32_t tab = pq->m * 16;
+    const size_t smem = (size_t)tab * 16 + (pq->metric == VDB_COSINE ? (size_t)tab * 4 : 0);
+    const uint64_t tiles = ceil_div<uint64_t>(n, ADC_THREADS);
+    const uint32_t occ = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem, 1)));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sm_count() * occ));
+    p.codes_t = codes_t;
+    p.n = n;
+    p.words = pq->words;
+    p.m = pq->m;
+    p.dist_cache = pq->d_dist_cache;
+    p.iters = (uint32_t)ceil_div<uint64_t>(tiles, grid);
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024)
+            VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADC_SMEM_MAX));
+        ProfScope prof("pq_adc", st);
+        kern<<<grid, ADC_THREADS, smem, st>>>(p);
+        VDB_LAUNCHED();
+    };
+    if (pq->metric == VDB_COSINE) go(pq_adc_global_kernel<VDB_COSINE, MODE>);
+    else go(pq_adc_global_kernel<VDB_L2SQR, MODE>);
+}
+
+static bool adc_global_supported(const vdb_pq* pq, uint32_t K) {
+    const size_t smem = (size_t)pq->m * 16 * 16 + (pq->metric == VDB_COSINE ? (size_t)pq->m * 16 * 4 : 0);
+    return pq->n_bits == 4 && pq->d_sample_t && pq->n >= 65536 && K >= 1 && K <= 4096 && smem <= ADC_SMEM_MAX;
+}
+
+// top-K (adc, id) keys per query through the global-threshold scan; [nq][K]
+static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K,
+                            uint32_t id_base, uint64_t* d_keys, cudaStream_t st) {
+    const uint32_t tab = pq->m * 16;
+    const uint64_t ns = pq->sample_n;
+    const uint32_t j0 = tensor_j0(K, ns, pq->n, 1e-5);
+    const uint32_t cap = next_pow2((uint32_t)std::min<uint64_t>(pq->n, std::max<uint64_t>(4ull * j0 * (pq->n / ns), 4096)));
+    DevBuf sall((size_t)nq * ns * 4, st), skeys((size_t)nq * ns * 8, st), jkeys((size_t)nq * j0 * 8, st), tau((size_t)nq * 4, st),
+        cnt((size_t)nq * 4, st), cand((size_t)nq * cap * 8, st), redo((size_t)nq * 4, st), nredo(4, st);
+    VDB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * 4, st));
+    VDB_CUDA(cudaMemsetAsync(cand.p, 0xff, (size_t)nq * cap * 8, st));
+    VDB_CUDA(cudaMemsetAsync(nredo.p, 0, 4, st));
+    // 1. thresholds from the sample
+    for (uint32_t q0 = 0; q0 < nq; q0 += GQ) {
+        AdcGlobalParams p{};
+        p.lut = d_lut + (size_t)q0 * tab;
+        p.qcache = d_qcache + q0;
+        p.nq_valid = std::min<uint32_t>(GQ, nq - q0);
+        p.all_out = sall.as<float>() + (size_t)q0 * ns;
+        launch_adc_global<0>(pq, p, pq->d_sample_t, ns, st);
+    }
+    floats_to_keys_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>((uint64_t)nq * ns, 256), 8192), 256, 0, st>>>(
+        sall.as<float>(), (uint64_t)nq * ns, ns, skeys.as<uint64_t>());
+    VDB_LAUNCHED();
+    launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j0, jkeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
+    tau_from_jkeys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, tau.as<float>());
+    VDB_LAUNCHED();
+    // 2. filter scan over the shard
+    for (uint32_t q0 = 0; q0 < nq; q0 += GQ) {
+        AdcGlobalParams p{};
+        p.lut = d_lut + (size_t)q0 * tab;
+        p.qcache = d_qcache + q0;
+        p.nq_valid = std::min<uint32_t>(GQ, nq - q0);
+        p.id_base = id_base;
+        p.tau = tau.as<float>() + q0;
+        p.cnt = cnt.as<uint32_t>() + q0;
+        p.cand = cand.as<uint64_t>() + (size_t)q0 * cap;
+        p.cap = cap;
+        launch_adc_global<1>(pq, p, pq->d_codes_t, pq->n, st);
+    }
+    // 3. exact top-K by (adc, id) from the short lists
+    launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, K, d_keys, nullptr, nullptr, nullptr, st);
+    // 4. queries whose list is too short or overflowed: per-CTA top-k kernel
+    const uint32_t need = (uint32_t)std::min<uint64_t>(K, pq->n);
+    adc_check_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(cnt.as<uint32_t>(), nq, need, cap, redo.as<uint32_t>(),
+                                                         nredo.as<uint32_t>());
+    VDB_LAUNCHED();
+    uint32_t h_redo = 0;
+    VDB_CUDA(cudaMemcpyAsync(&h_redo, nredo.p, 4, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaStreamSynchronize(st));
+    if (h_redo) {
+        DevBuf rlut((size_t)h_redo * tab * 4, st), rqc((size_t)h_redo * 4, st), rkeys((size_t)h_redo * K * 8, st);
+        gather_f32_rows_kernel<<<h_redo, 256, 0, st>>>(d_lut, tab, redo.as<uint32_t>(), h_redo, rlut.as<float>());
+        VDB_LAUNCHED();
+        gather_f32_rows_kernel<<<h_redo, 32, 0, st>>>(d_qcache, 1, redo.as<uint32_t>(), h_redo, rqc.as<float>());
+        VDB_LAUNCHED();
+        adc_scan(pq, rlut.as<float>(), rqc.as<float>(), h_redo, K, id_base, rkeys.as<uint64_t>(), nullptr, st);
+        scatter_u64_rows_kernel<<<h_redo, 256, 0, st>>>(rkeys.as<uint64_t>(), K, redo.as<uint32_t>(), h_redo, d_keys);
+        VDB_LAUNCHED();
+    }
+}
+
+// top-K ADC keys: global-threshold scan for batches on large shards, per-CTA top-k otherwise
+static void adc_topk(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K, uint32_t id_base,
+                     uint64_t* d_keys, cudaStream_t st) {
+    static const int force_old = getenv("VDB_ADC_OLD") ? atoi(getenv("VDB_ADC_OLD")) : 0;
+    if (!force_old && nq >= 4 && adc_global_supported(pq, K)) adc_topk_global(pq, d_lut, d_qcache, nq, K, id_base, d_keys, st);
+    else adc_scan(pq, d_lut, d_qcache, nq, K, id_base, d_keys, nullptr, st);
+}
+
+// stratified random sample of the code rows, in the scan's transposed layout
+__global__ void pq_sample_codes_kernel(const uint8_t* __restrict__ codes, uint64_t n, uint32_t enc, uint32_t ns,
+                                       uint8_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x;
+    if (i >= ns) return;
+    const uint64_t lo = (uint64_t)i * n / ns, hi = (uint64_t)(i + 1) * n / ns;
+    uint64_t h = (i + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 29;
+    const uint64_t row = lo + h % (hi > lo ? hi - lo : 1);
+    for (uint32_t e = threadIdx.x; e < enc; e += blockDim.x) out[(size_t)i * enc + e] = codes[row * enc + e];
+}
+
 // ---- table construction -------------------------------------------------------------------------------
 vdb_pq* pq_create(const vdb_dataset* ds, const void* h_codebooks, uint32_t m, uint32_t n_bits,
                   const uint8_t* h_codes_in, uint8_t* h_codes_out) {
@@ -469,6 +720,18 @@ vdb_pq* pq_create(const vdb_dataset* ds, const void* h_codebooks, uint32_t m, ui
             pq_transpose_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(tt, 256), 1u << 20), 256, 0, st>>>(
                 pq->d_codes, pq->n, pq->enc, pq->words, pq->d_codes_t);
             VDB_LAUNCHED();
+            if (pq->n >= 65536) {
+                pq->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(32768, pq->n / 2), std::max<uint64_t>(2048, pq->n / 30));
+                DevBuf srows((size_t)pq->sample_n * pq->enc, st);
+                pq_sample_codes_kernel<<<pq->sample_n, 128, 0, st>>>(pq->d_codes, pq->n, pq->enc, pq->sample_n, srows.as<uint8_t>());
+                VDB_LAUNCHED();
+                const uint64_t ts = ceil_div<uint64_t>(pq->sample_n, 32) * pq->words * 32;
+                VDB_CUDA(cudaMalloc(&pq->d_sample_t, ts * 4));
+                pq_transpose_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(ts, 256), 1u << 20), 256, 0, st>>>(
+                    srows.as<uint8_t>(), pq->sample_n, pq->enc, pq->words, pq->d_sample_t);
+                VDB_LAUNCHED();
+                VDB_CUDA(cudaStreamSynchronize(st));
+            }
             if (h_codes_out)
                 VDB_CUDA(cudaMemcpyAsync(h_codes_out, pq->d_codes, pq->n * pq->enc, cudaMemcpyDeviceToHost, st));
         }
@@ -490,6 +753,7 @@ void pq_destroy(vdb_pq* pq) {
     cudaFree(pq->d_cb_norm);
     cudaFree(pq->d_codes);
     cudaFree(pq->d_codes_t);
+    cudaFree(pq->d_sample_t);
     delete pq;
 }
 
@@ -573,7 +837,7 @@ void pq_adc_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries,
     const uint32_t tab = pq->m * pq->kc;
     DevBuf lut((size_t)nq * tab * 4, st), qcache((size_t)nq * 4, st);
     pq_lut(pq, d_queries, nq, lut.as<float>(), qcache.as<float>(), st);
-    adc_scan(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, d_keys, nullptr, st);
+    adc_topk(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, d_keys, st);
 }
 
 void pq_knn_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,
@@ -586,7 +850,7 @@ void pq_knn_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries,
     const uint32_t tab = pq->m * pq->kc;
     DevBuf lut((size_t)nq * tab * 4, st), qcache((size_t)nq * 4, st), cand((size_t)nq * kk * 8, st);
     pq_lut(pq, d_queries, nq, lut.as<float>(), qcache.as<float>(), st);
-    adc_scan(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, cand.as<uint64_t>(), nullptr, st);
+    adc_topk(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, cand.as<uint64_t>(), st);
     rerank_keys(ds, d_queries, nq, cand.as<uint64_t>(), kk, k, d_keys, st);
 }
 

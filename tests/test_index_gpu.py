@@ -272,3 +272,30 @@ def test_ivf_c3_shape_small(V, oracle):
         got = ivf.knn_with_ef_batch(q, 10, nprobe)
         want = oracle.ivf_knn(base, cent, off, mem, q, 10, nprobe, "l2sqr", nthreads=8)
         assert_knn_parity(base, q, "l2sqr", got, want, oracle)
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+@pytest.mark.parametrize("m", [8, 7])
+def test_pq_global_threshold_scan_large_shard(V, oracle, metric, m):
+    """Shards >= 65536 rows use the global-threshold ADC scan for batches: same candidates as the reference scan
+    (checked through knn_pq vs the oracle on identical codebooks), incl. odd m, many exact ADC ties and ef sweeps."""
+    rng = np.random.default_rng(21 + m)
+    n, dim = 70_000, 32
+    base = rng.random((n, dim), dtype=np.float32)
+    base[5000:5300] = base[17]                      # 300 identical rows: ADC ties decided by id
+    q = rng.random((9, dim), dtype=np.float32)
+    q[0] = base[17]
+    books = np.concatenate([np.ascontiguousarray(base[100:116, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(dim, m)])
+    vs = V.DeviceVecSet(base, metric)
+    pq = V.PQTable(vs, V.PQConfig(4, m, metric), books)
+    codes = oracle.pq_encode(base, books, m, 4, metric, nthreads=8)
+    assert (pq.encoded_vec_set == codes).all()
+    idx = V.FlatIndex(vs)
+    for k, ef in ((10, 50), (10, 300), (5, 1200), (3, 1)):
+        got = idx.knn_pq_batch(q, k, ef, pq)
+        want = oracle.flat_knn_pq(base, codes, books, m, 4, q, k, ef, metric, nthreads=8)
+        assert_knn_parity(base, q, metric, got, want, oracle)
+    # single query (per-CTA kernel) and the batch (global-threshold kernel) agree exactly
+    one = idx.knn_pq_batch(q[:1], 10, 300, pq)
+    many = idx.knn_pq_batch(q, 10, 300, pq)
+    assert (one[0][0] == many[0][0]).all() and (one[1][0].view(np.uint32) == many[1][0].view(np.uint32)).all()
