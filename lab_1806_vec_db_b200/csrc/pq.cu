@@ -534,10 +534,13 @@ static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache
 static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K,
                      uint32_t id_base, uint64_t* d_keys, float* d_all, cudaStream_t st);
 
+static int adc_gq() { return GQ; }
+
 template <int MODE>
 static void launch_adc_global(const vdb_pq* pq, AdcGlobalParams p, const uint32_t* codes_t, uint64_t n, cudaStream_t st) {
     const uint32_t tab = pq->m * 16;
-    const size_t smem = (size_t)tab * 16 + (pq->metric == VDB_COSINE ? (size_t)tab * 4 : 0);
+    const int gq = adc_gq();
+    const size_t smem = (size_t)tab * 4 * gq + (pq->metric == VDB_COSINE ? (size_t)tab * 4 : 0);
     const uint64_t tiles = ceil_div<uint64_t>(n, ADC_THREADS);
     const uint32_t occ = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem, 1)));
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sm_count() * occ));
@@ -576,11 +579,12 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
     VDB_CUDA(cudaMemsetAsync(cand.p, 0xff, (size_t)nq * cap * 8, st));
     VDB_CUDA(cudaMemsetAsync(nredo.p, 0, 4, st));
     // 1. thresholds from the sample
-    for (uint32_t q0 = 0; q0 < nq; q0 += GQ) {
+    const uint32_t gq = (uint32_t)adc_gq();
+    for (uint32_t q0 = 0; q0 < nq; q0 += gq) {
         AdcGlobalParams p{};
         p.lut = d_lut + (size_t)q0 * tab;
         p.qcache = d_qcache + q0;
-        p.nq_valid = std::min<uint32_t>(GQ, nq - q0);
+        p.nq_valid = std::min<uint32_t>(gq, nq - q0);
         p.all_out = sall.as<float>() + (size_t)q0 * ns;
         launch_adc_global<0>(pq, p, pq->d_sample_t, ns, st);
     }
@@ -591,11 +595,11 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
     tau_from_jkeys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, tau.as<float>());
     VDB_LAUNCHED();
     // 2. filter scan over the shard
-    for (uint32_t q0 = 0; q0 < nq; q0 += GQ) {
+    for (uint32_t q0 = 0; q0 < nq; q0 += gq) {
         AdcGlobalParams p{};
         p.lut = d_lut + (size_t)q0 * tab;
         p.qcache = d_qcache + q0;
-        p.nq_valid = std::min<uint32_t>(GQ, nq - q0);
+        p.nq_valid = std::min<uint32_t>(gq, nq - q0);
         p.id_base = id_base;
         p.tau = tau.as<float>() + q0;
         p.cnt = cnt.as<uint32_t>() + q0;
