@@ -537,6 +537,20 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
         dst[i] = __uint_as_float(r);
     }
 }
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, uint64_t count) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+static void u8_to_f32(const uint8_t* src, float* dst, uint64_t count, cudaStream_t st) {
+    if (count == 0) return;
+    u8_to_f32_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), (uint64_t)sm_count() * 32), 256, 0, st>>>(src, dst, count);
+    VDB_LAUNCHED();
+}
+// [nq][dim] u8 -> [nq][qpitch] f32 (zero padded)
+__global__ void u8_rows_to_f32_kernel(const uint8_t* __restrict__ src, uint32_t dim, uint32_t qpitch, float* __restrict__ dst) {
+    const uint32_t q = blockIdx.x;
+    for (uint32_t e = threadIdx.x; e < qpitch; e += blockDim.x) dst[(size_t)q * qpitch + e] = e < dim ? (float)src[(size_t)q * dim + e] : 0.f;
+}
 static void round_tf32(const float* src, float* dst, uint64_t count, cudaStream_t st) {
     if (count == 0) return;
     round_tf32_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), (uint64_t)sm_count() * 32), 256, 0, st>>>(src, dst, count);
@@ -583,11 +597,12 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
     ds->d_sqnorm = ds->d_lo = ds->d_tf32 = ds->d_sample = ds->d_sample_sq = ds->d_sample_rn = nullptr;
     VDB_CUDA(cudaMalloc(&ds->d_sqnorm, ds->n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_lo, ds->n * 4));
-    VDB_CUDA(cudaMalloc(&ds->d_tf32, ds->n * ds->pitch_bytes()));
-    round_tf32((const float*)ds->d_rows, ds->d_tf32, ds->n * ds->pitch, st);
+    VDB_CUDA(cudaMalloc(&ds->d_tf32, ds->n * (size_t)ds->pitch * 4));
+    if (ds->dtype == VDB_F32) round_tf32((const float*)ds->d_rows, ds->d_tf32, ds->n * ds->pitch, st);
+    else u8_to_f32((const uint8_t*)ds->d_rows, ds->d_tf32, ds->n * ds->pitch, st);  // 8-bit values are exact in TF32
     // ~3 % of the shard, so the sample pass stays a small fixed fraction of the filter pass on every shard size
     ds->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(G_SAMPLE, ds->n / 2), std::max<uint64_t>(2048, ds->n / 30));
-    VDB_CUDA(cudaMalloc(&ds->d_sample, (size_t)ds->sample_n * ds->pitch_bytes()));
+    VDB_CUDA(cudaMalloc(&ds->d_sample, (size_t)ds->sample_n * ds->pitch * 4));
     VDB_CUDA(cudaMalloc(&ds->d_sample_sq, (size_t)ds->sample_n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_sample_rn, (size_t)ds->sample_n * 4));
     vdb_dataset tmp = *ds;
@@ -782,11 +797,12 @@ __global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uin
     }
     if (!ok) redo[atomicAdd(nredo, 1u)] = q;
 }
-__global__ void gather_rows_kernel(const float* __restrict__ src, uint32_t dim, const uint32_t* __restrict__ idx,
-                                   uint32_t cnt, float* __restrict__ dst) {
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, uint32_t row_bytes, const uint32_t* __restrict__ idx,
+                                   uint32_t cnt, uint8_t* __restrict__ dst) {
     const uint32_t i = blockIdx.x;
     if (i >= cnt) return;
-    for (uint32_t e = threadIdx.x; e < dim; e += blockDim.x) dst[(size_t)i * dim + e] = src[(size_t)idx[i] * dim + e];
+    for (uint32_t e = threadIdx.x; e < row_bytes; e += blockDim.x)
+        dst[(size_t)i * row_bytes + e] = src[(size_t)idx[i] * row_bytes + e];
 }
 __global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, uint32_t k, const uint32_t* __restrict__ idx,
                                     uint32_t cnt, uint64_t* __restrict__ dst) {
@@ -798,7 +814,7 @@ __global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, uint32_t k
 constexpr uint32_t G_MAX_K = 1024;
 
 bool flat_gemm_supported(const vdb_dataset* ds, uint32_t nq, uint32_t k) {
-    return ds->dtype == VDB_F32 && k >= 1 && k <= G_MAX_K && ds->n >= 65536 &&
+    return (ds->dtype == VDB_F32 || ds->dtype == VDB_U8) && k >= 1 && k <= G_MAX_K && ds->n >= 65536 &&
            nq >= 1 && ((uintptr_t)ds->d_rows & 15) == 0;
 }
 
@@ -845,7 +861,9 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
     const uint32_t dim = ds->dim;
     // pruning-bound coefficient: both operands rounded to TF32 (2^-11 each, products then exact in fp32) plus
     // dim fp32 accumulation steps, times 2 for the -2 q.x term
-    const float c = 2.0f * (ldexpf(1.0f, -10) * 1.001f + (float)dim * ldexpf(1.0f, -23));
+    // (u8 rows and queries are exact in TF32: only the accumulation term remains)
+    const float c = ds->dtype == VDB_F32 ? 2.0f * (ldexpf(1.0f, -10) * 1.001f + (float)dim * ldexpf(1.0f, -23))
+                                         : 2.0f * (ldexpf(1.0f, -20) + (float)dim * ldexpf(1.0f, -23));
     auto tq = new vdb_tq();
     try {
         tq->ds = ds;
@@ -859,15 +877,21 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
         tq->qsq = DevBuf((size_t)nq * 4, st);
         tq->qcm = DevBuf((size_t)nq * 4, st);
         tq->cnt = DevBuf((size_t)nq * 4, st);
-        if (tq->qpitch != dim) VDB_CUDA(cudaMemsetAsync(tq->qcopy.p, 0, qbytes, st));
-        VDB_CUDA(cudaMemcpy2DAsync(tq->qcopy.p, (size_t)tq->qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
-                                   cudaMemcpyDeviceToDevice, st));
+        if (ds->dtype == VDB_U8) {
+            u8_rows_to_f32_kernel<<<nq, 128, 0, st>>>((const uint8_t*)d_queries, dim, tq->qpitch, tq->qcopy.as<float>());
+            VDB_LAUNCHED();
+        } else {
+            if (tq->qpitch != dim) VDB_CUDA(cudaMemsetAsync(tq->qcopy.p, 0, qbytes, st));
+            VDB_CUDA(cudaMemcpy2DAsync(tq->qcopy.p, (size_t)tq->qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
+                                       cudaMemcpyDeviceToDevice, st));
+        }
         round_tf32(tq->qcopy.as<float>(), tq->qround.as<float>(), (uint64_t)nq * tq->qpitch, st);
         if (ds->metric == VDB_L2SQR) {
             vdb_dataset qd = *ds;
             qd.d_rows = tq->qcopy.p;
             qd.n = nq;
             qd.pitch = tq->qpitch;
+            qd.dtype = VDB_F32;
             qd.metric = VDB_L2SQR;
             row_cache(&qd, tq->qsq.as<float>(), st);
             qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qsq.as<float>(), nq, c, tq->qcm.as<float>());
@@ -912,7 +936,7 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     cudaStream_t st = tq->st;
     const uint64_t ns = ds->sample_n;
     VDB_REQUIRE(j >= 1 && j <= ns, "sample order statistic %u out of range (sample %llu)", j, (unsigned long long)ns);
-    const CUtensorMap ms = make_map(ds->d_sample, ds->dim, ns, ds->pitch_bytes(), GN / gemm_ctas());
+    const CUtensorMap ms = make_map(ds->d_sample, ds->dim, ns, (uint64_t)ds->pitch * 4, GN / gemm_ctas());
     GemmParams ps = base_params(tq);
     ps.nrows = ns;
     ps.row_stride = 1;
@@ -963,7 +987,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     DevBuf cand((size_t)nq * cap * 8, st);
     VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
     {
-        const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, ds->pitch_bytes(), GN / gemm_ctas());
+        const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, (uint64_t)ds->pitch * 4, GN / gemm_ctas());
         GemmParams pf = base_params(tq);
         pf.sqnorm = ds->d_sqnorm;
         pf.rnorm = ds->d_lo;
@@ -1030,9 +1054,10 @@ static void flat_gemm_keys_chunk(const vdb_dataset* ds, const void* d_queries, u
         g_gemm_cands += h_cands;
         g_gemm_queries += nq;
         if (h_redo) {  // exact streaming scan for the queries whose candidate set could not be proven complete
-            DevBuf rq((size_t)h_redo * ds->dim * 4, st), rkeys((size_t)h_redo * k * 8, st);
-            gather_rows_kernel<<<h_redo, 128, 0, st>>>((const float*)d_queries, ds->dim, redo.as<uint32_t>(), h_redo,
-                                                       rq.as<float>());
+            const uint32_t row_bytes = ds->dim * ds->elem_size();
+            DevBuf rq((size_t)h_redo * row_bytes, st), rkeys((size_t)h_redo * k * 8, st);
+            gather_rows_kernel<<<h_redo, 128, 0, st>>>((const uint8_t*)d_queries, row_bytes, redo.as<uint32_t>(), h_redo,
+                                                       rq.as<uint8_t>());
             VDB_LAUNCHED();
             flat_scan_keys(ds, rq.p, h_redo, k, rkeys.as<uint64_t>(), st);
             scatter_keys_kernel<<<h_redo, 128, 0, st>>>(rkeys.as<uint64_t>(), k, redo.as<uint32_t>(), h_redo, d_keys);
@@ -1053,7 +1078,8 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     VDB_REQUIRE(flat_gemm_supported(ds, nq, k), "tensor-core Flat path: unsupported dataset/k");
     for (uint32_t q0 = 0; q0 < nq; q0 += G_QUERY_CHUNK) {
         const uint32_t cn = std::min(G_QUERY_CHUNK, nq - q0);
-        flat_gemm_keys_chunk(ds, (const float*)d_queries + (size_t)q0 * ds->dim, cn, k, d_keys + (size_t)q0 * k, st);
+        flat_gemm_keys_chunk(ds, (const uint8_t*)d_queries + (size_t)q0 * ds->dim * ds->elem_size(), cn, k,
+                             d_keys + (size_t)q0 * k, st);
     }
 }
 

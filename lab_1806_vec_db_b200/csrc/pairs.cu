@@ -22,6 +22,7 @@ struct PairParams {
     const float* cacheB;
     const uint8_t* valid;    // optional per-pair mask (invalid pairs are skipped, out = 0)
     bool vec4;               // f32 rows, dim % 4 == 0, 16-byte aligned bases and strides: use 128-bit loads
+    uint32_t chunk;          // scan-order modes: elements per lane and step (4 for f32 rows, 16 for u8 rows)
     uint32_t dim;
     uint64_t npairs;
     const uint64_t* npairs_dev;  // optional: the pair count lives on the device (npairs is then the grid bound)
@@ -84,10 +85,9 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
                     }
                 }
             } else
-            for (uint32_t c = lane; c * 4 < p.dim; c += 32) {
-#pragma unroll
-                for (uint32_t i = 0; i < 4; ++i) {
-                    const uint32_t e = c * 4 + i;
+            for (uint32_t c = lane; c * p.chunk < p.dim; c += 32) {
+                for (uint32_t i = 0; i < p.chunk; ++i) {
+                    const uint32_t e = c * p.chunk + i;
                     if (e < p.dim) {
                         const float xv = (float)b[e], qv = (float)a[e];
                         if (MODE == PM_L2_SCANORDER) {
@@ -213,12 +213,14 @@ void exact_pair_distances_masked(const vdb_dataset* ds, const void* d_queries, u
     p.npairs = npairs;
     p.npairs_dev = d_npairs;
     p.out = d_out;
-    const bool scan_order = ds->dtype == VDB_F32 && (ds->metric == VDB_L2SQR || d_qnorm != nullptr);
+    // the queries passed here are always the f32 copy; u8 rows are walked in the scan kernel's 16-element steps
+    const bool scan_order = ds->metric == VDB_L2SQR || d_qnorm != nullptr;
     p.cacheA = d_qnorm;
-    p.vec4 = scan_order && ds->dim % 4 == 0 && qpitch % 4 == 0 && ds->pitch % 4 == 0 &&
+    p.chunk = ds->dtype == VDB_F32 ? 4 : 16;
+    p.vec4 = scan_order && ds->dtype == VDB_F32 && ds->dim % 4 == 0 && qpitch % 4 == 0 && ds->pitch % 4 == 0 &&
              ((uintptr_t)d_queries & 15) == 0 && ((uintptr_t)ds->d_rows & 15) == 0;
     const int so_mode = ds->metric == VDB_L2SQR ? PM_L2_SCANORDER : PM_COS_SCANORDER;
-    launch_pairs(scan_order ? so_mode : (ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE), false, ds->dtype, p, st);
+    launch_pairs(scan_order ? so_mode : (ds->metric == VDB_L2SQR ? PM_L2 : PM_COSINE), true, ds->dtype, p, st);
 }
 
 void cached_pair_distances(const vdb_dataset* ds, const void* d_queries, const float* d_qcache,

@@ -60,7 +60,7 @@ class ShardedFlatIndex:
             import torch
             lib = L.lib()
             n, ns, mn = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
-            ok = (self.vec_set.dtype == np.float32 and
+            ok = (self.vec_set.dtype in (np.float32, np.uint8) and
                   lib.vdb_tq_info(self.vec_set._h, C.byref(n), C.byref(ns), C.byref(mn)) == L.OK)
             t = torch.tensor([float(n.value), float(ns.value), 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
             m = torch.tensor([mn.value], dtype=torch.float32, device=dev)

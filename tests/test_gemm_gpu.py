@@ -163,11 +163,36 @@ def test_cosine_tensor_path_zero_vectors_and_signs(oracle):
     assert tens[0][4, 0] == 1234
 
 
-def test_auto_path_keeps_scan_for_unsupported_cases(oracle):
-    """u8 rows have no tensor route: the auto path must silently use the exact scan (same results)."""
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_u8_rows_through_the_tensor_path(oracle, metric):
+    """u8 rows and queries are exact in TF32, so the pruning bound only carries the accumulation term; results must
+    be bit-identical to the forced scan (16-element steps of the u8 scan kernel) and match the oracle."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(8)
+    proto = rng.integers(0, 200, (64, 100), dtype=np.uint8)
+    base = np.clip(proto[rng.integers(0, 64, 70_000)].astype(np.int16) + rng.integers(-20, 21, (70_000, 100)), 0, 255).astype(np.uint8)
+    q = np.clip(proto[rng.integers(0, 64, 150)].astype(np.int16) + rng.integers(-20, 21, (150, 100)), 0, 255).astype(np.uint8)
+    base[900:910] = base[3]
+    idx = V.FlatIndex.from_vec_set(base, metric)
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, 20)
+        L.check(lib.vdb_flat_set_path(2))
+        tens = idx.knn_batch(q, 20)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    want = oracle.flat_knn(base, q[:24], 20, metric, 8)
+    assert_knn_parity(base, q[:24], metric, tuple(a[:24] for a in tens), want, oracle)
+
+
+def test_auto_path_keeps_scan_for_small_shards(oracle):
+    """Shards under 65536 rows have no tensor route: the auto path must silently use the exact scan."""
     import lab_1806_vec_db_b200 as V
     rng = np.random.default_rng(3)
-    b8 = rng.integers(0, 256, (70_000, 32), dtype=np.uint8)
+    b8 = rng.integers(0, 256, (7_000, 32), dtype=np.uint8)
     q8 = rng.integers(0, 256, (20, 32), dtype=np.uint8)
     got = V.FlatIndex.from_vec_set(b8, "l2sqr").knn_batch(q8, 5)
     want = oracle.flat_knn(b8, q8, 5, "l2sqr", 8)
