@@ -49,6 +49,8 @@ def main():
     ap.add_argument("--nq", type=int, default=1000)
     ap.add_argument("--what", default="ivf,pq")
     ap.add_argument("--cpu-queries", type=int, default=8)
+    ap.add_argument("--pq-m", type=int, default=240)
+    ap.add_argument("--ef", default="240:600:60", help="start:end:step of the PQ ef sweep")
     args = ap.parse_args()
     import torch
     import lab_1806_vec_db_b200 as V
@@ -121,11 +123,12 @@ def main():
 
     if "pq" in args.what:
         t0 = time.perf_counter()
-        cfg = V.PQConfig(4, 240, "l2sqr", 10_000, 20, 1e-6)
-        train = np.ascontiguousarray(base_host[rng.permutation(args.n)[:10_000]])
+        M = args.pq_m
+        cfg = V.PQConfig(4, M, "l2sqr", min(10_000, args.n), 20, 1e-6)
+        train = np.ascontiguousarray(base_host[rng.permutation(args.n)[:min(10_000, args.n)]])
         books = []
         train_dev = V.DeviceVecSet(train, "l2sqr")
-        for lo, hi in V.pq_groups(DIM, 240):
+        for lo, hi in V.pq_groups(DIM, M):
             km = V.KMeans.from_vec_set(train_dev, V.KMeansConfig(16, 20, 1e-6, "l2sqr", (lo, hi)), rng)
             books.append(km.centroids.reshape(-1))
         train_dev.close()
@@ -136,13 +139,14 @@ def main():
         t_encode = time.perf_counter() - t0
         ns = 2000
         t0 = time.perf_counter()
-        c_cpu = O.pq_encode(base_host[:ns], books, 240, 4, "l2sqr", nthreads=1)  # the reference encodes serially
+        c_cpu = O.pq_encode(base_host[:ns], books, M, 4, "l2sqr", nthreads=1)  # the reference encodes serially
         cpu_encode_s = (time.perf_counter() - t0) * args.n / ns
         assert (c_cpu == pq.encoded_vec_set[:ns]).all(), "PQ codes differ from the oracle"
-        print(json.dumps({"config": "C4 PQ build", "n": args.n, "m": 240, "n_bits": 4, "gpu_train_s": t_train,
+        print(json.dumps({"config": "C4 PQ build", "n": args.n, "m": M, "n_bits": 4, "gpu_train_s": t_train,
                           "gpu_encode_s_incl_d2h": t_encode, "cpu_encode_s_extrapolated_1_thread": cpu_encode_s,
                           "codes_bit_exact_vs_oracle_on_rows": ns}), flush=True)
-        for ef in range(240, 601, 60):
+        e0, e1, es = (int(x) for x in args.ef.split(":"))
+        for ef in range(e0, e1 + 1, es):
             ids, dd, cnt = dev_out()
 
             def run():
@@ -153,13 +157,13 @@ def main():
             rec = recall_at(ids.cpu().numpy(), gt_ids)
             nc = args.cpu_queries
             t0 = time.perf_counter()
-            oi, od, oc = O.flat_knn_pq(base_host, pq.encoded_vec_set, books, 240, 4, q_host[:nc], k, ef, "l2sqr",
+            oi, od, oc = O.flat_knn_pq(base_host, pq.encoded_vec_set, books, M, 4, q_host[:nc], k, ef, "l2sqr",
                                        nthreads=cores)
             cpu_qps = nc / (time.perf_counter() - t0)
             same = float((ids[:nc].cpu().numpy() == oi.astype(np.int64)).mean())
-            gbs = args.n * 120 * ((args.nq + 3) // 4) / (ms * 1e-3) / 1e9
+            gbs = args.n * ((M + 1) // 2) * ((args.nq + 3) // 4) / (ms * 1e-3) / 1e9
             print(json.dumps({"config": "C4 Flat+PQ search", "ef": ef, "k": k, "nq": args.nq, "qps": args.nq / ms * 1e3,
-                              "ms_per_batch": ms, "recall@10": rec, "code_bytes_per_pass": args.n * 120,
+                              "ms_per_batch": ms, "recall@10": rec, "code_bytes_per_pass": args.n * ((M + 1) // 2),
                               "achieved_code_gbs": gbs, "cpu_qps": cpu_qps, "cpu_cores": cores, "cpu_queries": nc,
                               "gpu_vs_oracle_exact_id_rate": same}), flush=True)
 

@@ -175,10 +175,10 @@ struct AdcParams {
     const uint32_t* codes_t;
     uint64_t n;
     uint32_t words, m, kc;
-    const float* lut;         // [nq_pass][m*kc]
+    const float* lut;         // [nq][m*kc]   (blockIdx.y selects the group of NQ queries)
     const float* dist_cache;  // [m*kc]
-    const float* qcache;      // [nq_pass]
-    uint32_t nq_valid;
+    const float* qcache;      // [nq]
+    uint32_t nq_total;        // queries of this launch
     uint32_t K, P, limit;
     uint32_t id_base;
     uint32_t iters;           // row tiles per CTA
@@ -188,9 +188,16 @@ struct AdcParams {
 
 // LUT_SMEM: lookup tables staged in shared memory (4-bit codes); otherwise read through L1 (8-bit codes)
 template <int NQ, int NBITS, int METRIC, bool LUT_SMEM>
-__global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParams p) {
+__global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(AdcParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tab = p.m * p.kc;
+    // this CTA's group of NQ queries
+    const uint32_t q_first = blockIdx.y * NQ;
+    const uint32_t nq_valid = min((uint32_t)NQ, p.nq_total - q_first);
+    p.lut += (size_t)q_first * tab;
+    p.qcache += q_first;
+    if (p.partial) p.partial += (size_t)q_first * gridDim.x * p.K;
+    if (p.all_out) p.all_out += (size_t)q_first * p.n;
     float* s_lut = reinterpret_cast<float*>(smem);
     float* s_dc = s_lut + (LUT_SMEM ? (size_t)NQ * tab : 0);
     uint8_t* after = reinterpret_cast<uint8_t*>(s_dc + ((LUT_SMEM && METRIC == VDB_COSINE) ? tab : 0));
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParam
     TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
     if (LUT_SMEM) {
         for (uint32_t i = threadIdx.x; i < NQ * tab; i += blockDim.x)
-            s_lut[i] = (i / tab < p.nq_valid) ? p.lut[i] : 0.f;
+            s_lut[i] = (i / tab < nq_valid) ? p.lut[i] : 0.f;
         if (METRIC == VDB_COSINE)
             for (uint32_t i = threadIdx.x; i < tab; i += blockDim.x) s_dc[i] = p.dist_cache[i];
     }
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParam
     const int lane = threadIdx.x & 31;
     float qn[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) qn[q] = (METRIC == VDB_COSINE && q < (int)p.nq_valid) ? p.qcache[q] : 0.f;
+    for (int q = 0; q < NQ; ++q) qn[q] = (METRIC == VDB_COSINE && q < (int)nq_valid) ? p.qcache[q] : 0.f;
     constexpr int KC = NBITS == 4 ? 16 : 256;
 
     // one table lookup for all NQ queries; the branch on LUT_SMEM is compile-time so the shared-memory path
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParam
         bool want = false;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            if (q < (int)p.nq_valid && in) {
+            if (q < (int)nq_valid && in) {
                 float d = sum[q];
                 if (METRIC == VDB_COSINE) {
                     const float den = fmaxf(__fmul_rn(sqrtf(cdp), qn[q]), 1e-10f);
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(ADC_THREADS) pq_adc_scan_kernel(const AdcParam
     }
     if (do_topk) {
         topk.final_flush();
-        for (uint32_t i = threadIdx.x; i < p.nq_valid * p.K; i += blockDim.x) {
+        for (uint32_t i = threadIdx.x; i < nq_valid * p.K; i += blockDim.x) {
             const uint32_t qi = i / p.K, j = i - qi * p.K;
             p.partial[((size_t)qi * gridDim.x + blockIdx.x) * p.K + j] = topk.seg(qi)[j];
         }
@@ -438,13 +445,13 @@ __global__ void scatter_u64_rows_kernel(const uint64_t* __restrict__ src, uint32
 constexpr size_t ADC_SMEM_MAX = 200 * 1024;
 
 template <int NQ>
-static void adc_launch(const vdb_pq* pq, const AdcParams& p, bool lut_smem, uint32_t grid, size_t smem,
+static void adc_launch(const vdb_pq* pq, const AdcParams& p, bool lut_smem, uint32_t grid, uint32_t groups, size_t smem,
                        cudaStream_t st) {
     auto go = [&](auto kern) {
         if (smem > 48 * 1024)
             VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADC_SMEM_MAX));
         ProfScope prof("pq_adc", st);
-        kern<<<grid, ADC_THREADS, smem, st>>>(p);
+        kern<<<dim3(grid, groups), ADC_THREADS, smem, st>>>(p);
         VDB_LAUNCHED();
     };
     const bool cosine = pq->metric == VDB_COSINE;
@@ -482,6 +489,7 @@ static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache
     static const int nqt_env = getenv("VDB_ADC_NQ") ? atoi(getenv("VDB_ADC_NQ")) : 0;
     int nqt = (nqt_env == 1 || nqt_env == 2 || nqt_env == 4) ? nqt_env : 4;
     bool lut_smem = true;
+    while (nqt > 1 && (uint32_t)(nqt >> 1) >= nq) nqt >>= 1;  // no wider than the batch
     while (nqt > 1 && smem_for(nqt, true) > ADC_SMEM_MAX) nqt >>= 1;
     if (smem_for(nqt, true) > ADC_SMEM_MAX) lut_smem = false;
     VDB_REQUIRE(smem_for(nqt, lut_smem) <= ADC_SMEM_MAX, "ADC scan: ef=%u too large for the fused top-k", K);
@@ -503,33 +511,29 @@ static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache
     p.iters = (uint32_t)ceil_div<uint64_t>(tiles, grid);
     const size_t per_q = (size_t)grid * K * 8;
     uint32_t chunk = topk ? (uint32_t)std::max<size_t>(4, (size_t)(64u << 20) / std::max<size_t>(per_q, 1)) : nq;
-    chunk = std::min(round_up(chunk, 4u), round_up(nq, 4u));
+    chunk = std::min(std::min(round_up(chunk, 4u), round_up(nq, 4u)), 65535u * (uint32_t)nqt);  // gridDim.y limit
     DevBuf partial(topk ? per_q * chunk : 0, st);
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t qn = std::min(chunk, nq - q0);
-        for (uint32_t qq = 0; qq < qn;) {
-            const uint32_t left = qn - qq;
-            int t = nqt;
-            while (t > 1 && (uint32_t)(t >> 1) >= left) t >>= 1;
-            const uint32_t now = std::min<uint32_t>(left, t);
-            p.lut = d_lut + (size_t)(q0 + qq) * tab;
-            p.qcache = d_qcache + (q0 + qq);
-            p.nq_valid = now;
-            p.partial = topk ? partial.as<uint64_t>() + (size_t)qq * grid * K : nullptr;
-            p.all_out = topk ? nullptr : d_all + (size_t)(q0 + qq) * pq->n;
-            const size_t smem = smem_for(t, lut_smem);
-            switch (t) {
-                case 1: adc_launch<1>(pq, p, lut_smem, grid, smem, st); break;
-                case 2: adc_launch<2>(pq, p, lut_smem, grid, smem, st); break;
-                default: adc_launch<4>(pq, p, lut_smem, grid, smem, st); break;
-            }
-            qq += now;
+        // one launch for all query groups of the chunk: blockIdx.y = group of nqt queries
+        p.lut = d_lut + (size_t)q0 * tab;
+        p.qcache = d_qcache + q0;
+        p.nq_total = qn;
+        p.partial = topk ? partial.as<uint64_t>() : nullptr;
+        p.all_out = topk ? nullptr : d_all + (size_t)q0 * pq->n;
+        const uint32_t groups = ceil_div(qn, (uint32_t)nqt);
+        const size_t smem = smem_for(nqt, lut_smem);
+        switch (nqt) {
+            case 1: adc_launch<1>(pq, p, lut_smem, grid, groups, smem, st); break;
+            case 2: adc_launch<2>(pq, p, lut_smem, grid, groups, smem, st); break;
+            default: adc_launch<4>(pq, p, lut_smem, grid, groups, smem, st); break;
         }
         if (topk)
             launch_merge_keys(partial.as<uint64_t>(), grid, qn, K, false, K, d_keys + (size_t)q0 * K, nullptr,
                               nullptr, nullptr, st);
     }
 }
+
 
 static void adc_scan(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K,
                      uint32_t id_base, uint64_t* d_keys, float* d_all, cudaStream_t st);
