@@ -23,7 +23,9 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "index.cuh"
 #include "topk.cuh"
@@ -204,6 +206,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 }
 
 // ---- kernel ----------------------------------------------------------------------------------------------------
+// one unit of work: query rows [q0, q_end) (at most GM * CTAS of them) against database rows [r0, r_end)
+struct GemmItem {
+    uint32_t q0, q_end;
+    uint64_t r0, r_end;
+};
+struct ItemView {
+    uint32_t q0, q_end, ntile, slab;
+    uint64_t r0, r_end;
+};
+
 struct GemmParams {
     uint32_t nq;            // queries
     uint64_t nrows;         // rows addressed by the B tensor map (sample rows or all rows)
@@ -227,7 +239,32 @@ struct GemmParams {
     uint64_t* cand;         // [nq][cap]  (S' bits << 32 | local row)
     uint32_t cap;
     uint32_t* work_counter; // dynamic item scheduler (zeroed before the launch)
+    // table mode (IVF: one rectangular block per (list, query group)): explicit items instead of the slab x unit grid
+    const GemmItem* items;  // nullptr -> the grid of plan_gemm
+    uint32_t nitems;
+    const uint32_t* qmap;   // table mode: row of the gathered query matrix -> query that owns the candidate list
 };
+
+template <int CTAS>
+__device__ __forceinline__ ItemView decode_item(const GemmParams& p, uint32_t item) {
+    ItemView v;
+    if (p.items) {
+        const GemmItem it = p.items[item];
+        v.q0 = it.q0;
+        v.q_end = it.q_end;
+        v.r0 = it.r0;
+        v.r_end = it.r_end;
+        v.slab = item;
+    } else {
+        v.slab = item / p.nqt;
+        v.q0 = (item - v.slab * p.nqt) * GM * CTAS;
+        v.q_end = p.nq;
+        v.r0 = (uint64_t)v.slab * p.tiles_per_slab * GN;
+        v.r_end = min(p.nrows, v.r0 + (uint64_t)p.tiles_per_slab * GN);
+    }
+    v.ntile = (uint32_t)((v.r_end - v.r0 + GN - 1) / GN);
+    return v;
+}
 
 template <int MODE, int CTAS, int METRIC>
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -278,7 +315,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint32_t items = p.nqt * p.nslabs;
+    const uint32_t items = p.items ? p.nitems : p.nqt * p.nslabs;
     // ---- dynamic scheduler: the leader's producer draws item ids from a global counter and publishes them to
     // every role of the CTA (pair) through a small shared-memory queue. Items are taken in global order, so the
     // CTAs in flight always work on neighbouring slabs (shared in L2) no matter how their speeds drift apart.
@@ -314,23 +351,23 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     item = take_item(n);
                 }
                 if (item == G_NO_ITEM) break;
-                const uint32_t slab = item / p.nqt, qt = (item - slab * p.nqt) * CTAS + cta_rank;
-                const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
-                for (uint32_t t = t0; t < t1; ++t) {
+                const ItemView iv = decode_item<CTAS>(p, item);
+                const int qrow = (int)(iv.q0 + cta_rank * GM);
+                for (uint32_t t = 0; t < iv.ntile; ++t) {
+                    const int brow = (int)(iv.r0 + (uint64_t)t * GN + cta_rank * Cfg::B_ROWS);
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
                         if (CTAS == 1) {
                             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                            tma_load_2d(sa, &map_q, (int)(kb * GK), (int)(qt * GM), &full_bar[stage]);
-                            tma_load_2d(sa + G_A_BYTES, &map_x, (int)(kb * GK), (int)(t * GN), &full_bar[stage]);
+                            tma_load_2d(sa, &map_q, (int)(kb * GK), qrow, &full_bar[stage]);
+                            tma_load_2d(sa + G_A_BYTES, &map_x, (int)(kb * GK), brow, &full_bar[stage]);
                         } else {
                             // both CTAs' bytes are accounted on the LEADER's barrier
                             if (leader) mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * CTAS);
                             const uint32_t lbar = smem_u32(&full_bar[stage]) & PEER_MASK;
-                            tma_load_2d_2sm(sa, &map_q, (int)(kb * GK), (int)(qt * GM), lbar);
-                            tma_load_2d_2sm(sa + G_A_BYTES, &map_x, (int)(kb * GK),
-                                            (int)(t * GN + cta_rank * Cfg::B_ROWS), lbar);
+                            tma_load_2d_2sm(sa, &map_q, (int)(kb * GK), qrow, lbar);
+                            tma_load_2d_2sm(sa + G_A_BYTES, &map_x, (int)(kb * GK), brow, lbar);
                         }
                         if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
@@ -344,9 +381,8 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (uint32_t n = 0;; ++n) {
                 const uint32_t item = take_item(n);
                 if (item == G_NO_ITEM) break;
-                const uint32_t slab = item / p.nqt;
-                const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
-                for (uint32_t t = t0; t < t1; ++t) {
+                const ItemView iv = decode_item<CTAS>(p, item);
+                for (uint32_t t = 0; t < iv.ntile; ++t) {
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * GN;
@@ -381,10 +417,11 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (lane == 0) item = take_item(n);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item == G_NO_ITEM) break;
-            const uint32_t slab = item / p.nqt, qt = (item - slab * p.nqt) * CTAS + cta_rank;
-            const uint32_t t0 = slab * p.tiles_per_slab, t1 = min(p.ntiles, t0 + p.tiles_per_slab);
-            const uint32_t q = qt * GM + threadIdx.x;
-            const bool qok = q < p.nq;
+            const ItemView iv = decode_item<CTAS>(p, item);
+            const uint32_t slab = iv.slab;
+            const uint32_t q = iv.q0 + cta_rank * GM + threadIdx.x;   // row of the (gathered) query matrix
+            const bool qok = q < iv.q_end;
+            const uint32_t oq = (qok && p.qmap) ? p.qmap[q] : q;        // query that owns the candidate list
             const float cq = qok ? p.qcm[q] : 0.f;
             const float qn = (METRIC == VDB_COSINE && qok) ? p.qnorm[q] : 0.f;
             float tau = 0.f;
@@ -394,13 +431,14 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) best[i] = __uint_as_float(0x7f800000u);
             }
-            for (uint32_t t = t0; t < t1; ++t) {
+            for (uint32_t t = 0; t < iv.ntile; ++t) {
                 // stage the row-norm tiles of this N-tile (2 x GN floats) while the MMAs run
                 float* sq = norm_tiles + acc * 2 * GN;
                 float* rn = sq + GN;
+                const uint64_t tile_row0 = iv.r0 + (uint64_t)t * GN;
                 for (uint32_t c = threadIdx.x; c < GN; c += 128) {
-                    const uint64_t brow = (uint64_t)t * GN + c;
-                    const bool ok = brow < p.nrows;
+                    const uint64_t brow = tile_row0 + c;
+                    const bool ok = brow < iv.r_end;
                     const uint64_t row = brow * p.row_stride;
                     sq[c] = ok ? p.sqnorm[row] : __uint_as_float(0x7f800000u);  // +inf: never a candidate
                     rn[c] = ok ? p.rnorm[row] : 0.f;
@@ -426,11 +464,11 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                 // norm product falls under the reference's 1e-10 clamp are always kept (sq = 1/||x||)
                                 s = fmaf(-(cq * sq[c0 + j]), dot, p.kc);
                                 if (qn * rn[c0 + j] < 2e-10f) s = __uint_as_float(0xff800000u);
-                                if ((uint64_t)t * GN + c0 + j >= p.nrows) s = __uint_as_float(0x7f800000u);  // padding row
+                                if (tile_row0 + c0 + j >= iv.r_end) s = __uint_as_float(0x7f800000u);  // padding row
                             }
                             if (MODE == 0) {
-                                const uint64_t brow = (uint64_t)t * GN + c0 + j;
-                                if (brow < p.nrows) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(s, (uint32_t)brow);
+                                const uint64_t brow = tile_row0 + c0 + j;
+                                if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(s, (uint32_t)brow);
                             } else if (MODE == 2) {
                                 if (s < best[G_TOPJ - 1]) {  // rare after the first few hundred rows: bubble s into place
                                     float v = s;
@@ -442,10 +480,10 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                     }
                                 }
                             } else if (s < tau) {
-                                const uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
+                                const uint32_t pos = atomicAdd(&p.cand_cnt[oq], 1u);
                                 if (pos < p.cap)
-                                    p.cand[(uint64_t)q * p.cap + pos] =
-                                        ((uint64_t)__float_as_uint(s) << 32) | (uint32_t)((uint64_t)t * GN + c0 + j);
+                                    p.cand[(uint64_t)oq * p.cap + pos] =
+                                        ((uint64_t)__float_as_uint(s) << 32) | (uint32_t)(tile_row0 + c0 + j);
                             }
                         }
                     }
@@ -657,7 +695,7 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
         configured = true;
     }
     const uint32_t sms = (uint32_t)sm_count();
-    const uint32_t units = std::min(sms / CTAS, p.nqt * p.nslabs);
+    const uint32_t units = std::min(sms / CTAS, p.items ? p.nitems : p.nqt * p.nslabs);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units * CTAS);
     cfg.blockDim = dim3(G_THREADS);
@@ -756,14 +794,15 @@ __global__ void __launch_bounds__(1024) cand_offsets_kernel(const uint32_t* __re
 }
 // candidate (S', local row) lists -> dense rerank inputs at off[q]
 __global__ void cand_to_pairs_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap,
-                                     const uint64_t* __restrict__ off, uint32_t* __restrict__ qidx,
-                                     uint32_t* __restrict__ rid) {
+                                     const uint64_t* __restrict__ off, const uint32_t* __restrict__ pos_to_row,
+                                     uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid) {
     const uint32_t q = blockIdx.x;
     const uint32_t c = min(cnt[q], cap);
     const uint64_t o = off[q];
     for (uint32_t j = threadIdx.x; j < c; j += blockDim.x) {
         qidx[o + j] = q;
-        rid[o + j] = (uint32_t)cand[(uint64_t)q * cap + j];
+        const uint32_t pos = (uint32_t)cand[(uint64_t)q * cap + j];
+        rid[o + j] = pos_to_row ? pos_to_row[pos] : pos;  // IVF: list-order position -> row id
     }
 }
 __global__ void rekey_dev_count_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ ids, uint32_t id_base,
@@ -1005,7 +1044,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     DevBuf off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st), keys2(total * 8, st);
     cand_offsets_kernel<<<1, 1024, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
     VDB_LAUNCHED();
-    cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, off.as<uint64_t>(),
+    cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, off.as<uint64_t>(), nullptr,
                                              qidx.as<uint32_t>(), rid.as<uint32_t>());
     VDB_LAUNCHED();
     const uint64_t* d_total = off.as<uint64_t>() + nq;
@@ -1081,6 +1120,246 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
         flat_gemm_keys_chunk(ds, (const uint8_t*)d_queries + (size_t)q0 * ds->dim * ds->elem_size(), cn, k,
                              d_keys + (size_t)q0 * k, st);
     }
+}
+
+
+// ---- IVF probe scan on the tensor cores ---------------------------------------------------------------------------
+// A batch of queries probing nlist lists is a block-sparse contraction: list l's rows x the queries that probe l.
+// Rows and norms are kept a second time in LIST ORDER (position p <-> members[p]) so every list is a contiguous row
+// range the TMA can tile; the queries are gathered list by list into one matrix; the work items of the contraction
+// kernel are (list, tile of <= 256 gathered queries, range of row tiles). The threshold needs no sampling here:
+// tau_q = the k-th smallest EXACT distance over the first S rows of q's visit sequence. Every probed row with
+// d <= that value has S' <= d - ||q||^2 <= tau_q, so the candidate set provably contains q's k best probed rows;
+// only a candidate-list overflow sends a query back to the FP32 list scan.
+__global__ void gather_round_rows_kernel(const float* __restrict__ rows_tf32, const float* __restrict__ colA,
+                                         const float* __restrict__ rn, const uint32_t* __restrict__ members, uint64_t n,
+                                         uint32_t pitch, float* __restrict__ out, float* __restrict__ outA,
+                                         float* __restrict__ outR) {
+    const uint64_t p = blockIdx.x;
+    if (p >= n) return;
+    const uint64_t row = members[p];
+    const float4* src = reinterpret_cast<const float4*>(rows_tf32 + row * pitch);
+    float4* dst = reinterpret_cast<float4*>(out + p * pitch);
+    for (uint32_t e = threadIdx.x; e < pitch / 4; e += blockDim.x) dst[e] = src[e];
+    if (threadIdx.x == 0) {
+        outA[p] = colA[row];
+        outR[p] = rn[row];
+    }
+}
+
+static std::mutex g_ivf_side_mu;
+static void ensure_ivf_side(const vdb_dataset* ds, const vdb_ivf* civf, cudaStream_t st) {
+    vdb_ivf* ivf = const_cast<vdb_ivf*>(civf);
+    std::lock_guard<std::mutex> lk(g_ivf_side_mu);
+    if (ivf->d_rows_lo) return;
+    ensure_side_arrays(ds, st);
+    VDB_CUDA(cudaMalloc(&ivf->d_rows_lo, ds->n * (size_t)ds->pitch * 4));
+    VDB_CUDA(cudaMalloc(&ivf->d_colA_lo, ds->n * 4));
+    VDB_CUDA(cudaMalloc(&ivf->d_rn_lo, ds->n * 4));
+    gather_round_rows_kernel<<<(uint32_t)ds->n, 128, 0, st>>>(ds->d_tf32, ds->d_sqnorm, ds->d_lo, ivf->d_members, ds->n, ds->pitch,
+                                                             ivf->d_rows_lo, ivf->d_colA_lo, ivf->d_rn_lo);
+    VDB_LAUNCHED();
+    VDB_CUDA(cudaStreamSynchronize(st));
+}
+
+// first S rows of every query's visit sequence (probed lists in probe order) as rerank pairs
+__global__ void ivf_subset_kernel(const uint64_t* __restrict__ probes, uint32_t nprobe, const uint64_t* __restrict__ offsets,
+                                  const uint32_t* __restrict__ members, uint32_t S, uint32_t* __restrict__ qidx,
+                                  uint32_t* __restrict__ rid, uint8_t* __restrict__ valid) {
+    const uint32_t q = blockIdx.x;
+    for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
+        uint32_t left = s, row = 0;
+        bool ok = false;
+        for (uint32_t j = 0; j < nprobe && !ok; ++j) {
+            const uint64_t pk = probes[(size_t)q * nprobe + j];
+            if (pk == KEY_NONE) break;
+            const uint32_t c = key_id(pk);
+            const uint64_t len = offsets[c + 1] - offsets[c];
+            if (left < len) {
+                row = members[offsets[c] + left];
+                ok = true;
+            } else {
+                left -= (uint32_t)len;
+            }
+        }
+        qidx[(size_t)q * S + s] = q;
+        rid[(size_t)q * S + s] = row;
+        valid[(size_t)q * S + s] = ok;
+    }
+}
+// tau' in the units of the pruning score: L2Sqr: d_k - ||q||^2, cosine: d_k; +inf when fewer than k rows are probed
+__global__ void ivf_tau_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, const float* __restrict__ qsq,
+                               float* __restrict__ tau) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint64_t kk = keys[(size_t)q * k + (k - 1)];
+    if (kk == KEY_NONE) {
+        tau[q] = __uint_as_float(0x7f800000u);
+        return;
+    }
+    const float dk = key_dist(kk);
+    const float shift = qsq ? qsq[q] : 0.f;
+    tau[q] = (dk - shift) + 2e-5f * (fabsf(dk) + shift) + 1e-30f;
+}
+__global__ void gather_query_side_kernel(const float* __restrict__ qround, uint32_t qpitch, const float* __restrict__ qcm,
+                                         const float* __restrict__ qnorm, const float* __restrict__ tau,
+                                         const uint32_t* __restrict__ qmap, uint32_t G, float* __restrict__ outq,
+                                         float* __restrict__ out_qcm, float* __restrict__ out_qnorm, float* __restrict__ out_tau) {
+    const uint32_t g = blockIdx.x;
+    if (g >= G) return;
+    const uint32_t q = qmap[g];
+    const float4* src = reinterpret_cast<const float4*>(qround + (size_t)q * qpitch);
+    float4* dst = reinterpret_cast<float4*>(outq + (size_t)g * qpitch);
+    for (uint32_t e = threadIdx.x; e < qpitch / 4; e += blockDim.x) dst[e] = src[e];
+    if (threadIdx.x == 0) {
+        out_qcm[g] = qcm[q];
+        if (qnorm) out_qnorm[g] = qnorm[q];
+        out_tau[g] = tau[q];
+    }
+}
+__global__ void overflow_list_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap, uint32_t* __restrict__ list,
+                                     uint32_t* __restrict__ nlist) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq && cnt[q] > cap) list[atomicAdd(nlist, 1u)] = q;
+}
+
+bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
+                     const std::vector<uint64_t>& h_probes, const std::vector<uint64_t>& h_off, uint32_t nq, uint32_t nprobe,
+                     uint32_t k, uint64_t* d_keys, cudaStream_t st) {
+    if (!flat_gemm_supported(ds, nq, k) || ds->dtype != VDB_F32 || k > 512) return false;
+    ensure_ivf_side(ds, ivf, st);
+    const uint32_t ctas = (uint32_t)gemm_ctas();
+    const uint32_t QT = GM * ctas;
+    // ---- host: group the (query, list) pairs by list, build the gathered query order and the work items ----
+    std::vector<std::vector<uint32_t>> by_list(ivf->nlist);
+    for (uint32_t q = 0; q < nq; ++q)
+        for (uint32_t j = 0; j < nprobe; ++j) {
+            const uint64_t pk = h_probes[(size_t)q * nprobe + j];
+            if (pk != KEY_NONE) by_list[key_id(pk)].push_back(q);
+        }
+    std::vector<uint32_t> qmap;
+    std::vector<GemmItem> items;
+    qmap.reserve((size_t)nq * nprobe);
+    const uint32_t tiles_per_item = 8;
+    for (uint32_t l = 0; l < ivf->nlist; ++l) {
+        const uint64_t r0 = h_off[l], r1 = h_off[l + 1];
+        if (r1 == r0 || by_list[l].empty()) continue;
+        const uint32_t g0 = (uint32_t)qmap.size();
+        qmap.insert(qmap.end(), by_list[l].begin(), by_list[l].end());
+        const uint32_t g1 = (uint32_t)qmap.size();
+        // row ranges outermost, query tiles innermost: CTAs in flight share the same rows in L2
+        for (uint64_t r = r0; r < r1; r += (uint64_t)tiles_per_item * GN)
+            for (uint32_t g = g0; g < g1; g += QT)
+                items.push_back(GemmItem{g, std::min(g1, g + QT), r, std::min<uint64_t>(r1, r + (uint64_t)tiles_per_item * GN)});
+    }
+    if (items.empty()) {
+        VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
+        return true;
+    }
+    const uint32_t G = (uint32_t)qmap.size();
+    vdb_tq* tq = tensor_begin(ds, d_queries, nq, st);
+    try {
+        const bool cosine = ds->metric == VDB_COSINE;
+        // ---- thresholds: exact distances over the first S rows of every visit sequence ----
+        // S balances the two exact-distance passes: S subset rows against ~k * visited / S surviving candidates
+        const double visited = (double)nprobe * (double)ds->n / (double)ivf->nlist;
+        static const uint32_t s_env = getenv("VDB_IVF_SUBSET") ? (uint32_t)atoi(getenv("VDB_IVF_SUBSET")) : 0;
+        const uint32_t S = s_env ? s_env
+                                 : std::min(4096u, (uint32_t)next_pow2(std::max<uint32_t>(std::max(256u, 2 * k),
+                                                                                         (uint32_t)std::sqrt((double)k * visited))));
+        DevBuf tau((size_t)nq * 4, st);
+        {
+            const uint64_t cnt = (uint64_t)nq * S;
+            DevBuf qidx(cnt * 4, st), rid(cnt * 4, st), valid(cnt, st), dist(cnt * 4, st), skeys(cnt * 8, st), kkeys((size_t)nq * k * 8, st);
+            ivf_subset_kernel<<<nq, 128, 0, st>>>(d_probes, nprobe, ivf->d_offsets, ivf->d_members, S, qidx.as<uint32_t>(),
+                                                  rid.as<uint32_t>(), valid.as<uint8_t>());
+            VDB_LAUNCHED();
+            exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), valid.as<uint8_t>(),
+                                        cnt, dist.as<float>(), st, nullptr, cosine ? tq->qtile.qcache.as<float>() : nullptr);
+            rekey_based(dist.as<float>(), rid.as<uint32_t>(), 0, valid.as<uint8_t>(), cnt, skeys.as<uint64_t>(), st);
+            launch_merge_keys(skeys.as<uint64_t>(), 1, nq, S, false, k, kkeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
+            ivf_tau_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(kkeys.as<uint64_t>(), nq, k, cosine ? nullptr : tq->qsq.as<float>(),
+                                                              tau.as<float>());
+            VDB_LAUNCHED();
+        }
+        // ---- gathered query matrix and its per-row scalars ----
+        DevBuf d_qmap((size_t)G * 4, st), d_items(items.size() * sizeof(GemmItem), st), qg((size_t)G * tq->qpitch * 4, st),
+            qcm_g((size_t)G * 4, st), qn_g((size_t)G * 4, st), tau_g((size_t)G * 4, st);
+        VDB_CUDA(cudaMemcpyAsync(d_qmap.p, qmap.data(), (size_t)G * 4, cudaMemcpyHostToDevice, st));
+        VDB_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(GemmItem), cudaMemcpyHostToDevice, st));
+        gather_query_side_kernel<<<G, 128, 0, st>>>(tq->qround.as<float>(), tq->qpitch, tq->qcm.as<float>(),
+                                                    cosine ? tq->qtile.qcache.as<float>() : nullptr, tau.as<float>(),
+                                                    d_qmap.as<uint32_t>(), G, qg.as<float>(), qcm_g.as<float>(),
+                                                    qn_g.as<float>(), tau_g.as<float>());
+        VDB_LAUNCHED();
+        // ---- filter pass over the probed (list, query tile) blocks ----
+        const uint32_t cap = 8192;
+        DevBuf cand((size_t)nq * cap * 8, st);
+        VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
+        {
+            const CUtensorMap mq = make_map(qg.as<float>(), ds->dim, G, (uint64_t)tq->qpitch * 4, GM);
+            const CUtensorMap mx = make_map(ivf->d_rows_lo, ds->dim, ds->n, (uint64_t)ds->pitch * 4, GN / ctas);
+            GemmParams pf{};
+            pf.nq = G;
+            pf.kblocks = ceil_div(ds->dim, (uint32_t)GK);
+            pf.qcm = qcm_g.as<float>();
+            pf.qnorm = cosine ? qn_g.as<float>() : nullptr;
+            pf.kc = tq->kc;
+            pf.sqnorm = ivf->d_colA_lo;
+            pf.rnorm = ivf->d_rn_lo;
+            pf.nrows = ds->n;
+            pf.row_stride = 1;
+            pf.tau = tau_g.as<float>();
+            pf.cand_cnt = tq->cnt.as<uint32_t>();
+            pf.cand = cand.as<uint64_t>();
+            pf.cap = cap;
+            pf.items = d_items.as<GemmItem>();
+            pf.nitems = (uint32_t)items.size();
+            pf.qmap = d_qmap.as<uint32_t>();
+            plan_gemm(pf);
+            launch_gemm(1, ds->metric, mq, mx, pf, st);
+        }
+        // ---- exact rerank (the FP32 list scan's arithmetic) and top-k ----
+        const uint64_t total = (uint64_t)nq * cap;
+        DevBuf off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st), keys2(total * 8, st);
+        cand_offsets_kernel<<<1, 1024, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
+        VDB_LAUNCHED();
+        cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, off.as<uint64_t>(),
+                                                 ivf->d_members, qidx.as<uint32_t>(), rid.as<uint32_t>());
+        VDB_LAUNCHED();
+        const uint64_t* d_total = off.as<uint64_t>() + nq;
+        exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
+                                    dist.as<float>(), st, d_total, cosine ? tq->qtile.qcache.as<float>() : nullptr);
+        rekey_dev_count_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(),
+                                                                        (uint32_t)ds->id_base, d_total, keys2.as<uint64_t>());
+        VDB_LAUNCHED();
+        launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, off.as<uint64_t>());
+        // ---- queries whose candidate list overflowed: FP32 list scan ----
+        DevBuf ovl((size_t)nq * 4, st), novl(4, st);
+        VDB_CUDA(cudaMemsetAsync(novl.p, 0, 4, st));
+        overflow_list_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, ovl.as<uint32_t>(), novl.as<uint32_t>());
+        VDB_LAUNCHED();
+        uint32_t h_n = 0;
+        VDB_CUDA(cudaMemcpyAsync(&h_n, novl.p, 4, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaStreamSynchronize(st));
+        if (h_n) {
+            std::vector<uint32_t> sel(h_n);
+            VDB_CUDA(cudaMemcpyAsync(sel.data(), ovl.p, (size_t)h_n * 4, cudaMemcpyDeviceToHost, st));
+            VDB_CUDA(cudaStreamSynchronize(st));
+            std::sort(sel.begin(), sel.end());
+            DevBuf rk((size_t)h_n * k * 8, st), dsel((size_t)h_n * 4, st);
+            ivf_list_major_subset(ds, ivf, d_queries, d_probes, sel.data(), h_n, nprobe, k, rk.as<uint64_t>(), st);
+            VDB_CUDA(cudaMemcpyAsync(dsel.p, sel.data(), (size_t)h_n * 4, cudaMemcpyHostToDevice, st));
+            scatter_keys_kernel<<<h_n, 128, 0, st>>>(rk.as<uint64_t>(), k, dsel.as<uint32_t>(), h_n, d_keys);
+            VDB_LAUNCHED();
+            VDB_CUDA(cudaStreamSynchronize(st));
+        }
+    } catch (...) {
+        tensor_end(tq);
+        throw;
+    }
+    tensor_end(tq);
+    return true;
 }
 
 // debug / test entry: S' keys of every (query, sampled row) pair, [nq][nrows] (mode 0 of the kernel)

@@ -35,6 +35,10 @@ struct vdb_ivf {
     uint64_t* d_offsets = nullptr;  // [nlist+1]
     uint32_t* d_members = nullptr;  // [n] local row ids, ascending inside a list
     uint32_t max_list = 0;
+    // lazily built for the tensor-core probe scan: rows / norms permuted into list order (position p <-> members[p])
+    float* d_rows_lo = nullptr;   // [n][pitch] TF32-rounded (u8: exact f32)
+    float* d_colA_lo = nullptr;   // [n] ||x||^2 (L2Sqr) or 1/||x|| (cosine)
+    float* d_rn_lo = nullptr;     // [n] ||x||
 };
 
 namespace vdb {
@@ -83,6 +87,13 @@ void rerank_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cons
 // ivf.cu
 vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nlist, uint32_t* h_assign_out);
 void ivf_destroy(vdb_ivf* ivf);
+// flat_gemm.cu: tensor-core probe scan for query batches (returns false when the shard / batch is not eligible)
+bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
+                     const std::vector<uint64_t>& h_probes, const std::vector<uint64_t>& h_off, uint32_t nq, uint32_t nprobe,
+                     uint32_t k, uint64_t* d_keys, cudaStream_t st);
+void ivf_list_major_subset(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
+                           const uint32_t* h_sel, uint32_t nsel, uint32_t nprobe, uint32_t k, uint64_t* d_keys_sel,
+                           cudaStream_t st);
 void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
                   uint32_t n_probes, uint64_t* d_keys, cudaStream_t st);
 

@@ -11,6 +11,7 @@
 // stream 8 rows at a time, partial top-k lists are merged per query. Ties at the k-th distance are resolved
 // by (distance, id) instead of the reference's visit order (documented in DESIGN.md; within the parity rule).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "index.cuh"
@@ -392,17 +393,15 @@ void ivf_destroy(vdb_ivf* ivf) {
     cudaFree(ivf->d_centroids);
     cudaFree(ivf->d_offsets);
     cudaFree(ivf->d_members);
+    cudaFree(ivf->d_rows_lo);
+    cudaFree(ivf->d_colA_lo);
+    cudaFree(ivf->d_rn_lo);
     delete ivf;
 }
 
-static void ivf_list_major(const vdb_dataset* ds, const vdb_ivf* ivf, const QueryTile& qt, const uint64_t* d_probes,
-                           uint32_t nq, uint32_t nprobe, uint32_t k, uint64_t* d_keys, cudaStream_t st) {
-    // probe table to the host (nq * nprobe keys), grouping on the host, item table back to the device
-    std::vector<uint64_t> probes((size_t)nq * nprobe);
-    VDB_CUDA(cudaMemcpyAsync(probes.data(), d_probes, probes.size() * 8, cudaMemcpyDeviceToHost, st));
-    std::vector<uint64_t> off(ivf->nlist + 1);
-    VDB_CUDA(cudaMemcpyAsync(off.data(), ivf->d_offsets, off.size() * 8, cudaMemcpyDeviceToHost, st));
-    VDB_CUDA(cudaStreamSynchronize(st));
+static void ivf_list_major(const vdb_dataset* ds, const vdb_ivf* ivf, const QueryTile& qt, const std::vector<uint64_t>& probes,
+                           const std::vector<uint64_t>& off, uint32_t nq, uint32_t nprobe, uint32_t k, uint64_t* d_keys,
+                           cudaStream_t st) {
     std::vector<std::vector<uint32_t>> by_list(ivf->nlist);
     for (uint32_t q = 0; q < nq; ++q)
         for (uint32_t j = 0; j < nprobe; ++j) {
@@ -492,6 +491,34 @@ static void ivf_list_major(const vdb_dataset* ds, const vdb_ivf* ivf, const Quer
     VDB_LAUNCHED();
 }
 
+__global__ void gather_bytes_rows_kernel(const uint8_t* __restrict__ src, uint32_t row_bytes, const uint32_t* __restrict__ idx,
+                                         uint32_t cnt, uint8_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x;
+    if (i >= cnt) return;
+    for (uint32_t e = threadIdx.x; e < row_bytes; e += blockDim.x)
+        dst[(size_t)i * row_bytes + e] = src[(size_t)idx[i] * row_bytes + e];
+}
+
+// FP32 list-major scan of a subset of the batch (queries h_sel[0..nsel)); keys out: [nsel][k]
+void ivf_list_major_subset(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
+                           const uint32_t* h_sel, uint32_t nsel, uint32_t nprobe, uint32_t k, uint64_t* d_keys_sel,
+                           cudaStream_t st) {
+    if (nsel == 0) return;
+    const uint32_t row_bytes = ds->dim * ds->elem_size();
+    DevBuf sel((size_t)nsel * 4, st), q((size_t)nsel * row_bytes, st), pr((size_t)nsel * nprobe * 8, st);
+    VDB_CUDA(cudaMemcpyAsync(sel.p, h_sel, (size_t)nsel * 4, cudaMemcpyHostToDevice, st));
+    gather_bytes_rows_kernel<<<nsel, 128, 0, st>>>((const uint8_t*)d_queries, row_bytes, sel.as<uint32_t>(), nsel, q.as<uint8_t>());
+    VDB_LAUNCHED();
+    gather_bytes_rows_kernel<<<nsel, 64, 0, st>>>((const uint8_t*)d_probes, nprobe * 8, sel.as<uint32_t>(), nsel, pr.as<uint8_t>());
+    VDB_LAUNCHED();
+    std::vector<uint64_t> h_probes((size_t)nsel * nprobe), h_off(ivf->nlist + 1);
+    VDB_CUDA(cudaMemcpyAsync(h_probes.data(), pr.p, h_probes.size() * 8, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaMemcpyAsync(h_off.data(), ivf->d_offsets, h_off.size() * 8, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaStreamSynchronize(st));
+    QueryTile qt = prepare_queries(ds, q.p, nsel, st);
+    ivf_list_major(ds, ivf, qt, h_probes, h_off, nsel, nprobe, k, d_keys_sel, st);
+}
+
 void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
                   uint32_t n_probes, uint64_t* d_keys, cudaStream_t st) {
     VDB_REQUIRE(n_probes > 0, "The number of probes should be greater than 0.");
@@ -511,11 +538,21 @@ void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queri
     launch_merge_keys(ckeys.as<uint64_t>(), 1, nq, ivf->nlist, false, nprobe, probes.as<uint64_t>(), nullptr, nullptr,
                       nullptr, st);
     // 2. list scan
-    QueryTile qt = prepare_queries(ds, d_queries, nq, st);
     if (nq >= 4) {
-        ivf_list_major(ds, ivf, qt, probes.as<uint64_t>(), nq, nprobe, k, d_keys, st);
+        // probe table to the host (nq * nprobe keys): the grouping by list is host work, the item tables go back
+        std::vector<uint64_t> h_probes((size_t)nq * nprobe), h_off(ivf->nlist + 1);
+        VDB_CUDA(cudaMemcpyAsync(h_probes.data(), probes.p, h_probes.size() * 8, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaMemcpyAsync(h_off.data(), ivf->d_offsets, h_off.size() * 8, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaStreamSynchronize(st));
+        static const int no_tensor = getenv("VDB_IVF_NO_TENSOR") ? atoi(getenv("VDB_IVF_NO_TENSOR")) : 0;
+        if (!no_tensor && nq >= 16 &&
+            ivf_tensor_keys(ds, ivf, d_queries, probes.as<uint64_t>(), h_probes, h_off, nq, nprobe, k, d_keys, st))
+            return;
+        QueryTile qt = prepare_queries(ds, d_queries, nq, st);
+        ivf_list_major(ds, ivf, qt, h_probes, h_off, nq, nprobe, k, d_keys, st);
         return;
     }
+    QueryTile qt = prepare_queries(ds, d_queries, nq, st);
     const uint32_t period = IVF_WARPS * IVF_R;
     const uint32_t P = topk_segment_size(k, period);
     const size_t smem = (size_t)qt.qstride * 4 + TopkSmem::bytes(1, P) + 16 + (size_t)round_up(nprobe + 1, 2u) * 4 +

@@ -299,3 +299,32 @@ def test_pq_global_threshold_scan_large_shard(V, oracle, metric, m):
     one = idx.knn_pq_batch(q[:1], 10, 300, pq)
     many = idx.knn_pq_batch(q, 10, 300, pq)
     assert (one[0][0] == many[0][0]).all() and (one[1][0].view(np.uint32) == many[1][0].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_ivf_tensor_probe_scan_large_shard(V, oracle, metric):
+    """Shards >= 65536 rows scan the probed lists on the tensor cores for batches of >= 16 queries (list-ordered TF32
+    rows, gathered query groups, exact rerank): ids and distance bits must equal the FP32 list scan (batches of < 16
+    take it) and the oracle, incl. duplicate rows (ties by id), an empty list, k larger than some visit sets, ragged
+    dims and short probe counts."""
+    rng = np.random.default_rng(77)
+    n, dim, nlist = 70_000, 100, 48
+    proto = rng.random((nlist - 1, dim), dtype=np.float32)
+    base = (proto[rng.integers(0, nlist - 1, n)] + 0.08 * rng.standard_normal((n, dim))).astype(np.float32)
+    base[3000:3040] = base[11]                       # ties decided by id
+    cent = np.concatenate([proto, np.full((1, dim), 50.0, np.float32)])   # last centroid: nobody's nearest -> empty list
+    q = (proto[rng.integers(0, nlist - 1, 40)] + 0.08 * rng.standard_normal((40, dim))).astype(np.float32)
+    q[0] = base[11]
+    vs = V.DeviceVecSet(base, metric)
+    ivf = V.IVFIndex(vs, cent)
+    a = oracle.kmeans_assign(base, cent, metric, nthreads=8)
+    assert (ivf.assignment == a).all()
+    off, mem = oracle.ivf_lists(a, nlist)
+    for k, nprobe in ((10, 4), (100, 1), (3, 48), (300, 2)):
+        got = ivf.knn_with_ef_batch(q, k, nprobe)
+        want = oracle.ivf_knn(base, cent, off, mem, q, k, nprobe, metric, nthreads=8)
+        assert_knn_parity(base, q, metric, got, want, oracle)
+        fp32 = ivf.knn_with_ef_batch(q[:9], k, nprobe)     # < 16 queries: FP32 list-major scan
+        assert (fp32[0] == got[0][:9]).all()
+        assert (fp32[1].view(np.uint32) == got[1][:9].view(np.uint32)).all()
+        assert (fp32[2] == got[2][:9]).all()
