@@ -254,7 +254,7 @@ __device__ __forceinline__ ItemView decode_item(const GemmParams& p, uint32_t it
         v.q_end = it.q_end;
         v.r0 = it.r0;
         v.r_end = it.r_end;
-        v.slab = item;
+        v.slab = 0;  // mode 2: every gathered query row belongs to exactly one item
     } else {
         v.slab = item / p.nqt;
         v.q0 = (item - v.slab * p.nqt) * GM * CTAS;
@@ -718,8 +718,8 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
 
 // mode 0 = store every score, 1 = filter, 2 = per-slab smallest scores; `p` must have been planned (plan_gemm)
 static void launch_gemm(int mode, int metric, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p,
-                        cudaStream_t st) {
-    const int sel = (gemm_ctas() == 2 ? 6 : 0) + mode * 2 + (metric == VDB_COSINE ? 1 : 0);
+                        cudaStream_t st, int ctas = 0) {
+    const int sel = ((ctas ? ctas : gemm_ctas()) == 2 ? 6 : 0) + mode * 2 + (metric == VDB_COSINE ? 1 : 0);
     switch (sel) {
         case 0: launch_gemm_t<0, 1, VDB_L2SQR>(mq, mx, p, st); break;
         case 1: launch_gemm_t<0, 1, VDB_COSINE>(mq, mx, p, st); break;
@@ -1127,10 +1127,15 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
 // A batch of queries probing nlist lists is a block-sparse contraction: list l's rows x the queries that probe l.
 // Rows and norms are kept a second time in LIST ORDER (position p <-> members[p]) so every list is a contiguous row
 // range the TMA can tile; the queries are gathered list by list into one matrix; the work items of the contraction
-// kernel are (list, tile of <= 256 gathered queries, range of row tiles). The threshold needs no sampling here:
-// tau_q = the k-th smallest EXACT distance over the first S rows of q's visit sequence. Every probed row with
-// d <= that value has S' <= d - ||q||^2 <= tau_q, so the candidate set provably contains q's k best probed rows;
-// only a candidate-list overflow sends a query back to the FP32 list scan.
+// kernel are (list, tile of gathered queries, range of row tiles). Query tiles of <= 128 rows run on single CTAs
+// (M = 128), larger ones on CTA pairs (M = 256). Thresholds:
+//   k/16 small (j0 <= 16): a stratified 1/16 sample of every list (also kept in list order) is scored first, the
+//     j0-th smallest sampled S' over the probed lists (+ margin) is tau, as in the Flat path;
+//   else: tau = the k-th smallest EXACT distance over the first S rows of the visit sequence (complete by construction).
+// Candidates are reranked with the FP32 list scan's arithmetic; queries failing the completeness check or overflowing
+// their candidate list are redone by the FP32 list scan.
+constexpr uint32_t IVF_SAMPLE_RATE = 16;
+
 __global__ void gather_round_rows_kernel(const float* __restrict__ rows_tf32, const float* __restrict__ colA,
                                          const float* __restrict__ rn, const uint32_t* __restrict__ members, uint64_t n,
                                          uint32_t pitch, float* __restrict__ out, float* __restrict__ outA,
@@ -1146,20 +1151,67 @@ __global__ void gather_round_rows_kernel(const float* __restrict__ rows_tf32, co
         outR[p] = rn[row];
     }
 }
+// sample row s of list l = one hashed position out of the s-th bucket of IVF_SAMPLE_RATE consecutive list positions
+__global__ void ivf_sample_gather_kernel(const float* __restrict__ rows_lo, const float* __restrict__ colA_lo,
+                                         const float* __restrict__ rn_lo, const uint64_t* __restrict__ offsets,
+                                         const uint64_t* __restrict__ soff, uint32_t nlist, uint32_t pitch,
+                                         float* __restrict__ out, float* __restrict__ outA, float* __restrict__ outR) {
+    const uint64_t s = blockIdx.x;
+    uint32_t lo = 0, hi = nlist;  // largest l with soff[l] <= s
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (soff[mid] <= s) lo = mid;
+        else hi = mid;
+    }
+    const uint64_t b0 = offsets[lo] + (s - soff[lo]) * IVF_SAMPLE_RATE;
+    const uint64_t b1 = min(offsets[lo + 1], b0 + IVF_SAMPLE_RATE);
+    uint64_t h = (s + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 29;
+    const uint64_t pos = b0 + h % (b1 - b0);
+    const float4* src = reinterpret_cast<const float4*>(rows_lo + pos * pitch);
+    float4* dst = reinterpret_cast<float4*>(out + s * pitch);
+    for (uint32_t e = threadIdx.x; e < pitch / 4; e += blockDim.x) dst[e] = src[e];
+    if (threadIdx.x == 0) {
+        outA[s] = colA_lo[pos];
+        outR[s] = rn_lo[pos];
+    }
+}
 
 static std::mutex g_ivf_side_mu;
-static void ensure_ivf_side(const vdb_dataset* ds, const vdb_ivf* civf, cudaStream_t st) {
+static void ensure_ivf_side(const vdb_dataset* ds, const vdb_ivf* civf, const std::vector<uint64_t>& h_off, cudaStream_t st) {
     vdb_ivf* ivf = const_cast<vdb_ivf*>(civf);
     std::lock_guard<std::mutex> lk(g_ivf_side_mu);
     if (ivf->d_rows_lo) return;
     ensure_side_arrays(ds, st);
-    VDB_CUDA(cudaMalloc(&ivf->d_rows_lo, ds->n * (size_t)ds->pitch * 4));
-    VDB_CUDA(cudaMalloc(&ivf->d_colA_lo, ds->n * 4));
-    VDB_CUDA(cudaMalloc(&ivf->d_rn_lo, ds->n * 4));
+    float *rows = nullptr, *colA = nullptr, *rn = nullptr;
+    VDB_CUDA(cudaMalloc(&rows, ds->n * (size_t)ds->pitch * 4));
+    VDB_CUDA(cudaMalloc(&colA, ds->n * 4));
+    VDB_CUDA(cudaMalloc(&rn, ds->n * 4));
     gather_round_rows_kernel<<<(uint32_t)ds->n, 128, 0, st>>>(ds->d_tf32, ds->d_sqnorm, ds->d_lo, ivf->d_members, ds->n, ds->pitch,
-                                                             ivf->d_rows_lo, ivf->d_colA_lo, ivf->d_rn_lo);
+                                                             rows, colA, rn);
     VDB_LAUNCHED();
+    ivf->h_samp_off.assign(ivf->nlist + 1, 0);
+    for (uint32_t l = 0; l < ivf->nlist; ++l)
+        ivf->h_samp_off[l + 1] = ivf->h_samp_off[l] + ceil_div<uint64_t>(h_off[l + 1] - h_off[l], IVF_SAMPLE_RATE);
+    ivf->samp_n = ivf->h_samp_off[ivf->nlist];
+    VDB_CUDA(cudaMalloc(&ivf->d_samp_rows, std::max<uint64_t>(ivf->samp_n, 1) * (size_t)ds->pitch * 4));
+    VDB_CUDA(cudaMalloc(&ivf->d_samp_colA, std::max<uint64_t>(ivf->samp_n, 1) * 4));
+    VDB_CUDA(cudaMalloc(&ivf->d_samp_rn, std::max<uint64_t>(ivf->samp_n, 1) * 4));
+    if (ivf->samp_n) {
+        DevBuf soff((size_t)(ivf->nlist + 1) * 8, st);
+        VDB_CUDA(cudaMemcpyAsync(soff.p, ivf->h_samp_off.data(), (size_t)(ivf->nlist + 1) * 8, cudaMemcpyHostToDevice, st));
+        ivf_sample_gather_kernel<<<(uint32_t)ivf->samp_n, 128, 0, st>>>(rows, colA, rn, ivf->d_offsets, soff.as<uint64_t>(),
+                                                                       ivf->nlist, ds->pitch, ivf->d_samp_rows,
+                                                                       ivf->d_samp_colA, ivf->d_samp_rn);
+        VDB_LAUNCHED();
+        VDB_CUDA(cudaStreamSynchronize(st));
+    }
     VDB_CUDA(cudaStreamSynchronize(st));
+    ivf->d_colA_lo = colA;
+    ivf->d_rn_lo = rn;
+    ivf->d_rows_lo = rows;
 }
 
 // first S rows of every query's visit sequence (probed lists in probe order) as rerank pairs
@@ -1201,10 +1253,27 @@ __global__ void ivf_tau_kernel(const uint64_t* __restrict__ keys, uint32_t nq, u
     const float shift = qsq ? qsq[q] : 0.f;
     tau[q] = (dk - shift) + 2e-5f * (fabsf(dk) + shift) + 1e-30f;
 }
+// the 16 smallest sampled scores of every probed list of a query, side by side: [nq][nprobe][G_TOPJ]
+__global__ void ivf_collect_sample_kernel(const uint64_t* __restrict__ skeys, const uint32_t* __restrict__ gpos, uint32_t nprobe,
+                                          uint64_t* __restrict__ out) {
+    const uint32_t q = blockIdx.x;
+    for (uint32_t e = threadIdx.x; e < nprobe * G_TOPJ; e += blockDim.x) {
+        const uint32_t g = gpos[(size_t)q * nprobe + e / G_TOPJ];
+        out[(size_t)q * nprobe * G_TOPJ + e] = g == 0xffffffffu ? KEY_NONE : skeys[(size_t)g * G_TOPJ + e % G_TOPJ];
+    }
+}
+// tau = S'_(j0) of the sample + margin; +inf when the probed lists hold fewer than j0 sampled rows
+__global__ void ivf_sample_tau_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j0, const float* __restrict__ qcm,
+                                      float margin, float* __restrict__ tau) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint64_t kk = keys[(size_t)q * j0 + (j0 - 1)];
+    const float s = kk == KEY_NONE ? __uint_as_float(0x7f800000u) : key_dist(kk);
+    tau[q] = s + 2.5f * (qcm ? qcm[q] * margin : margin);
+}
 __global__ void gather_query_side_kernel(const float* __restrict__ qround, uint32_t qpitch, const float* __restrict__ qcm,
-                                         const float* __restrict__ qnorm, const float* __restrict__ tau,
-                                         const uint32_t* __restrict__ qmap, uint32_t G, float* __restrict__ outq,
-                                         float* __restrict__ out_qcm, float* __restrict__ out_qnorm, float* __restrict__ out_tau) {
+                                         const float* __restrict__ qnorm, const uint32_t* __restrict__ qmap, uint32_t G,
+                                         float* __restrict__ outq, float* __restrict__ out_qcm, float* __restrict__ out_qnorm) {
     const uint32_t g = blockIdx.x;
     if (g >= G) return;
     const uint32_t q = qmap[g];
@@ -1214,45 +1283,73 @@ __global__ void gather_query_side_kernel(const float* __restrict__ qround, uint3
     if (threadIdx.x == 0) {
         out_qcm[g] = qcm[q];
         if (qnorm) out_qnorm[g] = qnorm[q];
-        out_tau[g] = tau[q];
     }
 }
-__global__ void overflow_list_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap, uint32_t* __restrict__ list,
-                                     uint32_t* __restrict__ nlist) {
+__global__ void gather_f32_kernel(const float* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t cnt,
+                                  float* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) dst[i] = src[idx[i]];
+}
+// completeness: no overflow, and (unless the threshold is complete by construction) the k-th exact distance lies
+// strictly inside the threshold; tau = +inf keeps every probed row, so short visit sets pass
+__global__ void ivf_check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, const uint32_t* __restrict__ cnt,
+                                 uint32_t cap, const float* __restrict__ tau, const float* __restrict__ qsq, int by_construction,
+                                 uint32_t* __restrict__ redo, uint32_t* __restrict__ nredo) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq && cnt[q] > cap) list[atomicAdd(nlist, 1u)] = q;
+    if (q >= nq) return;
+    bool ok = cnt[q] <= cap;
+    if (ok && !by_construction && tau[q] != __uint_as_float(0x7f800000u)) {
+        const uint64_t kk = keys[(size_t)q * k + (k - 1)];
+        ok = kk != KEY_NONE;
+        if (ok) {
+            const float dk = key_dist(kk);
+            const float shift = qsq ? qsq[q] : 0.f;
+            const float slack = 2e-5f * (fabsf(dk) + shift + fabsf(tau[q]));
+            ok = (dk - shift) < tau[q] - slack;
+        }
+    }
+    if (!ok) redo[atomicAdd(nredo, 1u)] = q;
 }
 
 bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
                      const std::vector<uint64_t>& h_probes, const std::vector<uint64_t>& h_off, uint32_t nq, uint32_t nprobe,
                      uint32_t k, uint64_t* d_keys, cudaStream_t st) {
     if (!flat_gemm_supported(ds, nq, k) || ds->dtype != VDB_F32 || k > 512) return false;
-    ensure_ivf_side(ds, ivf, st);
-    const uint32_t ctas = (uint32_t)gemm_ctas();
-    const uint32_t QT = GM * ctas;
+    ensure_ivf_side(ds, ivf, h_off, st);
     // ---- host: group the (query, list) pairs by list, build the gathered query order and the work items ----
-    std::vector<std::vector<uint32_t>> by_list(ivf->nlist);
+    std::vector<std::vector<uint32_t>> by_list(ivf->nlist);   // entries: q * nprobe + j
     for (uint32_t q = 0; q < nq; ++q)
         for (uint32_t j = 0; j < nprobe; ++j) {
             const uint64_t pk = h_probes[(size_t)q * nprobe + j];
-            if (pk != KEY_NONE) by_list[key_id(pk)].push_back(q);
+            if (pk != KEY_NONE) by_list[key_id(pk)].push_back(q * nprobe + j);
         }
-    std::vector<uint32_t> qmap;
-    std::vector<GemmItem> items;
+    std::vector<uint32_t> qmap, gpos((size_t)nq * nprobe, 0xffffffffu);
+    std::vector<GemmItem> items[2], sitems[2];   // [0]: single CTAs (<= 128 gathered queries), [1]: CTA pairs
     qmap.reserve((size_t)nq * nprobe);
+    static const uint32_t force_ctas = getenv("VDB_IVF_CTAS") ? (uint32_t)atoi(getenv("VDB_IVF_CTAS")) : 0;
     const uint32_t tiles_per_item = 8;
     for (uint32_t l = 0; l < ivf->nlist; ++l) {
         const uint64_t r0 = h_off[l], r1 = h_off[l + 1];
         if (r1 == r0 || by_list[l].empty()) continue;
         const uint32_t g0 = (uint32_t)qmap.size();
-        qmap.insert(qmap.end(), by_list[l].begin(), by_list[l].end());
+        for (uint32_t e : by_list[l]) {
+            gpos[e] = (uint32_t)qmap.size();
+            qmap.push_back(e / nprobe);
+        }
         const uint32_t g1 = (uint32_t)qmap.size();
-        // row ranges outermost, query tiles innermost: CTAs in flight share the same rows in L2
-        for (uint64_t r = r0; r < r1; r += (uint64_t)tiles_per_item * GN)
-            for (uint32_t g = g0; g < g1; g += QT)
-                items.push_back(GemmItem{g, std::min(g1, g + QT), r, std::min<uint64_t>(r1, r + (uint64_t)tiles_per_item * GN)});
+        const uint64_t s0 = ivf->h_samp_off[l], s1 = ivf->h_samp_off[l + 1];
+        // query tiles: 256 rows on a CTA pair, a remainder of <= 128 rows on a single CTA
+        for (uint32_t g = g0; g < g1;) {
+            const uint32_t left = g1 - g;
+            const uint32_t pair = force_ctas ? force_ctas - 1 : (left > GM ? 1u : 0u);
+            const uint32_t len = std::min(left, pair ? 2u * GM : (uint32_t)GM);
+            for (uint64_t r = r0; r < r1; r += (uint64_t)tiles_per_item * GN)
+                items[pair].push_back(GemmItem{g, g + len, r, std::min<uint64_t>(r1, r + (uint64_t)tiles_per_item * GN)});
+            sitems[pair].push_back(GemmItem{g, g + len, s0, s1});
+            g += len;
+        }
     }
-    if (items.empty()) {
+    if (qmap.empty()) {
         VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
         return true;
     }
@@ -1260,15 +1357,66 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
     vdb_tq* tq = tensor_begin(ds, d_queries, nq, st);
     try {
         const bool cosine = ds->metric == VDB_COSINE;
-        // ---- thresholds: exact distances over the first S rows of every visit sequence ----
-        // S balances the two exact-distance passes: S subset rows against ~k * visited / S surviving candidates
-        const double visited = (double)nprobe * (double)ds->n / (double)ivf->nlist;
-        static const uint32_t s_env = getenv("VDB_IVF_SUBSET") ? (uint32_t)atoi(getenv("VDB_IVF_SUBSET")) : 0;
-        const uint32_t S = s_env ? s_env
-                                 : std::min(4096u, (uint32_t)next_pow2(std::max<uint32_t>(std::max(256u, 2 * k),
-                                                                                         (uint32_t)std::sqrt((double)k * visited))));
-        DevBuf tau((size_t)nq * 4, st);
-        {
+        // ---- gathered query matrix, its per-row scalars, item tables ----
+        DevBuf d_qmap((size_t)G * 4, st), qg((size_t)G * tq->qpitch * 4, st), qcm_g((size_t)G * 4, st), qn_g((size_t)G * 4, st),
+            tau_g((size_t)G * 4, st), tau((size_t)nq * 4, st);
+        VDB_CUDA(cudaMemcpyAsync(d_qmap.p, qmap.data(), (size_t)G * 4, cudaMemcpyHostToDevice, st));
+        gather_query_side_kernel<<<G, 128, 0, st>>>(tq->qround.as<float>(), tq->qpitch, tq->qcm.as<float>(),
+                                                    cosine ? tq->qtile.qcache.as<float>() : nullptr, d_qmap.as<uint32_t>(), G,
+                                                    qg.as<float>(), qcm_g.as<float>(), qn_g.as<float>());
+        VDB_LAUNCHED();
+        const CUtensorMap mq = make_map(qg.as<float>(), ds->dim, G, (uint64_t)tq->qpitch * 4, GM);
+        GemmParams base{};
+        base.nq = G;
+        base.kblocks = ceil_div(ds->dim, (uint32_t)GK);
+        base.qcm = qcm_g.as<float>();
+        base.qnorm = cosine ? qn_g.as<float>() : nullptr;
+        base.kc = tq->kc;
+        base.row_stride = 1;
+        base.qmap = d_qmap.as<uint32_t>();
+        base.nslabs = 1;
+        auto run_items = [&](int mode, const std::vector<GemmItem>* tabs, const float* rows, uint64_t nrows, GemmParams p) {
+            for (uint32_t pair = 0; pair < 2; ++pair) {
+                if (tabs[pair].empty()) continue;
+                DevBuf d_items(tabs[pair].size() * sizeof(GemmItem), st);
+                VDB_CUDA(cudaMemcpyAsync(d_items.p, tabs[pair].data(), tabs[pair].size() * sizeof(GemmItem),
+                                         cudaMemcpyHostToDevice, st));
+                const CUtensorMap mx = make_map(rows, ds->dim, nrows, (uint64_t)ds->pitch * 4, GN / (pair + 1));
+                p.nrows = nrows;
+                p.items = d_items.as<GemmItem>();
+                p.nitems = (uint32_t)tabs[pair].size();
+                launch_gemm(mode, ds->metric, mq, mx, p, st, (int)pair + 1);
+            }
+        };
+        // ---- thresholds ----
+        const uint32_t j0 = tensor_j0(k, 1u << 20, (uint64_t)IVF_SAMPLE_RATE << 20);
+        static const int force_subset = getenv("VDB_IVF_SUBSET") ? atoi(getenv("VDB_IVF_SUBSET")) : 0;
+        const bool by_sample = j0 <= (uint32_t)G_TOPJ && ivf->samp_n > 0 && !force_subset;
+        if (by_sample) {
+            DevBuf skeys((size_t)G * G_TOPJ * 8, st), d_gpos((size_t)nq * nprobe * 4, st),
+                ckeys((size_t)nq * nprobe * G_TOPJ * 8, st), jkeys((size_t)nq * j0 * 8, st);
+            VDB_CUDA(cudaMemsetAsync(skeys.p, 0xff, (size_t)G * G_TOPJ * 8, st));
+            VDB_CUDA(cudaMemcpyAsync(d_gpos.p, gpos.data(), (size_t)nq * nprobe * 4, cudaMemcpyHostToDevice, st));
+            GemmParams ps = base;
+            ps.sqnorm = ivf->d_samp_colA;
+            ps.rnorm = ivf->d_samp_rn;
+            ps.out_keys = skeys.as<uint64_t>();
+            run_items(2, sitems, ivf->d_samp_rows, ivf->samp_n, ps);
+            ivf_collect_sample_kernel<<<nq, 128, 0, st>>>(skeys.as<uint64_t>(), d_gpos.as<uint32_t>(), nprobe, ckeys.as<uint64_t>());
+            VDB_LAUNCHED();
+            launch_merge_keys(ckeys.as<uint64_t>(), 1, nq, nprobe * G_TOPJ, false, j0, jkeys.as<uint64_t>(), nullptr, nullptr,
+                              nullptr, st);
+            ivf_sample_tau_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0,
+                                                                     cosine ? nullptr : tq->qcm.as<float>(),
+                                                                     cosine ? tq->cbound : ds->mean_norm, tau.as<float>());
+            VDB_LAUNCHED();
+        } else {
+            // S balances the two exact-distance passes: S subset rows against ~k * visited / S surviving candidates
+            const double visited = (double)nprobe * (double)ds->n / (double)ivf->nlist;
+            const uint32_t S = force_subset > 1
+                                   ? (uint32_t)force_subset
+                                   : std::min(4096u, (uint32_t)next_pow2(std::max<uint32_t>(
+                                                         std::max(256u, 2 * k), (uint32_t)std::sqrt((double)k * visited))));
             const uint64_t cnt = (uint64_t)nq * S;
             DevBuf qidx(cnt * 4, st), rid(cnt * 4, st), valid(cnt, st), dist(cnt * 4, st), skeys(cnt * 8, st), kkeys((size_t)nq * k * 8, st);
             ivf_subset_kernel<<<nq, 128, 0, st>>>(d_probes, nprobe, ivf->d_offsets, ivf->d_members, S, qidx.as<uint32_t>(),
@@ -1282,42 +1430,21 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
                                                               tau.as<float>());
             VDB_LAUNCHED();
         }
-        // ---- gathered query matrix and its per-row scalars ----
-        DevBuf d_qmap((size_t)G * 4, st), d_items(items.size() * sizeof(GemmItem), st), qg((size_t)G * tq->qpitch * 4, st),
-            qcm_g((size_t)G * 4, st), qn_g((size_t)G * 4, st), tau_g((size_t)G * 4, st);
-        VDB_CUDA(cudaMemcpyAsync(d_qmap.p, qmap.data(), (size_t)G * 4, cudaMemcpyHostToDevice, st));
-        VDB_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(GemmItem), cudaMemcpyHostToDevice, st));
-        gather_query_side_kernel<<<G, 128, 0, st>>>(tq->qround.as<float>(), tq->qpitch, tq->qcm.as<float>(),
-                                                    cosine ? tq->qtile.qcache.as<float>() : nullptr, tau.as<float>(),
-                                                    d_qmap.as<uint32_t>(), G, qg.as<float>(), qcm_g.as<float>(),
-                                                    qn_g.as<float>(), tau_g.as<float>());
+        gather_f32_kernel<<<ceil_div(G, 256u), 256, 0, st>>>(tau.as<float>(), d_qmap.as<uint32_t>(), G, tau_g.as<float>());
         VDB_LAUNCHED();
         // ---- filter pass over the probed (list, query tile) blocks ----
         const uint32_t cap = 8192;
         DevBuf cand((size_t)nq * cap * 8, st);
         VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
         {
-            const CUtensorMap mq = make_map(qg.as<float>(), ds->dim, G, (uint64_t)tq->qpitch * 4, GM);
-            const CUtensorMap mx = make_map(ivf->d_rows_lo, ds->dim, ds->n, (uint64_t)ds->pitch * 4, GN / ctas);
-            GemmParams pf{};
-            pf.nq = G;
-            pf.kblocks = ceil_div(ds->dim, (uint32_t)GK);
-            pf.qcm = qcm_g.as<float>();
-            pf.qnorm = cosine ? qn_g.as<float>() : nullptr;
-            pf.kc = tq->kc;
+            GemmParams pf = base;
             pf.sqnorm = ivf->d_colA_lo;
             pf.rnorm = ivf->d_rn_lo;
-            pf.nrows = ds->n;
-            pf.row_stride = 1;
             pf.tau = tau_g.as<float>();
             pf.cand_cnt = tq->cnt.as<uint32_t>();
             pf.cand = cand.as<uint64_t>();
             pf.cap = cap;
-            pf.items = d_items.as<GemmItem>();
-            pf.nitems = (uint32_t)items.size();
-            pf.qmap = d_qmap.as<uint32_t>();
-            plan_gemm(pf);
-            launch_gemm(1, ds->metric, mq, mx, pf, st);
+            run_items(1, items, ivf->d_rows_lo, ds->n, pf);
         }
         // ---- exact rerank (the FP32 list scan's arithmetic) and top-k ----
         const uint64_t total = (uint64_t)nq * cap;
@@ -1334,17 +1461,24 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
                                                                         (uint32_t)ds->id_base, d_total, keys2.as<uint64_t>());
         VDB_LAUNCHED();
         launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, off.as<uint64_t>());
-        // ---- queries whose candidate list overflowed: FP32 list scan ----
-        DevBuf ovl((size_t)nq * 4, st), novl(4, st);
-        VDB_CUDA(cudaMemsetAsync(novl.p, 0, 4, st));
-        overflow_list_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, ovl.as<uint32_t>(), novl.as<uint32_t>());
+        // ---- completeness check; failing queries: FP32 list scan ----
+        DevBuf redo((size_t)nq * 4, st), nredo(4, st);
+        VDB_CUDA(cudaMemsetAsync(nredo.p, 0, 4, st));
+        ivf_check_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(d_keys, nq, k, tq->cnt.as<uint32_t>(), cap, tau.as<float>(),
+                                                            cosine ? nullptr : tq->qsq.as<float>(), by_sample ? 0 : 1,
+                                                            redo.as<uint32_t>(), nredo.as<uint32_t>());
         VDB_LAUNCHED();
         uint32_t h_n = 0;
-        VDB_CUDA(cudaMemcpyAsync(&h_n, novl.p, 4, cudaMemcpyDeviceToHost, st));
+        uint64_t h_cands = 0;
+        VDB_CUDA(cudaMemcpyAsync(&h_n, nredo.p, 4, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaMemcpyAsync(&h_cands, d_total, 8, cudaMemcpyDeviceToHost, st));
         VDB_CUDA(cudaStreamSynchronize(st));
+        g_gemm_redo += h_n;
+        g_gemm_cands += h_cands;
+        g_gemm_queries += nq;
         if (h_n) {
             std::vector<uint32_t> sel(h_n);
-            VDB_CUDA(cudaMemcpyAsync(sel.data(), ovl.p, (size_t)h_n * 4, cudaMemcpyDeviceToHost, st));
+            VDB_CUDA(cudaMemcpyAsync(sel.data(), redo.p, (size_t)h_n * 4, cudaMemcpyDeviceToHost, st));
             VDB_CUDA(cudaStreamSynchronize(st));
             std::sort(sel.begin(), sel.end());
             DevBuf rk((size_t)h_n * k * 8, st), dsel((size_t)h_n * 4, st);

@@ -39,6 +39,10 @@ struct vdb_ivf {
     float* d_rows_lo = nullptr;   // [n][pitch] TF32-rounded (u8: exact f32)
     float* d_colA_lo = nullptr;   // [n] ||x||^2 (L2Sqr) or 1/||x|| (cosine)
     float* d_rn_lo = nullptr;     // [n] ||x||
+    // stratified 1/16 sample of every list, also in list order (threshold pass of the tensor-core probe scan)
+    float* d_samp_rows = nullptr, *d_samp_colA = nullptr, *d_samp_rn = nullptr;
+    std::vector<uint64_t> h_samp_off;  // [nlist+1]
+    uint64_t samp_n = 0;
 };
 
 namespace vdb {

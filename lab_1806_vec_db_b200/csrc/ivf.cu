@@ -394,6 +394,9 @@ void ivf_destroy(vdb_ivf* ivf) {
     cudaFree(ivf->d_offsets);
     cudaFree(ivf->d_members);
     cudaFree(ivf->d_rows_lo);
+    cudaFree(ivf->d_samp_rows);
+    cudaFree(ivf->d_samp_colA);
+    cudaFree(ivf->d_samp_rn);
     cudaFree(ivf->d_colA_lo);
     cudaFree(ivf->d_rn_lo);
     delete ivf;

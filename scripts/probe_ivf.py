@@ -34,8 +34,11 @@ for nq in (1000, 10000):
         wall = (time.perf_counter() - t0) / 3 * 1e3
         L.check(lib.vdb_prof_enable(0))
         out = {}
-        for name in (b"ivf_scan", b"kmeans_assign", b"merge"):
+        for name in (b"ivf_scan", b"kmeans_assign", b"merge", b"flat_gemm", b"rerank"):
             t, c = C.c_double(0), C.c_uint64(0)
             L.check(lib.vdb_prof_read(name, C.byref(t), C.byref(c)))
             out[name.decode()] = round(t.value / 3, 2)
+        g0, g1, g2 = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        L.check(lib.vdb_flat_gemm_stats(C.byref(g0), C.byref(g1), C.byref(g2)))
+        out["cum stats(queries,cands,fallbacks)"] = [g0.value, g1.value, g2.value]
         print(f"nq={nq} nprobe={nprobe}: wall {wall:.2f} ms ({nq/wall*1e3:.0f} QPS) kernels(ms/call): {out}", flush=True)
