@@ -108,6 +108,11 @@ void rekey(const float* d_dist, const uint32_t* d_ids, const uint8_t* d_valid, u
 void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, const uint8_t* d_valid, uint64_t count,
                  uint64_t* d_keys, cudaStream_t st);
 
+// pq_gemm.cu
+bool pq_tensor_supported(const vdb_pq* pq, uint32_t nq);
+void pq_tensor_filter(const vdb_pq* pq, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base, uint32_t* d_cnt,
+                      uint64_t* d_cand, uint32_t cap, cudaStream_t st);
+
 // flat_gemm.cu
 void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
                      uint64_t* d_out_keys, cudaStream_t st);

@@ -598,7 +598,10 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
     launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j0, jkeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
     tau_from_jkeys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, tau.as<float>());
     VDB_LAUNCHED();
-    // 2. filter scan over the shard
+    // 2. filter scan over the shard (batches: bf16 one-hot contraction on the tensor cores + exact re-evaluation)
+    if (pq_tensor_supported(pq, nq))
+        pq_tensor_filter(pq, d_lut, nq, tau.as<float>(), id_base, cnt.as<uint32_t>(), cand.as<uint64_t>(), cap, st);
+    else
     for (uint32_t q0 = 0; q0 < nq; q0 += gq) {
         AdcGlobalParams p{};
         p.lut = d_lut + (size_t)q0 * tab;

@@ -1,0 +1,349 @@
+// pq_gemm.cu — K4t: the 4-bit PQ ADC scan of a query batch as a tensor-core contraction (L2Sqr tables).
+//
+// Replaces the inner loop of PQTable::k_nearest over all rows (reference src/index_algorithm/pq_table.rs, ADC lookup
+// d(q, row) = sum_g LUT_q[g][code(row, g)], flat_index.rs knn_pq) for large batches. The lookup is a dot product
+// with a ONE-HOT vector: adc(q, row) = < onehot(row), LUT_q > over K = m * 16 columns. The tensor cores evaluate it
+// in BF16 and only PRUNE: every LUT entry of an L2Sqr table is >= 0, so the BF16 rounding of the table is a RELATIVE
+// error (2^-9 per entry, one-hot entries are exact) and
+//     S' = S_bf16 * (1 - 2^-9 * 1.05 - m * 2^-21) - 1e-35  <=  adc_exact(q, row)
+// holds for every pair. Rows with S' <= tau_q (tau_q: the exact-ADC threshold of the global-threshold scan, pq.cu)
+// become coarse candidates; their ADC value is then re-evaluated with the reference's arithmetic (sequential f32 sum
+// in group order) and the rows with adc <= tau_q go on exactly as in the FP32 scan — the candidate set is identical.
+//
+// Kernel (sm_100a, one CTA per SM, 320 threads):
+//   warps 6-9  generators: thread = row of the 128-row tile; per k-block (4 groups = 64 bf16 columns = one 128-byte
+//              swizzle row) they expand 4 code nibbles into the one-hot A tile directly in shared memory
+//              (8 x 16-byte chunks, chunk j of row r at position j ^ (r & 7): the layout TMA's 128B swizzle produces),
+//              fence.proxy.async, arrive on the stage's full barrier
+//   warp 4     TMA producer: LUT tile (256 queries x 64 columns, bf16) of the k-block, same barrier (expect_tx)
+//   warp 5     one thread issues tcgen05.mma.kind::f16 (M = 128 rows, N = 256 queries, K = 16 x 4 per k-block)
+//              into double-buffered TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator
+//   warps 0-3  epilogue: tcgen05.ld (thread = row, registers = queries), threshold test, candidate append
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "index.cuh"
+#include "tc.cuh"
+#include "topk.cuh"
+
+namespace vdb {
+
+constexpr int PM = 128;                    // rows per tile (TMEM lanes)
+constexpr int PN = 256;                    // queries per tile (TMEM columns per accumulator)
+constexpr int PK = 64;                     // bf16 columns per k-block = 4 groups x 16 centroids = 128 bytes
+constexpr int P_A_BYTES = PM * PK * 2;     // 16 KB generated one-hot tile
+constexpr int P_B_BYTES = PN * PK * 2;     // 32 KB LUT tile
+constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+constexpr int P_STAGES = 4;
+constexpr int P_THREADS = 320;
+constexpr int P_TMEM_COLS = 512;
+constexpr uint32_t P_MAX_ENC = 128;        // m <= 256 groups
+constexpr uint32_t P_SMEM = 1024 + P_STAGES * P_STAGE_BYTES + PM * P_MAX_ENC + PN * 4 + 256;
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
+constexpr uint32_t P_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+struct PqGemmParams {
+    const uint8_t* codes;   // [n][enc] reference layout (low nibble = even group)
+    uint64_t n;
+    uint32_t enc, m, kblocks;
+    uint32_t nq;
+    const float* tau;       // [nq] exact-ADC thresholds
+    float factor;           // 1 - relative bound of the bf16 evaluation
+    uint32_t* ccnt;         // [nq] coarse candidate counters
+    uint32_t* ccand;        // [nq][ccap] rows
+    uint32_t ccap;
+    uint32_t tiles_per_item, nrow_items, nqt;
+};
+
+__global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_constant__ CUtensorMap map_lut, const PqGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    uint8_t* codes_s = smem + P_STAGES * P_STAGE_BYTES;                   // [PM][enc]
+    float* tau_s = reinterpret_cast<float*>(codes_s + PM * P_MAX_ENC);    // [PN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tau_s + PN);
+    uint64_t* full_bar = bars;                 // [P_STAGES]
+    uint64_t* empty_bar = bars + P_STAGES;     // [P_STAGES]
+    uint64_t* tfull_bar = bars + 2 * P_STAGES; // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1 + 4);   // TMA expect_tx arrive + one arrive per generator warp
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, P_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t nitems = p.nrow_items * p.nqt;
+
+    if (warp == 4) {
+        // ===== TMA producer: the LUT tile of every k-block =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const uint32_t ri = item / p.nqt, qt = item - ri * p.nqt;
+                const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
+                const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+                for (uint32_t t = 0; t < ntile; ++t)
+                    for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], P_B_BYTES);
+                        tma_load_2d(smem_u32(stage_base + stage * P_STAGE_BYTES) + P_A_BYTES, &map_lut, (int)(kb * PK),
+                                    (int)(qt * PN), &full_bar[stage]);
+                        if (++stage == P_STAGES) stage = 0, phase ^= 1;
+                    }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const uint32_t ri = item / p.nqt;
+                const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
+                const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+                for (uint32_t t = 0; t < ntile; ++t) {
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * PN;
+                    for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * P_STAGE_BYTES);
+                        const uint64_t da = umma_desc(sa), db = umma_desc(sa + P_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < PK / 16; ++k)  // 16 bf16 = 32 bytes (2 x 16 B units) per K step
+                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, P_IDESC, (kb | k) != 0);
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == P_STAGES) stage = 0, phase ^= 1;
+                    }
+                    umma_commit(&tfull_bar[acc]);
+                    if (++acc == 2) acc = 0, acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== generators: code nibbles -> one-hot bf16 rows, written in the 128B-swizzle layout =====
+        const uint32_t r = threadIdx.x - 192;  // row of the tile
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const uint32_t ri = item / p.nqt;
+            const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
+            const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+            for (uint32_t t = 0; t < ntile; ++t) {
+                const uint64_t row0 = r0 + (uint64_t)t * PM;
+                const uint32_t rows = (uint32_t)min((uint64_t)PM, p.n - row0);
+                asm volatile("bar.sync 2, 128;" ::: "memory");  // every generator is done with the previous code tile
+                {
+                    const uint32_t bytes = rows * p.enc;          // contiguous in the reference layout
+                    const uint8_t* src = p.codes + row0 * p.enc;  // row0 * enc is a multiple of 128
+                    const uint32_t vec = bytes / 16;
+                    for (uint32_t e = r; e < vec; e += 128)
+                        reinterpret_cast<uint4*>(codes_s)[e] = __ldg(reinterpret_cast<const uint4*>(src) + e);
+                    for (uint32_t e = vec * 16 + r; e < bytes; e += 128) codes_s[e] = __ldg(src + e);
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const bool row_ok = r < rows;
+                const uint8_t* my = codes_s + r * p.enc;
+                for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* arow = stage_base + stage * P_STAGE_BYTES + r * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t g = kb * 4 + i;
+                        const bool ok = row_ok && g < p.m;
+                        const uint32_t byte = ok ? my[g >> 1] : 0u;
+                        const uint32_t c = (g & 1) ? (byte >> 4) : (byte & 0xfu);
+                        const uint32_t one = ok ? (0x3F80u << ((c & 1) * 16)) : 0u;  // bf16 1.0 in the low / high half
+                        const uint32_t w = (c & 7) >> 1;
+                        uint4 v;
+                        v.x = w == 0 ? one : 0u;
+                        v.y = w == 1 ? one : 0u;
+                        v.z = w == 2 ? one : 0u;
+                        v.w = w == 3 ? one : 0u;
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        const uint32_t j0 = 2 * i, j1 = 2 * i + 1;
+                        *reinterpret_cast<uint4*>(arow + ((j0 ^ (r & 7)) << 4)) = c < 8 ? v : z;
+                        *reinterpret_cast<uint4*>(arow + ((j1 ^ (r & 7)) << 4)) = c < 8 ? z : v;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    if (++stage == P_STAGES) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 0-3, thread = row (TMEM lane), registers = queries =====
+        uint32_t acc = 0, acc_phase = 0;
+        const uint32_t lane_base = (uint32_t)warp * 32;
+        for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const uint32_t ri = item / p.nqt, qt = item - ri * p.nqt;
+            const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
+            const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+            const uint32_t q0 = qt * PN;
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's thresholds are no longer read
+            for (uint32_t c = threadIdx.x; c < PN; c += 128)
+                tau_s[c] = (q0 + c) < p.nq ? p.tau[q0 + c] : __uint_as_float(0xff800000u);  // -inf: nothing passes
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (uint32_t t = 0; t < ntile; ++t) {
+                const uint64_t row = r0 + (uint64_t)t * PM + threadIdx.x;
+                const bool row_ok = row < p.n;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (lane_base << 16) + acc * PN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < PN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = fmaf(__uint_as_float(v[j]), p.factor, -1e-35f);
+                            if (!(s > tau_s[c0 + j])) {  // also keeps NaN (the exact re-evaluation decides)
+                                const uint32_t q = q0 + c0 + j;
+                                if (q < p.nq) {
+                                    const uint32_t pos = atomicAdd(&p.ccnt[q], 1u);
+                                    if (pos < p.ccap) p.ccand[(size_t)q * p.ccap + pos] = (uint32_t)row;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) acc = 0, acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, P_TMEM_COLS);
+}
+
+// [nq][m*16] f32 -> [nq][kpad] bf16 (round to nearest), zero padded to whole k-blocks
+__global__ void lut_to_bf16_kernel(const float* __restrict__ lut, uint32_t tab, uint32_t kpad, uint64_t count,
+                                   __nv_bfloat16* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t q = i / kpad;
+        const uint32_t e = (uint32_t)(i - q * kpad);
+        out[i] = __float2bfloat16_rn(e < tab ? lut[q * tab + e] : 0.f);
+    }
+}
+
+// exact ADC (reference arithmetic: sequential f32 sum in group order) of the coarse candidates; rows with
+// adc <= tau join the candidate list of the global-threshold scan. One CTA per query, its LUT in shared memory.
+__global__ void __launch_bounds__(256) pq_exact_cands_kernel(const uint8_t* __restrict__ codes, uint32_t enc, uint32_t m,
+                                                             const float* __restrict__ lut, const float* __restrict__ tau,
+                                                             const uint32_t* __restrict__ ccnt, const uint32_t* __restrict__ ccand,
+                                                             uint32_t ccap, uint32_t id_base, uint32_t* __restrict__ cnt,
+                                                             uint64_t* __restrict__ cand, uint32_t cap) {
+    extern __shared__ __align__(16) float s_lut[];
+    const uint32_t q = blockIdx.x, tab = m * 16;
+    for (uint32_t e = threadIdx.x; e < tab; e += blockDim.x) s_lut[e] = lut[(size_t)q * tab + e];
+    __syncthreads();
+    const uint32_t total = ccnt[q];
+    if (total > ccap) {  // coarse list overflowed: force the redo path
+        if (threadIdx.x == 0) cnt[q] = cap + 1;
+        return;
+    }
+    const float t = tau[q];
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint32_t row = ccand[(size_t)q * ccap + i];
+        const uint8_t* cr = codes + (size_t)row * enc;
+        float s = 0.f;
+        for (uint32_t g = 0; g < m; g += 2) {
+            const uint32_t byte = cr[g >> 1];
+            s = __fadd_rn(s, s_lut[g * 16 + (byte & 0xfu)]);
+            if (g + 1 < m) s = __fadd_rn(s, s_lut[(g + 1) * 16 + (byte >> 4)]);
+        }
+        if (!(s > t)) {
+            const uint32_t pos = atomicAdd(&cnt[q], 1u);
+            if (pos < cap) cand[(size_t)q * cap + pos] = make_key(s, id_base + row);
+        }
+    }
+}
+
+bool pq_tensor_supported(const vdb_pq* pq, uint32_t nq) {
+    static const int off = getenv("VDB_PQ_NO_TENSOR") ? atoi(getenv("VDB_PQ_NO_TENSOR")) : 0;
+    static const int min_nq = getenv("VDB_PQ_TENSOR_MIN_NQ") ? atoi(getenv("VDB_PQ_TENSOR_MIN_NQ")) : 32;
+    return !off && pq->n_bits == 4 && pq->metric == VDB_L2SQR && pq->enc <= P_MAX_ENC && pq->n >= 65536 && nq >= (uint32_t)min_nq &&
+           ((uintptr_t)pq->d_codes & 15) == 0;
+}
+
+// FILTER step of the global-threshold scan on the tensor cores: on return cnt[q] / cand[q][] hold exactly the rows
+// with adc <= tau_q (as keys), or cnt[q] > cap when a list overflowed.
+void pq_tensor_filter(const vdb_pq* pq, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base, uint32_t* d_cnt,
+                      uint64_t* d_cand, uint32_t cap, cudaStream_t st) {
+    const uint32_t tab = pq->m * 16;
+    const uint32_t kblocks = ceil_div(pq->m, 4u);
+    const uint32_t kpad = kblocks * PK;
+    const uint32_t ccap = 2 * cap;
+    DevBuf lut16((size_t)nq * kpad * 2, st), ccnt((size_t)nq * 4, st), ccand((size_t)nq * ccap * 4, st);
+    VDB_CUDA(cudaMemsetAsync(ccnt.p, 0, (size_t)nq * 4, st));
+    const uint64_t count = (uint64_t)nq * kpad;
+    lut_to_bf16_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), (uint64_t)sm_count() * 16), 256, 0, st>>>(
+        d_lut, tab, kpad, count, lut16.as<__nv_bfloat16>());
+    VDB_LAUNCHED();
+    const CUtensorMap map = make_map_bf16(lut16.p, kpad, nq, (uint64_t)kpad * 2, PN);
+    PqGemmParams p{};
+    p.codes = pq->d_codes;
+    p.n = pq->n;
+    p.enc = pq->enc;
+    p.m = pq->m;
+    p.kblocks = kblocks;
+    p.nq = nq;
+    p.tau = d_tau;
+    p.factor = 1.0f - (ldexpf(1.05f, -9) + (float)pq->m * ldexpf(1.0f, -21));
+    p.ccnt = ccnt.as<uint32_t>();
+    p.ccand = ccand.as<uint32_t>();
+    p.ccap = ccap;
+    p.nqt = ceil_div(nq, (uint32_t)PN);
+    const uint64_t row_tiles = ceil_div<uint64_t>(pq->n, PM);
+    // items small enough that every SM gets several, large enough to amortise the threshold-tile reload
+    p.tiles_per_item = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, row_tiles * p.nqt / ((uint64_t)sm_count() * 4)));
+    p.nrow_items = (uint32_t)ceil_div<uint64_t>(row_tiles, p.tiles_per_item);
+    static thread_local bool configured = false;
+    if (!configured) {
+        VDB_CUDA(cudaFuncSetAttribute(pq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        configured = true;
+    }
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(), p.nrow_items * p.nqt);
+    {
+        ProfScope prof("pq_gemm", st);
+        pq_gemm_kernel<<<grid, P_THREADS, P_SMEM, st>>>(map, p);
+        VDB_LAUNCHED();
+    }
+    {
+        ProfScope prof("pq_exact", st);
+        pq_exact_cands_kernel<<<nq, 256, (size_t)tab * 4, st>>>(pq->d_codes, pq->enc, pq->m, d_lut, d_tau, ccnt.as<uint32_t>(),
+                                                              ccand.as<uint32_t>(), ccap, id_base, d_cnt, d_cand, cap);
+        VDB_LAUNCHED();
+    }
+}
+
+}  // namespace vdb

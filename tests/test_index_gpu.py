@@ -328,3 +328,52 @@ def test_ivf_tensor_probe_scan_large_shard(V, oracle, metric):
         assert (fp32[0] == got[0][:9]).all()
         assert (fp32[1].view(np.uint32) == got[1][:9].view(np.uint32)).all()
         assert (fp32[2] == got[2][:9]).all()
+
+
+def test_ivf_tensor_probe_scan_u8(V, oracle):
+    """u8 rows (exact in TF32) through the tensor probe scan: same ids / distance bits as the FP32 list scan and the oracle."""
+    rng = np.random.default_rng(78)
+    n, dim, nlist = 66_000, 72, 20
+    proto = rng.integers(0, 256, (nlist, dim))
+    base = np.clip(proto[rng.integers(0, nlist, n)] + rng.integers(-30, 31, (n, dim)), 0, 255).astype(np.uint8)
+    base[100:130] = base[7]
+    cent = proto.astype(np.uint8)
+    q = np.clip(proto[rng.integers(0, nlist, 33)] + rng.integers(-30, 31, (33, dim)), 0, 255).astype(np.uint8)
+    q[1] = base[7]
+    vs = V.DeviceVecSet(base, "l2sqr")
+    ivf = V.IVFIndex(vs, cent)
+    a = oracle.kmeans_assign(base, cent, "l2sqr", nthreads=8)
+    assert (ivf.assignment == a).all()
+    off, mem = oracle.ivf_lists(a, nlist)
+    for k, nprobe in ((10, 3), (50, 1)):
+        got = ivf.knn_with_ef_batch(q, k, nprobe)
+        want = oracle.ivf_knn(base, cent, off, mem, q, k, nprobe, "l2sqr", nthreads=8)
+        assert_knn_parity(base, q, "l2sqr", got, want, oracle)
+        fp32 = ivf.knn_with_ef_batch(q[:9], k, nprobe)
+        assert (fp32[0] == got[0][:9]).all() and (fp32[1].view(np.uint32) == got[1][:9].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("m", [8, 7, 13])
+def test_pq_tensor_filter_large_shard(V, oracle, m):
+    """Batches of >= 32 queries on shards >= 65536 rows (4-bit, L2Sqr) prune the ADC scan on the tensor cores (bf16
+    one-hot contraction, lower bound) and re-evaluate the survivors with the reference arithmetic: candidates, ids and
+    distance bits must equal the FP32 scan's / the oracle's, incl. odd m (padded groups), exact ADC ties and a ragged
+    last row tile."""
+    rng = np.random.default_rng(31 + m)
+    n, dim = 70_001, 40
+    base = rng.random((n, dim), dtype=np.float32)
+    base[5000:5300] = base[17]                      # 300 identical rows: ADC ties decided by id
+    q = rng.random((70, dim), dtype=np.float32)
+    q[0] = base[17]
+    books = np.concatenate([np.ascontiguousarray(base[100:116, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(dim, m)])
+    vs = V.DeviceVecSet(base, "l2sqr")
+    pq = V.PQTable(vs, V.PQConfig(4, m, "l2sqr"), books)
+    codes = oracle.pq_encode(base, books, m, 4, "l2sqr", nthreads=8)
+    assert (pq.encoded_vec_set == codes).all()
+    idx = V.FlatIndex(vs)
+    for k, ef in ((10, 50), (10, 300), (5, 1200), (3, 1)):
+        got = idx.knn_pq_batch(q, k, ef, pq)
+        want = oracle.flat_knn_pq(base, codes, books, m, 4, q, k, ef, "l2sqr", nthreads=8)
+        assert_knn_parity(base, q, "l2sqr", got, want, oracle)
+        few = idx.knn_pq_batch(q[:9], k, ef, pq)     # < 32 queries: FP32 global-threshold scan
+        assert (few[0] == got[0][:9]).all() and (few[1].view(np.uint32) == got[1][:9].view(np.uint32)).all()
