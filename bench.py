@@ -411,6 +411,8 @@ def run_ours(args):
         "tensor_path": tensor_stats(lib),
         "hbm_scan": hbm_scan,
     }
+    if idx.phase_ms.get("calls"):  # VDB_PHASE_TIMING=1: per-phase device time of the sharded search (rank 0), ms per call
+        line["phase_ms"] = {k_: round(v / idx.phase_ms["calls"], 4) for k_, v in idx.phase_ms.items() if k_ != "calls"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -20,6 +20,7 @@ struct vdb_pq {
     uint8_t* d_codes = nullptr;     // [n][enc] reference layout
     uint32_t* d_codes_t = nullptr;  // [ceil(n/32)][words][32] transposed for the ADC scan
     uint32_t* d_sample_t = nullptr; // the same layout for a stratified random row sample (thresholds of the scan)
+    uint8_t* d_sample = nullptr;    // the sampled code rows in the reference layout [sample_n][enc] (tensor-core sample pass)
     uint32_t sample_n = 0;
 };
 
@@ -110,8 +111,10 @@ void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, c
 
 // pq_gemm.cu
 bool pq_tensor_supported(const vdb_pq* pq, uint32_t nq);
-void pq_tensor_filter(const vdb_pq* pq, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base, uint32_t* d_cnt,
-                      uint64_t* d_cand, uint32_t cap, cudaStream_t st);
+void pq_tensor_lut(const vdb_pq* pq, const float* d_lut, uint32_t nq, DevBuf& lut16, cudaStream_t st);
+void pq_tensor_sample(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, float* d_all, cudaStream_t st);
+void pq_tensor_filter(const vdb_pq* pq, const DevBuf& lut16, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base,
+                      uint32_t* d_cnt, uint64_t* d_cand, uint32_t cap, cudaStream_t st);
 
 // flat_gemm.cu
 void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,

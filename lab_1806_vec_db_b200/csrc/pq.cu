@@ -584,6 +584,12 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
     VDB_CUDA(cudaMemsetAsync(nredo.p, 0, 4, st));
     // 1. thresholds from the sample
     const uint32_t gq = (uint32_t)adc_gq();
+    const bool tensor = pq_tensor_supported(pq, nq);
+    DevBuf lut16;
+    if (tensor) {
+        pq_tensor_lut(pq, d_lut, nq, lut16, st);
+        pq_tensor_sample(pq, lut16, nq, sall.as<float>(), st);
+    } else
     for (uint32_t q0 = 0; q0 < nq; q0 += gq) {
         AdcGlobalParams p{};
         p.lut = d_lut + (size_t)q0 * tab;
@@ -599,8 +605,8 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
     tau_from_jkeys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, tau.as<float>());
     VDB_LAUNCHED();
     // 2. filter scan over the shard (batches: bf16 one-hot contraction on the tensor cores + exact re-evaluation)
-    if (pq_tensor_supported(pq, nq))
-        pq_tensor_filter(pq, d_lut, nq, tau.as<float>(), id_base, cnt.as<uint32_t>(), cand.as<uint64_t>(), cap, st);
+    if (tensor)
+        pq_tensor_filter(pq, lut16, d_lut, nq, tau.as<float>(), id_base, cnt.as<uint32_t>(), cand.as<uint64_t>(), cap, st);
     else
     for (uint32_t q0 = 0; q0 < nq; q0 += gq) {
         AdcGlobalParams p{};
@@ -733,13 +739,13 @@ vdb_pq* pq_create(const vdb_dataset* ds, const void* h_codebooks, uint32_t m, ui
             VDB_LAUNCHED();
             if (pq->n >= 65536) {
                 pq->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(32768, pq->n / 2), std::max<uint64_t>(2048, pq->n / 30));
-                DevBuf srows((size_t)pq->sample_n * pq->enc, st);
-                pq_sample_codes_kernel<<<pq->sample_n, 128, 0, st>>>(pq->d_codes, pq->n, pq->enc, pq->sample_n, srows.as<uint8_t>());
+                VDB_CUDA(cudaMalloc(&pq->d_sample, round_up((size_t)pq->sample_n * pq->enc, (size_t)16)));
+                pq_sample_codes_kernel<<<pq->sample_n, 128, 0, st>>>(pq->d_codes, pq->n, pq->enc, pq->sample_n, pq->d_sample);
                 VDB_LAUNCHED();
                 const uint64_t ts = ceil_div<uint64_t>(pq->sample_n, 32) * pq->words * 32;
                 VDB_CUDA(cudaMalloc(&pq->d_sample_t, ts * 4));
                 pq_transpose_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(ts, 256), 1u << 20), 256, 0, st>>>(
-                    srows.as<uint8_t>(), pq->sample_n, pq->enc, pq->words, pq->d_sample_t);
+                    pq->d_sample, pq->sample_n, pq->enc, pq->words, pq->d_sample_t);
                 VDB_LAUNCHED();
                 VDB_CUDA(cudaStreamSynchronize(st));
             }
@@ -765,6 +771,7 @@ void pq_destroy(vdb_pq* pq) {
     cudaFree(pq->d_codes);
     cudaFree(pq->d_codes_t);
     cudaFree(pq->d_sample_t);
+    cudaFree(pq->d_sample);
     delete pq;
 }
 
@@ -772,6 +779,7 @@ void pq_lut(const vdb_pq* pq, const void* d_queries, uint32_t nq, float* d_lut, 
     if (nq == 0) return;
     const uint64_t total = (uint64_t)nq * pq->m * pq->kc;
     const uint32_t grid = (uint32_t)ceil_div<uint64_t>(std::max<uint64_t>(total, nq), 256);
+    ProfScope prof("pq_lut", st);
     if (pq->dtype == VDB_F32)
         pq_lut_kernel<float><<<grid, 256, 0, st>>>((const float*)d_queries, nq, pq->dim, (const float*)pq->d_codebooks,
                                                   pq->d_groups, pq->m, pq->kc, pq->metric, d_lut, d_qcache);

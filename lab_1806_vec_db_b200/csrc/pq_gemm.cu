@@ -65,8 +65,11 @@ struct PqGemmParams {
     uint32_t* ccand;        // [nq][ccap] rows
     uint32_t ccap;
     uint32_t tiles_per_item, nrow_items, nqt;
+    float* all_out;         // MODE 0: [nq][n] upper bounds of the exact ADC values (sample pass)
+    float up_factor;        // MODE 0: 1 + relative bound
 };
 
+template <int MODE>  // 0: store every score (sample pass), 1: filter against tau
 __global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_constant__ CUtensorMap map_lut, const PqGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -206,8 +209,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_cons
             const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
             const uint32_t q0 = qt * PN;
             asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's thresholds are no longer read
-            for (uint32_t c = threadIdx.x; c < PN; c += 128)
-                tau_s[c] = (q0 + c) < p.nq ? p.tau[q0 + c] : __uint_as_float(0xff800000u);  // -inf: nothing passes
+            if (MODE == 1)
+                for (uint32_t c = threadIdx.x; c < PN; c += 128)
+                    tau_s[c] = (q0 + c) < p.nq ? p.tau[q0 + c] : __uint_as_float(0xff800000u);  // -inf: nothing passes
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (uint32_t t = 0; t < ntile; ++t) {
                 const uint64_t row = r0 + (uint64_t)t * PM + threadIdx.x;
@@ -222,6 +226,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_cons
                     if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
+                            if (MODE == 0) {
+                                // a warp stores 32 consecutive rows of one query: 128-byte segments
+                                const uint32_t q = q0 + c0 + j;
+                                if (q < p.nq) p.all_out[(size_t)q * p.n + row] = __uint_as_float(v[j]) * p.up_factor;
+                                continue;
+                            }
                             const float s = fmaf(__uint_as_float(v[j]), p.factor, -1e-35f);
                             if (!(s > tau_s[c0 + j])) {  // also keeps NaN (the exact re-evaluation decides)
                                 const uint32_t q = q0 + c0 + j;
@@ -292,52 +302,72 @@ bool pq_tensor_supported(const vdb_pq* pq, uint32_t nq) {
     static const int off = getenv("VDB_PQ_NO_TENSOR") ? atoi(getenv("VDB_PQ_NO_TENSOR")) : 0;
     static const int min_nq = getenv("VDB_PQ_TENSOR_MIN_NQ") ? atoi(getenv("VDB_PQ_TENSOR_MIN_NQ")) : 32;
     return !off && pq->n_bits == 4 && pq->metric == VDB_L2SQR && pq->enc <= P_MAX_ENC && pq->n >= 65536 && nq >= (uint32_t)min_nq &&
-           ((uintptr_t)pq->d_codes & 15) == 0;
+           ((uintptr_t)pq->d_codes & 15) == 0 && pq->d_sample != nullptr;
 }
 
-// FILTER step of the global-threshold scan on the tensor cores: on return cnt[q] / cand[q][] hold exactly the rows
-// with adc <= tau_q (as keys), or cnt[q] > cap when a list overflowed.
-void pq_tensor_filter(const vdb_pq* pq, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base, uint32_t* d_cnt,
-                      uint64_t* d_cand, uint32_t cap, cudaStream_t st) {
-    const uint32_t tab = pq->m * 16;
-    const uint32_t kblocks = ceil_div(pq->m, 4u);
-    const uint32_t kpad = kblocks * PK;
-    const uint32_t ccap = 2 * cap;
-    DevBuf lut16((size_t)nq * kpad * 2, st), ccnt((size_t)nq * 4, st), ccand((size_t)nq * ccap * 4, st);
-    VDB_CUDA(cudaMemsetAsync(ccnt.p, 0, (size_t)nq * 4, st));
+static uint32_t pq_kpad(const vdb_pq* pq) { return ceil_div(pq->m, 4u) * PK; }
+
+// bf16 copy of the batch's lookup tables, [nq][kpad]
+void pq_tensor_lut(const vdb_pq* pq, const float* d_lut, uint32_t nq, DevBuf& lut16, cudaStream_t st) {
+    const uint32_t kpad = pq_kpad(pq);
+    lut16 = DevBuf((size_t)nq * kpad * 2, st);
     const uint64_t count = (uint64_t)nq * kpad;
     lut_to_bf16_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), (uint64_t)sm_count() * 16), 256, 0, st>>>(
-        d_lut, tab, kpad, count, lut16.as<__nv_bfloat16>());
+        d_lut, pq->m * 16, kpad, count, lut16.as<__nv_bfloat16>());
     VDB_LAUNCHED();
+}
+
+template <int MODE>
+static void launch_pq_gemm(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, const uint8_t* codes, uint64_t n, PqGemmParams p,
+                           cudaStream_t st) {
+    const uint32_t kpad = pq_kpad(pq);
     const CUtensorMap map = make_map_bf16(lut16.p, kpad, nq, (uint64_t)kpad * 2, PN);
-    PqGemmParams p{};
-    p.codes = pq->d_codes;
-    p.n = pq->n;
+    p.codes = codes;
+    p.n = n;
     p.enc = pq->enc;
     p.m = pq->m;
-    p.kblocks = kblocks;
+    p.kblocks = kpad / PK;
     p.nq = nq;
-    p.tau = d_tau;
-    p.factor = 1.0f - (ldexpf(1.05f, -9) + (float)pq->m * ldexpf(1.0f, -21));
-    p.ccnt = ccnt.as<uint32_t>();
-    p.ccand = ccand.as<uint32_t>();
-    p.ccap = ccap;
     p.nqt = ceil_div(nq, (uint32_t)PN);
-    const uint64_t row_tiles = ceil_div<uint64_t>(pq->n, PM);
+    const uint64_t row_tiles = ceil_div<uint64_t>(n, PM);
     // items small enough that every SM gets several, large enough to amortise the threshold-tile reload
     p.tiles_per_item = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, row_tiles * p.nqt / ((uint64_t)sm_count() * 4)));
     p.nrow_items = (uint32_t)ceil_div<uint64_t>(row_tiles, p.tiles_per_item);
     static thread_local bool configured = false;
     if (!configured) {
-        VDB_CUDA(cudaFuncSetAttribute(pq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        VDB_CUDA(cudaFuncSetAttribute(pq_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         configured = true;
     }
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(), p.nrow_items * p.nqt);
-    {
-        ProfScope prof("pq_gemm", st);
-        pq_gemm_kernel<<<grid, P_THREADS, P_SMEM, st>>>(map, p);
-        VDB_LAUNCHED();
-    }
+    ProfScope prof("pq_gemm", st);
+    pq_gemm_kernel<MODE><<<grid, P_THREADS, P_SMEM, st>>>(map, p);
+    VDB_LAUNCHED();
+}
+
+// SAMPLE step: upper bounds of the ADC values of the sampled rows, [nq][sample_n]. The thresholds derived from them
+// need not be exact — the count check of the scan verifies every query afterwards.
+void pq_tensor_sample(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, float* d_all, cudaStream_t st) {
+    PqGemmParams p{};
+    p.all_out = d_all;
+    p.up_factor = 1.0f + (ldexpf(1.05f, -9) + (float)pq->m * ldexpf(1.0f, -21));
+    launch_pq_gemm<0>(pq, lut16, nq, pq->d_sample, pq->sample_n, p, st);
+}
+
+// FILTER step of the global-threshold scan on the tensor cores: on return cnt[q] / cand[q][] hold exactly the rows
+// with adc <= tau_q (as keys), or cnt[q] > cap when a list overflowed.
+void pq_tensor_filter(const vdb_pq* pq, const DevBuf& lut16, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base,
+                      uint32_t* d_cnt, uint64_t* d_cand, uint32_t cap, cudaStream_t st) {
+    const uint32_t tab = pq->m * 16;
+    const uint32_t ccap = 2 * cap;
+    DevBuf ccnt((size_t)nq * 4, st), ccand((size_t)nq * ccap * 4, st);
+    VDB_CUDA(cudaMemsetAsync(ccnt.p, 0, (size_t)nq * 4, st));
+    PqGemmParams p{};
+    p.tau = d_tau;
+    p.factor = 1.0f - (ldexpf(1.05f, -9) + (float)pq->m * ldexpf(1.0f, -21));
+    p.ccnt = ccnt.as<uint32_t>();
+    p.ccand = ccand.as<uint32_t>();
+    p.ccap = ccap;
+    launch_pq_gemm<1>(pq, lut16, nq, pq->d_codes, pq->n, p, st);
     {
         ProfScope prof("pq_exact", st);
         pq_exact_cands_kernel<<<nq, 256, (size_t)tab * 4, st>>>(pq->d_codes, pq->enc, pq->m, d_lut, d_tau, ccnt.as<uint32_t>(),

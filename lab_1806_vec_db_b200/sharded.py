@@ -5,6 +5,7 @@ torch is used here only as plumbing (device buffers, streams, torch.distributed)
 step is a kernel of libvdb_b200.so.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -48,11 +49,16 @@ class ShardedFlatIndex:
 
     TENSOR_MIN_NQ = 12
     QUERY_CHUNK = 16384
+    PIPELINE_CHUNKS = int(os.environ.get("VDB_GEMM_CHUNKS", "1"))  # > 1: two-stream chunk pipeline (measured: no gain)
 
     def __init__(self, vec_set, rank=0, world=1):
         self.vec_set = vec_set
         self.rank, self.world = rank, world
         self._tensor = None  # (n_total, sample_total, mean_norm) once known; False if unsupported
+        self._streams = None
+        self.last_fallbacks = 0
+        self.phase_timing = bool(int(os.environ.get("VDB_PHASE_TIMING", "0")))
+        self.phase_ms = {}
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def _tensor_info(self, dev):
@@ -97,41 +103,79 @@ class ShardedFlatIndex:
                                                    C.c_void_p(out.data_ptr()), st))
         return out
 
-    def _tensor_keys(self, q, k, st, info):
-        """Global [nq, k] keys through the tensor-core phases (identical on every rank)."""
+    def _tensor_enqueue(self, q, k, info):
+        """Enqueue one chunk's tensor-core phases on the CURRENT torch stream without any host synchronisation.
+        Returns the state `_tensor_finish` needs (the global [nq, k] keys are complete unless the check flags a query)."""
         import torch
         lib = L.lib()
         n_total, ns_total, mean_norm = info
         nq, dev = q.shape[0], q.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         j0 = int(lib.vdb_tq_j0(k, ns_total, n_total))
         j = max(1, min(j0, ns_total // self.world))
         tq = C.c_void_p()
+        marks = []
+
+        def mark(name):  # optional per-phase device timing (VDB_PHASE_TIMING=1): events on the chunk's stream
+            if self.phase_timing:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         L.check(lib.vdb_tq_begin_dev(self.vec_set._h, C.c_void_p(q.data_ptr()), nq, st, C.byref(tq)))
         try:
+            mark("begin")
             jkeys = torch.empty((nq, j), dtype=torch.int64, device=dev)
             L.check(lib.vdb_tq_sample_dev(tq, j, C.c_void_p(jkeys.data_ptr())))
+            mark("sample")
             allj = self._gather(jkeys)
+            mark("gather_sample")
             tau = torch.empty((nq,), dtype=torch.float32, device=dev)
             L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(allj.data_ptr()), self.world, j, min(j0, j * self.world),
                                        mean_norm, C.c_void_p(tau.data_ptr())))
+            mark("tau")
             keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
             ovf = torch.empty((nq,), dtype=torch.int32, device=dev)
             L.check(lib.vdb_tq_filter_dev(tq, k, C.c_void_p(tau.data_ptr()), C.c_void_p(keys.data_ptr()),
                                           C.c_void_p(ovf.data_ptr())))
+            mark("filter_rerank")
             allk = self._gather(keys)
             if self.world > 1:
                 import torch.distributed as dist
                 dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+            mark("gather_keys")
             merged = self._merge_to_keys(allk, nq, k, st) if self.world > 1 else keys
+            mark("merge")
             redo = torch.empty((nq,), dtype=torch.int32, device=dev)
             nredo = torch.zeros((1,), dtype=torch.int32, device=dev)
             L.check(lib.vdb_tq_check_dev(tq, C.c_void_p(merged.data_ptr()), k, n_total, C.c_void_p(tau.data_ptr()),
                                          C.c_void_p(ovf.data_ptr()), C.c_void_p(redo.data_ptr()),
                                          C.c_void_p(nredo.data_ptr())))
-            nr = int(nredo.item())  # identical on every rank (same merged keys, same tau, reduced flags)
-            self.last_fallbacks = nr
+            mark("check")
+        except Exception:
+            lib.vdb_tq_end(tq)
+            raise
+        # every tensor the enqueued work touches stays referenced until _tensor_finish
+        return {"tq": tq, "q": q, "merged": merged, "redo": redo, "nredo": nredo, "marks": marks,
+                "keep": (jkeys, allj, tau, keys, ovf, allk)}
+
+    def _tensor_finish(self, state, k):
+        """After the chunk's stream has been joined: read the check result, redo flagged queries by the exact scan."""
+        import torch
+        lib = L.lib()
+        try:
+            merged, q = state["merged"], state["q"]
+            st = C.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+            nr = int(state["nredo"].item())  # identical on every rank (same merged keys, same tau, reduced flags)
+            marks = state["marks"]
+            if marks:
+                for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                    self.phase_ms[name] = self.phase_ms.get(name, 0.0) + a.elapsed_time(b)
+                self.phase_ms["calls"] = self.phase_ms.get("calls", 0) + 1
+            self.last_fallbacks += nr
             if nr:
-                sel = torch.sort(redo[:nr].long()).values
+                sel = torch.sort(state["redo"][:nr].long()).values
                 rq = q.index_select(0, sel).contiguous()
                 rk = self._scan_keys(rq, k, st)
                 rall = self._gather(rk)
@@ -139,7 +183,45 @@ class ShardedFlatIndex:
                 merged.index_copy_(0, sel, rmerged)
             return merged
         finally:
-            lib.vdb_tq_end(tq)
+            lib.vdb_tq_end(state["tq"])
+
+    def _tensor_keys(self, q, k, info):
+        """Global [nq, k] keys through the tensor-core phases (identical on every rank). Chunks of <= 16384 queries bound
+        the scratch; the checks are read back once at the end. With VDB_GEMM_CHUNKS > 1 the chunks alternate between
+        two side streams (tail of one chunk under the contraction of the next) - measured slower on 8 B200
+        (6.23 / 6.55 / 7.05 ms per 10k-query step with 1 / 2 / 4 chunks), so it is off by default."""
+        import torch
+        nq, dev = q.shape[0], q.device
+        self.last_fallbacks = 0
+        per = -(-nq // max(1, self.PIPELINE_CHUNKS))             # ceil(nq / chunks)
+        csize = nq if (nq < 4096 or self.PIPELINE_CHUNKS <= 1) else max(1024, -(-per // 256) * 256)  # whole 256-query tiles
+        csize = min(csize, self.QUERY_CHUNK)
+        bounds = [(c0, min(nq, c0 + csize)) for c0 in range(0, nq, csize)]
+        if len(bounds) == 1:
+            return self._tensor_finish(self._tensor_enqueue(q, k, info), k)
+        cur = torch.cuda.current_stream(dev)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        states = []
+        try:
+            for s in self._streams:
+                s.wait_stream(cur)
+            for i, (c0, c1) in enumerate(bounds):
+                with torch.cuda.stream(self._streams[i & 1]):
+                    states.append(self._tensor_enqueue(q[c0:c1], k, info))
+            for s in self._streams:
+                cur.wait_stream(s)
+            parts = []
+            while states:
+                parts.append(self._tensor_finish(states.pop(0), k))
+            out = torch.cat(parts, 0)
+            for t in parts:
+                t.record_stream(cur)
+            return out
+        finally:
+            for stt in states:  # only on an exception: release the remaining contexts once their work has drained
+                torch.cuda.synchronize(dev)
+                L.lib().vdb_tq_end(stt["tq"])
 
     # ---- search --------------------------------------------------------------------------------------------
     def knn_batch_dev(self, q, k):
@@ -159,9 +241,7 @@ class ShardedFlatIndex:
         info = self._tensor_info(dev) if (nq >= self.TENSOR_MIN_NQ and 1 <= k <= 1024) else False
         if info:
             # chunks bound the candidate / rerank scratch of the filter phase
-            parts = [self._tensor_keys(q[c0:c0 + self.QUERY_CHUNK].contiguous(), k, st, info)
-                     for c0 in range(0, nq, self.QUERY_CHUNK)]
-            merged = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+            merged = self._tensor_keys(q.contiguous(), k, info)
         else:
             merged = self._merge_to_keys(self._gather(self._scan_keys(q, k, st)), nq, k, st)
         L.check(lib.vdb_decode_keys_dev(C.c_void_p(merged.data_ptr()), nq, k, C.c_void_p(ids.data_ptr()),
