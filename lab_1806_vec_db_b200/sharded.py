@@ -252,7 +252,20 @@ class ShardedFlatIndex:
         """End-to-end call with HOST buffers: H2D of the queries, search, D2H of the results."""
         import torch
         dev = torch.device("cuda", torch.cuda.current_device())
-        q = queries_pinned.to(dev, non_blocking=True)
+        nq = queries_pinned.shape[0]
+        if self.world > 1 and nq >= 64 * self.world:
+            # every rank holds the same host batch: upload 1/world of it over this GPU's PCIe link and exchange the
+            # slices over NVLink (one all-gather) instead of pushing the whole batch through every link
+            import torch.distributed as dist
+            per = -(-nq // self.world)
+            lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+            local = torch.zeros((per,) + tuple(queries_pinned.shape[1:]), dtype=queries_pinned.dtype, device=dev)
+            local[:hi - lo].copy_(queries_pinned[lo:hi], non_blocking=True)
+            q_all = torch.empty((self.world * per,) + tuple(queries_pinned.shape[1:]), dtype=queries_pinned.dtype, device=dev)
+            dist.all_gather_into_tensor(q_all, local)
+            q = q_all[:nq]
+        else:
+            q = queries_pinned.to(dev, non_blocking=True)
         ids, dd, cnt = self.knn_batch_dev(q, k)
         if out is None:
             out = (torch.empty(ids.shape, dtype=ids.dtype, pin_memory=True),
