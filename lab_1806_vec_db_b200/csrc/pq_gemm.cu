@@ -31,25 +31,43 @@
 
 namespace vdb {
 
-constexpr int PM = 128;                    // rows per tile (TMEM lanes)
+constexpr int PM = 128;                    // rows per CTA and tile (TMEM lanes)
 constexpr int PN = 256;                    // queries per tile (TMEM columns per accumulator)
 constexpr int PK = 64;                     // bf16 columns per k-block = 4 groups x 16 centroids = 128 bytes
 constexpr int P_A_BYTES = PM * PK * 2;     // 16 KB generated one-hot tile
-constexpr int P_B_BYTES = PN * PK * 2;     // 32 KB LUT tile
-constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
-constexpr int P_STAGES = 4;
-constexpr int P_THREADS = 320;
+constexpr int P_BASE_THREADS = 192;        // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer; then GG x 4 generator warps
 constexpr int P_TMEM_COLS = 512;
 constexpr uint32_t P_MAX_ENC = 128;        // m <= 256 groups
-constexpr uint32_t P_SMEM = 1024 + P_STAGES * P_STAGE_BYTES + PM * P_MAX_ENC + PN * 4 + 256;
-// instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
-constexpr uint32_t P_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+constexpr int P_MAX_STAGES = 6;
+// CTAS = 1: one CTA computes 128 rows x 256 queries. CTAS = 2: a CTA pair (cta_group::2) computes 256 rows x 256
+// queries; each CTA generates the one-hot rows of its own 128 rows and loads HALF of the LUT tile, so the shared-memory
+// traffic per MMA cycle drops 1.5x (ncu: the single-CTA kernel keeps the tensor pipe only 56 % busy at 103 B/clk of
+// shared-memory traffic).
+template <int CTAS> struct PqCfg {
+    static constexpr int B_ROWS = PN / CTAS;                   // queries loaded per CTA and k-block
+    static constexpr int B_BYTES = B_ROWS * PK * 2;
+    static constexpr int STAGE_BYTES = P_A_BYTES + B_BYTES;    // 48 KB / 32 KB
+    static constexpr int STAGES = CTAS == 1 ? 4 : 6;           // 192 KB either way
+    static constexpr uint32_t SMEM = 1024 + STAGES * STAGE_BYTES + PM * P_MAX_ENC + PN * 4 + 256;
+    // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PN >> 3) << 17) |
+                                      ((uint32_t)((PM * CTAS) >> 4) << 24);
+};
+constexpr uint32_t P_PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-pair peer bit of a shared::cluster address (-> even CTA)
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
@@ -69,111 +87,143 @@ struct PqGemmParams {
     float up_factor;        // MODE 0: 1 + relative bound
 };
 
-template <int MODE>  // 0: store every score (sample pass), 1: filter against tau
-__global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_constant__ CUtensorMap map_lut, const PqGemmParams p) {
+// MODE 0: store every score (sample pass), 1: filter against tau. GG generator groups of 4 warps take the k-blocks
+// round-robin: one group's chain per k-block (wait -> LDS -> STS -> proxy fence -> arrive) is longer than the MMAs of a
+// k-block, so several chains have to be in flight.
+template <int MODE, int CTAS, int GG>
+__global__ void __launch_bounds__(P_BASE_THREADS + 128 * GG, 1) pq_gemm_kernel(const __grid_constant__ CUtensorMap map_lut, const PqGemmParams p) {
+    using Cfg = PqCfg<CTAS>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr uint32_t TM = PM * CTAS;  // rows per tile of the CTA (pair)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stage_base = smem;
-    uint8_t* codes_s = smem + P_STAGES * P_STAGE_BYTES;                   // [PM][enc]
+    uint8_t* codes_s = smem + STAGES * Cfg::STAGE_BYTES;                  // [PM][enc]
     float* tau_s = reinterpret_cast<float*>(codes_s + PM * P_MAX_ENC);    // [PN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tau_s + PN);
-    uint64_t* full_bar = bars;                 // [P_STAGES]
-    uint64_t* empty_bar = bars + P_STAGES;     // [P_STAGES]
-    uint64_t* tfull_bar = bars + 2 * P_STAGES; // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+    uint64_t* full_bar = bars;                      // [STAGES]  (pair mode: the leader's copy is the live one)
+    uint64_t* empty_bar = bars + P_MAX_STAGES;      // [STAGES]  per CTA
+    uint64_t* tfull_bar = bars + 2 * P_MAX_STAGES;  // [2]       per CTA
+    uint64_t* tempty_bar = tfull_bar + 2;           // [2]       (pair mode: the leader's copy is the live one)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1 + 4);   // TMA expect_tx arrive + one arrive per generator warp
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1 + 4 * CTAS);  // TMA expect_tx arrive + one arrive per generator warp (of every CTA)
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], 4 * CTAS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(tmem_slot, P_TMEM_COLS);
+    if (warp == 5) {
+        if (CTAS == 2) tmem_alloc2(tmem_slot, P_TMEM_COLS);
+        else tmem_alloc(tmem_slot, P_TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / TMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t nitems = p.nrow_items * p.nqt;
+    const uint32_t unit = blockIdx.x / CTAS, nunits = gridDim.x / CTAS;  // a unit = one CTA or one CTA pair
 
     if (warp == 4) {
-        // ===== TMA producer: the LUT tile of every k-block =====
+        // ===== TMA producer: this CTA's share of the LUT tile of every k-block =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (uint32_t item = unit; item < nitems; item += nunits) {
                 const uint32_t ri = item / p.nqt, qt = item - ri * p.nqt;
-                const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
-                const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+                const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * TM;
+                const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + TM - 1) / TM);
+                const int qrow = (int)(qt * PN + cta_rank * Cfg::B_ROWS);
                 for (uint32_t t = 0; t < ntile; ++t)
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], P_B_BYTES);
-                        tma_load_2d(smem_u32(stage_base + stage * P_STAGE_BYTES) + P_A_BYTES, &map_lut, (int)(kb * PK),
-                                    (int)(qt * PN), &full_bar[stage]);
-                        if (++stage == P_STAGES) stage = 0, phase ^= 1;
+                        const uint32_t dst = smem_u32(stage_base + stage * Cfg::STAGE_BYTES) + P_A_BYTES;
+                        if (CTAS == 1) {
+                            mbar_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+                            tma_load_2d(dst, &map_lut, (int)(kb * PK), qrow, &full_bar[stage]);
+                        } else {
+                            // both CTAs' bytes are accounted on the LEADER's barrier
+                            if (leader) mbar_expect_tx(&full_bar[stage], Cfg::B_BYTES * CTAS);
+                            tma_load_2d_2sm(dst, &map_lut, (int)(kb * PK), qrow, smem_u32(&full_bar[stage]) & P_PEER_MASK);
+                        }
+                        if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
             }
         }
     } else if (warp == 5) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (one elected thread of the leader CTA) =====
+        if (lane == 0 && leader) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (uint32_t item = unit; item < nitems; item += nunits) {
                 const uint32_t ri = item / p.nqt;
-                const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
-                const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+                const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * TM;
+                const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + TM - 1) / TM);
                 for (uint32_t t = 0; t < ntile; ++t) {
-                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    if (CTAS == 2) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+                    else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * PN;
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
+                        // the peer's generators arrive with release.cluster: acquire at cluster scope
+                        if (CTAS == 2) mbar_wait_cluster(&full_bar[stage], phase);
+                        else mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(stage_base + stage * P_STAGE_BYTES);
+                        const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
                         const uint64_t da = umma_desc(sa), db = umma_desc(sa + P_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < PK / 16; ++k)  // 16 bf16 = 32 bytes (2 x 16 B units) per K step
-                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, P_IDESC, (kb | k) != 0);
-                        umma_commit(&empty_bar[stage]);
-                        if (++stage == P_STAGES) stage = 0, phase ^= 1;
+                        for (int k = 0; k < PK / 16; ++k) {  // 16 bf16 = 32 bytes (2 x 16 B units) per K step
+                            if (CTAS == 1) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                            else umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                        }
+                        if (CTAS == 1) umma_commit(&empty_bar[stage]);
+                        else umma_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
+                        if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
-                    umma_commit(&tfull_bar[acc]);
+                    if (CTAS == 1) umma_commit(&tfull_bar[acc]);
+                    else umma_commit_2sm(&tfull_bar[acc]);
                     if (++acc == 2) acc = 0, acc_phase ^= 1;
                 }
             }
         }
     } else if (warp >= 6) {
         // ===== generators: code nibbles -> one-hot bf16 rows, written in the 128B-swizzle layout =====
-        const uint32_t r = threadIdx.x - 192;  // row of the tile
-        uint32_t stage = 0, phase = 0;
-        for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const uint32_t gt = threadIdx.x - P_BASE_THREADS;
+        const uint32_t gg = gt >> 7;   // generator group
+        const uint32_t r = gt & 127;   // row of this CTA's half of the tile
+        uint32_t kbc = 0;              // running k-block counter of this CTA (all groups count alike)
+        for (uint32_t item = unit; item < nitems; item += nunits) {
             const uint32_t ri = item / p.nqt;
-            const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
-            const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+            const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * TM;
+            const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + TM - 1) / TM);
             for (uint32_t t = 0; t < ntile; ++t) {
-                const uint64_t row0 = r0 + (uint64_t)t * PM;
-                const uint32_t rows = (uint32_t)min((uint64_t)PM, p.n - row0);
-                asm volatile("bar.sync 2, 128;" ::: "memory");  // every generator is done with the previous code tile
+                const uint64_t row0 = r0 + (uint64_t)t * TM + cta_rank * PM;
+                const uint32_t rows = row0 < p.n ? (uint32_t)min((uint64_t)PM, p.n - row0) : 0u;
+                // every generator is done with the previous code tile
+                asm volatile("bar.sync 2, %0;" ::"n"(128 * GG) : "memory");
                 {
                     const uint32_t bytes = rows * p.enc;          // contiguous in the reference layout
                     const uint8_t* src = p.codes + row0 * p.enc;  // row0 * enc is a multiple of 128
                     const uint32_t vec = bytes / 16;
-                    for (uint32_t e = r; e < vec; e += 128)
+                    for (uint32_t e = gt; e < vec; e += 128 * GG)
                         reinterpret_cast<uint4*>(codes_s)[e] = __ldg(reinterpret_cast<const uint4*>(src) + e);
-                    for (uint32_t e = vec * 16 + r; e < bytes; e += 128) codes_s[e] = __ldg(src + e);
+                    for (uint32_t e = vec * 16 + gt; e < bytes; e += 128 * GG) codes_s[e] = __ldg(src + e);
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(128 * GG) : "memory");
                 const bool row_ok = r < rows;
                 const uint8_t* my = codes_s + r * p.enc;
-                for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                for (uint32_t kb = 0; kb < p.kblocks; ++kb, ++kbc) {
+                    if (kbc % GG != gg) continue;
+                    const uint32_t stage = kbc % STAGES, phase = (kbc / STAGES) & 1;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* arow = stage_base + stage * P_STAGE_BYTES + r * 128;
+                    uint8_t* arow = stage_base + stage * Cfg::STAGE_BYTES + r * 128;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t g = kb * 4 + i;
@@ -194,8 +244,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_cons
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[stage]);
-                    if (++stage == P_STAGES) stage = 0, phase ^= 1;
+                    if (lane == 0) {
+                        if (CTAS == 1) mbar_arrive(&full_bar[stage]);
+                        else mbar_arrive_cluster_release(smem_u32(&full_bar[stage]) & P_PEER_MASK);
+                    }
                 }
             }
         }
@@ -203,10 +255,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_cons
         // ===== epilogue: warps 0-3, thread = row (TMEM lane), registers = queries =====
         uint32_t acc = 0, acc_phase = 0;
         const uint32_t lane_base = (uint32_t)warp * 32;
-        for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        for (uint32_t item = unit; item < nitems; item += nunits) {
             const uint32_t ri = item / p.nqt, qt = item - ri * p.nqt;
-            const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * PM;
-            const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + PM - 1) / PM);
+            const uint64_t r0 = (uint64_t)ri * p.tiles_per_item * TM;
+            const uint32_t ntile = (uint32_t)min((uint64_t)p.tiles_per_item, (p.n - r0 + TM - 1) / TM);
             const uint32_t q0 = qt * PN;
             asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's thresholds are no longer read
             if (MODE == 1)
@@ -214,7 +266,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_cons
                     tau_s[c] = (q0 + c) < p.nq ? p.tau[q0 + c] : __uint_as_float(0xff800000u);  // -inf: nothing passes
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (uint32_t t = 0; t < ntile; ++t) {
-                const uint64_t row = r0 + (uint64_t)t * PM + threadIdx.x;
+                const uint64_t row = r0 + (uint64_t)t * TM + cta_rank * PM + threadIdx.x;
                 const bool row_ok = row < p.n;
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
@@ -243,16 +295,24 @@ __global__ void __launch_bounds__(P_THREADS, 1) pq_gemm_kernel(const __grid_cons
                         }
                     }
                 }
+                // hand the accumulator back to the MMA issuer: one arrive per warp, on the leader's barrier
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) {
+                    if (CTAS == 1) mbar_arrive(&tempty_bar[acc]);
+                    else mbar_arrive_cluster_release(smem_u32(&tempty_bar[acc]) & P_PEER_MASK);
+                }
                 if (++acc == 2) acc = 0, acc_phase ^= 1;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, P_TMEM_COLS);
+    if (CTAS == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still uses it
+    if (warp == 5) {
+        if (CTAS == 2) tmem_dealloc2(tmem_base, P_TMEM_COLS);
+        else tmem_dealloc(tmem_base, P_TMEM_COLS);
+    }
 }
 
 // [nq][m*16] f32 -> [nq][kpad] bf16 (round to nearest), zero padded to whole k-blocks
@@ -317,11 +377,17 @@ void pq_tensor_lut(const vdb_pq* pq, const float* d_lut, uint32_t nq, DevBuf& lu
     VDB_LAUNCHED();
 }
 
-template <int MODE>
-static void launch_pq_gemm(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, const uint8_t* codes, uint64_t n, PqGemmParams p,
-                           cudaStream_t st) {
+static int pq_ctas() {
+    static const int v = getenv("VDB_PQ_CTAS") ? atoi(getenv("VDB_PQ_CTAS")) : 1;
+    return v == 2 ? 2 : 1;
+}
+
+template <int MODE, int CTAS, int GG>
+static void launch_pq_gemm_t(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, const uint8_t* codes, uint64_t n, PqGemmParams p,
+                             cudaStream_t st) {
+    using Cfg = PqCfg<CTAS>;
     const uint32_t kpad = pq_kpad(pq);
-    const CUtensorMap map = make_map_bf16(lut16.p, kpad, nq, (uint64_t)kpad * 2, PN);
+    const CUtensorMap map = make_map_bf16(lut16.p, kpad, nq, (uint64_t)kpad * 2, Cfg::B_ROWS);
     p.codes = codes;
     p.n = n;
     p.enc = pq->enc;
@@ -329,19 +395,47 @@ static void launch_pq_gemm(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, c
     p.kblocks = kpad / PK;
     p.nq = nq;
     p.nqt = ceil_div(nq, (uint32_t)PN);
-    const uint64_t row_tiles = ceil_div<uint64_t>(n, PM);
-    // items small enough that every SM gets several, large enough to amortise the threshold-tile reload
-    p.tiles_per_item = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, row_tiles * p.nqt / ((uint64_t)sm_count() * 4)));
+    const uint32_t units = (uint32_t)sm_count() / CTAS;
+    const uint64_t row_tiles = ceil_div<uint64_t>(n, PM * CTAS);
+    // items small enough that every unit gets several, large enough to amortise the threshold-tile reload
+    p.tiles_per_item = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, row_tiles * p.nqt / ((uint64_t)units * 4)));
     p.nrow_items = (uint32_t)ceil_div<uint64_t>(row_tiles, p.tiles_per_item);
+    auto kern = pq_gemm_kernel<MODE, CTAS, GG>;
     static thread_local bool configured = false;
     if (!configured) {
-        VDB_CUDA(cudaFuncSetAttribute(pq_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
-    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(), p.nrow_items * p.nqt);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::min<uint32_t>(units, p.nrow_items * p.nqt) * CTAS);
+    cfg.blockDim = dim3(P_BASE_THREADS + 128 * GG);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     ProfScope prof("pq_gemm", st);
-    pq_gemm_kernel<MODE><<<grid, P_THREADS, P_SMEM, st>>>(map, p);
+    VDB_CUDA(cudaLaunchKernelEx(&cfg, kern, map, p));
     VDB_LAUNCHED();
+}
+
+template <int MODE>
+static void launch_pq_gemm(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, const uint8_t* codes, uint64_t n, PqGemmParams p,
+                           cudaStream_t st) {
+    static const int gg = getenv("VDB_PQ_GEN") ? atoi(getenv("VDB_PQ_GEN")) : 4;
+    if (pq_ctas() == 2) {
+        if (gg >= 4) launch_pq_gemm_t<MODE, 2, 4>(pq, lut16, nq, codes, n, p, st);
+        else if (gg == 2) launch_pq_gemm_t<MODE, 2, 2>(pq, lut16, nq, codes, n, p, st);
+        else launch_pq_gemm_t<MODE, 2, 1>(pq, lut16, nq, codes, n, p, st);
+    } else {
+        if (gg >= 4) launch_pq_gemm_t<MODE, 1, 4>(pq, lut16, nq, codes, n, p, st);
+        else if (gg == 2) launch_pq_gemm_t<MODE, 1, 2>(pq, lut16, nq, codes, n, p, st);
+        else launch_pq_gemm_t<MODE, 1, 1>(pq, lut16, nq, codes, n, p, st);
+    }
 }
 
 // SAMPLE step: upper bounds of the ADC values of the sampled rows, [nq][sample_n]. The thresholds derived from them
