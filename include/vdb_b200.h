@@ -37,6 +37,7 @@ enum { VDB_F32 = 0, VDB_U8 = 1 };       /* Scalar, src/scalar.rs:117-119 */
 typedef struct vdb_dataset vdb_dataset; /* device mirror of one VecSet<T> (or one row shard of it) */
 typedef struct vdb_pq vdb_pq;           /* device mirror of a PQTable<T> (src/distance/pq_table.rs:116-137) */
 typedef struct vdb_ivf vdb_ivf;         /* device mirror of an IVFIndex<T> (src/index_algorithm/ivf_index.rs:34-47) */
+typedef struct vdb_hnsw vdb_hnsw;       /* device mirror of an HNSWIndex<T> (src/index_algorithm/hnsw_index.rs:99-141) */
 
 /* ---- runtime ------------------------------------------------------------------------------ */
 const char* vdb_last_error(void);
@@ -231,6 +232,28 @@ int vdb_flat_gemm_stats(uint64_t* queries, uint64_t* candidates, uint64_t* fallb
 int vdb_ivf_knn_keys_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
                          uint32_t n_probes, uint64_t* d_keys, void* stream);
 
+/* ---- HNSW ------------------------------------------------------------------------------------- */
+/* HNSWIndex::build_on_vec_set (src/index_algorithm/hnsw_index.rs:585-600; IndexBuilder::new :495-537, add :538-572,
+ * add_parallel :399-457) over the rows of `ds` in row order, graph resident on the device. M / ef_construction as in
+ * HNSWConfig (:41-59; max_m0 = 2 M, ef_construction = max(ef_construction, 2 M)). levels[i] = rand_level (:145-149)
+ * of row i, drawn by the CALLER's RNG in row order (floor(-ln(u) / ln M)); host array of n entries. A batch of new
+ * nodes (at most max_batch, and at most inserted / M as in next_batch_size :389-395) is searched read-only on the
+ * current graph plus brute force inside the batch, then linked in batch order - the reference's batch semantics. */
+int vdb_hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* levels,
+                   uint32_t max_batch, vdb_hnsw** out);
+int vdb_hnsw_destroy(vdb_hnsw* h);
+/* n, M, effective ef_construction, enter_point (-1 when empty), enter_level. Any pointer may be NULL. */
+int vdb_hnsw_info(const vdb_hnsw* h, uint64_t* n, uint32_t* M, uint32_t* ef_construction, int64_t* enter_point,
+                  int32_t* enter_level);
+/* level-0 adjacency as the reference stores it (level0_links :110-112, links_len): links0[n * 2M], len0[n]. */
+int vdb_hnsw_links0(const vdb_hnsw* h, uint32_t* links0, uint32_t* len0);
+/* IndexKNNWithEf::knn_with_ef (:616-625) for nq queries: greedy descent from the enter point, search_on_level with
+ * max(ef, k) on level 0, the k best by (distance, id). Distances are the cached form (dist_with_cache :351-355). */
+int vdb_hnsw_knn(const vdb_dataset* ds, const vdb_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                 uint64_t* ids, float* dist, uint32_t* counts);
+int vdb_hnsw_knn_dev(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, uint32_t nq, uint32_t k,
+                     uint32_t ef, uint64_t* d_ids, float* d_dist, uint32_t* d_counts, void* stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the calling process since load. */
 uint64_t vdb_launch_count(void);
@@ -238,7 +261,7 @@ uint64_t vdb_launch_count(void);
  * kernels with CUDA events on the launching stream. vdb_prof_read synchronises the device, then
  * returns the accumulated milliseconds and launch count of kernel `name` since the last reset
  * (names: "flat_scan", "flat_gemm", "rerank", "merge", "pq_adc", "pq_encode", "ivf_scan",
- * "kmeans_assign"). */
+ * "kmeans_assign", "pq_gemm", "pq_exact", "pq_lut", "hnsw_search", "hnsw_select", "hnsw_arrange"). */
 int vdb_prof_enable(int on);
 int vdb_prof_reset(void);
 int vdb_prof_read(const char* name, double* ms, uint64_t* launches);

@@ -65,6 +65,12 @@ SIGNATURES = {
     "vdb_ivf_knn_keys_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
     "vdb_ivf_create": (i32, [vp, vp, u32, vp, vp]),
     "vdb_ivf_destroy": (i32, [vp]),
+    "vdb_hnsw_build": (i32, [vp, u32, u32, vp, u32, vp]),
+    "vdb_hnsw_destroy": (i32, [vp]),
+    "vdb_hnsw_info": (i32, [vp, vp, vp, vp, vp, vp]),
+    "vdb_hnsw_links0": (i32, [vp, vp, vp]),
+    "vdb_hnsw_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
+    "vdb_hnsw_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     "vdb_ivf_lists": (i32, [vp, vp, vp]),
     "vdb_ivf_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
     "vdb_ivf_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),

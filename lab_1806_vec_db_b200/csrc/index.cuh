@@ -46,7 +46,32 @@ struct vdb_ivf {
     uint64_t samp_n = 0;
 };
 
+// device mirror of HNSWIndex<T> (reference src/index_algorithm/hnsw_index.rs:99-141)
+struct vdb_hnsw {
+    int device = 0;
+    uint64_t n = 0;
+    uint32_t dim = 0;
+    int dtype = VDB_F32, metric = VDB_L2SQR;
+    uint32_t M = 0, M0 = 0, ef_construction = 0;
+    std::vector<uint32_t> h_level;     // vec_level
+    uint32_t* d_links0 = nullptr;      // level0_links [n][M0]
+    uint32_t* d_len0 = nullptr;        // links_len[.][0]
+    uint32_t* d_ulinks = nullptr;      // other_links: slot (uoff[node] + level - 1) holds M links
+    uint32_t* d_ulen = nullptr;        // links_len[.][level >= 1] per slot
+    uint64_t* d_uoff = nullptr;        // [n+1] prefix sum of the node levels
+    uint32_t* d_level = nullptr;       // [n]
+    float* d_cache = nullptr;          // dist_cache [n]
+    int64_t enter_point = -1;
+    int enter_level = -1;
+};
+
 namespace vdb {
+
+// hnsw.cu
+vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch);
+void hnsw_destroy(vdb_hnsw* h);
+void hnsw_knn_keys(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
+                   uint64_t* d_keys, cudaStream_t st);
 
 // kmeans.cu
 void kmeans_assign_exact(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, int metric, uint32_t lo,

@@ -440,3 +440,105 @@ class IVFIndex:
             self.close()
         except Exception:
             pass
+
+
+# ---- HNSW --------------------------------------------------------------------------------------------------------
+class HNSWConfig(NamedTuple):
+    """HNSWConfig (hnsw_index.rs:41-71)."""
+    max_elements: int = 0
+    ef_construction: int = 200
+    M: int = 16
+
+
+def hnsw_rand_levels(n, M, rng):
+    """rand_level (hnsw_index.rs:145-149) for n rows in row order: floor(-ln(u) / ln(M)), u uniform f32 in [0, 1)."""
+    u = rng.random(n, dtype=np.float32)
+    u = np.maximum(u, np.float32(2.0 ** -24))  # the reference would overflow usize on u == 0
+    inv_log_m = np.float32(1.0) / np.log(np.float32(M))
+    return np.floor(-np.log(u) * inv_log_m).astype(np.uint32)
+
+
+class HNSWIndex:
+    """HNSWIndex<T> (hnsw_index.rs:99-141): the graph lives in HBM, built batch by batch on the device."""
+
+    MAX_BATCH = 2048
+
+    def __init__(self, vec_set: DeviceVecSet, config: HNSWConfig = HNSWConfig(), rng=None, levels=None):
+        self.vec_set = vec_set
+        self.config = config
+        rng = rng if rng is not None else np.random.default_rng()
+        n = len(vec_set)
+        self.levels = (np.ascontiguousarray(levels, dtype=np.uint32) if levels is not None
+                       else hnsw_rand_levels(n, config.M, rng))
+        if self.levels.shape != (n,):
+            raise ValueError("one level per row is required")
+        self._h = C.c_void_p()
+        L.check(L.lib().vdb_hnsw_build(vec_set._h, config.M, config.ef_construction, L.ptr(self.levels), self.MAX_BATCH,
+                                       C.byref(self._h)))
+        efc = C.c_uint32(0)
+        L.check(L.lib().vdb_hnsw_info(self._h, None, None, C.byref(efc), None, None))
+        self.ef_construction = int(efc.value)
+        self.default_ef = self.ef_construction // 2  # hnsw_index.rs:505
+
+    @classmethod
+    def build_on_vec_set(cls, vec_set, dist="l2sqr", config: HNSWConfig = HNSWConfig(), rng=None):
+        """IndexBuilder::build_on_vec_set (hnsw_index.rs:585-600)."""
+        if not isinstance(vec_set, DeviceVecSet):
+            vec_set = DeviceVecSet(vec_set, dist)
+        return cls(vec_set, config, rng)
+
+    from_vec_set = build_on_vec_set
+
+    def __len__(self):
+        return len(self.vec_set)
+
+    @property
+    def enter_point(self):
+        ep, el = C.c_int64(-1), C.c_int32(-1)
+        L.check(L.lib().vdb_hnsw_info(self._h, None, None, None, C.byref(ep), C.byref(el)))
+        return int(ep.value), int(el.value)
+
+    def level0_links(self):
+        """(links [n, 2M] u32, lengths [n] u32) as the reference stores them (hnsw_index.rs:110-112)."""
+        n = len(self.vec_set)
+        links = np.zeros((n, 2 * self.config.M), np.uint32)
+        lens = np.zeros(n, np.uint32)
+        L.check(L.lib().vdb_hnsw_links0(self._h, L.ptr(links), L.ptr(lens)))
+        return links, lens
+
+    def set_default_ef(self, ef):
+        if ef <= 0:
+            raise ValueError("The search radius should be positive.")
+        self.default_ef = ef
+
+    def knn_with_ef_batch(self, queries, k, ef):
+        vs = self.vec_set
+        q = _as_rows(queries, vs.dtype)
+        if q.shape[1] != vs.dim:
+            raise ValueError("The dimension of the query doesn't match.")
+        if ef <= 0:
+            raise ValueError("The search radius should be positive.")
+        nq = q.shape[0]
+        ids = np.full((nq, k), np.iinfo(np.uint64).max, np.uint64)
+        dist = np.full((nq, k), np.nan, np.float32)
+        counts = np.zeros(nq, np.uint32)
+        L.check(L.lib().vdb_hnsw_knn(vs._h, self._h, L.ptr(q), nq, k, ef, L.ptr(ids), L.ptr(dist), L.ptr(counts)))
+        return ids, dist, counts
+
+    def knn_with_ef(self, query, k, ef):
+        """IndexKNNWithEf::knn_with_ef (hnsw_index.rs:616-625)."""
+        return _pairs(*self.knn_with_ef_batch(np.asarray(query).reshape(1, -1), k, ef))[0]
+
+    def knn(self, query, k):
+        return self.knn_with_ef(query, k, self.default_ef)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            L.lib().vdb_hnsw_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

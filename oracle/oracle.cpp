@@ -441,6 +441,136 @@ void kmeans_pp(const T* rows, size_t n, size_t dim, int metric, size_t k, size_t
     } while (0)
 #define D1(dtype, expr) DISPATCH(dtype, expr, expr)
 
+
+/* ---- hnsw_index.rs: HNSWIndex restated for one thread (add :538-572 for every row, i.e. the reference's own path
+ * while len < start_batch_since and whenever it is given one vector at a time; knn_with_ef :616-625). The graph of
+ * the reference is RNG- and thread-count dependent, so this is a recall yardstick, not a golden graph. ---- */
+template <class T> struct Hnsw {
+    const T* rows;
+    size_t n = 0, dim, m, max_m0, ef_c;
+    int metric;
+    std::vector<uint32_t> level0;            /* [n][max_m0] */
+    std::vector<std::vector<uint32_t>> other; /* [n][level * m] */
+    std::vector<std::vector<size_t>> len;     /* [n][level + 1] */
+    std::vector<size_t> vec_level;
+    std::vector<float> cache;
+    long enter_level = -1, enter_point = -1;
+
+    size_t limit(size_t level) const { return level == 0 ? max_m0 : m; }
+    const uint32_t* links(size_t v, size_t level) const {
+        return level == 0 ? &level0[v * max_m0] : &other[v][m * (level - 1)];
+    }
+    uint32_t* links(size_t v, size_t level) { return level == 0 ? &level0[v * max_m0] : &other[v][m * (level - 1)]; }
+    float d_cached(size_t idx, const T* q, float qc) const { /* dist_with_cache :351-355 */
+        const T* v = rows + idx * dim;
+        return metric == ORC_L2SQR ? l2sqr_cached(v, q, dim, cache[idx], qc) : cosine_cached(v, q, dim, cache[idx], qc);
+    }
+    float inner(size_t a, size_t b) const { return d_cached(a, rows + b * dim, cache[b]); } /* :356-358 */
+    template <class F> ResultSet search_on_level(size_t enter, size_t level, size_t ef, F dist_fn) const { /* :258-291 */
+        std::set<size_t> visited;
+        std::set<Pair, PairLess> queue;
+        ResultSet result(ef);
+        visited.insert(enter);
+        Pair ep{dist_fn(enter), enter};
+        result.add(ep);
+        queue.insert(ep);
+        while (!queue.empty()) {
+            Pair p = *queue.begin();
+            queue.erase(queue.begin());
+            /* check_candidate :55-57 */
+            if (!(result.s.size() < result.k || PairLess()(p, *std::prev(result.s.end())))) break;
+            const uint32_t* lk = links(p.i, level);
+            for (size_t j = 0; j < len[p.i][level]; ++j) {
+                size_t nb = lk[j];
+                if (!visited.insert(nb).second) continue;
+                Pair np{dist_fn(nb), nb};
+                result.add(np);
+                queue.insert(np);
+            }
+        }
+        return result;
+    }
+    template <class F> size_t greedy(size_t target, F dist_fn) const { /* :306-350 */
+        size_t level = (size_t)enter_level, cur = (size_t)enter_point;
+        while (level > target) {
+            float cur_d = dist_fn(cur);
+            for (;;) {
+                bool flag = false;
+                size_t at = cur;
+                const uint32_t* lk = links(at, level);
+                for (size_t j = 0; j < len[at][level]; ++j) {
+                    float nd = dist_fn(lk[j]);
+                    if (nd < cur_d) {
+                        cur_d = nd;
+                        cur = lk[j];
+                        flag = true;
+                    }
+                }
+                if (!flag) break;
+            }
+            --level;
+        }
+        return cur;
+    }
+    std::vector<Pair> heuristic(const std::set<Pair, PairLess>& cand, size_t mm) const { /* candidate_pair.rs:85-99 */
+        std::vector<Pair> nb;
+        for (const Pair& p : cand) {
+            if (nb.size() >= mm) break;
+            bool ok = true;
+            for (const Pair& r : nb)
+                if (!(inner(p.i, r.i) >= p.d)) {
+                    ok = false;
+                    break;
+                }
+            if (ok) nb.push_back(p);
+        }
+        return nb;
+    }
+    void arrange(size_t v, size_t level, size_t nv) { /* :204-224 */
+        size_t lim = limit(level);
+        std::vector<uint32_t> lk(links(v, level), links(v, level) + len[v][level]);
+        lk.push_back((uint32_t)nv);
+        if (lk.size() > lim) {
+            ResultSet set(lim + 1);
+            for (uint32_t x : lk) set.add(Pair{inner(v, x), x});
+            auto keep = heuristic(set.s, lim);
+            lk.clear();
+            for (const Pair& p : keep) lk.push_back((uint32_t)p.i);
+        }
+        len[v][level] = lk.size();
+        std::copy(lk.begin(), lk.end(), links(v, level));
+    }
+    void add(size_t idx, size_t level) { /* push_init :241-256 + add :538-572 */
+        level0.resize((idx + 1) * max_m0, 0);
+        other.emplace_back(m * level, 0u);
+        len.emplace_back(level + 1, (size_t)0);
+        vec_level.push_back(level);
+        const T* v = rows + idx * dim;
+        cache.push_back(metric == ORC_L2SQR ? dot(v, v, dim) : vec_norm(v, dim));
+        n = idx + 1;
+        if (enter_point < 0) {
+            enter_level = (long)level;
+            enter_point = (long)idx;
+            return;
+        }
+        const float qc = cache[idx];
+        auto dist_fn = [&](size_t i) { return d_cached(i, v, qc); };
+        size_t cur = (long)level < enter_level ? greedy(level, dist_fn) : (size_t)enter_point;
+        for (long l = std::min<long>((long)level, enter_level); l >= 0; --l) {
+            ResultSet cand = search_on_level(cur, (size_t)l, ef_c, dist_fn);
+            cur = cand.s.begin()->i;
+            auto nb = heuristic(cand.s, m); /* connect_new_links :226-239 */
+            for (size_t j = 0; j < nb.size(); ++j) links(idx, (size_t)l)[j] = (uint32_t)nb[j].i;
+            len[idx][(size_t)l] = nb.size();
+            for (const Pair& p : nb) arrange(p.i, (size_t)l, idx);
+        }
+        if ((long)level > enter_level) {
+            enter_level = (long)level;
+            enter_point = (long)idx;
+        }
+    }
+};
+
 extern "C" {
 
 float orc_dot(const void* a, const void* b, size_t dim, int dtype) {
@@ -609,6 +739,54 @@ int orc_gather_dist(const void* base, size_t dim, int dtype, int metric, const f
                      : cosine_cached((const T*)query, v, dim, query_cache, row_cache[cand[j]]);
     });
     return 0;
+}
+
+
+/* HNSW handle (f32 / u8 rows are borrowed: the caller keeps `rows` alive) */
+void* orc_hnsw_build(const void* rows, size_t n, size_t dim, int dtype, int metric, size_t m, size_t ef_construction,
+                     const uint32_t* levels) {
+    D1(dtype, {
+        auto* h = new Hnsw<T>();
+        h->rows = (const T*)rows;
+        h->dim = dim;
+        h->m = m;
+        h->max_m0 = 2 * m;                                   /* :503 */
+        h->ef_c = std::max(ef_construction, 2 * m);          /* :504 */
+        h->metric = metric;
+        for (size_t i = 0; i < n; ++i) h->add(i, levels[i]);
+        return (void*)h;
+    });
+    return nullptr;
+}
+int orc_hnsw_knn(const void* handle, int dtype, const void* queries, size_t nq, size_t k, size_t ef, uint64_t* ids,
+                 float* dists, uint32_t* counts, int nthreads) {
+    D1(dtype, {
+        const auto* h = (const Hnsw<T>*)handle;
+        parallel_for(nq, nthreads, [&](size_t q) {
+            const T* qv = (const T*)queries + q * h->dim;
+            if (h->n == 0) {
+                counts[q] = 0;
+                return;
+            }
+            const float qc = h->metric == ORC_L2SQR ? dot(qv, qv, h->dim) : vec_norm(qv, h->dim);
+            auto dist_fn = [&](size_t i) { return h->d_cached(i, qv, qc); };
+            size_t ep = h->greedy(0, dist_fn);
+            ResultSet r = h->search_on_level(ep, 0, std::max(ef, k), dist_fn);
+            counts[q] = (uint32_t)emit(r, k, ids + q * k, dists + q * k);
+        });
+    });
+    return 0;
+}
+int orc_hnsw_links0(const void* handle, int dtype, uint32_t* links0, uint32_t* len0) {
+    D1(dtype, {
+        const auto* h = (const Hnsw<T>*)handle;
+        std::copy(h->level0.begin(), h->level0.end(), links0);
+        for (size_t i = 0; i < h->n; ++i) len0[i] = (uint32_t)h->len[i][0];
+    });
+    return 0;
+}
+void orc_hnsw_free(void* handle, int dtype) {
+    D1(dtype, { delete (Hnsw<T>*)handle; });
 }
 
 /* candidate_pair.rs:127-140 */

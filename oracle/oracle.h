@@ -109,6 +109,13 @@ int orc_gather_dist(const void* base, size_t dim, int dtype, int metric, const f
                     float* out);
 
 /* candidate_pair.rs:127-140 */
+/* HNSW (hnsw_index.rs), single-thread restatement: sequential add of every row with the given levels, knn_with_ef */
+void* orc_hnsw_build(const void* rows, size_t n, size_t dim, int dtype, int metric, size_t m, size_t ef_construction,
+                     const uint32_t* levels);
+int orc_hnsw_knn(const void* handle, int dtype, const void* queries, size_t nq, size_t k, size_t ef, uint64_t* ids,
+                 float* dists, uint32_t* counts, int nthreads);
+int orc_hnsw_links0(const void* handle, int dtype, uint32_t* links0, uint32_t* len0);
+void orc_hnsw_free(void* handle, int dtype);
 float orc_recall(const uint64_t* gnd, size_t n_gnd, const uint64_t* pred, size_t n_pred);
 
 #ifdef __cplusplus

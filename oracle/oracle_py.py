@@ -261,3 +261,48 @@ def gather_dist(base, row_cache, query, query_cache, cand, metric):
 def recall(gnd, pred):
     gnd, pred = _c(gnd, np.uint64), _c(pred, np.uint64)
     return lib().orc_recall(_p(gnd), gnd.size, _p(pred), pred.size)
+
+
+class HnswOracle:
+    """Single-thread restatement of HNSWIndex (sequential add of every row, knn_with_ef); recall yardstick."""
+
+    def __init__(self, base, metric, m, ef_construction, levels):
+        self.base = _c(base)
+        self.dt = _dt(self.base)
+        levels = _c(levels, np.uint32)
+        f = lib().orc_hnsw_build
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]
+        lib().orc_hnsw_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int]
+        lib().orc_hnsw_links0.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib().orc_hnsw_free.argtypes = [C.c_void_p, C.c_int]
+        lib().orc_hnsw_free.restype = None
+        self.h = C.c_void_p(f(_p(self.base), C.c_size_t(self.base.shape[0]), C.c_size_t(self.base.shape[1]),
+                                   self.dt, _METRIC[metric], C.c_size_t(m), C.c_size_t(ef_construction), _p(levels)))
+        self.m = m
+
+    def knn(self, queries, k, ef, nthreads=1):
+        q = _c(queries)
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), np.uint64)
+        dd = np.zeros((nq, k), np.float32)
+        cnt = np.zeros(nq, np.uint32)
+        lib().orc_hnsw_knn(self.h, self.dt, _p(q), C.c_size_t(nq), C.c_size_t(k), C.c_size_t(ef), _p(ids), _p(dd),
+                           _p(cnt), nthreads)
+        return ids, dd, cnt
+
+    def links0(self):
+        n = self.base.shape[0]
+        links = np.zeros((n, 2 * self.m), np.uint32)
+        lens = np.zeros(n, np.uint32)
+        lib().orc_hnsw_links0(self.h, self.dt, _p(links), _p(lens))
+        return links, lens
+
+    def __del__(self):
+        try:
+            f = lib().orc_hnsw_free
+            f.restype = None
+            f(self.h, self.dt)
+        except Exception:
+            pass

@@ -1,0 +1,137 @@
+"""HNSW on the device (hnsw.cu) vs the single-thread CPU restatement of hnsw_index.rs (oracle) and exact Flat results.
+The reference's graph is RNG / thread-count dependent, so parity is: identical algorithm on identical levels
+(sequential insertion reproduces the oracle's adjacency almost everywhere), recall@10 not below the oracle's, the
+reference's own unit test (ids == Flat ids), structural invariants, and cached-form distances within the parity tolerance."""
+import numpy as np
+import pytest
+
+from conftest import RTOL, close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def V():
+    import lab_1806_vec_db_b200 as V
+    return V
+
+
+def recall(ids, gt):
+    return float(np.mean([len(set(a.tolist()) & set(b.tolist())) / len(b) for a, b in zip(ids, gt)]))
+
+
+def check_graph(links, lens, n, M):
+    assert lens.max() <= 2 * M
+    for i in range(n):
+        row = links[i, :lens[i]]
+        assert (row < n).all() and (row != i).all(), f"bad link at node {i}"
+        assert len(set(row.tolist())) == len(row), f"duplicate link at node {i}"
+    assert (lens[1:] > 0).all() or n < 3
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_hnsw_gist_1000_vs_oracle(V, fixtures, oracle, metric):
+    from oracle.oracle_py import HnswOracle
+    base, test = fixtures["base"], fixtures["test"][:200]
+    M, efc = 16, 200
+    levels = V.hnsw_rand_levels(len(base), M, np.random.default_rng(5))
+    ref = HnswOracle(base, metric, M, efc, levels)
+    vs = V.DeviceVecSet(base, metric)
+    idx = V.HNSWIndex(vs, V.HNSWConfig(0, efc, M), levels=levels)
+    assert idx.default_ef == 100 and idx.ef_construction == 200
+    ep = idx.enter_point
+    top = int(levels.max())
+    assert ep == (int(np.argmax(levels == top)), top)   # first row that reaches the highest level
+    links, lens = idx.level0_links()
+    check_graph(links, lens, len(base), M)
+    gt = oracle.flat_knn(base, test, 10, metric, nthreads=8)[0]
+    row_cache = np.array([oracle.dist_cache(v, metric) for v in base], np.float32)
+    for ef in (10, 50, 100):
+        ids, dd, cnt = idx.knn_with_ef_batch(test, 10, ef)
+        oi, od, oc = ref.knn(test, 10, ef, nthreads=8)
+        r_gpu, r_cpu = recall(ids, gt), recall(oi, gt)
+        assert r_gpu >= r_cpu - 0.02, (ef, r_gpu, r_cpu)
+        assert (cnt == 10).all()
+        assert (np.diff(dd, axis=1) >= 0).all()
+        # returned distances are the reference's cached form (distance/mod.rs:54-57, 67-69)
+        for qi in (0, 7, 199):
+            qc = oracle.dist_cache(test[qi], metric)
+            want = oracle.gather_dist(base, row_cache, test[qi], qc, ids[qi], metric)
+            assert close(dd[qi], want, RTOL, 2e-6).all()
+    assert recall(idx.knn_with_ef_batch(test, 10, 100)[0], gt) >= 0.99
+    # single-query trait call == batch row
+    one = idx.knn_with_ef(test[3], 10, 50)
+    many = idx.knn_with_ef_batch(test, 10, 50)
+    assert [p.index for p in one] == many[0][3].tolist()
+
+
+def test_hnsw_sequential_insertion_reproduces_the_oracle_graph(V, fixtures, oracle):
+    """max_batch = 1 is the reference's `add` path: same candidates, same heuristic, same back-link pruning. Only
+    the summation order of the dot products differs from the CPU, so almost every adjacency list must be identical."""
+    from oracle.oracle_py import HnswOracle
+    base = fixtures["base"][:600]
+    M, efc = 8, 40
+    levels = V.hnsw_rand_levels(len(base), M, np.random.default_rng(11))
+    ref_links, ref_lens = HnswOracle(base, "l2sqr", M, efc, levels).links0()
+    vs = V.DeviceVecSet(base, "l2sqr")
+    old = V.HNSWIndex.MAX_BATCH
+    V.HNSWIndex.MAX_BATCH = 1
+    try:
+        idx = V.HNSWIndex(vs, V.HNSWConfig(0, efc, M), levels=levels)
+    finally:
+        V.HNSWIndex.MAX_BATCH = old
+    links, lens = idx.level0_links()
+    check_graph(links, lens, len(base), M)
+    same = sum(1 for i in range(len(base))
+               if lens[i] == ref_lens[i] and set(links[i, :lens[i]].tolist()) == set(ref_links[i, :ref_lens[i]].tolist()))
+    assert same >= 0.95 * len(base), same
+
+
+def test_hnsw_reference_unit_test_shape(V, fixtures, oracle):
+    """hnsw_index.rs:776-786: dim clipped to 12, k = 6, query = row 200: the ids equal the Flat index's ids."""
+    base = np.ascontiguousarray(fixtures["base"][:, :12])
+    vs = V.DeviceVecSet(base, "l2sqr")
+    idx = V.HNSWIndex(vs, V.HNSWConfig(0, 200, 16), rng=np.random.default_rng(42))
+    got = idx.knn(base[200], 6)
+    want = oracle.flat_knn(base, base[200:201], 6, "l2sqr")[0][0]
+    assert [p.index for p in got] == want.tolist()
+    assert got[0].index == 200 and abs(got[0].distance) < 1e-6
+    with pytest.raises(ValueError):
+        idx.knn_with_ef(base[0], 3, 0)
+    with pytest.raises(ValueError):
+        idx.knn_with_ef(base[0, :5], 3, 10)
+
+
+def test_hnsw_batched_build_20k_and_u8(V, oracle):
+    """Batches of up to 2048 new nodes (read-only search + in-batch brute force + grouped back-links): recall must match
+    the sequentially built CPU graph; also u8 rows, k > ef, ef larger than the set."""
+    from oracle.oracle_py import HnswOracle
+    rng = np.random.default_rng(3)
+    n, dim, M, efc = 20_000, 64, 12, 100
+    proto = rng.random((200, dim), dtype=np.float32)
+    base = (proto[rng.integers(0, 200, n)] + 0.1 * rng.standard_normal((n, dim))).astype(np.float32)
+    q = (proto[rng.integers(0, 200, 300)] + 0.1 * rng.standard_normal((300, dim))).astype(np.float32)
+    levels = V.hnsw_rand_levels(n, M, rng)
+    ref = HnswOracle(base, "l2sqr", M, efc, levels)
+    vs = V.DeviceVecSet(base, "l2sqr")
+    idx = V.HNSWIndex(vs, V.HNSWConfig(0, efc, M), levels=levels)
+    links, lens = idx.level0_links()
+    check_graph(links, lens, n, M)
+    gt = oracle.flat_knn(base, q, 10, "l2sqr", nthreads=8)[0]
+    for ef in (20, 60, 200):
+        r_gpu = recall(idx.knn_with_ef_batch(q, 10, ef)[0], gt)
+        r_cpu = recall(ref.knn(q, 10, ef, nthreads=8)[0], gt)
+        assert r_gpu >= r_cpu - 0.03, (ef, r_gpu, r_cpu)
+    ids, dd, cnt = idx.knn_with_ef_batch(q[:4], 30, 5)    # ef = max(ef, k)
+    assert (cnt == 30).all()
+    # u8 rows
+    b8 = rng.integers(0, 256, (3000, 48)).astype(np.uint8)
+    q8 = b8[:50].copy()
+    vs8 = V.DeviceVecSet(b8, "l2sqr")
+    i8 = V.HNSWIndex(vs8, V.HNSWConfig(0, 64, 8), rng=rng)
+    ids, dd, cnt = i8.knn_with_ef_batch(q8, 1, 64)
+    assert (ids[:, 0] == np.arange(50)).mean() >= 0.98 and (dd[ids[:, 0] == np.arange(50), 0] == 0).all()
+    # tiny sets
+    t = V.HNSWIndex(V.DeviceVecSet(base[:3], "l2sqr"), V.HNSWConfig(0, 10, 4), rng=rng)
+    ids, dd, cnt = t.knn_with_ef_batch(base[:2], 5, 10)
+    assert (cnt == 3).all() and ids[0, 0] == 0 and ids[1, 0] == 1
