@@ -48,6 +48,9 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--nq", type=int, default=1000)
     ap.add_argument("--what", default="ivf,pq")
+    ap.add_argument("--hnsw-m", type=int, default=16)
+    ap.add_argument("--hnsw-efc", type=int, default=200)
+    ap.add_argument("--hnsw-ef", default="120:360:40", help="start:end:step of the HNSW ef sweep")
     ap.add_argument("--cpu-queries", type=int, default=8)
     ap.add_argument("--pq-m", type=int, default=240)
     ap.add_argument("--ef", default="240:600:60", help="start:end:step of the PQ ef sweep")
@@ -166,6 +169,37 @@ def main():
                               "ms_per_batch": ms, "recall@10": rec, "code_bytes_per_pass": args.n * ((M + 1) // 2),
                               "achieved_code_gbs": gbs, "cpu_qps": cpu_qps, "cpu_cores": cores, "cpu_queries": nc,
                               "gpu_vs_oracle_exact_id_rate": same}), flush=True)
+
+    if "hnsw" in args.what:
+        # C5: config/bench_hnsw.toml (M = 16 default, ef_construction = 200, ef 120..360 step 40, k = 10)
+        L.check(lib.vdb_prof_reset())
+        L.check(lib.vdb_prof_enable(1))
+        t0 = time.perf_counter()
+        hn = V.HNSWIndex(vs, V.HNSWConfig(0, args.hnsw_efc, args.hnsw_m), rng=np.random.default_rng(42))
+        t_build = time.perf_counter() - t0
+        L.check(lib.vdb_prof_enable(0))
+        kern = {}
+        for name in (b"hnsw_search", b"hnsw_select", b"hnsw_arrange"):
+            t, c = C.c_double(0), C.c_uint64(0)
+            L.check(lib.vdb_prof_read(name, C.byref(t), C.byref(c)))
+            kern[name.decode()] = {"s": t.value / 1e3, "launches": c.value}
+        links, lens = hn.level0_links()
+        print(json.dumps({"config": "C5 HNSW build", "n": args.n, "M": args.hnsw_m, "ef_construction": args.hnsw_efc,
+                          "gpu_build_s": t_build, "inserts_per_s": args.n / t_build, "kernels": kern,
+                          "level0_degree_mean": float(lens.mean()), "level0_degree_max": int(lens.max()),
+                          "enter": hn.enter_point, "max_batch": V.HNSWIndex.MAX_BATCH}), flush=True)
+        e0, e1, es = (int(x) for x in args.hnsw_ef.split(":"))
+        for ef in range(e0, e1 + 1, es):
+            ids, dd, cnt = dev_out()
+
+            def run():
+                L.check(lib.vdb_hnsw_knn_dev(vs._h, hn._h, C.c_void_p(q_dev.data_ptr()), args.nq, k, ef,
+                                             C.c_void_p(ids.data_ptr()), C.c_void_p(dd.data_ptr()),
+                                             C.c_void_p(cnt.data_ptr()), st))
+            ms, _ = timed(run)
+            rec = recall_at(ids.cpu().numpy(), gt_ids)
+            print(json.dumps({"config": "C5 HNSW search", "ef": ef, "k": k, "nq": args.nq, "qps": args.nq / ms * 1e3,
+                              "ms_per_batch": ms, "recall@10": rec}), flush=True)
 
 
 if __name__ == "__main__":

@@ -254,6 +254,13 @@ int vdb_hnsw_knn(const vdb_dataset* ds, const vdb_hnsw* h, const void* queries, 
 int vdb_hnsw_knn_dev(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, uint32_t nq, uint32_t k,
                      uint32_t ef, uint64_t* d_ids, float* d_dist, uint32_t* d_counts, void* stream);
 
+/* IndexPQ::knn_pq on the graph (:672-697): the walk uses ADC distances of the 4-bit codes, all max(ef, k) results
+ * are then re-scored exactly and the k best returned (ResultSet::pq_resort, candidate_pair.rs:102-108). */
+int vdb_hnsw_knn_pq(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq, const void* queries, uint32_t nq,
+                    uint32_t k, uint32_t ef, uint64_t* ids, float* dist, uint32_t* counts);
+int vdb_hnsw_knn_pq_dev(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq, const void* d_queries, uint32_t nq,
+                        uint32_t k, uint32_t ef, uint64_t* d_ids, float* d_dist, uint32_t* d_counts, void* stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the calling process since load. */
 uint64_t vdb_launch_count(void);

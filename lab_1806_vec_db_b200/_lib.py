@@ -71,6 +71,8 @@ SIGNATURES = {
     "vdb_hnsw_links0": (i32, [vp, vp, vp]),
     "vdb_hnsw_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
     "vdb_hnsw_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
+    "vdb_hnsw_knn_pq": (i32, [vp, vp, vp, vp, u32, u32, u32, vp, vp, vp]),
+    "vdb_hnsw_knn_pq_dev": (i32, [vp, vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     "vdb_ivf_lists": (i32, [vp, vp, vp]),
     "vdb_ivf_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
     "vdb_ivf_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),

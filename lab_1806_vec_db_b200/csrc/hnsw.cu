@@ -160,12 +160,17 @@ struct HnswSearchParams {
     int build;
     const uint64_t* out_off;   // build: first list of query i; its list of level l is out_off[i] + l
     uint64_t* out_keys;        // [lists][ef] ascending, KEY_NONE padded; ids plain
+    // PQ mode (knn_pq :672-697): distances are ADC sums over the 4-bit codes instead of row dot products
+    const uint8_t* codes;      // [n][enc]
+    uint32_t enc, m;
+    const float* lut;          // [nq][m*16]
+    const float* dcache;       // [m*16] (cosine: ||c||^2 per centroid)
 };
 
-template <typename T, int METRIC>
+template <typename T, int METRIC, bool PQ>
 __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearchParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    float* qs = reinterpret_cast<float*>(smem);                                  // [dimpad]
+    float* qs = reinterpret_cast<float*>(smem);                                  // [dimpad]: query, or LUT (+ dist_cache) in PQ mode
     uint64_t* resA = reinterpret_cast<uint64_t*>(qs + p.dimpad);                 // [ef]
     uint64_t* resB = resA + p.ef;                                                // [ef]
     uint64_t* nk = resB + p.ef;                                                  // [32]
@@ -180,13 +185,39 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearc
 
     for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {
         const uint32_t qrow = p.qrow_base + q;
-        const T* qsrc = p.build ? rows + (size_t)qrow * p.pitch : reinterpret_cast<const T*>(p.queries) + (size_t)q * p.dim;
         __syncthreads();
-        stage_row<T>(qsrc, p.dim, p.dimpad, qs);
+        if (PQ) {
+            const uint32_t tab = p.m * 16;
+            for (uint32_t e = threadIdx.x; e < tab; e += blockDim.x) {
+                qs[e] = p.lut[(size_t)q * tab + e];
+                if (METRIC == VDB_COSINE) qs[tab + e] = p.dcache[e];
+            }
+        } else {
+            const T* qsrc = p.build ? rows + (size_t)qrow * p.pitch : reinterpret_cast<const T*>(p.queries) + (size_t)q * p.dim;
+            stage_row<T>(qsrc, p.dim, p.dimpad, qs);
+        }
         const float qc = p.build ? p.rcache[qrow] : p.qcache[q];
         const uint32_t target = p.build ? p.level[qrow] : 0u;
         __syncthreads();
         auto dist_to = [&](uint32_t id) -> float {  // warp-wide
+            if (PQ) {  // ADC (pq_table.rs:239-301): lanes take the groups round-robin
+                const uint8_t* code = p.codes + (size_t)id * p.enc;
+                const uint32_t tab = p.m * 16;
+                float sv = 0.f, cv = 0.f;
+                for (uint32_t g = lane; g < p.m; g += 32) {
+                    const uint32_t byte = code[g >> 1];
+                    const uint32_t e = g * 16 + ((g & 1) ? (byte >> 4) : (byte & 0xfu));
+                    sv += qs[e];
+                    if (METRIC == VDB_COSINE) cv += qs[tab + e];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                    if (METRIC == VDB_COSINE) cv += __shfl_xor_sync(0xffffffffu, cv, o);
+                }
+                if (METRIC == VDB_L2SQR) return sv;
+                return 1.0f - sv / fmaxf(sqrtf(cv) * qc, 1e-10f);
+            }
             const float dot = warp_dot_row<T>(rows + (size_t)id * p.pitch, qs, p.pitch, lane);
             return cached_dist<METRIC>(dot, p.rcache[id], qc);
         };
@@ -484,7 +515,8 @@ __global__ void iota_pairs_kernel(const uint64_t* __restrict__ keys, uint32_t nq
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
-static uint32_t hash_cap_for(uint32_t ef) { return ef <= 256 ? 16384u : 32768u; }
+// visited-set capacity: a search visits ~10-15 nodes per expansion; beyond 7/8 full further neighbours are ignored
+static uint32_t hash_cap_for(uint32_t ef) { return ef <= 128 ? 8192u : (ef <= 640 ? 16384u : 32768u); }
 
 template <typename KernT, typename ParamT>
 static void launch_dyn(KernT kern, uint32_t grid, size_t smem, const ParamT& p, cudaStream_t st) {
@@ -494,18 +526,25 @@ static void launch_dyn(KernT kern, uint32_t grid, size_t smem, const ParamT& p, 
 }
 
 static void launch_search(const vdb_dataset* ds, const HnswSearchParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)p.dimpad * 4 + (size_t)p.ef * 16 + 32 * 8 + 64 * 4 + (size_t)(p.hash_mask + 1) * 4;
+    const bool pq = p.codes != nullptr;
+    const size_t vec_floats = pq ? (size_t)p.m * 16 * (ds->metric == VDB_COSINE ? 2 : 1) : (size_t)p.dimpad;
+    const size_t smem = round_up(vec_floats, (size_t)4) * 4 + (size_t)p.ef * 16 + 32 * 8 + 64 * 4 + (size_t)(p.hash_mask + 1) * 4;
     VDB_REQUIRE(smem <= 200 * 1024, "HNSW search: ef=%u / dim=%u do not fit in shared memory", p.ef, p.dim);
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
     const uint32_t grid = std::min<uint32_t>(p.nq, (uint32_t)sm_count() * per_sm);
     ProfScope prof("hnsw_search", st);
     const bool l2 = ds->metric == VDB_L2SQR;
-    if (ds->dtype == VDB_F32) {
-        if (l2) launch_dyn(hnsw_search_kernel<float, VDB_L2SQR>, grid, smem, p, st);
-        else launch_dyn(hnsw_search_kernel<float, VDB_COSINE>, grid, smem, p, st);
+    HnswSearchParams q = p;
+    if (pq) q.dimpad = (uint32_t)round_up(vec_floats, (size_t)4);  // the kernel's vector area holds the tables
+    if (pq) {
+        if (l2) launch_dyn(hnsw_search_kernel<uint8_t, VDB_L2SQR, true>, grid, smem, q, st);
+        else launch_dyn(hnsw_search_kernel<uint8_t, VDB_COSINE, true>, grid, smem, q, st);
+    } else if (ds->dtype == VDB_F32) {
+        if (l2) launch_dyn(hnsw_search_kernel<float, VDB_L2SQR, false>, grid, smem, q, st);
+        else launch_dyn(hnsw_search_kernel<float, VDB_COSINE, false>, grid, smem, q, st);
     } else {
-        if (l2) launch_dyn(hnsw_search_kernel<uint8_t, VDB_L2SQR>, grid, smem, p, st);
-        else launch_dyn(hnsw_search_kernel<uint8_t, VDB_COSINE>, grid, smem, p, st);
+        if (l2) launch_dyn(hnsw_search_kernel<uint8_t, VDB_L2SQR, false>, grid, smem, q, st);
+        else launch_dyn(hnsw_search_kernel<uint8_t, VDB_COSINE, false>, grid, smem, q, st);
     }
 }
 
@@ -723,6 +762,21 @@ vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction
     return h;
 }
 
+// the k best by (cached-form distance, id) of the first `take` entries of every [ef] candidate list
+static void exact_topk_of(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, const float* d_qcache,
+                          const uint64_t* d_cand, uint32_t nq, uint32_t ef, uint32_t k, uint64_t* d_keys, cudaStream_t st,
+                          uint32_t take = 0) {
+    if (take == 0) take = ef;
+    const uint64_t cnt = (uint64_t)nq * take;
+    DevBuf qidx(cnt * 4, st), rid(cnt * 4, st), valid(cnt, st), dist(cnt * 4, st), keys2(cnt * 8, st);
+    iota_pairs_kernel<<<(uint32_t)ceil_div<uint64_t>(cnt, 256), 256, 0, st>>>(d_cand, nq, ef, take, qidx.as<uint32_t>(),
+                                                                            rid.as<uint32_t>(), valid.as<uint8_t>());
+    VDB_LAUNCHED();
+    cached_pair_distances(ds, d_queries, d_qcache, h->d_cache, qidx.as<uint32_t>(), rid.as<uint32_t>(), cnt, dist.as<float>(), st);
+    rekey_based(dist.as<float>(), rid.as<uint32_t>(), (uint32_t)ds->id_base, valid.as<uint8_t>(), cnt, keys2.as<uint64_t>(), st);
+    launch_merge_keys(keys2.as<uint64_t>(), 1, nq, take, false, k, d_keys, nullptr, nullptr, nullptr, st);
+}
+
 // knn_with_ef (:616-625) for a batch: [nq][k] keys ascending by (distance, id); distances are the cached form,
 // re-evaluated by the pair kernel that also serves vdb_gather_dist
 void hnsw_knn_keys(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, uint32_t nq, uint32_t k, uint32_t ef_in,
@@ -761,17 +815,55 @@ void hnsw_knn_keys(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queri
     sp.build = 0;
     sp.out_keys = cand.as<uint64_t>();
     launch_search(ds, sp, st);
-    // the k best of the ef results, cached-form distances from the pair kernel
-    const uint64_t cnt = (uint64_t)nq * k;
-    DevBuf qidx(cnt * 4, st), rid(cnt * 4, st), valid(cnt, st), dist(cnt * 4, st), keys2(cnt * 8, st);
-    iota_pairs_kernel<<<(uint32_t)ceil_div<uint64_t>(cnt, 256), 256, 0, st>>>(cand.as<uint64_t>(), nq, ef, std::min(k, ef),
-                                                                            qidx.as<uint32_t>(), rid.as<uint32_t>(),
-                                                                            valid.as<uint8_t>());
-    VDB_LAUNCHED();
-    cached_pair_distances(ds, d_queries, qcache.as<float>(), h->d_cache, qidx.as<uint32_t>(), rid.as<uint32_t>(), cnt,
-                          dist.as<float>(), st);
-    rekey_based(dist.as<float>(), rid.as<uint32_t>(), (uint32_t)ds->id_base, valid.as<uint8_t>(), cnt, keys2.as<uint64_t>(), st);
-    launch_merge_keys(keys2.as<uint64_t>(), 1, nq, k, false, k, d_keys, nullptr, nullptr, nullptr, st);
+    // into_sorted_vec_limit(k): the k best of the ef results
+    exact_topk_of(ds, h, d_queries, qcache.as<float>(), cand.as<uint64_t>(), nq, ef, k, d_keys, st, k);
+}
+
+// HNSWIndex::knn_pq (:672-697): the graph is walked with ADC distances, then ALL max(ef, k) results are re-scored
+// with the exact cached form and the k best by (distance, id) returned (ResultSet::pq_resort, candidate_pair.rs:102-108)
+void hnsw_knn_pq_keys(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,
+                      uint32_t ef_in, uint64_t* d_keys, cudaStream_t st) {
+    VDB_REQUIRE(ds->n == h->n && ds->dim == h->dim && ds->dtype == h->dtype && ds->metric == h->metric,
+                "HNSW index was built for a different vector set");
+    VDB_REQUIRE(pq->metric == ds->metric, "Distance algorithm mismatch.");
+    VDB_REQUIRE(pq->n == ds->n && pq->dim == ds->dim, "PQ table was built for a different vector set");
+    VDB_REQUIRE(pq->n_bits == 4, "HNSW + PQ search supports 4-bit codes");
+    if (nq == 0 || k == 0) return;
+    if (h->n == 0) {
+        VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
+        return;
+    }
+    const uint32_t ef = std::max(ef_in, k);
+    VDB_REQUIRE(ef <= 4096, "HNSW search: ef=%u is too large (max 4096)", ef);
+    const uint32_t tab = pq->m * 16;
+    DevBuf lut((size_t)nq * tab * 4, st), qn((size_t)nq * 4, st), qcache((size_t)nq * 4, st), cand((size_t)nq * ef * 8, st);
+    pq_lut(pq, d_queries, nq, lut.as<float>(), qn.as<float>(), st);
+    {
+        vdb_dataset qd = *ds;
+        qd.d_rows = const_cast<void*>(d_queries);
+        qd.n = nq;
+        qd.pitch = ds->dim;
+        row_cache(&qd, qcache.as<float>(), st);
+    }
+    HnswSearchParams sp{};
+    sp.g = graph_of(h);
+    sp.dim = ds->dim;
+    sp.rcache = h->d_cache;
+    sp.qcache = qn.as<float>();  // cosine: ||q|| of the lookup table (pq_table.rs:215-221)
+    sp.nq = nq;
+    sp.ef = ef;
+    sp.hash_mask = hash_cap_for(ef) - 1;
+    sp.enter_point = (uint32_t)h->enter_point;
+    sp.enter_level = (uint32_t)h->enter_level;
+    sp.build = 0;
+    sp.out_keys = cand.as<uint64_t>();
+    sp.codes = pq->d_codes;
+    sp.enc = pq->enc;
+    sp.m = pq->m;
+    sp.lut = lut.as<float>();
+    sp.dcache = pq->d_dist_cache;
+    launch_search(ds, sp, st);
+    exact_topk_of(ds, h, d_queries, qcache.as<float>(), cand.as<uint64_t>(), nq, ef, k, d_keys, st);
 }
 
 }  // namespace vdb

@@ -72,6 +72,8 @@ vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction
 void hnsw_destroy(vdb_hnsw* h);
 void hnsw_knn_keys(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
                    uint64_t* d_keys, cudaStream_t st);
+void hnsw_knn_pq_keys(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,
+                      uint32_t ef, uint64_t* d_keys, cudaStream_t st);
 
 // kmeans.cu
 void kmeans_assign_exact(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, int metric, uint32_t lo,

@@ -532,6 +532,25 @@ class HNSWIndex:
     def knn(self, query, k):
         return self.knn_with_ef(query, k, self.default_ef)
 
+    def knn_pq_batch(self, queries, k, ef, pq_table):
+        vs = self.vec_set
+        q = _as_rows(queries, vs.dtype)
+        if q.shape[1] != vs.dim:
+            raise ValueError("The dimension of the query doesn't match.")
+        if ef <= 0:
+            raise ValueError("The search radius should be positive.")
+        nq = q.shape[0]
+        ids = np.full((nq, k), np.iinfo(np.uint64).max, np.uint64)
+        dist = np.full((nq, k), np.nan, np.float32)
+        counts = np.zeros(nq, np.uint32)
+        L.check(L.lib().vdb_hnsw_knn_pq(vs._h, self._h, pq_table._h, L.ptr(q), nq, k, ef, L.ptr(ids), L.ptr(dist),
+                                        L.ptr(counts)))
+        return ids, dist, counts
+
+    def knn_pq(self, query, k, ef, pq_table):
+        """IndexPQ::knn_pq (hnsw_index.rs:672-697)."""
+        return _pairs(*self.knn_pq_batch(np.asarray(query).reshape(1, -1), k, ef, pq_table))[0]
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             L.lib().vdb_hnsw_destroy(self._h)

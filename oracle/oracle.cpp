@@ -777,6 +777,35 @@ int orc_hnsw_knn(const void* handle, int dtype, const void* queries, size_t nq, 
     });
     return 0;
 }
+/* HNSWIndex::knn_pq (hnsw_index.rs:672-697): graph walk with ADC distances, then pq_resort with dist_with_cache */
+int orc_hnsw_knn_pq(const void* handle, int dtype, const void* queries, size_t nq, size_t k, size_t ef, const uint8_t* codes,
+                    const void* codebooks, size_t m, size_t n_bits, uint64_t* ids, float* dists, uint32_t* counts, int nthreads) {
+    D1(dtype, {
+        const auto* h = (const Hnsw<T>*)handle;
+        const size_t kc = (size_t)1 << n_bits;
+        const size_t enc = n_bits == 4 ? (m + 1) / 2 : m;
+        std::vector<float> dcache(m * kc);
+        pq_dist_cache<T>(h->dim, h->metric, (const T*)codebooks, m, n_bits, dcache.data());
+        parallel_for(nq, nthreads, [&](size_t q) {
+            const T* qv = (const T*)queries + q * h->dim;
+            if (h->n == 0) {
+                counts[q] = 0;
+                return;
+            }
+            std::vector<float> lut(m * kc);
+            float qn;
+            pq_lookup(qv, h->dim, h->metric, (const T*)codebooks, m, n_bits, lut.data(), &qn);
+            auto dist_fn = [&](size_t i) { return pq_adc(codes + i * enc, m, n_bits, h->metric, lut.data(), dcache.data(), qn); };
+            size_t ep = h->greedy(0, dist_fn);
+            ResultSet r = h->search_on_level(ep, 0, std::max(ef, k), dist_fn);
+            const float qc = h->metric == ORC_L2SQR ? dot(qv, qv, h->dim) : vec_norm(qv, h->dim);
+            ResultSet rs(k);
+            for (const Pair& p : r.s) rs.add({h->d_cached(p.i, qv, qc), p.i});
+            counts[q] = (uint32_t)emit(rs, k, ids + q * k, dists + q * k);
+        });
+    });
+    return 0;
+}
 int orc_hnsw_links0(const void* handle, int dtype, uint32_t* links0, uint32_t* len0) {
     D1(dtype, {
         const auto* h = (const Hnsw<T>*)handle;

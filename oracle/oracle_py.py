@@ -292,6 +292,18 @@ class HnswOracle:
                            _p(cnt), nthreads)
         return ids, dd, cnt
 
+    def knn_pq(self, queries, k, ef, codes, codebooks, m, n_bits, nthreads=1):
+        q, codes, codebooks = _c(queries), _c(codes, np.uint8), _c(codebooks)
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), np.uint64)
+        dd = np.zeros((nq, k), np.float32)
+        cnt = np.zeros(nq, np.uint32)
+        f = lib().orc_hnsw_knn_pq
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                      C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        f(self.h, self.dt, _p(q), nq, k, ef, _p(codes), _p(codebooks), m, n_bits, _p(ids), _p(dd), _p(cnt), nthreads)
+        return ids, dd, cnt
+
     def links0(self):
         n = self.base.shape[0]
         links = np.zeros((n, 2 * self.m), np.uint32)

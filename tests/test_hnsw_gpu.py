@@ -135,3 +135,35 @@ def test_hnsw_batched_build_20k_and_u8(V, oracle):
     t = V.HNSWIndex(V.DeviceVecSet(base[:3], "l2sqr"), V.HNSWConfig(0, 10, 4), rng=rng)
     ids, dd, cnt = t.knn_with_ef_batch(base[:2], 5, 10)
     assert (cnt == 3).all() and ids[0, 0] == 0 and ids[1, 0] == 1
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_hnsw_knn_pq_vs_oracle(V, fixtures, oracle, metric):
+    """HNSWIndex::knn_pq (hnsw_index.rs:672-697): graph walk with ADC distances + exact resort of all ef results. Same
+    levels, codebooks and codes on both sides; the graphs are built independently, so compare by recall and check the
+    returned distances against the cached form."""
+    from oracle.oracle_py import HnswOracle
+    base, test = fixtures["base"], fixtures["test"][:150]
+    M, efc, m = 16, 200, 96
+    rng = np.random.default_rng(9)
+    levels = V.hnsw_rand_levels(len(base), M, rng)
+    books = np.concatenate([np.ascontiguousarray(base[100:116, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(960, m)])
+    vs = V.DeviceVecSet(base, metric)
+    pq = V.PQTable(vs, V.PQConfig(4, m, metric), books)
+    codes = oracle.pq_encode(base, books, m, 4, metric, nthreads=8)
+    assert (pq.encoded_vec_set == codes).all()
+    idx = V.HNSWIndex(vs, V.HNSWConfig(0, efc, M), levels=levels)
+    ref = HnswOracle(base, metric, M, efc, levels)
+    gt = oracle.flat_knn(base, test, 10, metric, nthreads=8)[0]
+    row_cache = np.array([oracle.dist_cache(v, metric) for v in base], np.float32)
+    for ef in (20, 100):
+        ids, dd, cnt = idx.knn_pq_batch(test, 10, ef, pq)
+        oi, od, oc = ref.knn_pq(test, 10, ef, codes, books, m, 4, nthreads=8)
+        r_gpu, r_cpu = recall(ids, gt), recall(oi, gt)
+        assert r_gpu >= r_cpu - 0.03, (ef, r_gpu, r_cpu)
+        assert (cnt == 10).all() and (np.diff(dd, axis=1) >= 0).all()
+        for qi in (0, 5):
+            want = oracle.gather_dist(base, row_cache, test[qi], oracle.dist_cache(test[qi], metric), ids[qi], metric)
+            assert close(dd[qi], want, RTOL, 2e-6).all()
+    one = idx.knn_pq(test[2], 10, 100, pq)
+    assert [p.index for p in one] == idx.knn_pq_batch(test, 10, 100, pq)[0][2].tolist()
