@@ -3,13 +3,14 @@
 names/arguments (src/pyo3/mod.rs, lab_1806_vec_db.pyi) so `VecDB.search / build_pq_table / build_hnsw_index` callers
 can switch without code changes. Storage, locking and autosave are out of scope: tables live in memory.
 
-Deviation (documented in DESIGN.md): `build_hnsw_index` only marks the table; searches keep using the exact GPU
-Flat index (which ignores `ef` exactly like the reference's Flat arm, dynamic_index.rs:77) — results are the exact
-neighbours the HNSW graph approximates. The graph build itself is host-side work outside this round's path.
+`build_hnsw_index` builds the graph on the device (hnsw.cu) and the search policy follows DynamicIndex
+(src/database/dynamic_index.rs:63-93). Deviation: the reference inserts vectors added AFTER the build into the existing
+graph one by one (dynamic_index.rs:44-55); here an add marks the graph stale and the next search rebuilds it in one
+batched pass (the device build of 1M x 960 takes ~13 s), so searches always see every vector.
 """
 import numpy as np
 
-from .index import DeviceVecSet, FlatIndex, PQConfig, PQTable
+from .index import DeviceVecSet, FlatIndex, HNSWConfig, HNSWIndex, PQConfig, PQTable
 from . import _lib as L
 
 
@@ -25,7 +26,9 @@ class MetadataVecTable:
         self.metadata = []
         self.vec_set = None                                   # GPU mirror, created on first use
         self.pq_table = None
-        self._hnsw = False
+        self._hnsw = None                                     # HNSWIndex, or None (DynamicIndex::Flat)
+        self._hnsw_efc = None
+        self._hnsw_stale = False
         self.rng = rng if rng is not None else np.random.default_rng()  # from_entropy, metadata_vec_table.rs:18
 
     def __len__(self):
@@ -58,6 +61,8 @@ class MetadataVecTable:
         self.rows = np.concatenate([self.rows, new])
         if self.vec_set is not None:
             self.vec_set.push(new)                             # VecSet::push on the mirror
+        if self._hnsw is not None:
+            self._hnsw_stale = True                            # DynamicIndex::HNSW add (:44-55): see the module note
 
     def delete(self, pattern):
         self.clear_hnsw_index()                                # :170
@@ -75,13 +80,27 @@ class MetadataVecTable:
 
     # ---- indexes ----
     def build_hnsw_index(self, ef_construction=None):
-        self._hnsw = True
+        """metadata_vec_table.rs:84-98: skipped when already built; HNSWConfig defaults (M = 16, ef_construction = 200)."""
+        if self._hnsw is not None:
+            return
+        self._hnsw_efc = ef_construction
+        self._build_hnsw()
+
+    def _build_hnsw(self):
+        cfg = HNSWConfig(len(self), 200 if self._hnsw_efc is None else self._hnsw_efc, 16)
+        if self._hnsw is not None:
+            self._hnsw.close()
+        self._hnsw = HNSWIndex(self._mirror(), cfg, self.rng)
+        self._hnsw_stale = False
 
     def clear_hnsw_index(self):
-        self._hnsw = False
+        if self._hnsw is not None:
+            self._hnsw.close()
+        self._hnsw = None
+        self._hnsw_stale = False
 
     def has_hnsw_index(self):
-        return self._hnsw
+        return self._hnsw is not None
 
     def build_pq_table(self, train_proportion=None, n_bits=None, m=None):
         """metadata_vec_table.rs:112-152 (note: n_bits is validated, then 4 is always used, :140)."""
@@ -117,11 +136,18 @@ class MetadataVecTable:
         q = np.ascontiguousarray(query, np.float32).reshape(-1)
         if q.size != self.dim_:
             raise ValueError("The dimension of the query doesn't match.")
-        flat = FlatIndex(self._mirror())
-        if ef is not None and self.pq_table is not None:
-            results = flat.knn_pq(q, k, ef, self.pq_table)
+        if self._hnsw is not None:
+            if self._hnsw_stale:
+                self._build_hnsw()
+            inner = self._hnsw
         else:
-            results = flat.knn(q, k)  # Flat ignores ef (dynamic_index.rs:77)
+            inner = FlatIndex(self._mirror())
+        if ef is not None and self.pq_table is not None:
+            results = inner.knn_pq(q, k, ef, self.pq_table)
+        elif ef is not None and self._hnsw is not None:
+            results = inner.knn_with_ef(q, k, ef)
+        else:
+            results = inner.knn(q, k)  # Flat ignores ef (dynamic_index.rs:77); HNSW uses its default ef
         ub = np.inf if upper_bound is None else upper_bound
         return [(dict(self.metadata[p.index]), p.distance) for p in results if p.distance <= ub]
 

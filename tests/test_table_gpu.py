@@ -70,3 +70,27 @@ def test_search_variants_against_oracle(fixtures, oracle):
     assert t.pq_table.config.n_bits == 4 and t.pq_table.config.k_means_size == 150
     got = t.search(q, 5, ef=300)                                                      # ef >= n: rerank of everything
     assert [int(m["i"]) for m, _ in got] == want[0][0].tolist()
+
+
+def test_hnsw_variants_of_the_search_policy(fixtures, oracle):
+    """DynamicIndex::HNSW arms (dynamic_index.rs:63-93): knn -> default ef, knn_with_ef, knn_pq on the graph; an add
+    after the build is visible to the next search; delete clears the graph."""
+    from lab_1806_vec_db_b200.table import MetadataVecTable
+    base = fixtures["base"][:400]
+    t = MetadataVecTable(960, "l2sqr", np.random.default_rng(7))
+    t.batch_add(base[:350], [{"i": str(i)} for i in range(350)])
+    t.build_hnsw_index(64)
+    assert t.has_hnsw_index()
+    q = fixtures["test"][1]
+    want = oracle.flat_knn(base[:350], q.reshape(1, -1), 5, "l2sqr")[0][0].tolist()
+    assert [int(m["i"]) for m, _ in t.search(q, 5)] == want                 # default ef = ef_construction / 2
+    assert [int(m["i"]) for m, _ in t.search(q, 5, ef=200)] == want
+    t.build_pq_table(0.5, 4, 240)
+    got = [int(m["i"]) for m, _ in t.search(q, 5, ef=350)]                  # graph walk with ADC, exact resort
+    assert len(set(got) & set(want)) >= 4
+    t.batch_add(base[350:], [{"i": str(i)} for i in range(350, 400)])      # drops PQ, graph follows the new rows
+    assert t.has_hnsw_index() and not t.has_pq_table()
+    got = t.search(base[399], 1, ef=100)
+    assert got[0][0]["i"] == "399" and abs(got[0][1]) < 1e-5
+    t.delete({"i": "0"})
+    assert not t.has_hnsw_index()
