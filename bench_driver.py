@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """bench_driver.py — runs a reference BenchConfig TOML (examples/bench.rs:70-92) on the GPU backend and appends a
 `[[results]]` block in the reference's ResultList TOML format (bench.rs:312-368), so curves are directly comparable
-with data/t_bench*.toml. Supported `algorithm` tables: `IVF` and `Flat` (with or without `[PQ]`); HNSW configs are
-rejected (the graph walk is host-side work that this backend does not implement yet).
+with data/t_bench*.toml. Supported `algorithm` tables: `HNSW`, `IVF` and `Flat`, each with or without `[PQ]`
+(HNSW + PQ = IndexPQ::knn_pq on the graph, hnsw_index.rs:672-697).
 
   python bench_driver.py config/bench_10000_ivf.toml [--repeat-times N]
 
@@ -60,13 +60,22 @@ def main():
         index = V.IVFIndex.from_vec_set(vs, base, dist, V.IVFConfig(a["k"], a.get("k_means_size"), a["k_means_max_iter"],
                                                                     a["k_means_tol"]), rng)
         search = lambda ef: index.knn_with_ef_batch(test, k, ef)  # noqa: E731
+    elif "HNSW" in algo:
+        a = algo["HNSW"]
+        t0 = time.perf_counter()
+        index = V.HNSWIndex(vs, V.HNSWConfig(a.get("max_elements", 0), a.get("ef_construction", 200), a.get("M", 16)), rng)
+        print(f"HNSW build: {time.perf_counter() - t0:.2f} s for {len(base)} vectors", flush=True)
+        if pq is None:
+            search = lambda ef: index.knn_with_ef_batch(test, k, ef)  # noqa: E731
+        else:
+            search = lambda ef: index.knn_pq_batch(test, k, ef, pq)  # noqa: E731
     elif "Flat" in algo or "flat" in algo:
         if pq is None:
             search = lambda ef: flat.knn_batch(test, k)  # noqa: E731
         else:
             search = lambda ef: flat.knn_pq_batch(test, k, ef, pq)  # noqa: E731
     else:
-        raise SystemExit(f"unsupported algorithm table {list(algo)}: only IVF and Flat(+PQ) run on this backend")
+        raise SystemExit(f"unsupported algorithm table {list(algo)}")
     res = {"label": cfg["label"], "ef": [], "search_time": [], "recall": []}
     for ef in cfg["ef_values"]:
         search(ef)  # warm-up

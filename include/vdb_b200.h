@@ -247,6 +247,14 @@ int vdb_hnsw_info(const vdb_hnsw* h, uint64_t* n, uint32_t* M, uint32_t* ef_cons
                   int32_t* enter_level);
 /* level-0 adjacency as the reference stores it (level0_links :110-112, links_len): links0[n * 2M], len0[n]. */
 int vdb_hnsw_links0(const vdb_hnsw* h, uint32_t* links0, uint32_t* len0);
+/* Upper levels (other_links :113-119, links_len): for every node its level_i lists of M links, nodes in row order,
+ * levels 1..level_i in order: ulinks[sum(levels) * M], ulen[sum(levels)]. levels[n] is filled when non-NULL. */
+int vdb_hnsw_upper(const vdb_hnsw* h, uint32_t* levels, uint32_t* ulinks, uint32_t* ulen);
+/* An index built elsewhere - e.g. deserialised from the reference's bincode file (IndexSerdeExternalVecSet
+ * :641-668) - over the rows of `ds`: same layouts as vdb_hnsw_links0 / vdb_hnsw_upper. */
+int vdb_hnsw_create_from_graph(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* levels,
+                               const uint32_t* links0, const uint32_t* len0, const uint32_t* ulinks, const uint32_t* ulen,
+                               int64_t enter_point, int32_t enter_level, vdb_hnsw** out);
 /* IndexKNNWithEf::knn_with_ef (:616-625) for nq queries: greedy descent from the enter point, search_on_level with
  * max(ef, k) on level 0, the k best by (distance, id). Distances are the cached form (dist_with_cache :351-355). */
 int vdb_hnsw_knn(const vdb_dataset* ds, const vdb_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef,

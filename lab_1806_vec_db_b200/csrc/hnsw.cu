@@ -572,48 +572,102 @@ void hnsw_destroy(vdb_hnsw* h) {
     delete h;
 }
 
-// HNSWIndex::build_on_vec_set (:585-600) over the rows of `ds` in row order. `h_levels[i]` is rand_level (:145-149)
-// of row i, drawn by the caller's RNG in row order like the reference does.
-vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch) {
+// allocation + level tables shared by build and load
+static void hnsw_alloc(vdb_hnsw* h, const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels,
+                       cudaStream_t st) {
     VDB_REQUIRE(M >= 2 && M <= HN_MAX_M0 / 2, "HNSW: M must be in [2, %u]", HN_MAX_M0 / 2);
     VDB_REQUIRE(ds->n < (1ull << 31), "HNSW: at most 2^31 rows");
-    VDB_REQUIRE(((uintptr_t)ds->d_rows & 15) == 0, "HNSW: rows must be 16-byte aligned");
+    VDB_REQUIRE(((uintptr_t)ds->d_rows & 15) == 0 && ds->pitch % 4 == 0, "HNSW: rows must be 16-byte aligned");
+    const uint64_t n = ds->n;
+    h->device = ds->device;
+    h->n = n;
+    h->dim = ds->dim;
+    h->dtype = ds->dtype;
+    h->metric = ds->metric;
+    h->M = M;
+    h->M0 = 2 * M;
+    h->ef_construction = std::max(ef_construction, 2 * M);  // :504
+    h->h_level.assign(h_levels, h_levels + n);
+    std::vector<uint64_t> uoff(n + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        VDB_REQUIRE(h_levels[i] < 64, "HNSW: level %u of row %llu is out of range", h_levels[i], (unsigned long long)i);
+        uoff[i + 1] = uoff[i] + h_levels[i];
+    }
+    h->slots = uoff[n];
+    const uint64_t slots = std::max<uint64_t>(uoff[n], 1);
+    VDB_CUDA(cudaMalloc(&h->d_links0, std::max<uint64_t>(n, 1) * h->M0 * 4));
+    VDB_CUDA(cudaMalloc(&h->d_len0, std::max<uint64_t>(n, 1) * 4));
+    VDB_CUDA(cudaMalloc(&h->d_ulinks, slots * M * 4));
+    VDB_CUDA(cudaMalloc(&h->d_ulen, slots * 4));
+    VDB_CUDA(cudaMalloc(&h->d_uoff, (n + 1) * 8));
+    VDB_CUDA(cudaMalloc(&h->d_level, std::max<uint64_t>(n, 1) * 4));
+    VDB_CUDA(cudaMalloc(&h->d_cache, std::max<uint64_t>(n, 1) * 4));
+    VDB_CUDA(cudaMemsetAsync(h->d_links0, 0, std::max<uint64_t>(n, 1) * h->M0 * 4, st));
+    VDB_CUDA(cudaMemsetAsync(h->d_ulinks, 0, slots * M * 4, st));
+    VDB_CUDA(cudaMemsetAsync(h->d_len0, 0, std::max<uint64_t>(n, 1) * 4, st));
+    VDB_CUDA(cudaMemsetAsync(h->d_ulen, 0, slots * 4, st));
+    VDB_CUDA(cudaMemcpyAsync(h->d_uoff, uoff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n) {
+        VDB_CUDA(cudaMemcpyAsync(h->d_level, h_levels, n * 4, cudaMemcpyHostToDevice, st));
+        row_cache(ds, h->d_cache, st);  // push_init :251-254 / init_dist_cache_after_load :371-379
+    }
+    VDB_CUDA(cudaStreamSynchronize(st));
+}
+
+// an index built elsewhere (e.g. a bincode file of the reference, formats.py): links in the reference's layout —
+// links0 [n][2M] + len0 [n]; upper levels concatenated per node ([level_i][M] links, [level_i] lengths)
+vdb_hnsw* hnsw_from_graph(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels,
+                          const uint32_t* links0, const uint32_t* len0, const uint32_t* ulinks, const uint32_t* ulen,
+                          int64_t enter_point, int32_t enter_level) {
     auto h = new vdb_hnsw();
     cudaStream_t st = nullptr;
     try {
         VDB_CUDA(cudaSetDevice(ds->device));
         VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        hnsw_alloc(h, ds, M, ef_construction, h_levels, st);
         const uint64_t n = ds->n;
-        h->device = ds->device;
-        h->n = n;
-        h->dim = ds->dim;
-        h->dtype = ds->dtype;
-        h->metric = ds->metric;
-        h->M = M;
-        h->M0 = 2 * M;
-        h->ef_construction = std::max(ef_construction, 2 * M);  // :504
-        h->h_level.assign(h_levels, h_levels + n);
-        std::vector<uint64_t> uoff(n + 1, 0);
-        for (uint64_t i = 0; i < n; ++i) {
-            VDB_REQUIRE(h_levels[i] < 64, "HNSW: level %u of row %llu is out of range", h_levels[i], (unsigned long long)i);
-            uoff[i + 1] = uoff[i] + h_levels[i];
-        }
-        const uint64_t slots = std::max<uint64_t>(uoff[n], 1);
-        VDB_CUDA(cudaMalloc(&h->d_links0, std::max<uint64_t>(n, 1) * h->M0 * 4));
-        VDB_CUDA(cudaMalloc(&h->d_len0, std::max<uint64_t>(n, 1) * 4));
-        VDB_CUDA(cudaMalloc(&h->d_ulinks, slots * M * 4));
-        VDB_CUDA(cudaMalloc(&h->d_ulen, slots * 4));
-        VDB_CUDA(cudaMalloc(&h->d_uoff, (n + 1) * 8));
-        VDB_CUDA(cudaMalloc(&h->d_level, std::max<uint64_t>(n, 1) * 4));
-        VDB_CUDA(cudaMalloc(&h->d_cache, std::max<uint64_t>(n, 1) * 4));
-        VDB_CUDA(cudaMemsetAsync(h->d_len0, 0, std::max<uint64_t>(n, 1) * 4, st));
-        VDB_CUDA(cudaMemsetAsync(h->d_ulen, 0, slots * 4, st));
-        VDB_CUDA(cudaMemcpyAsync(h->d_uoff, uoff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
         if (n) {
-            VDB_CUDA(cudaMemcpyAsync(h->d_level, h_levels, n * 4, cudaMemcpyHostToDevice, st));
-            row_cache(ds, h->d_cache, st);  // push_init :251-254
+            VDB_REQUIRE(enter_point >= 0 && (uint64_t)enter_point < n && enter_level >= 0 &&
+                            (uint32_t)enter_level == h_levels[enter_point],
+                        "HNSW: enter point %lld / level %d do not match the level table", (long long)enter_point, enter_level);
+            for (uint64_t i = 0; i < n; ++i) {
+                VDB_REQUIRE(len0[i] <= h->M0, "HNSW: links_len[%llu][0] exceeds 2M", (unsigned long long)i);
+                for (uint32_t j = 0; j < len0[i]; ++j)
+                    VDB_REQUIRE(links0[i * h->M0 + j] < n, "HNSW: link of row %llu out of range", (unsigned long long)i);
+            }
+            for (uint64_t s = 0; s < h->slots; ++s) {
+                VDB_REQUIRE(ulen[s] <= M, "HNSW: an upper-level list exceeds M");
+                for (uint32_t j = 0; j < ulen[s]; ++j) VDB_REQUIRE(ulinks[s * M + j] < n, "HNSW: upper link out of range");
+            }
+            VDB_CUDA(cudaMemcpyAsync(h->d_links0, links0, n * h->M0 * 4, cudaMemcpyHostToDevice, st));
+            VDB_CUDA(cudaMemcpyAsync(h->d_len0, len0, n * 4, cudaMemcpyHostToDevice, st));
+            if (h->slots) {
+                VDB_CUDA(cudaMemcpyAsync(h->d_ulinks, ulinks, h->slots * M * 4, cudaMemcpyHostToDevice, st));
+                VDB_CUDA(cudaMemcpyAsync(h->d_ulen, ulen, h->slots * 4, cudaMemcpyHostToDevice, st));
+            }
+            h->enter_point = enter_point;
+            h->enter_level = enter_level;
         }
         VDB_CUDA(cudaStreamSynchronize(st));
+        cudaStreamDestroy(st);
+    } catch (...) {
+        if (st) cudaStreamDestroy(st);
+        hnsw_destroy(h);
+        throw;
+    }
+    return h;
+}
+
+// HNSWIndex::build_on_vec_set (:585-600) over the rows of `ds` in row order. `h_levels[i]` is rand_level (:145-149)
+// of row i, drawn by the caller's RNG in row order like the reference does.
+vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch) {
+    auto h = new vdb_hnsw();
+    cudaStream_t st = nullptr;
+    try {
+        VDB_CUDA(cudaSetDevice(ds->device));
+        VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        hnsw_alloc(h, ds, M, ef_construction, h_levels, st);
+        const uint64_t n = ds->n;
         if (n == 0) {
             cudaStreamDestroy(st);
             return h;
@@ -622,7 +676,6 @@ vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction
         h->enter_level = (int)h_levels[0];
         const uint32_t ef = h->ef_construction;
         const uint32_t dimpad = round_up(ds->pitch, 4u);
-        VDB_REQUIRE(ds->pitch % 4 == 0, "HNSW: row pitch must be a multiple of 4 elements");
         const bool l2 = ds->metric == VDB_L2SQR;
         uint64_t done = 1;
         std::vector<uint32_t> task_node, task_lvl, h_sel, h_selcnt, grp_node, grp_lvl, grp_off, inc;

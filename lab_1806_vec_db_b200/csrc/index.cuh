@@ -59,6 +59,7 @@ struct vdb_hnsw {
     uint32_t* d_ulinks = nullptr;      // other_links: slot (uoff[node] + level - 1) holds M links
     uint32_t* d_ulen = nullptr;        // links_len[.][level >= 1] per slot
     uint64_t* d_uoff = nullptr;        // [n+1] prefix sum of the node levels
+    uint64_t slots = 0;                // sum of the node levels
     uint32_t* d_level = nullptr;       // [n]
     float* d_cache = nullptr;          // dist_cache [n]
     int64_t enter_point = -1;
@@ -70,6 +71,9 @@ namespace vdb {
 // hnsw.cu
 vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch);
 void hnsw_destroy(vdb_hnsw* h);
+vdb_hnsw* hnsw_from_graph(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels,
+                          const uint32_t* links0, const uint32_t* len0, const uint32_t* ulinks, const uint32_t* ulen,
+                          int64_t enter_point, int32_t enter_level);
 void hnsw_knn_keys(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
                    uint64_t* d_keys, cudaStream_t st);
 void hnsw_knn_pq_keys(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,

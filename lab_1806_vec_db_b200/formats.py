@@ -287,6 +287,84 @@ def load_flat_index(data) -> str:
     return DIST_NAME[struct.unpack("<I", data)[0]]
 
 
+# ---- HNSWIndex (hnsw_index.rs:99-141; serde field order = declaration order, dist_cache is #[serde(skip)]) ------------
+class HNSWIndexRecord(NamedTuple):
+    dim: int
+    dist: str
+    max_elements: int
+    m: int
+    max_m0: int
+    ef_construction: int
+    default_ef: int
+    inv_log_m: float
+    start_batch_since: int
+    vec_set: np.ndarray          # [n, dim]; empty when saved with save_without_vec_set (:642-655)
+    level0_links: np.ndarray     # [n * max_m0] u32
+    other_links: list            # per node: [level * m] u32
+    links_len: list              # per node: [level + 1] usize
+    vec_level: np.ndarray        # [n] usize
+    num_deleted: int
+    enter_level: int             # or None
+    enter_point: int             # or None
+
+
+def dump_hnsw_index(t: HNSWIndexRecord, dtype=np.float32) -> bytes:
+    w = _W()
+    w.u64(t.dim); w.u32(DIST_TAG[t.dist]); w.u64(t.max_elements); w.u64(t.m); w.u64(t.max_m0)
+    w.u64(t.ef_construction); w.u64(t.default_ef); w.f32(t.inv_log_m); w.u64(t.start_batch_since)
+    vs = np.asarray(t.vec_set, dtype)
+    w.u64(t.dim)
+    w.array(vs, dtype)
+    w.array(t.level0_links, np.uint32)
+    w.u64(len(t.other_links))
+    for v in t.other_links:
+        w.array(v, np.uint32)
+    w.u64(len(t.links_len))
+    for v in t.links_len:
+        w.array(v, np.uint64)
+    w.array(t.vec_level, np.uint64)
+    w.u64(t.num_deleted); w.opt_u64(t.enter_level); w.opt_u64(t.enter_point)
+    return bytes(w.b)
+
+
+def load_hnsw_index(data, dtype=np.float32) -> HNSWIndexRecord:
+    r = _R(data)
+    dim, dist, max_elements, m, max_m0 = r.u64(), DIST_NAME[r.u32()], r.u64(), r.u64(), r.u64()
+    efc, default_ef, inv_log_m, sbs = r.u64(), r.u64(), r.f32(), r.u64()
+    vdim = r.u64()
+    vdata = r.array(dtype)
+    vs = vdata.reshape(-1, vdim) if vdata.size else np.zeros((0, vdim), dtype)
+    level0 = r.array(np.uint32)
+    other = [r.array(np.uint32) for _ in range(r.u64())]
+    lens = [r.array(np.uint64) for _ in range(r.u64())]
+    vec_level = r.array(np.uint64)
+    num_deleted, enter_level, enter_point = r.u64(), r.opt_u64(), r.opt_u64()
+    r.done()
+    return HNSWIndexRecord(dim, dist, max_elements, m, max_m0, efc, default_ef, inv_log_m, sbs, vs, level0, other, lens,
+                           vec_level, num_deleted, enter_level, enter_point)
+
+
+def hnsw_index_record(index, with_vec_set=False, rows=None) -> HNSWIndexRecord:
+    """Record of a device-resident HNSWIndex (index.py) in the reference's layout."""
+    links0, len0 = index.level0_links()
+    levels, ulinks, ulen = index.upper_links()
+    m = index.config.M
+    other, lens, o = [], [], 0
+    for i, lv in enumerate(levels):
+        lv = int(lv)
+        other.append(ulinks[o * m:(o + lv) * m].copy())
+        lens.append(np.concatenate([[len0[i]], ulen[o:o + lv]]).astype(np.uint64))
+        o += lv
+    ep, el = index.enter_point
+    n = len(levels)
+    dist = "l2sqr" if index.vec_set.metric == 0 else "cosine"
+    return HNSWIndexRecord(index.vec_set.dim, dist, index.config.max_elements, m, 2 * m, index.ef_construction,
+                           index.default_ef, float(np.float32(1.0) / np.log(np.float32(m))), 1000,
+                           (np.asarray(rows) if with_vec_set else np.zeros((0, index.vec_set.dim), index.vec_set.dtype)),
+                           links0.reshape(-1), other, lens, np.asarray(levels, np.uint64), 0,
+                           (el if n else None), (ep if n else None))
+
+
 # ---- bench driver files (examples/bench.rs) --------------------------------------------------------------------------
 def load_bench_config(path) -> dict:
     """BenchConfig (bench.rs:70-92) as a dict; `ef` is expanded like BenchEf (range -> list)."""

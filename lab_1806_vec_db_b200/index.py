@@ -506,6 +506,42 @@ class HNSWIndex:
         L.check(L.lib().vdb_hnsw_links0(self._h, L.ptr(links), L.ptr(lens)))
         return links, lens
 
+    def upper_links(self):
+        """(levels [n], links [sum(levels) * M], lengths [sum(levels)]): other_links / links_len of the reference."""
+        n = len(self.vec_set)
+        levels = np.zeros(n, np.uint32)
+        slots = int(self.levels.sum())
+        ulinks = np.zeros(max(slots, 1) * self.config.M, np.uint32)
+        ulen = np.zeros(max(slots, 1), np.uint32)
+        L.check(L.lib().vdb_hnsw_upper(self._h, L.ptr(levels), L.ptr(ulinks), L.ptr(ulen)))
+        return levels, ulinks[:slots * self.config.M], ulen[:slots]
+
+    @classmethod
+    def from_record(cls, vec_set: DeviceVecSet, rec):
+        """IndexSerdeExternalVecSet::load_with_external_vec_set (hnsw_index.rs:656-668): the graph of a bincode
+        HNSWIndex file (formats.load_hnsw_index) over the rows of `vec_set`."""
+        n = len(vec_set)
+        if len(rec.vec_level) != n or rec.dim != vec_set.dim:
+            raise ValueError("the index file does not describe this vector set")
+        self = cls.__new__(cls)
+        self.vec_set = vec_set
+        self.config = HNSWConfig(rec.max_elements, rec.ef_construction, rec.m)
+        self.levels = np.asarray(rec.vec_level, np.uint32)
+        links0 = np.ascontiguousarray(rec.level0_links, np.uint32).reshape(n, rec.max_m0)
+        len0 = np.array([int(l[0]) for l in rec.links_len], np.uint32) if n else np.zeros(0, np.uint32)
+        ulinks = (np.concatenate([np.asarray(o, np.uint32) for o in rec.other_links]) if n else np.zeros(0, np.uint32))
+        ulen = (np.concatenate([np.asarray(l[1:], np.uint32) for l in rec.links_len]) if n else np.zeros(0, np.uint32))
+        ulinks = np.ascontiguousarray(ulinks if ulinks.size else np.zeros(1, np.uint32), np.uint32)
+        ulen = np.ascontiguousarray(ulen if ulen.size else np.zeros(1, np.uint32), np.uint32)
+        self._h = C.c_void_p()
+        L.check(L.lib().vdb_hnsw_create_from_graph(vec_set._h, rec.m, rec.ef_construction, L.ptr(self.levels), L.ptr(links0),
+                                                   L.ptr(len0), L.ptr(ulinks), L.ptr(ulen),
+                                                   -1 if rec.enter_point is None else rec.enter_point,
+                                                   -1 if rec.enter_level is None else rec.enter_level, C.byref(self._h)))
+        self.ef_construction = rec.ef_construction
+        self.default_ef = rec.default_ef
+        return self
+
     def set_default_ef(self, ef):
         if ef <= 0:
             raise ValueError("The search radius should be positive.")

@@ -814,6 +814,19 @@ int orc_hnsw_links0(const void* handle, int dtype, uint32_t* links0, uint32_t* l
     });
     return 0;
 }
+/* upper levels, per node levels 1..level in order: ulinks [sum(levels)][m], ulen [sum(levels)] */
+int orc_hnsw_upper(const void* handle, int dtype, uint32_t* ulinks, uint32_t* ulen) {
+    D1(dtype, {
+        const auto* h = (const Hnsw<T>*)handle;
+        size_t o = 0;
+        for (size_t i = 0; i < h->n; ++i)
+            for (size_t l = 1; l <= h->vec_level[i]; ++l) {
+                std::copy(h->other[i].begin() + h->m * (l - 1), h->other[i].begin() + h->m * l, ulinks + o * h->m);
+                ulen[o++] = (uint32_t)h->len[i][l];
+            }
+    });
+    return 0;
+}
 void orc_hnsw_free(void* handle, int dtype) {
     D1(dtype, { delete (Hnsw<T>*)handle; });
 }

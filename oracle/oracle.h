@@ -117,6 +117,7 @@ int orc_hnsw_knn(const void* handle, int dtype, const void* queries, size_t nq, 
 int orc_hnsw_knn_pq(const void* handle, int dtype, const void* queries, size_t nq, size_t k, size_t ef, const uint8_t* codes,
                     const void* codebooks, size_t m, size_t n_bits, uint64_t* ids, float* dists, uint32_t* counts, int nthreads);
 int orc_hnsw_links0(const void* handle, int dtype, uint32_t* links0, uint32_t* len0);
+int orc_hnsw_upper(const void* handle, int dtype, uint32_t* ulinks, uint32_t* ulen);
 void orc_hnsw_free(void* handle, int dtype);
 float orc_recall(const uint64_t* gnd, size_t n_gnd, const uint64_t* pred, size_t n_pred);
 

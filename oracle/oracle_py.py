@@ -270,6 +270,7 @@ class HnswOracle:
         self.base = _c(base)
         self.dt = _dt(self.base)
         levels = _c(levels, np.uint32)
+        self.levels = levels
         f = lib().orc_hnsw_build
         f.restype = C.c_void_p
         f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]
@@ -310,6 +311,15 @@ class HnswOracle:
         lens = np.zeros(n, np.uint32)
         lib().orc_hnsw_links0(self.h, self.dt, _p(links), _p(lens))
         return links, lens
+
+    def upper(self):
+        slots = int(self.levels.sum())
+        ul = np.zeros(max(slots, 1) * self.m, np.uint32)
+        un = np.zeros(max(slots, 1), np.uint32)
+        f = lib().orc_hnsw_upper
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        f(self.h, self.dt, _p(ul), _p(un))
+        return ul[:slots * self.m], un[:slots]
 
     def __del__(self):
         try:

@@ -61,3 +61,25 @@ def test_driver_runs_reference_style_configs(tmp_path, fixtures):
     assert by["Flat+PQ"]["recall"][-1] > 0.9          # t_bench_1e4.toml reports 0.99+ for Flat+PQ at ef 100-200
     pq = F.load_pq_table(open(f"{d}/pq.bin", "rb").read())
     assert pq.m == 240 and pq.encoded_vec_set.shape == (1000, 120) and len(pq.group_k_means) == 240
+
+
+def test_driver_runs_hnsw_configs(tmp_path, fixtures):
+    """config/bench_hnsw.toml and config/bench_pq_240_hnsw.toml shapes (HNSW, HNSW + PQ) on the shipped fixture."""
+    from lab_1806_vec_db_b200 import formats as F
+    d = str(tmp_path)
+    F.save_raw(f"{d}/base.bin", fixtures["base"])
+    F.save_raw(f"{d}/test.bin", fixtures["test"][:100])
+    body = "max_elements = 1000\nef_construction = 200\n"
+    open(f"{d}/hnsw.toml", "w").write(CONFIG.format(label="HNSW", d=d, ef0=40, ef1=120, step=40, algo="HNSW", algo_body=body,
+                                                    pq=""))
+    open(f"{d}/hnsw_pq.toml", "w").write(CONFIG.format(label="HNSW+PQ m=240", d=d, ef0=100, ef1=300, step=100, algo="HNSW",
+                                                       algo_body=body, pq=PQ.format(d=d)))
+    for cfg in ("hnsw.toml", "hnsw_pq.toml"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench_driver.py"), f"{d}/{cfg}"], capture_output=True,
+                           text=True, cwd=ROOT, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = F.load_result_list(open(f"{d}/bench.toml").read())
+    by = {r["label"]: r for r in res["results"]}
+    assert by["HNSW"]["ef"] == [40, 80, 120] and by["HNSW+PQ m=240"]["ef"] == [100, 200, 300]
+    assert by["HNSW"]["recall"][-1] >= 0.99          # the reference's 10k-row HNSW reaches 0.9927 at ef = 120
+    assert by["HNSW+PQ m=240"]["recall"][-1] >= 0.97

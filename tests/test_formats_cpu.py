@@ -99,3 +99,33 @@ def test_reference_files_parse():
     again = F.load_result_list(text)
     assert again["title"] == res["title"] and again["results"][0]["ef"] == res["results"][0]["ef"]
     assert np.allclose(again["results"][2]["search_time"], res["results"][2]["search_time"])
+
+
+def test_hnsw_index_bincode_layout_known_answer():
+    """HNSWIndex serde (hnsw_index.rs:99-141): field order of the struct, usize -> u64, Option tag u8, Vec = u64 len +
+    items, dist_cache skipped; byte-level check of a 2-node graph and a round trip."""
+    import struct
+    from lab_1806_vec_db_b200 import formats as F
+    rec = F.HNSWIndexRecord(dim=3, dist="cosine", max_elements=2, m=2, max_m0=4, ef_construction=4, default_ef=2,
+                            inv_log_m=1.4426950216293335, start_batch_since=1000,
+                            vec_set=np.zeros((0, 3), np.float32),
+                            level0_links=np.array([1, 0, 0, 0, 0, 0, 0, 0], np.uint32),
+                            other_links=[np.array([1, 0], np.uint32), np.zeros(0, np.uint32)],
+                            links_len=[np.array([1, 0], np.uint64), np.array([1], np.uint64)],
+                            vec_level=np.array([1, 0], np.uint64), num_deleted=0, enter_level=1, enter_point=0)
+    data = F.dump_hnsw_index(rec)
+    head = struct.pack("<QIQQQQQfQ", 3, 1, 2, 2, 4, 4, 2, 1.4426950216293335, 1000)   # HNSWInnerConfig, Cosine = tag 1
+    assert data[:len(head)] == head
+    o = len(head)
+    assert data[o:o + 16] == struct.pack("<QQ", 3, 0)                                   # VecSet {dim, data: []}
+    o += 16
+    assert data[o:o + 8] == struct.pack("<Q", 8) and data[o + 8:o + 12] == struct.pack("<I", 1)
+    tail = struct.pack("<Q", 0) + b"\x01" + struct.pack("<Q", 1) + b"\x01" + struct.pack("<Q", 0)
+    assert data.endswith(tail)                                                          # num_deleted, Some(1), Some(0)
+    back = F.load_hnsw_index(data)
+    assert back.dist == "cosine" and back.m == 2 and back.enter_level == 1 and back.enter_point == 0
+    assert (back.level0_links == rec.level0_links).all() and (back.vec_level == rec.vec_level).all()
+    assert [a.tolist() for a in back.other_links] == [[1, 0], []]
+    assert [a.tolist() for a in back.links_len] == [[1, 0], [1]]
+    empty = F.load_hnsw_index(F.dump_hnsw_index(rec._replace(enter_level=None, enter_point=None)))
+    assert empty.enter_level is None and empty.enter_point is None

@@ -167,3 +167,43 @@ def test_hnsw_knn_pq_vs_oracle(V, fixtures, oracle, metric):
             assert close(dd[qi], want, RTOL, 2e-6).all()
     one = idx.knn_pq(test[2], 10, 100, pq)
     assert [p.index for p in one] == idx.knn_pq_batch(test, 10, 100, pq)[0][2].tolist()
+
+
+def test_hnsw_bincode_round_trip_and_oracle_graph_import(V, fixtures, oracle):
+    """The device graph is written in the reference's bincode HNSWIndex layout (save_without_vec_set, :642-655), read
+    back and re-created over the same rows (load_with_external_vec_set, :656-668): identical search results. A graph
+    built by the CPU restatement is imported the same way and searched on the device: ids equal the CPU search."""
+    from lab_1806_vec_db_b200 import formats as F
+    from oracle.oracle_py import HnswOracle
+    base, test = fixtures["base"][:700], fixtures["test"][:64]
+    M, efc = 8, 60
+    levels = V.hnsw_rand_levels(len(base), M, np.random.default_rng(21))
+    vs = V.DeviceVecSet(base, "l2sqr")
+    idx = V.HNSWIndex(vs, V.HNSWConfig(len(base), efc, M), levels=levels)
+    rec = F.hnsw_index_record(idx)
+    blob = F.dump_hnsw_index(rec)
+    back = F.load_hnsw_index(blob)
+    assert back.m == M and back.max_m0 == 2 * M and back.ef_construction == efc and back.vec_set.shape == (0, 960)
+    assert (back.vec_level == levels).all() and [len(o) for o in back.other_links] == (levels * M).tolist()
+    idx2 = V.HNSWIndex.from_record(vs, back)
+    a, b = idx.knn_with_ef_batch(test, 10, 50), idx2.knn_with_ef_batch(test, 10, 50)
+    assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all()
+    # CPU-built graph -> record -> device
+    ref = HnswOracle(base, "l2sqr", M, efc, levels)
+    l0, n0 = ref.links0()
+    ul, un = ref.upper()
+    lens, other, o = [], [], 0
+    for i, lv in enumerate(levels):
+        lv = int(lv)
+        other.append(ul[o * M:(o + lv) * M])
+        lens.append(np.concatenate([[n0[i]], un[o:o + lv]]).astype(np.uint64))
+        o += lv
+    top = int(levels.max())
+    rec2 = back._replace(level0_links=l0.reshape(-1), other_links=other, links_len=lens,
+                         enter_level=top, enter_point=int(np.argmax(levels == top)))
+    idx3 = V.HNSWIndex.from_record(vs, F.load_hnsw_index(F.dump_hnsw_index(rec2)))
+    got = idx3.knn_with_ef_batch(test, 10, 50)[0]
+    want = ref.knn(test, 10, 50, nthreads=8)[0]
+    assert (got == want).mean() >= 0.995       # same graph, same algorithm; only fp summation order differs
+    with pytest.raises(V.VdbError):
+        V.HNSWIndex.from_record(vs, rec2._replace(level0_links=np.full_like(rec2.level0_links, 5000)))
