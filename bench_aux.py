@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--hnsw-m", type=int, default=16)
     ap.add_argument("--hnsw-efc", type=int, default=200)
     ap.add_argument("--hnsw-ef", default="120:360:40", help="start:end:step of the HNSW ef sweep")
+    ap.add_argument("--hnsw-cpu", action="store_true", help="also build / search the CPU restatement (small n only)")
+    ap.add_argument("--hnsw-pq", action="store_true", help="also HNSW + PQ (config/bench_pq_240_hnsw.toml): knn_pq on the graph")
     ap.add_argument("--cpu-queries", type=int, default=8)
     ap.add_argument("--pq-m", type=int, default=240)
     ap.add_argument("--ef", default="240:600:60", help="start:end:step of the PQ ef sweep")
@@ -124,7 +126,7 @@ def main():
                               "achieved_gbs": gbs, "hbm_frac_of_6551": gbs / 6551.4, "cpu_qps": cpu_qps,
                               "cpu_cores": cores, "cpu_queries": nc, "gpu_vs_oracle_exact_id_rate": same}), flush=True)
 
-    if "pq" in args.what:
+    def build_pq():
         t0 = time.perf_counter()
         M = args.pq_m
         cfg = V.PQConfig(4, M, "l2sqr", min(10_000, args.n), 20, 1e-6)
@@ -139,7 +141,10 @@ def main():
         t_train = time.perf_counter() - t0
         t0 = time.perf_counter()
         pq = V.PQTable(vs, cfg, books)
-        t_encode = time.perf_counter() - t0
+        return M, books, pq, t_train, time.perf_counter() - t0
+
+    if "pq" in args.what:
+        M, books, pq, t_train, t_encode = build_pq()
         ns = 2000
         t0 = time.perf_counter()
         c_cpu = O.pq_encode(base_host[:ns], books, M, 4, "l2sqr", nthreads=1)  # the reference encodes serially
@@ -188,9 +193,22 @@ def main():
                           "gpu_build_s": t_build, "inserts_per_s": args.n / t_build, "kernels": kern,
                           "level0_degree_mean": float(lens.mean()), "level0_degree_max": int(lens.max()),
                           "enter": hn.enter_point, "max_batch": V.HNSWIndex.MAX_BATCH}), flush=True)
+        ref = None
+        if args.hnsw_cpu:
+            from oracle.oracle_py import HnswOracle
+            t0 = time.perf_counter()
+            ref = HnswOracle(base_host, "l2sqr", args.hnsw_m, args.hnsw_efc, hn.levels)   # same levels, one thread
+            print(json.dumps({"config": "C5 HNSW build (CPU restatement, 1 thread)", "n": args.n,
+                              "cpu_build_s": time.perf_counter() - t0}), flush=True)
         e0, e1, es = (int(x) for x in args.hnsw_ef.split(":"))
         for ef in range(e0, e1 + 1, es):
             ids, dd, cnt = dev_out()
+            if ref is not None:
+                t0 = time.perf_counter()
+                oi, _, _ = ref.knn(q_host, k, ef, nthreads=cores)
+                cpu_s = time.perf_counter() - t0
+                print(json.dumps({"config": "C5 HNSW search (CPU restatement)", "ef": ef, "cpu_qps": args.nq / cpu_s,
+                                  "cpu_cores": cores, "recall@10": recall_at(oi.astype(np.int64), gt_ids)}), flush=True)
 
             def run():
                 L.check(lib.vdb_hnsw_knn_dev(vs._h, hn._h, C.c_void_p(q_dev.data_ptr()), args.nq, k, ef,
@@ -200,6 +218,20 @@ def main():
             rec = recall_at(ids.cpu().numpy(), gt_ids)
             print(json.dumps({"config": "C5 HNSW search", "ef": ef, "k": k, "nq": args.nq, "qps": args.nq / ms * 1e3,
                               "ms_per_batch": ms, "recall@10": rec}), flush=True)
+        if args.hnsw_pq:
+            M, books, pq, t_train, t_encode = build_pq()
+            e0, e1, es = (int(x) for x in args.ef.split(":"))
+            for ef in range(e0, e1 + 1, es):
+                ids, dd, cnt = dev_out()
+
+                def run():
+                    L.check(lib.vdb_hnsw_knn_pq_dev(vs._h, hn._h, pq._h, C.c_void_p(q_dev.data_ptr()), args.nq, k, ef,
+                                                    C.c_void_p(ids.data_ptr()), C.c_void_p(dd.data_ptr()),
+                                                    C.c_void_p(cnt.data_ptr()), st))
+                ms, _ = timed(run)
+                rec = recall_at(ids.cpu().numpy(), gt_ids)
+                print(json.dumps({"config": "C5 HNSW+PQ search", "m": M, "ef": ef, "k": k, "nq": args.nq,
+                                  "qps": args.nq / ms * 1e3, "ms_per_batch": ms, "recall@10": rec}), flush=True)
 
 
 if __name__ == "__main__":

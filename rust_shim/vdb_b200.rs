@@ -15,6 +15,7 @@ use crate::{
 #[repr(C)] pub struct vdb_dataset { _p: [u8; 0] }
 #[repr(C)] pub struct vdb_pq { _p: [u8; 0] }
 #[repr(C)] pub struct vdb_ivf { _p: [u8; 0] }
+#[repr(C)] pub struct vdb_hnsw { _p: [u8; 0] }
 
 extern "C" {
     pub fn vdb_last_error() -> *const c_char;
@@ -44,6 +45,18 @@ extern "C" {
     pub fn vdb_ivf_destroy(ivf: *mut vdb_ivf) -> c_int;
     pub fn vdb_ivf_knn(ds: *const vdb_dataset, ivf: *const vdb_ivf, queries: *const c_void, nq: u32, k: u32,
                        n_probes: u32, ids: *mut u64, dist: *mut f32, counts: *mut u32) -> c_int;
+    pub fn vdb_hnsw_build(ds: *const vdb_dataset, m: u32, ef_construction: u32, levels: *const u32, max_batch: u32,
+                          out: *mut *mut vdb_hnsw) -> c_int;
+    pub fn vdb_hnsw_destroy(h: *mut vdb_hnsw) -> c_int;
+    pub fn vdb_hnsw_knn(ds: *const vdb_dataset, h: *const vdb_hnsw, queries: *const c_void, nq: u32, k: u32, ef: u32,
+                        ids: *mut u64, dist: *mut f32, counts: *mut u32) -> c_int;
+    pub fn vdb_hnsw_knn_pq(ds: *const vdb_dataset, h: *const vdb_hnsw, pq: *const vdb_pq, queries: *const c_void, nq: u32,
+                           k: u32, ef: u32, ids: *mut u64, dist: *mut f32, counts: *mut u32) -> c_int;
+    pub fn vdb_hnsw_links0(h: *const vdb_hnsw, links0: *mut u32, len0: *mut u32) -> c_int;
+    pub fn vdb_hnsw_upper(h: *const vdb_hnsw, levels: *mut u32, ulinks: *mut u32, ulen: *mut u32) -> c_int;
+    pub fn vdb_hnsw_create_from_graph(ds: *const vdb_dataset, m: u32, ef_construction: u32, levels: *const u32,
+                                      links0: *const u32, len0: *const u32, ulinks: *const u32, ulen: *const u32,
+                                      enter_point: i64, enter_level: i32, out: *mut *mut vdb_hnsw) -> c_int;
     pub fn vdb_gather_dist(ds: *const vdb_dataset, queries: *const c_void, nq: u32, cand_ids: *const u32,
                            cand_off: *const u64, out: *mut f32) -> c_int;
     pub fn vdb_row_cache(ds: *const vdb_dataset, out: *mut f32) -> c_int;
