@@ -28,7 +28,7 @@
 
 namespace vdb {
 
-constexpr int HN_THREADS = 128;
+constexpr int HN_THREADS = 256;
 constexpr uint32_t HN_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t HN_MAX_M0 = 64;  // M <= 32
 
