@@ -319,6 +319,31 @@ class ShardedPQFlatIndex:
         return _gather_merge_decode(keys, nq, k, self.world, st)
 
 
+class ReplicatedHNSWIndex:
+    """HNSW does not shard (one walk depends on the previous hop): every rank holds the full
+    vectors and graph, the query batch is split across the ranks and the results are all-gathered."""
+
+    def __init__(self, hnsw_index, rank=0, world=1):
+        self.hnsw, self.rank, self.world = hnsw_index, rank, world
+
+    def knn_with_ef_batch_dev(self, q, k, ef):
+        import torch
+        nq, dev = q.shape[0], q.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        lib = L.lib()
+        per = -(-nq // self.world)
+        lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+        ids = torch.full((per, k), -1, dtype=torch.int64, device=dev)
+        dd = torch.full((per, k), float("nan"), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((per,), dtype=torch.int32, device=dev)
+        if hi > lo:
+            mine = q[lo:hi].contiguous()
+            L.check(lib.vdb_hnsw_knn_dev(self.hnsw.vec_set._h, self.hnsw._h, C.c_void_p(mine.data_ptr()), hi - lo, k, ef,
+                                         C.c_void_p(ids.data_ptr()), C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), st))
+        return (_gather(ids, self.world).reshape(-1, k)[:nq], _gather(dd, self.world).reshape(-1, k)[:nq],
+                _gather(cnt, self.world).reshape(-1)[:nq])
+
+
 def _gather(t, world):
     import torch
     if world == 1:

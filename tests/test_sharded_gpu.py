@@ -64,6 +64,18 @@ for k, ef in ((10, 240), (10, 5), (3, 600)):
     ids, dd, cnt = spq.knn_pq_batch_dev(qd[:32].contiguous(), k, ef)
     assert (ids.cpu().numpy() == want[0].astype(np.int64)).all(), ("pq", k, ef, rank)
     assert (dd.cpu().numpy().view(np.uint32) == want[1].view(np.uint32)).all()
+# ---- HNSW: replicas only, the query batch is split across the ranks ----
+from lab_1806_vec_db_b200.sharded import ReplicatedHNSWIndex
+sub = np.ascontiguousarray(base[:20000])
+hn = V.HNSWIndex(V.DeviceVecSet(sub, "l2sqr"), V.HNSWConfig(0, 100, 12), levels=V.hnsw_rand_levels(20000, 12, np.random.default_rng(2)))
+want = hn.knn_with_ef_batch(q[:101], 10, 64)
+ids, dd, cnt = ReplicatedHNSWIndex(hn, rank, world).knn_with_ef_batch_dev(qd[:101].contiguous(), 10, 64)
+exact = V.FlatIndex.from_vec_set(sub, "l2sqr").knn_batch(q[:101], 10)[0].astype(np.int64)
+got = ids.cpu().numpy()
+assert got.shape == (101, 10) and (cnt.cpu().numpy() == 10).all()
+lo_q, hi_q = rank * 51, min(101, rank * 51 + 51)     # this rank's slice was searched on this rank's replica
+assert (got[lo_q:hi_q] == want[0][lo_q:hi_q].astype(np.int64)).all()
+assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(got.tolist(), exact.tolist())]) >= 0.9   # every rank's part is a real search
 pin = torch.from_numpy(q).pin_memory()
 out = idx.knn_batch(pin, 10)
 assert (out[0].numpy() == full.knn_batch(q, 10)[0].astype(np.int64)).all()
