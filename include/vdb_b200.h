@@ -242,6 +242,11 @@ int vdb_ivf_knn_keys_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* 
 int vdb_hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* levels,
                    uint32_t max_batch, vdb_hnsw** out);
 int vdb_hnsw_destroy(vdb_hnsw* h);
+/* IndexBuilder::add / batch_add on a built index (:538-575; DynamicIndex::HNSW add, src/database/dynamic_index.rs:44-55):
+ * inserts the rows appended to `ds` since the build (vdb_dataset_append), rows [n_index, n_ds), with new_levels[i] =
+ * rand_level of row n_index + i. Same batch pipeline as the build. Not re-entrant with searches on the same handle
+ * (the reference holds the table's write lock here, database/mod.rs:217). */
+int vdb_hnsw_append(vdb_hnsw* h, const vdb_dataset* ds, const uint32_t* new_levels, uint32_t max_batch);
 /* n, M, effective ef_construction, enter_point (-1 when empty), enter_level. Any pointer may be NULL. */
 int vdb_hnsw_info(const vdb_hnsw* h, uint64_t* n, uint32_t* M, uint32_t* ef_construction, int64_t* enter_point,
                   int32_t* enter_level);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "vdb_ivf_destroy": (i32, [vp]),
     "vdb_hnsw_build": (i32, [vp, u32, u32, vp, u32, vp]),
     "vdb_hnsw_destroy": (i32, [vp]),
+    "vdb_hnsw_append": (i32, [vp, vp, vp, u32]),
     "vdb_hnsw_info": (i32, [vp, vp, vp, vp, vp, vp]),
     "vdb_hnsw_links0": (i32, [vp, vp, vp]),
     "vdb_hnsw_upper": (i32, [vp, vp, vp, vp]),

@@ -658,26 +658,22 @@ vdb_hnsw* hnsw_from_graph(const vdb_dataset* ds, uint32_t M, uint32_t ef_constru
     return h;
 }
 
-// HNSWIndex::build_on_vec_set (:585-600) over the rows of `ds` in row order. `h_levels[i]` is rand_level (:145-149)
-// of row i, drawn by the caller's RNG in row order like the reference does.
-vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch) {
-    auto h = new vdb_hnsw();
-    cudaStream_t st = nullptr;
-    try {
-        VDB_CUDA(cudaSetDevice(ds->device));
-        VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        hnsw_alloc(h, ds, M, ef_construction, h_levels, st);
-        const uint64_t n = ds->n;
-        if (n == 0) {
-            cudaStreamDestroy(st);
-            return h;
+// inserts rows [first, n) of `ds` into the graph, batch by batch (inner_batch_add :459-476 / add_parallel :399-457)
+static void hnsw_insert_range(vdb_hnsw* h, const vdb_dataset* ds, uint64_t first, uint32_t max_batch, cudaStream_t st) {
+    const uint64_t n = ds->n;
+    const uint32_t M = h->M;
+    const uint32_t* h_levels = h->h_level.data();
+    if (n == 0) return;
+    {
+        uint64_t done = first;
+        if (done == 0) {  // the first vector becomes the enter point (:543-551)
+            h->enter_point = 0;
+            h->enter_level = (int)h_levels[0];
+            done = 1;
         }
-        h->enter_point = 0;
-        h->enter_level = (int)h_levels[0];
         const uint32_t ef = h->ef_construction;
         const uint32_t dimpad = round_up(ds->pitch, 4u);
         const bool l2 = ds->metric == VDB_L2SQR;
-        uint64_t done = 1;
         std::vector<uint32_t> task_node, task_lvl, h_sel, h_selcnt, grp_node, grp_lvl, grp_off, inc;
         std::vector<uint64_t> out_off;
         while (done < n) {
@@ -806,6 +802,19 @@ vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction
             done += b;
         }
         VDB_CUDA(cudaStreamSynchronize(st));
+    }
+}
+
+// HNSWIndex::build_on_vec_set (:585-600) over the rows of `ds` in row order. `h_levels[i]` is rand_level (:145-149)
+// of row i, drawn by the caller's RNG in row order like the reference does.
+vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch) {
+    auto h = new vdb_hnsw();
+    cudaStream_t st = nullptr;
+    try {
+        VDB_CUDA(cudaSetDevice(ds->device));
+        VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        hnsw_alloc(h, ds, M, ef_construction, h_levels, st);
+        hnsw_insert_range(h, ds, 0, max_batch, st);
         cudaStreamDestroy(st);
     } catch (...) {
         if (st) cudaStreamDestroy(st);
@@ -813,6 +822,51 @@ vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction
         throw;
     }
     return h;
+}
+
+// IndexBuilder::batch_add on an existing index (:573-575; DynamicIndex::HNSW add, dynamic_index.rs:44-55): the rows
+// appended to `ds` since the index was built (rows [h->n, ds->n)) are inserted with the levels given for them.
+void hnsw_append(vdb_hnsw* h, const vdb_dataset* ds, const uint32_t* new_levels, uint32_t max_batch) {
+    VDB_REQUIRE(ds->n >= h->n && ds->dim == h->dim && ds->dtype == h->dtype && ds->metric == h->metric,
+                "HNSW index was built for a different vector set");
+    if (ds->n == h->n) return;
+    cudaStream_t st = nullptr;
+    VDB_CUDA(cudaSetDevice(ds->device));
+    VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    vdb_hnsw old = *h;  // device arrays of the old graph; the handle is re-pointed to larger ones below
+    try {
+        const uint64_t n0 = h->n, n = ds->n;
+        std::vector<uint32_t> levels = h->h_level;
+        levels.insert(levels.end(), new_levels, new_levels + (n - n0));
+        h->d_links0 = h->d_len0 = h->d_ulinks = h->d_ulen = h->d_level = nullptr;
+        h->d_uoff = nullptr;
+        h->d_cache = nullptr;
+        const uint64_t old_slots = old.slots;
+        hnsw_alloc(h, ds, old.M, old.ef_construction, levels.data(), st);
+        // nodes keep their ids and the upper-level slots of old nodes keep their positions (prefix sums only grow)
+        if (n0) {
+            VDB_CUDA(cudaMemcpyAsync(h->d_links0, old.d_links0, n0 * h->M0 * 4, cudaMemcpyDeviceToDevice, st));
+            VDB_CUDA(cudaMemcpyAsync(h->d_len0, old.d_len0, n0 * 4, cudaMemcpyDeviceToDevice, st));
+            if (old_slots) {
+                VDB_CUDA(cudaMemcpyAsync(h->d_ulinks, old.d_ulinks, old_slots * h->M * 4, cudaMemcpyDeviceToDevice, st));
+                VDB_CUDA(cudaMemcpyAsync(h->d_ulen, old.d_ulen, old_slots * 4, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        VDB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(old.d_links0);
+        cudaFree(old.d_len0);
+        cudaFree(old.d_ulinks);
+        cudaFree(old.d_ulen);
+        cudaFree(old.d_uoff);
+        cudaFree(old.d_level);
+        cudaFree(old.d_cache);
+        old.d_links0 = nullptr;
+        hnsw_insert_range(h, ds, n0, max_batch, st);
+        cudaStreamDestroy(st);
+    } catch (...) {
+        cudaStreamDestroy(st);
+        throw;
+    }
 }
 
 // the k best by (cached-form distance, id) of the first `take` entries of every [ef] candidate list

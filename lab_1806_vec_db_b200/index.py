@@ -489,6 +489,20 @@ class HNSWIndex:
 
     from_vec_set = build_on_vec_set
 
+    def batch_add_pushed(self, rng=None, levels=None):
+        """IndexBuilder::batch_add (hnsw_index.rs:573-575) for the rows pushed to `vec_set` since the last build / add:
+        they are inserted into the existing graph with the same batch pipeline as the build."""
+        n_old, n = len(self.levels), len(self.vec_set)
+        if n == n_old:
+            return
+        rng = rng if rng is not None else np.random.default_rng()
+        new = (np.ascontiguousarray(levels, dtype=np.uint32) if levels is not None
+               else hnsw_rand_levels(n - n_old, self.config.M, rng))
+        if new.shape != (n - n_old,):
+            raise ValueError("one level per new row is required")
+        L.check(L.lib().vdb_hnsw_append(self._h, self.vec_set._h, L.ptr(new), self.MAX_BATCH))
+        self.levels = np.concatenate([self.levels, new])
+
     def __len__(self):
         return len(self.vec_set)
 

@@ -3,10 +3,9 @@
 names/arguments (src/pyo3/mod.rs, lab_1806_vec_db.pyi) so `VecDB.search / build_pq_table / build_hnsw_index` callers
 can switch without code changes. Storage, locking and autosave are out of scope: tables live in memory.
 
-`build_hnsw_index` builds the graph on the device (hnsw.cu) and the search policy follows DynamicIndex
-(src/database/dynamic_index.rs:63-93). Deviation: the reference inserts vectors added AFTER the build into the existing
-graph one by one (dynamic_index.rs:44-55); here an add marks the graph stale and the next search rebuilds it in one
-batched pass (the device build of 1M x 960 takes ~13 s), so searches always see every vector.
+`build_hnsw_index` builds the graph on the device (hnsw.cu), the search policy follows DynamicIndex
+(src/database/dynamic_index.rs:63-93) and vectors added after the build are inserted into the existing graph
+(DynamicIndex::HNSW add / batch_add, dynamic_index.rs:44-55) with the same batched pipeline as the build.
 """
 import numpy as np
 
@@ -28,7 +27,6 @@ class MetadataVecTable:
         self.pq_table = None
         self._hnsw = None                                     # HNSWIndex, or None (DynamicIndex::Flat)
         self._hnsw_efc = None
-        self._hnsw_stale = False
         self.rng = rng if rng is not None else np.random.default_rng()  # from_entropy, metadata_vec_table.rs:18
 
     def __len__(self):
@@ -61,8 +59,8 @@ class MetadataVecTable:
         self.rows = np.concatenate([self.rows, new])
         if self.vec_set is not None:
             self.vec_set.push(new)                             # VecSet::push on the mirror
-        if self._hnsw is not None:
-            self._hnsw_stale = True                            # DynamicIndex::HNSW add (:44-55): see the module note
+            if self._hnsw is not None:
+                self._hnsw.batch_add_pushed(self.rng)          # DynamicIndex::HNSW batch_add (dynamic_index.rs:50-55)
 
     def delete(self, pattern):
         self.clear_hnsw_index()                                # :170
@@ -91,13 +89,11 @@ class MetadataVecTable:
         if self._hnsw is not None:
             self._hnsw.close()
         self._hnsw = HNSWIndex(self._mirror(), cfg, self.rng)
-        self._hnsw_stale = False
 
     def clear_hnsw_index(self):
         if self._hnsw is not None:
             self._hnsw.close()
         self._hnsw = None
-        self._hnsw_stale = False
 
     def has_hnsw_index(self):
         return self._hnsw is not None
@@ -137,8 +133,6 @@ class MetadataVecTable:
         if q.size != self.dim_:
             raise ValueError("The dimension of the query doesn't match.")
         if self._hnsw is not None:
-            if self._hnsw_stale:
-                self._build_hnsw()
             inner = self._hnsw
         else:
             inner = FlatIndex(self._mirror())

@@ -48,6 +48,7 @@ extern "C" {
     pub fn vdb_hnsw_build(ds: *const vdb_dataset, m: u32, ef_construction: u32, levels: *const u32, max_batch: u32,
                           out: *mut *mut vdb_hnsw) -> c_int;
     pub fn vdb_hnsw_destroy(h: *mut vdb_hnsw) -> c_int;
+    pub fn vdb_hnsw_append(h: *mut vdb_hnsw, ds: *const vdb_dataset, new_levels: *const u32, max_batch: u32) -> c_int;
     pub fn vdb_hnsw_knn(ds: *const vdb_dataset, h: *const vdb_hnsw, queries: *const c_void, nq: u32, k: u32, ef: u32,
                         ids: *mut u64, dist: *mut f32, counts: *mut u32) -> c_int;
     pub fn vdb_hnsw_knn_pq(ds: *const vdb_dataset, h: *const vdb_hnsw, pq: *const vdb_pq, queries: *const c_void, nq: u32,

@@ -207,3 +207,40 @@ def test_hnsw_bincode_round_trip_and_oracle_graph_import(V, fixtures, oracle):
     assert (got == want).mean() >= 0.995       # same graph, same algorithm; only fp summation order differs
     with pytest.raises(V.VdbError):
         V.HNSWIndex.from_record(vs, rec2._replace(level0_links=np.full_like(rec2.level0_links, 5000)))
+
+
+def test_hnsw_incremental_add_matches_one_shot_build(V, fixtures, oracle):
+    """IndexBuilder::batch_add on a built index: rows pushed after the build are inserted into the existing graph.
+    With the same levels the result is the graph of a one-shot build whose batches end at the same row (same batch
+    pipeline), so build(600) + add(400) with max_batch 1 equals build(1000) with max_batch 1; recall stays at the
+    one-shot level for batched adds."""
+    base, test = fixtures["base"], fixtures["test"][:100]
+    M, efc = 8, 60
+    levels = V.hnsw_rand_levels(1000, M, np.random.default_rng(4))
+    old = V.HNSWIndex.MAX_BATCH
+    try:
+        V.HNSWIndex.MAX_BATCH = 1
+        one = V.HNSWIndex(V.DeviceVecSet(base, "l2sqr"), V.HNSWConfig(0, efc, M), levels=levels)
+        vs = V.DeviceVecSet(base[:600], "l2sqr")
+        inc = V.HNSWIndex(vs, V.HNSWConfig(0, efc, M), levels=levels[:600])
+        vs.push(base[600:])
+        inc.batch_add_pushed(levels=levels[600:])
+    finally:
+        V.HNSWIndex.MAX_BATCH = old
+    a, b = one.level0_links(), inc.level0_links()
+    assert (a[1] == b[1]).all() and (a[0] == b[0]).all()
+    assert one.enter_point == inc.enter_point
+    la, lb = one.upper_links(), inc.upper_links()
+    assert all((x == y).all() for x, y in zip(la, lb))
+    # batched add (default batch size), searched
+    vs2 = V.DeviceVecSet(base[:300], "l2sqr")
+    idx = V.HNSWIndex(vs2, V.HNSWConfig(0, 200, 16), rng=np.random.default_rng(1))
+    for lo in (300, 301, 650):
+        hi = {300: 301, 301: 650, 650: 1000}[lo]
+        vs2.push(base[lo:hi])
+        idx.batch_add_pushed(np.random.default_rng(lo))
+    assert len(idx) == 1000
+    gt = oracle.flat_knn(base, test, 10, "l2sqr", nthreads=8)[0]
+    assert recall(idx.knn_with_ef_batch(test, 10, 100)[0], gt) >= 0.99
+    links, lens = idx.level0_links()
+    check_graph(links, lens, 1000, 16)
