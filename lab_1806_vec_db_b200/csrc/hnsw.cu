@@ -20,7 +20,7 @@
 // The graph itself is unpinned in the reference (RNG levels, thread count dependent batches), so parity is by
 // recall; the distances returned by a search are re-evaluated by the cached-form pair kernel (pairs.cu, K10).
 #include <algorithm>
-#include <map>
+#include <utility>
 #include <vector>
 
 #include "index.cuh"
@@ -676,6 +676,7 @@ static void hnsw_insert_range(vdb_hnsw* h, const vdb_dataset* ds, uint64_t first
         const bool l2 = ds->metric == VDB_L2SQR;
         std::vector<uint32_t> task_node, task_lvl, h_sel, h_selcnt, grp_node, grp_lvl, grp_off, inc;
         std::vector<uint64_t> out_off;
+        std::vector<std::pair<uint64_t, uint32_t>> back;
         while (done < n) {
             // batch size: the reference's min(threads * 4, n / M) with the thread term replaced by the grid capacity
             uint32_t b = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, done / M), max_batch);
@@ -749,21 +750,27 @@ static void hnsw_insert_range(vdb_hnsw* h, const vdb_dataset* ds, uint64_t first
             VDB_CUDA(cudaMemcpyAsync(h_sel.data(), d_sel.p, (size_t)ntasks * M * 4, cudaMemcpyDeviceToHost, st));
             VDB_CUDA(cudaMemcpyAsync(h_selcnt.data(), d_selcnt.p, (size_t)ntasks * 4, cudaMemcpyDeviceToHost, st));
             VDB_CUDA(cudaStreamSynchronize(st));
-            std::map<uint64_t, std::vector<uint32_t>> groups;  // (level << 32 | target) -> sources in batch order
+            // (level << 32 | target, source): a stable sort by key keeps the sources of a target in batch order
+            back.clear();
             for (uint32_t t = 0; t < ntasks; ++t)
                 for (uint32_t j = 0; j < h_selcnt[t]; ++j)
-                    groups[((uint64_t)task_lvl[t] << 32) | h_sel[(size_t)t * M + j]].push_back(task_node[t]);
-            if (!groups.empty()) {
+                    back.emplace_back(((uint64_t)task_lvl[t] << 32) | h_sel[(size_t)t * M + j], task_node[t]);
+            std::stable_sort(back.begin(), back.end(),
+                             [](const std::pair<uint64_t, uint32_t>& a, const std::pair<uint64_t, uint32_t>& b) { return a.first < b.first; });
+            if (!back.empty()) {
                 grp_node.clear();
                 grp_lvl.clear();
-                grp_off.assign(1, 0);
+                grp_off.clear();
                 inc.clear();
-                for (auto& kv : groups) {
-                    grp_node.push_back((uint32_t)kv.first);
-                    grp_lvl.push_back((uint32_t)(kv.first >> 32));
-                    inc.insert(inc.end(), kv.second.begin(), kv.second.end());
-                    grp_off.push_back((uint32_t)inc.size());
+                for (size_t e = 0; e < back.size(); ++e) {
+                    if (e == 0 || back[e].first != back[e - 1].first) {
+                        grp_node.push_back((uint32_t)back[e].first);
+                        grp_lvl.push_back((uint32_t)(back[e].first >> 32));
+                        grp_off.push_back((uint32_t)e);
+                    }
+                    inc.push_back(back[e].second);
                 }
+                grp_off.push_back((uint32_t)back.size());
                 const uint32_t ng = (uint32_t)grp_node.size();
                 DevBuf d_gn((size_t)ng * 4, st), d_gl((size_t)ng * 4, st), d_go((size_t)(ng + 1) * 4, st), d_inc(inc.size() * 4, st);
                 VDB_CUDA(cudaMemcpyAsync(d_gn.p, grp_node.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, st));
