@@ -134,6 +134,16 @@ int vdb_kmeans_pp_init_ds(const vdb_dataset* ds, uint32_t k, uint32_t sel_lo, ui
 int vdb_kmeans_pp_weights(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
                           const void* centroid, uint32_t sel_lo, uint32_t sel_hi, float* weights);
 
+/* The per-group k-means of PQTable::from_vec_set (src/distance/pq_table.rs:154-172) for ALL m groups at once on the
+ * training sample `train` (device resident): k = 2^n_bits centroids per group, k-means++ (k_means.rs:61-87) driven by
+ * the caller's draws - uniforms[g * (2k - 1) + ...] laid out per group as in vdb_kmeans_pp_init_ds - then Lloyd
+ * (:108-161) with the reference's arithmetic. init_codebooks != NULL skips k-means++ (then uniforms may be NULL); given
+ * the same initial centroids the result is bit-identical to m calls of vdb_kmeans_train_ds. codebooks (in/out layout):
+ * groups concatenated, [k][len_g] of the dataset dtype. iters (optional) receives the iterations run per group.
+ * Returns VDB_EUNSUPPORTED when k x max sub-dim does not fit one CTA's shared memory (use the per-group calls). */
+int vdb_pq_train_ds(const vdb_dataset* train, uint32_t m, uint32_t n_bits, uint32_t max_iter, float tol,
+                    const double* uniforms, const void* init_codebooks, void* codebooks, uint32_t* iters);
+
 /* ---- PQ ------------------------------------------------------------------------------------- */
 /* pq_groups (src/distance/pq_table.rs:38-53): out is [m, 2] (start, end). */
 int vdb_pq_groups(uint32_t dim, uint32_t m, uint32_t* out);
@@ -281,7 +291,7 @@ uint64_t vdb_launch_count(void);
  * kernels with CUDA events on the launching stream. vdb_prof_read synchronises the device, then
  * returns the accumulated milliseconds and launch count of kernel `name` since the last reset
  * (names: "flat_scan", "flat_gemm", "rerank", "merge", "pq_adc", "pq_encode", "ivf_scan",
- * "kmeans_assign", "pq_gemm", "pq_exact", "pq_lut", "hnsw_search", "hnsw_select", "hnsw_arrange"). */
+ * "kmeans_assign", "pq_gemm", "pq_exact", "pq_lut", "pq_train", "hnsw_search", "hnsw_select", "hnsw_arrange"). */
 int vdb_prof_enable(int on);
 int vdb_prof_reset(void);
 int vdb_prof_read(const char* name, double* ms, uint64_t* launches);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vdb_ivf_knn_keys_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
     "vdb_ivf_create": (i32, [vp, vp, u32, vp, vp]),
     "vdb_ivf_destroy": (i32, [vp]),
+    "vdb_pq_train_ds": (i32, [vp, u32, u32, u32, f32, vp, vp, vp, vp]),
     "vdb_hnsw_build": (i32, [vp, u32, u32, vp, u32, vp]),
     "vdb_hnsw_destroy": (i32, [vp]),
     "vdb_hnsw_append": (i32, [vp, vp, vp, u32]),

@@ -141,6 +141,12 @@ void rekey(const float* d_dist, const uint32_t* d_ids, const uint8_t* d_valid, u
 void rekey_based(const float* d_dist, const uint32_t* d_ids, uint32_t id_base, const uint8_t* d_valid, uint64_t count,
                  uint64_t* d_keys, cudaStream_t st);
 
+// kmeans.cu: batched PQ training
+bool pq_train_supported(uint32_t kc, uint32_t max_len);
+void pq_train_groups(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, int metric, uint32_t m, uint32_t kc, uint32_t max_len,
+                     const uint32_t* d_groups, const double* d_uniforms, const void* d_init, uint32_t max_iter, float tol,
+                     void* d_out, uint32_t* d_iters, cudaStream_t st);
+
 // pq_gemm.cu
 bool pq_tensor_supported(const vdb_pq* pq, uint32_t nq);
 void pq_tensor_lut(const vdb_pq* pq, const float* d_lut, uint32_t nq, DevBuf& lut16, cudaStream_t st);

@@ -365,4 +365,235 @@ void kmeans_pp_weights(const void* d_rows, uint64_t n, uint64_t pitch, int dtype
     VDB_LAUNCHED();
 }
 
+// ---- batched PQ training: every group's k-means (k-means++ init + Lloyd) in ONE launch --------------------------------
+// PQTable::from_vec_set trains one KMeans per group on the same sample (pq_table.rs:154-172), serially. A group is tiny
+// (C4: 10 000 rows x 4 dims x 16 centroids), so the per-group path is bound by launches and host round trips
+// (~100 per group). Here one CTA owns one group and runs the whole k_means_init (k_means.rs:61-87) and Lloyd loop
+// (:108-161) with the reference's arithmetic: sequential f32 distances, ties to the lowest centroid id, member sums in
+// ascending row order, empty clusters keep their centroid, max squared shift < tol. Given the same initial centroids
+// the result is bit-identical to vdb_kmeans_train (tested).
+struct PqTrainParams {
+    const void* rows;
+    uint64_t n, pitch;
+    uint32_t m, kc, max_iter;
+    float tol;
+    const uint32_t* groups;   // [m][3] (lo, len, codebook element offset)
+    const double* uniforms;   // [m][2 kc - 1] or nullptr when init != nullptr
+    const void* init;         // optional initial codebooks (same layout as out)
+    void* out;                // codebooks, groups concatenated, [kc][len] each
+    uint32_t* iters;          // [m]
+    float* w;                 // scratch [m][n]
+    uint8_t* assign;          // scratch [m][n]
+};
+
+template <typename T, int METRIC>
+__device__ __forceinline__ float seq_dist(const T* __restrict__ x, const float* __restrict__ c, uint32_t len, float cnorm) {
+    float s = 0.f, svv = 0.f;
+    for (uint32_t j = 0; j < len; ++j) {
+        const float xv = to_f32(x[j]), cv = c[j];
+        if (METRIC == VDB_L2SQR) {
+            const float df = __fsub_rn(xv, cv);
+            s = __fadd_rn(s, __fmul_rn(df, df));
+        } else {
+            s = __fadd_rn(s, __fmul_rn(xv, cv));
+            svv = __fadd_rn(svv, __fmul_rn(xv, xv));
+        }
+    }
+    if (METRIC == VDB_L2SQR) return s;
+    return __fsub_rn(1.0f, __fdiv_rn(s, fmaxf(__fmul_rn(sqrtf(svv), cnorm), 1e-10f)));
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256) pq_train_kernel(const PqTrainParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t g = blockIdx.x;
+    const uint32_t lo = p.groups[3 * g], len = p.groups[3 * g + 1], off = p.groups[3 * g + 2];
+    const uint32_t kc = p.kc;
+    float* cent = reinterpret_cast<float*>(smem);   // [kc][len]  current centroids (T-valued)
+    float* cnew = cent + (size_t)kc * len;           // [kc][len]
+    float* cnorm = cnew + (size_t)kc * len;          // [kc]
+    float* perc = cnorm + kc;                        // [kc]
+    __shared__ double tsum[256];
+    __shared__ int s_ok, s_pick_thread, s_conv;
+    __shared__ unsigned long long s_pick;
+    __shared__ double s_base, s_target;
+    const T* rows = reinterpret_cast<const T*>(p.rows);
+    T* out = reinterpret_cast<T*>(p.out) + off;
+    const uint64_t n = p.n;
+    float* w = p.w + (size_t)g * n;
+    uint8_t* asg = p.assign + (size_t)g * n;
+    const uint32_t tid = threadIdx.x;
+    auto sub = [&](uint64_t i) { return rows + i * p.pitch + lo; };
+    auto set_cnorm = [&]() {
+        if (METRIC == VDB_COSINE)
+            for (uint32_t c = tid; c < kc; c += blockDim.x) {
+                float s = 0.f;
+                for (uint32_t j = 0; j < len; ++j) s = __fadd_rn(s, __fmul_rn(cent[c * len + j], cent[c * len + j]));
+                cnorm[c] = sqrtf(s);
+            }
+    };
+    if (p.init) {
+        const T* ini = reinterpret_cast<const T*>(p.init) + off;
+        for (uint32_t e = tid; e < kc * len; e += blockDim.x) cent[e] = to_f32(ini[e]);
+        __syncthreads();
+    } else {
+        // ---- k_means_init: first = floor(u0 n); then weighted picks with the eager uniform fallback ----
+        const double* u = p.uniforms + (size_t)g * (2 * kc - 1);
+        const uint64_t chunk = (n + blockDim.x - 1) / blockDim.x;
+        const uint64_t i0 = min(n, (uint64_t)tid * chunk), i1 = min(n, i0 + chunk);
+        for (uint64_t i = i0; i < i1; ++i) w[i] = __uint_as_float(0x7f800000u);
+        uint64_t cur = (uint64_t)fmin((double)(n - 1), floor(u[0] * (double)n));
+        for (uint32_t r = 0; r < kc; ++r) {
+            __syncthreads();
+            for (uint32_t j = tid; j < len; j += blockDim.x) cent[r * len + j] = to_f32(sub(cur)[j]);
+            __syncthreads();
+            if (r + 1 == kc) break;
+            if (METRIC == VDB_COSINE && tid == 0) {
+                float s = 0.f;
+                for (uint32_t j = 0; j < len; ++j) s = __fadd_rn(s, __fmul_rn(cent[r * len + j], cent[r * len + j]));
+                cnorm[r] = sqrtf(s);
+            }
+            if (tid == 0) s_ok = 1;
+            __syncthreads();
+            double acc = 0.0;
+            bool ok = true;
+            for (uint64_t i = i0; i < i1; ++i) {
+                const float d = seq_dist<T, METRIC>(sub(i), cent + r * len, len, METRIC == VDB_COSINE ? cnorm[r] : 0.f);
+                const float x = fminf(w[i], d);
+                w[i] = x;
+                if (!(x >= 0.f) || isinf(x)) ok = false;
+                acc += (double)x;
+            }
+            tsum[tid] = acc;
+            if (!ok) s_ok = 0;
+            __syncthreads();
+            if (tid == 0) {
+                double total = 0.0;
+                for (uint32_t t = 0; t < blockDim.x; ++t) total += tsum[t];
+                s_pick = (unsigned long long)fmin((double)(n - 1), floor(u[2 * (r + 1)] * (double)n));  // fallback
+                s_pick_thread = -1;
+                if (s_ok && total > 0.0) {
+                    const double target = u[2 * (r + 1) - 1] * total;
+                    double pre = 0.0;
+                    s_pick = n - 1;
+                    for (uint32_t t = 0; t < blockDim.x; ++t) {
+                        if (target < pre + tsum[t]) {
+                            s_pick_thread = (int)t;
+                            s_base = pre;
+                            s_target = target;
+                            break;
+                        }
+                        pre += tsum[t];
+                    }
+                }
+            }
+            __syncthreads();
+            if ((int)tid == s_pick_thread) {
+                double a = s_base;
+                unsigned long long pick = i1 ? i1 - 1 : 0;
+                for (uint64_t i = i0; i < i1; ++i) {
+                    a += (double)w[i];
+                    if (s_target < a) {
+                        pick = i;
+                        break;
+                    }
+                }
+                s_pick = pick;
+            }
+            __syncthreads();
+            cur = s_pick;
+        }
+        __syncthreads();
+    }
+    // ---- Lloyd ----
+    uint32_t iters = 0;
+    for (uint32_t it = 0; it < p.max_iter; ++it) {
+        ++iters;
+        set_cnorm();
+        __syncthreads();
+        for (uint64_t i = tid; i < n; i += blockDim.x) {
+            const T* x = sub(i);
+            unsigned long long best = KEY_NONE;
+            for (uint32_t c = 0; c < kc; ++c) {
+                const unsigned long long key = make_key(seq_dist<T, METRIC>(x, cent + c * len, len, METRIC == VDB_COSINE ? cnorm[c] : 0.f), c);
+                best = key < best ? key : best;
+            }
+            asg[i] = (uint8_t)key_id(best);
+        }
+        __syncthreads();
+        for (uint32_t slot = tid; slot < kc * len; slot += blockDim.x) {
+            const uint32_t c = slot / len, j = slot - c * len;
+            float s = 0.f;
+            uint32_t cnt = 0;
+            for (uint64_t i = 0; i < n; ++i)
+                if (asg[i] == c) {
+                    s = __fadd_rn(s, to_f32(sub(i)[j]));
+                    ++cnt;
+                }
+            const float v = cnt ? __fdiv_rn(s, (float)cnt) : cent[slot];  // empty cluster keeps its centroid
+            cnew[slot] = to_f32(from_f32_as(v, (T*)nullptr));
+        }
+        __syncthreads();
+        for (uint32_t c = tid; c < kc; c += blockDim.x) {
+            float s = 0.f;
+            for (uint32_t j = 0; j < len; ++j) {
+                const float df = __fsub_rn(cent[c * len + j], cnew[c * len + j]);
+                s = __fadd_rn(s, __fmul_rn(df, df));
+            }
+            perc[c] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float mx = __uint_as_float(0xff800000u);
+            for (uint32_t c = 0; c < kc; ++c) mx = fmaxf(mx, perc[c]);
+            s_conv = mx < p.tol;
+        }
+        for (uint32_t e = tid; e < kc * len; e += blockDim.x) cent[e] = cnew[e];
+        __syncthreads();
+        if (s_conv) break;
+    }
+    for (uint32_t e = tid; e < kc * len; e += blockDim.x) out[e] = from_f32_as(cent[e], (T*)nullptr);
+    if (tid == 0) p.iters[g] = iters;
+}
+
+bool pq_train_supported(uint32_t kc, uint32_t max_len) { return kc <= 256 && (size_t)kc * max_len * 8 + kc * 8 <= 160 * 1024; }
+
+// groups: device [m][3]; uniforms: device [m][2 kc - 1] doubles (or nullptr with d_init); d_out / d_init: device codebooks
+void pq_train_groups(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, int metric, uint32_t m, uint32_t kc, uint32_t max_len,
+                     const uint32_t* d_groups, const double* d_uniforms, const void* d_init, uint32_t max_iter, float tol,
+                     void* d_out, uint32_t* d_iters, cudaStream_t st) {
+    VDB_REQUIRE(pq_train_supported(kc, max_len), "batched PQ training: k=%u x sub-dim %u does not fit in shared memory", kc, max_len);
+    VDB_REQUIRE(n > 0, "cannot train on an empty vector set");
+    DevBuf w((size_t)m * n * 4, st), asg((size_t)m * n, st);
+    PqTrainParams p{};
+    p.rows = d_rows;
+    p.n = n;
+    p.pitch = pitch;
+    p.m = m;
+    p.kc = kc;
+    p.max_iter = max_iter;
+    p.tol = tol;
+    p.groups = d_groups;
+    p.uniforms = d_uniforms;
+    p.init = d_init;
+    p.out = d_out;
+    p.iters = d_iters;
+    p.w = w.as<float>();
+    p.assign = asg.as<uint8_t>();
+    const size_t smem = (size_t)kc * max_len * 8 + (size_t)kc * 8;
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024) VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope prof("pq_train", st);
+        kern<<<m, 256, smem, st>>>(p);
+        VDB_LAUNCHED();
+    };
+    if (dtype == VDB_F32) {
+        if (metric == VDB_L2SQR) go(pq_train_kernel<float, VDB_L2SQR>);
+        else go(pq_train_kernel<float, VDB_COSINE>);
+    } else {
+        if (metric == VDB_L2SQR) go(pq_train_kernel<uint8_t, VDB_L2SQR>);
+        else go(pq_train_kernel<uint8_t, VDB_COSINE>);
+    }
+}
+
 }  // namespace vdb

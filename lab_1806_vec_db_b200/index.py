@@ -270,6 +270,32 @@ class PQConfig(NamedTuple):
     k_means_tol: float = 1e-6
 
 
+def train_codebooks(train_dev: DeviceVecSet, config: "PQConfig", rng=None, init_codebooks=None):
+    """The m per-group k-means of PQTable::from_vec_set (pq_table.rs:154-172) on a device-resident sample. All groups
+    are trained by one launch (vdb_pq_train_ds); the per-group path remains for shapes that do not fit one CTA."""
+    rng = rng if rng is not None else np.random.default_rng()
+    k, dim = 1 << config.n_bits, train_dev.dim
+    total = sum((hi - lo) * k for lo, hi in pq_groups(dim, config.m))
+    books = np.zeros(total, train_dev.dtype)
+    iters = np.zeros(config.m, np.uint32)
+    uni = None if init_codebooks is not None else np.ascontiguousarray(rng.random((config.m, 2 * k - 1)))
+    init = None if init_codebooks is None else np.ascontiguousarray(init_codebooks, dtype=train_dev.dtype)
+    rc = L.lib().vdb_pq_train_ds(train_dev._h, config.m, config.n_bits, config.k_means_max_iter, config.k_means_tol,
+                                 L.ptr(uni), L.ptr(init), L.ptr(books), L.ptr(iters))
+    if rc == L.EUNSUPPORTED:
+        parts, o = [], 0
+        for lo, hi in pq_groups(dim, config.m):
+            ini = None if init is None else init[o:o + k * (hi - lo)].reshape(k, hi - lo)
+            o += k * (hi - lo)
+            km = KMeans.from_vec_set(train_dev, KMeansConfig(k, config.k_means_max_iter, config.k_means_tol, config.dist,
+                                                             (lo, hi)), rng, ini)
+            parts.append(km.centroids.reshape(-1))
+        return np.concatenate(parts)
+    L.check(rc)
+    train_codebooks.last_iterations = iters
+    return books
+
+
 class PQTable:
     """PQTable<T> (pq_table.rs:116-137): codebooks + codes, device resident."""
 
@@ -302,14 +328,12 @@ class PQTable:
         if config.k_means_size is not None:
             perm = rng.permutation(len(rows_host))[:config.k_means_size]  # VecSet::random_sample (vec_set.rs:154-163)
             train = np.ascontiguousarray(rows_host[perm])
-        books = []
         train_dev = DeviceVecSet(train, config.dist)  # the sample is uploaded once for all m groups
-        for lo, hi in pq_groups(rows_host.shape[1], config.m):
-            km = KMeans.from_vec_set(train_dev, KMeansConfig(1 << config.n_bits, config.k_means_max_iter,
-                                                             config.k_means_tol, config.dist, (lo, hi)), rng)
-            books.append(km.centroids.reshape(-1))
-        train_dev.close()
-        return cls(vec_set, config, np.concatenate(books))
+        try:
+            books = train_codebooks(train_dev, config, rng)
+        finally:
+            train_dev.close()
+        return cls(vec_set, config, books)
 
     def create_lookup(self, queries):
         """PQTable::create_lookup (pq_table.rs:195-224) -> (lookup [nq, m*k], dist_cache [nq])."""

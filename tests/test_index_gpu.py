@@ -377,3 +377,68 @@ def test_pq_tensor_filter_large_shard(V, oracle, m):
         assert_knn_parity(base, q, "l2sqr", got, want, oracle)
         few = idx.knn_pq_batch(q[:9], k, ef, pq)     # < 32 queries: FP32 global-threshold scan
         assert (few[0] == got[0][:9]).all() and (few[1].view(np.uint32) == got[1][:9].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8])
+def test_batched_pq_training_bit_exact_vs_per_group(V, oracle, metric, dtype):
+    """vdb_pq_train_ds trains every group's k-means in one launch. Given the same initial centroids it must equal the
+    per-group Lloyd (vdb_kmeans_train_ds) and the oracle bit for bit: uneven groups (pq_groups(43, 9)), empty clusters
+    (duplicate initial centroids), u8 rows (Rust `as` cast of the means), early convergence."""
+    from lab_1806_vec_db_b200.index import train_codebooks
+    rng = np.random.default_rng(55)
+    n, dim, m = 1500, 43, 9
+    rows = (rng.random((n, dim)) * (255 if dtype == np.uint8 else 1)).astype(dtype)
+    rows[100:400] = rows[7]                              # heavy duplicates -> early convergence in some groups
+    cfg = V.PQConfig(4, m, metric, None, 12, 1e-6)
+    init, parts = [], []
+    vs = V.DeviceVecSet(rows, metric)
+    for lo, hi in V.pq_groups(dim, m):
+        ini = np.ascontiguousarray(rows[rng.integers(0, n, 16), lo:hi])
+        ini[3] = ini[2]                                  # duplicate centroid: the higher id stays empty forever
+        init.append(ini.reshape(-1))
+        km = V.KMeans.from_vec_set(vs, V.KMeansConfig(16, 12, 1e-6, metric, (lo, hi)), rng, ini)
+        parts.append(km.centroids.reshape(-1))
+        want, _ = oracle.kmeans_lloyd(rows, ini, metric, 12, 1e-6, sel=(lo, hi))
+        assert (np.asarray(want).reshape(-1).view(np.uint8) == km.centroids.reshape(-1).view(np.uint8)).all()
+    got = train_codebooks(vs, cfg, rng, np.concatenate(init))
+    assert (got.view(np.uint8) == np.concatenate(parts).view(np.uint8)).all()
+
+
+def test_batched_pq_training_end_to_end(V, fixtures, oracle):
+    """k-means++ + Lloyd for all groups in one launch: every initial centroid is a training row, quantisation error is
+    in line with the per-group path, and PQTable.from_vec_set (which now uses it) passes the reference's own test."""
+    from lab_1806_vec_db_b200.index import train_codebooks
+    base = fixtures["base"]
+    rng = np.random.default_rng(1)
+    vs = V.DeviceVecSet(base, "l2sqr")
+    cfg = V.PQConfig(4, 240, "l2sqr", None, 20, 1e-6)
+    books = train_codebooks(vs, cfg, rng)
+    assert books.shape == (240 * 16 * 4,) and np.isfinite(books).all()
+    assert (train_codebooks.last_iterations >= 1).all() and (train_codebooks.last_iterations <= 20).all()
+    pq = V.PQTable(vs, cfg, books)
+    codes = oracle.pq_encode(base, books, 240, 4, "l2sqr", nthreads=8)
+    assert (pq.encoded_vec_set == codes).all()
+    # quantisation error vs the per-group trainer on the same data
+    def qerr(bk):
+        c = oracle.pq_encode(base, bk, 240, 4, "l2sqr", nthreads=8)
+        rec = np.zeros_like(base)
+        o = 0
+        for g, (lo, hi) in enumerate(V.pq_groups(960, 240)):
+            cb = bk[o:o + 16 * (hi - lo)].reshape(16, hi - lo)
+            o += 16 * (hi - lo)
+            code = (c[:, g // 2] >> 4) if g % 2 else (c[:, g // 2] & 15)
+            rec[:, lo:hi] = cb[code]
+        return float(((rec - base) ** 2).sum(1).mean())
+    per_group = np.concatenate([V.KMeans.from_vec_set(vs, V.KMeansConfig(16, 20, 1e-6, "l2sqr", (lo, hi)), rng).centroids.reshape(-1)
+                                for lo, hi in V.pq_groups(960, 240)])
+    assert qerr(books) <= 1.05 * qerr(per_group)
+    # 0 iterations allowed: only k-means++ -> every centroid is a training row's sub-vector
+    cfg0 = V.PQConfig(4, 8, "l2sqr", None, 0, 1e-6)
+    b0 = train_codebooks(vs, cfg0, np.random.default_rng(2))
+    o = 0
+    for lo, hi in V.pq_groups(960, 8):
+        cb = b0[o:o + 16 * (hi - lo)].reshape(16, hi - lo)
+        o += 16 * (hi - lo)
+        for c in cb:
+            assert (np.abs(base[:, lo:hi] - c).max(1) == 0).any()
