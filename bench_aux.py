@@ -131,14 +131,17 @@ def main():
         M = args.pq_m
         cfg = V.PQConfig(4, M, "l2sqr", min(10_000, args.n), 20, 1e-6)
         train = np.ascontiguousarray(base_host[rng.permutation(args.n)[:min(10_000, args.n)]])
-        books = []
+        from lab_1806_vec_db_b200.index import train_codebooks
         train_dev = V.DeviceVecSet(train, "l2sqr")
-        for lo, hi in V.pq_groups(DIM, M):
-            km = V.KMeans.from_vec_set(train_dev, V.KMeansConfig(16, 20, 1e-6, "l2sqr", (lo, hi)), rng)
-            books.append(km.centroids.reshape(-1))
+        t1 = time.perf_counter()
+        books = train_codebooks(train_dev, cfg, rng)          # all m groups in one launch (vdb_pq_train_ds)
+        t_kernel = time.perf_counter() - t1
         train_dev.close()
-        books = np.concatenate(books)
         t_train = time.perf_counter() - t0
+        print(json.dumps({"config": "C4 PQ train", "m": M, "rows": len(train), "gpu_train_s_incl_upload": t_train,
+                          "gpu_train_call_s": t_kernel,
+                          "iterations_min_max": [int(train_codebooks.last_iterations.min()),
+                                                 int(train_codebooks.last_iterations.max())]}), flush=True)
         t0 = time.perf_counter()
         pq = V.PQTable(vs, cfg, books)
         return M, books, pq, t_train, time.perf_counter() - t0
