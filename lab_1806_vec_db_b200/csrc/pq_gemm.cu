@@ -37,7 +37,7 @@ constexpr int PK = 64;                     // bf16 columns per k-block = 4 group
 constexpr int P_A_BYTES = PM * PK * 2;     // 16 KB generated one-hot tile
 constexpr int P_BASE_THREADS = 192;        // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer; then GG x 4 generator warps
 constexpr int P_TMEM_COLS = 512;
-constexpr uint32_t P_MAX_ENC = 128;        // m <= 256 groups
+constexpr uint32_t P_MAX_ENC = 256;        // m <= 512 groups (the code tile of 128 rows must fit beside the stages)
 constexpr int P_MAX_STAGES = 6;
 // CTAS = 1: one CTA computes 128 rows x 256 queries. CTAS = 2: a CTA pair (cta_group::2) computes 256 rows x 256
 // queries; each CTA generates the one-hot rows of its own 128 rows and loads HALF of the LUT tile, so the shared-memory
@@ -48,7 +48,9 @@ template <int CTAS> struct PqCfg {
     static constexpr int B_BYTES = B_ROWS * PK * 2;
     static constexpr int STAGE_BYTES = P_A_BYTES + B_BYTES;    // 48 KB / 32 KB
     static constexpr int STAGES = CTAS == 1 ? 4 : 6;           // 192 KB either way
-    static constexpr uint32_t SMEM = 1024 + STAGES * STAGE_BYTES + PM * P_MAX_ENC + PN * 4 + 256;
+    static constexpr uint32_t smem_bytes(uint32_t enc) {  // align + stages + code tile + thresholds + barriers
+        return 1024 + STAGES * STAGE_BYTES + ((PM * enc + 15u) & ~15u) + PN * 4 + 256;
+    }
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PN >> 3) << 17) |
                                       ((uint32_t)((PM * CTAS) >> 4) << 24);
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(P_BASE_THREADS + 128 * GG, 1) pq_gemm_kernel(c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stage_base = smem;
     uint8_t* codes_s = smem + STAGES * Cfg::STAGE_BYTES;                  // [PM][enc]
-    float* tau_s = reinterpret_cast<float*>(codes_s + PM * P_MAX_ENC);    // [PN]
+    float* tau_s = reinterpret_cast<float*>(codes_s + ((PM * p.enc + 15u) & ~15u));  // [PN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tau_s + PN);
     uint64_t* full_bar = bars;                      // [STAGES]  (pair mode: the leader's copy is the live one)
     uint64_t* empty_bar = bars + P_MAX_STAGES;      // [STAGES]  per CTA
@@ -403,13 +405,13 @@ static void launch_pq_gemm_t(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq,
     auto kern = pq_gemm_kernel<MODE, CTAS, GG>;
     static thread_local bool configured = false;
     if (!configured) {
-        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes(P_MAX_ENC)));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(std::min<uint32_t>(units, p.nrow_items * p.nqt) * CTAS);
     cfg.blockDim = dim3(P_BASE_THREADS + 128 * GG);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.dynamicSmemBytes = Cfg::smem_bytes(pq->enc);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -442,3 +442,22 @@ def test_batched_pq_training_end_to_end(V, fixtures, oracle):
         o += 16 * (hi - lo)
         for c in cb:
             assert (np.abs(base[:, lo:hi] - c).max(1) == 0).any()
+
+
+def test_pq_tensor_filter_m320(V, oracle):
+    """m = 320 (the reference's published HNSW+PQ / Flat+PQ setting, config/bench_10000_pq_flat.toml): 160-byte codes,
+    80 k-blocks - the code tile is sized from the actual encoded_dim."""
+    rng = np.random.default_rng(320)
+    n, dim, m = 66_000, 330, 320
+    base = rng.random((n, dim), dtype=np.float32)
+    q = rng.random((40, dim), dtype=np.float32)
+    books = np.concatenate([np.ascontiguousarray(base[200:216, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(dim, m)])
+    vs = V.DeviceVecSet(base, "l2sqr")
+    pq = V.PQTable(vs, V.PQConfig(4, m, "l2sqr"), books)
+    codes = oracle.pq_encode(base, books, m, 4, "l2sqr", nthreads=8)
+    assert pq.encoded_vec_set.shape == (n, 160) and (pq.encoded_vec_set == codes).all()
+    idx = V.FlatIndex(vs)
+    for k, ef in ((10, 100), (10, 200)):
+        got = idx.knn_pq_batch(q, k, ef, pq)
+        want = oracle.flat_knn_pq(base, codes, books, m, 4, q, k, ef, "l2sqr", nthreads=8)
+        assert_knn_parity(base, q, "l2sqr", got, want, oracle)
