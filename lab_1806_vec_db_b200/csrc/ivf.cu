@@ -528,6 +528,13 @@ void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queri
     VDB_REQUIRE(ds->n == ivf->n && ds->dim == ivf->dim && ds->dtype == ivf->dtype && ds->metric == ivf->metric,
                 "IVF index was built for a different vector set");
     if (nq == 0 || k == 0) return;
+    if (nq > 16384) {  // chunks bound the candidate / rerank scratch of the batched paths
+        const size_t row_bytes = (size_t)ds->dim * ds->elem_size();
+        for (uint32_t q0 = 0; q0 < nq; q0 += 16384)
+            ivf_knn_keys(ds, ivf, (const uint8_t*)d_queries + (size_t)q0 * row_bytes, std::min(16384u, nq - q0), k, n_probes,
+                         d_keys + (size_t)q0 * k, st);
+        return;
+    }
     const uint32_t nprobe = std::min(n_probes, ivf->nlist);
     // 1. exact query-centroid distances, probe order = find_n_nearest (k_means.rs:174-191)
     DevBuf cdist((size_t)nq * ivf->nlist * 4, st), best((size_t)nq * 8, st), ckeys((size_t)nq * ivf->nlist * 8, st),

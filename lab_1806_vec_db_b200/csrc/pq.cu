@@ -646,8 +646,16 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
 static void adc_topk(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K, uint32_t id_base,
                      uint64_t* d_keys, cudaStream_t st) {
     static const int force_old = getenv("VDB_ADC_OLD") ? atoi(getenv("VDB_ADC_OLD")) : 0;
-    if (!force_old && nq >= 4 && adc_global_supported(pq, K)) adc_topk_global(pq, d_lut, d_qcache, nq, K, id_base, d_keys, st);
-    else adc_scan(pq, d_lut, d_qcache, nq, K, id_base, d_keys, nullptr, st);
+    if (!force_old && nq >= 4 && adc_global_supported(pq, K)) {
+        // chunks of 8192 queries bound the sample-score and candidate scratch (~1 GB + 8192 * cap * 12 B per chunk)
+        const uint32_t tab = pq->m * pq->kc;
+        for (uint32_t q0 = 0; q0 < nq; q0 += 8192) {
+            const uint32_t cn = std::min(8192u, nq - q0);
+            adc_topk_global(pq, d_lut + (size_t)q0 * tab, d_qcache + q0, cn, K, id_base, d_keys + (size_t)q0 * K, st);
+        }
+    } else {
+        adc_scan(pq, d_lut, d_qcache, nq, K, id_base, d_keys, nullptr, st);
+    }
 }
 
 // stratified random sample of the code rows, in the scan's transposed layout
