@@ -516,7 +516,7 @@ __global__ void iota_pairs_kernel(const uint64_t* __restrict__ keys, uint32_t nq
 
 // ---- host side -----------------------------------------------------------------------------------------------------
 // visited-set capacity: a search visits ~10-15 nodes per expansion; beyond 7/8 full further neighbours are ignored
-static uint32_t hash_cap_for(uint32_t ef) { return ef <= 128 ? 8192u : (ef <= 640 ? 16384u : 32768u); }
+static uint32_t hash_cap_for(uint32_t ef) { return ef <= 256 ? 8192u : (ef <= 640 ? 16384u : 32768u); }
 
 template <typename KernT, typename ParamT>
 static void launch_dyn(KernT kern, uint32_t grid, size_t smem, const ParamT& p, cudaStream_t st) {
