@@ -356,7 +356,7 @@ int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
             if (nq && d_counts) VDB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, st));
             return;
         }
-        vdb::launch_merge_keys(d_keys, nlists, nq, k, true, k, nullptr, d_ids, d_dist, d_counts, st);
+        vdb::launch_merge_sorted(d_keys, nlists, nq, k, k, nullptr, d_ids, d_dist, d_counts, st);
     });
 }
 
@@ -422,7 +422,7 @@ int vdb_merge_keys_to_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t
     return guarded([&] {
         VDB_REQUIRE(nq * (uint64_t)k == 0 || (d_keys && d_out_keys), "NULL argument");
         VDB_REQUIRE(nlists > 0, "nlists must be > 0");
-        vdb::launch_merge_keys(d_keys, nlists, nq, k, true, k, d_out_keys, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+        vdb::launch_merge_sorted(d_keys, nlists, nq, k, k, d_out_keys, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     });
 }
 int vdb_decode_keys_dev(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,

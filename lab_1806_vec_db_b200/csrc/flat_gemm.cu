@@ -826,7 +826,7 @@ void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j
     VDB_REQUIRE(j0 >= 1 && j0 <= (uint64_t)j * nlists, "j0 out of range");
     const uint32_t jj = std::min<uint64_t>(j0, (uint64_t)j * nlists);
     DevBuf merged((size_t)tq->nq * jj * 8, st);
-    launch_merge_keys(d_lists, nlists, tq->nq, j, true, jj, merged.as<uint64_t>(), nullptr, nullptr, nullptr, st);
+    launch_merge_sorted(d_lists, nlists, tq->nq, j, jj, merged.as<uint64_t>(), nullptr, nullptr, nullptr, st);  // per-shard lists are ascending
     const bool cosine = tq->ds->metric == VDB_COSINE;
     tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj,
                                                                   cosine ? nullptr : tq->qcm.as<float>(),

@@ -10,6 +10,8 @@
 // row byte, partial sums are reduced with a V-1 shuffle reduce-scatter, and candidates that beat the
 // CTA's current k-th best go to a shared-memory buffer that is bitonic-sorted only when it fills.
 // Algorithmic bytes per pass: n * pitch * sizeof(T) (+ the query tile and G*k keys).
+#include <cstdlib>
+
 #include "dataset.cuh"
 #include "topk.cuh"
 
@@ -249,6 +251,85 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off,
                                                            k, P, limit, d_out_keys, d_ids,
                                                            d_dist, d_counts);
+    VDB_LAUNCHED();
+}
+
+// ---- merge of SORTED lists (the per-shard [nq, k] results after the all-gather) -------------------------------------
+// Every key finds its rank in the union by binary searches in the other lists (ties between lists go to the lower
+// list index: stable), so there is no sort: nlists * len * (nlists - 1) * log2(len) shared-memory reads per query.
+// Lists are ascending with KEY_NONE padding at the end (the contract of vdb_*_keys_dev).
+__global__ void __launch_bounds__(256) merge_sorted_kernel(const uint64_t* __restrict__ keys, uint32_t nlists, uint32_t nq, uint32_t len,
+                                                          uint32_t k, uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids,
+                                                          float* __restrict__ dist, uint32_t* __restrict__ counts) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);  // [nlists][len]
+    uint64_t* o = s + (size_t)nlists * len;               // [k]
+    const uint32_t q = blockIdx.x, T = nlists * len;
+    __shared__ uint32_t valid;
+    if (threadIdx.x == 0) valid = 0;
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+        const uint32_t l = t / len, i = t - l * len;
+        s[t] = keys[((size_t)l * nq + q) * len + i];
+    }
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) o[j] = KEY_NONE;
+    __syncthreads();
+    uint32_t mine = 0;
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+        const uint64_t x = s[t];
+        if (x == KEY_NONE) continue;
+        ++mine;
+        const uint32_t l = t / len;
+        uint32_t rank = t - l * len;
+        for (uint32_t l2 = 0; l2 < nlists && rank < k; ++l2) {
+            if (l2 == l) continue;
+            const uint64_t* lst = s + (size_t)l2 * len;
+            uint32_t lo = 0, hi = len;
+            if (l2 < l) {  // elements <= x
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (lst[mid] <= x) lo = mid + 1;
+                    else hi = mid;
+                }
+            } else {       // elements < x
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (lst[mid] < x) lo = mid + 1;
+                    else hi = mid;
+                }
+            }
+            rank += lo;
+        }
+        if (rank < k) o[rank] = x;
+    }
+    if (mine) atomicAdd(&valid, mine);
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint64_t key = o[j];
+        if (out_keys) out_keys[(size_t)q * k + j] = key;
+        if (ids) {
+            const bool ok = key != KEY_NONE;
+            ids[(size_t)q * k + j] = ok ? (uint64_t)key_id(key) : KEY_NONE;
+            dist[(size_t)q * k + j] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+        }
+    }
+    if (threadIdx.x == 0 && counts) counts[q] = min(valid, k);
+}
+
+// list-major [nlists][nq][len] ascending lists -> the k smallest per query; falls back to the generic merge when the
+// lists of a query do not fit in shared memory
+void launch_merge_sorted(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, uint32_t k, uint64_t* d_out_keys,
+                         uint64_t* d_ids, float* d_dist, uint32_t* d_counts, cudaStream_t stream) {
+    if (nq == 0 || k == 0) return;
+    static const int generic = getenv("VDB_MERGE_GENERIC") ? atoi(getenv("VDB_MERGE_GENERIC")) : 0;
+    const size_t smem = ((size_t)nlists * len + k) * 8;
+    if (generic || nlists == 1 || smem > 96 * 1024) {
+        launch_merge_keys(d_keys, nlists, nq, len, true, k, d_out_keys, d_ids, d_dist, d_counts, stream);
+        return;
+    }
+    if (smem > 48 * 1024)
+        VDB_CUDA(cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof("merge", stream);
+    merge_sorted_kernel<<<nq, 256, smem, stream>>>(d_keys, nlists, nq, len, k, d_out_keys, d_ids, d_dist, d_counts);
     VDB_LAUNCHED();
 }
 

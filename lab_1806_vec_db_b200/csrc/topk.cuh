@@ -66,6 +66,8 @@ inline uint32_t topk_segment_size(uint32_t K, uint32_t period) { return next_pow
 
 // merges `nlists` ascending (or unsorted) key lists of length `len` per query into the k best.
 // in: keys[list][query][len] when list_major, else keys[query][list][len].
+void launch_merge_sorted(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, uint32_t k, uint64_t* d_out_keys,
+                         uint64_t* d_ids, float* d_dist, uint32_t* d_counts, cudaStream_t stream);
 void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
                        uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off = nullptr);

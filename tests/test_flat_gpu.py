@@ -145,3 +145,39 @@ def test_synthetic_large_properties(oracle):
     assert (np.diff(dist, axis=1) >= 0).all()
     want = oracle.flat_knn(base, q, 100, "l2sqr", 8)
     assert_knn_parity(base, q, "l2sqr", (ids, dist, counts), want, oracle)
+
+
+def test_merge_of_sorted_shard_lists_vs_numpy():
+    """vdb_merge_keys_to_keys_dev / vdb_merge_keys_dev merge ascending per-shard lists by rank (no sort): random lists
+    with KEY_NONE padding, short lists, equal keys in different lists (stable), k larger than the valid total."""
+    import ctypes as C
+    import torch
+    from lab_1806_vec_db_b200 import _lib as L
+    lib = L.lib()
+    rng = np.random.default_rng(8)
+    NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
+    for nlists, nq, k in ((8, 37, 100), (2, 5, 10), (5, 3, 600), (3, 4, 1)):
+        lists = np.full((nlists, nq, k), NONE, np.uint64)
+        for l in range(nlists):
+            for q in range(nq):
+                cnt = int(rng.integers(0, k + 1))
+                vals = rng.integers(0, 1 << 40, cnt).astype(np.uint64)
+                if l and cnt and rng.random() < 0.5:      # a key that also occurs in list 0
+                    src = lists[0, q][lists[0, q] != NONE]
+                    if len(src):
+                        vals[0] = src[0]
+                lists[l, q, :cnt] = np.sort(vals)
+        want = np.sort(lists.transpose(1, 0, 2).reshape(nq, -1), axis=1)[:, :k]
+        d = torch.from_numpy(lists.view(np.int64)).cuda()
+        out = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(lib.vdb_merge_keys_to_keys_dev(C.c_void_p(d.data_ptr()), nlists, nq, k, C.c_void_p(out.data_ptr()), st))
+        assert (out.cpu().numpy().view(np.uint64) == want).all(), (nlists, nq, k)
+        ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        dd = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        cnt = torch.empty((nq,), dtype=torch.int32, device="cuda")
+        L.check(lib.vdb_merge_keys_dev(C.c_void_p(d.data_ptr()), nlists, nq, k, C.c_void_p(ids.data_ptr()),
+                                       C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), st))
+        valid = (want != NONE)
+        assert (cnt.cpu().numpy() == valid.sum(1)).all()
+        assert (ids.cpu().numpy().view(np.uint64)[valid] == (want[valid] & np.uint64(0xFFFFFFFF))).all()
