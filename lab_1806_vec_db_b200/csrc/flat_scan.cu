@@ -184,12 +184,19 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
     float* __restrict__ dist, uint32_t* __restrict__ counts) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem);
-    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + P), K, P, 1, limit};
-    topk.init();
     const uint32_t q = blockIdx.x;
     // seg_off != nullptr: one variable-length list per query, keys[seg_off[q] .. seg_off[q+1])
     const uint64_t seg_base = seg_off ? seg_off[q] : 0;
     const uint64_t total = seg_off ? seg_off[q + 1] - seg_base : (uint64_t)nlists * len;
+    // a short list is sorted once in the smallest power-of-two segment that holds it (no intermediate flush)
+    uint32_t Pq = P, lim = limit;
+    if (total + K <= P) {
+        const uint32_t need = (uint32_t)total + K;
+        Pq = need <= 64 ? 64u : (1u << (32 - __clz(need - 1)));
+        lim = Pq - K;
+    }
+    TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + P), K, Pq, 1, lim};
+    topk.init();
     // one key per thread and round; the next round's key is loaded before this round's CTA-wide flush test so
     // the load latency overlaps the barrier
     const uint64_t rounds = (total + blockDim.x - 1) / blockDim.x;
