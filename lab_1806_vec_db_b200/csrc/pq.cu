@@ -107,6 +107,123 @@ __global__ void __launch_bounds__(256) pq_encode_kernel(const T* __restrict__ ro
     }
 }
 
+// K6b: 4-bit encode with everything staged in shared memory. The codebooks (16 x dim elements) are kept as
+// [j][c][group] so the lanes of a warp - consecutive code bytes, i.e. consecutive groups - read consecutive words; a
+// tile of rows is loaded with coalesced 128-bit loads. Same arithmetic as K6 (sequential f32 per sub-vector, ties to the
+// lowest centroid), so the codes are bit-identical; 66 ms -> a few ms for 1M x 960 (the per-thread global re-reads of K6
+// were L1-bound at 1 % of HBM bandwidth).
+constexpr int ENC_MAXL = 8;   // longest sub-vector handled in registers
+constexpr int ENC_ROWS = 8;   // rows per tile
+// nearest of the 16 centroids of group g for the sub-vector at rowS + lo, LEN elements (reference order, ties -> lowest id)
+template <int METRIC, int LEN>
+__device__ __forceinline__ uint32_t encode_group(const float* __restrict__ x, const float* __restrict__ cbS, const float* __restrict__ cnS,
+                                                 uint32_t mp, uint32_t g) {
+    float v[LEN];
+    float svv = 0.f;
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) {
+        v[j] = x[j];
+        if (METRIC == VDB_COSINE) svv = __fadd_rn(svv, __fmul_rn(v[j], v[j]));
+    }
+    const float vn = sqrtf(svv);
+    unsigned long long best = KEY_NONE;
+#pragma unroll
+    for (uint32_t c = 0; c < 16; ++c) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int j = 0; j < LEN; ++j) {
+            const float y = cbS[((size_t)j * 16 + c) * mp + g];
+            if (METRIC == VDB_L2SQR) {
+                const float df = __fsub_rn(v[j], y);
+                sacc = __fadd_rn(sacc, __fmul_rn(df, df));
+            } else {
+                sacc = __fadd_rn(sacc, __fmul_rn(v[j], y));
+            }
+        }
+        float d = sacc;
+        if (METRIC == VDB_COSINE) d = __fsub_rn(1.0f, __fdiv_rn(sacc, fmaxf(__fmul_rn(vn, cnS[c * mp + g]), 1e-10f)));
+        const unsigned long long key = make_key(d, c);
+        best = key < best ? key : best;
+    }
+    return key_id(best);
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256) pq_encode4_kernel(const T* __restrict__ rows, uint64_t n, uint64_t pitch, uint32_t dim,
+                                                         const T* __restrict__ cb, const uint32_t* __restrict__ groups,
+                                                         const float* __restrict__ cb_norm, uint32_t m, uint32_t enc,
+                                                         uint32_t max_len, uint8_t* __restrict__ codes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t mp = m + (m & 1);                               // even: a byte's two groups always exist in the table
+    float* cbS = reinterpret_cast<float*>(smem);                    // [max_len][16][mp]
+    float* cnS = cbS + (size_t)max_len * 16 * mp;                   // [16][mp]  ||c|| (cosine)
+    float* rowS = cnS + 16 * mp;                                    // [ENC_ROWS][dimp]
+    const uint32_t dimp = (dim + 3) & ~3u;
+    uint16_t* gl = reinterpret_cast<uint16_t*>(rowS + (size_t)ENC_ROWS * dimp);  // [mp][2] (lo, len)
+    for (uint32_t i = threadIdx.x; i < max_len * 16 * mp; i += blockDim.x) cbS[i] = 0.f;
+    for (uint32_t i = threadIdx.x; i < 16 * mp; i += blockDim.x) cnS[i] = 0.f;
+    for (uint32_t g = threadIdx.x; g < mp; g += blockDim.x) {
+        gl[2 * g] = g < m ? (uint16_t)groups[3 * g] : 0;
+        gl[2 * g + 1] = g < m ? (uint16_t)groups[3 * g + 1] : 0;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < m * 16; i += blockDim.x) {
+        const uint32_t g = i >> 4, c = i & 15;
+        const uint32_t len = groups[3 * g + 1], off = groups[3 * g + 2];
+        for (uint32_t j = 0; j < len; ++j) cbS[((size_t)j * 16 + c) * mp + g] = pq_f32(cb[off + (size_t)c * len + j]);
+        cnS[c * mp + g] = cb_norm[i];
+    }
+    __syncthreads();
+    const uint64_t ntiles = (n + ENC_ROWS - 1) / ENC_ROWS;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t row0 = tile * ENC_ROWS;
+        const uint32_t nr = (uint32_t)min((uint64_t)ENC_ROWS, n - row0);
+        if (sizeof(T) == 4 && (dim & 3) == 0 && (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0) {
+            const uint32_t d4 = dim >> 2;
+            for (uint32_t i = threadIdx.x; i < nr * d4; i += blockDim.x) {
+                const uint32_t r = i / d4, e = i - r * d4;
+                reinterpret_cast<float4*>(rowS + (size_t)r * dimp)[e] =
+                    __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rows) + (row0 + r) * pitch) + e);
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < nr * dim; i += blockDim.x) {
+                const uint32_t r = i / dim, e = i - r * dim;
+                rowS[(size_t)r * dimp + e] = pq_f32(rows[(row0 + r) * pitch + e]);
+            }
+        }
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < nr * enc; t += blockDim.x) {
+            const uint32_t r = t / enc, b = t - r * enc;
+            uint32_t byte = 0;
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t g = 2 * b + h;
+                if (g >= m) break;
+                const uint32_t lo = gl[2 * g], len = gl[2 * g + 1];
+                const float* x = rowS + (size_t)r * dimp + lo;
+                uint32_t code = 0;
+                switch (len) {
+                    case 1: code = encode_group<METRIC, 1>(x, cbS, cnS, mp, g); break;
+                    case 2: code = encode_group<METRIC, 2>(x, cbS, cnS, mp, g); break;
+                    case 3: code = encode_group<METRIC, 3>(x, cbS, cnS, mp, g); break;
+                    case 4: code = encode_group<METRIC, 4>(x, cbS, cnS, mp, g); break;
+                    case 5: code = encode_group<METRIC, 5>(x, cbS, cnS, mp, g); break;
+                    case 6: code = encode_group<METRIC, 6>(x, cbS, cnS, mp, g); break;
+                    case 7: code = encode_group<METRIC, 7>(x, cbS, cnS, mp, g); break;
+                    default: code = encode_group<METRIC, 8>(x, cbS, cnS, mp, g); break;
+                }
+                byte |= code << (4 * h);
+            }
+            codes[(row0 + r) * enc + b] = (uint8_t)byte;
+        }
+        __syncthreads();
+    }
+}
+static size_t encode4_smem(uint32_t m, uint32_t max_len, uint32_t dim) {
+    const uint32_t mp = m + (m & 1);
+    return ((size_t)max_len * 16 * mp + 16 * mp + (size_t)ENC_ROWS * ((dim + 3) & ~3u)) * 4 + (size_t)mp * 4;
+}
+
 // reference layout [n][enc] -> [ceil(n/32)][words][32] u32 (zero padded)
 __global__ void pq_transpose_kernel(const uint8_t* __restrict__ codes, uint64_t n, uint32_t enc, uint32_t words,
                                     uint32_t* __restrict__ out) {
@@ -727,7 +844,29 @@ vdb_pq* pq_create(const vdb_dataset* ds, const void* h_codebooks, uint32_t m, ui
                 const uint64_t total = pq->n * pq->enc;
                 const uint32_t grid = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(total, 256), (uint64_t)sm_count() * 32);
                 ProfScope prof("pq_encode", st);
+                static const int enc_old = getenv("VDB_PQ_ENCODE_OLD") ? atoi(getenv("VDB_PQ_ENCODE_OLD")) : 0;
+                const size_t smem4 = encode4_smem(m, pq->max_len, ds->dim);
+                const bool fast = !enc_old && n_bits == 4 && pq->max_len <= (uint32_t)ENC_MAXL && smem4 <= 200 * 1024 && ds->dim < 65536;
+                auto go4 = [&](auto kern, auto* tag) {
+                    using T = std::remove_pointer_t<decltype(tag)>;
+                    if (smem4 > 48 * 1024) VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+                    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem4));
+                    const uint32_t g4 = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(pq->n, ENC_ROWS), (uint64_t)sm_count() * per_sm);
+                    kern<<<g4, 256, smem4, st>>>((const T*)ds->d_rows, ds->n, (uint64_t)ds->pitch, ds->dim, (const T*)pq->d_codebooks,
+                                                 pq->d_groups, pq->d_cb_norm, m, pq->enc, pq->max_len, pq->d_codes);
+                };
+                if (fast) {
+                    if (ds->dtype == VDB_F32) {
+                        if (pq->metric == VDB_L2SQR) go4(pq_encode4_kernel<float, VDB_L2SQR>, (float*)nullptr);
+                        else go4(pq_encode4_kernel<float, VDB_COSINE>, (float*)nullptr);
+                    } else {
+                        if (pq->metric == VDB_L2SQR) go4(pq_encode4_kernel<uint8_t, VDB_L2SQR>, (uint8_t*)nullptr);
+                        else go4(pq_encode4_kernel<uint8_t, VDB_COSINE>, (uint8_t*)nullptr);
+                    }
+                    VDB_LAUNCHED();
+                }
                 auto go = [&](auto kern, auto* tag) {
+                    if (fast) return;
                     using T = std::remove_pointer_t<decltype(tag)>;
                     kern<<<grid, 256, 0, st>>>((const T*)ds->d_rows, ds->n, (uint64_t)ds->pitch, (const T*)pq->d_codebooks,
                                                pq->d_groups, pq->d_cb_norm, m, n_bits, pq->kc, pq->enc, pq->d_codes);
@@ -739,7 +878,7 @@ vdb_pq* pq_create(const vdb_dataset* ds, const void* h_codebooks, uint32_t m, ui
                     if (pq->metric == VDB_L2SQR) go(pq_encode_kernel<uint8_t, VDB_L2SQR>, (uint8_t*)nullptr);
                     else go(pq_encode_kernel<uint8_t, VDB_COSINE>, (uint8_t*)nullptr);
                 }
-                VDB_LAUNCHED();
+                if (!fast) VDB_LAUNCHED();
             }
             const uint64_t tt = ceil_div<uint64_t>(pq->n, 32) * pq->words * 32;
             pq_transpose_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(tt, 256), 1u << 20), 256, 0, st>>>(
