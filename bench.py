@@ -329,8 +329,8 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "flat_gemm_kernel", "achieved": achieved, "peak": sustained,
                 "unit": "TFLOP/s", "frac": achieved / sustained,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the filter launch from the committed ncu capture
-                # (profiles/r01_flat_gemm_ncu.md: 4.26 GB + 75 MB at 1M x 960, 10k queries; algorithmic 3.89 GB)
-                "traffic": (4.26e9 + 75e6 if (n_local == 1_000_000 and args.nq == 10_000) else None),
+                # (profiles/r01_flat_gemm_ncu.md: 4.19 GB + 77 MB at 1M x 960, 10k queries; algorithmic 3.89 GB)
+                "traffic": (4.19e9 + 76.8e6 if (n_local == 1_000_000 and args.nq == 10_000) else None),
                 "traffic_source": "ncu --set full capture, profiles/r01_flat_gemm_ncu.md (bytes per filter launch)",
                 "peak_source": "cuBLAS TF32 8192^3 measured in this run, sustained (burst %.1f); nominal dense TF32 "
                                "is 1100; MEASURED_PEAKS.json has bf16 only (%.1f sustained)"
