@@ -380,34 +380,60 @@ struct HnswSelectParams {
     uint32_t* selcnt;          // [tasks]
 };
 
-// heuristic over a sorted (distance, id) list: keep x when every kept y has d(x, y) >= d(x, base). Block-wide;
-// `xs` is a dimpad-float shared buffer. Returns the number kept (ids in kept[]).
+// heuristic over a sorted (distance, id) list: keep x when every kept y has d(x, y) >= d(x, base). Block-wide.
+// The candidates are tested a WINDOW at a time, one per warp, against the members kept so far (a candidate that fails
+// against them fails in the sequential loop too, because the kept set only grows); the survivors of a window are then
+// admitted in order, each later survivor re-tested against the member just admitted. The result is exactly the
+// sequential heuristic's. `xs` holds one dimpad-float staging buffer per warp. Returns the number kept (ids in kept[]).
+constexpr int HN_WARPS = HN_THREADS / 32;
 template <typename T, int METRIC>
 __device__ uint32_t heuristic_select(const T* rows, uint32_t pitch, uint32_t dim, uint32_t dimpad, const float* rcache,
-                                     const uint64_t* sorted, uint32_t count, uint32_t limit, float* xs, uint32_t* kept,
-                                     volatile int* flag) {
+                                     const uint64_t* sorted, uint32_t count, uint32_t limit, float* xs, uint32_t* kept) {
+    __shared__ int s_pass[HN_WARPS];
+    __shared__ uint32_t s_id[HN_WARPS];
+    __shared__ float s_dx[HN_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* xw = xs + (size_t)warp * dimpad;
     uint32_t nk = 0;
-    for (uint32_t i = 0; i < count && nk < limit; ++i) {
-        const uint64_t key = sorted[i];
-        if (key == KEY_NONE) break;
+    for (uint32_t i = 0; i < count && nk < limit; i += HN_WARPS) {
+        if (sorted[i] == KEY_NONE) break;
+        __syncthreads();
+        const uint32_t idx = i + warp;
+        const uint64_t key = idx < count ? sorted[idx] : KEY_NONE;
+        bool pass = key != KEY_NONE;
         const uint32_t x = key_id(key);
         const float dx = key_dist(key);
-        __syncthreads();
-        stage_row<T>(rows + (size_t)x * pitch, dim, dimpad, xs);
-        if (threadIdx.x == 0) *flag = 1;
-        __syncthreads();
-        const float cx = rcache[x];
-        for (uint32_t j = warp; j < nk; j += HN_THREADS / 32) {
-            const uint32_t y = kept[j];
-            const float dot = warp_dot_row<T>(rows + (size_t)y * pitch, xs, pitch, lane);
-            const float dxy = cached_dist<METRIC>(dot, cx, rcache[y]);
-            if (lane == 0 && !(dxy >= dx)) *flag = 0;
+        float cx = 0.f;
+        if (pass) {
+            const T* xr = rows + (size_t)x * pitch;
+            for (uint32_t e = lane; e < dimpad; e += 32) xw[e] = e < dim ? (float)xr[e] : 0.f;
+            __syncwarp();
+            cx = rcache[x];
+            for (uint32_t j = 0; j < nk; ++j) {
+                const uint32_t y = kept[j];
+                const float dot = warp_dot_row<T>(rows + (size_t)y * pitch, xw, pitch, lane);
+                if (!(cached_dist<METRIC>(dot, cx, rcache[y]) >= dx)) {
+                    pass = false;
+                    break;
+                }
+            }
+        }
+        if (lane == 0) {
+            s_pass[warp] = pass;
+            s_id[warp] = x;
+            s_dx[warp] = dx;
         }
         __syncthreads();
-        if (*flag) {
-            if (threadIdx.x == 0) kept[nk] = x;
+        for (int u = 0; u < HN_WARPS && nk < limit; ++u) {
+            if (!s_pass[u]) continue;  // uniform: read after a barrier
+            if (threadIdx.x == 0) kept[nk] = s_id[u];
             ++nk;
+            if (warp > u && s_pass[warp]) {  // later survivors must also clear the member just admitted
+                const uint32_t y = s_id[u];
+                const float dot = warp_dot_row<T>(rows + (size_t)y * pitch, xw, pitch, lane);
+                if (!(cached_dist<METRIC>(dot, cx, rcache[y]) >= dx) && lane == 0) s_pass[warp] = 0;
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -419,14 +445,13 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_select_kernel(const HnswSelec
     extern __shared__ __align__(16) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem);
     __shared__ uint32_t kept[HN_MAX_M0 + 1];
-    __shared__ int flag;
     const uint32_t t = blockIdx.x;
     if (t >= p.ntasks) return;
     const T* rows = reinterpret_cast<const T*>(p.rows);
     const uint32_t node = p.task_node[t], lvl = p.task_lvl[t];
     // the initial number of neighbours is limited to M even on level 0 (:231-235)
     const uint32_t nk = heuristic_select<T, METRIC>(rows, p.pitch, p.dim, p.dimpad, p.rcache, p.cand + (size_t)t * p.ef, p.ef, p.g.M, xs,
-                                                    kept, &flag);
+                                                    kept);
     uint32_t* dst = lvl == 0 ? p.g.links0 + (size_t)node * p.g.M0 : p.g.ulinks + (p.g.uoff[node] + (lvl - 1)) * p.g.M;
     for (uint32_t j = threadIdx.x; j < nk; j += blockDim.x) {
         dst[j] = kept[j];
@@ -456,10 +481,9 @@ template <typename T, int METRIC>
 __global__ void __launch_bounds__(HN_THREADS) hnsw_arrange_kernel(const HnswArrangeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     float* rs = reinterpret_cast<float*>(smem);  // row of the target
-    float* xs = rs + p.dimpad;                   // row of the candidate under test
+    float* xs = rs + p.dimpad;                   // one staging row per warp for the candidates under test
     __shared__ uint32_t lk[HN_MAX_M0 + 1], kept[HN_MAX_M0 + 1];
     __shared__ uint64_t keys[HN_MAX_M0 + 1], sorted[HN_MAX_M0 + 1];
-    __shared__ int flag;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x;
     if (g >= p.ngroups) return;
@@ -495,7 +519,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_arrange_kernel(const HnswArra
             sorted[rank] = k;
         }
         __syncthreads();
-        len = heuristic_select<T, METRIC>(rows, p.pitch, p.dim, p.dimpad, p.rcache, sorted, cnt, limit, xs, kept, &flag);
+        len = heuristic_select<T, METRIC>(rows, p.pitch, p.dim, p.dimpad, p.rcache, sorted, cnt, limit, xs, kept);
         for (uint32_t j = threadIdx.x; j < len; j += blockDim.x) lk[j] = kept[j];
         __syncthreads();
     }
@@ -735,7 +759,7 @@ static void hnsw_insert_range(vdb_hnsw* h, const vdb_dataset* ds, uint64_t first
             sl.selcnt = d_selcnt.as<uint32_t>();
             {
                 ProfScope prof("hnsw_select", st);
-                const size_t smem = (size_t)dimpad * 4;
+                const size_t smem = (size_t)HN_WARPS * dimpad * 4;  // one staging row per warp
                 if (ds->dtype == VDB_F32) {
                     if (l2) launch_dyn(hnsw_select_kernel<float, VDB_L2SQR>, ntasks, smem, sl, st);
                     else launch_dyn(hnsw_select_kernel<float, VDB_COSINE>, ntasks, smem, sl, st);
@@ -790,7 +814,7 @@ static void hnsw_insert_range(vdb_hnsw* h, const vdb_dataset* ds, uint64_t first
                 ap.grp_off = d_go.as<uint32_t>();
                 ap.inc = d_inc.as<uint32_t>();
                 ProfScope prof("hnsw_arrange", st);
-                const size_t smem = (size_t)dimpad * 8;
+                const size_t smem = (size_t)(1 + HN_WARPS) * dimpad * 4;
                 if (ds->dtype == VDB_F32) {
                     if (l2) launch_dyn(hnsw_arrange_kernel<float, VDB_L2SQR>, ng, smem, ap, st);
                     else launch_dyn(hnsw_arrange_kernel<float, VDB_COSINE>, ng, smem, ap, st);
