@@ -16,14 +16,21 @@ def test_concurrent_searches_on_one_handle(fixtures):
     flat = V.FlatIndex.from_vec_set(base, "l2sqr")
     cent = np.ascontiguousarray(base[:16])
     ivf = V.IVFIndex(flat.vec_set, cent)
-    serial = [(flat.knn_batch(q, 7), flat.knn_batch(q[:3], 7), ivf.knn_with_ef_batch(q, 7, 4)) for q in queries]
+    books = np.concatenate([np.ascontiguousarray(base[100:116, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(64, 16)])
+    pq = V.PQTable(flat.vec_set, V.PQConfig(4, 16, "l2sqr"), books)          # batches of 40: tensor-core ADC filter
+    hnsw = V.HNSWIndex(flat.vec_set, V.HNSWConfig(0, 40, 8), rng)
+
+    def all_searches(q):
+        return (flat.knn_batch(q, 7), flat.knn_batch(q[:3], 7), ivf.knn_with_ef_batch(q, 7, 4),
+                flat.knn_pq_batch(q, 7, 60, pq), hnsw.knn_with_ef_batch(q, 7, 30), hnsw.knn_pq_batch(q, 7, 30, pq))
+
+    serial = [all_searches(q) for q in queries]
     out, errs = [None] * 8, []
 
     def work(i):
         try:
             for _ in range(3):
-                out[i] = (flat.knn_batch(queries[i], 7), flat.knn_batch(queries[i][:3], 7),
-                          ivf.knn_with_ef_batch(queries[i], 7, 4))
+                out[i] = all_searches(queries[i])
         except Exception as e:  # noqa: BLE001
             errs.append(e)
 
