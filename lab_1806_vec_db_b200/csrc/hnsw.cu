@@ -20,6 +20,7 @@
 // The graph itself is unpinned in the reference (RNG levels, thread count dependent batches), so parity is by
 // recall; the distances returned by a search are re-evaluated by the cached-form pair kernel (pairs.cu, K10).
 #include <algorithm>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 
@@ -540,7 +541,10 @@ __global__ void iota_pairs_kernel(const uint64_t* __restrict__ keys, uint32_t nq
 
 // ---- host side -----------------------------------------------------------------------------------------------------
 // visited-set capacity: a search visits ~10-15 nodes per expansion; beyond 7/8 full further neighbours are ignored
-static uint32_t hash_cap_for(uint32_t ef) { return ef <= 256 ? 8192u : (ef <= 640 ? 16384u : 32768u); }
+static uint32_t hash_cap_for(uint32_t ef) {
+    static const uint32_t small_to = getenv("VDB_HNSW_SMALL_HASH_EF") ? (uint32_t)atoi(getenv("VDB_HNSW_SMALL_HASH_EF")) : 448u;
+    return ef <= small_to ? 8192u : (ef <= 640 ? 16384u : 32768u);
+}
 
 template <typename KernT, typename ParamT>
 static void launch_dyn(KernT kern, uint32_t grid, size_t smem, const ParamT& p, cudaStream_t st) {
