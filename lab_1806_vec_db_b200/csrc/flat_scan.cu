@@ -42,9 +42,14 @@ __device__ __forceinline__ float4 u4_as_f4(const uint4& u) {
     return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
                        __uint_as_float(u.w));
 }
+// u8 -> f32 without the quarter-rate I2F: 0x4B0000bb is the float 8388608 + bb, so one PRMT and one FADD (both full
+// rate) give the exact value; the u8 scan was conversion bound (0.355 ms per 0.96 GB pass)
 __device__ __forceinline__ float4 bytes_as_f4(uint32_t w) {
-    return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu),
-                       (float)(w >> 24));
+    const float magic = 8388608.0f;
+    return make_float4(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - magic,
+                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - magic,
+                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - magic,
+                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - magic);
 }
 __device__ __forceinline__ uint32_t u4_comp(const uint4& u, int i) {
     return i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w));
