@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "dataset.cuh"
+#include "scanmath.cuh"
 #include "topk.cuh"
 
 namespace vdb {
@@ -38,23 +39,6 @@ struct ScanParams {
     uint64_t* partial;     // [NQ][gridDim.x][K]
 };
 
-__device__ __forceinline__ float4 u4_as_f4(const uint4& u) {
-    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
-                       __uint_as_float(u.w));
-}
-// u8 -> f32 without the quarter-rate I2F: 0x4B0000bb is the float 8388608 + bb, so one PRMT and one FADD (both full
-// rate) give the exact value; the u8 scan was conversion bound (0.355 ms per 0.96 GB pass)
-__device__ __forceinline__ float4 bytes_as_f4(uint32_t w) {
-    const float magic = 8388608.0f;
-    return make_float4(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - magic,
-                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - magic,
-                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - magic,
-                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - magic);
-}
-__device__ __forceinline__ uint32_t u4_comp(const uint4& u, int i) {
-    return i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w));
-}
-
 // PL = 1: f32 rows (4 elements per 16-byte load); PL = 4: u8 rows (16 elements per load)
 template <int NQ, int R, int METRIC, int PL>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanParams p) {
@@ -65,13 +49,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t qs4 = p.qstride >> 2;  // float4 per query
     const uint32_t plane4 = p.nit * 32;   // float4 per plane
+    // u8 rows, L2Sqr: rows and queries both carry the 2^23 conversion bias (queries of a u8 set are u8 values, so
+    // q + 2^23 and the difference of the biased values are exact) - see row_pairs in scanmath.cuh
+    constexpr bool BIASED = PL == 4 && METRIC == VDB_L2SQR;
     float4* qs = reinterpret_cast<float4*>(smem);
+    const ulonglong2* qs2 = reinterpret_cast<const ulonglong2*>(smem);
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)NQ * p.qstride * 4);
     TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
 
-    for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x)
-        qs[i] = (i / qs4 < p.nq_valid) ? reinterpret_cast<const float4*>(p.q)[i]
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x) {
+        float4 v = (i / qs4 < p.nq_valid) ? reinterpret_cast<const float4*>(p.q)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BIASED) v = make_float4(v.x + U8_BIAS, v.y + U8_BIAS, v.z + U8_BIAS, v.w + U8_BIAS);
+        qs[i] = v;
+    }
     topk.init();
 
     const int pidx = lane >> SH;
@@ -81,82 +71,89 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     if (METRIC == VDB_COSINE && my_q < (int)p.nq_valid) qn = p.qcache[my_q];
 
     const uint64_t total_warps = (uint64_t)gridDim.x * SCAN_WARPS;
-    uint64_t g = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
     const uint64_t last_row = p.n - 1;
 
-    uint4 nxt[R], cur[R];
-    auto prefetch = [&](uint64_t gg, uint32_t it) {
-        const uint32_t c = it * 32 + lane;
-        const bool in = c < p.nvec;
+    // The (row group, 512-byte chunk) steps of a warp form one flat sequence; step t is computed from register buffer
+    // t & 1 while the loads of step t + 1 land in the other buffer, so nothing is copied between buffers and the
+    // prefetch runs across group boundaries. Addressing is incremental: one pointer per lane, rows of the group at
+    // r * pitch from it; the clamped (last group) and ragged (row end inside the last chunk) cases take a slow path.
+    constexpr bool SINGLE = PL == 4 && NQ >= 4;  // measured: only the u8 variants gain (0.98 -> 0.89 ms at 8 queries)
+    uint4 bufA[R], bufB[SINGLE ? 1 : R];
+    const uint32_t tail_lanes = p.nvec - (p.nit - 1) * 32;  // lanes with data in a row's last chunk (1..32)
+    uint64_t pg = (uint64_t)blockIdx.x * SCAN_WARPS + warp;  // group being prefetched
+    uint32_t pit = 0;                                        // its chunk iteration
+    const uint8_t* pptr = nullptr;
+    bool pclamp = false;
+    auto issue = [&](uint4 (&dst)[R]) {
+        if (pit == 0) {
+            const uint64_t row0 = pg * R;
+            pclamp = row0 + (R - 1) > last_row;
+            pptr = p.rows + (row0 < last_row ? row0 : last_row) * p.pitch_bytes + (size_t)lane * 16;
+        }
+        if (!pclamp && (pit + 1 < p.nit || tail_lanes == 32)) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            uint64_t row = gg * R + r;
-            row = row < last_row ? row : last_row;
-            nxt[r] = in ? ldg_stream_u4(p.rows + row * p.pitch_bytes + (size_t)c * 16)
-                        : make_uint4(0u, 0u, 0u, 0u);
+            for (int r = 0; r < R; ++r) dst[r] = ldg_stream_u4(pptr + (size_t)r * p.pitch_bytes);
+        } else {
+            const bool in = pit + 1 < p.nit || (uint32_t)lane < tail_lanes;
+            const uint64_t row0 = pg * R;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint64_t row = row0 + r < last_row ? row0 + r : last_row;
+                dst[r] = in ? ldg_stream_u4(p.rows + row * p.pitch_bytes + ((size_t)pit * 32 + lane) * 16)
+                            : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        pptr += 512;
+        if (++pit == p.nit) {
+            pit = 0;
+            pg += total_warps;
         }
     };
 
+    f32x2 acc2[V], xx2[R];  // (even, odd) partial sums, see scanmath.cuh
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc2[i] = 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r) xx2[r] = 0ull;
+    uint64_t g = pg;   // group being computed
+    uint32_t it = 0, gi = 0;
+    const ulonglong2* qp = qs2 + lane;  // this lane's chunk of query 0, plane 0
     bool want = false;
-    prefetch(g, 0);
-    for (uint32_t gi = 0; gi < p.iters; ++gi, g += total_warps) {
-        float acc[V];
-        float xx[R];
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = 0.f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) xx[r] = 0.f;
 
-        for (uint32_t it = 0; it < p.nit; ++it) {
+    auto accumulate = [&](const uint4 (&cur)[R]) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) cur[r] = nxt[r];
-            if (it + 1 < p.nit) prefetch(g, it + 1);
-            else if (gi + 1 < p.iters) prefetch(g + total_warps, 0);
-            const uint32_t c = it * 32 + lane;
+        for (int pl = 0; pl < PL; ++pl) {
+            f32x2 x01[R], x23[R];
 #pragma unroll
-            for (int pl = 0; pl < PL; ++pl) {
-                float4 x[R];
+            for (int r = 0; r < R; ++r) row_pairs<PL, BIASED>(cur[r], pl, x01[r], x23[r]);
+            if (METRIC == VDB_COSINE) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) xx2[r] = chunk_acc<false>(xx2[r], x01[r], x23[r], x01[r], x23[r]);
+            }
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                const ulonglong2 q = qp[(size_t)qi * qs4 + (size_t)pl * plane4];
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    {
-                    if constexpr (PL == 1) x[r] = u4_as_f4(cur[r]);
-                    else x[r] = bytes_as_f4(u4_comp(cur[r], pl));
-                }
-                if (METRIC == VDB_COSINE) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        xx[r] = fmaf(x[r].x, x[r].x, xx[r]);
-                        xx[r] = fmaf(x[r].y, x[r].y, xx[r]);
-                        xx[r] = fmaf(x[r].z, x[r].z, xx[r]);
-                        xx[r] = fmaf(x[r].w, x[r].w, xx[r]);
-                    }
-                }
-#pragma unroll
-                for (int qi = 0; qi < NQ; ++qi) {
-                    const float4 q = qs[(size_t)qi * qs4 + (size_t)pl * plane4 + c];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float a = acc[r * NQ + qi];
-                        if (METRIC == VDB_L2SQR) {
-                            const float d0 = x[r].x - q.x, d1 = x[r].y - q.y, d2 = x[r].z - q.z,
-                                        d3 = x[r].w - q.w;
-                            a = fmaf(d0, d0, a);
-                            a = fmaf(d1, d1, a);
-                            a = fmaf(d2, d2, a);
-                            a = fmaf(d3, d3, a);
-                        } else {
-                            a = fmaf(x[r].x, q.x, a);
-                            a = fmaf(x[r].y, q.y, a);
-                            a = fmaf(x[r].z, q.z, a);
-                            a = fmaf(x[r].w, q.w, a);
-                        }
-                        acc[r * NQ + qi] = a;
-                    }
-                }
+                    acc2[r * NQ + qi] = chunk_acc<METRIC == VDB_L2SQR>(acc2[r * NQ + qi], x01[r], x23[r], q.x, q.y);
             }
         }
-
-        // cross-lane reduction: lane L now holds the total of (row my_r, query my_q)
+        qp += 32;
+    };
+    auto finish = [&]() {
+        if (++it < p.nit) return;
+        // ---- end of a row group: cross-lane reduction, lane L then holds the total of (row my_r, query my_q) ----
+        float acc[V], xx[R];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            acc[i] = sum2(acc2[i]);
+            acc2[i] = 0ull;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            xx[r] = sum2(xx2[r]);
+            xx2[r] = 0ull;
+        }
         float tot = warp_reduce_scatter<V>(acc, lane);
         if (METRIC == VDB_COSINE) {
             const float xs = warp_reduce_scatter<R>(xx, lane);
@@ -171,6 +168,33 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
         if ((gi + 1) % p.sync_every == 0) {
             topk.maybe_flush(want);
             want = false;
+        }
+        it = 0;
+        ++gi;
+        g += total_warps;
+        qp = qs2 + lane;
+    };
+
+    const uint32_t steps = p.iters * p.nit;  // identical for every warp of the CTA (the flush barriers rely on it)
+    if (steps) issue(bufA);
+    if constexpr (SINGLE) {
+        // FP32-bound variants: one register buffer, reloaded as soon as the step's arithmetic has consumed it; the
+        // other warps of the scheduler cover the load latency, and the registers of a second buffer go to the schedule
+        for (uint32_t t = 0; t < steps; ++t) {
+            accumulate(bufA);
+            if (t + 1 < steps) issue(bufA);
+            finish();
+        }
+    } else {
+        for (uint32_t t = 0; t < steps; t += 2) {
+            if (t + 1 < steps) issue(bufB);
+            accumulate(bufA);
+            finish();
+            if (t + 1 < steps) {
+                if (t + 2 < steps) issue(bufA);
+                accumulate(bufB);
+                finish();
+            }
         }
     }
     topk.final_flush();

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "index.cuh"
+#include "scanmath.cuh"
 #include "topk.cuh"
 
 namespace vdb {
@@ -40,13 +41,6 @@ struct IvfScanParams {
     uint64_t* partial;       // [nq][splits][K]
 };
 
-__device__ __forceinline__ float4 ivf_u4_as_f4(const uint4& u) {
-    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
-}
-__device__ __forceinline__ float4 ivf_bytes_as_f4(uint32_t w) {
-    return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu), (float)(w >> 24));
-}
-
 template <int METRIC, int PL>
 __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -55,6 +49,7 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t qs4 = p.qstride >> 2, plane4 = p.nit * 32;
     float4* qs = reinterpret_cast<float4*>(smem);
+    const ulonglong2* qs2 = reinterpret_cast<const ulonglong2*>(smem);
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)p.qstride * 4);
     TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + p.P), p.K, p.P, 1, p.limit};
     uint32_t* pre = reinterpret_cast<uint32_t*>(tk + p.P) + 4;  // [nprobe+1] prefix of probed list lengths
@@ -101,9 +96,9 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
             }
             rid[r] = id;
         }
-        float acc[R], xx[R];
+        f32x2 acc2[R], xx2[R];  // (even, odd) chains of scanmath.cuh: the streaming scan's distance bits
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f, xx[r] = 0.f;
+        for (int r = 0; r < R; ++r) acc2[r] = 0ull, xx2[r] = 0ull;
         if (active) {
             for (uint32_t it = 0; it < p.nit; ++it) {
                 const uint32_t c = it * 32 + lane;
@@ -115,32 +110,20 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
                                : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int pl = 0; pl < PL; ++pl) {
-                    const float4 qv = qs[(size_t)pl * plane4 + c];
+                    const ulonglong2 qv = qs2[(size_t)pl * plane4 + c];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        float4 x;
-                        if constexpr (PL == 1) x = ivf_u4_as_f4(v[r]);
-                        else x = ivf_bytes_as_f4(pl == 0 ? v[r].x : (pl == 1 ? v[r].y : (pl == 2 ? v[r].z : v[r].w)));
-                        if (METRIC == VDB_L2SQR) {
-                            const float d0 = x.x - qv.x, d1 = x.y - qv.y, d2 = x.z - qv.z, d3 = x.w - qv.w;
-                            acc[r] = fmaf(d0, d0, acc[r]);
-                            acc[r] = fmaf(d1, d1, acc[r]);
-                            acc[r] = fmaf(d2, d2, acc[r]);
-                            acc[r] = fmaf(d3, d3, acc[r]);
-                        } else {
-                            acc[r] = fmaf(x.x, qv.x, acc[r]);
-                            acc[r] = fmaf(x.y, qv.y, acc[r]);
-                            acc[r] = fmaf(x.z, qv.z, acc[r]);
-                            acc[r] = fmaf(x.w, qv.w, acc[r]);
-                            xx[r] = fmaf(x.x, x.x, xx[r]);
-                            xx[r] = fmaf(x.y, x.y, xx[r]);
-                            xx[r] = fmaf(x.z, x.z, xx[r]);
-                            xx[r] = fmaf(x.w, x.w, xx[r]);
-                        }
+                        f32x2 x01, x23;
+                        row_pairs<PL, false>(v[r], pl, x01, x23);
+                        acc2[r] = chunk_acc<METRIC == VDB_L2SQR>(acc2[r], x01, x23, qv.x, qv.y);
+                        if (METRIC == VDB_COSINE) xx2[r] = chunk_acc<false>(xx2[r], x01, x23, x01, x23);
                     }
                 }
             }
         }
+        float acc[R], xx[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = sum2(acc2[r]), xx[r] = sum2(xx2[r]);
         float tot = warp_reduce_scatter<R>(acc, lane);  // lane L holds row L >> 2
         if (METRIC == VDB_COSINE) {
             const float xs = warp_reduce_scatter<R>(xx, lane);
@@ -201,6 +184,7 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t qs4 = p.qstride >> 2, plane4 = p.nit * 32;
     float4* qs = reinterpret_cast<float4*>(smem);
+    const ulonglong2* qs2 = reinterpret_cast<const ulonglong2*>(smem);
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)NQ * p.qstride * 4);
     TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
     for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x) {
@@ -227,11 +211,11 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
             const uint32_t pos = g * R + r;
             rid[r] = pos < item.nrows ? mem[pos] : 0xffffffffu;
         }
-        float acc[V], xx[R];
+        f32x2 acc2[V], xx2[R];
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        for (int i = 0; i < V; ++i) acc2[i] = 0ull;
 #pragma unroll
-        for (int r = 0; r < R; ++r) xx[r] = 0.f;
+        for (int r = 0; r < R; ++r) xx2[r] = 0ull;
         if (g < groups) {
             uint4 nxt[R], cur[R];
             auto load = [&](uint32_t it) {
@@ -250,45 +234,28 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
                 const uint32_t c = it * 32 + lane;
 #pragma unroll
                 for (int pl = 0; pl < PL; ++pl) {
-                    float4 x[R];
+                    f32x2 x01[R], x23[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if constexpr (PL == 1) x[r] = ivf_u4_as_f4(cur[r]);
-                        else x[r] = ivf_bytes_as_f4(pl == 0 ? cur[r].x : (pl == 1 ? cur[r].y : (pl == 2 ? cur[r].z : cur[r].w)));
-                    }
+                    for (int r = 0; r < R; ++r) row_pairs<PL, false>(cur[r], pl, x01[r], x23[r]);
                     if (METRIC == VDB_COSINE) {
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            xx[r] = fmaf(x[r].x, x[r].x, xx[r]);
-                            xx[r] = fmaf(x[r].y, x[r].y, xx[r]);
-                            xx[r] = fmaf(x[r].z, x[r].z, xx[r]);
-                            xx[r] = fmaf(x[r].w, x[r].w, xx[r]);
-                        }
+                        for (int r = 0; r < R; ++r) xx2[r] = chunk_acc<false>(xx2[r], x01[r], x23[r], x01[r], x23[r]);
                     }
 #pragma unroll
                     for (int qi = 0; qi < NQ; ++qi) {
-                        const float4 qv = qs[(size_t)qi * qs4 + (size_t)pl * plane4 + c];
+                        const ulonglong2 qv = qs2[(size_t)qi * qs4 + (size_t)pl * plane4 + c];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            float a = acc[r * NQ + qi];
-                            if (METRIC == VDB_L2SQR) {
-                                const float d0 = x[r].x - qv.x, d1 = x[r].y - qv.y, d2 = x[r].z - qv.z, d3 = x[r].w - qv.w;
-                                a = fmaf(d0, d0, a);
-                                a = fmaf(d1, d1, a);
-                                a = fmaf(d2, d2, a);
-                                a = fmaf(d3, d3, a);
-                            } else {
-                                a = fmaf(x[r].x, qv.x, a);
-                                a = fmaf(x[r].y, qv.y, a);
-                                a = fmaf(x[r].z, qv.z, a);
-                                a = fmaf(x[r].w, qv.w, a);
-                            }
-                            acc[r * NQ + qi] = a;
-                        }
+                        for (int r = 0; r < R; ++r)
+                            acc2[r * NQ + qi] = chunk_acc<METRIC == VDB_L2SQR>(acc2[r * NQ + qi], x01[r], x23[r], qv.x, qv.y);
                     }
                 }
             }
         }
+        float acc[V], xx[R];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = sum2(acc2[i]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) xx[r] = sum2(xx2[r]);
         float tot = warp_reduce_scatter<V>(acc, lane);
         if (METRIC == VDB_COSINE) {
             const float xs = warp_reduce_scatter<R>(xx, lane);

@@ -6,6 +6,7 @@
 //   DistanceAdapter<(&[T],f32),(&[T],f32)>        src/distance/mod.rs:120-129 (cached forms :54-57, :67-69)
 //   DistanceAlgorithm::dist_cache                 src/distance/mod.rs:31-36
 #include "dataset.cuh"
+#include "scanmath.cuh"
 
 namespace vdb {
 
@@ -46,13 +47,14 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
         const TB* b = (const TB*)p.B + ib * p.strideB;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         if (MODE == PM_L2_SCANORDER || MODE == PM_COS_SCANORDER) {
-            // same per-lane element order (float4 chunk c = it*32 + lane) and the same xor-butterfly as the
-            // streaming scan kernel (flat_scan.cu), so both Flat paths return bit-identical distances
+            // same per-lane chains (float4 chunk c = it*32 + lane, even / odd elements, see scanmath.cuh) and the same
+            // xor-butterfly as the streaming scan kernel (flat_scan.cu), so both Flat paths return bit-identical distances
             if (p.vec4) {
                 // 128-bit loads, 8 row chunks in flight per lane before the first use
                 const uint32_t nvec = p.dim >> 2;
                 const float4* a4 = reinterpret_cast<const float4*>(a);
                 const float4* b4 = reinterpret_cast<const float4*>(b);
+                f32x2 t0 = 0ull, t1 = 0ull;
                 for (uint32_t c0 = 0; c0 < nvec; c0 += 256) {
                     float4 xb[8];
 #pragma unroll
@@ -65,40 +67,33 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
                         const uint32_t c = c0 + u * 32 + lane;
                         if (c < nvec) {
                             const float4 q = __ldg(a4 + c);
+                            const f32x2 x01 = pk2f(xb[u].x, xb[u].y), x23 = pk2f(xb[u].z, xb[u].w);
+                            const f32x2 q01 = pk2f(q.x, q.y), q23 = pk2f(q.z, q.w);
+                            t0 = chunk_acc<MODE == PM_L2_SCANORDER>(t0, x01, x23, q01, q23);
+                            if (MODE == PM_COS_SCANORDER) t1 = chunk_acc<false>(t1, x01, x23, x01, x23);
+                        }
+                    }
+                }
+                s0 = sum2(t0);
+                s1 = sum2(t1);
+            } else {
+                ScalarChains c0, c1;
+                for (uint32_t c = lane; c * p.chunk < p.dim; c += 32) {
+                    for (uint32_t i = 0; i < p.chunk; ++i) {
+                        const uint32_t e = c * p.chunk + i;
+                        if (e < p.dim) {
+                            const float xv = (float)b[e], qv = (float)a[e];
                             if (MODE == PM_L2_SCANORDER) {
-                                const float d0 = xb[u].x - q.x, d1 = xb[u].y - q.y, d2 = xb[u].z - q.z, d3 = xb[u].w - q.w;
-                                s0 = fmaf(d0, d0, s0);
-                                s0 = fmaf(d1, d1, s0);
-                                s0 = fmaf(d2, d2, s0);
-                                s0 = fmaf(d3, d3, s0);
+                                c0.l2(e, xv, qv);
                             } else {
-                                s0 = fmaf(xb[u].x, q.x, s0);
-                                s0 = fmaf(xb[u].y, q.y, s0);
-                                s0 = fmaf(xb[u].z, q.z, s0);
-                                s0 = fmaf(xb[u].w, q.w, s0);
-                                s1 = fmaf(xb[u].x, xb[u].x, s1);
-                                s1 = fmaf(xb[u].y, xb[u].y, s1);
-                                s1 = fmaf(xb[u].z, xb[u].z, s1);
-                                s1 = fmaf(xb[u].w, xb[u].w, s1);
+                                c0.dot(e, xv, qv);
+                                c1.dot(e, xv, xv);
                             }
                         }
                     }
                 }
-            } else
-            for (uint32_t c = lane; c * p.chunk < p.dim; c += 32) {
-                for (uint32_t i = 0; i < p.chunk; ++i) {
-                    const uint32_t e = c * p.chunk + i;
-                    if (e < p.dim) {
-                        const float xv = (float)b[e], qv = (float)a[e];
-                        if (MODE == PM_L2_SCANORDER) {
-                            const float d = xv - qv;
-                            s0 = fmaf(d, d, s0);
-                        } else {
-                            s0 = fmaf(xv, qv, s0);
-                            s1 = fmaf(xv, xv, s1);
-                        }
-                    }
-                }
+                s0 = c0.total();
+                s1 = c1.total();
             }
         } else
         for (uint32_t e = lane; e < p.dim; e += 32) {

@@ -1,0 +1,128 @@
+// scanmath.cuh — the per-lane arithmetic of every "scan order" distance kernel (K1 flat_scan, K9 ivf scans, the
+// K2b rerank in pairs.cu), written with Blackwell's packed FP32 instructions.
+//
+// On sm_100a a 3-register scalar FFMA/FADD issues every other cycle per scheduler, FFMA2/FADD2 (PTX
+// fma/add/sub.rn.f32x2 on a 64-bit register pair) do two lanes' worth per issue: the scan kernels were FP32-issue
+// bound from 4 queries per row byte up, the packed forms halve their instruction count.
+//
+// Summation order (shared by all of these kernels, which is why the tensor-core path's rerank and the IVF probe
+// scans return the streaming scan's distance BITS): a lane owns the 4-element chunks c = it*32 + lane of a row
+// (16-element chunks for u8 rows, walked as four 4-element sub-chunks); inside a chunk the elements 0 and 2 go
+// to the EVEN chain, 1 and 3 to the ODD chain, each chain an fma sequence in chunk order; the lane's total is
+// even + odd; lanes are combined by the xor butterfly (warp_reduce_scatter pairs partners the same way).
+// Each half of a packed instruction is an IEEE fma/add, so a scalar kernel that follows the same two chains
+// produces the same bits (pairs.cu does for unaligned / u8 operands).
+#pragma once
+#include "common.cuh"
+
+namespace vdb {
+
+typedef unsigned long long f32x2;  // two f32 in one 64-bit register pair: {lo = even element, hi = odd element}
+
+__device__ __forceinline__ f32x2 pk2(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2f(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+constexpr float U8_BIAS = 8388608.0f;  // 2^23: 0x4B0000bb is the float 2^23 + bb
+
+__device__ __forceinline__ uint32_t u4_word(const uint4& u, int i) {
+    return i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w));
+}
+
+// One 16-byte load of a row -> the (x0,x1), (x2,x3) pairs of 4-element sub-chunk `pl`.
+// PL = 1: f32 rows (pl = 0). PL = 4: u8 rows, byte -> f32 without the quarter-rate I2F: one PRMT builds the bit
+// pattern of 2^23 + byte; BIASED keeps that bias (the caller's query values carry the same bias, so the L2
+// difference is exact and the conversion costs nothing), otherwise one packed subtract removes it.
+template <int PL, bool BIASED>
+__device__ __forceinline__ void row_pairs(const uint4& u, int pl, f32x2& x01, f32x2& x23) {
+    if constexpr (PL == 1) {
+        x01 = pk2(u.x, u.y);
+        x23 = pk2(u.z, u.w);
+    } else {
+        const uint32_t w = u4_word(u, pl);
+        x01 = pk2(__byte_perm(w, 0x4B000000u, 0x7650), __byte_perm(w, 0x4B000000u, 0x7651));
+        x23 = pk2(__byte_perm(w, 0x4B000000u, 0x7652), __byte_perm(w, 0x4B000000u, 0x7653));
+        if constexpr (!BIASED) {
+            const f32x2 m = pk2f(U8_BIAS, U8_BIAS);
+            x01 = sub2(x01, m);
+            x23 = sub2(x23, m);
+        }
+    }
+}
+
+// a += the chunk's contribution: L2Sqr -> (x - q)^2, otherwise x * q
+template <bool L2>
+__device__ __forceinline__ f32x2 chunk_acc(f32x2 a, f32x2 x01, f32x2 x23, f32x2 q01, f32x2 q23) {
+    if constexpr (L2) {
+        const f32x2 d01 = sub2(x01, q01), d23 = sub2(x23, q23);
+        a = fma2(d01, d01, a);
+        a = fma2(d23, d23, a);
+    } else {
+        a = fma2(x01, q01, a);
+        a = fma2(x23, q23, a);
+    }
+    return a;
+}
+
+// the two chains of chunk_acc with scalar instructions on a float2 (x = even chain, y = odd chain): bit-identical.
+// For the FP32-bound variants (4 and 8 queries per row byte) the scalar forms are faster: measured on B200, FFMA2 and
+// FADD2 have the lane throughput of the scalar instructions (128 lane-ops/clk/SM either way,
+// scripts/ubench/fp32_rate.cu) but the 8-query scan ran 10 % slower with them.
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+template <bool L2>
+__device__ __forceinline__ float2 chunk_acc_s(float2 a, const float4& x, const float4& q) {
+    if constexpr (L2) {
+        const float d0 = x.x - q.x, d1 = x.y - q.y, d2 = x.z - q.z, d3 = x.w - q.w;
+        a.x = fmaf(d0, d0, a.x);
+        a.y = fmaf(d1, d1, a.y);
+        a.x = fmaf(d2, d2, a.x);
+        a.y = fmaf(d3, d3, a.y);
+    } else {
+        a.x = fmaf(x.x, q.x, a.x);
+        a.y = fmaf(x.y, q.y, a.y);
+        a.x = fmaf(x.z, q.z, a.x);
+        a.y = fmaf(x.w, q.w, a.y);
+    }
+    return a;
+}
+
+// the same two chains element by element (element parity picks the chain); bit-identical to chunk_acc
+struct ScalarChains {
+    float even = 0.f, odd = 0.f;
+    __device__ __forceinline__ void l2(uint32_t e, float x, float q) {
+        const float d = x - q;
+        if (e & 1) odd = fmaf(d, d, odd);
+        else even = fmaf(d, d, even);
+    }
+    __device__ __forceinline__ void dot(uint32_t e, float x, float q) {
+        if (e & 1) odd = fmaf(x, q, odd);
+        else even = fmaf(x, q, even);
+    }
+    __device__ __forceinline__ float total() const { return even + odd; }
+};
+
+}  // namespace vdb

@@ -16,7 +16,10 @@ ds = V.DeviceVecSet.from_device(base.data_ptr(), n, dim, dim, np.float32, os.env
 lib = L.lib()
 L.check(lib.vdb_flat_set_path(1))
 stream = torch.cuda.current_stream().cuda_stream
-for nq, k in [(1, 10), (2, 10), (4, 10), (8, 10), (8, 100), (1, 100), (16, 10), (64, 100)]:
+cases = [(1, 10), (2, 10), (4, 10), (8, 10), (8, 100), (1, 100), (16, 10), (64, 100)]
+if os.environ.get("CASES"):  # e.g. CASES=8:10,4:10
+    cases = [tuple(int(v) for v in c.split(":")) for c in os.environ["CASES"].split(",")]
+for nq, k in cases:
     q = torch.rand((nq, dim), device=dev, generator=g)
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev); dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
     cnt = torch.empty(nq, dtype=torch.int32, device=dev)
