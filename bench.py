@@ -201,11 +201,12 @@ def run_reference(args):
         "impl": "reference", "metric": "QPS, exact Flat L2 kNN", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Flat L2Sqr exact kNN, synthetic GIST-shaped {args.n}x{DIM} f32, k={args.k} "
-                               f"(configs[1]); CPU step = {nqs}-query sample of the 10000-query batch",
-                   "n": args.n, "dim": DIM, "k": args.k, "nq_per_step": nqs},
+        # the GPU arm's config (same workload, same keys); the bounded CPU sample is described under cpu_baseline
+        "config": {"workload": f"Flat L2Sqr exact kNN, synthetic GIST-shaped {args.n}x{DIM} f32, "
+                               f"{args.nq}-query batch, k={args.k} (configs[1])",
+                   "n": args.n, "dim": DIM, "nq": args.nq, "k": args.k, "cpu_sample_queries_per_step": nqs},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": f"{nqs} queries x {args.n} rows per step, thread pool over queries "
+                         "sample": f"{nqs} of the {args.nq} queries x {args.n} rows per step, thread pool over queries "
                                    "(examples/bench.rs -t protocol); C++ restatement of the Rust path, "
                                    "sequential f32, -O3 -ffp-contract=off"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -401,8 +402,9 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"Flat L2Sqr exact kNN, synthetic GIST-shaped {args.n}x{DIM} f32, "
-                               f"{args.nq}-query batch, k={args.k} (configs[1]), rows sharded over {world} GPU(s)",
+                               f"{args.nq}-query batch, k={args.k} (configs[1])",
                    "n": args.n, "dim": DIM, "nq": args.nq, "k": args.k, "path": args.path,
+                   "sharding": f"rows in {world} contiguous block(s), one per GPU",
                    "l2_policy": "inputs (3.84 GB per pass) larger than the 126 MB L2"},
         "e2e": {"value": args.nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": args.nq * DIM * 4,
                 "d2h_bytes_per_step": args.nq * args.k * 12 + args.nq * 4, "ms_per_step": e2e_s * 1e3,

@@ -1,9 +1,13 @@
 // scanmath.cuh — the per-lane arithmetic of every "scan order" distance kernel (K1 flat_scan, K9 ivf scans, the
 // K2b rerank in pairs.cu), written with Blackwell's packed FP32 instructions.
 //
-// On sm_100a a 3-register scalar FFMA/FADD issues every other cycle per scheduler, FFMA2/FADD2 (PTX
-// fma/add/sub.rn.f32x2 on a 64-bit register pair) do two lanes' worth per issue: the scan kernels were FP32-issue
-// bound from 4 queries per row byte up, the packed forms halve their instruction count.
+// FFMA2/FADD2 (PTX fma/sub.rn.f32x2 on a 64-bit register pair) do two lanes' worth of FP32 work per issue slot.
+// Measured on B200 (scripts/ubench/fp32_rate.cu): scalar FFMA/FADD reach 1 warp instruction per clock and scheduler
+// = 128 lane-ops/clk/SM, the packed forms 0.5 per clock = the same 128 lane-ops/clk/SM. So they do not raise the FP32
+// ceiling, they free issue slots: the HBM-bound variants of the scan (1-2 queries per row byte, k = 100, cosine, u8
+// rows) gained 4-9 % with them, the FP32-bound 8-query variant did not (and pays for the second accumulator chain).
+// NB ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false, unlike the scalar forms, so the
+// bit-exact kernels (k-means assignment, PQ encode: rustc's unfused arithmetic) must not use them.
 //
 // Summation order (shared by all of these kernels, which is why the tensor-core path's rerank and the IVF probe
 // scans return the streaming scan's distance BITS): a lane owns the 4-element chunks c = it*32 + lane of a row
@@ -86,10 +90,8 @@ __device__ __forceinline__ f32x2 chunk_acc(f32x2 a, f32x2 x01, f32x2 x23, f32x2 
     return a;
 }
 
-// the two chains of chunk_acc with scalar instructions on a float2 (x = even chain, y = odd chain): bit-identical.
-// For the FP32-bound variants (4 and 8 queries per row byte) the scalar forms are faster: measured on B200, FFMA2 and
-// FADD2 have the lane throughput of the scalar instructions (128 lane-ops/clk/SM either way,
-// scripts/ubench/fp32_rate.cu) but the 8-query scan ran 10 % slower with them.
+// the two chains of chunk_acc with scalar instructions on a float2 (x = even chain, y = odd chain): bit-identical
+// (measured in the 8-query scan: same speed as the packed forms)
 __device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
