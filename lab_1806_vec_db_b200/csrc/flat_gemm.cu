@@ -491,8 +491,8 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
 static int gemm_ctas();
 // tiling of one pass: query-tile units x row slabs (small slabs, query tile fastest: the CTAs in flight share a few
 // row tiles and all query tiles in L2)
-static void plan_gemm(GemmParams& p) {
-    const uint32_t ctas = (uint32_t)gemm_ctas();
+static void plan_gemm(GemmParams& p, int ctas_sel = 0) {
+    const uint32_t ctas = (uint32_t)(ctas_sel ? ctas_sel : gemm_ctas());
     const uint32_t sms = (uint32_t)sm_count();
     p.ntiles = (uint32_t)ceil_div<uint64_t>(p.nrows, GN);
     p.nqt = ceil_div<uint32_t>(p.nq, GM * ctas);
@@ -712,6 +712,7 @@ struct vdb_tq {
     float kc = 0.f, cbound = 0.f;
     CUtensorMap mq;
     uint32_t cap = 0;
+    int ctas = 2;   // CTAs per work unit: pairs (M = 256 queries), single CTAs (M = 128) for batches of <= 128 queries
 };
 
 namespace vdb {
@@ -766,6 +767,10 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
             VDB_LAUNCHED();
         }
         tq->mq = make_map(tq->qround.as<float>(), dim, nq, (uint64_t)tq->qpitch * 4, GM);
+        // a batch that fits one 128-query tile runs on single CTAs: a CTA pair would spend half of its MMAs on padding
+        // (the pass is then HBM-bound on the TF32 copy of the rows instead of tensor-bound)
+        static const bool small_single = !(getenv("VDB_GEMM_SMALL_PAIRS") && atoi(getenv("VDB_GEMM_SMALL_PAIRS")));
+        tq->ctas = (small_single && nq <= (uint32_t)GM) ? 1 : gemm_ctas();
     } catch (...) {
         delete tq;
         throw;
@@ -797,24 +802,24 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     cudaStream_t st = tq->st;
     const uint64_t ns = ds->sample_n;
     VDB_REQUIRE(j >= 1 && j <= ns, "sample order statistic %u out of range (sample %llu)", j, (unsigned long long)ns);
-    const CUtensorMap ms = make_map(ds->d_sample, ds->dim, ns, (uint64_t)ds->pitch * 4, GN / gemm_ctas());
+    const CUtensorMap ms = make_map(ds->d_sample, ds->dim, ns, (uint64_t)ds->pitch * 4, GN / tq->ctas);
     GemmParams ps = base_params(tq);
     ps.nrows = ns;
     ps.row_stride = 1;
     ps.sqnorm = ds->d_sample_sq;
     ps.rnorm = ds->d_sample_rn;
-    plan_gemm(ps);
+    plan_gemm(ps, tq->ctas);
     if (j <= (uint32_t)G_TOPJ) {
         // the epilogue keeps each query's G_TOPJ smallest scores per slab in registers: nothing but
         // nq * nslabs * G_TOPJ keys ever reaches HBM
         DevBuf part((size_t)tq->nq * ps.nslabs * G_TOPJ * 8, st);
         ps.out_keys = part.as<uint64_t>();
-        launch_gemm(2, ds->metric, tq->mq, ms, ps, st);
+        launch_gemm(2, ds->metric, tq->mq, ms, ps, st, tq->ctas);
         launch_merge_keys(part.as<uint64_t>(), ps.nslabs, tq->nq, G_TOPJ, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
     } else {
         DevBuf skeys((size_t)tq->nq * ns * 8, st);
         ps.out_keys = skeys.as<uint64_t>();
-        launch_gemm(0, ds->metric, tq->mq, ms, ps, st);
+        launch_gemm(0, ds->metric, tq->mq, ms, ps, st, tq->ctas);
         launch_merge_keys(skeys.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
     }
 }
@@ -848,7 +853,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     DevBuf cand((size_t)nq * cap * 8, st);
     VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
     {
-        const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, (uint64_t)ds->pitch * 4, GN / gemm_ctas());
+        const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, (uint64_t)ds->pitch * 4, GN / tq->ctas);
         GemmParams pf = base_params(tq);
         pf.sqnorm = ds->d_sqnorm;
         pf.rnorm = ds->d_lo;
@@ -858,8 +863,8 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         pf.cand_cnt = tq->cnt.as<uint32_t>();
         pf.cand = cand.as<uint64_t>();
         pf.cap = cap;
-        plan_gemm(pf);
-        launch_gemm(1, ds->metric, tq->mq, mx, pf, st);
+        plan_gemm(pf, tq->ctas);
+        launch_gemm(1, ds->metric, tq->mq, mx, pf, st, tq->ctas);
     }
     // exact rerank of the candidates (compacted: only the valid pairs are touched)
     const uint64_t total = (uint64_t)nq * cap;  // capacity bound; the live count stays on the device

@@ -14,7 +14,7 @@ ds = V.DeviceVecSet.from_device(base.data_ptr(), n, DIM, DIM, np.float32, "l2sqr
 lib = L.lib()
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for k in (10, 100):
-    for nq in (8, 16, 32, 64, 128, 256, 512, 1024):
+    for nq in (4, 5, 6, 8, 12, 16, 32, 64, 128, 129, 256, 512, 1024):
         q = q_all[:nq].contiguous()
         ids = torch.empty((nq, k), dtype=torch.int64, device=dev); dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
         cnt = torch.empty(nq, dtype=torch.int32, device=dev)

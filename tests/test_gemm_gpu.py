@@ -106,10 +106,12 @@ def test_tensor_path_adversarial_ties_and_duplicates(oracle):
 
 
 @pytest.mark.parametrize("n,dim,nq,k", [(70_000, 12, 40, 6), (66_000, 13, 13, 1), (80_000, 100, 300, 1024),
-                                        (65_536, 960, 12, 10), (100_000, 36, 1000, 50)])
+                                        (65_536, 960, 12, 10), (100_000, 36, 1000, 50),
+                                        (70_000, 960, 128, 10), (70_000, 960, 129, 100)])
 def test_auto_path_edge_shapes_match_scan(n, dim, nq, k):
     """Auto path (tensor pruning from 12 queries up) on odd shapes: tiny / ragged dims (zero-filled TMA boxes),
-    k = 1 and k = 1024, the smallest supported shard. Must be bit-identical to the forced exact scan."""
+    k = 1 and k = 1024, the smallest supported shard, and both sides of the 128-query boundary between single CTAs
+    (M = 128) and CTA pairs (M = 256). Must be bit-identical to the forced exact scan."""
     import lab_1806_vec_db_b200 as V
     from lab_1806_vec_db_b200 import _lib as L
     rng = np.random.default_rng(n + dim)
