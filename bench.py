@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DIM = 960
+GEMM_PART_TRAFFIC = 1.413e9 + 26.7e6  # DRAM bytes of one filter launch (1/3 of the rows), see profiles/r01_flat_gemm_ncu.md
 CHUNK = 50_000  # rows per generator chunk (seeded per chunk so any sharding sees the same bits)
 
 
@@ -286,6 +287,33 @@ def run_ours(args):
         L.check(lib.vdb_prof_read(name.encode(), C.byref(t), C.byref(c)))
         prof[name] = (t.value, int(c.value))
 
+    # the same contraction kernel timed ALONE (VDB_GEMM_PARTS=1: one filter launch per step, the rerank strictly
+    # after it). In the timed region above the filter pass is cut into row parts and the rerank gathers of part i run
+    # on a side stream under the launch of part i + 1: the step is shorter, each launch is longer.
+    alone = None
+    if rank == 0 and world == 1 and args.path != "scan":
+        keep = os.environ.get("VDB_GEMM_PARTS")
+        os.environ["VDB_GEMM_PARTS"] = "1"
+        idx.knn_batch_dev(q_dev, args.k)
+        torch.cuda.synchronize()
+        L.check(lib.vdb_prof_reset())
+        L.check(lib.vdb_prof_enable(1))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            idx.knn_batch_dev(q_dev, args.k)
+        a1.record()
+        torch.cuda.synchronize()
+        L.check(lib.vdb_prof_enable(0))
+        t, c = C.c_double(0), C.c_uint64(0)
+        L.check(lib.vdb_prof_read(b"flat_gemm", C.byref(t), C.byref(c)))
+        alone = {"flat_gemm_ms_per_step": t.value / 3, "launches_per_step": int(c.value) // 3,
+                 "ms_per_step": a0.elapsed_time(a1) / 3}
+        if keep is None:
+            del os.environ["VDB_GEMM_PARTS"]
+        else:
+            os.environ["VDB_GEMM_PARTS"] = keep
+
     # ---- end-to-end timing through the host-buffer API (e2e) --------------------------------------
     q_np = q_pin.numpy()
     def e2e_call():
@@ -329,16 +357,24 @@ def run_ours(args):
         achieved = flops / (t_dom * 1e-3) / 1e12 if t_dom > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "flat_gemm_kernel", "achieved": achieved, "peak": sustained,
                 "unit": "TFLOP/s", "frac": achieved / sustained,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the filter launch from the committed ncu capture
-                # (profiles/r01_flat_gemm_ncu.md: 4.19 GB + 77 MB at 1M x 960, 10k queries; algorithmic 3.89 GB)
-                "traffic": (4.19e9 + 76.8e6 if (n_local == 1_000_000 and args.nq == 10_000) else None),
-                "traffic_source": "ncu --set full capture, profiles/r01_flat_gemm_ncu.md (bytes per filter launch)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one filter launch (a third of the rows) from the
+                # committed ncu capture (profiles/r01_flat_gemm_ncu.md; algorithmic: 1.28 GB rows + 38 MB queries)
+                "traffic": (GEMM_PART_TRAFFIC if (n_local == 1_000_000 and args.nq == 10_000) else None),
+                "traffic_source": "ncu --set full capture, profiles/r01_flat_gemm_ncu.md (bytes per filter launch = "
+                                  "one of the 3 row parts of a step)",
+                "algorithmic_bytes_per_launch": n_local * DIM * 4 / 3 + args.nq * DIM * 4,
                 "peak_source": "cuBLAS TF32 8192^3 measured in this run, sustained (burst %.1f); nominal dense TF32 "
                                "is 1100; MEASURED_PEAKS.json has bf16 only (%.1f sustained)"
                                % (burst, peaks.get("bf16_tflops_sustained") or 0.0),
                 "launches": c_dom, "avg_launch_ms": t_dom / max(c_dom, 1),
                 "flop_per_step": flops / args.steps}
     roof["kernel_share_of_step"] = t_dom / (ms * args.steps) if ms > 0 else None
+    if dom == "flat_gemm" and alone:
+        a_ach = 2.0 * args.nq * n_local * DIM / (alone["flat_gemm_ms_per_step"] * 1e-3) / 1e12
+        roof["note"] = ("achieved/frac are over the timed region, where the filter launches share the GPU with the "
+                        "rerank gathers of the previous row part (side stream); `alone` is the same kernel with "
+                        "VDB_GEMM_PARTS=1 (nothing concurrent), 3 extra steps after the timed region")
+        roof["alone"] = {"achieved": a_ach, "frac": a_ach / roof["peak"], **alone}
 
     # ---- CPU baseline (bounded sample) + parity spot check -----------------------------------------
     cpu = None
@@ -374,7 +410,7 @@ def run_ours(args):
         L.check(lib.vdb_flat_set_path(1))
         for nq1 in (1, 2, 4, 8):
             qs = q_dev[:nq1].contiguous()
-            for _ in range(3):
+            for _ in range(40 if nq1 == 1 else 3):  # the first case also brings the clocks back up after the CPU leg
                 idx.knn_batch_dev(qs, 10)
             L.check(lib.vdb_prof_reset())
             L.check(lib.vdb_prof_enable(1))

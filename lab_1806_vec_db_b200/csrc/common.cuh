@@ -182,6 +182,21 @@ __device__ __forceinline__ float4 ldg_stream_f4(const void* p) {
     return r;
 }
 
+// the same with an L2 evict-first policy: gathers that run next to the tensor-core contraction (rerank of one row part
+// under the contraction of the next) must not push the contraction's query / row tiles out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_stream_f4_ef(const void* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
 // Reduce V per-lane partials across the warp so that lane L ends up holding the warp-wide total
 // of value index (L >> (5 - log2 V)). V-1 + (5 - log2 V) shuffles instead of 5*V.
 template <int V>

@@ -78,7 +78,8 @@ struct GemmParams {
     uint32_t ntiles;        // ceil(nrows / GN)
     uint32_t nqt;           // query-tile UNITS: ceil(nq / (GM * CTAS))
     uint32_t tiles_per_slab;
-    uint32_t nslabs;
+    uint32_t nslabs;        // slabs covered by this launch
+    uint32_t slab0;         // first slab of this launch (the filter pass may be cut into row parts)
     const float* sqnorm;    // [n] ||x||^2
     const float* rnorm;     // [n] ||x||
     const float* qcm;       // [nq] L2Sqr: c * ||q|| (pruning-bound coefficient times the query norm); cosine: 1/||q||
@@ -110,8 +111,9 @@ __device__ __forceinline__ ItemView decode_item(const GemmParams& p, uint32_t it
         v.r_end = it.r_end;
         v.slab = 0;  // mode 2: every gathered query row belongs to exactly one item
     } else {
-        v.slab = item / p.nqt;
-        v.q0 = (item - v.slab * p.nqt) * GM * CTAS;
+        const uint32_t sl = item / p.nqt;
+        v.slab = p.slab0 + sl;
+        v.q0 = (item - sl * p.nqt) * GM * CTAS;
         v.q_end = p.nq;
         v.r0 = (uint64_t)v.slab * p.tiles_per_slab * GN;
         v.r_end = min(p.nrows, v.r0 + (uint64_t)p.tiles_per_slab * GN);
@@ -614,6 +616,67 @@ __global__ void __launch_bounds__(1024) cand_offsets_kernel(const uint32_t* __re
     }
     if (threadIdx.x == 0) off[nq] = carry;
 }
+// ---- row-part pipeline of the filter pass: candidates [prev[q], cur[q]) of every query (one row part) -------------
+// exclusive scan of the part's candidate counts; prev == nullptr -> 0
+__global__ void __launch_bounds__(1024) part_offsets_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ cur,
+                                                            uint32_t nq, uint32_t cap, uint64_t* __restrict__ off) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nq; base += blockDim.x) {
+        const uint32_t q = base + threadIdx.x;
+        const uint64_t v = q < nq ? min(cur[q], cap) - (prev ? min(prev[q], cap) : 0u) : 0u;
+        uint64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t before = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
+        if (q < nq) off[q] = before;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[nq] = carry;
+}
+__global__ void part_to_pairs_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ prev,
+                                     const uint32_t* __restrict__ cur, uint32_t cap, const uint64_t* __restrict__ off,
+                                     uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid) {
+    const uint32_t q = blockIdx.x;
+    const uint32_t j0 = prev ? min(prev[q], cap) : 0u, j1 = min(cur[q], cap);
+    const uint64_t o = off[q];
+    for (uint32_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+        qidx[o + (j - j0)] = q;
+        rid[o + (j - j0)] = (uint32_t)cand[(uint64_t)q * cap + j];
+    }
+}
+// exact distances of the part's pairs -> final keys, written over the candidate entries they came from
+__global__ void part_rekey_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ qidx,
+                                  const uint32_t* __restrict__ rid, const uint64_t* __restrict__ off, uint32_t nq,
+                                  const uint32_t* __restrict__ prev, uint32_t cap, uint32_t id_base,
+                                  uint64_t* __restrict__ cand) {
+    const uint64_t n = off[nq];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t q = qidx[i];
+        const uint32_t j = (prev ? min(prev[q], cap) : 0u) + (uint32_t)(i - off[q]);
+        cand[(uint64_t)q * cap + j] = make_key(dist[i], id_base + rid[i]);
+    }
+}
 // candidate (S', local row) lists -> dense rerank inputs at off[q]
 __global__ void cand_to_pairs_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap,
                                      const uint64_t* __restrict__ off, const uint32_t* __restrict__ pos_to_row,
@@ -839,6 +902,41 @@ void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j
     VDB_LAUNCHED();
 }
 
+// side stream of the filter pass (per host thread and device): reranks row part i under the contraction of part i + 1
+struct SideStream {
+    int device = -1;
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev = nullptr, ev2 = nullptr;
+    void ensure(int dev) {
+        if (device == dev) return;
+        release();
+        VDB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        VDB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        VDB_CUDA(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
+        device = dev;
+    }
+    void release() {
+        if (device < 0) return;
+        cudaStreamDestroy(s);
+        cudaEventDestroy(ev);
+        cudaEventDestroy(ev2);
+        device = -1;
+    }
+    ~SideStream() { release(); }
+};
+// sum of min(cnt, cap) over the queries (instrumentation: candidates reranked)
+__global__ void __launch_bounds__(1024) cand_total_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
+                                                          uint64_t* __restrict__ out) {
+    __shared__ unsigned long long sum;
+    if (threadIdx.x == 0) sum = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) mine += min(cnt[q], cap);
+    atomicAdd(&sum, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = sum;
+}
+
 // FILTER + RERANK: rows with S' < tau_q -> exact distances -> this shard's k best keys per query.
 // d_overflow[q] = 1 when the candidate list of q overflowed (its result is then incomplete).
 void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
@@ -852,41 +950,85 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     tq->cap = cap;
     DevBuf cand((size_t)nq * cap * 8, st);
     VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
-    {
-        const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, (uint64_t)ds->pitch * 4, GN / tq->ctas);
-        GemmParams pf = base_params(tq);
-        pf.sqnorm = ds->d_sqnorm;
-        pf.rnorm = ds->d_lo;
-        pf.nrows = ds->n;
-        pf.row_stride = 1;
-        pf.tau = d_tau;
-        pf.cand_cnt = tq->cnt.as<uint32_t>();
-        pf.cand = cand.as<uint64_t>();
-        pf.cap = cap;
-        plan_gemm(pf, tq->ctas);
-        launch_gemm(1, ds->metric, tq->mq, mx, pf, st, tq->ctas);
+    const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, (uint64_t)ds->pitch * 4, GN / tq->ctas);
+    GemmParams pf = base_params(tq);
+    pf.sqnorm = ds->d_sqnorm;
+    pf.rnorm = ds->d_lo;
+    pf.nrows = ds->n;
+    pf.row_stride = 1;
+    pf.tau = d_tau;
+    pf.cand_cnt = tq->cnt.as<uint32_t>();
+    pf.cand = cand.as<uint64_t>();
+    pf.cap = cap;
+    plan_gemm(pf, tq->ctas);
+    // The contraction is tensor-bound and leaves HBM idle, the exact rerank of its candidates is an HBM-bound gather:
+    // the pass is cut into row parts (slab ranges, so nothing is streamed twice) and the rerank of part i runs on a
+    // side stream under the contraction of part i + 1 (the rerank CTAs fit next to the one persistent contraction
+    // CTA per SM: 192 threads x <= 87 registers and no free shared memory needed). A part's candidates are the entries
+    // [snap[i-1][q], snap[i][q]) of every query's list (counter snapshots taken between the launches); their exact
+    // keys are written back over the entries they came from, so the final selection reads one [nq][cap] array.
+    const uint32_t total_slabs = pf.nslabs;
+    const char* parts_s = getenv("VDB_GEMM_PARTS");   // read per call: the probe scripts sweep it
+    const uint32_t parts_env = parts_s ? (uint32_t)atoi(parts_s) : 0;
+    const uint64_t tile_units = (uint64_t)pf.ntiles * pf.nqt;   // 256 x 256 (or 128 x 256) score tiles of the pass
+    // measured (scripts/probe_parts.py, probe_shard_phases.py): 1M x 960, 10k queries 39.2 -> 38.6 ms with 3 parts (the
+    // step is power-capped, so hiding the gathers slows the contraction by almost as much); a 125k-row shard with its
+    // own thresholds 9.6 -> 8.0 ms; the same shard under the global thresholds of an 8-way split 4.87 -> 4.77 ms;
+    // 8 parts cost more in launch tails than they hide
+    uint32_t parts = parts_env ? parts_env : (tile_units >= 8192 ? 3u : 1u);
+    parts = std::max(1u, std::min(parts, total_slabs));
+    static thread_local SideStream side;
+    if (parts > 1) side.ensure(ds->device);
+    cudaStream_t rs = parts > 1 ? side.s : st;   // rerank stream
+    DevBuf snaps((size_t)parts * nq * 4, st);
+    const uint64_t total = (uint64_t)nq * cap;  // capacity bound; the live counts stay on the device
+    DevBuf off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st);
+    if (parts > 1) {   // the side stream must not touch the scratch before the allocations above are ordered
+        VDB_CUDA(cudaEventRecord(side.ev, st));
+        VDB_CUDA(cudaStreamWaitEvent(rs, side.ev, 0));
     }
-    // exact rerank of the candidates (compacted: only the valid pairs are touched)
-    const uint64_t total = (uint64_t)nq * cap;  // capacity bound; the live count stays on the device
-    DevBuf off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st), keys2(total * 8, st);
-    cand_offsets_kernel<<<1, 1024, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
-    VDB_LAUNCHED();
-    cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, off.as<uint64_t>(), nullptr,
-                                             qidx.as<uint32_t>(), rid.as<uint32_t>());
-    VDB_LAUNCHED();
-    const uint64_t* d_total = off.as<uint64_t>() + nq;
-    exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
-                                dist.as<float>(), st, d_total,
-                                ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr);
-    rekey_dev_count_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(),
-                                                                    (uint32_t)ds->id_base, d_total, keys2.as<uint64_t>());
-    VDB_LAUNCHED();
-    launch_merge_keys(keys2.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, off.as<uint64_t>());
+    for (uint32_t part = 0; part < parts; ++part) {
+        const uint32_t s0 = (uint32_t)((uint64_t)total_slabs * part / parts), s1 = (uint32_t)((uint64_t)total_slabs * (part + 1) / parts);
+        GemmParams pp = pf;
+        pp.slab0 = s0;
+        pp.nslabs = s1 - s0;
+        launch_gemm(1, ds->metric, tq->mq, mx, pp, st, tq->ctas);
+        uint32_t* snap = snaps.as<uint32_t>() + (size_t)part * nq;
+        const uint32_t* prev = part ? snap - nq : nullptr;
+        VDB_CUDA(cudaMemcpyAsync(snap, tq->cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToDevice, st));
+        if (parts > 1) {
+            VDB_CUDA(cudaEventRecord(side.ev, st));
+            VDB_CUDA(cudaStreamWaitEvent(rs, side.ev, 0));
+        }
+        // exact rerank of the part's candidates (compacted: only the valid pairs are touched)
+        part_offsets_kernel<<<1, 1024, 0, rs>>>(prev, snap, nq, cap, off.as<uint64_t>());
+        VDB_LAUNCHED();
+        part_to_pairs_kernel<<<nq, 256, 0, rs>>>(cand.as<uint64_t>(), prev, snap, cap, off.as<uint64_t>(), qidx.as<uint32_t>(),
+                                                 rid.as<uint32_t>());
+        VDB_LAUNCHED();
+        exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
+                                    dist.as<float>(), rs, off.as<uint64_t>() + nq,
+                                    ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr);
+        part_rekey_kernel<<<(uint32_t)sm_count() * 8, 256, 0, rs>>>(dist.as<float>(), qidx.as<uint32_t>(), rid.as<uint32_t>(),
+                                                                   off.as<uint64_t>(), nq, prev, cap, (uint32_t)ds->id_base,
+                                                                   cand.as<uint64_t>());
+        VDB_LAUNCHED();
+    }
+    if (parts > 1) {
+        VDB_CUDA(cudaEventRecord(side.ev2, rs));
+        VDB_CUDA(cudaStreamWaitEvent(st, side.ev2, 0));
+    }
+    // the k best exact keys of every query's list (its first min(cnt, cap) entries)
+    launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr,
+                      tq->cnt.as<uint32_t>());
     if (d_overflow) {
         overflow_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, d_overflow);
         VDB_LAUNCHED();
     }
-    if (d_cand_total) VDB_CUDA(cudaMemcpyAsync(d_cand_total, d_total, 8, cudaMemcpyDeviceToDevice, st));
+    if (d_cand_total) {
+        cand_total_kernel<<<1, 1024, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, d_cand_total);
+        VDB_LAUNCHED();
+    }
 }
 
 // CHECK: the (merged) result of q is provably exact iff no shard overflowed and d_k - ||q||^2 < tau_q

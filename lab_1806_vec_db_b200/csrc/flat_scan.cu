@@ -209,14 +209,17 @@ constexpr int MERGE_THREADS = 256;
 constexpr int MERGE_UNROLL = 1;
 __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
     const uint64_t* __restrict__ keys, uint32_t nlists, uint32_t nq, uint32_t len, int list_major,
-    const uint64_t* __restrict__ seg_off, uint32_t K, uint32_t P, uint32_t limit, uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids,
-    float* __restrict__ dist, uint32_t* __restrict__ counts) {
+    const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ seg_cnt, uint32_t K, uint32_t P, uint32_t limit,
+    uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids, float* __restrict__ dist, uint32_t* __restrict__ counts) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem);
     const uint32_t q = blockIdx.x;
-    // seg_off != nullptr: one variable-length list per query, keys[seg_off[q] .. seg_off[q+1])
-    const uint64_t seg_base = seg_off ? seg_off[q] : 0;
-    const uint64_t total = seg_off ? seg_off[q + 1] - seg_base : (uint64_t)nlists * len;
+    // seg_off != nullptr: one variable-length list per query, keys[seg_off[q] .. seg_off[q+1]);
+    // seg_cnt != nullptr: the first min(seg_cnt[q], len) keys of the fixed-pitch list keys[q * len ..]
+    const bool seg = seg_off != nullptr || seg_cnt != nullptr;
+    const uint64_t seg_base = seg_off ? seg_off[q] : (seg_cnt ? (uint64_t)q * len : 0);
+    const uint64_t total = seg_off ? seg_off[q + 1] - seg_base
+                                   : (seg_cnt ? (uint64_t)min(seg_cnt[q], len) : (uint64_t)nlists * len);
     // a short list is sorted once in the smallest power-of-two segment that holds it (no intermediate flush)
     uint32_t Pq = P, lim = limit;
     if (total + K <= P) {
@@ -232,8 +235,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
     auto load_key = [&](uint64_t r) -> uint64_t {
         const uint64_t i = r * blockDim.x + threadIdx.x;
         if (i >= total) return KEY_NONE;
-        const uint64_t l = seg_off ? 0 : i / len, j = seg_off ? 0 : i - l * len;
-        const uint64_t src = seg_off ? seg_base + i
+        const uint64_t l = seg ? 0 : i / len, j = seg ? 0 : i - l * len;
+        const uint64_t src = seg ? seg_base + i
                                      : (list_major ? ((l * nq + q) * len + j) : (((uint64_t)q * nlists + l) * len + j));
         return keys[src];
     };
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
 
 void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
-                       uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off) {
+                       uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off, const uint32_t* d_seg_cnt) {
     if (nq == 0 || k == 0) return;
     // segment size: small inputs (K + all keys of a query fit in 1024 slots) are loaded completely and sorted once
     // in the smallest power-of-two segment; larger inputs stream through a K + 2 * 256 slot segment
@@ -284,7 +287,7 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
         VDB_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     ProfScope prof("merge", stream);
-    merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off,
+    merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off, d_seg_cnt,
                                                            k, P, limit, d_out_keys, d_ids,
                                                            d_dist, d_counts);
     VDB_LAUNCHED();

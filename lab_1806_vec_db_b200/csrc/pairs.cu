@@ -55,12 +55,13 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
                 const float4* a4 = reinterpret_cast<const float4*>(a);
                 const float4* b4 = reinterpret_cast<const float4*>(b);
                 f32x2 t0 = 0ull, t1 = 0ull;
+                const uint64_t pol = l2_evict_first_policy();
                 for (uint32_t c0 = 0; c0 < nvec; c0 += 256) {
                     float4 xb[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const uint32_t c = c0 + u * 32 + lane;
-                        xb[u] = c < nvec ? ldg_stream_f4(b4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xb[u] = c < nvec ? ldg_stream_f4_ef(b4 + c, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {

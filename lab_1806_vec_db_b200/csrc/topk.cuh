@@ -70,6 +70,7 @@ void launch_merge_sorted(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, u
                          uint64_t* d_ids, float* d_dist, uint32_t* d_counts, cudaStream_t stream);
 void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
-                       uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off = nullptr);
+                       uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off = nullptr,
+                       const uint32_t* d_seg_cnt = nullptr);
 
 }  // namespace vdb

@@ -16,7 +16,7 @@ lib = L.lib()
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 nn, ns, mn = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
 L.check(lib.vdb_tq_info(vs._h, C.byref(nn), C.byref(ns), C.byref(mn)))
-j0 = int(lib.vdb_tq_j0(k, ns.value, nn.value)); j = j0
+j0 = int(os.environ.get("J0", 0)) or int(lib.vdb_tq_j0(k, ns.value, nn.value)); j = j0  # J0=2 on a 125k shard ~ the global threshold of an 8-way split
 print("n", nn.value, "sample", ns.value, "j0", j0)
 names = ["begin", "sample", "tau", "filter", "check", "decode"]
 def once(record):
@@ -41,16 +41,18 @@ def once(record):
     lib.vdb_tq_end(tq)
     torch.cuda.synchronize()
     return [ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))], nr
-for _ in range(3): once(False)
-L.check(lib.vdb_prof_reset()); L.check(lib.vdb_prof_enable(1))
-acc = np.zeros(len(names)); R = 5
-for _ in range(R):
-    t, nr = once(True); acc += np.array(t)
-L.check(lib.vdb_prof_enable(0))
-print("phase ms:", {nm: round(v / R, 3) for nm, v in zip(names, acc)}, "total", round(acc.sum() / R, 3), "redo", nr)
-out = {}
-for name in (b"flat_gemm", b"rerank", b"merge"):
-    t, c = C.c_double(0), C.c_uint64(0)
-    L.check(lib.vdb_prof_read(name, C.byref(t), C.byref(c)))
-    out[name.decode()] = (round(t.value / R, 3), c.value // R)
-print("kernels (ms, launches):", out)
+for parts in [int(v) for v in os.environ.get("PARTS", "0").split(",")]:
+    os.environ["VDB_GEMM_PARTS"] = str(parts)
+    for _ in range(3): once(False)
+    L.check(lib.vdb_prof_reset()); L.check(lib.vdb_prof_enable(1))
+    acc = np.zeros(len(names)); R = 5
+    for _ in range(R):
+        t, nr = once(True); acc += np.array(t)
+    L.check(lib.vdb_prof_enable(0))
+    print("parts", parts, "phase ms:", {nm: round(float(v) / R, 3) for nm, v in zip(names, acc)}, "total", round(float(acc.sum()) / R, 3), "redo", nr)
+    out = {}
+    for name in (b"flat_gemm", b"rerank", b"merge"):
+        t, c = C.c_double(0), C.c_uint64(0)
+        L.check(lib.vdb_prof_read(name, C.byref(t), C.byref(c)))
+        out[name.decode()] = (round(t.value / R, 3), c.value // R)
+    print("   kernels (ms, launches):", out)
