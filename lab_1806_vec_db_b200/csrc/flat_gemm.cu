@@ -924,6 +924,14 @@ struct SideStream {
     }
     ~SideStream() { release(); }
 };
+// drains the side stream if the filter pass unwinds early (its scratch is freed in stream order on the MAIN stream)
+struct SideDrain {
+    cudaStream_t s;
+    bool armed;
+    ~SideDrain() {
+        if (armed) cudaStreamSynchronize(s);
+    }
+};
 // sum of min(cnt, cap) over the queries (instrumentation: candidates reranked)
 __global__ void __launch_bounds__(1024) cand_total_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
                                                           uint64_t* __restrict__ out) {
@@ -983,6 +991,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     DevBuf snaps((size_t)parts * nq * 4, st);
     const uint64_t total = (uint64_t)nq * cap;  // capacity bound; the live counts stay on the device
     DevBuf off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st);
+    SideDrain drain{rs, parts > 1};
     if (parts > 1) {   // the side stream must not touch the scratch before the allocations above are ordered
         VDB_CUDA(cudaEventRecord(side.ev, st));
         VDB_CUDA(cudaStreamWaitEvent(rs, side.ev, 0));
@@ -1018,6 +1027,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         VDB_CUDA(cudaEventRecord(side.ev2, rs));
         VDB_CUDA(cudaStreamWaitEvent(st, side.ev2, 0));
     }
+    drain.armed = false;   // from here on the main stream is ordered after the side stream
     // the k best exact keys of every query's list (its first min(cnt, cap) entries)
     launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr,
                       tq->cnt.as<uint32_t>());
