@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--path", default="auto", choices=["auto", "scan", "tensor"])
     ap.add_argument("--cpu-queries", type=int, default=0, help="CPU sample size (0 = 2 x cores, <= 128)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the IVF (configs[2]) and PQ (configs[3]) legs that follow the headline measurement at N=1")
     return ap.parse_args()
 
 
@@ -179,6 +181,80 @@ def tensor_stats(lib):
     if q.value == 0:
         return None
     return {"queries": q.value, "candidates_per_query": c.value / q.value, "exact_fallback_queries": f.value}
+
+
+def other_configs(V, L, lib, vs, base, q_dev, gt_ids, dev, n):
+    """configs[2] (IVF nlist=128, nprobe sweep) and configs[3] (PQ m=240 x 4 bits, ef sweep) of BASELINE.json on the same
+    rows: 1000 queries, k=10 (examples/bench.rs protocol), recall@10 against the exact Flat result of the headline leg.
+    Device-resident, CUDA events, 3 repetitions after one warm-up. bench_aux.py is the long form (CPU columns, HNSW)."""
+    import torch
+    from lab_1806_vec_db_b200.index import train_codebooks
+    nq, k = min(1000, q_dev.shape[0]), 10
+    q = q_dev[:nq].contiguous()
+    gt = gt_ids[:nq, :k]
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rng = np.random.default_rng(42)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps
+
+    def recall():
+        got = ids.cpu().numpy()
+        return float(np.mean([len(set(got[i]) & set(gt[i])) / k for i in range(nq)]))
+
+    def sample_rows(m):
+        sel = torch.as_tensor(rng.permutation(n)[:min(m, n)], device=dev)
+        return np.ascontiguousarray(base.index_select(0, sel).cpu().numpy())
+
+    out = {"nq": nq, "k": k, "recall_against": "exact Flat top-10 of the same queries (headline leg)"}
+    # ---- configs[2]: IVF ----
+    t0 = time.perf_counter()
+    km = V.KMeans.from_vec_set(sample_rows(100_000), V.KMeansConfig(128, 20, 1e-6, "l2sqr"), rng)
+    t_train = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ivf = V.IVFIndex(vs, km.centroids)
+    t_assign = time.perf_counter() - t0
+    rows = []
+    for nprobe in (8, 16, 24):
+        ms = timed(lambda: L.check(lib.vdb_ivf_knn_dev(vs._h, ivf._h, C.c_void_p(q.data_ptr()), nq, k, nprobe,
+                                                       C.c_void_p(ids.data_ptr()), C.c_void_p(dd.data_ptr()),
+                                                       C.c_void_p(cnt.data_ptr()), st)))
+        rows.append({"nprobe": nprobe, "qps": nq / ms * 1e3, "ms_per_batch": ms, "recall@10": recall()})
+    out["ivf"] = {"nlist": 128, "kmeans_rows": min(100_000, n), "kmeans_iters": int(km.iterations),
+                  "train_s": t_train, "assign_and_lists_s": t_assign, "search": rows}
+    del ivf
+    # ---- configs[3]: PQ table + Flat ADC scan + exact rerank ----
+    cfg = V.PQConfig(4, 240, "l2sqr", min(10_000, n), 20, 1e-6)
+    t0 = time.perf_counter()
+    train_dev = V.DeviceVecSet(sample_rows(10_000), "l2sqr")
+    books = train_codebooks(train_dev, cfg, rng)
+    train_dev.close()
+    t_train = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pq = V.PQTable(vs, cfg, books)
+    t_encode = time.perf_counter() - t0
+    rows = []
+    for ef in (240, 420, 600):
+        ms = timed(lambda: L.check(lib.vdb_pq_knn_dev(vs._h, pq._h, C.c_void_p(q.data_ptr()), nq, k, ef,
+                                                      C.c_void_p(ids.data_ptr()), C.c_void_p(dd.data_ptr()),
+                                                      C.c_void_p(cnt.data_ptr()), st)))
+        rows.append({"ef": ef, "qps": nq / ms * 1e3, "ms_per_batch": ms, "recall@10": recall()})
+    out["pq"] = {"m": 240, "n_bits": 4, "kmeans_rows": min(10_000, n), "train_s_incl_upload": t_train,
+                 "encode_s_incl_code_download": t_encode, "search": rows,
+                 "note": "the synthetic set has 1000 near-equidistant copies per prototype, which 4-bit PQ cannot rank: "
+                         "recall equals the CPU oracle's on the same codebooks (bench_aux.py, tests/test_index_gpu.py)"}
+    return out
 
 
 def run_reference(args):
@@ -380,7 +456,7 @@ def run_ours(args):
     cpu = None
     if world == 1:
         cores = os.cpu_count() or 1
-        nqs = args.cpu_queries or min(64, max(8, cores))
+        nqs = args.cpu_queries or min(128, max(16, 4 * cores))  # ~2.5 s of wall clock = ~40 core-seconds per pass
         base_host = base.cpu().numpy()
         q_host = q_pin[:nqs].numpy()
         qps_cpu, dt_cpu, ores = cpu_arm(base_host, q_host, args.k, cores, 1, 0)
@@ -432,6 +508,14 @@ def run_ours(args):
                                       "frac_whole_call": n_local * DIM * 4 / (call_ms * 1e-3) / 1e9 / peak_hbm})
         L.check(lib.vdb_flat_set_path({"auto": 0, "scan": 1, "tensor": 2}[args.path]))
 
+    # ---- the other single-GPU configs of BASELINE.json on the same rows (IVF, PQ) ----------------------------
+    other = None
+    if world == 1 and not args.no_other_configs and args.n >= 65536:
+        try:
+            other = other_configs(V, L, lib, vs, base, q_dev, res[0].cpu().numpy(), dev, args.n)
+        except Exception as e:  # the headline line must not be lost to an auxiliary leg
+            other = {"error": repr(e)}
+
     qps = args.nq / (ms * 1e-3)
     line = {
         "metric": "QPS, exact Flat L2 kNN", "value": qps, "unit": "queries/s", "n_gpus": world,
@@ -452,6 +536,7 @@ def run_ours(args):
         "kernel_ms": {k_: {"ms": v[0], "launches": v[1]} for k_, v in prof.items()},
         "tensor_path": tensor_stats(lib),
         "hbm_scan": hbm_scan,
+        "other_configs": other,
     }
     if idx.phase_ms.get("calls"):  # VDB_PHASE_TIMING=1: per-phase device time of the sharded search (rank 0), ms per call
         line["phase_ms"] = {k_: round(v / idx.phase_ms["calls"], 4) for k_, v in idx.phase_ms.items() if k_ != "calls"}

@@ -3,7 +3,7 @@
 # capture of the dominant kernel. Each only after the same command exited 0 without ncu.
 set -x
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 1 --cpu-queries 2"
+CMD="python bench.py --steps 1 --warmup 1 --cpu-queries 2 --no-other-configs"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
