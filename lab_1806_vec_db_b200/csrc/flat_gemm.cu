@@ -562,6 +562,33 @@ static void launch_gemm(int mode, int metric, const CUtensorMap& mq, const CUten
 
 // c * ||q|| per query; c bounds |S'_tf32 - S'_exact| / (||q|| ||x||): two TF32 operand roundings (2^-10 each,
 // truncation) + their product + K fp32 accumulation steps (K * 2^-23), times 2 for the -2 q.x term.
+// Query side of the tensor path in one pass (one warp per query): padded fp32 copy (exact rerank), TF32-rounded copy
+// (MMA operand) and, for L2Sqr, ||q||^2 and c * ||q||. The norm is summed exactly like row_cache's PM_SQNORM kernel
+// (lane-strided fma chain + xor butterfly), so thresholds do not depend on which of the two produced it.
+template <typename T>
+__global__ void __launch_bounds__(256) tq_prepare_kernel(const T* __restrict__ src, uint32_t nq, uint32_t dim, uint32_t qpitch,
+                                                         float c, float* __restrict__ qcopy, float* __restrict__ qround,
+                                                         float* __restrict__ qsq, float* __restrict__ qcm) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const T* row = src + (size_t)q * dim;
+    float s = 0.f;
+    for (uint32_t e = lane; e < qpitch; e += 32) {
+        const float v = e < dim ? (float)row[e] : 0.f;
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        qcopy[(size_t)q * qpitch + e] = v;
+        qround[(size_t)q * qpitch + e] = __uint_as_float(r);
+        if (e < dim) s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && qsq) {
+        qsq[q] = s;
+        qcm[q] = c * sqrtf(s);
+    }
+}
 __global__ void qcm_kernel(const float* __restrict__ qsq, uint32_t nq, float c, float* __restrict__ qcm) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) qcm[q] = c * sqrtf(qsq[q]);
@@ -802,26 +829,17 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
         tq->qsq = DevBuf((size_t)nq * 4, st);
         tq->qcm = DevBuf((size_t)nq * 4, st);
         tq->cnt = DevBuf((size_t)nq * 4, st);
-        if (ds->dtype == VDB_U8) {
-            u8_rows_to_f32_kernel<<<nq, 128, 0, st>>>((const uint8_t*)d_queries, dim, tq->qpitch, tq->qcopy.as<float>());
-            VDB_LAUNCHED();
-        } else {
-            if (tq->qpitch != dim) VDB_CUDA(cudaMemsetAsync(tq->qcopy.p, 0, qbytes, st));
-            VDB_CUDA(cudaMemcpy2DAsync(tq->qcopy.p, (size_t)tq->qpitch * 4, d_queries, (size_t)dim * 4, (size_t)dim * 4, nq,
-                                       cudaMemcpyDeviceToDevice, st));
-        }
-        round_tf32(tq->qcopy.as<float>(), tq->qround.as<float>(), (uint64_t)nq * tq->qpitch, st);
-        if (ds->metric == VDB_L2SQR) {
-            vdb_dataset qd = *ds;
-            qd.d_rows = tq->qcopy.p;
-            qd.n = nq;
-            qd.pitch = tq->qpitch;
-            qd.dtype = VDB_F32;
-            qd.metric = VDB_L2SQR;
-            row_cache(&qd, tq->qsq.as<float>(), st);
-            qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qsq.as<float>(), nq, c, tq->qcm.as<float>());
-            VDB_LAUNCHED();
-        } else {
+        const bool l2 = ds->metric == VDB_L2SQR;
+        float* qsq = l2 ? tq->qsq.as<float>() : nullptr;
+        const uint32_t pgrid = ceil_div(nq, 8u);   // 8 warps per CTA, one query each
+        if (ds->dtype == VDB_U8)
+            tq_prepare_kernel<uint8_t><<<pgrid, 256, 0, st>>>((const uint8_t*)d_queries, nq, dim, tq->qpitch, c,
+                                                              tq->qcopy.as<float>(), tq->qround.as<float>(), qsq, tq->qcm.as<float>());
+        else
+            tq_prepare_kernel<float><<<pgrid, 256, 0, st>>>((const float*)d_queries, nq, dim, tq->qpitch, c,
+                                                            tq->qcopy.as<float>(), tq->qround.as<float>(), qsq, tq->qcm.as<float>());
+        VDB_LAUNCHED();
+        if (!l2) {
             // cosine distance error <= (c/2) from the contraction + the reciprocal products of the epilogue
             tq->cbound = 0.5f * c + 1e-6f;
             tq->kc = 1.0f - tq->cbound;
@@ -893,9 +911,15 @@ void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j
     cudaStream_t st = tq->st;
     VDB_REQUIRE(j0 >= 1 && j0 <= (uint64_t)j * nlists, "j0 out of range");
     const uint32_t jj = std::min<uint64_t>(j0, (uint64_t)j * nlists);
+    const bool cosine = tq->ds->metric == VDB_COSINE;
+    if (nlists == 1) {   // a single ascending [nq][j] list: its jj-th entry is the order statistic, nothing to merge
+        tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(d_lists, tq->nq, j, jj, cosine ? nullptr : tq->qcm.as<float>(),
+                                                                      cosine ? tq->cbound : mean_norm, d_tau);
+        VDB_LAUNCHED();
+        return;
+    }
     DevBuf merged((size_t)tq->nq * jj * 8, st);
     launch_merge_sorted(d_lists, nlists, tq->nq, j, jj, merged.as<uint64_t>(), nullptr, nullptr, nullptr, st);  // per-shard lists are ascending
-    const bool cosine = tq->ds->metric == VDB_COSINE;
     tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj,
                                                                   cosine ? nullptr : tq->qcm.as<float>(),
                                                                   cosine ? tq->cbound : mean_norm, d_tau);
