@@ -113,16 +113,24 @@ class FlatIndex:
     def dim(self):
         return self.vec_set.dim
 
-    def knn_batch(self, queries, k):
-        """Returns (ids [nq,k] u64, dist [nq,k] f32, counts [nq] u32)."""
+    def knn_batch(self, queries, k, out=None):
+        """Returns (ids [nq,k] u64, dist [nq,k] f32, counts [nq] u32). `out` = caller-owned result arrays of those
+        shapes / dtypes to reuse across calls (e.g. page-locked memory), as a Rust caller reuses its Vecs."""
         vs = self.vec_set
         q = _as_rows(queries, vs.dtype)
         if q.shape[1] != vs.dim:
             raise ValueError("The dimension of the query doesn't match.")
         nq = q.shape[0]
-        ids = np.full((nq, k), np.iinfo(np.uint64).max, np.uint64)
-        dist = np.full((nq, k), np.nan, np.float32)
-        counts = np.zeros(nq, np.uint32)
+        if out is not None:
+            ids, dist, counts = out
+            if not (ids.shape == (nq, k) and ids.dtype == np.uint64 and ids.flags.c_contiguous and
+                    dist.shape == (nq, k) and dist.dtype == np.float32 and dist.flags.c_contiguous and
+                    counts.shape == (nq,) and counts.dtype == np.uint32 and counts.flags.c_contiguous):
+                raise ValueError("out must be C-contiguous (u64 [nq,k], f32 [nq,k], u32 [nq]) arrays")
+        else:
+            ids = np.full((nq, k), np.iinfo(np.uint64).max, np.uint64)
+            dist = np.full((nq, k), np.nan, np.float32)
+            counts = np.zeros(nq, np.uint32)
         L.check(L.lib().vdb_flat_knn(vs._h, L.ptr(q), nq, k, L.ptr(ids), L.ptr(dist), L.ptr(counts)))
         return ids, dist, counts
 
