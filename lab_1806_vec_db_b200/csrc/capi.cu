@@ -303,7 +303,7 @@ static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t 
         tensor = true;
     } else if (path == 0) {
         // measured crossover (scripts/probe_crossover.py, 1M x 960): a tensor pass costs 0.81-0.96 ms for any nq <= 128
-        // (single CTAs, M = 128), the 4-query scan pass 0.76 ms, the 8-query scan pass 1.05 ms
+        // (single CTAs, M = 128), the 4-query scan pass 0.70 ms, the 8-query scan pass 1.05 ms
         tensor = nq >= 5 && vdb::flat_gemm_supported(ds, nq, k);
     }
     if (tensor) vdb::flat_gemm_keys(ds, d_q, nq, k, d_keys, st);

@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     // prefetch runs across group boundaries. Addressing is incremental: one pointer per lane, rows of the group at
     // r * pitch from it; the clamped (last group) and ragged (row end inside the last chunk) cases take a slow path.
     constexpr bool SINGLE = PL == 4 && NQ >= 4;  // measured: only the u8 variants gain (0.98 -> 0.89 ms at 8 queries)
-    uint4 bufA[R], bufB[SINGLE ? 1 : R];
+    // 4 f32 queries: 32 accumulator registers leave room for a third buffer, i.e. two 512-byte steps in flight per
+    // warp (64 KB per SM like the 1- and 2-query variants with their 8-row groups)
+    constexpr bool TRIPLE = NQ == 4 && PL == 1;
+    uint4 bufA[R], bufB[SINGLE ? 1 : R], bufC[TRIPLE ? R : 1];
     const uint32_t tail_lanes = p.nvec - (p.nit - 1) * 32;  // lanes with data in a row's last chunk (1..32)
     uint64_t pg = (uint64_t)blockIdx.x * SCAN_WARPS + warp;  // group being prefetched
     uint32_t pit = 0;                                        // its chunk iteration
@@ -184,6 +187,23 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
             accumulate(bufA);
             if (t + 1 < steps) issue(bufA);
             finish();
+        }
+    } else if constexpr (TRIPLE) {
+        if (steps > 1) issue(bufB);
+        for (uint32_t t = 0; t < steps; t += 3) {
+            if (t + 2 < steps) issue(bufC);
+            accumulate(bufA);
+            finish();
+            if (t + 1 < steps) {
+                if (t + 3 < steps) issue(bufA);
+                accumulate(bufB);
+                finish();
+                if (t + 2 < steps) {
+                    if (t + 4 < steps) issue(bufB);
+                    accumulate(bufC);
+                    finish();
+                }
+            }
         }
     } else {
         for (uint32_t t = 0; t < steps; t += 2) {
