@@ -96,6 +96,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
         if (!pclamp && (pit + 1 < p.nit || tail_lanes == 32)) {
 #pragma unroll
             for (int r = 0; r < R; ++r) dst[r] = ldg_stream_u4(pptr + (size_t)r * p.pitch_bytes);
+        } else if (!pclamp) {
+            // a row's last, ragged chunk (every other step of a 960-byte u8 row): same addressing, lanes past the end
+            // of the row load nothing
+            const bool in = (uint32_t)lane < tail_lanes;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                dst[r] = in ? ldg_stream_u4(pptr + (size_t)r * p.pitch_bytes) : make_uint4(0u, 0u, 0u, 0u);
         } else {
             const bool in = pit + 1 < p.nit || (uint32_t)lane < tail_lanes;
             const uint64_t row0 = pg * R;
@@ -508,8 +515,15 @@ void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     }
     QueryTile qt = prepare_queries(ds, d_queries, nq, st);
 
-    // queries per pass: as many as fit (<= 8) next to the top-k segments in shared memory
-    const uint32_t period = 64;
+    // queries per pass: as many as fit (<= 8) next to the top-k segments in shared memory.
+    // The CTA-wide flush test (a barrier) runs every `sync_every` row groups: often enough that a query's segment
+    // cannot overflow between two tests (at most `period` appends), but not more often than every ~8 steps of 512
+    // bytes - short rows (u8 x 960 = 2 steps per group, 128-d f32 = 1) otherwise meet at a barrier after every group
+    // and lose the overlap between warps (measured neutral for u8 x 960, where something else bounds the pass at 0.253 ms).
+    auto sync_for = [&](uint32_t R) {
+        return std::max(std::max(1u, 64u / (SCAN_WARPS * R)), ceil_div(8u, qt.nit));
+    };
+    const uint32_t period = std::max(sync_for(4) * SCAN_WARPS * 4, sync_for(8) * SCAN_WARPS * 8);
     const uint32_t P = topk_segment_size(k, period);
     int nqt = 8;
     auto smem_for = [&](int t) { return (size_t)t * qt.qstride * 4 + TopkSmem::bytes(t, P); };
@@ -552,7 +566,7 @@ void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
             // every pass of a chunk must use the same grid so the partial layout is uniform
             if (grid_used == 0) grid_used = grid;
             p.iters = (uint32_t)ceil_div<uint64_t>(ngroups, (uint64_t)grid_used * SCAN_WARPS);
-            p.sync_every = std::max(1u, period / (SCAN_WARPS * R));
+            p.sync_every = sync_for((uint32_t)R);
             p.q = qt.q.as<float>() + (size_t)(q0 + qq) * qt.qstride;
             p.qcache = qt.qcache.as<float>() + (q0 + qq);
             p.nq_valid = now;
