@@ -199,8 +199,8 @@ __device__ __forceinline__ float4 ldg_stream_f4_ef(const void* p, uint64_t pol) 
 
 // Reduce V per-lane partials across the warp so that lane L ends up holding the warp-wide total
 // of value index (L >> (5 - log2 V)). V-1 + (5 - log2 V) shuffles instead of 5*V.
-template <int V>
-__device__ __forceinline__ float warp_reduce_scatter(float (&v)[V], int lane) {
+template <int V, typename T>
+__device__ __forceinline__ T warp_reduce_scatter(T (&v)[V], int lane) {
     static_assert(V >= 1 && V <= 32 && (V & (V - 1)) == 0, "V must be a power of two <= 32");
     int offset = 16;
 #pragma unroll
@@ -209,13 +209,13 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[V], int lane) {
         const bool upper = (lane & offset) != 0;
 #pragma unroll
         for (int j = 0; j < half; ++j) {
-            float send = upper ? v[j] : v[j + half];
-            float keep = upper ? v[j + half] : v[j];
+            T send = upper ? v[j] : v[j + half];
+            T keep = upper ? v[j + half] : v[j];
             v[j] = keep + __shfl_xor_sync(0xffffffffu, send, offset);
         }
         offset >>= 1;
     }
-    float r = v[0];
+    T r = v[0];
 #pragma unroll
     for (; offset >= 1; offset >>= 1) r += __shfl_xor_sync(0xffffffffu, r, offset);
     return r;

@@ -30,10 +30,10 @@ namespace vdb {
 inline uint32_t vec_elems(int dtype) { return dtype == VDB_F32 ? 4u : 16u; }  // elements per 16-byte load
 
 // ---- query preparation: T[nq][dim] -> f32 tile layout used by the scan kernels --------------
-// layout per query: [planes][nit*32] float4, where element e of the (zero padded) row lives in
-// plane (e % VEC) / 4, float4 index e / VEC, component e % 4  (VEC = 4 -> 1 plane, VEC = 16 -> 4).
+// f32 sets: per query [nit*32] float4, element e of the (zero padded) row in float4 e / 4, component e % 4.
+// u8 sets: per query the row's bytes, zero padded to nit * 512 bytes (qstride counts 4-byte words in both cases).
 struct QueryTile {
-    DevBuf q;        // [nq][qstride] f32
+    DevBuf q;        // [nq][qstride] f32 (f32 sets) / [nq][qstride * 4] bytes (u8 sets)
     DevBuf qcache;   // [nq] f32: ||q|| (cosine) / ||q||^2 (l2) in plain f32
     uint32_t qstride = 0;  // floats per query
     uint32_t nvec = 0, nit = 0;

@@ -48,20 +48,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     constexpr int SHR = 5 - Log2<R>::value;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t qs4 = p.qstride >> 2;  // float4 per query
-    const uint32_t plane4 = p.nit * 32;   // float4 per plane
-    // u8 rows, L2Sqr: rows and queries both carry the 2^23 conversion bias (queries of a u8 set are u8 values, so
-    // q + 2^23 and the difference of the biased values are exact) - see row_pairs in scanmath.cuh
-    constexpr bool BIASED = PL == 4 && METRIC == VDB_L2SQR;
+    // query tile in shared memory: f32 rows -> f32 values, u8 rows -> the queries' bytes (16 per lane and step), see
+    // prepare_queries; either way qs4 16-byte units per query
     float4* qs = reinterpret_cast<float4*>(smem);
     const ulonglong2* qs2 = reinterpret_cast<const ulonglong2*>(smem);
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)NQ * p.qstride * 4);
     TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
 
-    for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x) {
-        float4 v = (i / qs4 < p.nq_valid) ? reinterpret_cast<const float4*>(p.q)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (BIASED) v = make_float4(v.x + U8_BIAS, v.y + U8_BIAS, v.z + U8_BIAS, v.w + U8_BIAS);
-        qs[i] = v;
-    }
+    for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x)
+        qs[i] = (i / qs4 < p.nq_valid) ? reinterpret_cast<const float4*>(p.q)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     topk.init();
 
     const int pidx = lane >> SH;
@@ -120,29 +115,50 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
         }
     };
 
-    f32x2 acc2[V], xx2[R];  // (even, odd) partial sums, see scanmath.cuh
+    // f32 rows: (even, odd) partial sums in packed pairs; u8 rows: exact integer sums (scanmath.cuh)
+    constexpr bool U8 = PL == 4;
+    f32x2 acc2[U8 ? 1 : V], xx2[U8 ? 1 : R];
+    uint32_t acci[U8 ? V : 1], xxi[U8 ? R : 1];
+    if constexpr (U8) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc2[i] = 0ull;
+        for (int i = 0; i < V; ++i) acci[i] = 0u;
 #pragma unroll
-    for (int r = 0; r < R; ++r) xx2[r] = 0ull;
+        for (int r = 0; r < R; ++r) xxi[r] = 0u;
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc2[i] = 0ull;
+#pragma unroll
+        for (int r = 0; r < R; ++r) xx2[r] = 0ull;
+    }
     uint64_t g = pg;   // group being computed
     uint32_t it = 0, gi = 0;
     const ulonglong2* qp = qs2 + lane;  // this lane's chunk of query 0, plane 0
     bool want = false;
 
     auto accumulate = [&](const uint4 (&cur)[R]) {
+        if constexpr (U8) {
+            const uint4* qp4 = reinterpret_cast<const uint4*>(qp);
+            if (METRIC == VDB_COSINE) {
 #pragma unroll
-        for (int pl = 0; pl < PL; ++pl) {
+                for (int r = 0; r < R; ++r) xxi[r] = u8x16_acc<false>(xxi[r], cur[r], cur[r]);
+            }
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                const uint4 q = qp4[(size_t)qi * qs4];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acci[r * NQ + qi] = u8x16_acc<METRIC == VDB_L2SQR>(acci[r * NQ + qi], cur[r], q);
+            }
+        } else {
             f32x2 x01[R], x23[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) row_pairs<PL, BIASED>(cur[r], pl, x01[r], x23[r]);
+            for (int r = 0; r < R; ++r) row_pairs<1, false>(cur[r], 0, x01[r], x23[r]);
             if (METRIC == VDB_COSINE) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) xx2[r] = chunk_acc<false>(xx2[r], x01[r], x23[r], x01[r], x23[r]);
             }
 #pragma unroll
             for (int qi = 0; qi < NQ; ++qi) {
-                const ulonglong2 q = qp[(size_t)qi * qs4 + (size_t)pl * plane4];
+                const ulonglong2 q = qp[(size_t)qi * qs4];
 #pragma unroll
                 for (int r = 0; r < R; ++r)
                     acc2[r * NQ + qi] = chunk_acc<METRIC == VDB_L2SQR>(acc2[r * NQ + qi], x01[r], x23[r], q.x, q.y);
@@ -153,23 +169,43 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     auto finish = [&]() {
         if (++it < p.nit) return;
         // ---- end of a row group: cross-lane reduction, lane L then holds the total of (row my_r, query my_q) ----
-        float acc[V], xx[R];
+        float tot, xr = 0.f;
+        if constexpr (U8) {
+            uint32_t ti[V], xi[R];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            acc[i] = sum2(acc2[i]);
-            acc2[i] = 0ull;
-        }
+            for (int i = 0; i < V; ++i) {
+                ti[i] = acci[i];
+                acci[i] = 0u;
+            }
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            xx[r] = sum2(xx2[r]);
-            xx2[r] = 0ull;
+            for (int r = 0; r < R; ++r) {
+                xi[r] = xxi[r];
+                xxi[r] = 0u;
+            }
+            tot = (float)warp_reduce_scatter<V>(ti, lane);   // integer total, converted once
+            if (METRIC == VDB_COSINE) {
+                const uint32_t xs = warp_reduce_scatter<R>(xi, lane);
+                xr = (float)__shfl_sync(0xffffffffu, xs, my_r << SHR);
+            }
+        } else {
+            float acc[V], xx[R];
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                acc[i] = sum2(acc2[i]);
+                acc2[i] = 0ull;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                xx[r] = sum2(xx2[r]);
+                xx2[r] = 0ull;
+            }
+            tot = warp_reduce_scatter<V>(acc, lane);
+            if (METRIC == VDB_COSINE) {
+                const float xs = warp_reduce_scatter<R>(xx, lane);
+                xr = __shfl_sync(0xffffffffu, xs, my_r << SHR);
+            }
         }
-        float tot = warp_reduce_scatter<V>(acc, lane);
-        if (METRIC == VDB_COSINE) {
-            const float xs = warp_reduce_scatter<R>(xx, lane);
-            const float xr = __shfl_sync(0xffffffffu, xs, my_r << SHR);
-            tot = 1.0f - tot / fmaxf(sqrtf(xr) * qn, 1e-10f);
-        }
+        if (METRIC == VDB_COSINE) tot = 1.0f - tot / fmaxf(sqrtf(xr) * qn, 1e-10f);
         const uint64_t row = g * R + my_r;
         if (emitter && row < p.n) {
             const uint64_t key = make_key(tot, p.id_base + (uint32_t)row);
@@ -458,23 +494,45 @@ __global__ void prepare_queries_kernel(const T* __restrict__ src, uint32_t dim, 
     }
 }
 
+// u8 sets: the tile holds the queries' BYTES, zero padded to nit * 512 bytes per query (lane L of step it reads bytes
+// [(it*32 + L) * 16, +16), exactly the bytes it loads from a row), and the cache is computed in integers (exact)
+__global__ void prepare_queries_u8_kernel(const uint8_t* __restrict__ src, uint32_t dim, uint32_t qbytes, int metric,
+                                          uint8_t* __restrict__ tile, float* __restrict__ qcache) {
+    const uint32_t q = blockIdx.x;
+    __shared__ unsigned long long total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    unsigned long long ss = 0;
+    for (uint32_t i = threadIdx.x; i < qbytes; i += blockDim.x) {
+        const uint32_t v = i < dim ? src[(size_t)q * dim + i] : 0u;
+        tile[(size_t)q * qbytes + i] = (uint8_t)v;
+        ss += v * v;
+    }
+    atomicAdd(&total, ss);
+    __syncthreads();
+    if (threadIdx.x == 0) qcache[q] = metric == VDB_COSINE ? sqrtf((float)total) : (float)total;
+}
+
 QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st) {
     QueryTile t;
     const uint32_t vec = vec_elems(ds->dtype);
     t.nvec = ds->pitch / vec;
     t.nit = ceil_div(t.nvec, 32u);
-    t.qstride = t.nit * 32 * vec;
+    // floats per query for f32 sets; for u8 sets the same count of 4-byte words (= nit * 512 bytes of query bytes), so
+    // qstride * 4 is the tile's size in bytes per query for both
+    t.qstride = ds->dtype == VDB_F32 ? t.nit * 32 * vec : t.nit * 32 * 4;
     t.q = DevBuf((size_t)nq * t.qstride * 4, st);
     t.qcache = DevBuf((size_t)nq * 4, st);
     if (nq == 0) return t;
-    if (ds->dtype == VDB_F32)
+    if (ds->dtype == VDB_F32) {
         prepare_queries_kernel<float><<<nq, 256, 0, st>>>((const float*)d_queries, ds->dim, vec, t.nit,
                                                          t.qstride, ds->metric, t.q.as<float>(),
                                                          t.qcache.as<float>());
-    else
-        prepare_queries_kernel<uint8_t><<<nq, 256, 0, st>>>((const uint8_t*)d_queries, ds->dim, vec, t.nit,
-                                                           t.qstride, ds->metric, t.q.as<float>(),
-                                                           t.qcache.as<float>());
+    } else {
+        VDB_REQUIRE(ds->dim <= 65536, "u8 rows: dim %u too large for the 32-bit integer sums (max 65536)", ds->dim);
+        prepare_queries_u8_kernel<<<nq, 256, 0, st>>>((const uint8_t*)d_queries, ds->dim, t.qstride * 4, ds->metric,
+                                                      t.q.as<uint8_t>(), t.qcache.as<float>());
+    }
     VDB_LAUNCHED();
     return t;
 }

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
     constexpr int R = IVF_R;
     const uint32_t q = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t qs4 = p.qstride >> 2, plane4 = p.nit * 32;
+    const uint32_t qs4 = p.qstride >> 2;
     float4* qs = reinterpret_cast<float4*>(smem);
     const ulonglong2* qs2 = reinterpret_cast<const ulonglong2*>(smem);
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)p.qstride * 4);
@@ -96,9 +96,12 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
             }
             rid[r] = id;
         }
-        f32x2 acc2[R], xx2[R];  // (even, odd) chains of scanmath.cuh: the streaming scan's distance bits
+        // f32 rows: (even, odd) chains of scanmath.cuh; u8 rows: exact integer sums - the streaming scan's distance bits
+        constexpr bool U8 = PL == 4;
+        f32x2 acc2[R], xx2[R];
+        uint32_t acci[R], xxi[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc2[r] = 0ull, xx2[r] = 0ull;
+        for (int r = 0; r < R; ++r) acc2[r] = 0ull, xx2[r] = 0ull, acci[r] = 0u, xxi[r] = 0u;
         if (active) {
             for (uint32_t it = 0; it < p.nit; ++it) {
                 const uint32_t c = it * 32 + lane;
@@ -108,27 +111,37 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
                     v[r] = (c < p.nvec && rid[r] != 0xffffffffu)
                                ? ldg_stream_u4(p.rows + (uint64_t)rid[r] * p.pitch_bytes + (size_t)c * 16)
                                : make_uint4(0u, 0u, 0u, 0u);
+                if constexpr (U8) {
+                    const uint4 qb = reinterpret_cast<const uint4*>(qs2)[c];
 #pragma unroll
-                for (int pl = 0; pl < PL; ++pl) {
-                    const ulonglong2 qv = qs2[(size_t)pl * plane4 + c];
+                    for (int r = 0; r < R; ++r) {
+                        acci[r] = u8x16_acc<METRIC == VDB_L2SQR>(acci[r], v[r], qb);
+                        if (METRIC == VDB_COSINE) xxi[r] = u8x16_acc<false>(xxi[r], v[r], v[r]);
+                    }
+                } else {
+                    const ulonglong2 qv = qs2[c];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         f32x2 x01, x23;
-                        row_pairs<PL, false>(v[r], pl, x01, x23);
+                        row_pairs<1, false>(v[r], 0, x01, x23);
                         acc2[r] = chunk_acc<METRIC == VDB_L2SQR>(acc2[r], x01, x23, qv.x, qv.y);
                         if (METRIC == VDB_COSINE) xx2[r] = chunk_acc<false>(xx2[r], x01, x23, x01, x23);
                     }
                 }
             }
         }
-        float acc[R], xx[R];
+        float tot, xs = 0.f;
+        if constexpr (U8) {
+            tot = (float)warp_reduce_scatter<R>(acci, lane);  // lane L holds row L >> 2
+            if (METRIC == VDB_COSINE) xs = (float)warp_reduce_scatter<R>(xxi, lane);
+        } else {
+            float acc[R], xx[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = sum2(acc2[r]), xx[r] = sum2(xx2[r]);
-        float tot = warp_reduce_scatter<R>(acc, lane);  // lane L holds row L >> 2
-        if (METRIC == VDB_COSINE) {
-            const float xs = warp_reduce_scatter<R>(xx, lane);
-            tot = 1.0f - tot / fmaxf(sqrtf(xs) * qn, 1e-10f);
+            for (int r = 0; r < R; ++r) acc[r] = sum2(acc2[r]), xx[r] = sum2(xx2[r]);
+            tot = warp_reduce_scatter<R>(acc, lane);  // lane L holds row L >> 2
+            if (METRIC == VDB_COSINE) xs = warp_reduce_scatter<R>(xx, lane);
         }
+        if (METRIC == VDB_COSINE) tot = 1.0f - tot / fmaxf(sqrtf(xs) * qn, 1e-10f);
         const int my_r = lane >> 2;
         uint32_t my_id = 0xffffffffu;
 #pragma unroll
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
     constexpr int SH = 5 - Log2<V>::value, SHR = 5 - Log2<R>::value;
     const IvfItem item = p.items[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t qs4 = p.qstride >> 2, plane4 = p.nit * 32;
+    const uint32_t qs4 = p.qstride >> 2;
     float4* qs = reinterpret_cast<float4*>(smem);
     const ulonglong2* qs2 = reinterpret_cast<const ulonglong2*>(smem);
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)NQ * p.qstride * 4);
@@ -211,11 +224,20 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
             const uint32_t pos = g * R + r;
             rid[r] = pos < item.nrows ? mem[pos] : 0xffffffffu;
         }
-        f32x2 acc2[V], xx2[R];
+        constexpr bool U8 = PL == 4;   // u8 rows: exact integer sums (scanmath.cuh)
+        f32x2 acc2[U8 ? 1 : V], xx2[U8 ? 1 : R];
+        uint32_t acci[U8 ? V : 1], xxi[U8 ? R : 1];
+        if constexpr (U8) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc2[i] = 0ull;
+            for (int i = 0; i < V; ++i) acci[i] = 0u;
 #pragma unroll
-        for (int r = 0; r < R; ++r) xx2[r] = 0ull;
+            for (int r = 0; r < R; ++r) xxi[r] = 0u;
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc2[i] = 0ull;
+#pragma unroll
+            for (int r = 0; r < R; ++r) xx2[r] = 0ull;
+        }
         if (g < groups) {
             uint4 nxt[R], cur[R];
             auto load = [&](uint32_t it) {
@@ -232,18 +254,28 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
                 for (int r = 0; r < R; ++r) cur[r] = nxt[r];
                 if (it + 1 < p.nit) load(it + 1);
                 const uint32_t c = it * 32 + lane;
+                if constexpr (U8) {
+                    if (METRIC == VDB_COSINE) {
 #pragma unroll
-                for (int pl = 0; pl < PL; ++pl) {
+                        for (int r = 0; r < R; ++r) xxi[r] = u8x16_acc<false>(xxi[r], cur[r], cur[r]);
+                    }
+#pragma unroll
+                    for (int qi = 0; qi < NQ; ++qi) {
+                        const uint4 qb = reinterpret_cast<const uint4*>(qs2)[(size_t)qi * qs4 + c];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acci[r * NQ + qi] = u8x16_acc<METRIC == VDB_L2SQR>(acci[r * NQ + qi], cur[r], qb);
+                    }
+                } else {
                     f32x2 x01[R], x23[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) row_pairs<PL, false>(cur[r], pl, x01[r], x23[r]);
+                    for (int r = 0; r < R; ++r) row_pairs<1, false>(cur[r], 0, x01[r], x23[r]);
                     if (METRIC == VDB_COSINE) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) xx2[r] = chunk_acc<false>(xx2[r], x01[r], x23[r], x01[r], x23[r]);
                     }
 #pragma unroll
                     for (int qi = 0; qi < NQ; ++qi) {
-                        const ulonglong2 qv = qs2[(size_t)qi * qs4 + (size_t)pl * plane4 + c];
+                        const ulonglong2 qv = qs2[(size_t)qi * qs4 + c];
 #pragma unroll
                         for (int r = 0; r < R; ++r)
                             acc2[r * NQ + qi] = chunk_acc<METRIC == VDB_L2SQR>(acc2[r * NQ + qi], x01[r], x23[r], qv.x, qv.y);
@@ -251,17 +283,26 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
                 }
             }
         }
-        float acc[V], xx[R];
+        float tot, xr = 0.f;
+        if constexpr (U8) {
+            tot = (float)warp_reduce_scatter<V>(acci, lane);
+            if (METRIC == VDB_COSINE) {
+                const uint32_t xs = warp_reduce_scatter<R>(xxi, lane);
+                xr = (float)__shfl_sync(0xffffffffu, xs, my_r << SHR);
+            }
+        } else {
+            float acc[V], xx[R];
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = sum2(acc2[i]);
+            for (int i = 0; i < V; ++i) acc[i] = sum2(acc2[i]);
 #pragma unroll
-        for (int r = 0; r < R; ++r) xx[r] = sum2(xx2[r]);
-        float tot = warp_reduce_scatter<V>(acc, lane);
-        if (METRIC == VDB_COSINE) {
-            const float xs = warp_reduce_scatter<R>(xx, lane);
-            const float xr = __shfl_sync(0xffffffffu, xs, my_r << SHR);
-            tot = 1.0f - tot / fmaxf(sqrtf(xr) * qn, 1e-10f);
+            for (int r = 0; r < R; ++r) xx[r] = sum2(xx2[r]);
+            tot = warp_reduce_scatter<V>(acc, lane);
+            if (METRIC == VDB_COSINE) {
+                const float xs = warp_reduce_scatter<R>(xx, lane);
+                xr = __shfl_sync(0xffffffffu, xs, my_r << SHR);
+            }
         }
+        if (METRIC == VDB_COSINE) tot = 1.0f - tot / fmaxf(sqrtf(xr) * qn, 1e-10f);
         uint32_t my_id = 0xffffffffu;
 #pragma unroll
         for (int r = 0; r < R; ++r)

@@ -5,6 +5,8 @@
 //   DistanceAdapter<[T],[T]>::distance            reference src/distance/mod.rs:106-113
 //   DistanceAdapter<(&[T],f32),(&[T],f32)>        src/distance/mod.rs:120-129 (cached forms :54-57, :67-69)
 //   DistanceAlgorithm::dist_cache                 src/distance/mod.rs:31-36
+#include <type_traits>
+
 #include "dataset.cuh"
 #include "scanmath.cuh"
 
@@ -46,6 +48,24 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
         const TA* a = (const TA*)p.A + ia * p.strideA;
         const TB* b = (const TB*)p.B + ib * p.strideB;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        // u8 rows in the scan-order modes: exact integer sums like the streaming scan (scanmath.cuh), reduced in
+        // integers and converted once - the same bits whatever the order
+        constexpr bool INT_SUMS = (MODE == PM_L2_SCANORDER || MODE == PM_COS_SCANORDER) && std::is_same<TB, uint8_t>::value;
+        if constexpr (INT_SUMS) {
+            uint32_t si = 0, xi = 0;
+            for (uint32_t e = lane; e < p.dim; e += 32) {
+                const uint32_t xv = b[e], qv = (uint32_t)a[e];
+                if (MODE == PM_L2_SCANORDER) {
+                    const uint32_t d = xv > qv ? xv - qv : qv - xv;
+                    si += d * d;
+                } else {
+                    si += xv * qv;
+                    xi += xv * xv;
+                }
+            }
+            s0 = (float)__reduce_add_sync(0xffffffffu, si);
+            if (MODE == PM_COS_SCANORDER) s1 = (float)__reduce_add_sync(0xffffffffu, xi);
+        } else
         if (MODE == PM_L2_SCANORDER || MODE == PM_COS_SCANORDER) {
             // same per-lane chains (float4 chunk c = it*32 + lane, even / odd elements, see scanmath.cuh) and the same
             // xor-butterfly as the streaming scan kernel (flat_scan.cu), so both Flat paths return bit-identical distances
@@ -111,14 +131,16 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const PairParams p) {
                 }
             }
         }
+        if constexpr (!INT_SUMS) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            if (MODE == PM_COSINE) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                if (MODE == PM_COSINE) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (MODE == PM_COS_SCANORDER) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             }
-            if (MODE == PM_COS_SCANORDER) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         }
         if (lane == 0) {
             float r = s0;

@@ -90,6 +90,33 @@ __device__ __forceinline__ f32x2 chunk_acc(f32x2 a, f32x2 x01, f32x2 x23, f32x2 
     return a;
 }
 
+// ---- u8 rows: exact integer arithmetic ------------------------------------------------------------------------------
+// Rows and queries of a u8 set are bytes, so (x - q)^2, x * q and x * x are small integers: four of them per
+// instruction with VABSDIFF4 + IDP.4A into a u32 accumulator (960 x 255^2 < 2^26; the entry points require
+// dim <= 65536 so the sum cannot wrap). Integer sums are order-independent, i.e. the scan, the IVF scans and the rerank
+// agree bit for bit by construction, and the total is converted to f32 once (exact below 2^24, which is also where the
+// reference's sequential f32 sum of the same integers is exact).
+__device__ __forceinline__ uint32_t u8x4_l2(uint32_t x, uint32_t q, uint32_t acc) {
+    const uint32_t d = __vabsdiffu4(x, q);
+    return __dp4a(d, d, acc);
+}
+__device__ __forceinline__ uint32_t u8x4_dot(uint32_t x, uint32_t q, uint32_t acc) { return __dp4a(x, q, acc); }
+template <bool L2>
+__device__ __forceinline__ uint32_t u8x16_acc(uint32_t acc, const uint4& x, const uint4& q) {
+    if constexpr (L2) {
+        acc = u8x4_l2(x.x, q.x, acc);
+        acc = u8x4_l2(x.y, q.y, acc);
+        acc = u8x4_l2(x.z, q.z, acc);
+        acc = u8x4_l2(x.w, q.w, acc);
+    } else {
+        acc = u8x4_dot(x.x, q.x, acc);
+        acc = u8x4_dot(x.y, q.y, acc);
+        acc = u8x4_dot(x.z, q.z, acc);
+        acc = u8x4_dot(x.w, q.w, acc);
+    }
+    return acc;
+}
+
 // the two chains of chunk_acc with scalar instructions on a float2 (x = even chain, y = odd chain): bit-identical
 // (measured in the 8-query scan: same speed as the packed forms)
 __device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {

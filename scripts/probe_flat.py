@@ -11,8 +11,12 @@ from lab_1806_vec_db_b200 import _lib as L
 n = int(os.environ.get("N", 1_000_000)); dim = int(os.environ.get("DIM", 960))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(42)
+u8 = os.environ.get("DTYPE", "f32") == "u8"
 base = torch.rand((n, dim), device=dev, generator=g, dtype=torch.float32)
-ds = V.DeviceVecSet.from_device(base.data_ptr(), n, dim, dim, np.float32, os.environ.get("METRIC", "l2sqr"), keepalive=base)
+if u8:
+    base = (base * 255).round().to(torch.uint8)
+esz = 1 if u8 else 4
+ds = V.DeviceVecSet.from_device(base.data_ptr(), n, dim, dim, np.uint8 if u8 else np.float32, os.environ.get("METRIC", "l2sqr"), keepalive=base)
 lib = L.lib()
 L.check(lib.vdb_flat_set_path(1))
 stream = torch.cuda.current_stream().cuda_stream
@@ -21,6 +25,8 @@ if os.environ.get("CASES"):  # e.g. CASES=8:10,4:10
     cases = [tuple(int(v) for v in c.split(":")) for c in os.environ["CASES"].split(",")]
 for nq, k in cases:
     q = torch.rand((nq, dim), device=dev, generator=g)
+    if u8:
+        q = (q * 255).round().to(torch.uint8)
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev); dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
     cnt = torch.empty(nq, dtype=torch.int32, device=dev)
     def run():
@@ -35,5 +41,5 @@ for nq, k in cases:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     passes = (nq + 7) // 8
-    gbs = passes * n * dim * 4 / ms / 1e6
+    gbs = passes * n * dim * esz / ms / 1e6
     print(f"nq={nq:3d} k={k:4d}: {ms:8.3f} ms/call  {nq/ms*1e3:9.1f} QPS  {gbs:7.1f} GB/s ({gbs/6551.4*100:5.1f}% of measured HBM peak)", flush=True)
