@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
         } else {
             f32x2 x01[R], x23[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) row_pairs<1, false>(cur[r], 0, x01[r], x23[r]);
+            for (int r = 0; r < R; ++r) row_pairs(cur[r], x01[r], x23[r]);
             if (METRIC == VDB_COSINE) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) xx2[r] = chunk_acc<false>(xx2[r], x01[r], x23[r], x01[r], x23[r]);

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(IVF_THREADS) ivf_scan_kernel(const IvfScanPara
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         f32x2 x01, x23;
-                        row_pairs<1, false>(v[r], 0, x01, x23);
+                        row_pairs(v[r], x01, x23);
                         acc2[r] = chunk_acc<METRIC == VDB_L2SQR>(acc2[r], x01, x23, qv.x, qv.y);
                         if (METRIC == VDB_COSINE) xx2[r] = chunk_acc<false>(xx2[r], x01, x23, x01, x23);
                     }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(IVF_THREADS, 2) ivf_list_scan_kernel(const Ivf
                 } else {
                     f32x2 x01[R], x23[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) row_pairs<1, false>(cur[r], 0, x01[r], x23[r]);
+                    for (int r = 0; r < R; ++r) row_pairs(cur[r], x01[r], x23[r]);
                     if (METRIC == VDB_COSINE) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) xx2[r] = chunk_acc<false>(xx2[r], x01[r], x23[r], x01[r], x23[r]);

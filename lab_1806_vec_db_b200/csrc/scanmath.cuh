@@ -1,21 +1,20 @@
 // scanmath.cuh — the per-lane arithmetic of every "scan order" distance kernel (K1 flat_scan, K9 ivf scans, the
-// K2b rerank in pairs.cu), written with Blackwell's packed FP32 instructions.
+// K2b rerank in pairs.cu): packed FP32 pairs for f32 rows, exact integer byte arithmetic for u8 rows (further down).
 //
 // FFMA2/FADD2 (PTX fma/sub.rn.f32x2 on a 64-bit register pair) do two lanes' worth of FP32 work per issue slot.
 // Measured on B200 (scripts/ubench/fp32_rate.cu): scalar FFMA/FADD reach 1 warp instruction per clock and scheduler
 // = 128 lane-ops/clk/SM, the packed forms 0.5 per clock = the same 128 lane-ops/clk/SM. So they do not raise the FP32
-// ceiling, they free issue slots: the HBM-bound variants of the scan (1-2 queries per row byte, k = 100, cosine, u8
-// rows) gained 4-9 % with them, the FP32-bound 8-query variant did not (and pays for the second accumulator chain).
+// ceiling, they free issue slots: the HBM-bound variants of the scan (1-2 queries per row byte, k = 100, cosine)
+// gained 4-9 % with them, the FP32-bound 8-query variant did not (and pays for the second accumulator chain).
 // NB ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false, unlike the scalar forms, so the
 // bit-exact kernels (k-means assignment, PQ encode: rustc's unfused arithmetic) must not use them.
 //
 // Summation order (shared by all of these kernels, which is why the tensor-core path's rerank and the IVF probe
-// scans return the streaming scan's distance BITS): a lane owns the 4-element chunks c = it*32 + lane of a row
-// (16-element chunks for u8 rows, walked as four 4-element sub-chunks); inside a chunk the elements 0 and 2 go
-// to the EVEN chain, 1 and 3 to the ODD chain, each chain an fma sequence in chunk order; the lane's total is
+// scans return the streaming scan's distance BITS): a lane owns the 4-element chunks c = it*32 + lane of a row;
+// inside a chunk the elements 0 and 2 go to the EVEN chain, 1 and 3 to the ODD chain, each chain an fma sequence in chunk order; the lane's total is
 // even + odd; lanes are combined by the xor butterfly (warp_reduce_scatter pairs partners the same way).
 // Each half of a packed instruction is an IEEE fma/add, so a scalar kernel that follows the same two chains
-// produces the same bits (pairs.cu does for unaligned / u8 operands).
+// produces the same bits (pairs.cu does for unaligned operands).
 #pragma once
 #include "common.cuh"
 
@@ -49,31 +48,10 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return r;
 }
 
-constexpr float U8_BIAS = 8388608.0f;  // 2^23: 0x4B0000bb is the float 2^23 + bb
-
-__device__ __forceinline__ uint32_t u4_word(const uint4& u, int i) {
-    return i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w));
-}
-
-// One 16-byte load of a row -> the (x0,x1), (x2,x3) pairs of 4-element sub-chunk `pl`.
-// PL = 1: f32 rows (pl = 0). PL = 4: u8 rows, byte -> f32 without the quarter-rate I2F: one PRMT builds the bit
-// pattern of 2^23 + byte; BIASED keeps that bias (the caller's query values carry the same bias, so the L2
-// difference is exact and the conversion costs nothing), otherwise one packed subtract removes it.
-template <int PL, bool BIASED>
-__device__ __forceinline__ void row_pairs(const uint4& u, int pl, f32x2& x01, f32x2& x23) {
-    if constexpr (PL == 1) {
-        x01 = pk2(u.x, u.y);
-        x23 = pk2(u.z, u.w);
-    } else {
-        const uint32_t w = u4_word(u, pl);
-        x01 = pk2(__byte_perm(w, 0x4B000000u, 0x7650), __byte_perm(w, 0x4B000000u, 0x7651));
-        x23 = pk2(__byte_perm(w, 0x4B000000u, 0x7652), __byte_perm(w, 0x4B000000u, 0x7653));
-        if constexpr (!BIASED) {
-            const f32x2 m = pk2f(U8_BIAS, U8_BIAS);
-            x01 = sub2(x01, m);
-            x23 = sub2(x23, m);
-        }
-    }
+// One 16-byte load of an f32 row -> its (x0,x1), (x2,x3) pairs
+__device__ __forceinline__ void row_pairs(const uint4& u, f32x2& x01, f32x2& x23) {
+    x01 = pk2(u.x, u.y);
+    x23 = pk2(u.z, u.w);
 }
 
 // a += the chunk's contribution: L2Sqr -> (x - q)^2, otherwise x * q
