@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     // t & 1 while the loads of step t + 1 land in the other buffer, so nothing is copied between buffers and the
     // prefetch runs across group boundaries. Addressing is incremental: one pointer per lane, rows of the group at
     // r * pitch from it; the clamped (last group) and ragged (row end inside the last chunk) cases take a slow path.
-    constexpr bool SINGLE = PL == 4 && NQ >= 4;  // measured: only the u8 variants gain (0.98 -> 0.89 ms at 8 queries)
+    constexpr bool SINGLE = PL == 4 && NQ >= 4;  // one buffer for u8 rows with 4-8 queries (measured with the earlier FP32 u8 arithmetic: 0.98 -> 0.89 ms; f32 rows lose)
     // 4 f32 queries: 32 accumulator registers leave room for a third buffer, i.e. two 512-byte steps in flight per
     // warp (64 KB per SM like the 1- and 2-query variants with their 8-row groups)
     constexpr bool TRIPLE = NQ == 4 && PL == 1;
