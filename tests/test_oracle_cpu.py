@@ -177,3 +177,21 @@ def test_result_set_boundary_semantics(oracle):
 def test_recall(oracle):
     """candidate_pair.rs:127-140."""
     assert oracle.recall([1, 2, 3, 4], [4, 3, 9, 8]) == 0.5
+
+
+def test_u8_l2_is_an_exact_integer_below_2_pow_24(oracle):
+    """The reference casts u8 to f32 and sums (x - q)^2 sequentially in f32 (distance/mod.rs:86-94): every term and,
+    below 2^24, every partial sum is an integer, so the reference value IS the exact integer sum. The CUDA path computes
+    that integer directly (VABSDIFF4 + IDP.4A, csrc/scanmath.cuh) and converts it once - bit-identical in this range,
+    which covers GIST-shaped u8 data (960 dims, values around 18: sums of a few 10^5)."""
+    rng = np.random.default_rng(5)
+    for dim, hi in ((960, 64), (960, 256), (100, 256), (17, 256)):
+        a = rng.integers(0, hi, (50, dim), dtype=np.uint8)
+        b = rng.integers(0, hi, (50, dim), dtype=np.uint8)
+        exact = ((a.astype(np.int64) - b.astype(np.int64)) ** 2).sum(axis=1)
+        for i in range(50):
+            d = oracle.distance(a[i], b[i], "l2sqr")
+            if exact[i] < (1 << 24):
+                assert float(d) == float(exact[i])
+            else:   # above 2^24 the sequential f32 sum rounds: still within the parity rule of the exact value
+                assert abs(float(d) - float(exact[i])) <= 1e-5 * float(exact[i])
