@@ -195,3 +195,20 @@ def test_u8_l2_is_an_exact_integer_below_2_pow_24(oracle):
                 assert float(d) == float(exact[i])
             else:   # above 2^24 the sequential f32 sum rounds: still within the parity rule of the exact value
                 assert abs(float(d) - float(exact[i])) <= 1e-5 * float(exact[i])
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_u8_flat_oracle_equals_numpy_emulation(fixtures, oracle, metric):
+    """The reference's other scalar type (Scalar for u8, scalar.rs:39-46; u8 distances cast to f32 first,
+    distance/mod.rs:80-94): oracle == independent numpy emulation, bit for bit, on the byte-quantised GIST fixture
+    (values x 255, rounded) - 120 queries x 1000 rows x 960 dims, k = 10."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import np_emul as E
+    base = np.clip(np.rint(fixtures["base"] * 255.0), 0, 255).astype(np.uint8)
+    q = np.clip(np.rint(fixtures["test"][:120] * 255.0), 0, 255).astype(np.uint8)
+    ids, dd, cnt = oracle.flat_knn(base, q, 10, metric, os.cpu_count())
+    eids, edd = E.flat_knn(base, q, 10, metric)
+    assert (cnt == 10).all()
+    assert (ids.astype(np.int64) == eids).all()
+    assert (bits(dd) == bits(edd)).all()
