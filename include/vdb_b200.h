@@ -46,6 +46,14 @@ int vdb_device_count(int* out);
 /* Selects the CUDA device used by handles created afterwards on this thread. */
 int vdb_set_device(int device);
 
+/* Registers the devices of this process (SURVEY.md section 8b `vdb_init(devices[], n)`) and enables peer access between
+ * every pair (NVLink P2P). With n >= 2, vdb_dataset_create row-shards the set over them - contiguous blocks, shard s on
+ * devices[s] - and vdb_flat_knn on that handle is ONE call that runs on every device and merges
+ * the per-GPU top-k over peer memory: the reference's `knn` (src/index_algorithm/mod.rs:84-91) stays one call whatever
+ * the GPU count. A device may be listed more than once (several shards on one GPU; used by the single-GPU tests of the
+ * sharded path). n == 1 selects that device for the calling thread; n == 0 returns to single-device mode. */
+int vdb_init(const int* devices, uint32_t n);
+
 /* ---- VecSet mirror -------------------------------------------------------------------------- */
 /* Replaces the storage side of FlatIndex::from_vec_set (src/index_algorithm/flat_index.rs:59-70):
  * uploads `n` rows to HBM (rows padded to a 16-byte multiple so every row starts 128-bit aligned).
@@ -57,6 +65,14 @@ int vdb_dataset_create(const void* rows, uint64_t n, uint32_t dim, int dtype, in
  * must be a multiple of 16 and pad columns must be zero). The memory is NOT owned by the handle. */
 int vdb_dataset_create_dev(const void* d_rows, uint64_t n, uint32_t dim, uint32_t pitch, int dtype,
                            int metric, uint64_t id_base, vdb_dataset** out);
+/* Row-sharded set over rows already resident on the shards' devices: d_rows[s] holds counts[s] rows (global rows
+ * [sum(counts[:s]), ...)) on devices[s], all with the same pitch. The memory is NOT owned by the handle. */
+int vdb_dataset_create_sharded_dev(const void* const* d_rows, const uint64_t* counts, const int* devices, uint32_t nshards,
+                                   uint32_t dim, uint32_t pitch, int dtype, int metric, uint64_t id_base, vdb_dataset** out);
+/* Number of shards (0 for an unsharded set) and shard s: its own dataset handle (owned by the parent; valid for the
+ * per-shard entry points such as vdb_ivf_create / vdb_pq_create), device and global row block. Outputs may be NULL. */
+int vdb_dataset_shards(const vdb_dataset* ds, uint32_t* n);
+int vdb_dataset_shard(const vdb_dataset* ds, uint32_t s, vdb_dataset** shard, int* device, uint64_t* row_lo, uint64_t* row_hi);
 /* VecSet::push / DynamicIndex::batch_add (src/vec_set.rs:113-118, src/database/dynamic_index.rs:49-56) */
 int vdb_dataset_append(vdb_dataset* ds, const void* rows, uint64_t n);
 /* VecSet::swap_remove (src/vec_set.rs:131-137): row `idx` is overwritten by the last row. */
@@ -90,6 +106,12 @@ int vdb_flat_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32
                  float* dist, uint32_t* counts);
 int vdb_flat_knn_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
                      uint64_t* d_ids, float* d_dist, uint32_t* d_counts, void* stream);
+/* The same on a row-sharded set with the batch already resident on every shard's device: d_queries[s] = the whole
+ * [nq, dim] batch on shard s's device. Shard s OWNS the queries [s * per, min(nq, (s + 1) * per)), per = ceil(nq / G),
+ * and receives their merged results in d_ids[s] / d_dist[s] / d_counts[s] (arrays of at least `per` rows on its
+ * device). nq <= 16384 per call. Synchronous: every shard's stream has drained on return. */
+int vdb_flat_knn_sharded_dev(const vdb_dataset* ds, const void* const* d_queries, uint32_t nq, uint32_t k,
+                             uint64_t* const* d_ids, float* const* d_dist, uint32_t* const* d_counts);
 /* Row-sharded search, step 1: this shard's k best per query as packed sortable keys
  * (high 32 bits = order-preserving distance bits, low 32 bits = global id), [nq, k], ascending,
  * padded with UINT64_MAX. Step 2 (after an NCCL all-gather of the shards' keys):
@@ -101,6 +123,8 @@ int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
 /* Selects the Flat implementation: 0 = auto, 1 = FP32 streaming scan (K1), 2 = tensor-core
  * contraction + FP32 rerank (K2, batched L2Sqr f32 only). Results are identical either way. */
 int vdb_flat_set_path(int path);
+/* The same selection for ONE handle (-1 = follow the process default set by vdb_flat_set_path). */
+int vdb_dataset_set_flat_path(vdb_dataset* ds, int path);
 
 /* ---- k-means (IVF / PQ training) ---------------------------------------------------------- */
 /* find_nearest for n rows (src/distance/k_means.rs:40-57, 117-120, 166-170;
@@ -237,6 +261,10 @@ int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint
 uint64_t vdb_flat_gemm_fallbacks(void);
 /* Cumulative counters of the tensor path: queries served, candidates reranked, queries re-run exactly. */
 int vdb_flat_gemm_stats(uint64_t* queries, uint64_t* candidates, uint64_t* fallbacks);
+
+/* Test hook: every query whose batch index is a multiple of `every` fails the tensor path's completeness check and is
+ * re-run through the exact scan (0 = off), so that the fallback of the single-GPU and the sharded search can be tested. */
+int vdb_debug_force_redo(uint32_t every);
 
 /* Row-sharded IVF: this shard's [nq, k] packed keys (merge the shards' lists with vdb_merge_keys_dev). */
 int vdb_ivf_knn_keys_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,

@@ -6,5 +6,6 @@ hand-written sm_100a CUDA kernels (csrc/); there is no CPU fallback.
 """
 from ._lib import VdbError, lib  # noqa: F401
 from .index import (CandidatePair, DeviceVecSet, FlatIndex, HNSWConfig, HNSWIndex, IVFConfig, IVFIndex, KMeans, KMeansConfig,  # noqa: F401
-                    PQConfig, PQTable, calc_dist, calc_dist_batch, dist_cache, gather_dist, hnsw_rand_levels, k_means_init,
+                    PQConfig, PQTable, calc_dist, calc_dist_batch, dist_cache, gather_dist, hnsw_rand_levels, init_devices,
+                    k_means_init,
                     pq_groups)

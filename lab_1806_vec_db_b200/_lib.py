@@ -31,6 +31,13 @@ SIGNATURES = {
     "vdb_version": (i32, []),
     "vdb_device_count": (i32, [vp]),
     "vdb_set_device": (i32, [i32]),
+    "vdb_init": (i32, [vp, u32]),
+    "vdb_dataset_create_sharded_dev": (i32, [vp, vp, vp, u32, u32, u32, i32, i32, u64, vp]),
+    "vdb_dataset_shards": (i32, [vp, vp]),
+    "vdb_dataset_shard": (i32, [vp, u32, vp, vp, vp, vp]),
+    "vdb_dataset_set_flat_path": (i32, [vp, i32]),
+    "vdb_flat_knn_sharded_dev": (i32, [vp, vp, u32, u32, vp, vp, vp]),
+    "vdb_debug_force_redo": (i32, [u32]),
     "vdb_dataset_create": (i32, [vp, u64, u32, i32, i32, u64, vp]),
     "vdb_dataset_create_dev": (i32, [vp, u64, u32, u32, i32, i32, u64, vp]),
     "vdb_dataset_append": (i32, [vp, vp, u64]),

@@ -9,6 +9,7 @@
 #include "index.cuh"
 #include "topk.cuh"
 
+#include <functional>
 #include <map>
 #include <mutex>
 
@@ -17,7 +18,7 @@ bool g_prof_on = false;
 namespace {
 struct ProfEntry {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
-    cudaEvent_t open = nullptr;
+    std::map<cudaStream_t, cudaEvent_t> open;   // per launching stream: several devices / threads record concurrently
 };
 std::mutex g_prof_mu;
 std::map<std::string, ProfEntry> g_prof;
@@ -28,15 +29,33 @@ void prof_record(const char* name, cudaStream_t st, bool begin) {
     cudaEvent_t ev;
     if (cudaEventCreate(&ev) != cudaSuccess) return;
     cudaEventRecord(ev, st);
+    auto it = e.open.find(st);
     if (begin) {
-        e.open = ev;
-    } else if (e.open) {
-        e.spans.emplace_back(e.open, ev);
-        e.open = nullptr;
+        if (it != e.open.end()) cudaEventDestroy(it->second);
+        e.open[st] = ev;
+    } else if (it != e.open.end()) {
+        e.spans.emplace_back(it->second, ev);
+        e.open.erase(it);
     } else {
         cudaEventDestroy(ev);
     }
 }
+}  // namespace vdb
+
+namespace vdb {
+// multi.cu
+std::vector<int> registered_devices();
+void init_devices(const int* devices, uint32_t n);
+vdb_dataset* sharded_create(const std::vector<int>& devs, uint64_t n, uint32_t dim, int dtype, int metric, uint64_t id_base,
+                            const std::vector<uint64_t>* counts,
+                            const std::function<vdb_dataset*(uint32_t, int, uint64_t, uint64_t)>& make_shard);
+void sharded_destroy(vdb_dataset* md);
+void sharded_flat_knn(const vdb_dataset* md, const void* queries, uint32_t nq, uint32_t k, uint64_t* ids, float* dist,
+                      uint32_t* counts);
+void sharded_flat_knn_dev(const vdb_dataset* md, const void* const* d_queries, uint32_t nq, uint32_t k, uint64_t* const* d_ids,
+                          float* const* d_dist, uint32_t* const* d_counts);
+uint32_t sharded_count(const vdb_dataset* md);
+void sharded_info(const vdb_dataset* md, uint32_t s, int* device, uint64_t* lo, uint64_t* hi, vdb_dataset** ds);
 }  // namespace vdb
 
 namespace {
@@ -86,6 +105,13 @@ int current_device() {
     int d = 0;
     VDB_CUDA(cudaGetDevice(&d));
     return d;
+}
+
+// device of an unsharded handle; entry points without a row-sharded implementation refuse a sharded parent
+int dev_of(const vdb_dataset* ds) {
+    if (ds->sharded) vdb::fail(VDB_EUNSUPPORTED, "this entry point has no row-sharded implementation: call it on the shards "
+                                                 "(vdb_dataset_shard) or on an unsharded dataset");
+    return ds->device;
 }
 
 void check_dtype_metric(int dtype, int metric) {
@@ -168,6 +194,58 @@ int vdb_set_device(int device) {
 }
 
 // ---- dataset -------------------------------------------------------------------------------------
+static vdb_dataset* upload_dataset_on(int device, const void* rows, uint64_t n, uint32_t dim, int dtype, int metric,
+                                      uint64_t id_base) {
+    auto ds = new vdb_dataset();
+    ds->device = device;
+    DeviceGuard g(device);
+    ds->dim = dim;
+    ds->dtype = dtype;
+    ds->metric = metric;
+    ds->id_base = id_base;
+    ds->pitch = vdb::round_up(dim, vdb::vec_elems(dtype));
+    ds->n = n;
+    ds->cap = std::max<uint64_t>(n, 1);
+    try {
+        VDB_CUDA(cudaMalloc(&ds->d_rows, ds->cap * ds->pitch_bytes()));
+        CallStream cs;
+        upload_rows(ds, 0, rows, n, cs.s);
+        cs.sync();
+    } catch (...) {
+        if (ds->d_rows) cudaFree(ds->d_rows);
+        delete ds;
+        throw;
+    }
+    return ds;
+}
+
+static vdb_dataset* adopt_dataset_on(int device, const void* d_rows, uint64_t n, uint32_t dim, uint32_t pitch, int dtype,
+                                     int metric, uint64_t id_base) {
+    VDB_REQUIRE(((uintptr_t)d_rows & 15) == 0, "device rows must be 16-byte aligned");
+    auto ds = new vdb_dataset();
+    ds->device = device;
+    ds->d_rows = const_cast<void*>(d_rows);
+    ds->owned = false;
+    ds->n = ds->cap = n;
+    ds->dim = dim;
+    ds->pitch = pitch;
+    ds->dtype = dtype;
+    ds->metric = metric;
+    ds->id_base = id_base;
+    return ds;
+}
+
+int vdb_init(const int* devices, uint32_t n) {
+    return guarded([&] {
+        VDB_REQUIRE(devices || n == 0, "devices is NULL");
+        vdb::init_devices(devices, n);
+        if (n == 1) {
+            VDB_CUDA(cudaSetDevice(devices[0]));
+            t_device = devices[0];
+        }
+    });
+}
+
 int vdb_dataset_create(const void* rows, uint64_t n, uint32_t dim, int dtype, int metric, uint64_t id_base,
                        vdb_dataset** out) {
     return guarded([&] {
@@ -176,27 +254,19 @@ int vdb_dataset_create(const void* rows, uint64_t n, uint32_t dim, int dtype, in
         VDB_REQUIRE(rows || n == 0, "rows is NULL");
         check_dtype_metric(dtype, metric);
         VDB_REQUIRE(id_base + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
-        auto ds = new vdb_dataset();
-        ds->device = current_device();
-        DeviceGuard g(ds->device);
-        ds->dim = dim;
-        ds->dtype = dtype;
-        ds->metric = metric;
-        ds->id_base = id_base;
-        ds->pitch = vdb::round_up(dim, vdb::vec_elems(dtype));
-        ds->n = n;
-        ds->cap = std::max<uint64_t>(n, 1);
-        try {
-            VDB_CUDA(cudaMalloc(&ds->d_rows, ds->cap * ds->pitch_bytes()));
-            CallStream cs;
-            upload_rows(ds, 0, rows, n, cs.s);
-            cs.sync();
-        } catch (...) {
-            if (ds->d_rows) cudaFree(ds->d_rows);
-            delete ds;
-            throw;
+        const std::vector<int> devs = vdb::registered_devices();
+        if (devs.size() > 1) {
+            // vdb_init registered several devices: contiguous row blocks, one per device
+            const size_t rb = (size_t)dim * (dtype == VDB_F32 ? 4 : 1);
+            *out = vdb::sharded_create(devs, n, dim, dtype, metric, id_base, nullptr,
+                                       [&](uint32_t, int device, uint64_t lo, uint64_t hi) {
+                                           return upload_dataset_on(device, (const uint8_t*)rows + lo * rb, hi - lo, dim, dtype,
+                                                                    metric, id_base + lo);
+                                       });
+            return;
         }
-        *out = ds;
+        *out = upload_dataset_on(devs.size() == 1 && t_device < 0 ? devs[0] : current_device(), rows, n, dim, dtype, metric,
+                                 id_base);
     });
 }
 
@@ -207,28 +277,64 @@ int vdb_dataset_create_dev(const void* d_rows, uint64_t n, uint32_t dim, uint32_
         VDB_REQUIRE(dim > 0 && pitch >= dim, "need 0 < dim <= pitch");
         check_dtype_metric(dtype, metric);
         VDB_REQUIRE(pitch % vdb::vec_elems(dtype) == 0, "row pitch must be a multiple of 16 bytes");
-        VDB_REQUIRE(((uintptr_t)d_rows & 15) == 0, "device rows must be 16-byte aligned");
         VDB_REQUIRE(id_base + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
-        auto ds = new vdb_dataset();
-        ds->device = current_device();
-        ds->d_rows = const_cast<void*>(d_rows);
-        ds->owned = false;
-        ds->n = ds->cap = n;
-        ds->dim = dim;
-        ds->pitch = pitch;
-        ds->dtype = dtype;
-        ds->metric = metric;
-        ds->id_base = id_base;
-        *out = ds;
+        *out = adopt_dataset_on(current_device(), d_rows, n, dim, pitch, dtype, metric, id_base);
     });
+}
+
+int vdb_dataset_create_sharded_dev(const void* const* d_rows, const uint64_t* counts, const int* devices, uint32_t nshards,
+                                   uint32_t dim, uint32_t pitch, int dtype, int metric, uint64_t id_base, vdb_dataset** out) {
+    return guarded([&] {
+        VDB_REQUIRE(out && d_rows && counts && devices && nshards > 0, "NULL argument");
+        VDB_REQUIRE(dim > 0 && pitch >= dim, "need 0 < dim <= pitch");
+        check_dtype_metric(dtype, metric);
+        VDB_REQUIRE(pitch % vdb::vec_elems(dtype) == 0, "row pitch must be a multiple of 16 bytes");
+        uint64_t n = 0;
+        std::vector<uint64_t> cnt(counts, counts + nshards);
+        for (uint64_t c : cnt) n += c;
+        VDB_REQUIRE(id_base + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
+        std::vector<int> devs(devices, devices + nshards);
+        vdb::init_devices(devices, nshards);   // peer access between the shards' devices
+        *out = vdb::sharded_create(devs, n, dim, dtype, metric, id_base, &cnt,
+                                   [&](uint32_t s, int device, uint64_t lo, uint64_t hi) {
+                                       VDB_REQUIRE(d_rows[s] || hi == lo, "d_rows[%u] is NULL", s);
+                                       return adopt_dataset_on(device, d_rows[s], hi - lo, dim, pitch, dtype, metric, id_base + lo);
+                                   });
+    });
+}
+
+int vdb_dataset_shards(const vdb_dataset* ds, uint32_t* n) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && n, "NULL argument");
+        *n = vdb::sharded_count(ds);
+    });
+}
+int vdb_dataset_shard(const vdb_dataset* ds, uint32_t s, vdb_dataset** shard, int* device, uint64_t* row_lo, uint64_t* row_hi) {
+    return guarded([&] {
+        VDB_REQUIRE(ds, "NULL dataset");
+        VDB_REQUIRE(ds->sharded, "not a row-sharded dataset");
+        vdb::sharded_info(ds, s, device, row_lo, row_hi, shard);
+    });
+}
+int vdb_dataset_set_flat_path(vdb_dataset* ds, int path) {
+    return guarded([&] {
+        VDB_REQUIRE(ds, "NULL dataset");
+        VDB_REQUIRE(path >= -1 && path <= 2, "path must be -1 (process default), 0 (auto), 1 (scan) or 2 (tensor)");
+        ds->flat_path = path;
+    });
+}
+int vdb_debug_force_redo(uint32_t every) {
+    vdb::g_debug_force_redo = every;
+    return VDB_OK;
 }
 
 int vdb_dataset_append(vdb_dataset* ds, const void* rows, uint64_t n) {
     return guarded([&] {
         VDB_REQUIRE(ds && (rows || n == 0), "NULL argument");
+        dev_of(ds);
         VDB_REQUIRE(ds->owned, "cannot append to an adopted device dataset");
         VDB_REQUIRE(ds->id_base + ds->n + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         drop_side_arrays(ds);
         CallStream cs;
         if (ds->n + n > ds->cap) {  // amortised growth, like Vec::push
@@ -250,10 +356,11 @@ int vdb_dataset_append(vdb_dataset* ds, const void* rows, uint64_t n) {
 int vdb_dataset_swap_remove(vdb_dataset* ds, uint64_t idx) {
     return guarded([&] {
         VDB_REQUIRE(ds, "NULL dataset");
+        dev_of(ds);
         VDB_REQUIRE(ds->owned, "cannot mutate an adopted device dataset");
         VDB_REQUIRE(idx < ds->n, "swap_remove index %llu out of range (len %llu)", (unsigned long long)idx,
                     (unsigned long long)ds->n);
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         drop_side_arrays(ds);
         if (idx != ds->n - 1) {
             uint8_t* base = (uint8_t*)ds->d_rows;
@@ -278,6 +385,10 @@ int vdb_dataset_dim(const vdb_dataset* ds, uint32_t* dim) {
 int vdb_dataset_destroy(vdb_dataset* ds) {
     return guarded([&] {
         if (!ds) return;
+        if (ds->sharded) {
+            vdb::sharded_destroy(ds);
+            return;
+        }
         DeviceGuard g(ds->device);
         drop_side_arrays(ds);
         if (ds->owned && ds->d_rows) cudaFree(ds->d_rows);
@@ -295,7 +406,7 @@ int vdb_flat_set_path(int path) {
 
 static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t nq, uint32_t k, uint64_t* d_keys,
                                cudaStream_t st) {
-    const int path = vdb::g_flat_path;
+    const int path = ds->flat_path >= 0 ? ds->flat_path : vdb::g_flat_path.load();
     bool tensor = false;
     if (path == 2) {
         VDB_REQUIRE(vdb::flat_gemm_supported(ds, nq, k),
@@ -314,7 +425,7 @@ int vdb_flat_knn_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_t
                           void* stream) {
     return guarded([&] {
         VDB_REQUIRE(ds && (d_queries || nq == 0) && (d_keys || nq * (uint64_t)k == 0), "NULL argument");
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         flat_keys_dispatch(ds, d_queries, nq, k, d_keys, (cudaStream_t)stream);
     });
 }
@@ -325,7 +436,7 @@ int vdb_flat_knn_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
         VDB_REQUIRE(ds && (d_queries || nq == 0), "NULL argument");
         VDB_REQUIRE(nq == 0 || d_counts, "d_counts is NULL");
         VDB_REQUIRE(nq * (uint64_t)k == 0 || (d_ids && d_dist), "NULL result arrays");
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         cudaStream_t st = (cudaStream_t)stream;
         vdb::DevBuf keys((size_t)nq * k * 8, st);
         flat_keys_dispatch(ds, d_queries, nq, k, keys.as<uint64_t>(), st);
@@ -339,12 +450,25 @@ int vdb_flat_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32
         VDB_REQUIRE(ds && (queries || nq == 0), "NULL argument");
         VDB_REQUIRE(nq == 0 || counts, "counts is NULL");
         VDB_REQUIRE(nq * (uint64_t)k == 0 || (ids && dist), "NULL result arrays");
-        host_search(ds->device, queries, nq, (size_t)ds->dim * ds->elem_size(), k, ids, dist, counts,
+        if (ds->sharded) {   // vdb_init with several devices: the same call, spread over the shards (multi.cu)
+            vdb::sharded_flat_knn(ds, queries, nq, k, ids, dist, counts);
+            return;
+        }
+        host_search(dev_of(ds), queries, nq, (size_t)ds->dim * ds->elem_size(), k, ids, dist, counts,
                     [&](void* dq, uint64_t* dids, float* dd, uint32_t* dc, cudaStream_t st) {
                         vdb::DevBuf keys((size_t)nq * k * 8, st);
                         flat_keys_dispatch(ds, dq, nq, k, keys.as<uint64_t>(), st);
                         vdb::decode_keys(keys.as<uint64_t>(), nq, k, dids, dd, dc, st);
                     });
+    });
+}
+
+int vdb_flat_knn_sharded_dev(const vdb_dataset* ds, const void* const* d_queries, uint32_t nq, uint32_t k,
+                             uint64_t* const* d_ids, float* const* d_dist, uint32_t* const* d_counts) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && ds->sharded, "not a row-sharded dataset");
+        VDB_REQUIRE(nq == 0 || (d_queries && d_ids && d_dist && d_counts), "NULL argument");
+        vdb::sharded_flat_knn_dev(ds, d_queries, nq, k, d_ids, d_dist, d_counts);
     });
 }
 
@@ -365,7 +489,7 @@ int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
 int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm) {
     return guarded([&] {
         VDB_REQUIRE(ds, "NULL dataset");
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         CallStream cs;
         vdb::tensor_info(ds, n, sample_n, mean_norm, cs.s);
         cs.sync();
@@ -378,7 +502,7 @@ uint32_t vdb_tq_j0(uint32_t k, uint64_t sample_total, uint64_t n_total) {
 int vdb_tq_begin_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, void* stream, vdb_tq** out) {
     return guarded([&] {
         VDB_REQUIRE(ds && d_queries && out && nq > 0, "NULL argument");
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         *out = vdb::tensor_begin(ds, d_queries, nq, (cudaStream_t)stream);
     });
 }
@@ -415,7 +539,7 @@ int vdb_flat_scan_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_
                            void* stream) {
     return guarded([&] {
         VDB_REQUIRE(ds && (d_queries || nq == 0) && (d_keys || nq * (uint64_t)k == 0), "NULL argument");
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         vdb::flat_scan_keys(ds, d_queries, nq, k, d_keys, (cudaStream_t)stream);
     });
 }
@@ -439,15 +563,15 @@ int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint
                               uint64_t* d_out_keys, void* stream) {
     return guarded([&] {
         VDB_REQUIRE(ds && d_queries && d_out_keys, "NULL argument");
-        DeviceGuard g(ds->device);
+        DeviceGuard g(dev_of(ds));
         vdb::flat_gemm_store(ds, d_queries, nq, row_stride, c, d_out_keys, (cudaStream_t)stream);
     });
 }
-uint64_t vdb_flat_gemm_fallbacks(void) { return vdb::g_gemm_redo; }
+uint64_t vdb_flat_gemm_fallbacks(void) { return vdb::g_gemm_redo.load(); }
 int vdb_flat_gemm_stats(uint64_t* queries, uint64_t* candidates, uint64_t* fallbacks) {
-    if (queries) *queries = vdb::g_gemm_queries;
-    if (candidates) *candidates = vdb::g_gemm_cands;
-    if (fallbacks) *fallbacks = vdb::g_gemm_redo;
+    if (queries) *queries = vdb::g_gemm_queries.load();
+    if (candidates) *candidates = vdb::g_gemm_cands.load();
+    if (fallbacks) *fallbacks = vdb::g_gemm_redo.load();
     return VDB_OK;
 }
 
@@ -463,7 +587,7 @@ int vdb_prof_reset(void) {
                 cudaEventDestroy(sp.first);
                 cudaEventDestroy(sp.second);
             }
-            if (kv.second.open) cudaEventDestroy(kv.second.open);
+            for (auto& o : kv.second.open) cudaEventDestroy(o.second);
         }
         vdb::g_prof.clear();
     });

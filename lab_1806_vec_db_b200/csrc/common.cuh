@@ -117,6 +117,21 @@ inline int sm_count() {
     return cached;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to ONE device: the largest size configured so far is
+// remembered per (kernel instantiation, device) - `state` is a function-local static array of the caller - so a
+// process that drives several GPUs (vdb_init) configures every kernel once on each of them.
+constexpr int VDB_MAX_DEVICES = 64;
+template <class K>
+inline void ensure_dyn_smem(K kern, size_t bytes, std::atomic<size_t> (&state)[VDB_MAX_DEVICES]) {
+    int dev = 0;
+    VDB_CUDA(cudaGetDevice(&dev));
+    std::atomic<size_t>& s = state[dev & (VDB_MAX_DEVICES - 1)];
+    if (bytes <= s.load(std::memory_order_acquire)) return;
+    VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    size_t cur = s.load();
+    while (cur < bytes && !s.compare_exchange_weak(cur, bytes)) {}
+}
+
 inline uint32_t next_pow2(uint32_t v) {
     uint32_t p = 1;
     while (p < v) p <<= 1;

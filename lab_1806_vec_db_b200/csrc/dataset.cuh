@@ -21,6 +21,10 @@ struct vdb_dataset {
     uint32_t sample_n = 0;
     uint64_t side_n = 0;      // number of rows the side arrays cover
     float mean_norm = 0.f;    // mean ||x|| over a row sample (threshold margin of the tensor path)
+    int flat_path = -1;       // vdb_dataset_set_flat_path: 0 auto, 1 scan, 2 tensor; -1 = the process default
+    // row-sharded parent (vdb_init with several devices; multi.cu): the rows live in the shards' own vdb_dataset
+    // handles, this handle only carries n / dim / dtype / metric and the worker pool
+    struct vdb_sharded_state* sharded = nullptr;
     uint32_t elem_size() const { return dtype == VDB_F32 ? 4u : 1u; }
     size_t pitch_bytes() const { return (size_t)pitch * elem_size(); }
 };
@@ -60,6 +64,6 @@ void pair_distances(const vdb_dataset* ds, const float* d_qtile, uint32_t qstrid
                     const float* d_rowcache, const uint32_t* d_qidx, const uint32_t* d_rid, uint64_t npairs,
                     int mode, float* d_out, cudaStream_t st);
 
-extern int g_flat_path;
+extern std::atomic<int> g_flat_path;   // process default of the Flat path selection (vdb_flat_set_path)
 
 }  // namespace vdb

@@ -513,11 +513,8 @@ template <int MODE, int CTAS, int METRIC>
 static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st) {
     using Cfg = GemmCfg<CTAS>;
     auto kern = flat_gemm_kernel<MODE, CTAS, METRIC>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        configured = true;
-    }
+    static std::atomic<size_t> configured[VDB_MAX_DEVICES];
+    ensure_dyn_smem(kern, Cfg::SMEM, configured);
     const uint32_t sms = (uint32_t)sm_count();
     const uint32_t units = std::min(sms / CTAS, p.items ? p.nitems : p.nqt * p.nslabs);
     cudaLaunchConfig_t cfg{};
@@ -728,16 +725,20 @@ __global__ void overflow_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, u
     if (q < nq) flag[q] = cnt[q] > cap ? 1u : 0u;
 }
 // completeness check; failing queries are appended to redo[]
-__global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, uint64_t n,
+// keys / overflow are indexed by the LOCAL query i of the checked range [q0, q0 + cnt) (a row-sharded search checks
+// only the slice of queries a GPU owns); tau / qsq by the batch index q0 + i, which is also what redo[] receives.
+__global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t q0, uint32_t cnt, uint32_t k, uint64_t n,
                              const uint32_t* __restrict__ overflow, const float* __restrict__ tau,
-                             const float* __restrict__ qsq, uint32_t* __restrict__ redo, uint32_t* __restrict__ nredo) {
+                             const float* __restrict__ qsq, uint32_t force_mod, uint32_t* __restrict__ redo,
+                             uint32_t* __restrict__ nredo) {
     // qsq == nullptr: cosine (scores bound the distance itself); else L2Sqr (scores bound d - ||q||^2)
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const uint32_t q = q0 + i;
     const uint32_t need = (uint32_t)((uint64_t)k < n ? (uint64_t)k : n);
-    bool ok = !(overflow && overflow[q]);
+    bool ok = !(overflow && overflow[i]);
     if (ok && need) {
-        const uint64_t kk = keys[(size_t)q * k + (need - 1)];
+        const uint64_t kk = keys[(size_t)i * k + (need - 1)];
         ok = kk != KEY_NONE;  // fewer than `need` candidates survived the filter
         if (ok) {
             const float dk = key_dist(kk);
@@ -746,6 +747,7 @@ __global__ void check_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uin
             ok = (dk - shift) < tau[q] - slack;
         }
     }
+    if (force_mod && q % force_mod == 0) ok = false;
     if (!ok) redo[atomicAdd(nredo, 1u)] = q;
 }
 __global__ void gather_rows_kernel(const uint8_t* __restrict__ src, uint32_t row_bytes, const uint32_t* __restrict__ idx,
@@ -769,9 +771,12 @@ bool flat_gemm_supported(const vdb_dataset* ds, uint32_t nq, uint32_t k) {
            nq >= 1 && ((uintptr_t)ds->d_rows & 15) == 0;
 }
 
-uint64_t g_gemm_redo = 0;  // queries that needed the exact fallback (instrumentation)
-uint64_t g_gemm_cands = 0; // candidates reranked (instrumentation)
-uint64_t g_gemm_queries = 0;
+std::atomic<uint64_t> g_gemm_redo{0};  // queries that needed the exact fallback (instrumentation)
+std::atomic<uint64_t> g_gemm_cands{0}; // candidates reranked (instrumentation)
+std::atomic<uint64_t> g_gemm_queries{0};
+// test hook (vdb_debug_force_redo): every query whose index is a multiple of m fails the completeness check, so
+// the exact re-scan of flagged queries (single-GPU and sharded) can be exercised on purpose; 0 = off
+std::atomic<uint32_t> g_debug_force_redo{0};
 
 // ---- phases (also exported one by one for the row-sharded search, sharded.py) -------------------------------
 // j0: smallest order statistic of an `ns`-row uniform sample whose rank among the `n` rows is >= k with high
@@ -1068,10 +1073,17 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
 // CHECK: the (merged) result of q is provably exact iff no shard overflowed and d_k - ||q||^2 < tau_q
 void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,
                   const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo) {
+    tensor_check_range(tq, 0, tq->nq, d_keys, k, n_total, d_tau, d_overflow, d_redo, d_nredo);
+}
+// the same for the queries [q0, q0 + cnt) of the batch: d_keys [cnt][k] and d_overflow [cnt] are local to the range,
+// d_tau is the whole batch's; d_redo receives batch indices
+void tensor_check_range(vdb_tq* tq, uint32_t q0, uint32_t cnt, const uint64_t* d_keys, uint32_t k, uint64_t n_total,
+                        const float* d_tau, const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo) {
     VDB_CUDA(cudaMemsetAsync(d_nredo, 0, 4, tq->st));
-    check_kernel<<<ceil_div(tq->nq, 256u), 256, 0, tq->st>>>(d_keys, tq->nq, k, n_total, d_overflow, d_tau,
-                                                             tq->ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(),
-                                                             d_redo, d_nredo);
+    if (cnt == 0) return;
+    check_kernel<<<ceil_div(cnt, 256u), 256, 0, tq->st>>>(d_keys, q0, cnt, k, n_total, d_overflow, d_tau,
+                                                          tq->ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(),
+                                                          g_debug_force_redo.load(), d_redo, d_nredo);
     VDB_LAUNCHED();
 }
 

@@ -19,7 +19,7 @@
 namespace vdb {
 
 std::atomic<uint64_t> g_launches{0};
-int g_flat_path = 0;
+std::atomic<int> g_flat_path{0};
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
@@ -541,11 +541,8 @@ QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t
 template <int NQ, int R, int METRIC, int PL>
 static void launch_scan(const ScanParams& p, uint32_t grid, size_t smem, cudaStream_t st) {
     auto kern = flat_scan_kernel<NQ, R, METRIC, PL>;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static std::atomic<size_t> configured[VDB_MAX_DEVICES];
+    if (smem > 48 * 1024) ensure_dyn_smem(kern, smem, configured);
     ProfScope prof("flat_scan", st);
     kern<<<grid, SCAN_THREADS, smem, st>>>(p);
     VDB_LAUNCHED();

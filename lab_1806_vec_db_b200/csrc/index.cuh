@@ -157,7 +157,8 @@ void pq_tensor_filter(const vdb_pq* pq, const DevBuf& lut16, const float* d_lut,
 // flat_gemm.cu
 void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
                      uint64_t* d_out_keys, cudaStream_t st);
-extern uint64_t g_gemm_redo, g_gemm_cands, g_gemm_queries;
+extern std::atomic<uint64_t> g_gemm_redo, g_gemm_cands, g_gemm_queries;
+extern std::atomic<uint32_t> g_debug_force_redo;
 uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps = 2e-3);
 vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st);
 void tensor_end(vdb_tq* tq);
@@ -167,6 +168,8 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
                         uint32_t* d_overflow, uint64_t* d_cand_total);
 void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,
                   const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo);
+void tensor_check_range(vdb_tq* tq, uint32_t q0, uint32_t cnt, const uint64_t* d_keys, uint32_t k, uint64_t n_total,
+                        const float* d_tau, const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo);
 void tensor_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, cudaStream_t st);
 
 }  // namespace vdb

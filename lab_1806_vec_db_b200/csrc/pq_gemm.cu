@@ -403,11 +403,8 @@ static void launch_pq_gemm_t(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq,
     p.tiles_per_item = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, row_tiles * p.nqt / ((uint64_t)units * 4)));
     p.nrow_items = (uint32_t)ceil_div<uint64_t>(row_tiles, p.tiles_per_item);
     auto kern = pq_gemm_kernel<MODE, CTAS, GG>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes(P_MAX_ENC)));
-        configured = true;
-    }
+    static std::atomic<size_t> configured[VDB_MAX_DEVICES];
+    ensure_dyn_smem(kern, Cfg::smem_bytes(P_MAX_ENC), configured);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(std::min<uint32_t>(units, p.nrow_items * p.nqt) * CTAS);
     cfg.blockDim = dim3(P_BASE_THREADS + 128 * GG);

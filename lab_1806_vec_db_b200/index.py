@@ -27,8 +27,17 @@ def _as_rows(a, dtype=None):
     return np.ascontiguousarray(a)
 
 
+def init_devices(devices):
+    """vdb_init: the CUDA devices of this process. With two or more, DeviceVecSet(rows) row-shards the set over them
+    and every FlatIndex.knn / knn_batch on it is ONE C call that runs on all of them (peer-memory merge). A device may
+    be listed several times (several shards on one GPU). [] returns to single-device mode."""
+    arr = (C.c_int * max(1, len(devices)))(*devices)
+    L.check(L.lib().vdb_init(arr, len(devices)))
+
+
 class DeviceVecSet:
-    """Device mirror of VecSet<T> (reference src/vec_set.rs:15-30) — one row shard in HBM."""
+    """Device mirror of VecSet<T> (reference src/vec_set.rs:15-30) — one row shard in HBM, or, after
+    init_devices([...]) with several devices, the whole set row-sharded over them."""
 
     def __init__(self, rows, dist="l2sqr", id_base=0):
         rows = np.ascontiguousarray(rows)
@@ -57,6 +66,41 @@ class DeviceVecSet:
                                                self.id_base, C.byref(self._h)))
         self._keepalive = keepalive
         return self
+
+    @classmethod
+    def from_device_shards(cls, d_ptrs, counts, devices, dim, pitch, dtype, dist="l2sqr", id_base=0, keepalive=None):
+        """Row-sharded set over rows already resident on the shards' devices (shard s: counts[s] rows at d_ptrs[s] on
+        devices[s]); enables peer access between the devices."""
+        self = cls.__new__(cls)
+        self.dtype = np.dtype(dtype)
+        self.dim = int(dim)
+        self.metric = L.metric_code(dist)
+        self.id_base = int(id_base)
+        self._h = C.c_void_p()
+        g = len(d_ptrs)
+        code = L.F32 if self.dtype == np.float32 else L.U8
+        L.check(L.lib().vdb_dataset_create_sharded_dev((C.c_void_p * g)(*[int(p) for p in d_ptrs]),
+                                                       (C.c_uint64 * g)(*[int(c) for c in counts]),
+                                                       (C.c_int * g)(*[int(d) for d in devices]), g, dim, pitch, code,
+                                                       self.metric, self.id_base, C.byref(self._h)))
+        self._keepalive = keepalive
+        return self
+
+    def shards(self):
+        """[(device, row_lo, row_hi)] of a row-sharded set, [] otherwise."""
+        n = C.c_uint32()
+        L.check(L.lib().vdb_dataset_shards(self._h, C.byref(n)))
+        out = []
+        for s in range(n.value):
+            dev, lo, hi = C.c_int(), C.c_uint64(), C.c_uint64()
+            L.check(L.lib().vdb_dataset_shard(self._h, s, None, C.byref(dev), C.byref(lo), C.byref(hi)))
+            out.append((dev.value, int(lo.value), int(hi.value)))
+        return out
+
+    def set_flat_path(self, path):
+        """Flat implementation for THIS handle: "auto", "scan" (K1), "tensor" (K2) or None (process default)."""
+        code = {None: -1, "auto": 0, "scan": 1, "tensor": 2}[path]
+        L.check(L.lib().vdb_dataset_set_flat_path(self._h, code))
 
     def __len__(self):
         n = C.c_uint64()
@@ -138,6 +182,15 @@ class FlatIndex:
         """IndexKNN::knn (flat_index.rs:48-57)."""
         ids, dist, counts = self.knn_batch(np.asarray(query).reshape(1, -1), k)
         return _pairs(ids, dist, counts)[0]
+
+    def knn_batch_sharded_dev(self, d_queries, nq, k, d_ids, d_dist, d_counts):
+        """Device-resident search on a row-sharded set (vdb_flat_knn_sharded_dev): d_queries[s] = pointer of the whole
+        batch on shard s's device; shard s receives the results of queries [s * per, (s + 1) * per), per = ceil(nq / G),
+        in d_ids[s] / d_dist[s] / d_counts[s]. Pointers are raw integers. Synchronous."""
+        g = len(d_queries)
+        arr = lambda ps: (C.c_void_p * g)(*[int(p) for p in ps])  # noqa: E731
+        L.check(L.lib().vdb_flat_knn_sharded_dev(self.vec_set._h, arr(d_queries), nq, k, arr(d_ids), arr(d_dist),
+                                                 arr(d_counts)))
 
 
 def calc_dist(a, b, dist="cosine"):
