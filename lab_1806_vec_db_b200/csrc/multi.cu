@@ -480,8 +480,17 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
 
     std::vector<std::function<void(uint32_t)>> ph;
     // P0: queries
+    // vdb_prof_*: shard 0's device time per phase (a phase's span includes its wait for the slowest peer)
+    struct PhaseProf {
+        ProfScope* p = nullptr;
+        PhaseProf(bool on, const char* name, cudaStream_t st) {
+            if (on && g_prof_on) p = new ProfScope(name, st);
+        }
+        ~PhaseProf() { delete p; }
+    };
     ph.push_back([&](uint32_t s) {
         Shard& sh = S->shards[s];
+        PhaseProf pp(s == 0, "mg_queries", sh.st);
         if (!host) {
             qptr[s] = a.d_queries[s];
             return;
@@ -508,6 +517,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
     // P1: sample (tensor) / nothing (scan)
     ph.push_back([&](uint32_t s) {
         Shard& sh = S->shards[s];
+        PhaseProf pp(s == 0, "mg_sample", sh.st);
         if (q_exchange) wait_peers(S, s, EV_Q);
         if (!tensor) return;
         tqs[s] = tensor_begin(sh.ds, qptr[s], nq, sh.st);
@@ -522,6 +532,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
     ph.push_back([&](uint32_t s) {
         Shard& sh = S->shards[s];
         Local& L = loc[s];
+        PhaseProf pp(s == 0, "mg_filter", sh.st);
         L.keys = DevBuf((size_t)nq * k * 8, sh.st);
         if (tensor) {
             wait_peers(S, s, EV_S);
@@ -553,6 +564,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
     ph.push_back([&](uint32_t s) {
         Shard& sh = S->shards[s];
         Local& L = loc[s];
+        PhaseProf* pp = new PhaseProf(s == 0, "mg_merge", sh.st);
         wait_peers(S, s, EV_F);
         uint32_t lo, hi;
         slice(s, &lo, &hi);
@@ -582,6 +594,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
         }
         L = Local();   // stream-ordered frees
         if (tqs[s]) tensor_end(tqs[s]), tqs[s] = nullptr;
+        delete pp;
         VDB_CUDA(cudaStreamSynchronize(sh.st));
     });
     try {
