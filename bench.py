@@ -175,12 +175,19 @@ def measure_tf32_peak(dev, seconds=1.5):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def tensor_stats(lib):
+def tensor_stats(lib, ds_handle=None):
     q, c, f = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
     lib.vdb_flat_gemm_stats(C.byref(q), C.byref(c), C.byref(f))
     if q.value == 0:
         return None
-    return {"queries": q.value, "candidates_per_query": c.value / q.value, "exact_fallback_queries": f.value}
+    out = {"queries": q.value, "candidates_per_query": c.value / q.value, "exact_fallback_queries": f.value}
+    if ds_handle is not None:
+        kind, scale, mn, me, sb = C.c_int(-1), C.c_float(0), C.c_float(0), C.c_float(0), C.c_uint64(0)
+        if lib.vdb_dataset_operand_info(ds_handle, C.byref(kind), C.byref(scale), C.byref(mn), C.byref(me), C.byref(sb)) == 0:
+            out["operand"] = {"kind": {0: "tf32 (fp32 rows in place, hardware truncation)", 1: "fp16 copy (power-of-two scaled)"}.get(kind.value, "not built"),
+                              "scale": scale.value, "mean_row_norm": mn.value, "mean_operand_error_norm": me.value,
+                              "side_array_bytes": sb.value}
+    return out
 
 
 def other_configs(V, L, lib, vs, base, q_dev, gt_ids, dev, n):
@@ -767,7 +774,7 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "kernel_ms": {k_: {"ms": v[0], "launches": v[1]} for k_, v in prof.items()},
-        "tensor_path": tensor_stats(lib),
+        "tensor_path": tensor_stats(lib, vs._h),
         "hbm_scan": hbm_scan,
         "other_configs": other,
     }

@@ -224,16 +224,18 @@ int vdb_ivf_knn_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_que
  * vdb_merge_keys_dev -> check -> (rare) exact re-scan of the flagged queries -> end.  All pointers are device
  * pointers; everything runs on the stream given to begin. */
 typedef struct vdb_tq vdb_tq;
-/* n, sample size and mean row norm of this shard (builds the side arrays on first use). */
-int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm);
+/* n, sample size, mean row norm and mean operand-error norm of this shard (builds the side arrays on first use). */
+int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, float* mean_ex);
 /* Smallest sample order statistic whose rank among n_total rows is >= k with probability > 1 - 2e-3. */
 uint32_t vdb_tq_j0(uint32_t k, uint64_t sample_total, uint64_t n_total);
 int vdb_tq_begin_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, void* stream, vdb_tq** out);
 /* this shard's j smallest sampled pruning scores per query: d_keys [nq, j] ascending */
 int vdb_tq_sample_dev(vdb_tq* tq, uint32_t j, uint64_t* d_keys);
-/* merges nlists shards' sample keys ([nlists, nq, j]) and writes tau[q] = score_(j0) + margin(mean_norm) */
+/* merges nlists shards' sample keys ([nlists, nq, j]) and writes tau[q] = score_(j0) + margin(mean_norm, mean_ex); the
+ * two means must be the same on every shard (e.g. the maximum over the shards) so that all shards filter against
+ * identical thresholds */
 int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0,
-                   float mean_norm, float* d_tau);
+                   float mean_norm, float mean_ex, float* d_tau);
 /* filter pass + exact rerank: this shard's k best keys per query ([nq, k], KEY_NONE padded) and per-query
  * overflow flags (candidate list overflowed: the result for that query is not provably complete) */
 int vdb_tq_filter_dev(vdb_tq* tq, uint32_t k, const float* d_tau, uint64_t* d_keys, uint32_t* d_overflow);
@@ -253,10 +255,20 @@ int vdb_decode_keys_dev(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_
 
 /* ---- tensor-core path internals (tests / tuning) ---------------------------------------------- */
 /* Pruning scores of the tensor-core Flat path: out_keys[q * ns + i] = key(S'(q, row i*row_stride), i) for the
- * ns = n / row_stride sampled rows, S' = ||x||^2 - 2 q.x - c ||q|| ||x|| evaluated with TF32 tensor cores.
- * d_queries: device [nq, dim] f32. */
+ * ns = n / row_stride strided rows. S' is the search's own lower bound of d(q, x) - ||q||^2 (L2Sqr) / of the cosine
+ * distance, from the tensor-core contraction of the operand kind `kind` (0 = TF32: the fp32 rows in place, truncated by
+ * the hardware; 1 = FP16 copy scaled by a power of two; < 0 = the dataset's own choice) minus the rigorous bound built
+ * from the measured per-row / per-query operand errors. d_queries: device [nq, dim] of the dataset dtype. Synchronous. */
 int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride,
-                              float c, uint64_t* d_out_keys, void* stream);
+                              int kind, uint64_t* d_out_keys, void* stream);
+/* Side arrays of the tensor-core path of an (unsharded) dataset, built lazily by the first batched search and dropped on
+ * mutation: operand kind (-1 = not built, 0 = TF32: the fp32 rows in place, 1 = FP16 copy), its power-of-two scale, the
+ * mean row norm / mean operand-error norm, and the HBM bytes they occupy (FP16 kind: 2 bytes per element + 12 bytes per
+ * row, i.e. +50 % of an f32 set, +200 % of a u8 set; TF32 kind: 12 bytes per row). Outputs may be NULL. */
+int vdb_dataset_operand_info(const vdb_dataset* ds, int* kind, float* scale, float* mean_norm, float* mean_ex,
+                             uint64_t* side_bytes);
+/* Frees them (they are rebuilt by the next batched search). Not re-entrant with searches on the handle. */
+int vdb_dataset_drop_side_arrays(vdb_dataset* ds);
 /* Queries that failed the tensor path's completeness check and were re-run through the exact scan. */
 uint64_t vdb_flat_gemm_fallbacks(void);
 /* Cumulative counters of the tensor path: queries served, candidates reranked, queries re-run exactly. */

@@ -87,18 +87,20 @@ SIGNATURES = {
     "vdb_ivf_lists": (i32, [vp, vp, vp]),
     "vdb_ivf_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
     "vdb_ivf_knn_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
-    "vdb_tq_info": (i32, [vp, vp, vp, vp]),
+    "vdb_tq_info": (i32, [vp, vp, vp, vp, vp]),
     "vdb_tq_j0": (u32, [u32, u64, u64]),
     "vdb_tq_begin_dev": (i32, [vp, vp, u32, vp, vp]),
     "vdb_tq_sample_dev": (i32, [vp, u32, vp]),
-    "vdb_tq_tau_dev": (i32, [vp, vp, u32, u32, u32, f32, vp]),
+    "vdb_tq_tau_dev": (i32, [vp, vp, u32, u32, u32, f32, f32, vp]),
     "vdb_tq_filter_dev": (i32, [vp, u32, vp, vp, vp]),
     "vdb_tq_check_dev": (i32, [vp, vp, u32, u64, vp, vp, vp, vp]),
     "vdb_tq_end": (i32, [vp]),
     "vdb_flat_scan_keys_dev": (i32, [vp, vp, u32, u32, vp, vp]),
     "vdb_merge_keys_to_keys_dev": (i32, [vp, u32, u32, u32, vp, vp]),
     "vdb_decode_keys_dev": (i32, [vp, u32, u32, vp, vp, vp, vp]),
-    "vdb_debug_gemm_scores_dev": (i32, [vp, vp, u32, u32, f32, vp, vp]),
+    "vdb_debug_gemm_scores_dev": (i32, [vp, vp, u32, u32, i32, vp, vp]),
+    "vdb_dataset_operand_info": (i32, [vp, vp, vp, vp, vp, vp]),
+    "vdb_dataset_drop_side_arrays": (i32, [vp]),
     "vdb_flat_gemm_fallbacks": (u64, []),
     "vdb_flat_gemm_stats": (i32, [vp, vp, vp]),
     "vdb_launch_count": (u64, []),

@@ -132,20 +132,7 @@ void upload_rows(vdb_dataset* ds, uint64_t at, const void* rows, uint64_t n, cud
     }
 }
 
-void drop_side_arrays(vdb_dataset* ds) {
-    if (ds->d_lo) cudaFree(ds->d_lo);
-    if (ds->d_sqnorm) cudaFree(ds->d_sqnorm);
-    if (ds->d_tf32) cudaFree(ds->d_tf32);
-    if (ds->d_sample) cudaFree(ds->d_sample);
-    if (ds->d_sample_sq) cudaFree(ds->d_sample_sq);
-    if (ds->d_sample_rn) cudaFree(ds->d_sample_rn);
-    ds->d_sample = ds->d_sample_sq = ds->d_sample_rn = nullptr;
-    ds->sample_n = 0;
-    ds->d_tf32 = nullptr;
-    ds->d_lo = nullptr;
-    ds->d_sqnorm = nullptr;
-    ds->side_n = 0;
-}
+using vdb::drop_side_arrays;
 
 // copies nq query rows to the device, runs `body(d_queries, d_ids, d_dist, d_counts, stream)`, copies back
 template <class Body>
@@ -486,12 +473,12 @@ int vdb_merge_keys_dev(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     });
 }
 
-int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm) {
+int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, float* mean_ex) {
     return guarded([&] {
         VDB_REQUIRE(ds, "NULL dataset");
         DeviceGuard g(dev_of(ds));
         CallStream cs;
-        vdb::tensor_info(ds, n, sample_n, mean_norm, cs.s);
+        vdb::tensor_info(ds, n, sample_n, mean_norm, mean_ex, cs.s);
         cs.sync();
     });
 }
@@ -513,10 +500,10 @@ int vdb_tq_sample_dev(vdb_tq* tq, uint32_t j, uint64_t* d_keys) {
     });
 }
 int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm,
-                   float* d_tau) {
+                   float mean_ex, float* d_tau) {
     return guarded([&] {
         VDB_REQUIRE(tq && d_keys_lists && d_tau && nlists > 0, "NULL argument");
-        vdb::tensor_tau(tq, d_keys_lists, nlists, j, j0, mean_norm, d_tau);
+        vdb::tensor_tau(tq, d_keys_lists, nlists, j, j0, mean_norm, mean_ex, d_tau);
     });
 }
 int vdb_tq_filter_dev(vdb_tq* tq, uint32_t k, const float* d_tau, uint64_t* d_keys, uint32_t* d_overflow) {
@@ -559,12 +546,28 @@ int vdb_decode_keys_dev(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_
     });
 }
 
-int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
+int vdb_debug_gemm_scores_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, int kind,
                               uint64_t* d_out_keys, void* stream) {
     return guarded([&] {
         VDB_REQUIRE(ds && d_queries && d_out_keys, "NULL argument");
         DeviceGuard g(dev_of(ds));
-        vdb::flat_gemm_store(ds, d_queries, nq, row_stride, c, d_out_keys, (cudaStream_t)stream);
+        vdb::flat_gemm_store(ds, d_queries, nq, row_stride, kind, d_out_keys, (cudaStream_t)stream);
+    });
+}
+int vdb_dataset_operand_info(const vdb_dataset* ds, int* kind, float* scale, float* mean_norm, float* mean_ex,
+                             uint64_t* side_bytes) {
+    return guarded([&] {
+        VDB_REQUIRE(ds, "NULL dataset");
+        dev_of(ds);
+        vdb::operand_info(ds, kind, scale, mean_norm, mean_ex, side_bytes);
+    });
+}
+int vdb_dataset_drop_side_arrays(vdb_dataset* ds) {
+    return guarded([&] {
+        VDB_REQUIRE(ds, "NULL dataset");
+        DeviceGuard g(dev_of(ds));
+        VDB_CUDA(cudaDeviceSynchronize());
+        drop_side_arrays(ds);
     });
 }
 uint64_t vdb_flat_gemm_fallbacks(void) { return vdb::g_gemm_redo.load(); }

@@ -14,13 +14,21 @@ struct vdb_dataset {
     uint64_t id_base = 0;
     // lazily built side arrays for the tensor-core path (K2); invalidated on mutation
     float* d_lo = nullptr;    // ||x|| (fp32), [n]
-    float* d_tf32 = nullptr;  // rows rounded to TF32 (round-to-nearest), [n][pitch]: the tensor-core operand
-    float* d_sqnorm = nullptr;  // ||x||^2 (fp32), [n]
-    float* d_sample = nullptr;  // stratified random row sample (TF32-rounded), [sample_n][pitch]
-    float* d_sample_sq = nullptr, *d_sample_rn = nullptr;  // its ||x||^2 and ||x||
+    float* d_sqnorm = nullptr;  // L2Sqr: ||x||^2; cosine: 1 / ||x||  (fp32), [n]
+    float* d_ex = nullptr;    // operand error norm: L2Sqr ||x - x~||, cosine ||x - x~|| / ||x||  (x~ = what the MMA consumes), [n]
+    // the tensor-core operand: kind 1 = an FP16 copy [n][op_pitch] of the rows scaled by the power of two op_scale
+    // (d_op); kind 0 = the fp32 rows themselves, truncated to TF32 by the hardware (d_op == nullptr, nothing is copied)
+    void* d_op = nullptr;
+    int op_kind = 0;
+    bool op_owned = false;
+    uint32_t op_pitch = 0;    // elements per operand row
+    float op_scale = 1.0f;
+    void* d_sample = nullptr;  // stratified random sample of the operand rows, [sample_n][op row bytes]
+    float* d_sample_sq = nullptr, *d_sample_rn = nullptr, *d_sample_ex = nullptr;  // the sampled rows' scalars
     uint32_t sample_n = 0;
     uint64_t side_n = 0;      // number of rows the side arrays cover
     float mean_norm = 0.f;    // mean ||x|| over a row sample (threshold margin of the tensor path)
+    float mean_ex = 0.f;      // mean of d_ex over the same rows
     int flat_path = -1;       // vdb_dataset_set_flat_path: 0 auto, 1 scan, 2 tensor; -1 = the process default
     // row-sharded parent (vdb_init with several devices; multi.cu): the rows live in the shards' own vdb_dataset
     // handles, this handle only carries n / dim / dtype / metric and the worker pool
@@ -64,6 +72,7 @@ void pair_distances(const vdb_dataset* ds, const float* d_qtile, uint32_t qstrid
                     const float* d_rowcache, const uint32_t* d_qidx, const uint32_t* d_rid, uint64_t npairs,
                     int mode, float* d_out, cudaStream_t st);
 
+void drop_side_arrays(vdb_dataset* ds);   // flat_gemm.cu: frees the lazily built side arrays (called on mutation)
 extern std::atomic<int> g_flat_path;   // process default of the Flat path selection (vdb_flat_set_path)
 
 }  // namespace vdb

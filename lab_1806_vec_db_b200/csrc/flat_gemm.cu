@@ -6,8 +6,11 @@
 // Pipeline (all on the caller's stream):
 //   1. side arrays per dataset: ||x||^2 and ||x|| (fp32), built once and cached on the handle
 //   2. SAMPLE pass  : S' over a strided row sample, per query the j-th smallest S' becomes tau_q
-//   3. FILTER pass  : for every (query, row): S' = ||x||^2 - 2 q.x - c ||q|| ||x||  (a LOWER bound of
-//                     d(q,x) - ||q||^2: c bounds the TF32 rounding of the contraction);
+//   3. FILTER pass  : for every (query, row): S' = ||x||^2 - 2 q~.x~ - b(q, x)  (a LOWER bound of d(q,x) - ||q||^2:
+//                     q~, x~ are the operands the tensor core consumes - FP16 copies scaled by exact powers of two,
+//                     or the fp32 values truncated to TF32 by the hardware - and
+//                     b = 2 (||q~|| ||x - x~|| + ||q - q~|| ||x~|| + dim 2^-23 ||q~|| ||x~||) uses the EXACT per-row /
+//                     per-query operand errors ||x - x~||, ||q - q~|| (Cauchy-Schwarz), not a worst-case constant);
 //                     rows with S' < tau_q are appended to the query's candidate list
 //   4. RERANK       : exact difference-form distances of the candidates (pairs.cu), top-k by (d, id)
 //   5. CHECK        : the candidate set is provably complete iff  d_k - ||q||^2 < tau_q  (every excluded
@@ -20,6 +23,7 @@
 // K=8 per instruction) into double-buffered TMEM accumulators, four epilogue warps read them back with
 // tcgen05.ld (thread = query, registers = rows) and apply the per-query threshold in registers.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cmath>
 #include <cstdlib>
@@ -36,22 +40,31 @@ namespace vdb {
 // ---- tile configuration ---------------------------------------------------------------------------------
 constexpr int GM = 128;              // queries per tile (TMEM lanes)
 constexpr int GN = 256;              // database rows per tile (TMEM columns per accumulator)
-constexpr int GK = 32;               // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int G_A_BYTES = GM * GK * 4;   // 16 KB: 128 queries x 128 B
+constexpr int GKB = 128;             // bytes of one operand row per k-block = one 128-byte swizzle row
+constexpr int G_A_BYTES = GM * GKB;  // 16 KB: 128 queries x 128 B
+// operand kinds of the contraction. FP16 has TF32's 10 mantissa bits at twice the tensor rate and half the operand
+// bytes; its 5-bit exponent is handled by exact power-of-two scales per dataset / per query, and whatever the
+// conversion loses (underflow included) is measured per row and folded into the pruning bound.
+enum { KIND_TF32 = 0, KIND_F16 = 1 };
+template <int KIND> struct KindCfg {
+    static constexpr int ELEM = KIND == KIND_F16 ? 2 : 4;       // bytes per operand element
+    static constexpr int GKE = GKB / ELEM;                      // elements per k-block: 32 (tf32) / 64 (f16)
+    static constexpr uint32_t FMT = KIND == KIND_F16 ? 0u : 2u;  // UMMA a/b format: F16 = 0, TF32 = 2
+};
 constexpr int G_THREADS = 192;       // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
 constexpr int G_TMEM_COLS = 512;     // 2 accumulators x 256 columns
 constexpr int G_MAX_STAGES = 6;
 // CTAS = 1: one CTA computes a 128 x 256 tile. CTAS = 2: a CTA pair (cta_group::2) computes 256 x 256, each CTA
 // loads its own 128 queries and HALF of the 256 database rows, so the shared-memory fill per MMA cycle drops 1.5x.
-template <int CTAS> struct GemmCfg {
+template <int CTAS, int KIND = KIND_TF32> struct GemmCfg {
     static constexpr int B_ROWS = GN / CTAS;                    // database rows loaded per CTA and k-block
-    static constexpr int B_BYTES = B_ROWS * GK * 4;
+    static constexpr int B_BYTES = B_ROWS * GKB;
     static constexpr int STAGE_BYTES = G_A_BYTES + B_BYTES;     // 48 KB / 32 KB
     static constexpr int STAGES = CTAS == 1 ? 4 : 6;            // 192 KB either way
-    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 2 * GN * 4 /*norm tiles*/ + 512 /*barriers*/;
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) |
-                                      ((uint32_t)((GM * CTAS) >> 4) << 24);
+    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 3 * GN * 4 /*row-scalar tiles*/ + 512 /*barriers*/;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32 or F16, both K-major, N>>3, M>>4
+    static constexpr uint32_t IDESC = (1u << 4) | (KindCfg<KIND>::FMT << 7) | (KindCfg<KIND>::FMT << 10) |
+                                      ((uint32_t)(GN >> 3) << 17) | ((uint32_t)((GM * CTAS) >> 4) << 24);
 };
 constexpr uint32_t G_SAMPLE = 32768;  // sampled rows for the thresholds
 constexpr int G_TOPJ = 16;             // order statistics kept in registers by the sample pass (mode 2)
@@ -74,17 +87,21 @@ struct GemmParams {
     uint32_t nq;            // queries
     uint64_t nrows;         // rows addressed by the B tensor map (sample rows or all rows)
     uint32_t row_stride;    // database row of B row i is i * row_stride
-    uint32_t kblocks;       // ceil(dim / 32)
+    uint32_t kblocks;       // ceil(dim / elements per k-block)
     uint32_t ntiles;        // ceil(nrows / GN)
     uint32_t nqt;           // query-tile UNITS: ceil(nq / (GM * CTAS))
     uint32_t tiles_per_slab;
     uint32_t nslabs;        // slabs covered by this launch
     uint32_t slab0;         // first slab of this launch (the filter pass may be cut into row parts)
-    const float* sqnorm;    // [n] ||x||^2
+    // S' = sqnorm[x] + qd[q] * acc - qab[q] * ex[x] - qb[q] * rnorm[x]                       (L2Sqr)
+    // S' = qb[q] - (qd[q] * sqnorm[x]) * acc - qab[q] * ex[x]                                (cosine)
+    const float* sqnorm;    // [n] L2Sqr: ||x||^2;  cosine: 1 / ||x|| (0 for zero rows)
     const float* rnorm;     // [n] ||x||
-    const float* qcm;       // [nq] L2Sqr: c * ||q|| (pruning-bound coefficient times the query norm); cosine: 1/||q||
+    const float* ex;        // [n] L2Sqr: ||x - x~||;  cosine: ||x - x~|| / ||x||   (x~ = the operand the MMA consumes)
+    const float* qd;        // [nq] L2Sqr: -2 / (s_q s_x);  cosine: 1 / (s_q s_x ||q||)   (s = power-of-two operand scales)
+    const float* qab;       // [nq] coefficient of ex
+    const float* qb;        // [nq] L2Sqr: coefficient of ||x||;  cosine: 1 - (query-side share of the error bound)
     const float* qnorm;     // [nq] cosine: ||q||
-    float kc;               // cosine: 1 - (bound on the cosine-distance error)
     // mode 0: store keys (S', sample index) to out_keys[nq][nrows]
     // mode 2: per (query, slab) the G_TOPJ smallest S' as keys to out_keys[nq][nslabs][G_TOPJ]
     uint64_t* out_keys;
@@ -122,16 +139,17 @@ __device__ __forceinline__ ItemView decode_item(const GemmParams& p, uint32_t it
     return v;
 }
 
-template <int MODE, int CTAS, int METRIC>
+template <int MODE, int CTAS, int METRIC, int KIND>
 __global__ void __launch_bounds__(G_THREADS, 1)
 flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
-    using Cfg = GemmCfg<CTAS>;
+    using Cfg = GemmCfg<CTAS, KIND>;
+    constexpr int GKE = KindCfg<KIND>::GKE;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* stage_base = smem;
-    float* norm_tiles = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2 acc][2 arrays][GN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(norm_tiles + 2 * 2 * GN);
+    float* norm_tiles = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2 acc][3 arrays][GN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(norm_tiles + 2 * 3 * GN);
     uint64_t* full_bar = bars;                       // [STAGES]  (pair mode: the leader's copy is the live one)
     uint64_t* empty_bar = bars + G_MAX_STAGES;       // [STAGES]  per CTA
     uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES;   // [2]       per CTA
@@ -216,14 +234,14 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
                         if (CTAS == 1) {
                             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                            tma_load_2d(sa, &map_q, (int)(kb * GK), qrow, &full_bar[stage]);
-                            tma_load_2d(sa + G_A_BYTES, &map_x, (int)(kb * GK), brow, &full_bar[stage]);
+                            tma_load_2d(sa, &map_q, (int)(kb * GKE), qrow, &full_bar[stage]);
+                            tma_load_2d(sa + G_A_BYTES, &map_x, (int)(kb * GKE), brow, &full_bar[stage]);
                         } else {
                             // both CTAs' bytes are accounted on the LEADER's barrier
                             if (leader) mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * CTAS);
                             const uint32_t lbar = smem_u32(&full_bar[stage]) & PEER_MASK;
-                            tma_load_2d_2sm(sa, &map_q, (int)(kb * GK), qrow, lbar);
-                            tma_load_2d_2sm(sa + G_A_BYTES, &map_x, (int)(kb * GK), brow, lbar);
+                            tma_load_2d_2sm(sa, &map_q, (int)(kb * GKE), qrow, lbar);
+                            tma_load_2d_2sm(sa + G_A_BYTES, &map_x, (int)(kb * GKE), brow, lbar);
                         }
                         if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
@@ -248,9 +266,14 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
                         const uint64_t da = umma_desc(sa), db = umma_desc(sa + G_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < GK / 8; ++k) {  // advance 32 bytes (2 x 16B units) per K=8 step
-                            if (CTAS == 1) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
-                            else umma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                        for (int k = 0; k < GKB / 32; ++k) {  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16): 2 x 16B units
+                            if (KIND == KIND_F16) {
+                                if (CTAS == 1) umma_f16(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                                else umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                            } else {
+                                if (CTAS == 1) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                                else umma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) != 0);
+                            }
                         }
                         // frees the smem stage (in both CTAs) when these MMAs retire
                         if (CTAS == 1) umma_commit(&empty_bar[stage]);
@@ -278,7 +301,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint32_t q = iv.q0 + cta_rank * GM + threadIdx.x;   // row of the (gathered) query matrix
             const bool qok = q < iv.q_end;
             const uint32_t oq = (qok && p.qmap) ? p.qmap[q] : q;        // query that owns the candidate list
-            const float cq = qok ? p.qcm[q] : 0.f;
+            const float qd = qok ? p.qd[q] : 0.f, qab = qok ? p.qab[q] : 0.f, qb = qok ? p.qb[q] : 0.f;
             const float qn = (METRIC == VDB_COSINE && qok) ? p.qnorm[q] : 0.f;
             float tau = 0.f;
             if (MODE == 1) tau = qok ? p.tau[q] : __uint_as_float(0xff800000u);  // -inf: nothing passes
@@ -288,58 +311,95 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) best[i] = __uint_as_float(0x7f800000u);
             }
             for (uint32_t t = 0; t < iv.ntile; ++t) {
-                // stage the row-norm tiles of this N-tile (2 x GN floats) while the MMAs run
-                float* sq = norm_tiles + acc * 2 * GN;
+                // stage the row-scalar tiles of this N-tile (3 x GN floats) while the MMAs run
+                float* sq = norm_tiles + acc * 3 * GN;
                 float* rn = sq + GN;
+                float* ex = rn + GN;
                 const uint64_t tile_row0 = iv.r0 + (uint64_t)t * GN;
                 for (uint32_t c = threadIdx.x; c < GN; c += 128) {
                     const uint64_t brow = tile_row0 + c;
                     const bool ok = brow < iv.r_end;
                     const uint64_t row = brow * p.row_stride;
-                    sq[c] = ok ? p.sqnorm[row] : __uint_as_float(0x7f800000u);  // +inf: never a candidate
-                    rn[c] = ok ? p.rnorm[row] : 0.f;
+                    if (METRIC == VDB_L2SQR) {
+                        sq[c] = ok ? p.sqnorm[row] : __uint_as_float(0x7f800000u);  // +inf: never a candidate
+                        rn[c] = ok ? p.rnorm[row] : 0.f;
+                        ex[c] = ok ? p.ex[row] : 0.f;
+                    } else {   // padding: S' = qb - 0 * acc - qab * (-inf) = +inf, and never under the norm clamp
+                        sq[c] = ok ? p.sqnorm[row] : 0.f;
+                        rn[c] = ok ? p.rnorm[row] : __uint_as_float(0x7f800000u);
+                        ex[c] = ok ? p.ex[row] : __uint_as_float(0xff800000u);
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (lane_base << 16) + acc * GN;
+                // the row scalars are read with 128-bit SHARED loads (every lane reads the same address: one broadcast
+                // wavefront per 4 rows and array). Reading them through the generic pointers costs a generic-space LD per
+                // row and array, which made this loop - not the MMAs - the bound of the whole kernel.
+                const uint32_t sq_s = smem_u32(sq), rn_s = smem_u32(rn), ex_s = smem_u32(ex);
+                // cosine: a row is under the reference's 1e-10 norm-product clamp iff ||x|| < 2e-10 / ||q|| (always kept)
+                const float rthr = METRIC == VDB_COSINE ? (qn > 0.f ? 2e-10f / qn : __uint_as_float(0x7f800000u)) : 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < GN; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     if (qok) {
+                        // Hot path: 3 FMAs + 1 predicate-chained compare per score, ONE branch per 32 scores. The scores
+                        // replace the accumulator values in v[]; only a thread that saw a passing (or NaN) score walks
+                        // its 32 values again in the rare path below.
+                        const float thr = MODE == 1 ? tau : (MODE == 2 ? best[MODE == 2 ? G_TOPJ - 1 : 0] : 0.f);
+                        bool none = true;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float dot = __uint_as_float(v[j]);
-                            float s;
-                            if (METRIC == VDB_L2SQR) {
-                                // S' = ||x||^2 - c||q|| ||x|| - 2 q.x   (lower bound of d - ||q||^2)
-                                s = fmaf(-2.0f, dot, fmaf(-cq, rn[c0 + j], sq[c0 + j]));
-                            } else {
-                                // S' = (1 - bound) - q.x / (||q|| ||x||)  (lower bound of the cosine distance); rows whose
-                                // norm product falls under the reference's 1e-10 clamp are always kept (sq = 1/||x||)
-                                s = fmaf(-(cq * sq[c0 + j]), dot, p.kc);
-                                if (qn * rn[c0 + j] < 2e-10f) s = __uint_as_float(0xff800000u);
-                                if (tile_row0 + c0 + j >= iv.r_end) s = __uint_as_float(0x7f800000u);  // padding row
-                            }
-                            if (MODE == 0) {
-                                const uint64_t brow = tile_row0 + c0 + j;
-                                if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(s, (uint32_t)brow);
-                            } else if (MODE == 2) {
-                                if (s < best[G_TOPJ - 1]) {  // rare after the first few hundred rows: bubble s into place
-                                    float v = s;
+                        for (int j4 = 0; j4 < 32; j4 += 4) {
+                            const float4 sq4 = lds_f4(sq_s + (c0 + j4) * 4), rn4 = lds_f4(rn_s + (c0 + j4) * 4),
+                                         ex4 = lds_f4(ex_s + (c0 + j4) * 4);
+                            const float sqv[4] = {sq4.x, sq4.y, sq4.z, sq4.w}, rnv[4] = {rn4.x, rn4.y, rn4.z, rn4.w},
+                                        exv[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
 #pragma unroll
-                                    for (int i = 0; i < G_TOPJ; ++i) {
-                                        const float lo = fminf(best[i], v);
-                                        v = fmaxf(best[i], v);
-                                        best[i] = lo;
-                                    }
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = j4 + jj;
+                                const float dot = __uint_as_float(v[j]);
+                                float sc;
+                                if (METRIC == VDB_L2SQR) {
+                                    // S' = ||x||^2 - 2 q~.x~ / (s_q s_x) - b(q, x)   (lower bound of d - ||q||^2)
+                                    sc = fmaf(qd, dot, fmaf(-qab, exv[jj], fmaf(-qb, rnv[jj], sqv[jj])));
+                                } else {
+                                    // S' = (1 - bound) - q~.x~ / (s_q s_x ||q|| ||x||)  (lower bound of the cosine distance;
+                                    // sq = 1/||x||). Padding rows are staged with ex = -inf: S' = +inf.
+                                    sc = fmaf(-(qd * sqv[jj]), dot, fmaf(-qab, exv[jj], qb));
+                                    if (rnv[jj] < rthr) sc = __uint_as_float(0xff800000u);
                                 }
-                            } else if (s < tau) {
-                                const uint32_t pos = atomicAdd(&p.cand_cnt[oq], 1u);
-                                if (pos < p.cap)
-                                    p.cand[(uint64_t)oq * p.cap + pos] =
-                                        ((uint64_t)__float_as_uint(s) << 32) | (uint32_t)(tile_row0 + c0 + j);
+                                v[j] = __float_as_uint(sc);
+                                if (MODE != 0) none = none && (sc >= thr);   // a NaN score fails the test: rare path
+                            }
+                        }
+                        if (MODE == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const uint64_t brow = tile_row0 + c0 + j;
+                                if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(__uint_as_float(v[j]), (uint32_t)brow);
+                            }
+                        } else if (!none) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float sc = __uint_as_float(v[j]);
+                                if (MODE == 2) {
+                                    if (sc < best[MODE == 2 ? G_TOPJ - 1 : 0]) {  // bubble sc into place
+                                        float w = sc;
+#pragma unroll
+                                        for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) {
+                                            const float lo = fminf(best[i], w);
+                                            w = fmaxf(best[i], w);
+                                            best[i] = lo;
+                                        }
+                                    }
+                                } else if (!(sc >= tau)) {   // NaN scores (non-finite rows / queries) are kept: the exact rerank decides
+                                    const uint32_t pos = atomicAdd(&p.cand_cnt[oq], 1u);
+                                    if (pos < p.cap)
+                                        p.cand[(uint64_t)oq * p.cap + pos] =
+                                            ((uint64_t)__float_as_uint(sc) << 32) | (uint32_t)(tile_row0 + c0 + j);
+                                }
                             }
                         }
                     }
@@ -390,40 +450,95 @@ __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v,
     }
 }
 
-// round-to-nearest TF32 copy: the tensor core then consumes exactly representable operands, so the only operand
-// error is this rounding (2^-11 relative) instead of the hardware's truncation (2^-10)
-__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, uint64_t count) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
-        dst[i] = __uint_as_float(r);
+// ---- operand copies and per-row error norms ---------------------------------------------------------------------------
+// One warp per row. FP16 kind: writes x~ = fp16(x * s_x) (s_x an exact power of two) and ||x - x~ / s_x||; TF32 kind: the
+// hardware truncates the fp32 bits to TF32 itself (no copy), the error of THAT truncation is what is measured (a
+// round-to-nearest unit would err less than truncation on every element, so the norm bounds it too). u8 rows are exact
+// in FP16. Non-finite rows get sqnorm = -inf ("always a candidate": the exact rerank decides) and error 0.
+// Norm sums follow row_cache's arithmetic (lane-strided fma chain + xor butterfly).
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) row_side_kernel(const T* __restrict__ rows, uint64_t n, uint32_t dim, uint32_t pitch,
+                                                       float scale, uint32_t op_pitch, __half* __restrict__ op,
+                                                       int cosine, float* __restrict__ colA, float* __restrict__ rn,
+                                                       float* __restrict__ ex) {
+    const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const T* src = rows + row * pitch;
+    const float inv_scale = 1.0f / scale;
+    float ss = 0.f, ee = 0.f;
+    bool finite = true;
+    const uint32_t span = KIND == KIND_F16 ? op_pitch : dim;
+    for (uint32_t e = lane; e < span; e += 32) {
+        const float v = e < dim ? (float)src[e] : 0.f;
+        float back;
+        if (KIND == KIND_F16) {
+            const __half h = __float2half_rn(v * scale);
+            op[row * op_pitch + e] = h;
+            back = __half2float(h) * inv_scale;
+        } else {
+            back = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        }
+        finite = finite && (fabsf(v) <= 3.0e38f) && (fabsf(back) <= 3.0e38f);
+        const float d = v - back;
+        ss = fmaf(v, v, ss);
+        ee = fmaf(d, d, ee);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        ee += __shfl_xor_sync(0xffffffffu, ee, o);
+    }
+    finite = __all_sync(0xffffffffu, finite);
+    if (lane == 0) {
+        const float norm = sqrtf(ss);
+        float err = sqrtf(ee) * 1.0001f;
+        if (!finite) {
+            colA[row] = cosine ? 0.f : __uint_as_float(0xff800000u);
+            rn[row] = 0.f;     // cosine: a zero norm product puts the row under the reference's clamp -> always kept
+            ex[row] = 0.f;
+            return;
+        }
+        rn[row] = norm;
+        if (cosine) {
+            colA[row] = norm > 0.f ? 1.0f / norm : 0.f;
+            ex[row] = norm > 0.f ? err / norm * 1.0001f : 0.f;
+        } else {
+            colA[row] = ss;
+            ex[row] = err;
+        }
     }
 }
-__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, uint64_t count) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
-        dst[i] = (float)src[i];
+
+// max |x| over the set (non-finite values ignored), as raw float bits (non-negative floats order like integers)
+template <typename T>
+__global__ void __launch_bounds__(256) absmax_kernel(const T* __restrict__ rows, uint64_t n, uint32_t dim, uint32_t pitch,
+                                                     uint32_t* __restrict__ out) {
+    float m = 0.f;
+    const uint64_t total = n * pitch;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float v = fabsf((float)rows[i]);
+        if (v <= 3.0e38f) m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
-static void u8_to_f32(const uint8_t* src, float* dst, uint64_t count, cudaStream_t st) {
-    if (count == 0) return;
-    u8_to_f32_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), (uint64_t)sm_count() * 32), 256, 0, st>>>(src, dst, count);
-    VDB_LAUNCHED();
-}
-// [nq][dim] u8 -> [nq][qpitch] f32 (zero padded)
-__global__ void u8_rows_to_f32_kernel(const uint8_t* __restrict__ src, uint32_t dim, uint32_t qpitch, float* __restrict__ dst) {
-    const uint32_t q = blockIdx.x;
-    for (uint32_t e = threadIdx.x; e < qpitch; e += blockDim.x) dst[(size_t)q * qpitch + e] = e < dim ? (float)src[(size_t)q * dim + e] : 0.f;
-}
-static void round_tf32(const float* src, float* dst, uint64_t count, cudaStream_t st) {
-    if (count == 0) return;
-    round_tf32_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(count, 256), (uint64_t)sm_count() * 32), 256, 0, st>>>(src, dst, count);
-    VDB_LAUNCHED();
+
+// exact power of two that brings a largest magnitude `m` to (2^13, 2^14]: a factor 4 under FP16's largest finite value
+static float f16_scale_for(float m) {
+    if (!(m > 0.f) || !std::isfinite(m)) return 1.0f;
+    int e = 0;
+    std::frexp(m, &e);   // m = f * 2^e, f in [0.5, 1)
+    return std::ldexp(1.0f, std::max(-100, std::min(100, 14 - e)));
 }
 
 // stratified random sample: one row per bucket of n/ns consecutive rows, at a hashed offset inside the bucket
-// (a plain stride would alias with periodic data)
-__global__ void gather_sample_kernel(const float* __restrict__ rows_tf32, const float* __restrict__ sqnorm,
-                                     const float* __restrict__ rnorm, uint64_t n, uint32_t pitch, uint32_t ns,
-                                     float* __restrict__ out, float* __restrict__ out_sq, float* __restrict__ out_rn) {
+// (a plain stride would alias with periodic data). Operand rows are copied as 16-byte units.
+__global__ void gather_sample_kernel(const uint4* __restrict__ op_rows, uint32_t row_u4, const float* __restrict__ colA,
+                                     const float* __restrict__ rnorm, const float* __restrict__ ex, uint64_t n, uint32_t ns,
+                                     uint4* __restrict__ out, float* __restrict__ out_sq, float* __restrict__ out_rn,
+                                     float* __restrict__ out_ex) {
     const uint32_t i = blockIdx.x;
     if (i >= ns) return;
     const uint64_t lo = (uint64_t)i * n / ns, hi = (uint64_t)(i + 1) * n / ns;
@@ -432,63 +547,136 @@ __global__ void gather_sample_kernel(const float* __restrict__ rows_tf32, const 
     h *= 0x94D049BB133111EBull;
     h ^= h >> 29;
     const uint64_t row = lo + h % (hi > lo ? hi - lo : 1);
-    for (uint32_t e = threadIdx.x; e < pitch; e += blockDim.x) out[(size_t)i * pitch + e] = rows_tf32[row * pitch + e];
+    for (uint32_t e = threadIdx.x; e < row_u4; e += blockDim.x) out[(size_t)i * row_u4 + e] = op_rows[row * row_u4 + e];
     if (threadIdx.x == 0) {
-        out_sq[i] = sqnorm[row];
+        out_sq[i] = colA[row];
         out_rn[i] = rnorm[row];
+        out_ex[i] = ex[row];
     }
 }
 
-__global__ void rinv_kernel(const float* __restrict__ rn, uint64_t n, float* __restrict__ out) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        out[i] = rn[i] > 0.f ? 1.0f / rn[i] : 0.f;
+void drop_side_arrays(vdb_dataset* ds) {
+    for (void* p : {(void*)ds->d_lo, (void*)ds->d_sqnorm, (void*)ds->d_ex, ds->d_op, ds->d_sample, (void*)ds->d_sample_sq,
+                    (void*)ds->d_sample_rn, (void*)ds->d_sample_ex})
+        if (p) cudaFree(p);
+    ds->d_lo = ds->d_sqnorm = ds->d_ex = ds->d_sample_sq = ds->d_sample_rn = ds->d_sample_ex = nullptr;
+    ds->d_op = ds->d_sample = nullptr;
+    ds->sample_n = 0;
+    ds->side_n = 0;
+}
+
+static int forced_kind() {   // VDB_GEMM_KIND = tf32 | f16 (tests / tuning); default: chosen per dataset
+    const char* e = getenv("VDB_GEMM_KIND");
+    if (!e) return -1;
+    return (e[0] == 't' || e[0] == '0') ? KIND_TF32 : KIND_F16;
 }
 
 static std::mutex g_side_mu;
-// ||x||^2 and ||x|| per row, cached on the (logically const) dataset handle
-static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st) {
+// per-row scalars, the MMA operand (an FP16 copy, or the fp32 rows in place for the TF32 kind) and the threshold
+// sample, cached on the (logically const) dataset handle; `kind` < 0: choose
+static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st, int kind = -1) {
     vdb_dataset* ds = const_cast<vdb_dataset*>(cds);
     std::lock_guard<std::mutex> lk(g_side_mu);
-    if (ds->d_sqnorm && ds->side_n == ds->n) return;
-    if (ds->d_sqnorm) cudaFree(ds->d_sqnorm);
-    if (ds->d_lo) cudaFree(ds->d_lo);
-    if (ds->d_tf32) cudaFree(ds->d_tf32);
-    if (ds->d_sample) cudaFree(ds->d_sample);
-    if (ds->d_sample_sq) cudaFree(ds->d_sample_sq);
-    if (ds->d_sample_rn) cudaFree(ds->d_sample_rn);
-    ds->d_sqnorm = ds->d_lo = ds->d_tf32 = ds->d_sample = ds->d_sample_sq = ds->d_sample_rn = nullptr;
-    VDB_CUDA(cudaMalloc(&ds->d_sqnorm, ds->n * 4));
-    VDB_CUDA(cudaMalloc(&ds->d_lo, ds->n * 4));
-    VDB_CUDA(cudaMalloc(&ds->d_tf32, ds->n * (size_t)ds->pitch * 4));
-    if (ds->dtype == VDB_F32) round_tf32((const float*)ds->d_rows, ds->d_tf32, ds->n * ds->pitch, st);
-    else u8_to_f32((const uint8_t*)ds->d_rows, ds->d_tf32, ds->n * ds->pitch, st);  // 8-bit values are exact in TF32
+    if (kind < 0) kind = forced_kind();
+    if (ds->d_sqnorm && ds->side_n == ds->n && (kind < 0 || kind == ds->op_kind)) return;
+    drop_side_arrays(ds);
+    const bool u8 = ds->dtype == VDB_U8;
+    const bool cosine = ds->metric == VDB_COSINE;
+    if (u8) kind = KIND_F16;   // 8-bit values are exact in FP16; there is no in-place operand for bytes
+    const uint64_t n = ds->n;
+    VDB_CUDA(cudaMalloc(&ds->d_sqnorm, n * 4));
+    VDB_CUDA(cudaMalloc(&ds->d_lo, n * 4));
+    VDB_CUDA(cudaMalloc(&ds->d_ex, n * 4));
+    const uint32_t grid = (uint32_t)ceil_div<uint64_t>(n, 8);   // 8 warps per CTA, one row each
+    auto means = [&](float* m_norm, float* m_ex) {
+        DevBuf m(8, st);
+        const uint64_t stride = std::max<uint64_t>(1, n / 65536);
+        mean_kernel<<<1, 1024, 0, st>>>(ds->d_lo, n, stride, m.as<float>());
+        VDB_LAUNCHED();
+        mean_kernel<<<1, 1024, 0, st>>>(ds->d_ex, n, stride, m.as<float>() + 1);
+        VDB_LAUNCHED();
+        float h[2];
+        VDB_CUDA(cudaMemcpyAsync(h, m.p, 8, cudaMemcpyDeviceToHost, st));
+        VDB_CUDA(cudaStreamSynchronize(st));
+        *m_norm = h[0];
+        *m_ex = h[1];
+    };
+    auto build_f16 = [&]() {
+        float scale = 1.0f;
+        if (!u8) {
+            DevBuf mx(4, st);
+            VDB_CUDA(cudaMemsetAsync(mx.p, 0, 4, st));
+            absmax_kernel<float><<<(uint32_t)sm_count() * 8, 256, 0, st>>>((const float*)ds->d_rows, n, ds->dim, ds->pitch, mx.as<uint32_t>());
+            VDB_LAUNCHED();
+            float h = 0.f;
+            VDB_CUDA(cudaMemcpyAsync(&h, mx.p, 4, cudaMemcpyDeviceToHost, st));
+            VDB_CUDA(cudaStreamSynchronize(st));
+            scale = f16_scale_for(h);
+        }
+        ds->op_scale = scale;
+        ds->op_pitch = round_up(ds->dim, 8u);   // 16-byte rows for the TMA
+        VDB_CUDA(cudaMalloc(&ds->d_op, n * (size_t)ds->op_pitch * 2));
+        if (u8)
+            row_side_kernel<uint8_t, KIND_F16><<<grid, 256, 0, st>>>((const uint8_t*)ds->d_rows, n, ds->dim, ds->pitch, scale, ds->op_pitch,
+                                                                     (__half*)ds->d_op, cosine, ds->d_sqnorm, ds->d_lo, ds->d_ex);
+        else
+            row_side_kernel<float, KIND_F16><<<grid, 256, 0, st>>>((const float*)ds->d_rows, n, ds->dim, ds->pitch, scale, ds->op_pitch,
+                                                                   (__half*)ds->d_op, cosine, ds->d_sqnorm, ds->d_lo, ds->d_ex);
+        VDB_LAUNCHED();
+        ds->op_kind = KIND_F16;
+        ds->op_owned = true;
+    };
+    auto build_tf32 = [&]() {
+        row_side_kernel<float, KIND_TF32><<<grid, 256, 0, st>>>((const float*)ds->d_rows, n, ds->dim, ds->pitch, 1.0f, 0, nullptr, cosine,
+                                                                ds->d_sqnorm, ds->d_lo, ds->d_ex);
+        VDB_LAUNCHED();
+        ds->op_kind = KIND_TF32;
+        ds->op_scale = 1.0f;
+        ds->op_pitch = ds->pitch;
+        ds->d_op = nullptr;     // the fp32 rows themselves are the operand
+        ds->op_owned = false;
+    };
+    if (kind == KIND_TF32) {
+        build_tf32();
+        means(&ds->mean_norm, &ds->mean_ex);
+    } else {
+        build_f16();
+        means(&ds->mean_norm, &ds->mean_ex);
+        // FP16 carries TF32's mantissa: its measured error norm sits at ~2^-12 of the row norm. Rows whose dynamic range
+        // exceeds FP16's exponent (tiny components flushed next to large ones) show up as a larger norm; then the TF32
+        // kind (8-bit exponent, operand = the fp32 rows in place) prunes better.
+        const float rel = cosine ? ds->mean_ex : (ds->mean_norm > 0.f ? ds->mean_ex / ds->mean_norm : 0.f);
+        if (kind < 0 && !u8 && rel > 1.0e-3f) {
+            cudaFree(ds->d_op);
+            ds->d_op = nullptr;
+            build_tf32();
+            means(&ds->mean_norm, &ds->mean_ex);
+        }
+    }
     // ~3 % of the shard, so the sample pass stays a small fixed fraction of the filter pass on every shard size
-    ds->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(G_SAMPLE, ds->n / 2), std::max<uint64_t>(2048, ds->n / 30));
-    VDB_CUDA(cudaMalloc(&ds->d_sample, (size_t)ds->sample_n * ds->pitch * 4));
+    ds->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(G_SAMPLE, n / 2), std::max<uint64_t>(2048, n / 30));
+    const size_t op_row_bytes = ds->op_kind == KIND_F16 ? (size_t)ds->op_pitch * 2 : ds->pitch_bytes();
+    VDB_CUDA(cudaMalloc(&ds->d_sample, (size_t)ds->sample_n * op_row_bytes));
     VDB_CUDA(cudaMalloc(&ds->d_sample_sq, (size_t)ds->sample_n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_sample_rn, (size_t)ds->sample_n * 4));
-    vdb_dataset tmp = *ds;
-    tmp.metric = VDB_COSINE;
-    row_cache(&tmp, ds->d_lo, st);  // ||x||
-    if (ds->metric == VDB_L2SQR) {
-        tmp.metric = VDB_L2SQR;
-        row_cache(&tmp, ds->d_sqnorm, st);  // ||x||^2
-    } else {
-        rinv_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(ds->n, 256), 65535), 256, 0, st>>>(ds->d_lo, ds->n, ds->d_sqnorm);
-        VDB_LAUNCHED();  // 1/||x|| (0 for zero rows)
-    }
-    gather_sample_kernel<<<ds->sample_n, 256, 0, st>>>(ds->d_tf32, ds->d_sqnorm, ds->d_lo, ds->n, ds->pitch, ds->sample_n,
-                                                       ds->d_sample, ds->d_sample_sq, ds->d_sample_rn);
+    VDB_CUDA(cudaMalloc(&ds->d_sample_ex, (size_t)ds->sample_n * 4));
+    gather_sample_kernel<<<ds->sample_n, 128, 0, st>>>((const uint4*)(ds->op_kind == KIND_F16 ? ds->d_op : ds->d_rows),
+                                                       (uint32_t)(op_row_bytes / 16), ds->d_sqnorm, ds->d_lo, ds->d_ex, n, ds->sample_n,
+                                                       (uint4*)ds->d_sample, ds->d_sample_sq, ds->d_sample_rn, ds->d_sample_ex);
     VDB_LAUNCHED();
-    {
-        DevBuf m(4, st);
-        mean_kernel<<<1, 1024, 0, st>>>(ds->d_lo, ds->n, std::max<uint64_t>(1, ds->n / 65536), m.as<float>());
-        VDB_LAUNCHED();
-        VDB_CUDA(cudaMemcpyAsync(&ds->mean_norm, m.p, 4, cudaMemcpyDeviceToHost, st));
-        VDB_CUDA(cudaStreamSynchronize(st));
-    }
-    ds->side_n = ds->n;
+    VDB_CUDA(cudaStreamSynchronize(st));
+    ds->side_n = n;
 }
+
+// tensor map of `nrows` operand rows of the dataset's kind starting at `base` (row pitch in bytes)
+static CUtensorMap make_op_map(int kind, const void* base, uint32_t dim, uint64_t nrows, uint64_t pitch_bytes, uint32_t box_rows) {
+    return kind == KIND_F16 ? make_map_f16(base, dim, nrows, pitch_bytes, box_rows) : make_map(base, dim, nrows, pitch_bytes, box_rows);
+}
+static const void* op_rows_of(const vdb_dataset* ds) { return ds->op_kind == KIND_F16 ? ds->d_op : ds->d_rows; }
+static size_t op_row_bytes_of(const vdb_dataset* ds) {
+    return ds->op_kind == KIND_F16 ? (size_t)ds->op_pitch * 2 : ds->pitch_bytes();
+}
+static uint32_t kblocks_of(int kind, uint32_t dim) { return ceil_div(dim, kind == KIND_F16 ? 64u : 32u); }
 
 static int gemm_ctas();
 // tiling of one pass: query-tile units x row slabs (small slabs, query tile fastest: the CTAs in flight share a few
@@ -509,10 +697,10 @@ static int gemm_ctas() {
     return v == 1 ? 1 : 2;
 }
 
-template <int MODE, int CTAS, int METRIC>
+template <int MODE, int CTAS, int METRIC, int KIND>
 static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st) {
-    using Cfg = GemmCfg<CTAS>;
-    auto kern = flat_gemm_kernel<MODE, CTAS, METRIC>;
+    using Cfg = GemmCfg<CTAS, KIND>;
+    auto kern = flat_gemm_kernel<MODE, CTAS, METRIC, KIND>;
     static std::atomic<size_t> configured[VDB_MAX_DEVICES];
     ensure_dyn_smem(kern, Cfg::SMEM, configured);
     const uint32_t sms = (uint32_t)sm_count();
@@ -537,71 +725,140 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
     VDB_LAUNCHED();
 }
 
-// mode 0 = store every score, 1 = filter, 2 = per-slab smallest scores; `p` must have been planned (plan_gemm)
-static void launch_gemm(int mode, int metric, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p,
-                        cudaStream_t st, int ctas = 0) {
-    const int sel = ((ctas ? ctas : gemm_ctas()) == 2 ? 6 : 0) + mode * 2 + (metric == VDB_COSINE ? 1 : 0);
-    switch (sel) {
-        case 0: launch_gemm_t<0, 1, VDB_L2SQR>(mq, mx, p, st); break;
-        case 1: launch_gemm_t<0, 1, VDB_COSINE>(mq, mx, p, st); break;
-        case 2: launch_gemm_t<1, 1, VDB_L2SQR>(mq, mx, p, st); break;
-        case 3: launch_gemm_t<1, 1, VDB_COSINE>(mq, mx, p, st); break;
-        case 4: launch_gemm_t<2, 1, VDB_L2SQR>(mq, mx, p, st); break;
-        case 5: launch_gemm_t<2, 1, VDB_COSINE>(mq, mx, p, st); break;
-        case 6: launch_gemm_t<0, 2, VDB_L2SQR>(mq, mx, p, st); break;
-        case 7: launch_gemm_t<0, 2, VDB_COSINE>(mq, mx, p, st); break;
-        case 8: launch_gemm_t<1, 2, VDB_L2SQR>(mq, mx, p, st); break;
-        case 9: launch_gemm_t<1, 2, VDB_COSINE>(mq, mx, p, st); break;
-        case 10: launch_gemm_t<2, 2, VDB_L2SQR>(mq, mx, p, st); break;
-        default: launch_gemm_t<2, 2, VDB_COSINE>(mq, mx, p, st); break;
+template <int MODE, int CTAS>
+static void launch_gemm_mk(int metric, int kind, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st) {
+    if (metric == VDB_COSINE) {
+        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_F16>(mq, mx, p, st);
+        else launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_TF32>(mq, mx, p, st);
+    } else {
+        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_F16>(mq, mx, p, st);
+        else launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_TF32>(mq, mx, p, st);
     }
 }
 
-// c * ||q|| per query; c bounds |S'_tf32 - S'_exact| / (||q|| ||x||): two TF32 operand roundings (2^-10 each,
-// truncation) + their product + K fp32 accumulation steps (K * 2^-23), times 2 for the -2 q.x term.
-// Query side of the tensor path in one pass (one warp per query): padded fp32 copy (exact rerank), TF32-rounded copy
-// (MMA operand) and, for L2Sqr, ||q||^2 and c * ||q||. The norm is summed exactly like row_cache's PM_SQNORM kernel
-// (lane-strided fma chain + xor butterfly), so thresholds do not depend on which of the two produced it.
-template <typename T>
+// mode 0 = store every score, 1 = filter, 2 = per-slab smallest scores; `p` must have been planned (plan_gemm)
+static void launch_gemm(int mode, int metric, int kind, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p,
+                        cudaStream_t st, int ctas = 0) {
+    const bool pair = (ctas ? ctas : gemm_ctas()) == 2;
+    switch (mode * 2 + (pair ? 1 : 0)) {
+        case 0: launch_gemm_mk<0, 1>(metric, kind, mq, mx, p, st); break;
+        case 1: launch_gemm_mk<0, 2>(metric, kind, mq, mx, p, st); break;
+        case 2: launch_gemm_mk<1, 1>(metric, kind, mq, mx, p, st); break;
+        case 3: launch_gemm_mk<1, 2>(metric, kind, mq, mx, p, st); break;
+        case 4: launch_gemm_mk<2, 1>(metric, kind, mq, mx, p, st); break;
+        default: launch_gemm_mk<2, 2>(metric, kind, mq, mx, p, st); break;
+    }
+}
+
+// Query side of the tensor path in one pass (one warp per query): padded fp32 copy (exact rerank), the MMA operand
+// q~ (FP16 of q * s_q with s_q an exact power of two chosen per query, or q rounded to TF32), ||q||^2, the operand
+// error ||q - q~|| and a flag for non-finite queries (they are answered by the exact scan). The norm is summed exactly
+// like row_cache's PM_SQNORM kernel (lane-strided fma chain + xor butterfly), so thresholds do not depend on which of
+// the two produced it.
+template <typename T, int KIND>
 __global__ void __launch_bounds__(256) tq_prepare_kernel(const T* __restrict__ src, uint32_t nq, uint32_t dim, uint32_t qpitch,
-                                                         float c, float* __restrict__ qcopy, float* __restrict__ qround,
-                                                         float* __restrict__ qsq, float* __restrict__ qcm) {
+                                                         uint32_t op_pitch, float* __restrict__ qcopy, void* __restrict__ qop,
+                                                         float* __restrict__ qsq, float* __restrict__ qerr,
+                                                         float* __restrict__ qscale, uint32_t* __restrict__ qbad) {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
     const T* row = src + (size_t)q * dim;
-    float s = 0.f;
-    for (uint32_t e = lane; e < qpitch; e += 32) {
+    float scale = 1.0f;
+    bool finite = true;
+    if (KIND == KIND_F16) {
+        float m = 0.f;
+        for (uint32_t e = lane; e < dim; e += 32) {
+            const float v = fabsf((float)row[e]);
+            finite = finite && (v <= 3.0e38f);
+            m = fmaxf(m, v <= 3.0e38f ? v : 0.f);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m > 0.f) {
+            int e2 = (int)((__float_as_uint(m) >> 23) & 0xff) - 126;   // m = f * 2^e2, f in [0.5, 1) (normal m)
+            e2 = max(-100, min(100, 14 - e2));
+            scale = __uint_as_float((uint32_t)(e2 + 127) << 23);
+        }
+    }
+    const float inv_scale = 1.0f / scale;
+    float s = 0.f, ee = 0.f;
+    const uint32_t span = max(qpitch, op_pitch);
+    for (uint32_t e = lane; e < span; e += 32) {
         const float v = e < dim ? (float)row[e] : 0.f;
-        uint32_t r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-        qcopy[(size_t)q * qpitch + e] = v;
-        qround[(size_t)q * qpitch + e] = __uint_as_float(r);
-        if (e < dim) s = fmaf(v, v, s);
+        float back;
+        if (KIND == KIND_F16) {
+            const __half h = __float2half_rn(v * scale);
+            if (e < op_pitch) reinterpret_cast<__half*>(qop)[(size_t)q * op_pitch + e] = h;
+            back = __half2float(h) * inv_scale;
+        } else {
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+            if (e < op_pitch) reinterpret_cast<float*>(qop)[(size_t)q * op_pitch + e] = __uint_as_float(r);
+            back = __uint_as_float(r);
+        }
+        if (e < qpitch) qcopy[(size_t)q * qpitch + e] = v;
+        finite = finite && (fabsf(v) <= 3.0e38f);
+        if (e < dim) {
+            const float d = v - back;
+            s = fmaf(v, v, s);
+            ee = fmaf(d, d, ee);
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && qsq) {
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ee += __shfl_xor_sync(0xffffffffu, ee, o);
+    }
+    finite = __all_sync(0xffffffffu, finite);
+    if (lane == 0) {
         qsq[q] = s;
-        qcm[q] = c * sqrtf(s);
+        qerr[q] = sqrtf(ee) * 1.0001f;
+        qscale[q] = scale;
+        qbad[q] = finite ? 0u : 1u;
     }
 }
-__global__ void qcm_kernel(const float* __restrict__ qsq, uint32_t nq, float c, float* __restrict__ qcm) {
+
+// Pruning-bound coefficients per query (see GemmParams). With q = q~/s_q + dq, x = x~/s_x + dx, ||dq|| = eq, ||dx|| = ex and
+// the fp32 accumulation error of the contraction bounded by ACC * ||q~|| ||x~|| (ACC = dim * 2^-23):
+//   |q.x - acc / (s_q s_x)| <= ACC qn' xn' + qn' ex + eq xn',   qn' = ||q|| + eq,  xn' = ||x|| + ex
+// L2Sqr:  S' = ||x||^2 - 2 acc / (s_q s_x) - 2 (that bound) = sq + qd acc - qab ex - qb rn  with
+//         qd = -2 / (s_q s_x), qb = 2 (ACC qn' + eq), qab = 2 qn' + qb
+// cosine: S' = 1 - acc / (s_q s_x ||q|| ||x||) - bound / (||q|| ||x||) - 1e-6 = qb - (qd / ||x||) acc - qab exr  with eqr = eq / ||q||,
+//         exr = ex / ||x||, qd = 1 / (s_q s_x ||q||), qb = 1 - 1e-6 - (ACC (1 + eqr) + eqr), qab = (1 + eqr)(1 + ACC) + eqr
+__global__ void tq_coeff_kernel(const float* __restrict__ qsq, const float* __restrict__ qerr, const float* __restrict__ qscale,
+                                const float* __restrict__ qnorm_cos, uint32_t nq, float acc, float row_scale,
+                                float* __restrict__ qd, float* __restrict__ qab, float* __restrict__ qb) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) qcm[q] = c * sqrtf(qsq[q]);
-}
-// cosine: qcm = 1/||q|| with ||q|| exactly as the streaming scan computes it (prepare_queries)
-__global__ void qinv_kernel(const float* __restrict__ qn, uint32_t nq, float* __restrict__ qinv) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) qinv[q] = qn[q] > 0.f ? 1.0f / qn[q] : 0.f;
+    if (q >= nq) return;
+    const float eq = qerr[q];
+    const float inv_scales = 1.0f / (qscale[q] * row_scale);   // powers of two: exact
+    if (!qnorm_cos) {
+        const float qn1 = (sqrtf(qsq[q]) + eq) * 1.0001f;
+        const float b = 2.0f * (acc * qn1 + eq) * 1.0001f;
+        qd[q] = -2.0f * inv_scales;
+        qb[q] = b;
+        qab[q] = 2.0f * qn1 + b;
+    } else {
+        const float qn = qnorm_cos[q];
+        const float eqr = qn > 0.f ? eq / qn * 1.0001f : 0.f;
+        qd[q] = qn > 0.f ? inv_scales / qn : 0.f;
+        qb[q] = 1.0f - 1e-6f - (acc * (1.0f + eqr) + eqr) * 1.0001f;
+        qab[q] = ((1.0f + eqr) * (1.0f + acc) + eqr) * 1.0001f;
+    }
 }
 // tau_q = (j0-th smallest sampled S') + margin. j0 is chosen so that the k-th best S' of the shard is <= S'_(j0)
-// with high probability; because S <= S' + 2 c||q|| ||x||, the margin (2.5 x the pruning bound at the mean row
-// norm) keeps the k-th EXACT distance inside the threshold. The check kernel verifies it per query afterwards.
+// with high probability; because S <= S' + 2 b(q, x), the margin (2.5 x the pruning bound at the mean row error / mean
+// row norm) keeps the k-th EXACT distance inside the threshold. The check kernel verifies it per query afterwards.
 __global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, uint32_t j0,
-                                     const float* __restrict__ qcm, float mean_norm, float* __restrict__ tau) {
+                                     const float* __restrict__ qab, const float* __restrict__ qb, float mean_norm, float mean_ex,
+                                     int cosine, float* __restrict__ tau) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) tau[q] = key_dist(keys[(size_t)q * j + (j0 - 1)]) + 2.5f * (qcm ? qcm[q] * mean_norm : mean_norm);
+    if (q >= nq) return;
+    const uint64_t kk = keys[(size_t)q * j + (j0 - 1)];
+    const float s = kk == KEY_NONE ? __uint_as_float(0x7f800000u) : key_dist(kk);
+    const float b = cosine ? (1.0f - qb[q]) + qab[q] * mean_ex : qab[q] * mean_ex + qb[q] * mean_norm;
+    tau[q] = s + 3.0f * b;
 }
 // exclusive scan of min(cnt, cap) over the queries (one block; nq is at most a few 100k)
 __global__ void __launch_bounds__(1024) cand_offsets_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
@@ -720,9 +977,10 @@ __global__ void rekey_dev_count_kernel(const float* __restrict__ dist, const uin
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
         keys[j] = make_key(dist[j], ids[j] + id_base);
 }
-__global__ void overflow_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap, uint32_t* __restrict__ flag) {
+__global__ void overflow_kernel(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ qbad, uint32_t nq, uint32_t cap,
+                                uint32_t* __restrict__ flag) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) flag[q] = cnt[q] > cap ? 1u : 0u;
+    if (q < nq) flag[q] = (cnt[q] > cap || qbad[q]) ? 1u : 0u;   // non-finite queries go to the exact scan
 }
 // completeness check; failing queries are appended to redo[]
 // keys / overflow are indexed by the LOCAL query i of the checked range [q0, q0 + cnt) (a row-sharded search checks
@@ -795,16 +1053,16 @@ uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps) {
 
 }  // namespace vdb
 
-// per-call query context of the tensor path: padded fp32 copy (exact rerank), TF32-rounded copy (MMA operand),
-// ||q||^2, c||q|| and the TMA descriptor of the rounded copy
+// per-call query context of the tensor path: padded fp32 copy (exact rerank), the MMA operand q~, ||q||^2, the
+// pruning-bound coefficients and the TMA descriptor of the operand
 struct vdb_tq {
     const vdb_dataset* ds = nullptr;
     const void* d_queries = nullptr;
-    uint32_t nq = 0, qpitch = 0;
+    uint32_t nq = 0, qpitch = 0, op_pitch = 0;
+    int kind = 0;
     cudaStream_t st = nullptr;
-    vdb::DevBuf qcopy, qround, qsq, qcm, cnt;
+    vdb::DevBuf qcopy, qop, qsq, qerr, qscale, qbad, qd, qab, qb, cnt;
     vdb::QueryTile qtile;   // cosine: ||q|| exactly as the streaming scan computes it
-    float kc = 0.f, cbound = 0.f;
     CUtensorMap mq;
     uint32_t cap = 0;
     int ctas = 2;   // CTAs per work unit: pairs (M = 256 queries), single CTAs (M = 128) for batches of <= 128 queries
@@ -812,49 +1070,42 @@ struct vdb_tq {
 
 namespace vdb {
 
-vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st) {
-    VDB_REQUIRE(flat_gemm_supported(ds, nq, 1), "tensor-core Flat path: unsupported dataset");
-    ensure_side_arrays(ds, st);
+vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, bool any_size) {
+    VDB_REQUIRE(any_size || flat_gemm_supported(ds, nq, 1), "tensor-core Flat path: unsupported dataset");
+    ensure_side_arrays(ds, st, any_size ? ds->op_kind : -1);
     const uint32_t dim = ds->dim;
-    // pruning-bound coefficient: both operands rounded to TF32 (2^-11 each, products then exact in fp32) plus
-    // dim fp32 accumulation steps, times 2 for the -2 q.x term
-    // (u8 rows and queries are exact in TF32: only the accumulation term remains)
-    const float c = ds->dtype == VDB_F32 ? 2.0f * (ldexpf(1.0f, -10) * 1.001f + (float)dim * ldexpf(1.0f, -23))
-                                         : 2.0f * (ldexpf(1.0f, -20) + (float)dim * ldexpf(1.0f, -23));
+    const float acc = (float)dim * ldexpf(1.0f, -23);   // fp32 accumulation of the contraction
     auto tq = new vdb_tq();
     try {
         tq->ds = ds;
         tq->d_queries = d_queries;
         tq->nq = nq;
         tq->st = st;
+        tq->kind = ds->op_kind;
         tq->qpitch = round_up(dim, 4u);
-        const size_t qbytes = (size_t)nq * tq->qpitch * 4;
-        tq->qcopy = DevBuf(qbytes, st);
-        tq->qround = DevBuf(qbytes, st);
-        tq->qsq = DevBuf((size_t)nq * 4, st);
-        tq->qcm = DevBuf((size_t)nq * 4, st);
-        tq->cnt = DevBuf((size_t)nq * 4, st);
+        tq->op_pitch = tq->kind == KIND_F16 ? round_up(dim, 8u) : tq->qpitch;
+        tq->qcopy = DevBuf((size_t)nq * tq->qpitch * 4, st);
+        tq->qop = DevBuf((size_t)nq * tq->op_pitch * (tq->kind == KIND_F16 ? 2 : 4), st);
+        for (DevBuf* b : {&tq->qsq, &tq->qerr, &tq->qscale, &tq->qbad, &tq->qd, &tq->qab, &tq->qb, &tq->cnt})
+            *b = DevBuf((size_t)nq * 4, st);
         const bool l2 = ds->metric == VDB_L2SQR;
-        float* qsq = l2 ? tq->qsq.as<float>() : nullptr;
         const uint32_t pgrid = ceil_div(nq, 8u);   // 8 warps per CTA, one query each
-        if (ds->dtype == VDB_U8)
-            tq_prepare_kernel<uint8_t><<<pgrid, 256, 0, st>>>((const uint8_t*)d_queries, nq, dim, tq->qpitch, c,
-                                                              tq->qcopy.as<float>(), tq->qround.as<float>(), qsq, tq->qcm.as<float>());
-        else
-            tq_prepare_kernel<float><<<pgrid, 256, 0, st>>>((const float*)d_queries, nq, dim, tq->qpitch, c,
-                                                            tq->qcopy.as<float>(), tq->qround.as<float>(), qsq, tq->qcm.as<float>());
-        VDB_LAUNCHED();
-        if (!l2) {
-            // cosine distance error <= (c/2) from the contraction + the reciprocal products of the epilogue
-            tq->cbound = 0.5f * c + 1e-6f;
-            tq->kc = 1.0f - tq->cbound;
-            tq->qtile = prepare_queries(ds, d_queries, nq, st);
-            qinv_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qtile.qcache.as<float>(), nq, tq->qcm.as<float>());
+        auto prep = [&](auto kern, auto* src) {
+            kern<<<pgrid, 256, 0, st>>>(src, nq, dim, tq->qpitch, tq->op_pitch, tq->qcopy.as<float>(), tq->qop.p, tq->qsq.as<float>(),
+                                        tq->qerr.as<float>(), tq->qscale.as<float>(), tq->qbad.as<uint32_t>());
             VDB_LAUNCHED();
-        }
-        tq->mq = make_map(tq->qround.as<float>(), dim, nq, (uint64_t)tq->qpitch * 4, GM);
+        };
+        if (ds->dtype == VDB_U8) prep(tq_prepare_kernel<uint8_t, KIND_F16>, (const uint8_t*)d_queries);
+        else if (tq->kind == KIND_F16) prep(tq_prepare_kernel<float, KIND_F16>, (const float*)d_queries);
+        else prep(tq_prepare_kernel<float, KIND_TF32>, (const float*)d_queries);
+        if (!l2) tq->qtile = prepare_queries(ds, d_queries, nq, st);
+        tq_coeff_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->qsq.as<float>(), tq->qerr.as<float>(), tq->qscale.as<float>(),
+                                                            l2 ? nullptr : tq->qtile.qcache.as<float>(), nq, acc, ds->op_scale,
+                                                            tq->qd.as<float>(), tq->qab.as<float>(), tq->qb.as<float>());
+        VDB_LAUNCHED();
+        tq->mq = make_op_map(tq->kind, tq->qop.p, dim, nq, (uint64_t)tq->op_pitch * (tq->kind == KIND_F16 ? 2 : 4), GM);
         // a batch that fits one 128-query tile runs on single CTAs: a CTA pair would spend half of its MMAs on padding
-        // (the pass is then HBM-bound on the TF32 copy of the rows instead of tensor-bound)
+        // (the pass is then HBM-bound on the operand rows instead of tensor-bound)
         static const bool small_single = !(getenv("VDB_GEMM_SMALL_PAIRS") && atoi(getenv("VDB_GEMM_SMALL_PAIRS")));
         tq->ctas = (small_single && nq <= (uint32_t)GM) ? 1 : gemm_ctas();
     } catch (...) {
@@ -864,21 +1115,35 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
     return tq;
 }
 void tensor_end(vdb_tq* tq) { delete tq; }
-void tensor_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, cudaStream_t st) {
+void operand_info(const vdb_dataset* ds, int* kind, float* scale, float* mean_norm, float* mean_ex, uint64_t* side_bytes) {
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    const bool built = ds->d_sqnorm && ds->side_n == ds->n;
+    if (kind) *kind = built ? ds->op_kind : -1;
+    if (scale) *scale = ds->op_scale;
+    if (mean_norm) *mean_norm = ds->mean_norm;
+    if (mean_ex) *mean_ex = ds->mean_ex;
+    if (side_bytes)
+        *side_bytes = built ? ds->n * 12 + (ds->op_kind == KIND_F16 ? ds->n * (uint64_t)ds->op_pitch * 2 : 0) +
+                                  (uint64_t)ds->sample_n * (op_row_bytes_of(ds) + 12)
+                            : 0;
+}
+void tensor_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, float* mean_ex, cudaStream_t st) {
     VDB_REQUIRE(flat_gemm_supported(ds, 1, 1), "tensor-core Flat path: unsupported dataset");
     ensure_side_arrays(ds, st);
     if (n) *n = ds->n;
     if (sample_n) *sample_n = ds->sample_n;
     if (mean_norm) *mean_norm = ds->mean_norm;
+    if (mean_ex) *mean_ex = ds->mean_ex;
 }
 
 static GemmParams base_params(const vdb_tq* tq) {
     GemmParams p{};
     p.nq = tq->nq;
-    p.kblocks = ceil_div(tq->ds->dim, (uint32_t)GK);
-    p.qcm = tq->qcm.as<float>();
+    p.kblocks = kblocks_of(tq->kind, tq->ds->dim);
+    p.qd = tq->qd.as<float>();
+    p.qab = tq->qab.as<float>();
+    p.qb = tq->qb.as<float>();
     p.qnorm = tq->ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr;
-    p.kc = tq->kc;
     return p;
 }
 
@@ -888,46 +1153,47 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     cudaStream_t st = tq->st;
     const uint64_t ns = ds->sample_n;
     VDB_REQUIRE(j >= 1 && j <= ns, "sample order statistic %u out of range (sample %llu)", j, (unsigned long long)ns);
-    const CUtensorMap ms = make_map(ds->d_sample, ds->dim, ns, (uint64_t)ds->pitch * 4, GN / tq->ctas);
+    const CUtensorMap ms = make_op_map(tq->kind, ds->d_sample, ds->dim, ns, op_row_bytes_of(ds), GN / tq->ctas);
     GemmParams ps = base_params(tq);
     ps.nrows = ns;
     ps.row_stride = 1;
     ps.sqnorm = ds->d_sample_sq;
     ps.rnorm = ds->d_sample_rn;
+    ps.ex = ds->d_sample_ex;
     plan_gemm(ps, tq->ctas);
     if (j <= (uint32_t)G_TOPJ) {
         // the epilogue keeps each query's G_TOPJ smallest scores per slab in registers: nothing but
         // nq * nslabs * G_TOPJ keys ever reaches HBM
         DevBuf part((size_t)tq->nq * ps.nslabs * G_TOPJ * 8, st);
         ps.out_keys = part.as<uint64_t>();
-        launch_gemm(2, ds->metric, tq->mq, ms, ps, st, tq->ctas);
+        launch_gemm(2, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas);
         launch_merge_keys(part.as<uint64_t>(), ps.nslabs, tq->nq, G_TOPJ, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
     } else {
         DevBuf skeys((size_t)tq->nq * ns * 8, st);
         ps.out_keys = skeys.as<uint64_t>();
-        launch_gemm(0, ds->metric, tq->mq, ms, ps, st, tq->ctas);
+        launch_gemm(0, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas);
         launch_merge_keys(skeys.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
     }
 }
 
-// TAU: merge `nlists` shards' [nq][j] sample keys (list-major) and set tau_q = S'_(j0) + margin
-void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm,
+// TAU: merge `nlists` shards' [nq][j] sample keys (list-major) and set tau_q = S'_(j0) + margin; mean_norm / mean_ex are
+// the set-wide means (identical on every shard, so every shard derives the same thresholds)
+void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm, float mean_ex,
                 float* d_tau) {
     cudaStream_t st = tq->st;
     VDB_REQUIRE(j0 >= 1 && j0 <= (uint64_t)j * nlists, "j0 out of range");
     const uint32_t jj = std::min<uint64_t>(j0, (uint64_t)j * nlists);
-    const bool cosine = tq->ds->metric == VDB_COSINE;
+    const int cosine = tq->ds->metric == VDB_COSINE;
     if (nlists == 1) {   // a single ascending [nq][j] list: its jj-th entry is the order statistic, nothing to merge
-        tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(d_lists, tq->nq, j, jj, cosine ? nullptr : tq->qcm.as<float>(),
-                                                                      cosine ? tq->cbound : mean_norm, d_tau);
+        tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(d_lists, tq->nq, j, jj, tq->qab.as<float>(), tq->qb.as<float>(),
+                                                                      mean_norm, mean_ex, cosine, d_tau);
         VDB_LAUNCHED();
         return;
     }
     DevBuf merged((size_t)tq->nq * jj * 8, st);
     launch_merge_sorted(d_lists, nlists, tq->nq, j, jj, merged.as<uint64_t>(), nullptr, nullptr, nullptr, st);  // per-shard lists are ascending
-    tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj,
-                                                                  cosine ? nullptr : tq->qcm.as<float>(),
-                                                                  cosine ? tq->cbound : mean_norm, d_tau);
+    tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj, tq->qab.as<float>(),
+                                                                  tq->qb.as<float>(), mean_norm, mean_ex, cosine, d_tau);
     VDB_LAUNCHED();
 }
 
@@ -987,10 +1253,11 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     tq->cap = cap;
     DevBuf cand((size_t)nq * cap * 8, st);
     VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
-    const CUtensorMap mx = make_map(ds->d_tf32, dim, ds->n, (uint64_t)ds->pitch * 4, GN / tq->ctas);
+    const CUtensorMap mx = make_op_map(tq->kind, op_rows_of(ds), dim, ds->n, op_row_bytes_of(ds), GN / tq->ctas);
     GemmParams pf = base_params(tq);
     pf.sqnorm = ds->d_sqnorm;
     pf.rnorm = ds->d_lo;
+    pf.ex = ds->d_ex;
     pf.nrows = ds->n;
     pf.row_stride = 1;
     pf.tau = d_tau;
@@ -1014,6 +1281,21 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     // 8 parts cost more in launch tails than they hide
     uint32_t parts = parts_env ? parts_env : (tile_units >= 8192 ? 3u : 1u);
     parts = std::max(1u, std::min(parts, total_slabs));
+    // part i covers a share proportional to ratio^i of the slabs: the rerank of the LAST part is the only one that is
+    // not hidden under a contraction launch, so later parts are made smaller
+    const char* ratio_s = getenv("VDB_GEMM_PART_RATIO");
+    const double ratio = ratio_s ? std::max(0.2, std::min(1.0, atof(ratio_s))) : 1.0;
+    std::vector<uint32_t> part_end(parts);
+    {
+        double total_w = 0, w = 1.0, acc_w = 0;
+        for (uint32_t i = 0; i < parts; ++i, w *= ratio) total_w += w;
+        w = 1.0;
+        for (uint32_t i = 0; i < parts; ++i, w *= ratio) {
+            acc_w += w;
+            part_end[i] = i + 1 == parts ? total_slabs : std::max<uint32_t>(i + 1, (uint32_t)std::llround(total_slabs * acc_w / total_w));
+        }
+        for (uint32_t i = 0; i + 1 < parts; ++i) part_end[i] = std::min(part_end[i], total_slabs - (parts - 1 - i));
+    }
     static thread_local SideStream side;
     if (parts > 1) side.ensure(ds->device);
     cudaStream_t rs = parts > 1 ? side.s : st;   // rerank stream
@@ -1026,11 +1308,11 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         VDB_CUDA(cudaStreamWaitEvent(rs, side.ev, 0));
     }
     for (uint32_t part = 0; part < parts; ++part) {
-        const uint32_t s0 = (uint32_t)((uint64_t)total_slabs * part / parts), s1 = (uint32_t)((uint64_t)total_slabs * (part + 1) / parts);
+        const uint32_t s0 = part ? part_end[part - 1] : 0u, s1 = part_end[part];
         GemmParams pp = pf;
         pp.slab0 = s0;
         pp.nslabs = s1 - s0;
-        launch_gemm(1, ds->metric, tq->mq, mx, pp, st, tq->ctas);
+        launch_gemm(1, ds->metric, tq->kind, tq->mq, mx, pp, st, tq->ctas);
         uint32_t* snap = snaps.as<uint32_t>() + (size_t)part * nq;
         const uint32_t* prev = part ? snap - nq : nullptr;
         VDB_CUDA(cudaMemcpyAsync(snap, tq->cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToDevice, st));
@@ -1061,7 +1343,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr,
                       tq->cnt.as<uint32_t>());
     if (d_overflow) {
-        overflow_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, d_overflow);
+        overflow_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), tq->qbad.as<uint32_t>(), nq, cap, d_overflow);
         VDB_LAUNCHED();
     }
     if (d_cand_total) {
@@ -1110,7 +1392,7 @@ static void chunk_enqueue(const vdb_dataset* ds, const void* d_queries, uint32_t
     cs.nredo = DevBuf(4, st);
     cs.ctotal = DevBuf(8, st);
     tensor_sample_keys(cs.tq, j0, jkeys.as<uint64_t>());
-    tensor_tau(cs.tq, jkeys.as<uint64_t>(), 1, j0, j0, ds->mean_norm, tau.as<float>());
+    tensor_tau(cs.tq, jkeys.as<uint64_t>(), 1, j0, j0, ds->mean_norm, ds->mean_ex, tau.as<float>());
     tensor_filter_keys(cs.tq, k, j0, tau.as<float>(), d_keys, overflow.as<uint32_t>(), cs.ctotal.as<uint64_t>());
     tensor_check(cs.tq, d_keys, k, ds->n, tau.as<float>(), overflow.as<uint32_t>(), cs.redo.as<uint32_t>(),
                  cs.nredo.as<uint32_t>());
@@ -1223,26 +1505,26 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
 // their candidate list are redone by the FP32 list scan.
 constexpr uint32_t IVF_SAMPLE_RATE = 16;
 
-__global__ void gather_round_rows_kernel(const float* __restrict__ rows_tf32, const float* __restrict__ colA,
-                                         const float* __restrict__ rn, const uint32_t* __restrict__ members, uint64_t n,
-                                         uint32_t pitch, float* __restrict__ out, float* __restrict__ outA,
-                                         float* __restrict__ outR) {
+__global__ void gather_op_rows_kernel(const uint4* __restrict__ op_rows, uint32_t row_u4, const float* __restrict__ colA,
+                                      const float* __restrict__ rn, const float* __restrict__ ex,
+                                      const uint32_t* __restrict__ members, uint64_t n, uint4* __restrict__ out,
+                                      float* __restrict__ outA, float* __restrict__ outR, float* __restrict__ outE) {
     const uint64_t p = blockIdx.x;
     if (p >= n) return;
     const uint64_t row = members[p];
-    const float4* src = reinterpret_cast<const float4*>(rows_tf32 + row * pitch);
-    float4* dst = reinterpret_cast<float4*>(out + p * pitch);
-    for (uint32_t e = threadIdx.x; e < pitch / 4; e += blockDim.x) dst[e] = src[e];
+    for (uint32_t e = threadIdx.x; e < row_u4; e += blockDim.x) out[p * row_u4 + e] = op_rows[row * row_u4 + e];
     if (threadIdx.x == 0) {
         outA[p] = colA[row];
         outR[p] = rn[row];
+        outE[p] = ex[row];
     }
 }
 // sample row s of list l = one hashed position out of the s-th bucket of IVF_SAMPLE_RATE consecutive list positions
-__global__ void ivf_sample_gather_kernel(const float* __restrict__ rows_lo, const float* __restrict__ colA_lo,
-                                         const float* __restrict__ rn_lo, const uint64_t* __restrict__ offsets,
-                                         const uint64_t* __restrict__ soff, uint32_t nlist, uint32_t pitch,
-                                         float* __restrict__ out, float* __restrict__ outA, float* __restrict__ outR) {
+__global__ void ivf_sample_gather_kernel(const uint4* __restrict__ rows_lo, uint32_t row_u4, const float* __restrict__ colA_lo,
+                                         const float* __restrict__ rn_lo, const float* __restrict__ ex_lo,
+                                         const uint64_t* __restrict__ offsets, const uint64_t* __restrict__ soff, uint32_t nlist,
+                                         uint4* __restrict__ out, float* __restrict__ outA, float* __restrict__ outR,
+                                         float* __restrict__ outE) {
     const uint64_t s = blockIdx.x;
     uint32_t lo = 0, hi = nlist;  // largest l with soff[l] <= s
     while (hi - lo > 1) {
@@ -1257,12 +1539,11 @@ __global__ void ivf_sample_gather_kernel(const float* __restrict__ rows_lo, cons
     h *= 0x94D049BB133111EBull;
     h ^= h >> 29;
     const uint64_t pos = b0 + h % (b1 - b0);
-    const float4* src = reinterpret_cast<const float4*>(rows_lo + pos * pitch);
-    float4* dst = reinterpret_cast<float4*>(out + s * pitch);
-    for (uint32_t e = threadIdx.x; e < pitch / 4; e += blockDim.x) dst[e] = src[e];
+    for (uint32_t e = threadIdx.x; e < row_u4; e += blockDim.x) out[s * row_u4 + e] = rows_lo[pos * row_u4 + e];
     if (threadIdx.x == 0) {
         outA[s] = colA_lo[pos];
         outR[s] = rn_lo[pos];
+        outE[s] = ex_lo[pos];
     }
 }
 
@@ -1270,34 +1551,42 @@ static std::mutex g_ivf_side_mu;
 static void ensure_ivf_side(const vdb_dataset* ds, const vdb_ivf* civf, const std::vector<uint64_t>& h_off, cudaStream_t st) {
     vdb_ivf* ivf = const_cast<vdb_ivf*>(civf);
     std::lock_guard<std::mutex> lk(g_ivf_side_mu);
-    if (ivf->d_rows_lo) return;
     ensure_side_arrays(ds, st);
-    float *rows = nullptr, *colA = nullptr, *rn = nullptr;
-    VDB_CUDA(cudaMalloc(&rows, ds->n * (size_t)ds->pitch * 4));
+    if (ivf->d_rows_lo && ivf->op_kind == ds->op_kind) return;
+    VDB_REQUIRE(!ivf->d_rows_lo, "IVF tensor path: the dataset's operand kind changed under a built index");
+    const size_t rowb = op_row_bytes_of(ds);
+    const uint32_t row_u4 = (uint32_t)(rowb / 16);
+    void* rows = nullptr;
+    float *colA = nullptr, *rn = nullptr, *ex = nullptr;
+    VDB_CUDA(cudaMalloc(&rows, ds->n * rowb));
     VDB_CUDA(cudaMalloc(&colA, ds->n * 4));
     VDB_CUDA(cudaMalloc(&rn, ds->n * 4));
-    gather_round_rows_kernel<<<(uint32_t)ds->n, 128, 0, st>>>(ds->d_tf32, ds->d_sqnorm, ds->d_lo, ivf->d_members, ds->n, ds->pitch,
-                                                             rows, colA, rn);
+    VDB_CUDA(cudaMalloc(&ex, ds->n * 4));
+    gather_op_rows_kernel<<<(uint32_t)ds->n, 128, 0, st>>>((const uint4*)op_rows_of(ds), row_u4, ds->d_sqnorm, ds->d_lo, ds->d_ex,
+                                                          ivf->d_members, ds->n, (uint4*)rows, colA, rn, ex);
     VDB_LAUNCHED();
     ivf->h_samp_off.assign(ivf->nlist + 1, 0);
     for (uint32_t l = 0; l < ivf->nlist; ++l)
         ivf->h_samp_off[l + 1] = ivf->h_samp_off[l] + ceil_div<uint64_t>(h_off[l + 1] - h_off[l], IVF_SAMPLE_RATE);
     ivf->samp_n = ivf->h_samp_off[ivf->nlist];
-    VDB_CUDA(cudaMalloc(&ivf->d_samp_rows, std::max<uint64_t>(ivf->samp_n, 1) * (size_t)ds->pitch * 4));
+    VDB_CUDA(cudaMalloc(&ivf->d_samp_rows, std::max<uint64_t>(ivf->samp_n, 1) * rowb));
     VDB_CUDA(cudaMalloc(&ivf->d_samp_colA, std::max<uint64_t>(ivf->samp_n, 1) * 4));
     VDB_CUDA(cudaMalloc(&ivf->d_samp_rn, std::max<uint64_t>(ivf->samp_n, 1) * 4));
+    VDB_CUDA(cudaMalloc(&ivf->d_samp_ex, std::max<uint64_t>(ivf->samp_n, 1) * 4));
     if (ivf->samp_n) {
         DevBuf soff((size_t)(ivf->nlist + 1) * 8, st);
         VDB_CUDA(cudaMemcpyAsync(soff.p, ivf->h_samp_off.data(), (size_t)(ivf->nlist + 1) * 8, cudaMemcpyHostToDevice, st));
-        ivf_sample_gather_kernel<<<(uint32_t)ivf->samp_n, 128, 0, st>>>(rows, colA, rn, ivf->d_offsets, soff.as<uint64_t>(),
-                                                                       ivf->nlist, ds->pitch, ivf->d_samp_rows,
-                                                                       ivf->d_samp_colA, ivf->d_samp_rn);
+        ivf_sample_gather_kernel<<<(uint32_t)ivf->samp_n, 128, 0, st>>>((const uint4*)rows, row_u4, colA, rn, ex, ivf->d_offsets,
+                                                                       soff.as<uint64_t>(), ivf->nlist, (uint4*)ivf->d_samp_rows,
+                                                                       ivf->d_samp_colA, ivf->d_samp_rn, ivf->d_samp_ex);
         VDB_LAUNCHED();
         VDB_CUDA(cudaStreamSynchronize(st));
     }
     VDB_CUDA(cudaStreamSynchronize(st));
     ivf->d_colA_lo = colA;
     ivf->d_rn_lo = rn;
+    ivf->d_ex_lo = ex;
+    ivf->op_kind = ds->op_kind;
     ivf->d_rows_lo = rows;
 }
 
@@ -1349,26 +1638,19 @@ __global__ void ivf_collect_sample_kernel(const uint64_t* __restrict__ skeys, co
         out[(size_t)q * nprobe * G_TOPJ + e] = g == 0xffffffffu ? KEY_NONE : skeys[(size_t)g * G_TOPJ + e % G_TOPJ];
     }
 }
-// tau = S'_(j0) of the sample + margin; +inf when the probed lists hold fewer than j0 sampled rows
-__global__ void ivf_sample_tau_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j0, const float* __restrict__ qcm,
-                                      float margin, float* __restrict__ tau) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    const uint64_t kk = keys[(size_t)q * j0 + (j0 - 1)];
-    const float s = kk == KEY_NONE ? __uint_as_float(0x7f800000u) : key_dist(kk);
-    tau[q] = s + 2.5f * (qcm ? qcm[q] * margin : margin);
-}
-__global__ void gather_query_side_kernel(const float* __restrict__ qround, uint32_t qpitch, const float* __restrict__ qcm,
+__global__ void gather_query_side_kernel(const uint4* __restrict__ qop, uint32_t row_u4, const float* __restrict__ qd,
+                                         const float* __restrict__ qab, const float* __restrict__ qb,
                                          const float* __restrict__ qnorm, const uint32_t* __restrict__ qmap, uint32_t G,
-                                         float* __restrict__ outq, float* __restrict__ out_qcm, float* __restrict__ out_qnorm) {
+                                         uint4* __restrict__ outq, float* __restrict__ out_qd, float* __restrict__ out_qab,
+                                         float* __restrict__ out_qb, float* __restrict__ out_qnorm) {
     const uint32_t g = blockIdx.x;
     if (g >= G) return;
     const uint32_t q = qmap[g];
-    const float4* src = reinterpret_cast<const float4*>(qround + (size_t)q * qpitch);
-    float4* dst = reinterpret_cast<float4*>(outq + (size_t)g * qpitch);
-    for (uint32_t e = threadIdx.x; e < qpitch / 4; e += blockDim.x) dst[e] = src[e];
+    for (uint32_t e = threadIdx.x; e < row_u4; e += blockDim.x) outq[(size_t)g * row_u4 + e] = qop[(size_t)q * row_u4 + e];
     if (threadIdx.x == 0) {
-        out_qcm[g] = qcm[q];
+        out_qd[g] = qd[q];
+        out_qab[g] = qab[q];
+        out_qb[g] = qb[q];
         if (qnorm) out_qnorm[g] = qnorm[q];
     }
 }
@@ -1445,34 +1727,37 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
     try {
         const bool cosine = ds->metric == VDB_COSINE;
         // ---- gathered query matrix, its per-row scalars, item tables ----
-        DevBuf d_qmap((size_t)G * 4, st), qg((size_t)G * tq->qpitch * 4, st), qcm_g((size_t)G * 4, st), qn_g((size_t)G * 4, st),
-            tau_g((size_t)G * 4, st), tau((size_t)nq * 4, st);
+        const size_t q_rowb = (size_t)tq->op_pitch * (tq->kind == KIND_F16 ? 2 : 4);
+        DevBuf d_qmap((size_t)G * 4, st), qg((size_t)G * q_rowb, st), qd_g((size_t)G * 4, st), qab_g((size_t)G * 4, st),
+            qb_g((size_t)G * 4, st), qn_g((size_t)G * 4, st), tau_g((size_t)G * 4, st), tau((size_t)nq * 4, st);
         VDB_CUDA(cudaMemcpyAsync(d_qmap.p, qmap.data(), (size_t)G * 4, cudaMemcpyHostToDevice, st));
-        gather_query_side_kernel<<<G, 128, 0, st>>>(tq->qround.as<float>(), tq->qpitch, tq->qcm.as<float>(),
+        gather_query_side_kernel<<<G, 128, 0, st>>>((const uint4*)tq->qop.p, (uint32_t)(q_rowb / 16), tq->qd.as<float>(),
+                                                    tq->qab.as<float>(), tq->qb.as<float>(),
                                                     cosine ? tq->qtile.qcache.as<float>() : nullptr, d_qmap.as<uint32_t>(), G,
-                                                    qg.as<float>(), qcm_g.as<float>(), qn_g.as<float>());
+                                                    (uint4*)qg.p, qd_g.as<float>(), qab_g.as<float>(), qb_g.as<float>(), qn_g.as<float>());
         VDB_LAUNCHED();
-        const CUtensorMap mq = make_map(qg.as<float>(), ds->dim, G, (uint64_t)tq->qpitch * 4, GM);
+        const CUtensorMap mq = make_op_map(tq->kind, qg.p, ds->dim, G, q_rowb, GM);
         GemmParams base{};
         base.nq = G;
-        base.kblocks = ceil_div(ds->dim, (uint32_t)GK);
-        base.qcm = qcm_g.as<float>();
+        base.kblocks = kblocks_of(tq->kind, ds->dim);
+        base.qd = qd_g.as<float>();
+        base.qab = qab_g.as<float>();
+        base.qb = qb_g.as<float>();
         base.qnorm = cosine ? qn_g.as<float>() : nullptr;
-        base.kc = tq->kc;
         base.row_stride = 1;
         base.qmap = d_qmap.as<uint32_t>();
         base.nslabs = 1;
-        auto run_items = [&](int mode, const std::vector<GemmItem>* tabs, const float* rows, uint64_t nrows, GemmParams p) {
+        auto run_items = [&](int mode, const std::vector<GemmItem>* tabs, const void* rows, uint64_t nrows, GemmParams p) {
             for (uint32_t pair = 0; pair < 2; ++pair) {
                 if (tabs[pair].empty()) continue;
                 DevBuf d_items(tabs[pair].size() * sizeof(GemmItem), st);
                 VDB_CUDA(cudaMemcpyAsync(d_items.p, tabs[pair].data(), tabs[pair].size() * sizeof(GemmItem),
                                          cudaMemcpyHostToDevice, st));
-                const CUtensorMap mx = make_map(rows, ds->dim, nrows, (uint64_t)ds->pitch * 4, GN / (pair + 1));
+                const CUtensorMap mx = make_op_map(tq->kind, rows, ds->dim, nrows, op_row_bytes_of(ds), GN / (pair + 1));
                 p.nrows = nrows;
                 p.items = d_items.as<GemmItem>();
                 p.nitems = (uint32_t)tabs[pair].size();
-                launch_gemm(mode, ds->metric, mq, mx, p, st, (int)pair + 1);
+                launch_gemm(mode, ds->metric, tq->kind, mq, mx, p, st, (int)pair + 1);
             }
         };
         // ---- thresholds ----
@@ -1487,15 +1772,17 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
             GemmParams ps = base;
             ps.sqnorm = ivf->d_samp_colA;
             ps.rnorm = ivf->d_samp_rn;
+            ps.ex = ivf->d_samp_ex;
             ps.out_keys = skeys.as<uint64_t>();
             run_items(2, sitems, ivf->d_samp_rows, ivf->samp_n, ps);
             ivf_collect_sample_kernel<<<nq, 128, 0, st>>>(skeys.as<uint64_t>(), d_gpos.as<uint32_t>(), nprobe, ckeys.as<uint64_t>());
             VDB_LAUNCHED();
             launch_merge_keys(ckeys.as<uint64_t>(), 1, nq, nprobe * G_TOPJ, false, j0, jkeys.as<uint64_t>(), nullptr, nullptr,
                               nullptr, st);
-            ivf_sample_tau_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0,
-                                                                     cosine ? nullptr : tq->qcm.as<float>(),
-                                                                     cosine ? tq->cbound : ds->mean_norm, tau.as<float>());
+            // +inf when the probed lists hold fewer than j0 sampled rows
+            tau_from_keys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, j0, tq->qab.as<float>(),
+                                                                    tq->qb.as<float>(), ds->mean_norm, ds->mean_ex, cosine ? 1 : 0,
+                                                                    tau.as<float>());
             VDB_LAUNCHED();
         } else {
             // S balances the two exact-distance passes: S subset rows against ~k * visited / S surviving candidates
@@ -1527,6 +1814,7 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
             GemmParams pf = base;
             pf.sqnorm = ivf->d_colA_lo;
             pf.rnorm = ivf->d_rn_lo;
+            pf.ex = ivf->d_ex_lo;
             pf.tau = tau_g.as<float>();
             pf.cand_cnt = tq->cnt.as<uint32_t>();
             pf.cand = cand.as<uint64_t>();
@@ -1583,36 +1871,32 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
     return true;
 }
 
-// debug / test entry: S' keys of every (query, sampled row) pair, [nq][nrows] (mode 0 of the kernel)
-void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
+// debug / test entry: the pruning scores S' of every (query, strided row) pair as keys, [nq][n / row_stride] (mode 0 of
+// the kernel), computed by the very pipeline of the search (operand copies, error norms, coefficients) with the operand
+// kind forced to `kind` (0 = TF32 on the fp32 rows in place, 1 = FP16 copy; < 0: the dataset's own choice)
+void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, int kind,
                      uint64_t* d_out_keys, cudaStream_t st) {
-    VDB_REQUIRE(ds->dtype == VDB_F32 && ds->metric == VDB_L2SQR && ds->dim % 4 == 0 && ((uintptr_t)d_queries & 15) == 0 &&
-                    row_stride >= 1,
-                "flat_gemm_store: f32 L2Sqr rows, dim %% 4 == 0 and aligned queries only");
-    ensure_side_arrays(ds, st);
-    const uint64_t ns = ds->n / row_stride;
-    DevBuf qsq((size_t)nq * 4, st), qcm((size_t)nq * 4, st);
-    vdb_dataset qd = *ds;
-    qd.d_rows = const_cast<void*>(d_queries);
-    qd.n = nq;
-    qd.pitch = ds->dim;
-    qd.metric = VDB_L2SQR;
-    row_cache(&qd, qsq.as<float>(), st);
-    qcm_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(qsq.as<float>(), nq, c, qcm.as<float>());
-    VDB_LAUNCHED();
-    GemmParams p{};
-    p.nq = nq;
-    p.kblocks = ceil_div(ds->dim, (uint32_t)GK);
-    p.sqnorm = ds->d_sqnorm;
-    p.rnorm = ds->d_lo;
-    p.qcm = qcm.as<float>();
-    p.nrows = ns;
-    p.row_stride = row_stride;
-    p.out_keys = d_out_keys;
-    const CUtensorMap mq = make_map(d_queries, ds->dim, nq, (uint64_t)ds->dim * 4, GM);
-    const CUtensorMap ms = make_map(ds->d_rows, ds->dim, ns, ds->pitch_bytes() * row_stride, GN / gemm_ctas());
-    plan_gemm(p);
-    launch_gemm(0, VDB_L2SQR, mq, ms, p, st);
+    VDB_REQUIRE(row_stride >= 1 && ds->n >= row_stride, "flat_gemm_store: bad row stride");
+    ensure_side_arrays(ds, st, kind);
+    vdb_tq* tq = tensor_begin(ds, d_queries, nq, st, true);   // the debug entry also serves sets of < 65536 rows
+    try {
+        const uint64_t ns = ds->n / row_stride;
+        GemmParams p = base_params(tq);
+        p.sqnorm = ds->d_sqnorm;
+        p.rnorm = ds->d_lo;
+        p.ex = ds->d_ex;
+        p.nrows = ns;
+        p.row_stride = row_stride;
+        p.out_keys = d_out_keys;
+        const CUtensorMap ms = make_op_map(tq->kind, op_rows_of(ds), ds->dim, ns, op_row_bytes_of(ds) * row_stride, GN / gemm_ctas());
+        plan_gemm(p);
+        launch_gemm(0, ds->metric, tq->kind, tq->mq, ms, p, st);
+        VDB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        tensor_end(tq);
+        throw;
+    }
+    tensor_end(tq);
 }
 
 }  // namespace vdb

@@ -37,11 +37,14 @@ struct vdb_ivf {
     uint32_t* d_members = nullptr;  // [n] local row ids, ascending inside a list
     uint32_t max_list = 0;
     // lazily built for the tensor-core probe scan: rows / norms permuted into list order (position p <-> members[p])
-    float* d_rows_lo = nullptr;   // [n][pitch] TF32-rounded (u8: exact f32)
+    void* d_rows_lo = nullptr;    // [n][op row bytes] operand rows of the dataset's kind (FP16 copy / fp32 rows)
+    int op_kind = 0;
     float* d_colA_lo = nullptr;   // [n] ||x||^2 (L2Sqr) or 1/||x|| (cosine)
     float* d_rn_lo = nullptr;     // [n] ||x||
+    float* d_ex_lo = nullptr;     // [n] operand error norm
     // stratified 1/16 sample of every list, also in list order (threshold pass of the tensor-core probe scan)
-    float* d_samp_rows = nullptr, *d_samp_colA = nullptr, *d_samp_rn = nullptr;
+    void* d_samp_rows = nullptr;
+    float* d_samp_colA = nullptr, *d_samp_rn = nullptr, *d_samp_ex = nullptr;
     std::vector<uint64_t> h_samp_off;  // [nlist+1]
     uint64_t samp_n = 0;
 };
@@ -155,21 +158,23 @@ void pq_tensor_filter(const vdb_pq* pq, const DevBuf& lut16, const float* d_lut,
                       uint32_t* d_cnt, uint64_t* d_cand, uint32_t cap, cudaStream_t st);
 
 // flat_gemm.cu
-void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, float c,
+void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t row_stride, int kind,
                      uint64_t* d_out_keys, cudaStream_t st);
 extern std::atomic<uint64_t> g_gemm_redo, g_gemm_cands, g_gemm_queries;
 extern std::atomic<uint32_t> g_debug_force_redo;
 uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps = 2e-3);
-vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st);
+vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, bool any_size = false);
+void operand_info(const vdb_dataset* ds, int* kind, float* scale, float* mean_norm, float* mean_ex, uint64_t* side_bytes);
 void tensor_end(vdb_tq* tq);
 void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys);
-void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm, float* d_tau);
+void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm, float mean_ex,
+                float* d_tau);
 void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
                         uint32_t* d_overflow, uint64_t* d_cand_total);
 void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,
                   const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo);
 void tensor_check_range(vdb_tq* tq, uint32_t q0, uint32_t cnt, const uint64_t* d_keys, uint32_t k, uint64_t n_total,
                         const float* d_tau, const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo);
-void tensor_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, cudaStream_t st);
+void tensor_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, float* mean_ex, cudaStream_t st);
 
 }  // namespace vdb

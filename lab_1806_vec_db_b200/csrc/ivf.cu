@@ -407,6 +407,8 @@ void ivf_destroy(vdb_ivf* ivf) {
     cudaFree(ivf->d_samp_rn);
     cudaFree(ivf->d_colA_lo);
     cudaFree(ivf->d_rn_lo);
+    cudaFree(ivf->d_ex_lo);
+    cudaFree(ivf->d_samp_ex);
     delete ivf;
 }
 

@@ -192,7 +192,7 @@ struct vdb_sharded_state {
     // tensor-path facts, gathered on first use
     bool tensor_known = false, tensor_ok = false;
     uint64_t ns_total = 0, ns_min = 0;
-    float mean_norm = 0.f;
+    float mean_norm = 0.f, mean_ex = 0.f;
 };
 
 namespace vdb {
@@ -387,14 +387,14 @@ static void ensure_tensor_facts(const vdb_dataset* md) {
     if (S->tensor_known) return;
     const uint32_t G = (uint32_t)S->shards.size();
     std::vector<uint64_t> ns(G, 0);
-    std::vector<float> mn(G, 0.f);
+    std::vector<float> mn(G, 0.f), me(G, 0.f);
     std::vector<int> ok(G, 0);
     std::vector<std::function<void(uint32_t)>> ph = {[&](uint32_t s) {
         Shard& sh = S->shards[s];
         if (!flat_gemm_supported(sh.ds, 1, 1)) return;
         uint64_t n = 0;
         uint32_t sn = 0;
-        tensor_info(sh.ds, &n, &sn, &mn[s], sh.st);
+        tensor_info(sh.ds, &n, &sn, &mn[s], &me[s], sh.st);
         VDB_CUDA(cudaStreamSynchronize(sh.st));
         ns[s] = sn;
         ok[s] = 1;
@@ -403,12 +403,13 @@ static void ensure_tensor_facts(const vdb_dataset* md) {
     S->tensor_ok = true;
     S->ns_total = 0;
     S->ns_min = ~0ull;
-    S->mean_norm = 0.f;
+    S->mean_norm = S->mean_ex = 0.f;
     for (uint32_t s = 0; s < G; ++s) {
         S->tensor_ok = S->tensor_ok && ok[s];
         S->ns_total += ns[s];
         S->ns_min = std::min<uint64_t>(S->ns_min, ns[s]);
         S->mean_norm = std::max(S->mean_norm, mn[s]);
+        S->mean_ex = std::max(S->mean_ex, me[s]);
     }
     S->tensor_known = true;
 }
@@ -540,7 +541,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
             L.ovf = DevBuf((size_t)nq * 4, sh.st);
             L.ctotal = DevBuf(8, sh.st);
             tensor_tau(tqs[s], (const uint64_t*)sh.jall.p, G, j, (uint32_t)std::min<uint64_t>(j0, (uint64_t)j * G), S->mean_norm,
-                       L.tau.as<float>());
+                       S->mean_ex, L.tau.as<float>());
             tensor_filter_keys(tqs[s], k, 0, L.tau.as<float>(), L.keys.as<uint64_t>(), L.ovf.as<uint32_t>(),
                                L.ctotal.as<uint64_t>());
             VDB_CUDA(cudaMemcpyAsync(sh.h_stat, L.ctotal.p, 8, cudaMemcpyDeviceToHost, sh.st));

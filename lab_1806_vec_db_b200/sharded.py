@@ -65,11 +65,11 @@ class ShardedFlatIndex:
         if self._tensor is None:
             import torch
             lib = L.lib()
-            n, ns, mn = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
+            n, ns, mn, me = C.c_uint64(0), C.c_uint32(0), C.c_float(0), C.c_float(0)
             ok = (self.vec_set.dtype in (np.float32, np.uint8) and
-                  lib.vdb_tq_info(self.vec_set._h, C.byref(n), C.byref(ns), C.byref(mn)) == L.OK)
+                  lib.vdb_tq_info(self.vec_set._h, C.byref(n), C.byref(ns), C.byref(mn), C.byref(me)) == L.OK)
             t = torch.tensor([float(n.value), float(ns.value), 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
-            m = torch.tensor([mn.value], dtype=torch.float32, device=dev)
+            m = torch.tensor([mn.value, me.value], dtype=torch.float32, device=dev)
             if self.world > 1:
                 import torch.distributed as dist
                 okmin = t[2:3].clone()
@@ -77,7 +77,7 @@ class ShardedFlatIndex:
                 dist.all_reduce(okmin, op=dist.ReduceOp.MIN)
                 dist.all_reduce(m, op=dist.ReduceOp.MAX)
                 ok = bool(okmin.item() > 0)
-            self._tensor = (int(t[0].item()), int(t[1].item()), float(m.item())) if ok else False
+            self._tensor = (int(t[0].item()), int(t[1].item()), float(m[0].item()), float(m[1].item())) if ok else False
         return self._tensor
 
     def _gather(self, t):
@@ -108,7 +108,7 @@ class ShardedFlatIndex:
         Returns the state `_tensor_finish` needs (the global [nq, k] keys are complete unless the check flags a query)."""
         import torch
         lib = L.lib()
-        n_total, ns_total, mean_norm = info
+        n_total, ns_total, mean_norm, mean_ex = info
         nq, dev = q.shape[0], q.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         j0 = int(lib.vdb_tq_j0(k, ns_total, n_total))
@@ -133,7 +133,7 @@ class ShardedFlatIndex:
             mark("gather_sample")
             tau = torch.empty((nq,), dtype=torch.float32, device=dev)
             L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(allj.data_ptr()), self.world, j, min(j0, j * self.world),
-                                       mean_norm, C.c_void_p(tau.data_ptr())))
+                                       mean_norm, mean_ex, C.c_void_p(tau.data_ptr())))
             mark("tau")
             keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
             ovf = torch.empty((nq,), dtype=torch.int32, device=dev)

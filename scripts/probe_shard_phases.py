@@ -15,7 +15,8 @@ vs = V.DeviceVecSet.from_device(base.data_ptr(), n, DIM, DIM, np.float32, "l2sqr
 lib = L.lib()
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 nn, ns, mn = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
-L.check(lib.vdb_tq_info(vs._h, C.byref(nn), C.byref(ns), C.byref(mn)))
+me = C.c_float(0)
+L.check(lib.vdb_tq_info(vs._h, C.byref(nn), C.byref(ns), C.byref(mn), C.byref(me)))
 j0 = int(os.environ.get("J0", 0)) or int(lib.vdb_tq_j0(k, ns.value, nn.value)); j = j0  # J0=2 on a 125k shard ~ the global threshold of an 8-way split
 print("n", nn.value, "sample", ns.value, "j0", j0)
 names = ["begin", "sample", "tau", "filter", "check", "decode"]
@@ -27,7 +28,7 @@ def once(record):
     jkeys = torch.empty((nq, j), dtype=torch.int64, device=dev)
     L.check(lib.vdb_tq_sample_dev(tq, j, C.c_void_p(jkeys.data_ptr()))); ev[2].record()
     tau = torch.empty((nq,), dtype=torch.float32, device=dev)
-    L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(jkeys.data_ptr()), 1, j, j0, mn, C.c_void_p(tau.data_ptr()))); ev[3].record()
+    L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(jkeys.data_ptr()), 1, j, j0, mn, me, C.c_void_p(tau.data_ptr()))); ev[3].record()
     keys = torch.empty((nq, k), dtype=torch.int64, device=dev); ovf = torch.empty((nq,), dtype=torch.int32, device=dev)
     L.check(lib.vdb_tq_filter_dev(tq, k, C.c_void_p(tau.data_ptr()), C.c_void_p(keys.data_ptr()), C.c_void_p(ovf.data_ptr()))); ev[4].record()
     redo = torch.empty((nq,), dtype=torch.int32, device=dev); nredo = torch.zeros((1,), dtype=torch.int32, device=dev)

@@ -9,42 +9,83 @@ from conftest import assert_knn_parity
 pytestmark = pytest.mark.gpu
 
 
-def _scores(V, base, q, stride, c):
+def _scores(V, base, q, stride, kind, metric="l2sqr"):
     import torch
     from lab_1806_vec_db_b200 import _lib as L
     from lab_1806_vec_db_b200.sharded import unpack_keys
-    vs = V.DeviceVecSet(base, "l2sqr")
+    vs = V.DeviceVecSet(base, metric)
     dq = torch.from_numpy(q).cuda()
     ns = base.shape[0] // stride
     out = torch.empty((q.shape[0], ns), dtype=torch.int64, device="cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    L.check(L.lib().vdb_debug_gemm_scores_dev(vs._h, C.c_void_p(dq.data_ptr()), q.shape[0], stride, c,
+    L.check(L.lib().vdb_debug_gemm_scores_dev(vs._h, C.c_void_p(dq.data_ptr()), q.shape[0], stride, kind,
                                               C.c_void_p(out.data_ptr()), st))
     torch.cuda.synchronize()
     s, idx = unpack_keys(out.cpu().numpy().astype(np.uint64))
     return s, idx
 
 
+def _operand_errors(x, kind):
+    """||x - x~|| per row for the operand the tensor core consumes (numpy model of csrc/flat_gemm.cu::row_side_kernel):
+    kind 1: x~ = fp16(x * s) / s with one power-of-two scale for the whole array; kind 0: fp32 bits truncated to TF32."""
+    x = np.asarray(x, np.float32)
+    if kind == 1:
+        m = float(np.abs(x).max())
+        s = np.float32(2.0 ** (14 - np.frexp(m)[1])) if m > 0 else np.float32(1)
+        back = (x * s).astype(np.float16).astype(np.float32) / s
+    else:
+        back = (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    return np.sqrt(((x.astype(np.float64) - back.astype(np.float64)) ** 2).sum(1))
+
+
+@pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("n,dim,nq,stride", [(1024, 960, 128, 1), (5000, 960, 300, 1), (5000, 960, 130, 3),
                                              (777, 100, 5, 1), (4096, 32, 256, 2), (3000, 2052, 64, 1)])
-def test_contraction_scores_match_numpy(n, dim, nq, stride):
+def test_pruning_scores_are_tight_lower_bounds(n, dim, nq, stride, kind):
+    """The invariant the exactness of the tensor path rests on: for EVERY (query, row) pair the pruning score S' is a
+    lower bound of d(q, x) - ||q||^2, and it is no further below it than twice the rigorous bound
+    b = 2 (||q|| ex + eq ||x|| + dim 2^-23 ||q|| ||x||) built from the measured operand errors ex, eq."""
     import lab_1806_vec_db_b200 as V
     rng = np.random.default_rng(n + dim)
     base = rng.random((n, dim), dtype=np.float32)
-    q = rng.random((nq, dim), dtype=np.float32)
-    for c in (0.0, 4.1e-3):
-        s, idx = _scores(V, base, q, stride, c)
-        rows = base[::stride][: n // stride].astype(np.float64)
-        qq = q.astype(np.float64)
-        xn2 = (rows * rows).sum(1)
-        want = xn2[None, :] - 2.0 * qq @ rows.T - c * np.sqrt((qq * qq).sum(1))[:, None] * np.sqrt(xn2)[None, :]
-        assert (idx == np.arange(n // stride)[None, :]).all()
-        # TF32 operand rounding: |error| <= 2 * 2^-9 * ||q|| ||x|| (+ fp32 accumulation)
-        bound = 4.2e-3 * np.sqrt((qq * qq).sum(1))[:, None] * np.sqrt(xn2)[None, :] + 1e-4
-        err = np.abs(s.astype(np.float64) - want)
-        assert (err <= bound).all(), float((err / bound).max())
-        # and the scores are genuinely tensor-core results, not the exact fp32 values
-        assert err.max() > 0
+    base[::7] *= np.float32(1e-3)                      # rows of very different magnitude share one FP16 scale
+    q = rng.random((nq, dim), dtype=np.float32) * np.float32(3.0)
+    s, idx = _scores(V, base, q, stride, kind)
+    rows = base[::stride][: n // stride]
+    assert (idx == np.arange(n // stride)[None, :]).all()
+    r64, q64 = rows.astype(np.float64), q.astype(np.float64)
+    xn, qn = np.sqrt((r64 * r64).sum(1)), np.sqrt((q64 * q64).sum(1))
+    exact = (xn * xn)[None, :] - 2.0 * q64 @ r64.T
+    ex = _operand_errors(base, kind)[::stride][: n // stride]
+    if kind == 1:   # queries carry their own power-of-two scale
+        eq = np.array([_operand_errors(q[i:i + 1], 1)[0] for i in range(nq)])
+    else:           # queries are rounded to nearest TF32: at most half the truncation error per element
+        eq = _operand_errors(q, 0)
+    b = 2.0 * (qn[:, None] * ex[None, :] + eq[:, None] * xn[None, :] + dim * 2.0 ** -23 * qn[:, None] * xn[None, :])
+    gap = exact - s.astype(np.float64)
+    fp32_noise = 4e-6 * ((xn * xn)[None, :] + qn[:, None] * xn[None, :])
+    assert (gap >= -fp32_noise).all(), float((gap / fp32_noise).min())          # lower bound
+    assert (gap <= 2.0 * 1.01 * b + fp32_noise).all(), float((gap / (2 * b + fp32_noise)).max())   # and a tight one
+    # the scores are genuinely tensor-core results of rounded operands, not exact fp32 values minus the bound
+    assert np.abs(gap - b).max() > 0
+
+
+def test_cosine_pruning_scores_are_lower_bounds():
+    import lab_1806_vec_db_b200 as V
+    rng = np.random.default_rng(5)
+    base = rng.random((3000, 480), dtype=np.float32)
+    base[17] = 0.0                                       # a zero row sits under the reference's 1e-10 clamp: always kept
+    q = rng.random((200, 480), dtype=np.float32)
+    for kind in (0, 1):
+        s, _ = _scores(V, base, q, 1, kind, "cosine")
+        r64, q64 = base.astype(np.float64), q.astype(np.float64)
+        xn, qn = np.sqrt((r64 * r64).sum(1)), np.sqrt((q64 * q64).sum(1))
+        exact = 1.0 - (q64 @ r64.T) / np.maximum(qn[:, None] * xn[None, :], 1e-10)
+        assert np.isneginf(s[:, 17]).all()
+        keep = np.arange(3000) != 17
+        gap = exact[:, keep] - s[:, keep].astype(np.float64)
+        assert (gap >= -2e-6).all(), float(gap.min())
+        assert (gap <= 4.5e-3).all(), float(gap.max())
 
 
 def _synthetic(n, nq, seed=0):
@@ -57,10 +98,13 @@ def _synthetic(n, nq, seed=0):
 
 @pytest.mark.parametrize("k", [10, 100])
 @pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
-def test_tensor_path_identical_to_exact_scan(oracle, k, metric):
-    """The tensor cores only prune: ids and distances must equal the exact scan's (and the oracle's)."""
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+def test_tensor_path_identical_to_exact_scan(oracle, k, metric, kind, monkeypatch):
+    """The tensor cores only prune: ids and distances must equal the exact scan's (and the oracle's), whichever
+    operand kind feeds the contraction (FP16 copy, or the fp32 rows truncated to TF32 in place)."""
     import lab_1806_vec_db_b200 as V
     from lab_1806_vec_db_b200 import _lib as L
+    monkeypatch.setenv("VDB_GEMM_KIND", kind)
     n, nq = 140_000, 300
     base, q = _synthetic(n, nq)
     idx = V.FlatIndex.from_vec_set(base, metric)
@@ -218,3 +262,49 @@ def test_tensor_path_large_query_batch_is_chunked():
     finally:
         L.check(lib.vdb_flat_set_path(0))
     assert (auto[0][sel] == scan[0]).all() and (auto[1][sel].view(np.uint32) == scan[1].view(np.uint32)).all()
+
+
+def test_nonfinite_rows_and_queries_take_the_exact_route(oracle):
+    """Rows with inf / NaN components are always kept as candidates (the exact rerank gives them their inf / NaN
+    distance, which sorts last), a NaN query is answered by the exact scan: identical to the forced scan."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    base, q = _synthetic(70_000, 40, seed=11)
+    base[5, 7] = np.inf
+    base[6, 0] = np.nan
+    q[3, 100] = np.nan
+    idx = V.FlatIndex.from_vec_set(base, "l2sqr")
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, 10)
+        L.check(lib.vdb_flat_set_path(2))
+        tens = idx.knn_batch(q, 10)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    assert np.isnan(tens[1][3]).all() and not np.isnan(np.delete(tens[1], 3, 0)).any()
+
+
+def test_rows_of_wildly_different_magnitude_fall_back_to_tf32_operands():
+    """Cosine over rows whose magnitudes span 12 decades: one FP16 scale for the set flushes the small rows, the
+    measured operand-error norm shows it and the TF32 kind (fp32 rows in place) is selected; results still equal the scan."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(12)
+    base = rng.standard_normal((70_000, 64)).astype(np.float32) * (10.0 ** rng.uniform(-6, 6, (70_000, 1))).astype(np.float32)
+    q = rng.standard_normal((64, 64)).astype(np.float32)
+    q[:32] = base[rng.integers(0, 70_000, 32)] * np.float32(1.5) + np.float32(0.01) * q[:32]
+    idx = V.FlatIndex.from_vec_set(base, "cosine")
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, 10)
+        L.check(lib.vdb_flat_set_path(2))
+        fb0 = lib.vdb_flat_gemm_fallbacks()
+        tens = idx.knn_batch(q, 10)
+        fallbacks = lib.vdb_flat_gemm_fallbacks() - fb0
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
+    assert fallbacks < 32
