@@ -175,6 +175,20 @@ def measure_tf32_peak(dev, seconds=1.5):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
+def tensor_peak(dev, peaks, f16):
+    """Roofline denominator of the contraction. FP16 operands: the driver-written dense bf16 figure of
+    MEASURED_PEAKS.json (fp16 and bf16 share the tensor rate), sustained - the kernel is timed inside a long step.
+    TF32 operands: MEASURED_PEAKS.json has no TF32 figure, so cuBLAS TF32 8192^3 is measured here, next to the kernel."""
+    if f16 and peaks.get("bf16_tflops_sustained"):
+        return (peaks["bf16_tflops_sustained"],
+                "MEASURED_PEAKS.json bf16_tflops_sustained (driver-written; burst %.1f)" % (peaks.get("bf16_tflops") or 0.0))
+    if f16:
+        return 1403.0, "fallback: B200_PROFILING.md sustained dense bf16 figure (MEASURED_PEAKS.json absent)"
+    burst, sustained = measure_tf32_peak(dev)
+    return sustained, ("cuBLAS TF32 8192^3 measured in this run, sustained (burst %.1f); nominal dense TF32 is 1100; "
+                       "MEASURED_PEAKS.json has bf16 only (%.1f sustained)" % (burst, peaks.get("bf16_tflops_sustained") or 0.0))
+
+
 def tensor_stats(lib, ds_handle=None):
     q, c, f = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
     lib.vdb_flat_gemm_stats(C.byref(q), C.byref(c), C.byref(f))
@@ -478,11 +492,16 @@ def run_ours_multi(args):
                 "algorithmic_bytes_per_launch": per_launch, "scope": "per GPU"}
     else:
         flops = 2.0 * args.nq * n_local * DIM * args.steps * world     # all launches of all GPUs
-        burst, sustained = measure_tf32_peak(dev)
+        kind = C.c_int(-1)
+        sh0 = C.c_void_p()
+        L.check(lib.vdb_dataset_shard(vs._h, 0, C.byref(sh0), None, None, None))
+        lib.vdb_dataset_operand_info(sh0, C.byref(kind), None, None, None, None)
+        f16 = kind.value == 1
+        peak, peak_src = tensor_peak(dev, peaks, f16)
         achieved = flops / (t_dom * 1e-3) / 1e12 if t_dom > 0 else 0.0  # t_dom sums the launches of all GPUs
-        roof = {"bound": "tensor", "kernel": "flat_gemm_kernel", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": achieved / sustained, "traffic": None, "scope": "per GPU (launch times summed over the GPUs)",
-                "peak_source": "cuBLAS TF32 8192^3 measured in this run on GPU 0, sustained (burst %.1f)" % burst,
+        roof = {"bound": "tensor", "kernel": "flat_gemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "scope": "per GPU (launch times summed over the GPUs)",
+                "operand_kind": "f16 x f16 -> f32" if f16 else "tf32 x tf32 -> f32", "peak_source": peak_src,
                 "launches": c_dom, "avg_launch_ms": t_dom / max(c_dom, 1), "flop_per_step_per_gpu": 2.0 * args.nq * n_local * DIM}
     roof["kernel_share_of_step"] = t_dom / world / (ms * args.steps) if ms > 0 else None
 
@@ -682,19 +701,19 @@ def run_ours(args):
     else:
         # dense contraction: 2*nq*n*dim FLOP per step (the sample pass adds ns/n ~ 3 % more, not counted), DESIGN.md K2
         flops = 2.0 * args.nq * n_local * DIM * args.steps
-        burst, sustained = measure_tf32_peak(dev)
+        tstats = tensor_stats(lib, vs._h) or {}
+        f16 = "fp16" in (tstats.get("operand") or {}).get("kind", "")
+        peak, peak_src = tensor_peak(dev, peaks, f16)
         achieved = flops / (t_dom * 1e-3) / 1e12 if t_dom > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "flat_gemm_kernel", "achieved": achieved, "peak": sustained,
-                "unit": "TFLOP/s", "frac": achieved / sustained,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one filter launch (a third of the rows) from the
-                # committed ncu capture (profiles/r01_flat_gemm_ncu.md; algorithmic: 1.28 GB rows + 38 MB queries)
-                "traffic": (GEMM_PART_TRAFFIC if (n_local == 1_000_000 and args.nq == 10_000) else None),
-                "traffic_source": "ncu --set full capture, profiles/r01_flat_gemm_ncu.md (bytes per filter launch = "
+        roof = {"bound": "tensor", "kernel": "flat_gemm_kernel", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak,
+                "operand_kind": "f16 x f16 -> f32 (tcgen05.mma.kind::f16)" if f16 else "tf32 x tf32 -> f32 (tcgen05.mma.kind::tf32)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one filter launch from the committed ncu capture
+                "traffic": (GEMM_PART_TRAFFIC if (n_local == 1_000_000 and args.nq == 10_000 and f16) else None),
+                "traffic_source": "ncu --set full capture, profiles/r02_flat_gemm_ncu.md (bytes per filter launch = "
                                   "one of the 3 row parts of a step)",
-                "algorithmic_bytes_per_launch": n_local * DIM * 4 / 3 + args.nq * DIM * 4,
-                "peak_source": "cuBLAS TF32 8192^3 measured in this run, sustained (burst %.1f); nominal dense TF32 "
-                               "is 1100; MEASURED_PEAKS.json has bf16 only (%.1f sustained)"
-                               % (burst, peaks.get("bf16_tflops_sustained") or 0.0),
+                "algorithmic_bytes_per_launch": n_local * DIM * (2 if f16 else 4) / 3 + args.nq * DIM * (2 if f16 else 4),
+                "peak_source": peak_src,
                 "launches": c_dom, "avg_launch_ms": t_dom / max(c_dom, 1),
                 "flop_per_step": flops / args.steps}
     roof["kernel_share_of_step"] = t_dom / (ms * args.steps) if ms > 0 else None

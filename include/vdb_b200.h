@@ -229,13 +229,16 @@ int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* m
 /* Smallest sample order statistic whose rank among n_total rows is >= k with probability > 1 - 2e-3. */
 uint32_t vdb_tq_j0(uint32_t k, uint64_t sample_total, uint64_t n_total);
 int vdb_tq_begin_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, void* stream, vdb_tq** out);
-/* this shard's j smallest sampled pruning scores per query: d_keys [nq, j] ascending */
+/* number of sampled rows to re-evaluate per query for the order statistic j0 (a few more than j0; at most sample_min,
+ * the smallest shard's sample size) */
+uint32_t vdb_tq_sample_j(uint32_t j0, uint64_t sample_min);
+/* the j best sampled rows of every query by pruning score, re-evaluated exactly: d_keys [nq, j] = (exact distance,
+ * global id) keys, ascending, KEY_NONE padded */
 int vdb_tq_sample_dev(vdb_tq* tq, uint32_t j, uint64_t* d_keys);
-/* merges nlists shards' sample keys ([nlists, nq, j]) and writes tau[q] = score_(j0) + margin(mean_norm, mean_ex); the
- * two means must be the same on every shard (e.g. the maximum over the shards) so that all shards filter against
- * identical thresholds */
-int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0,
-                   float mean_norm, float mean_ex, float* d_tau);
+/* merges nlists shards' sample keys ([nlists, nq, j]) and writes tau[q] = (j0-th smallest exact sample distance) -
+ * ||q||^2 (cosine: the distance itself): every row of the true top-k has a pruning score below it whenever the j0-th
+ * sampled distance is not better than the k-th best of the set (vdb_tq_j0), which vdb_tq_check_dev verifies per query */
+int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0, float* d_tau);
 /* filter pass + exact rerank: this shard's k best keys per query ([nq, k], KEY_NONE padded) and per-query
  * overflow flags (candidate list overflowed: the result for that query is not provably complete) */
 int vdb_tq_filter_dev(vdb_tq* tq, uint32_t k, const float* d_tau, uint64_t* d_keys, uint32_t* d_overflow);

@@ -91,7 +91,8 @@ SIGNATURES = {
     "vdb_tq_j0": (u32, [u32, u64, u64]),
     "vdb_tq_begin_dev": (i32, [vp, vp, u32, vp, vp]),
     "vdb_tq_sample_dev": (i32, [vp, u32, vp]),
-    "vdb_tq_tau_dev": (i32, [vp, vp, u32, u32, u32, f32, f32, vp]),
+    "vdb_tq_tau_dev": (i32, [vp, vp, u32, u32, u32, vp]),
+    "vdb_tq_sample_j": (u32, [u32, u64]),
     "vdb_tq_filter_dev": (i32, [vp, u32, vp, vp, vp]),
     "vdb_tq_check_dev": (i32, [vp, vp, u32, u64, vp, vp, vp, vp]),
     "vdb_tq_end": (i32, [vp]),

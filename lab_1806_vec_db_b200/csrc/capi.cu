@@ -499,11 +499,11 @@ int vdb_tq_sample_dev(vdb_tq* tq, uint32_t j, uint64_t* d_keys) {
         vdb::tensor_sample_keys(tq, j, d_keys);
     });
 }
-int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm,
-                   float mean_ex, float* d_tau) {
+uint32_t vdb_tq_sample_j(uint32_t j0, uint64_t sample_min) { return vdb::tensor_sample_j(j0, sample_min); }
+int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, uint32_t j, uint32_t j0, float* d_tau) {
     return guarded([&] {
         VDB_REQUIRE(tq && d_keys_lists && d_tau && nlists > 0, "NULL argument");
-        vdb::tensor_tau(tq, d_keys_lists, nlists, j, j0, mean_norm, mean_ex, d_tau);
+        vdb::tensor_tau(tq, d_keys_lists, nlists, j, j0, d_tau);
     });
 }
 int vdb_tq_filter_dev(vdb_tq* tq, uint32_t k, const float* d_tau, uint64_t* d_keys, uint32_t* d_overflow) {

@@ -25,6 +25,7 @@ struct vdb_dataset {
     float op_scale = 1.0f;
     void* d_sample = nullptr;  // stratified random sample of the operand rows, [sample_n][op row bytes]
     float* d_sample_sq = nullptr, *d_sample_rn = nullptr, *d_sample_ex = nullptr;  // the sampled rows' scalars
+    uint32_t* d_sample_row = nullptr;  // and the local row each of them was taken from
     uint32_t sample_n = 0;
     uint64_t side_n = 0;      // number of rows the side arrays cover
     float mean_norm = 0.f;    // mean ||x|| over a row sample (threshold margin of the tensor path)

@@ -305,10 +305,11 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const float qn = (METRIC == VDB_COSINE && qok) ? p.qnorm[q] : 0.f;
             float tau = 0.f;
             if (MODE == 1) tau = qok ? p.tau[q] : __uint_as_float(0xff800000u);  // -inf: nothing passes
-            float best[MODE == 2 ? G_TOPJ : 1];  // mode 2: this query's smallest scores of the slab, ascending
+            float best[MODE == 2 ? G_TOPJ : 1];     // mode 2: this query's smallest scores of the slab, ascending,
+            uint32_t bidx[MODE == 2 ? G_TOPJ : 1];  // and the rows (of the B tensor) they belong to
             if (MODE == 2) {
 #pragma unroll
-                for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) best[i] = __uint_as_float(0x7f800000u);
+                for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) best[i] = __uint_as_float(0x7f800000u), bidx[i] = 0xffffffffu;
             }
             for (uint32_t t = 0; t < iv.ntile; ++t) {
                 // stage the row-scalar tiles of this N-tile (3 x GN floats) while the MMAs run
@@ -385,13 +386,15 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                             for (int j = 0; j < 32; ++j) {
                                 const float sc = __uint_as_float(v[j]);
                                 if (MODE == 2) {
-                                    if (sc < best[MODE == 2 ? G_TOPJ - 1 : 0]) {  // bubble sc into place
+                                    if (sc < best[MODE == 2 ? G_TOPJ - 1 : 0]) {  // bubble (sc, row) into place
                                         float w = sc;
+                                        uint32_t wi = (uint32_t)(tile_row0 + c0 + j);
 #pragma unroll
                                         for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) {
-                                            const float lo = fminf(best[i], w);
-                                            w = fmaxf(best[i], w);
-                                            best[i] = lo;
+                                            const bool lt = w < best[i];
+                                            const float lo = lt ? w : best[i], hi = lt ? best[i] : w;
+                                            const uint32_t loi = lt ? wi : bidx[i], hii = lt ? bidx[i] : wi;
+                                            best[i] = lo, bidx[i] = loi, w = hi, wi = hii;
                                         }
                                     }
                                 } else if (!(sc >= tau)) {   // NaN scores (non-finite rows / queries) are kept: the exact rerank decides
@@ -416,7 +419,8 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (MODE == 2 && qok) {
 #pragma unroll
                 for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i)
-                    p.out_keys[((uint64_t)q * p.nslabs + slab) * G_TOPJ + i] = make_key(best[i], slab * G_TOPJ + i);
+                    p.out_keys[((uint64_t)q * p.nslabs + slab) * G_TOPJ + i] =
+                        bidx[i] == 0xffffffffu ? KEY_NONE : make_key(best[i], bidx[i]);
             }
         }
     }
@@ -538,7 +542,7 @@ static float f16_scale_for(float m) {
 __global__ void gather_sample_kernel(const uint4* __restrict__ op_rows, uint32_t row_u4, const float* __restrict__ colA,
                                      const float* __restrict__ rnorm, const float* __restrict__ ex, uint64_t n, uint32_t ns,
                                      uint4* __restrict__ out, float* __restrict__ out_sq, float* __restrict__ out_rn,
-                                     float* __restrict__ out_ex) {
+                                     float* __restrict__ out_ex, uint32_t* __restrict__ out_row) {
     const uint32_t i = blockIdx.x;
     if (i >= ns) return;
     const uint64_t lo = (uint64_t)i * n / ns, hi = (uint64_t)(i + 1) * n / ns;
@@ -552,15 +556,17 @@ __global__ void gather_sample_kernel(const uint4* __restrict__ op_rows, uint32_t
         out_sq[i] = colA[row];
         out_rn[i] = rnorm[row];
         out_ex[i] = ex[row];
+        out_row[i] = (uint32_t)row;
     }
 }
 
 void drop_side_arrays(vdb_dataset* ds) {
     for (void* p : {(void*)ds->d_lo, (void*)ds->d_sqnorm, (void*)ds->d_ex, ds->d_op, ds->d_sample, (void*)ds->d_sample_sq,
-                    (void*)ds->d_sample_rn, (void*)ds->d_sample_ex})
+                    (void*)ds->d_sample_rn, (void*)ds->d_sample_ex, (void*)ds->d_sample_row})
         if (p) cudaFree(p);
     ds->d_lo = ds->d_sqnorm = ds->d_ex = ds->d_sample_sq = ds->d_sample_rn = ds->d_sample_ex = nullptr;
     ds->d_op = ds->d_sample = nullptr;
+    ds->d_sample_row = nullptr;
     ds->sample_n = 0;
     ds->side_n = 0;
 }
@@ -660,9 +666,10 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st, int kind
     VDB_CUDA(cudaMalloc(&ds->d_sample_sq, (size_t)ds->sample_n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_sample_rn, (size_t)ds->sample_n * 4));
     VDB_CUDA(cudaMalloc(&ds->d_sample_ex, (size_t)ds->sample_n * 4));
+    VDB_CUDA(cudaMalloc(&ds->d_sample_row, (size_t)ds->sample_n * 4));
     gather_sample_kernel<<<ds->sample_n, 128, 0, st>>>((const uint4*)(ds->op_kind == KIND_F16 ? ds->d_op : ds->d_rows),
                                                        (uint32_t)(op_row_bytes / 16), ds->d_sqnorm, ds->d_lo, ds->d_ex, n, ds->sample_n,
-                                                       (uint4*)ds->d_sample, ds->d_sample_sq, ds->d_sample_rn, ds->d_sample_ex);
+                                                       (uint4*)ds->d_sample, ds->d_sample_sq, ds->d_sample_rn, ds->d_sample_ex, ds->d_sample_row);
     VDB_LAUNCHED();
     VDB_CUDA(cudaStreamSynchronize(st));
     ds->side_n = n;
@@ -847,9 +854,9 @@ __global__ void tq_coeff_kernel(const float* __restrict__ qsq, const float* __re
         qab[q] = ((1.0f + eqr) * (1.0f + acc) + eqr) * 1.0001f;
     }
 }
-// tau_q = (j0-th smallest sampled S') + margin. j0 is chosen so that the k-th best S' of the shard is <= S'_(j0)
-// with high probability; because S <= S' + 2 b(q, x), the margin (2.5 x the pruning bound at the mean row error / mean
-// row norm) keeps the k-th EXACT distance inside the threshold. The check kernel verifies it per query afterwards.
+// IVF probe scan: tau_q = (j0-th smallest sampled S') + margin. j0 is chosen so that the k-th best S' of the probed rows
+// is <= S'_(j0) with high probability; because S <= S' + 2 b(q, x), the margin (3 x the pruning bound at the mean row
+// error / mean row norm) keeps the k-th EXACT distance inside the threshold. The check kernel verifies it per query.
 __global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, uint32_t j0,
                                      const float* __restrict__ qab, const float* __restrict__ qb, float mean_norm, float mean_ex,
                                      int cosine, float* __restrict__ tau) {
@@ -859,6 +866,35 @@ __global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t
     const float s = kk == KEY_NONE ? __uint_as_float(0x7f800000u) : key_dist(kk);
     const float b = cosine ? (1.0f - qb[q]) + qab[q] * mean_ex : qab[q] * mean_ex + qb[q] * mean_norm;
     tau[q] = s + 3.0f * b;
+}
+// Flat: the sample keys carry EXACT distances (the j best sampled rows by pruning score are re-evaluated in fp32), so
+// tau_q = d_(j0) - ||q||^2 (cosine: d_(j0)) needs no margin: every row x of the true top-k has S'(x) <= d(x) - ||q||^2
+// <= d_k - ||q||^2 <= d_(j0) - ||q||^2 whenever the j0-th sampled distance is not better than the k-th best of the set
+// (probability > 1 - 2e-3 by the choice of j0, verified per query by the check kernel). The slack keeps the check's
+// strict comparison satisfiable when the j0-th sampled row IS the k-th best.
+__global__ void tau_exact_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, uint32_t j0,
+                                 const float* __restrict__ qsq, float* __restrict__ tau) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint64_t kk = keys[(size_t)q * j + (j0 - 1)];
+    if (kk == KEY_NONE) {
+        tau[q] = __uint_as_float(0x7f800000u);   // fewer than j0 sampled rows: keep everything
+        return;
+    }
+    const float d = key_dist(kk), shift = qsq ? qsq[q] : 0.f;
+    tau[q] = (d - shift) + 1e-4f * (fabsf(d) + shift) + 1e-30f;
+}
+// (query, source row) pairs of the j best sampled rows of every query; KEY_NONE entries are masked out
+__global__ void sample_pairs_kernel(const uint64_t* __restrict__ keys, uint64_t count, uint32_t j,
+                                    const uint32_t* __restrict__ sample_row, uint32_t* __restrict__ qidx,
+                                    uint32_t* __restrict__ rid, uint8_t* __restrict__ valid) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t kk = keys[i];
+        const bool ok = kk != KEY_NONE;
+        qidx[i] = (uint32_t)(i / j);
+        rid[i] = ok ? sample_row[key_id(kk)] : 0u;
+        valid[i] = ok;
+    }
 }
 // exclusive scan of min(cnt, cap) over the queries (one block; nq is at most a few 100k)
 __global__ void __launch_bounds__(1024) cand_offsets_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
@@ -1147,7 +1183,8 @@ static GemmParams base_params(const vdb_tq* tq) {
     return p;
 }
 
-// SAMPLE: this shard's j smallest sampled S' keys per query, [nq][j] ascending
+// SAMPLE: the j best sampled rows of every query by pruning score, re-evaluated exactly: d_jkeys [nq][j] = keys
+// (exact distance, global row id), ascending, KEY_NONE padded
 void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     const vdb_dataset* ds = tq->ds;
     cudaStream_t st = tq->st;
@@ -1161,40 +1198,55 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     ps.rnorm = ds->d_sample_rn;
     ps.ex = ds->d_sample_ex;
     plan_gemm(ps, tq->ctas);
+    const uint64_t cnt = (uint64_t)tq->nq * j;
+    DevBuf skeys(cnt * 8, st);
     if (j <= (uint32_t)G_TOPJ) {
         // the epilogue keeps each query's G_TOPJ smallest scores per slab in registers: nothing but
         // nq * nslabs * G_TOPJ keys ever reaches HBM
         DevBuf part((size_t)tq->nq * ps.nslabs * G_TOPJ * 8, st);
         ps.out_keys = part.as<uint64_t>();
         launch_gemm(2, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas);
-        launch_merge_keys(part.as<uint64_t>(), ps.nslabs, tq->nq, G_TOPJ, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
+        launch_merge_keys(part.as<uint64_t>(), ps.nslabs, tq->nq, G_TOPJ, false, j, skeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
     } else {
-        DevBuf skeys((size_t)tq->nq * ns * 8, st);
-        ps.out_keys = skeys.as<uint64_t>();
+        DevBuf all((size_t)tq->nq * ns * 8, st);
+        ps.out_keys = all.as<uint64_t>();
         launch_gemm(0, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas);
-        launch_merge_keys(skeys.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
+        launch_merge_keys(all.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, skeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
     }
+    // exact fp32 distances of those rows (the rerank's arithmetic), sorted ascending per query
+    DevBuf qidx(cnt * 4, st), rid(cnt * 4, st), valid(cnt, st), dist(cnt * 4, st), ekeys(cnt * 8, st);
+    sample_pairs_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(cnt, 256), 65535), 256, 0, st>>>(
+        skeys.as<uint64_t>(), cnt, j, ds->d_sample_row, qidx.as<uint32_t>(), rid.as<uint32_t>(), valid.as<uint8_t>());
+    VDB_LAUNCHED();
+    exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), valid.as<uint8_t>(), cnt,
+                                dist.as<float>(), st, nullptr, ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr);
+    rekey_based(dist.as<float>(), rid.as<uint32_t>(), (uint32_t)ds->id_base, valid.as<uint8_t>(), cnt, ekeys.as<uint64_t>(), st);
+    launch_merge_keys(ekeys.as<uint64_t>(), 1, tq->nq, j, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
 }
 
-// TAU: merge `nlists` shards' [nq][j] sample keys (list-major) and set tau_q = S'_(j0) + margin; mean_norm / mean_ex are
-// the set-wide means (identical on every shard, so every shard derives the same thresholds)
-void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm, float mean_ex,
-                float* d_tau) {
+// TAU: merge `nlists` shards' [nq][j] exact sample keys (list-major) and set tau_q from the j0-th smallest
+void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float* d_tau) {
     cudaStream_t st = tq->st;
     VDB_REQUIRE(j0 >= 1 && j0 <= (uint64_t)j * nlists, "j0 out of range");
     const uint32_t jj = std::min<uint64_t>(j0, (uint64_t)j * nlists);
-    const int cosine = tq->ds->metric == VDB_COSINE;
+    const float* qsq = tq->ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>();
     if (nlists == 1) {   // a single ascending [nq][j] list: its jj-th entry is the order statistic, nothing to merge
-        tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(d_lists, tq->nq, j, jj, tq->qab.as<float>(), tq->qb.as<float>(),
-                                                                      mean_norm, mean_ex, cosine, d_tau);
+        tau_exact_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(d_lists, tq->nq, j, jj, qsq, d_tau);
         VDB_LAUNCHED();
         return;
     }
     DevBuf merged((size_t)tq->nq * jj * 8, st);
     launch_merge_sorted(d_lists, nlists, tq->nq, j, jj, merged.as<uint64_t>(), nullptr, nullptr, nullptr, st);  // per-shard lists are ascending
-    tau_from_keys_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj, tq->qab.as<float>(),
-                                                                  tq->qb.as<float>(), mean_norm, mean_ex, cosine, d_tau);
+    tau_exact_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(merged.as<uint64_t>(), tq->nq, jj, jj, qsq, d_tau);
     VDB_LAUNCHED();
+}
+
+// number of sampled rows re-evaluated per query for the order statistic j0: a few more than j0 when they come for free
+// (the epilogue keeps G_TOPJ per slab anyway), because the j0-th smallest EXACT distance need not be among the j0
+// smallest pruning scores
+uint32_t tensor_sample_j(uint32_t j0, uint64_t sample_n) {
+    const uint32_t j = j0 <= (uint32_t)G_TOPJ ? std::min<uint32_t>(G_TOPJ, j0 + 4) : j0 + j0 / 4;
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(j, sample_n));
 }
 
 // side stream of the filter pass (per host thread and device): reranks row part i under the contraction of part i + 1
@@ -1294,7 +1346,10 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
             acc_w += w;
             part_end[i] = i + 1 == parts ? total_slabs : std::max<uint32_t>(i + 1, (uint32_t)std::llround(total_slabs * acc_w / total_w));
         }
-        for (uint32_t i = 0; i + 1 < parts; ++i) part_end[i] = std::min(part_end[i], total_slabs - (parts - 1 - i));
+        for (uint32_t i = 0; i + 1 < parts; ++i) {   // every part gets at least one slab
+            if (i) part_end[i] = std::max(part_end[i], part_end[i - 1] + 1);
+            part_end[i] = std::min(part_end[i], total_slabs - (parts - 1 - i));
+        }
     }
     static thread_local SideStream side;
     if (parts > 1) side.ensure(ds->device);
@@ -1386,13 +1441,13 @@ static void chunk_enqueue(const vdb_dataset* ds, const void* d_queries, uint32_t
     cs.d_keys = d_keys;
     cs.nq = nq;
     cs.tq = tensor_begin(ds, d_queries, nq, st);
-    const uint32_t j0 = tensor_j0(k, ds->sample_n, ds->n);
-    DevBuf jkeys((size_t)nq * j0 * 8, st), tau((size_t)nq * 4, st), overflow((size_t)nq * 4, st);
+    const uint32_t j0 = tensor_j0(k, ds->sample_n, ds->n), j = tensor_sample_j(j0, ds->sample_n);
+    DevBuf jkeys((size_t)nq * j * 8, st), tau((size_t)nq * 4, st), overflow((size_t)nq * 4, st);
     cs.redo = DevBuf((size_t)nq * 4, st);
     cs.nredo = DevBuf(4, st);
     cs.ctotal = DevBuf(8, st);
-    tensor_sample_keys(cs.tq, j0, jkeys.as<uint64_t>());
-    tensor_tau(cs.tq, jkeys.as<uint64_t>(), 1, j0, j0, ds->mean_norm, ds->mean_ex, tau.as<float>());
+    tensor_sample_keys(cs.tq, j, jkeys.as<uint64_t>());
+    tensor_tau(cs.tq, jkeys.as<uint64_t>(), 1, j, std::min(j0, j), tau.as<float>());
     tensor_filter_keys(cs.tq, k, j0, tau.as<float>(), d_keys, overflow.as<uint32_t>(), cs.ctotal.as<uint64_t>());
     tensor_check(cs.tq, d_keys, k, ds->n, tau.as<float>(), overflow.as<uint32_t>(), cs.redo.as<uint32_t>(),
                  cs.nredo.as<uint32_t>());

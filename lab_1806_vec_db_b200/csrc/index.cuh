@@ -167,8 +167,8 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
 void operand_info(const vdb_dataset* ds, int* kind, float* scale, float* mean_norm, float* mean_ex, uint64_t* side_bytes);
 void tensor_end(vdb_tq* tq);
 void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys);
-void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float mean_norm, float mean_ex,
-                float* d_tau);
+void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float* d_tau);
+uint32_t tensor_sample_j(uint32_t j0, uint64_t sample_n);
 void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
                         uint32_t* d_overflow, uint64_t* d_cand_total);
 void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,

@@ -435,7 +435,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
     uint32_t j0 = 0, j = 0;
     if (tensor) {
         j0 = tensor_j0(k, S->ns_total, md->n);
-        j = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(j0, S->ns_min));
+        j = tensor_sample_j(j0, S->ns_min);
     }
     // small host batches are uploaded whole by every shard (no exchange); large ones slice by slice + NVLink broadcast
     const bool q_exchange = host && (size_t)nq * rb >= (256u << 10) && G > 1;
@@ -540,8 +540,8 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
             L.tau = DevBuf((size_t)nq * 4, sh.st);
             L.ovf = DevBuf((size_t)nq * 4, sh.st);
             L.ctotal = DevBuf(8, sh.st);
-            tensor_tau(tqs[s], (const uint64_t*)sh.jall.p, G, j, (uint32_t)std::min<uint64_t>(j0, (uint64_t)j * G), S->mean_norm,
-                       S->mean_ex, L.tau.as<float>());
+            tensor_tau(tqs[s], (const uint64_t*)sh.jall.p, G, j, (uint32_t)std::min<uint64_t>(j0, (uint64_t)j * G),
+                       L.tau.as<float>());
             tensor_filter_keys(tqs[s], k, 0, L.tau.as<float>(), L.keys.as<uint64_t>(), L.ovf.as<uint32_t>(),
                                L.ctotal.as<uint64_t>());
             VDB_CUDA(cudaMemcpyAsync(sh.h_stat, L.ctotal.p, 8, cudaMemcpyDeviceToHost, sh.st));

@@ -112,7 +112,7 @@ class ShardedFlatIndex:
         nq, dev = q.shape[0], q.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         j0 = int(lib.vdb_tq_j0(k, ns_total, n_total))
-        j = max(1, min(j0, ns_total // self.world))
+        j = int(lib.vdb_tq_sample_j(j0, max(1, ns_total // self.world)))
         tq = C.c_void_p()
         marks = []
 
@@ -133,7 +133,7 @@ class ShardedFlatIndex:
             mark("gather_sample")
             tau = torch.empty((nq,), dtype=torch.float32, device=dev)
             L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(allj.data_ptr()), self.world, j, min(j0, j * self.world),
-                                       mean_norm, mean_ex, C.c_void_p(tau.data_ptr())))
+                                       C.c_void_p(tau.data_ptr())))
             mark("tau")
             keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
             ovf = torch.empty((nq,), dtype=torch.int32, device=dev)

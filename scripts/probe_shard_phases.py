@@ -28,7 +28,7 @@ def once(record):
     jkeys = torch.empty((nq, j), dtype=torch.int64, device=dev)
     L.check(lib.vdb_tq_sample_dev(tq, j, C.c_void_p(jkeys.data_ptr()))); ev[2].record()
     tau = torch.empty((nq,), dtype=torch.float32, device=dev)
-    L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(jkeys.data_ptr()), 1, j, j0, mn, me, C.c_void_p(tau.data_ptr()))); ev[3].record()
+    L.check(lib.vdb_tq_tau_dev(tq, C.c_void_p(jkeys.data_ptr()), 1, j, j0, C.c_void_p(tau.data_ptr()))); ev[3].record()
     keys = torch.empty((nq, k), dtype=torch.int64, device=dev); ovf = torch.empty((nq,), dtype=torch.int32, device=dev)
     L.check(lib.vdb_tq_filter_dev(tq, k, C.c_void_p(tau.data_ptr()), C.c_void_p(keys.data_ptr()), C.c_void_p(ovf.data_ptr()))); ev[4].record()
     redo = torch.empty((nq,), dtype=torch.int32, device=dev); nredo = torch.zeros((1,), dtype=torch.int32, device=dev)
