@@ -311,79 +311,96 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) best[i] = __uint_as_float(0x7f800000u), bidx[i] = 0xffffffffu;
             }
-            for (uint32_t t = 0; t < iv.ntile; ++t) {
-                // stage the row-scalar tiles of this N-tile (3 x GN floats) while the MMAs run
-                float* sq = norm_tiles + acc * 3 * GN;
-                float* rn = sq + GN;
-                float* ex = rn + GN;
+            // Row scalars of a tile (3 x GN floats: two rows per thread and array). The loads of tile t + 1 are issued
+            // before tile t is scored and stored to the other buffer after it, so their latency hides under the
+            // scoring loop; only an item's first tile pays it.
+            float pre[6];
+            auto load_scalars = [&](uint32_t t) {
                 const uint64_t tile_row0 = iv.r0 + (uint64_t)t * GN;
-                for (uint32_t c = threadIdx.x; c < GN; c += 128) {
-                    const uint64_t brow = tile_row0 + c;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint64_t brow = tile_row0 + threadIdx.x + h * 128;
                     const bool ok = brow < iv.r_end;
                     const uint64_t row = brow * p.row_stride;
                     if (METRIC == VDB_L2SQR) {
-                        sq[c] = ok ? p.sqnorm[row] : __uint_as_float(0x7f800000u);  // +inf: never a candidate
-                        rn[c] = ok ? p.rnorm[row] : 0.f;
-                        ex[c] = ok ? p.ex[row] : 0.f;
+                        pre[h * 3 + 0] = ok ? p.sqnorm[row] : __uint_as_float(0x7f800000u);  // +inf: never a candidate
+                        pre[h * 3 + 1] = ok ? p.rnorm[row] : 0.f;
+                        pre[h * 3 + 2] = ok ? p.ex[row] : 0.f;
                     } else {   // padding: S' = qb - 0 * acc - qab * (-inf) = +inf, and never under the norm clamp
-                        sq[c] = ok ? p.sqnorm[row] : 0.f;
-                        rn[c] = ok ? p.rnorm[row] : __uint_as_float(0x7f800000u);
-                        ex[c] = ok ? p.ex[row] : __uint_as_float(0xff800000u);
+                        pre[h * 3 + 0] = ok ? p.sqnorm[row] : 0.f;
+                        pre[h * 3 + 1] = ok ? p.rnorm[row] : __uint_as_float(0x7f800000u);
+                        pre[h * 3 + 2] = ok ? p.ex[row] : __uint_as_float(0xff800000u);
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+            };
+            auto store_scalars = [&](uint32_t buf) {
+                const uint32_t base = smem_u32(norm_tiles + buf * 3 * GN) + threadIdx.x * 4;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) sts_f32(base + (a * GN + h * 128) * 4, pre[h * 3 + a]);
+            };
+            load_scalars(0);
+            store_scalars(acc);
+            for (uint32_t t = 0; t < iv.ntile; ++t) {
+                const uint64_t tile_row0 = iv.r0 + (uint64_t)t * GN;
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp has stored this tile's scalars and left tile t - 1
+                const bool more = t + 1 < iv.ntile;
+                if (more) load_scalars(t + 1);
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (lane_base << 16) + acc * GN;
                 // the row scalars are read with 128-bit SHARED loads (every lane reads the same address: one broadcast
-                // wavefront per 4 rows and array). Reading them through the generic pointers costs a generic-space LD per
+                // wavefront per 4 rows and array). Reading them through generic pointers costs a generic-space LD per
                 // row and array, which made this loop - not the MMAs - the bound of the whole kernel.
-                const uint32_t sq_s = smem_u32(sq), rn_s = smem_u32(rn), ex_s = smem_u32(ex);
+                const uint32_t sq_s = smem_u32(norm_tiles + acc * 3 * GN), rn_s = sq_s + GN * 4, ex_s = rn_s + GN * 4;
                 // cosine: a row is under the reference's 1e-10 norm-product clamp iff ||x|| < 2e-10 / ||q|| (always kept)
                 const float rthr = METRIC == VDB_COSINE ? (qn > 0.f ? 2e-10f / qn : __uint_as_float(0x7f800000u)) : 0.f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < GN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    if (qok) {
-                        // Hot path: 3 FMAs + 1 predicate-chained compare per score, ONE branch per 32 scores. The scores
-                        // replace the accumulator values in v[]; only a thread that saw a passing (or NaN) score walks
-                        // its 32 values again in the rare path below.
-                        const float thr = MODE == 1 ? tau : (MODE == 2 ? best[MODE == 2 ? G_TOPJ - 1 : 0] : 0.f);
-                        bool none = true;
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(taddr, va);
+                tmem_ld_wait(va);
+                // scores of the 32 columns in v[]: 3 FMAs + one predicate-chained compare per score, a flag per group of 8
+                auto score = [&](uint32_t (&v)[32], int c0) {
+                    if (!qok) return;
+                    const float thr = MODE == 1 ? tau : (MODE == 2 ? best[MODE == 2 ? G_TOPJ - 1 : 0] : 0.f);
+                    bool none[4] = {true, true, true, true};
 #pragma unroll
-                        for (int j4 = 0; j4 < 32; j4 += 4) {
-                            const float4 sq4 = lds_f4(sq_s + (c0 + j4) * 4), rn4 = lds_f4(rn_s + (c0 + j4) * 4),
-                                         ex4 = lds_f4(ex_s + (c0 + j4) * 4);
-                            const float sqv[4] = {sq4.x, sq4.y, sq4.z, sq4.w}, rnv[4] = {rn4.x, rn4.y, rn4.z, rn4.w},
-                                        exv[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 sq4 = lds_f4(sq_s + (c0 + j4) * 4), rn4 = lds_f4(rn_s + (c0 + j4) * 4),
+                                     ex4 = lds_f4(ex_s + (c0 + j4) * 4);
+                        const float sqv[4] = {sq4.x, sq4.y, sq4.z, sq4.w}, rnv[4] = {rn4.x, rn4.y, rn4.z, rn4.w},
+                                    exv[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = j4 + jj;
-                                const float dot = __uint_as_float(v[j]);
-                                float sc;
-                                if (METRIC == VDB_L2SQR) {
-                                    // S' = ||x||^2 - 2 q~.x~ / (s_q s_x) - b(q, x)   (lower bound of d - ||q||^2)
-                                    sc = fmaf(qd, dot, fmaf(-qab, exv[jj], fmaf(-qb, rnv[jj], sqv[jj])));
-                                } else {
-                                    // S' = (1 - bound) - q~.x~ / (s_q s_x ||q|| ||x||)  (lower bound of the cosine distance;
-                                    // sq = 1/||x||). Padding rows are staged with ex = -inf: S' = +inf.
-                                    sc = fmaf(-(qd * sqv[jj]), dot, fmaf(-qab, exv[jj], qb));
-                                    if (rnv[jj] < rthr) sc = __uint_as_float(0xff800000u);
-                                }
-                                v[j] = __float_as_uint(sc);
-                                if (MODE != 0) none = none && (sc >= thr);   // a NaN score fails the test: rare path
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 + jj;
+                            const float dot = __uint_as_float(v[j]);
+                            float sc;
+                            if (METRIC == VDB_L2SQR) {
+                                // S' = ||x||^2 - 2 q~.x~ / (s_q s_x) - b(q, x)   (lower bound of d - ||q||^2)
+                                sc = fmaf(qd, dot, fmaf(-qab, exv[jj], fmaf(-qb, rnv[jj], sqv[jj])));
+                            } else {
+                                // S' = (1 - bound) - q~.x~ / (s_q s_x ||q|| ||x||)  (lower bound of the cosine distance;
+                                // sq = 1/||x||). Padding rows are staged with ex = -inf: S' = +inf.
+                                sc = fmaf(-(qd * sqv[jj]), dot, fmaf(-qab, exv[jj], qb));
+                                if (rnv[jj] < rthr) sc = __uint_as_float(0xff800000u);
                             }
+                            v[j] = __float_as_uint(sc);
+                            if (MODE != 0) none[j >> 3] = none[j >> 3] && (sc >= thr);   // a NaN score fails the test
                         }
-                        if (MODE == 0) {
+                    }
+                    if (MODE == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const uint64_t brow = tile_row0 + c0 + j;
-                                if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(__uint_as_float(v[j]), (uint32_t)brow);
-                            }
-                        } else if (!none) {
+                        for (int j = 0; j < 32; ++j) {
+                            const uint64_t brow = tile_row0 + c0 + j;
+                            if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(__uint_as_float(v[j]), (uint32_t)brow);
+                        }
+                    } else if (!(none[0] && none[1] && none[2] && none[3])) {
+                        // rare path: only the groups of 8 in which this thread saw a passing (or NaN) score are walked again
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
+                        for (int g = 0; g < 4; ++g) {
+                            if (none[g]) continue;
+#pragma unroll
+                            for (int j = g * 8; j < g * 8 + 8; ++j) {
                                 const float sc = __uint_as_float(v[j]);
                                 if (MODE == 2) {
                                     if (sc < best[MODE == 2 ? G_TOPJ - 1 : 0]) {  // bubble (sc, row) into place
@@ -406,6 +423,16 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                             }
                         }
                     }
+                };
+                // the TMEM load of chunk c + 1 is in flight while chunk c is scored
+#pragma unroll 1
+                for (int c0 = 0; c0 < GN; c0 += 64) {
+                    tmem_ld32_issue(taddr + c0 + 32, vb);
+                    score(va, c0);
+                    tmem_ld_wait(vb);
+                    if (c0 + 64 < GN) tmem_ld32_issue(taddr + c0 + 64, va);
+                    score(vb, c0 + 32);
+                    if (c0 + 64 < GN) tmem_ld_wait(va);
                 }
                 // hand the accumulator back to the MMA issuer: one arrive per warp, on the leader's barrier
                 tc_fence_before();
@@ -414,6 +441,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     if (CTAS == 1) mbar_arrive(&tempty_bar[acc]);
                     else mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_MASK);
                 }
+                if (more) store_scalars(acc ^ 1);
                 if (++acc == 2) acc = 0, acc_phase ^= 1;
             }
             if (MODE == 2 && qok) {
