@@ -278,6 +278,42 @@ def other_configs(V, L, lib, vs, base, q_dev, gt_ids, dev, n):
     return out
 
 
+def single_query_e2e(flat, q_host, n_rows, peak_gbs, k=10, seconds=0.4):
+    """vdb_flat_knn with nq = 1 and HOST pointers from T caller threads on one handle (the reference searches one query
+    per call from rayon workers / Python threads: examples/bench.rs:410-416, src/database/mod.rs:248-256). Concurrent
+    calls are coalesced into shared database passes by the library. Wall-clock QPS over `seconds` per case."""
+    import threading
+    out = {"k": k, "api": "vdb_flat_knn(nq=1, host pointers)", "cases": []}
+    ref = [flat.knn_batch(q_host[i:i + 1], k) for i in range(64)]
+    for threads in (1, 8, 32):
+        counts, same, stop = [0] * threads, [True] * threads, [False]
+
+        def work(t):
+            i = t
+            ids = np.empty((1, k), np.uint64); dd = np.empty((1, k), np.float32); cnt = np.empty((1,), np.uint32)
+            while not stop[0]:
+                flat.knn_batch(q_host[i % 64:i % 64 + 1], k, (ids, dd, cnt))
+                same[t] = same[t] and bool((ids == ref[i % 64][0]).all() and (dd.view(np.uint32) == ref[i % 64][1].view(np.uint32)).all())
+                counts[t] += 1
+                i += threads
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]
+        time.sleep(seconds)
+        stop[0] = True
+        [t.join() for t in th]
+        dt = time.perf_counter() - t0
+        qps = sum(counts) / dt
+        case = {"threads": threads, "qps": qps, "results_bit_identical_to_single_calls": all(same)}
+        if threads == 1:
+            case["ms_per_call"] = 1e3 / qps
+            case["frac_of_hbm_peak_whole_call"] = n_rows * DIM * 4 * qps / 1e9 / peak_gbs
+        else:
+            case["speedup_vs_1_thread"] = qps / out["cases"][0]["qps"]
+        out["cases"].append(case)
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port) on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -766,6 +802,11 @@ def run_ours(args):
                                       "frac_whole_call": n_local * DIM * 4 / (call_ms * 1e-3) / 1e9 / peak_hbm})
         L.check(lib.vdb_flat_set_path({"auto": 0, "scan": 1, "tensor": 2}[args.path]))
 
+    # ---- the reference's real call pattern: ONE query per knn call, host pointers, from 1 / 8 / 32 caller threads ----
+    single = None
+    if world == 1:
+        single = single_query_e2e(flat, q_pin.numpy(), n_local, peaks.get("hbm_gbs") or 6650.0)
+
     # ---- the other single-GPU configs of BASELINE.json on the same rows (IVF, PQ) ----------------------------
     other = None
     if world == 1 and not args.no_other_configs and args.n >= 65536:
@@ -795,6 +836,7 @@ def run_ours(args):
         "kernel_ms": {k_: {"ms": v[0], "launches": v[1]} for k_, v in prof.items()},
         "tensor_path": tensor_stats(lib, vs._h),
         "hbm_scan": hbm_scan,
+        "e2e_single_query": single,
         "other_configs": other,
     }
     if idx.phase_ms.get("calls"):  # VDB_PHASE_TIMING=1: per-phase device time of the sharded search (rank 0), ms per call

@@ -53,6 +53,8 @@ SIGNATURES = {
     "vdb_flat_knn_keys_dev": (i32, [vp, vp, u32, u32, vp, vp]),
     "vdb_merge_keys_dev": (i32, [vp, u32, u32, u32, vp, vp, vp, vp]),
     "vdb_flat_set_path": (i32, [i32]),
+    "vdb_set_batching": (i32, [i32]),
+    "vdb_batch_stats": (i32, [vp, vp, vp]),
     "vdb_kmeans_assign": (i32, [vp, u64, u32, i32, i32, vp, u32, u32, u32, vp]),
     "vdb_kmeans_assign_ds": (i32, [vp, vp, u32, u32, u32, vp]),
     "vdb_kmeans_train": (i32, [vp, u64, u32, i32, i32, vp, u32, u32, u32, u32, f32, vp]),

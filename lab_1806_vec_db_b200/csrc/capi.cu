@@ -9,11 +9,15 @@
 #include "index.cuh"
 #include "topk.cuh"
 
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <functional>
 #include <map>
 #include <mutex>
 
 namespace vdb {
+std::atomic<bool> g_batching{true};
 bool g_prof_on = false;
 namespace {
 struct ProfEntry {
@@ -91,11 +95,30 @@ struct DeviceGuard {
 };
 
 // per-call stream for the host-pointer entry points: re-entrant, no cross-call serialisation
+// Stream of the host-pointer entry points: one per (calling thread, device), created on first use and kept for the
+// life of the thread (re-entrant: concurrent callers never share a stream; no create / destroy per call).
+struct ThreadStreams {
+    cudaStream_t s[vdb::VDB_MAX_DEVICES] = {};
+    ~ThreadStreams() {
+        for (int d = 0; d < vdb::VDB_MAX_DEVICES; ++d)
+            if (s[d]) {
+                int prev = 0;
+                if (cudaGetDevice(&prev) != cudaSuccess) break;   // the runtime is shutting down
+                cudaSetDevice(d);
+                cudaStreamDestroy(s[d]);
+                cudaSetDevice(prev);
+            }
+    }
+};
+thread_local ThreadStreams t_streams;
 struct CallStream {
     cudaStream_t s = nullptr;
-    CallStream() { VDB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
-    ~CallStream() {
-        if (s) cudaStreamDestroy(s);
+    CallStream() {   // the current device is the handle's (DeviceGuard)
+        int dev = 0;
+        VDB_CUDA(cudaGetDevice(&dev));
+        cudaStream_t& slot = t_streams.s[dev & (vdb::VDB_MAX_DEVICES - 1)];
+        if (!slot) VDB_CUDA(cudaStreamCreateWithFlags(&slot, cudaStreamNonBlocking));
+        s = slot;
     }
     void sync() { VDB_CUDA(cudaStreamSynchronize(s)); }
 };
@@ -157,6 +180,40 @@ void host_search(int device, const void* queries, uint32_t nq, size_t qbytes_per
     cs.sync();
 }
 }  // namespace
+
+struct vdb_batcher {
+    std::mutex mu;
+    std::condition_variable cv;
+    struct Req {
+        const void* q;
+        uint32_t k;
+        uint64_t* ids;
+        float* dist;
+        uint32_t* count;
+        int state = 0;   // 0 pending, 1 done, 2 failed
+        int code = 0;
+        std::string err;
+    };
+    std::deque<Req*> pending;
+    bool leader_active = false;
+    uint32_t last_batch = 1;
+    cudaStream_t st = nullptr;
+    uint8_t* h_stage = nullptr;   // pinned: queries in, packed results out
+    size_t h_cap = 0;
+    uint8_t* d_stage = nullptr;
+    size_t d_cap = 0;
+    uint64_t batches = 0, served = 0;
+};
+constexpr uint32_t BATCH_MAX = 64;
+
+static void batcher_free(vdb_batcher* b) {
+    if (!b) return;
+    if (b->st) cudaStreamSynchronize(b->st), cudaStreamDestroy(b->st);
+    if (b->h_stage) cudaFreeHost(b->h_stage);
+    if (b->d_stage) cudaFree(b->d_stage);
+    delete b;
+}
+
 
 extern "C" {
 
@@ -310,6 +367,23 @@ int vdb_dataset_set_flat_path(vdb_dataset* ds, int path) {
         ds->flat_path = path;
     });
 }
+int vdb_set_batching(int on) {
+    vdb::g_batching = on != 0;
+    return VDB_OK;
+}
+int vdb_batch_stats(const vdb_dataset* ds, uint64_t* batches, uint64_t* queries) {
+    return guarded([&] {
+        VDB_REQUIRE(ds, "NULL dataset");
+        vdb_batcher* b = ds->batcher;
+        uint64_t nb = 0, nq = 0;
+        if (b) {
+            std::lock_guard<std::mutex> lk(b->mu);
+            nb = b->batches, nq = b->served;
+        }
+        if (batches) *batches = nb;
+        if (queries) *queries = nq;
+    });
+}
 int vdb_debug_force_redo(uint32_t every) {
     vdb::g_debug_force_redo = every;
     return VDB_OK;
@@ -377,6 +451,7 @@ int vdb_dataset_destroy(vdb_dataset* ds) {
             return;
         }
         DeviceGuard g(ds->device);
+        batcher_free(ds->batcher);
         drop_side_arrays(ds);
         if (ds->owned && ds->d_rows) cudaFree(ds->d_rows);
         delete ds;
@@ -400,12 +475,134 @@ static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t 
                     "tensor-core Flat path needs f32 rows, at least 65536 of them, and k <= 1024");
         tensor = true;
     } else if (path == 0) {
-        // measured crossover (scripts/probe_crossover.py, 1M x 960): a tensor pass costs 0.81-0.96 ms for any nq <= 128
-        // (single CTAs, M = 128), the 4-query scan pass 0.70 ms, the 8-query scan pass 1.05 ms
-        tensor = nq >= 5 && vdb::flat_gemm_supported(ds, nq, k);
+        // measured crossover (scripts/probe_parts2.py, 1M x 960 f32): the tensor pass streams the FP16 operand copy (half
+        // the bytes of the rows) and costs 0.50-0.59 ms for any nq <= 128 (single CTAs, M = 128); the exact scan costs
+        // 0.59 ms for 1-2 queries (99 % of the HBM roofline of the fp32 rows), 0.70 ms for 3-4, 1.04 ms for 5-8
+        tensor = nq >= 3 && vdb::flat_gemm_supported(ds, nq, k);
     }
     if (tensor) vdb::flat_gemm_keys(ds, d_q, nq, k, d_keys, st);
     else vdb::flat_scan_keys(ds, d_q, nq, k, d_keys, st);
+}
+
+
+// ---- coalescing of concurrent single-query calls -----------------------------------------------------------------------
+// The reference's call pattern is ONE query per knn call from many threads (rayon workers: examples/bench.rs:410-416,
+// src/bin/gen_gnd.rs:65-68; Python threads under a read lock: src/database/mod.rs:248-256). Every such call is a full
+// pass over the rows, so concurrent callers are served together: the first caller becomes the leader of a batch, the
+// requests that arrive while a batch runs (or within a <= 50 us window when the previous batch showed that several
+// callers are active) form the next batch, one database pass answers them all, and results are bit-identical to the
+// individual calls (the scan and the tensor path return the same bits for any batch composition). A lone caller never
+// waits: its request is the whole batch. Staging buffers and the stream are owned by the dataset handle.
+static std::mutex g_batcher_mu;
+static vdb_batcher* batcher_of(const vdb_dataset* cds) {
+    vdb_dataset* ds = const_cast<vdb_dataset*>(cds);
+    std::lock_guard<std::mutex> lk(g_batcher_mu);
+    if (!ds->batcher) {
+        auto b = new vdb_batcher();
+        DeviceGuard g(ds->device);
+        VDB_CUDA(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+        ds->batcher = b;
+    }
+    return ds->batcher;
+}
+
+// one database pass for `reqs` (same k): stage -> H2D -> search -> decode -> one D2H -> scatter
+static void batcher_run(const vdb_dataset* ds, vdb_batcher* b, std::vector<vdb_batcher::Req*>& reqs) {
+    DeviceGuard g(ds->device);
+    const uint32_t nb = (uint32_t)reqs.size(), k = reqs[0]->k;
+    const size_t rb = (size_t)ds->dim * ds->elem_size();
+    const size_t q_bytes = vdb::round_up<size_t>(nb * rb, 16);
+    const size_t ids_off = q_bytes, dist_off = ids_off + (size_t)nb * k * 8, cnt_off = dist_off + vdb::round_up<size_t>((size_t)nb * k * 4, 16);
+    const size_t total = cnt_off + vdb::round_up<size_t>((size_t)nb * 4, 16);
+    if (total > b->h_cap) {
+        if (b->h_stage) VDB_CUDA(cudaFreeHost(b->h_stage));
+        b->h_stage = nullptr;
+        b->h_cap = 0;
+        VDB_CUDA(cudaHostAlloc((void**)&b->h_stage, total * 2, cudaHostAllocDefault));
+        b->h_cap = total * 2;
+    }
+    if (total > b->d_cap) {
+        if (b->d_stage) VDB_CUDA(cudaFree(b->d_stage));
+        b->d_stage = nullptr;
+        b->d_cap = 0;
+        VDB_CUDA(cudaMalloc((void**)&b->d_stage, total * 2));
+        b->d_cap = total * 2;
+    }
+    for (uint32_t i = 0; i < nb; ++i) memcpy(b->h_stage + i * rb, reqs[i]->q, rb);
+    cudaStream_t st = b->st;
+    VDB_CUDA(cudaMemcpyAsync(b->d_stage, b->h_stage, nb * rb, cudaMemcpyHostToDevice, st));
+    uint64_t* d_ids = (uint64_t*)(b->d_stage + ids_off);
+    float* d_dist = (float*)(b->d_stage + dist_off);
+    uint32_t* d_cnt = (uint32_t*)(b->d_stage + cnt_off);
+    {
+        vdb::DevBuf keys((size_t)nb * k * 8, st);
+        flat_keys_dispatch(ds, b->d_stage, nb, k, keys.as<uint64_t>(), st);
+        vdb::decode_keys(keys.as<uint64_t>(), nb, k, d_ids, d_dist, d_cnt, st);
+    }
+    VDB_CUDA(cudaMemcpyAsync(b->h_stage + ids_off, b->d_stage + ids_off, total - ids_off, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < nb; ++i) {
+        memcpy(reqs[i]->ids, b->h_stage + ids_off + (size_t)i * k * 8, (size_t)k * 8);
+        memcpy(reqs[i]->dist, b->h_stage + dist_off + (size_t)i * k * 4, (size_t)k * 4);
+        *reqs[i]->count = ((const uint32_t*)(b->h_stage + cnt_off))[i];
+    }
+}
+
+static void batched_single_knn(const vdb_dataset* ds, const void* query, uint32_t k, uint64_t* ids, float* dist, uint32_t* count) {
+    vdb_batcher* b = batcher_of(ds);
+    vdb_batcher::Req me{query, k, ids, dist, count};
+    std::unique_lock<std::mutex> lk(b->mu);
+    b->pending.push_back(&me);
+    b->cv.notify_all();   // a leader inside its collection window counts the arrivals
+    while (me.state == 0) {
+        if (b->leader_active) {
+            b->cv.wait(lk);
+            continue;
+        }
+        // lead: serve batches until this thread's own request has been answered, then hand over
+        b->leader_active = true;
+        while (me.state == 0) {
+            if (b->last_batch > 1 && b->pending.size() < b->last_batch) {
+                // several callers were active a moment ago: give them <= 50 us to line up behind this request
+                const uint32_t want = b->last_batch;
+                b->cv.wait_for(lk, std::chrono::microseconds(50), [&] { return b->pending.size() >= want; });
+            }
+            std::vector<vdb_batcher::Req*> batch;
+            const uint32_t bk = b->pending.front()->k;
+            for (auto it = b->pending.begin(); it != b->pending.end() && batch.size() < BATCH_MAX;) {
+                if ((*it)->k == bk) {
+                    batch.push_back(*it);
+                    it = b->pending.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+            lk.unlock();
+            int code = 0;
+            std::string err;
+            try {
+                batcher_run(ds, b, batch);
+            } catch (const vdb::Error& e) {
+                code = e.code, err = e.what();
+            } catch (const std::exception& e) {
+                code = VDB_ECUDA, err = e.what();
+            }
+            lk.lock();
+            for (auto* r : batch) {
+                r->state = code ? 2 : 1;
+                r->code = code;
+                r->err = err;
+            }
+            b->last_batch = (uint32_t)batch.size();
+            b->batches += 1;
+            b->served += batch.size();
+            b->cv.notify_all();
+        }
+        b->leader_active = false;
+        b->cv.notify_all();   // a waiting caller takes over the queue
+    }
+    lk.unlock();
+    if (me.state == 2) throw vdb::Error(me.code, me.err);
 }
 
 int vdb_flat_knn_keys_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys,
@@ -439,6 +636,10 @@ int vdb_flat_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32
         VDB_REQUIRE(nq * (uint64_t)k == 0 || (ids && dist), "NULL result arrays");
         if (ds->sharded) {   // vdb_init with several devices: the same call, spread over the shards (multi.cu)
             vdb::sharded_flat_knn(ds, queries, nq, k, ids, dist, counts);
+            return;
+        }
+        if (nq == 1 && k > 0 && ds->n > 0 && vdb::g_batching.load()) {   // the trait's call: coalesced with concurrent callers
+            batched_single_knn(ds, queries, k, ids, dist, counts);
             return;
         }
         host_search(dev_of(ds), queries, nq, (size_t)ds->dim * ds->elem_size(), k, ids, dist, counts,

@@ -34,6 +34,7 @@ struct vdb_dataset {
     // row-sharded parent (vdb_init with several devices; multi.cu): the rows live in the shards' own vdb_dataset
     // handles, this handle only carries n / dim / dtype / metric and the worker pool
     struct vdb_sharded_state* sharded = nullptr;
+    struct vdb_batcher* batcher = nullptr;   // coalesces concurrent single-query host calls (capi.cu), created on first use
     uint32_t elem_size() const { return dtype == VDB_F32 ? 4u : 1u; }
     size_t pitch_bytes() const { return (size_t)pitch * elem_size(); }
 };
@@ -74,6 +75,7 @@ void pair_distances(const vdb_dataset* ds, const float* d_qtile, uint32_t qstrid
                     int mode, float* d_out, cudaStream_t st);
 
 void drop_side_arrays(vdb_dataset* ds);   // flat_gemm.cu: frees the lazily built side arrays (called on mutation)
+extern std::atomic<bool> g_batching;
 extern std::atomic<int> g_flat_path;   // process default of the Flat path selection (vdb_flat_set_path)
 
 }  // namespace vdb
