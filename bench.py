@@ -74,6 +74,35 @@ def synth(proto, lo, hi, seed, dev):
     return out
 
 
+def synth_clustered(proto, lo, hi, seed, dev, latent=32, spread=0.03, noise=0.004):
+    """Second synthetic set for the recall-calibrated legs (IVF / PQ / HNSW): rows [lo, hi) of a mixture of LOW-RANK
+    clouds. Row i = prototype i % 1000 + L z_i + isotropic noise, z_i ~ N(0, 1)^latent, L a fixed [latent, 960] matrix
+    giving a per-dimension standard deviation `spread`; clamped to [0, 1] on the 1e-4 grid of the real GIST data. Inside
+    a prototype's cloud the distances now vary with the latent coordinates (relative contrast ~2 between the nearest
+    neighbours and a typical member, as in real descriptors), whereas the flat set of bench.synth has 1000
+    near-equidistant copies per prototype that PQ / HNSW can only rank by chance (recall ~ ef / 1000)."""
+    import torch
+    proto = torch.as_tensor(proto, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(977)                      # L depends on nothing but this constant
+    lmat = torch.randn((latent, DIM), generator=g, device=dev) * (spread / latent ** 0.5)
+    out = torch.empty((hi - lo, DIM), dtype=torch.float32, device=dev)
+    c = lo // CHUNK
+    while c * CHUNK < hi:
+        c_lo, c_hi = c * CHUNK, (c + 1) * CHUNK
+        g2 = torch.Generator(device=dev)
+        g2.manual_seed(seed * 1_000_003 + c)
+        z = torch.randn((CHUNK, DIM), generator=g2, device=dev, dtype=torch.float32)
+        zl = torch.randn((CHUNK, latent), generator=g2, device=dev, dtype=torch.float32)
+        a, b = max(lo, c_lo), min(hi, c_hi)
+        idx = torch.arange(a, b, device=dev) % proto.shape[0]
+        x = proto[idx] + zl[a - c_lo:b - c_lo] @ lmat + noise * z[a - c_lo:b - c_lo]
+        out[a - lo:b - lo] = torch.round(x.clamp_(0.0, 1.0) * 1e4) / 1e4
+        del z, zl
+        c += 1
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -278,33 +307,32 @@ def other_configs(V, L, lib, vs, base, q_dev, gt_ids, dev, n):
     return out
 
 
-def single_query_e2e(flat, q_host, n_rows, peak_gbs, k=10, seconds=0.4):
-    """vdb_flat_knn with nq = 1 and HOST pointers from T caller threads on one handle (the reference searches one query
-    per call from rayon workers / Python threads: examples/bench.rs:410-416, src/database/mod.rs:248-256). Concurrent
-    calls are coalesced into shared database passes by the library. Wall-clock QPS over `seconds` per case."""
-    import threading
-    out = {"k": k, "api": "vdb_flat_knn(nq=1, host pointers)", "cases": []}
-    ref = [flat.knn_batch(q_host[i:i + 1], k) for i in range(64)]
-    for threads in (1, 8, 32):
-        counts, same, stop = [0] * threads, [True] * threads, [False]
-
-        def work(t):
-            i = t
-            ids = np.empty((1, k), np.uint64); dd = np.empty((1, k), np.float32); cnt = np.empty((1,), np.uint32)
-            while not stop[0]:
-                flat.knn_batch(q_host[i % 64:i % 64 + 1], k, (ids, dd, cnt))
-                same[t] = same[t] and bool((ids == ref[i % 64][0]).all() and (dd.view(np.uint32) == ref[i % 64][1].view(np.uint32)).all())
-                counts[t] += 1
-                i += threads
-        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-        t0 = time.perf_counter()
-        [t.start() for t in th]
-        time.sleep(seconds)
-        stop[0] = True
-        [t.join() for t in th]
-        dt = time.perf_counter() - t0
-        qps = sum(counts) / dt
-        case = {"threads": threads, "qps": qps, "results_bit_identical_to_single_calls": all(same)}
+def single_query_e2e(flat, q_host, n_rows, peak_gbs, k=10):
+    """vdb_flat_knn with nq = 1 and HOST pointers from T native caller threads on one handle (the reference searches
+    one query per call from rayon workers / Python threads: examples/bench.rs:410-416, src/database/mod.rs:248-256;
+    vdb_parallel_knn is that loop). Concurrent calls are coalesced into shared database passes by the library."""
+    from lab_1806_vec_db_b200 import _lib as L
+    lib = L.lib()
+    out = {"k": k, "api": "vdb_flat_knn(nq=1, host pointers), one call per query from T native threads", "cases": []}
+    ref = None
+    for threads, nq in ((1, 256), (8, 2048), (32, 4096)):
+        q = np.ascontiguousarray(q_host[:nq])
+        ids = np.empty((nq, k), np.uint64); dd = np.empty((nq, k), np.float32); cnt = np.empty((nq,), np.uint32)
+        secs = C.c_double(0)
+        nb0, ns0 = C.c_uint64(0), C.c_uint64(0)
+        lib.vdb_batch_stats(flat.vec_set._h, C.byref(nb0), C.byref(ns0))
+        for _ in range(2):   # first round = warm-up
+            L.check(lib.vdb_parallel_knn(flat.vec_set._h, L.ptr(q), nq, k, threads, L.ptr(ids), L.ptr(dd), L.ptr(cnt), C.byref(secs)))
+        nb1, ns1 = C.c_uint64(0), C.c_uint64(0)
+        lib.vdb_batch_stats(flat.vec_set._h, C.byref(nb1), C.byref(ns1))
+        if ref is None:
+            ref = (ids.copy(), dd.copy())
+        m = min(nq, ref[0].shape[0])
+        qps = nq / secs.value
+        case = {"threads": threads, "calls": nq, "qps": qps,
+                "queries_per_database_pass": (ns1.value - ns0.value) / max(1, nb1.value - nb0.value),
+                "results_bit_identical_to_1_thread": bool((ids[:m] == ref[0][:m]).all() and
+                                                          (dd[:m].view(np.uint32) == ref[1][:m].view(np.uint32)).all())}
         if threads == 1:
             case["ms_per_call"] = 1e3 / qps
             case["frac_of_hbm_peak_whole_call"] = n_rows * DIM * 4 * qps / 1e9 / peak_gbs

@@ -114,11 +114,16 @@ int vdb_flat_knn_sharded_dev(const vdb_dataset* ds, const void* const* d_queries
                              uint64_t* const* d_ids, float* const* d_dist, uint32_t* const* d_counts);
 /* Concurrent nq == 1 calls of vdb_flat_knn on one handle - the reference's call pattern: one query per knn call from
  * rayon workers / Python threads under a read lock (examples/bench.rs:410-416, src/database/mod.rs:248-256) - are
- * coalesced: calls that arrive while a database pass is running (or within <= 50 us of each other once several callers
+ * coalesced: calls that arrive while a database pass is running (or within <= 120 us of each other once several callers
  * have been seen) are answered by ONE pass. Results are bit-identical to individual calls. On by default;
  * vdb_set_batching(0) turns it off process-wide. vdb_batch_stats: passes run / queries served through the batcher. */
 int vdb_set_batching(int on);
 int vdb_batch_stats(const vdb_dataset* ds, uint64_t* batches, uint64_t* queries);
+/* The rayon loop of the reference's drivers (examples/bench.rs:410-416 `-t`, src/bin/gen_gnd.rs:65-68) for hosts without
+ * a native thread pool: nq queries, ONE vdb_flat_knn(nq = 1) call each, issued from `threads` native threads. Results
+ * as vdb_flat_knn with nq queries; *seconds (optional) = wall time of the loop. */
+int vdb_parallel_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32_t k, uint32_t threads, uint64_t* ids,
+                     float* dist, uint32_t* counts, double* seconds);
 /* Row-sharded search, step 1: this shard's k best per query as packed sortable keys
  * (high 32 bits = order-preserving distance bits, low 32 bits = global id), [nq, k], ascending,
  * padded with UINT64_MAX. Step 2 (after an NCCL all-gather of the shards' keys):

@@ -54,6 +54,7 @@ SIGNATURES = {
     "vdb_merge_keys_dev": (i32, [vp, u32, u32, u32, vp, vp, vp, vp]),
     "vdb_flat_set_path": (i32, [i32]),
     "vdb_set_batching": (i32, [i32]),
+    "vdb_parallel_knn": (i32, [vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     "vdb_batch_stats": (i32, [vp, vp, vp]),
     "vdb_kmeans_assign": (i32, [vp, u64, u32, i32, i32, vp, u32, u32, u32, vp]),
     "vdb_kmeans_assign_ds": (i32, [vp, vp, u32, u32, u32, vp]),

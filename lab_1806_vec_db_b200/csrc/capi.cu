@@ -15,6 +15,7 @@
 #include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 
 namespace vdb {
 std::atomic<bool> g_batching{true};
@@ -205,6 +206,7 @@ struct vdb_batcher {
     uint64_t batches = 0, served = 0;
 };
 constexpr uint32_t BATCH_MAX = 64;
+constexpr uint32_t BATCH_WINDOW_US = 120;
 
 static void batcher_free(vdb_batcher* b) {
     if (!b) return;
@@ -489,7 +491,7 @@ static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t 
 // The reference's call pattern is ONE query per knn call from many threads (rayon workers: examples/bench.rs:410-416,
 // src/bin/gen_gnd.rs:65-68; Python threads under a read lock: src/database/mod.rs:248-256). Every such call is a full
 // pass over the rows, so concurrent callers are served together: the first caller becomes the leader of a batch, the
-// requests that arrive while a batch runs (or within a <= 50 us window when the previous batch showed that several
+// requests that arrive while a batch runs (or within a <= 120 us window when the previous batch showed that several
 // callers are active) form the next batch, one database pass answers them all, and results are bit-identical to the
 // individual calls (the scan and the tensor path return the same bits for any batch composition). A lone caller never
 // waits: its request is the whole batch. Staging buffers and the stream are owned by the dataset handle.
@@ -563,9 +565,11 @@ static void batched_single_knn(const vdb_dataset* ds, const void* query, uint32_
         b->leader_active = true;
         while (me.state == 0) {
             if (b->last_batch > 1 && b->pending.size() < b->last_batch) {
-                // several callers were active a moment ago: give them <= 50 us to line up behind this request
+                // several callers were active a moment ago: give them a moment to line up behind this request (they are
+                // waking up from the previous batch: a futex wake-up takes tens of microseconds; a database pass takes
+                // >= 500 us at 1M x 960, so a fuller batch repays the wait many times over)
                 const uint32_t want = b->last_batch;
-                b->cv.wait_for(lk, std::chrono::microseconds(50), [&] { return b->pending.size() >= want; });
+                b->cv.wait_for(lk, std::chrono::microseconds(BATCH_WINDOW_US), [&] { return b->pending.size() >= want; });
             }
             std::vector<vdb_batcher::Req*> batch;
             const uint32_t bk = b->pending.front()->k;
@@ -657,6 +661,32 @@ int vdb_flat_knn_sharded_dev(const vdb_dataset* ds, const void* const* d_queries
         VDB_REQUIRE(ds && ds->sharded, "not a row-sharded dataset");
         VDB_REQUIRE(nq == 0 || (d_queries && d_ids && d_dist && d_counts), "NULL argument");
         vdb::sharded_flat_knn_dev(ds, d_queries, nq, k, d_ids, d_dist, d_counts);
+    });
+}
+
+// The rayon loop of the reference's drivers (examples/bench.rs:410-416 `-t`, src/bin/gen_gnd.rs:65-68): nq queries, ONE
+// vdb_flat_knn(nq = 1) call each, issued from `threads` native threads (query i goes to thread i % threads).
+int vdb_parallel_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32_t k, uint32_t threads, uint64_t* ids,
+                     float* dist, uint32_t* counts, double* seconds) {
+    return guarded([&] {
+        VDB_REQUIRE(ds && (queries || nq == 0) && threads >= 1 && threads <= 1024, "bad argument");
+        VDB_REQUIRE(nq == 0 || (counts && (k == 0 || (ids && dist))), "NULL result arrays");
+        const size_t rb = (size_t)ds->dim * ds->elem_size();
+        std::vector<std::thread> th;
+        std::vector<int> rc(threads, 0);
+        std::vector<std::string> msg(threads);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (uint32_t t = 0; t < threads; ++t)
+            th.emplace_back([&, t] {
+                for (uint32_t i = t; i < nq && rc[t] == 0; i += threads) {
+                    rc[t] = vdb_flat_knn(ds, (const uint8_t*)queries + i * rb, 1, k, ids + (size_t)i * k, dist + (size_t)i * k, counts + i);
+                    if (rc[t]) msg[t] = vdb_last_error();
+                }
+            });
+        for (auto& x : th) x.join();
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (uint32_t t = 0; t < threads; ++t)
+            if (rc[t]) throw vdb::Error(rc[t], msg[t]);
     });
 }
 
