@@ -74,7 +74,7 @@ def synth(proto, lo, hi, seed, dev):
     return out
 
 
-def synth_clustered(proto, lo, hi, seed, dev, latent=32, spread=0.03, noise=0.004):
+def synth_clustered(proto, lo, hi, seed, dev, latent=32, spread=0.010, noise=0.018):
     """Second synthetic set for the recall-calibrated legs (IVF / PQ / HNSW): rows [lo, hi) of a mixture of LOW-RANK
     clouds. Row i = prototype i % 1000 + L z_i + isotropic noise, z_i ~ N(0, 1)^latent, L a fixed [latent, 960] matrix
     giving a per-dimension standard deviation `spread`; clamped to [0, 1] on the 1e-4 grid of the real GIST data. Inside
@@ -231,150 +231,6 @@ def tensor_stats(lib, ds_handle=None):
                               "scale": scale.value, "mean_row_norm": mn.value, "mean_operand_error_norm": me.value,
                               "side_array_bytes": sb.value}
     return out
-
-
-def other_configs(V, L, lib, vs, base, q_dev, gt_ids, dev, n):
-    """configs[2] (IVF nlist=128, nprobe sweep) and configs[3] (PQ m=240 x 4 bits, ef sweep) of BASELINE.json on the same
-    rows: 1000 queries, k=10 (examples/bench.rs protocol), recall@10 against the exact Flat result of the headline leg.
-    Device-resident, CUDA events, 3 repetitions after one warm-up. bench_aux.py is the long form (CPU columns, HNSW)."""
-    import torch
-    from lab_1806_vec_db_b200.index import train_codebooks
-    nq, k = min(1000, q_dev.shape[0]), 10
-    q = q_dev[:nq].contiguous()
-    gt = gt_ids[:nq, :k]
-    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    rng = np.random.default_rng(42)
-    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
-
-    def timed(fn, reps=3):
-        fn()
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(reps):
-            fn()
-        a1.record()
-        torch.cuda.synchronize()
-        return a0.elapsed_time(a1) / reps
-
-    def recall():
-        got = ids.cpu().numpy()
-        return float(np.mean([len(set(got[i]) & set(gt[i])) / k for i in range(nq)]))
-
-    def sample_rows(m):
-        sel = torch.as_tensor(rng.permutation(n)[:min(m, n)], device=dev)
-        return np.ascontiguousarray(base.index_select(0, sel).cpu().numpy())
-
-    out = {"nq": nq, "k": k, "recall_against": "exact Flat top-10 of the same queries (headline leg)"}
-    # ---- configs[2]: IVF ----
-    t0 = time.perf_counter()
-    km = V.KMeans.from_vec_set(sample_rows(100_000), V.KMeansConfig(128, 20, 1e-6, "l2sqr"), rng)
-    t_train = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ivf = V.IVFIndex(vs, km.centroids)
-    t_assign = time.perf_counter() - t0
-    rows = []
-    for nprobe in (8, 16, 24):
-        ms = timed(lambda: L.check(lib.vdb_ivf_knn_dev(vs._h, ivf._h, C.c_void_p(q.data_ptr()), nq, k, nprobe,
-                                                       C.c_void_p(ids.data_ptr()), C.c_void_p(dd.data_ptr()),
-                                                       C.c_void_p(cnt.data_ptr()), st)))
-        rows.append({"nprobe": nprobe, "qps": nq / ms * 1e3, "ms_per_batch": ms, "recall@10": recall()})
-    out["ivf"] = {"nlist": 128, "kmeans_rows": min(100_000, n), "kmeans_iters": int(km.iterations),
-                  "train_s": t_train, "assign_and_lists_s": t_assign, "search": rows}
-    del ivf
-    # ---- configs[3]: PQ table + Flat ADC scan + exact rerank ----
-    cfg = V.PQConfig(4, 240, "l2sqr", min(10_000, n), 20, 1e-6)
-    t0 = time.perf_counter()
-    train_dev = V.DeviceVecSet(sample_rows(10_000), "l2sqr")
-    books = train_codebooks(train_dev, cfg, rng)
-    train_dev.close()
-    t_train = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    pq = V.PQTable(vs, cfg, books)
-    t_encode = time.perf_counter() - t0
-    rows = []
-    for ef in (240, 420, 600):
-        ms = timed(lambda: L.check(lib.vdb_pq_knn_dev(vs._h, pq._h, C.c_void_p(q.data_ptr()), nq, k, ef,
-                                                      C.c_void_p(ids.data_ptr()), C.c_void_p(dd.data_ptr()),
-                                                      C.c_void_p(cnt.data_ptr()), st)))
-        rows.append({"ef": ef, "qps": nq / ms * 1e3, "ms_per_batch": ms, "recall@10": recall()})
-    out["pq"] = {"m": 240, "n_bits": 4, "kmeans_rows": min(10_000, n), "train_s_incl_upload": t_train,
-                 "encode_s_incl_code_download": t_encode, "search": rows,
-                 "note": "the synthetic set has 1000 near-equidistant copies per prototype, which 4-bit PQ cannot rank: "
-                         "recall equals the CPU oracle's on the same codebooks (bench_aux.py, tests/test_index_gpu.py)"}
-    return out
-
-
-def single_query_e2e(flat, q_host, n_rows, peak_gbs, k=10):
-    """vdb_flat_knn with nq = 1 and HOST pointers from T native caller threads on one handle (the reference searches
-    one query per call from rayon workers / Python threads: examples/bench.rs:410-416, src/database/mod.rs:248-256;
-    vdb_parallel_knn is that loop). Concurrent calls are coalesced into shared database passes by the library."""
-    from lab_1806_vec_db_b200 import _lib as L
-    lib = L.lib()
-    out = {"k": k, "api": "vdb_flat_knn(nq=1, host pointers), one call per query from T native threads", "cases": []}
-    ref = None
-    for threads, nq in ((1, 256), (8, 2048), (32, 4096)):
-        q = np.ascontiguousarray(q_host[:nq])
-        ids = np.empty((nq, k), np.uint64); dd = np.empty((nq, k), np.float32); cnt = np.empty((nq,), np.uint32)
-        secs = C.c_double(0)
-        nb0, ns0 = C.c_uint64(0), C.c_uint64(0)
-        lib.vdb_batch_stats(flat.vec_set._h, C.byref(nb0), C.byref(ns0))
-        for _ in range(2):   # first round = warm-up
-            L.check(lib.vdb_parallel_knn(flat.vec_set._h, L.ptr(q), nq, k, threads, L.ptr(ids), L.ptr(dd), L.ptr(cnt), C.byref(secs)))
-        nb1, ns1 = C.c_uint64(0), C.c_uint64(0)
-        lib.vdb_batch_stats(flat.vec_set._h, C.byref(nb1), C.byref(ns1))
-        if ref is None:
-            ref = (ids.copy(), dd.copy())
-        m = min(nq, ref[0].shape[0])
-        qps = nq / secs.value
-        case = {"threads": threads, "calls": nq, "qps": qps,
-                "queries_per_database_pass": (ns1.value - ns0.value) / max(1, nb1.value - nb0.value),
-                "results_bit_identical_to_1_thread": bool((ids[:m] == ref[0][:m]).all() and
-                                                          (dd[:m].view(np.uint32) == ref[1][:m].view(np.uint32)).all())}
-        if threads == 1:
-            case["ms_per_call"] = 1e3 / qps
-            case["frac_of_hbm_peak_whole_call"] = n_rows * DIM * 4 * qps / 1e9 / peak_gbs
-        else:
-            case["speedup_vs_1_thread"] = qps / out["cases"][0]["qps"]
-        out["cases"].append(case)
-    return out
-
-
-def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the box's host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    nqs = args.cpu_queries or min(128, 2 * cores)
-    base1000, test1000 = load_fixtures()
-    try:
-        import torch
-        dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
-    except Exception:
-        dev = None
-    import torch
-    base = synth(base1000, 0, args.n, 42, dev).cpu().numpy()
-    q = synth(test1000, 0, nqs, 43, dev).cpu().numpy()
-    qps, dt, _ = cpu_arm(base, q, args.k, cores, max(1, args.steps), min(args.warmup, 1))
-    line = {
-        "impl": "reference", "metric": "QPS, exact Flat L2 kNN", "value": qps, "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the GPU arm's config (same workload, same keys); the bounded CPU sample is described under cpu_baseline
-        "config": {"workload": f"Flat L2Sqr exact kNN, synthetic GIST-shaped {args.n}x{DIM} f32, "
-                               f"{args.nq}-query batch, k={args.k} (configs[1])",
-                   "n": args.n, "dim": DIM, "nq": args.nq, "k": args.k, "cpu_sample_queries_per_step": nqs},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": f"{nqs} of the {args.nq} queries x {args.n} rows per step, thread pool over queries "
-                                   "(examples/bench.rs -t protocol); C++ restatement of the Rust path, "
-                                   "sequential f32, -O3 -ffp-contract=off"},
-        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
 
 
 def run_ours_multi(args):
@@ -839,7 +695,8 @@ def run_ours(args):
     other = None
     if world == 1 and not args.no_other_configs and args.n >= 65536:
         try:
-            other = other_configs(V, L, lib, vs, base, q_dev, res[0].cpu().numpy(), dev, args.n)
+            import bench_configs
+            other = bench_configs.run_all(V, L, lib, dev, peaks, base, q_dev, synth_clustered, base1000, args.n)
         except Exception as e:  # the headline line must not be lost to an auxiliary leg
             other = {"error": repr(e)}
 

@@ -758,6 +758,46 @@ void* orc_hnsw_build(const void* rows, size_t n, size_t dim, int dtype, int metr
     });
     return nullptr;
 }
+/* An index whose graph was built elsewhere (HNSWIndex deserialisation, hnsw_index.rs:641-668, followed by
+ * init_dist_cache_after_load :371-379): levels[n], level-0 links [n][2m] + lengths, upper levels per node in row order
+ * ([sum(levels)][m] + lengths). Lets the CPU search walk the very graph the GPU built. */
+void* orc_hnsw_from_graph(const void* rows, size_t n, size_t dim, int dtype, int metric, size_t m, size_t ef_construction,
+                          const uint32_t* levels, const uint32_t* links0, const uint32_t* len0, const uint32_t* ulinks,
+                          const uint32_t* ulen, long enter_point, long enter_level) {
+    D1(dtype, {
+        auto* h = new Hnsw<T>();
+        h->rows = (const T*)rows;
+        h->n = n;
+        h->dim = dim;
+        h->m = m;
+        h->max_m0 = 2 * m;
+        h->ef_c = std::max(ef_construction, 2 * m);
+        h->metric = metric;
+        h->level0.assign(links0, links0 + n * h->max_m0);
+        h->other.resize(n);
+        h->len.resize(n);
+        h->vec_level.resize(n);
+        h->cache.resize(n);
+        size_t slot = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const size_t lv = levels[i];
+            h->vec_level[i] = lv;
+            h->len[i].assign(lv + 1, 0);
+            h->len[i][0] = len0[i];
+            h->other[i].assign(lv * m, 0);
+            for (size_t l = 1; l <= lv; ++l, ++slot) {
+                h->len[i][l] = ulen[slot];
+                std::copy(ulinks + slot * m, ulinks + (slot + 1) * m, h->other[i].begin() + (l - 1) * m);
+            }
+            const T* v = h->rows + i * dim;
+            h->cache[i] = metric == ORC_L2SQR ? dot(v, v, dim) : vec_norm(v, dim);   /* dist_cache, distance/mod.rs:31-36 */
+        }
+        h->enter_point = enter_point;
+        h->enter_level = enter_level;
+        return (void*)h;
+    });
+    return nullptr;
+}
 int orc_hnsw_knn(const void* handle, int dtype, const void* queries, size_t nq, size_t k, size_t ef, uint64_t* ids,
                  float* dists, uint32_t* counts, int nthreads) {
     D1(dtype, {

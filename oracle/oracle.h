@@ -112,6 +112,10 @@ int orc_gather_dist(const void* base, size_t dim, int dtype, int metric, const f
 /* HNSW (hnsw_index.rs), single-thread restatement: sequential add of every row with the given levels, knn_with_ef */
 void* orc_hnsw_build(const void* rows, size_t n, size_t dim, int dtype, int metric, size_t m, size_t ef_construction,
                      const uint32_t* levels);
+/* the same object over a graph built elsewhere (layouts of vdb_hnsw_links0 / vdb_hnsw_upper) */
+void* orc_hnsw_from_graph(const void* rows, size_t n, size_t dim, int dtype, int metric, size_t m, size_t ef_construction,
+                          const uint32_t* levels, const uint32_t* links0, const uint32_t* len0, const uint32_t* ulinks,
+                          const uint32_t* ulen, long enter_point, long enter_level);
 int orc_hnsw_knn(const void* handle, int dtype, const void* queries, size_t nq, size_t k, size_t ef, uint64_t* ids,
                  float* dists, uint32_t* counts, int nthreads);
 int orc_hnsw_knn_pq(const void* handle, int dtype, const void* queries, size_t nq, size_t k, size_t ef, const uint8_t* codes,

@@ -283,6 +283,30 @@ class HnswOracle:
                                    self.dt, _METRIC[metric], C.c_size_t(m), C.c_size_t(ef_construction), _p(levels)))
         self.m = m
 
+    @classmethod
+    def from_graph(cls, base, metric, m, ef_construction, levels, links0, len0, ulinks, ulen, enter_point, enter_level):
+        """The CPU search over a graph built elsewhere (e.g. by the GPU build): layouts of vdb_hnsw_links0 / _upper."""
+        self = cls.__new__(cls)
+        self.base = _c(base)
+        self.dt = _dt(self.base)
+        self.levels = _c(levels, np.uint32)
+        self.m = m
+        self._keep = (_c(links0, np.uint32), _c(len0, np.uint32), _c(ulinks, np.uint32), _c(ulen, np.uint32))
+        f = lib().orc_hnsw_from_graph
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long]
+        lib().orc_hnsw_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int]
+        lib().orc_hnsw_free.argtypes = [C.c_void_p, C.c_int]
+        lib().orc_hnsw_free.restype = None
+        ul = self._keep[2] if self._keep[2].size else np.zeros(1, np.uint32)
+        un = self._keep[3] if self._keep[3].size else np.zeros(1, np.uint32)
+        self.h = C.c_void_p(f(_p(self.base), self.base.shape[0], self.base.shape[1], self.dt, _METRIC[metric], m,
+                              ef_construction, _p(self.levels), _p(self._keep[0]), _p(self._keep[1]), _p(ul), _p(un),
+                              int(enter_point), int(enter_level)))
+        return self
+
     def knn(self, queries, k, ef, nthreads=1):
         q = _c(queries)
         nq = q.shape[0]
