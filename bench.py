@@ -233,6 +233,76 @@ def tensor_stats(lib, ds_handle=None):
     return out
 
 
+def single_query_e2e(flat, q_host, n_rows, peak_gbs, k=10):
+    """vdb_flat_knn with nq = 1 and HOST pointers from T native caller threads on one handle (the reference searches
+    one query per call from rayon workers / Python threads: examples/bench.rs:410-416, src/database/mod.rs:248-256;
+    vdb_parallel_knn is that loop). Concurrent calls are coalesced into shared database passes by the library."""
+    from lab_1806_vec_db_b200 import _lib as L
+    lib = L.lib()
+    out = {"k": k, "api": "vdb_flat_knn(nq=1, host pointers), one call per query from T native threads", "cases": []}
+    ref = None
+    for threads, nq in ((1, 256), (8, 2048), (32, 4096)):
+        q = np.ascontiguousarray(q_host[:nq])
+        ids = np.empty((nq, k), np.uint64); dd = np.empty((nq, k), np.float32); cnt = np.empty((nq,), np.uint32)
+        secs = C.c_double(0)
+        nb0, ns0 = C.c_uint64(0), C.c_uint64(0)
+        lib.vdb_batch_stats(flat.vec_set._h, C.byref(nb0), C.byref(ns0))
+        for _ in range(2):   # first round = warm-up
+            L.check(lib.vdb_parallel_knn(flat.vec_set._h, L.ptr(q), nq, k, threads, L.ptr(ids), L.ptr(dd), L.ptr(cnt), C.byref(secs)))
+        nb1, ns1 = C.c_uint64(0), C.c_uint64(0)
+        lib.vdb_batch_stats(flat.vec_set._h, C.byref(nb1), C.byref(ns1))
+        if ref is None:
+            ref = (ids.copy(), dd.copy())
+        m = min(nq, ref[0].shape[0])
+        qps = nq / secs.value
+        case = {"threads": threads, "calls": nq, "qps": qps,
+                "queries_per_database_pass": (ns1.value - ns0.value) / max(1, nb1.value - nb0.value),
+                "results_bit_identical_to_1_thread": bool((ids[:m] == ref[0][:m]).all() and
+                                                          (dd[:m].view(np.uint32) == ref[1][:m].view(np.uint32)).all())}
+        if threads == 1:
+            case["ms_per_call"] = 1e3 / qps
+            case["frac_of_hbm_peak_whole_call"] = n_rows * DIM * 4 * qps / 1e9 / peak_gbs
+        else:
+            case["speedup_vs_1_thread"] = qps / out["cases"][0]["qps"]
+        out["cases"].append(case)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nqs = args.cpu_queries or min(128, 2 * cores)
+    base1000, test1000 = load_fixtures()
+    try:
+        import torch
+        dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+    except Exception:
+        dev = None
+    import torch
+    base = synth(base1000, 0, args.n, 42, dev).cpu().numpy()
+    q = synth(test1000, 0, nqs, 43, dev).cpu().numpy()
+    qps, dt, _ = cpu_arm(base, q, args.k, cores, max(1, args.steps), min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "QPS, exact Flat L2 kNN", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        # the GPU arm's config (same workload, same keys); the bounded CPU sample is described under cpu_baseline
+        "config": {"workload": f"Flat L2Sqr exact kNN, synthetic GIST-shaped {args.n}x{DIM} f32, "
+                               f"{args.nq}-query batch, k={args.k} (configs[1])",
+                   "n": args.n, "dim": DIM, "nq": args.nq, "k": args.k, "cpu_sample_queries_per_step": nqs},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{nqs} of the {args.nq} queries x {args.n} rows per step, thread pool over queries "
+                                   "(examples/bench.rs -t protocol); C++ restatement of the Rust path, "
+                                   "sequential f32, -O3 -ffp-contract=off"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ours_multi(args):
     """N > 1: ONE process (rank 0) drives all N GPUs through the single C call a Rust host would make
     (vdb_flat_knn on a row-sharded handle: csrc/multi.cu - worker thread + stream per GPU, per-GPU top-k merged over
