@@ -332,6 +332,12 @@ int vdb_hnsw_knn(const vdb_dataset* ds, const vdb_hnsw* h, const void* queries, 
 int vdb_hnsw_knn_dev(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queries, uint32_t nq, uint32_t k,
                      uint32_t ef, uint64_t* d_ids, float* d_dist, uint32_t* d_counts, void* stream);
 
+/* Visited sets: the reference's is unbounded (:258-291); here a search keeps it in shared memory up to ef = 896 and in
+ * global memory (4 ef 2M slots per search) beyond. A neighbour that cannot be recorded because a set is 7/8 full would
+ * cost recall, so it is never dropped silently: vdb_hnsw_build / _append / _knn / _knn_pq fail with VDB_EUNSUPPORTED;
+ * after the asynchronous `_dev` searches the count since the last check is read with vdb_hnsw_overflow (must be 0). */
+int vdb_hnsw_overflow(const vdb_hnsw* h, uint32_t* count);
+
 /* IndexPQ::knn_pq on the graph (:672-697): the walk uses ADC distances of the 4-bit codes, all max(ef, k) results
  * are then re-scored exactly and the k best returned (ResultSet::pq_resort, candidate_pair.rs:102-108). */
 int vdb_hnsw_knn_pq(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq, const void* queries, uint32_t nq,

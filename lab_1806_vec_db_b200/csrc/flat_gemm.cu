@@ -716,13 +716,13 @@ static uint32_t kblocks_of(int kind, uint32_t dim) { return ceil_div(dim, kind =
 static int gemm_ctas();
 // tiling of one pass: query-tile units x row slabs (small slabs, query tile fastest: the CTAs in flight share a few
 // row tiles and all query tiles in L2)
-static void plan_gemm(GemmParams& p, int ctas_sel = 0) {
+static void plan_gemm(GemmParams& p, int ctas_sel = 0, uint32_t tps_want = 0) {
     const uint32_t ctas = (uint32_t)(ctas_sel ? ctas_sel : gemm_ctas());
     const uint32_t sms = (uint32_t)sm_count();
     p.ntiles = (uint32_t)ceil_div<uint64_t>(p.nrows, GN);
     p.nqt = ceil_div<uint32_t>(p.nq, GM * ctas);
     static const uint32_t tps_env = getenv("VDB_GEMM_TPS") ? (uint32_t)atoi(getenv("VDB_GEMM_TPS")) : 0;
-    const uint32_t tps = tps_env ? tps_env : 4u;
+    const uint32_t tps = tps_want ? tps_want : (tps_env ? tps_env : 4u);
     p.tiles_per_slab = std::max(1u, std::min(tps, ceil_div(p.ntiles * p.nqt, sms / ctas)));
     p.nslabs = ceil_div(p.ntiles, p.tiles_per_slab);
 }
@@ -1225,7 +1225,17 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     ps.sqnorm = ds->d_sample_sq;
     ps.rnorm = ds->d_sample_rn;
     ps.ex = ds->d_sample_ex;
-    plan_gemm(ps, tq->ctas);
+    // The top-G_TOPJ epilogue pays a warp-wide insertion whenever ANY of its 32 queries sees a new best: ~512 (1 + ln(T / 512))
+    // times per slab of T rows, i.e. on nearly every row of a 1024-row slab but on a quarter of an 8192-row one. Long slabs
+    // (as long as the items still cover the SMs about twice) keep the sample pass near the filter pass's rate per row.
+    static const uint32_t stps_env = getenv("VDB_GEMM_SAMPLE_TPS") ? (uint32_t)atoi(getenv("VDB_GEMM_SAMPLE_TPS")) : 0;
+    uint32_t stps = 4;
+    if (j <= (uint32_t)G_TOPJ) {
+        const uint32_t ntiles = (uint32_t)ceil_div<uint64_t>(ns, GN), nqt = ceil_div(tq->nq, (uint32_t)(GM * tq->ctas));
+        const uint32_t units = (uint32_t)sm_count() / tq->ctas;
+        stps = stps_env ? stps_env : std::max(4u, std::min(32u, (uint32_t)((uint64_t)ntiles * nqt / (2 * units))));
+    }
+    plan_gemm(ps, tq->ctas, stps);
     const uint64_t cnt = (uint64_t)tq->nq * j;
     DevBuf skeys(cnt * 8, st);
     if (j <= (uint32_t)G_TOPJ) {

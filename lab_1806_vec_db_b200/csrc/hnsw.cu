@@ -157,6 +157,8 @@ struct HnswSearchParams {
     uint32_t qrow_base;        // build: query i is row qrow_base + i
     const uint32_t* level;     // build: level of every row
     uint32_t nq, ef, hash_mask;
+    uint32_t* ghash;           // visited sets in GLOBAL memory, one of hash_mask + 1 slots per CTA (large ef); nullptr: shared memory
+    uint32_t* overflow;        // counts neighbours that could not be recorded because a visited set was 7/8 full
     uint32_t enter_point, enter_level;
     int build;
     const uint64_t* out_off;   // build: first list of query i; its list of level l is out_off[i] + l
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearc
     uint64_t* resB = resA + p.ef;                                                // [ef]
     uint64_t* nk = resB + p.ef;                                                  // [32]
     uint32_t* nb = reinterpret_cast<uint32_t*>(nk + 32);                         // [64]
-    uint32_t* hash = nb + 64;                                                    // [hash_mask + 1]
+    uint32_t* hash = p.ghash ? p.ghash + (size_t)blockIdx.x * (p.hash_mask + 1) : nb + 64;   // [hash_mask + 1]
     __shared__ int s_best;
     __shared__ uint32_t s_m, s_hcount, s_cur;
     __shared__ float s_curd;
@@ -302,9 +304,13 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearc
                         const uint32_t j = j0 + lane;
                         bool fresh = false;
                         uint32_t id = 0;
-                        if (j < len && s_hcount + base < hlimit) {
-                            id = lk[j];
-                            fresh = hash_insert(hash, p.hash_mask, id);
+                        if (j < len) {
+                            if (s_hcount + base < hlimit) {
+                                id = lk[j];
+                                fresh = hash_insert(hash, p.hash_mask, id);
+                            } else {
+                                atomicAdd(p.overflow, 1u);   // never silent: the host turns this into an error
+                            }
                         }
                         const uint32_t bal = __ballot_sync(0xffffffffu, fresh);
                         if (fresh) nb[base + __popc(bal & ((1u << lane) - 1))] = id;
@@ -540,10 +546,20 @@ __global__ void iota_pairs_kernel(const uint64_t* __restrict__ keys, uint32_t nq
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
-// visited-set capacity: a search visits ~10-15 nodes per expansion; beyond 7/8 full further neighbours are ignored
-static uint32_t hash_cap_for(uint32_t ef) {
+// Visited-set capacity. The reference's visited set is unbounded (hnsw_index.rs:258-291); here a search records at
+// most 2M nodes per expansion and typically 10-15. Up to ef = 896 the set lives in shared memory (8192 / 16384 / 32768
+// slots); beyond it lives in global memory with 4 ef 2M slots per CTA - room for 3.5 ef expansions of 2M fresh
+// neighbours each before the 7/8 fill limit, which a search that expands about ef entries cannot approach. A neighbour
+// that still cannot be recorded is counted (HnswSearchParams::overflow) and the call fails instead of losing recall.
+constexpr uint32_t HN_SMEM_HASH_MAX_EF = 896;
+static uint32_t hash_cap_for(uint32_t ef, uint32_t M0) {
     static const uint32_t small_to = getenv("VDB_HNSW_SMALL_HASH_EF") ? (uint32_t)atoi(getenv("VDB_HNSW_SMALL_HASH_EF")) : 448u;
-    return ef <= small_to ? 8192u : (ef <= 640 ? 16384u : 32768u);
+    static const uint32_t force = getenv("VDB_HNSW_HASH_SLOTS") ? (uint32_t)atoi(getenv("VDB_HNSW_HASH_SLOTS")) : 0u;   // tests
+    if (force) return next_pow2(force);
+    if (ef <= small_to) return 8192u;
+    if (ef <= 640) return 16384u;
+    if (ef <= HN_SMEM_HASH_MAX_EF) return 32768u;
+    return next_pow2(4u * ef * std::max(M0, 1u));
 }
 
 template <typename KernT, typename ParamT>
@@ -553,16 +569,26 @@ static void launch_dyn(KernT kern, uint32_t grid, size_t smem, const ParamT& p, 
     VDB_LAUNCHED();
 }
 
-static void launch_search(const vdb_dataset* ds, const HnswSearchParams& p, cudaStream_t st) {
+// `overflow` = the handle's device counter (vdb_hnsw::d_overflow)
+static void launch_search(const vdb_dataset* ds, const HnswSearchParams& p, uint32_t* overflow, cudaStream_t st) {
     const bool pq = p.codes != nullptr;
     const size_t vec_floats = pq ? (size_t)p.m * 16 * (ds->metric == VDB_COSINE ? 2 : 1) : (size_t)p.dimpad;
-    const size_t smem = round_up(vec_floats, (size_t)4) * 4 + (size_t)p.ef * 16 + 32 * 8 + 64 * 4 + (size_t)(p.hash_mask + 1) * 4;
+    const uint32_t slots = p.hash_mask + 1;
+    const bool global_hash = slots > 32768u;
+    const size_t smem = round_up(vec_floats, (size_t)4) * 4 + (size_t)p.ef * 16 + 32 * 8 + 64 * 4 + (global_hash ? 0 : (size_t)slots * 4);
     VDB_REQUIRE(smem <= 200 * 1024, "HNSW search: ef=%u / dim=%u do not fit in shared memory", p.ef, p.dim);
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
-    const uint32_t grid = std::min<uint32_t>(p.nq, (uint32_t)sm_count() * per_sm);
+    uint32_t grid = std::min<uint32_t>(p.nq, (uint32_t)sm_count() * per_sm);
+    DevBuf ghash;
+    if (global_hash) {   // bound the tables to 1 GiB
+        grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, (1ull << 30) / ((uint64_t)slots * 4)));
+        ghash = DevBuf((size_t)grid * slots * 4, st);
+    }
     ProfScope prof("hnsw_search", st);
     const bool l2 = ds->metric == VDB_L2SQR;
     HnswSearchParams q = p;
+    q.ghash = ghash.as<uint32_t>();
+    q.overflow = overflow;
     if (pq) q.dimpad = (uint32_t)round_up(vec_floats, (size_t)4);  // the kernel's vector area holds the tables
     if (pq) {
         if (l2) launch_dyn(hnsw_search_kernel<uint8_t, VDB_L2SQR, true>, grid, smem, q, st);
@@ -573,6 +599,20 @@ static void launch_search(const vdb_dataset* ds, const HnswSearchParams& p, cuda
     } else {
         if (l2) launch_dyn(hnsw_search_kernel<uint8_t, VDB_L2SQR, false>, grid, smem, q, st);
         else launch_dyn(hnsw_search_kernel<uint8_t, VDB_COSINE, false>, grid, smem, q, st);
+    }
+}
+
+// A search that could not record a neighbour in its visited set may have lost recall: fail loudly (reads and clears the
+// handle's counter; the stream is synchronised)
+void hnsw_check_overflow(const vdb_hnsw* h, cudaStream_t st) {
+    if (!h->d_overflow) return;
+    uint32_t v = 0;
+    VDB_CUDA(cudaMemcpyAsync(&v, h->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    VDB_CUDA(cudaStreamSynchronize(st));
+    if (v) {
+        VDB_CUDA(cudaMemsetAsync(h->d_overflow, 0, 4, st));
+        fail(VDB_EUNSUPPORTED, "HNSW: the visited set of a search overflowed (%u neighbours could not be recorded); results "
+                               "would lose recall, so the call fails - lower ef", v);
     }
 }
 
@@ -597,6 +637,7 @@ void hnsw_destroy(vdb_hnsw* h) {
     cudaFree(h->d_uoff);
     cudaFree(h->d_level);
     cudaFree(h->d_cache);
+    cudaFree(h->d_overflow);
     delete h;
 }
 
@@ -630,6 +671,8 @@ static void hnsw_alloc(vdb_hnsw* h, const vdb_dataset* ds, uint32_t M, uint32_t 
     VDB_CUDA(cudaMalloc(&h->d_uoff, (n + 1) * 8));
     VDB_CUDA(cudaMalloc(&h->d_level, std::max<uint64_t>(n, 1) * 4));
     VDB_CUDA(cudaMalloc(&h->d_cache, std::max<uint64_t>(n, 1) * 4));
+    VDB_CUDA(cudaMalloc(&h->d_overflow, 4));
+    VDB_CUDA(cudaMemsetAsync(h->d_overflow, 0, 4, st));
     VDB_CUDA(cudaMemsetAsync(h->d_links0, 0, std::max<uint64_t>(n, 1) * h->M0 * 4, st));
     VDB_CUDA(cudaMemsetAsync(h->d_ulinks, 0, slots * M * 4, st));
     VDB_CUDA(cudaMemsetAsync(h->d_len0, 0, std::max<uint64_t>(n, 1) * 4, st));
@@ -739,13 +782,13 @@ static void hnsw_insert_range(vdb_hnsw* h, const vdb_dataset* ds, uint64_t first
             sp.level = h->d_level;
             sp.nq = b;
             sp.ef = ef;
-            sp.hash_mask = hash_cap_for(ef) - 1;
+            sp.hash_mask = hash_cap_for(ef, h->M0) - 1;
             sp.enter_point = (uint32_t)h->enter_point;
             sp.enter_level = (uint32_t)h->enter_level;
             sp.build = 1;
             sp.out_off = d_out_off.as<uint64_t>();
             sp.out_keys = d_cand.as<uint64_t>();
-            launch_search(ds, sp, st);
+            launch_search(ds, sp, h->d_overflow, st);
             // 2. connect_new_links: heuristic(M) -> links of the new nodes
             HnswSelectParams sl{};
             sl.g = graph_of(h);
@@ -850,6 +893,7 @@ vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction
         VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         hnsw_alloc(h, ds, M, ef_construction, h_levels, st);
         hnsw_insert_range(h, ds, 0, max_batch, st);
+        hnsw_check_overflow(h, st);
         cudaStreamDestroy(st);
     } catch (...) {
         if (st) cudaStreamDestroy(st);
@@ -868,40 +912,55 @@ void hnsw_append(vdb_hnsw* h, const vdb_dataset* ds, const uint32_t* new_levels,
     cudaStream_t st = nullptr;
     VDB_CUDA(cudaSetDevice(ds->device));
     VDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    vdb_hnsw old = *h;  // device arrays of the old graph; the handle is re-pointed to larger ones below
+    // The grown graph is assembled in a TEMPORARY handle and swapped into *h only once every allocation and copy has
+    // succeeded: on failure (growing a large graph while the old one is resident makes out-of-memory plausible) the
+    // caller's handle still describes the old, intact graph and nothing leaks.
+    auto free_arrays = [](vdb_hnsw& g) {
+        cudaFree(g.d_links0);
+        cudaFree(g.d_len0);
+        cudaFree(g.d_ulinks);
+        cudaFree(g.d_ulen);
+        cudaFree(g.d_uoff);
+        cudaFree(g.d_level);
+        cudaFree(g.d_cache);
+        cudaFree(g.d_overflow);
+        g.d_links0 = g.d_len0 = g.d_ulinks = g.d_ulen = g.d_level = g.d_overflow = nullptr;
+        g.d_uoff = nullptr;
+        g.d_cache = nullptr;
+    };
+    vdb_hnsw grown = *h;   // scalars (enter point, M, ...) carried over; the array pointers are replaced by hnsw_alloc
+    grown.d_links0 = grown.d_len0 = grown.d_ulinks = grown.d_ulen = grown.d_level = grown.d_overflow = nullptr;
+    grown.d_uoff = nullptr;
+    grown.d_cache = nullptr;
     try {
         const uint64_t n0 = h->n, n = ds->n;
         std::vector<uint32_t> levels = h->h_level;
         levels.insert(levels.end(), new_levels, new_levels + (n - n0));
-        h->d_links0 = h->d_len0 = h->d_ulinks = h->d_ulen = h->d_level = nullptr;
-        h->d_uoff = nullptr;
-        h->d_cache = nullptr;
-        const uint64_t old_slots = old.slots;
-        hnsw_alloc(h, ds, old.M, old.ef_construction, levels.data(), st);
+        const uint64_t old_slots = h->slots;
+        hnsw_alloc(&grown, ds, h->M, h->ef_construction, levels.data(), st);
         // nodes keep their ids and the upper-level slots of old nodes keep their positions (prefix sums only grow)
         if (n0) {
-            VDB_CUDA(cudaMemcpyAsync(h->d_links0, old.d_links0, n0 * h->M0 * 4, cudaMemcpyDeviceToDevice, st));
-            VDB_CUDA(cudaMemcpyAsync(h->d_len0, old.d_len0, n0 * 4, cudaMemcpyDeviceToDevice, st));
+            VDB_CUDA(cudaMemcpyAsync(grown.d_links0, h->d_links0, n0 * h->M0 * 4, cudaMemcpyDeviceToDevice, st));
+            VDB_CUDA(cudaMemcpyAsync(grown.d_len0, h->d_len0, n0 * 4, cudaMemcpyDeviceToDevice, st));
             if (old_slots) {
-                VDB_CUDA(cudaMemcpyAsync(h->d_ulinks, old.d_ulinks, old_slots * h->M * 4, cudaMemcpyDeviceToDevice, st));
-                VDB_CUDA(cudaMemcpyAsync(h->d_ulen, old.d_ulen, old_slots * 4, cudaMemcpyDeviceToDevice, st));
+                VDB_CUDA(cudaMemcpyAsync(grown.d_ulinks, h->d_ulinks, old_slots * h->M * 4, cudaMemcpyDeviceToDevice, st));
+                VDB_CUDA(cudaMemcpyAsync(grown.d_ulen, h->d_ulen, old_slots * 4, cudaMemcpyDeviceToDevice, st));
             }
         }
         VDB_CUDA(cudaStreamSynchronize(st));
-        cudaFree(old.d_links0);
-        cudaFree(old.d_len0);
-        cudaFree(old.d_ulinks);
-        cudaFree(old.d_ulen);
-        cudaFree(old.d_uoff);
-        cudaFree(old.d_level);
-        cudaFree(old.d_cache);
-        old.d_links0 = nullptr;
-        hnsw_insert_range(h, ds, n0, max_batch, st);
-        cudaStreamDestroy(st);
+        hnsw_insert_range(&grown, ds, n0, max_batch, st);
+        VDB_CUDA(cudaStreamSynchronize(st));
+        hnsw_check_overflow(&grown, st);
     } catch (...) {
+        cudaStreamSynchronize(st);
+        free_arrays(grown);
         cudaStreamDestroy(st);
         throw;
     }
+    vdb_hnsw old = *h;
+    *h = grown;            // commit
+    free_arrays(old);
+    cudaStreamDestroy(st);
 }
 
 // the k best by (cached-form distance, id) of the first `take` entries of every [ef] candidate list
@@ -951,12 +1010,12 @@ void hnsw_knn_keys(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_queri
     sp.qcache = qcache.as<float>();
     sp.nq = nq;
     sp.ef = ef;
-    sp.hash_mask = hash_cap_for(ef) - 1;
+    sp.hash_mask = hash_cap_for(ef, h->M0) - 1;
     sp.enter_point = (uint32_t)h->enter_point;
     sp.enter_level = (uint32_t)h->enter_level;
     sp.build = 0;
     sp.out_keys = cand.as<uint64_t>();
-    launch_search(ds, sp, st);
+    launch_search(ds, sp, h->d_overflow, st);
     // into_sorted_vec_limit(k): the k best of the ef results
     exact_topk_of(ds, h, d_queries, qcache.as<float>(), cand.as<uint64_t>(), nq, ef, k, d_keys, st, k);
 }
@@ -994,7 +1053,7 @@ void hnsw_knn_pq_keys(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq
     sp.qcache = qn.as<float>();  // cosine: ||q|| of the lookup table (pq_table.rs:215-221)
     sp.nq = nq;
     sp.ef = ef;
-    sp.hash_mask = hash_cap_for(ef) - 1;
+    sp.hash_mask = hash_cap_for(ef, h->M0) - 1;
     sp.enter_point = (uint32_t)h->enter_point;
     sp.enter_level = (uint32_t)h->enter_level;
     sp.build = 0;
@@ -1004,7 +1063,7 @@ void hnsw_knn_pq_keys(const vdb_dataset* ds, const vdb_hnsw* h, const vdb_pq* pq
     sp.m = pq->m;
     sp.lut = lut.as<float>();
     sp.dcache = pq->d_dist_cache;
-    launch_search(ds, sp, st);
+    launch_search(ds, sp, h->d_overflow, st);
     exact_topk_of(ds, h, d_queries, qcache.as<float>(), cand.as<uint64_t>(), nq, ef, k, d_keys, st);
 }
 

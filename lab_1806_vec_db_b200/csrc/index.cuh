@@ -65,6 +65,7 @@ struct vdb_hnsw {
     uint64_t slots = 0;                // sum of the node levels
     uint32_t* d_level = nullptr;       // [n]
     float* d_cache = nullptr;          // dist_cache [n]
+    uint32_t* d_overflow = nullptr;    // neighbours a search could not record in its visited set (must stay 0)
     int64_t enter_point = -1;
     int enter_level = -1;
 };
@@ -74,6 +75,7 @@ namespace vdb {
 // hnsw.cu
 vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch);
 void hnsw_destroy(vdb_hnsw* h);
+void hnsw_check_overflow(const vdb_hnsw* h, cudaStream_t st);
 void hnsw_append(vdb_hnsw* h, const vdb_dataset* ds, const uint32_t* new_levels, uint32_t max_batch);
 vdb_hnsw* hnsw_from_graph(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels,
                           const uint32_t* links0, const uint32_t* len0, const uint32_t* ulinks, const uint32_t* ulen,

@@ -244,3 +244,82 @@ def test_hnsw_incremental_add_matches_one_shot_build(V, fixtures, oracle):
     assert recall(idx.knn_with_ef_batch(test, 10, 100)[0], gt) >= 0.99
     links, lens = idx.level0_links()
     check_graph(links, lens, 1000, 16)
+
+
+def test_large_ef_uses_the_global_visited_set_and_matches_the_oracle_on_the_same_graph(V, oracle):
+    """ef >= 2048: at ~10 fresh nodes per expansion a shared-memory visited set (28 672 usable slots) would fill up and
+    silently drop neighbours; the set now lives in global memory for ef > 896. Parity is checked the strong way: the
+    oracle's knn_with_ef walks the VERY graph the GPU built (orc_hnsw_from_graph), so both searches must return the same
+    ids (up to near-ties of the cached-form distance), and no search may have overflowed."""
+    import ctypes as C
+    from oracle.oracle_py import HnswOracle
+    rng = np.random.default_rng(21)
+    n, dim, M = 30_000, 48, 16
+    base = rng.random((n, dim), dtype=np.float32)
+    q = rng.random((40, dim), dtype=np.float32)
+    vs = V.DeviceVecSet(base, "l2sqr")
+    idx = V.HNSWIndex(vs, V.HNSWConfig(0, 200, M), rng=np.random.default_rng(3))
+    links0, len0 = idx.level0_links()
+    levels, ulinks, ulen = idx.upper_links()
+    ep, el = idx.enter_point
+    cpu = HnswOracle.from_graph(base, "l2sqr", M, 200, levels, links0, len0, ulinks, ulen, ep, el)
+    gt = V.FlatIndex(vs).knn_batch(q, 10)[0]
+    for ef in (64, 2048, 4096):
+        ids, dd, cnt = idx.knn_with_ef_batch(q, 10, ef)
+        oi, od, _ = cpu.knn(q, 10, ef, nthreads=8)
+        same = (ids.astype(np.int64) == oi.astype(np.int64))
+        assert same.mean() >= 0.98, (ef, float(same.mean()))
+        assert np.allclose(dd, od, rtol=1e-4, atol=1e-5)
+        if ef >= 2048:
+            assert recall(ids, gt) >= 0.999      # ef far above k on 30k rows: the walk reaches every true neighbour
+    ov = C.c_uint32(7)
+    V._lib.check(V.lib().vdb_hnsw_overflow(idx._h, C.byref(ov)))
+    assert ov.value == 0
+
+
+def test_a_full_visited_set_is_an_error_not_a_silent_loss(V, monkeypatch):
+    """With the visited set forced down to 64 slots every search overflows: the host call must FAIL (VDB_EUNSUPPORTED)."""
+    monkeypatch.setenv("VDB_HNSW_HASH_SLOTS", "64")
+    import subprocess, sys, textwrap, os
+    # the override is read once per process: run the failing search in a child
+    code = textwrap.dedent("""
+        import numpy as np, sys
+        sys.path.insert(0, %r)
+        import lab_1806_vec_db_b200 as V
+        rng = np.random.default_rng(22)
+        base = rng.random((5000, 32), dtype=np.float32)
+        try:
+            idx = V.HNSWIndex(V.DeviceVecSet(base, "l2sqr"), V.HNSWConfig(0, 40, 8), rng=np.random.default_rng(1))
+            idx.knn_with_ef_batch(base[:4], 5, 100)
+        except V.VdbError as e:
+            assert e.code == 4 and "visited set" in str(e), e
+            print("raised")
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "raised" in r.stdout, r.stdout + r.stderr
+
+
+def test_append_leaves_the_index_intact_when_it_fails(V):
+    """vdb_hnsw_append builds the grown graph aside and swaps it in only on success (a failed cudaMalloc must not
+    leave the handle with dangling or null arrays): a rejected append - here a bad level table - keeps the old graph
+    searchable and bit-identical."""
+    rng = np.random.default_rng(23)
+    base = rng.random((4000, 24), dtype=np.float32)
+    vs = V.DeviceVecSet(base[:3000], "l2sqr")
+    idx = V.HNSWIndex(vs, V.HNSWConfig(0, 60, 8), rng=np.random.default_rng(2))
+    before = idx.knn_with_ef_batch(base[:16], 5, 50)
+    l0 = idx.level0_links()
+    vs.push(base[3000:])
+    bad = np.full(1000, 200, np.uint32)                        # level 200 is out of range: hnsw_alloc rejects it
+    rc = V.lib().vdb_hnsw_append(idx._h, vs._h, V._lib.ptr(bad), 256)
+    assert rc != 0
+    n = V._lib.C.c_uint64(0)
+    V._lib.check(V.lib().vdb_hnsw_info(idx._h, V._lib.C.byref(n), None, None, None, None))
+    assert n.value == 3000                                     # the handle still describes the old graph
+    links = np.zeros((3000, 16), np.uint32); lens = np.zeros(3000, np.uint32)
+    V._lib.check(V.lib().vdb_hnsw_links0(idx._h, V._lib.ptr(links), V._lib.ptr(lens)))
+    assert (links == l0[0]).all() and (lens == l0[1]).all()
+    good = V.hnsw_rand_levels(1000, 8, np.random.default_rng(4))
+    V._lib.check(V.lib().vdb_hnsw_append(idx._h, vs._h, V._lib.ptr(good), 256))   # and a proper append still works
+    V._lib.check(V.lib().vdb_hnsw_info(idx._h, V._lib.C.byref(n), None, None, None, None))
+    assert n.value == 4000
