@@ -22,6 +22,7 @@ struct vdb_pq {
     uint32_t* d_sample_t = nullptr; // the same layout for a stratified random row sample (thresholds of the scan)
     uint8_t* d_sample = nullptr;    // the sampled code rows in the reference layout [sample_n][enc] (tensor-core sample pass)
     uint32_t sample_n = 0;
+    std::vector<vdb_pq*> shards;    // row-sharded parent (multi.cu): one table per shard, the arrays above stay empty
 };
 
 // device mirror of IVFIndex<T> (reference src/index_algorithm/ivf_index.rs:34-47)
@@ -47,6 +48,8 @@ struct vdb_ivf {
     float* d_samp_colA = nullptr, *d_samp_rn = nullptr, *d_samp_ex = nullptr;
     std::vector<uint64_t> h_samp_off;  // [nlist+1]
     uint64_t samp_n = 0;
+    std::vector<vdb_ivf*> shards;      // row-sharded parent (multi.cu): one index per shard, the arrays above stay empty
+    const struct vdb_dataset* parent = nullptr;   // the sharded dataset it was built on
 };
 
 // device mirror of HNSWIndex<T> (reference src/index_algorithm/hnsw_index.rs:99-141)
@@ -71,6 +74,16 @@ struct vdb_hnsw {
 };
 
 namespace vdb {
+
+// multi.cu: IVF / PQ on a row-sharded dataset
+vdb_ivf* sharded_ivf_create(const vdb_dataset* md, const void* h_centroids, uint32_t nlist, uint32_t* h_assign_out);
+void sharded_ivf_lists(const vdb_dataset* md, const vdb_ivf* ivf, uint64_t* offsets, uint32_t* members);
+void sharded_ivf_knn(const vdb_dataset* md, const vdb_ivf* ivf, const void* queries, uint32_t nq, uint32_t k, uint32_t n_probes,
+                     uint64_t* ids, float* dist, uint32_t* counts);
+vdb_pq* sharded_pq_create(const vdb_dataset* md, const void* h_codebooks, uint32_t m, uint32_t n_bits, const uint8_t* h_codes_in,
+                          uint8_t* h_codes_out);
+void sharded_pq_knn(const vdb_dataset* md, const vdb_pq* pq, const void* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                    uint64_t* ids, float* dist, uint32_t* counts);
 
 // hnsw.cu
 vdb_hnsw* hnsw_build(const vdb_dataset* ds, uint32_t M, uint32_t ef_construction, const uint32_t* h_levels, uint32_t max_batch);

@@ -414,8 +414,11 @@ static void ensure_tensor_facts(const vdb_dataset* md) {
     S->tensor_known = true;
 }
 
-// one chunk of at most SHARD_QUERY_CHUNK queries
-static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int path) {
+// shard-local search of a single-exchange call (IVF): enqueues [nq, k] ascending keys for shard s on `st`
+using KeyProducer = std::function<void(uint32_t s, const void* d_q, uint32_t nq, uint32_t k, uint64_t* d_keys, cudaStream_t st)>;
+
+// one chunk of at most SHARD_QUERY_CHUNK queries. producer == nullptr: Flat (tensor phases or exact scan per shard)
+static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int path, const KeyProducer* producer = nullptr) {
     vdb_sharded_state* S = md->sharded;
     const uint32_t G = (uint32_t)S->shards.size();
     const uint32_t nq = a.nq, k = a.k;
@@ -427,7 +430,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
         *hi = std::min(nq, (h + 1) * per);
     };
     bool tensor = false;
-    if (path != 1 && k >= 1 && k <= 1024 && (path == 2 || nq >= SHARD_TENSOR_MIN_NQ)) {
+    if (!producer && path != 1 && k >= 1 && k <= 1024 && (path == 2 || nq >= SHARD_TENSOR_MIN_NQ)) {
         ensure_tensor_facts(md);
         tensor = S->tensor_ok;
         VDB_REQUIRE(tensor || path != 2, "tensor-core Flat path needs f32/u8 shards of at least 65536 rows and k <= 1024");
@@ -545,6 +548,8 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
             tensor_filter_keys(tqs[s], k, 0, L.tau.as<float>(), L.keys.as<uint64_t>(), L.ovf.as<uint32_t>(),
                                L.ctotal.as<uint64_t>());
             VDB_CUDA(cudaMemcpyAsync(sh.h_stat, L.ctotal.p, 8, cudaMemcpyDeviceToHost, sh.st));
+        } else if (producer) {
+            (*producer)(s, qptr[s], nq, k, L.keys.as<uint64_t>(), sh.st);
         } else {
             flat_scan_keys(sh.ds, qptr[s], nq, k, L.keys.as<uint64_t>(), sh.st);
         }
@@ -726,6 +731,235 @@ void sharded_flat_knn_dev(const vdb_dataset* md, const void* const* d_queries, u
     a.d_dist = d_dist;
     a.d_counts = d_counts;
     sharded_flat_chunk(md, a, effective_path(md));
+}
+
+// ---- row-sharded IVF: centroids replicated, every shard holds its slice of every list -------------------
+vdb_ivf* sharded_ivf_create(const vdb_dataset* md, const void* h_centroids, uint32_t nlist, uint32_t* h_assign_out) {
+    vdb_sharded_state* S = md->sharded;
+    auto ivf = new vdb_ivf();
+    ivf->device = md->device;
+    ivf->nlist = nlist;
+    ivf->dim = md->dim;
+    ivf->dtype = md->dtype;
+    ivf->metric = md->metric;
+    ivf->n = md->n;
+    ivf->parent = md;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    try {
+        for (auto& sh : S->shards) {
+            VDB_CUDA(cudaSetDevice(sh.device));
+            ivf->shards.push_back(ivf_create(sh.ds, h_centroids, nlist, h_assign_out ? h_assign_out + sh.lo : nullptr));
+        }
+    } catch (...) {
+        for (size_t i = 0; i < ivf->shards.size(); ++i) {
+            cudaSetDevice(S->shards[i].device);
+            ivf_destroy(ivf->shards[i]);
+        }
+        cudaSetDevice(prev);
+        delete ivf;
+        throw;
+    }
+    cudaSetDevice(prev);
+    return ivf;
+}
+
+// the global lists: list l = the shards' slices of l in shard order (members ascending: shards are contiguous row blocks)
+void sharded_ivf_lists(const vdb_dataset* md, const vdb_ivf* ivf, uint64_t* offsets, uint32_t* members) {
+    vdb_sharded_state* S = md->sharded;
+    const uint32_t G = (uint32_t)S->shards.size(), nlist = ivf->nlist;
+    std::vector<std::vector<uint64_t>> off(G, std::vector<uint64_t>(nlist + 1));
+    std::vector<std::vector<uint32_t>> mem(G);
+    int prev = 0;
+    VDB_CUDA(cudaGetDevice(&prev));
+    for (uint32_t s = 0; s < G; ++s) {
+        const vdb_ivf* sv = ivf->shards[s];
+        VDB_CUDA(cudaSetDevice(S->shards[s].device));
+        VDB_CUDA(cudaMemcpy(off[s].data(), sv->d_offsets, (size_t)(nlist + 1) * 8, cudaMemcpyDeviceToHost));
+        mem[s].resize(sv->n);
+        if (sv->n) VDB_CUDA(cudaMemcpy(mem[s].data(), sv->d_members, sv->n * 4, cudaMemcpyDeviceToHost));
+    }
+    VDB_CUDA(cudaSetDevice(prev));
+    uint64_t at = 0;
+    for (uint32_t l = 0; l < nlist; ++l) {
+        offsets[l] = at;
+        for (uint32_t s = 0; s < G; ++s)
+            for (uint64_t i = off[s][l]; i < off[s][l + 1]; ++i) members[at++] = (uint32_t)(S->shards[s].lo + mem[s][i]);
+    }
+    offsets[nlist] = at;
+}
+
+// IndexKNNWithEf::knn_with_ef on the sharded set: every shard probes its slices of the n_probes nearest lists, the
+// per-shard [nq, k] keys are merged by (distance, global id) on the queries' owners
+void sharded_ivf_knn(const vdb_dataset* md, const vdb_ivf* ivf, const void* queries, uint32_t nq, uint32_t k, uint32_t n_probes,
+                     uint64_t* ids, float* dist, uint32_t* counts) {
+    vdb_sharded_state* S = md->sharded;
+    if (nq == 0) return;
+    if (k == 0) {
+        memset(counts, 0, (size_t)nq * 4);
+        return;
+    }
+    VDB_REQUIRE(ivf->shards.size() == S->shards.size(), "IVF index was not built on this sharded set");
+    std::lock_guard<std::mutex> lk(S->call_mu);
+    const size_t rb = (size_t)md->dim * md->elem_size();
+    KeyProducer prod = [&](uint32_t s, const void* d_q, uint32_t n, uint32_t kk, uint64_t* d_keys, cudaStream_t st) {
+        ivf_knn_keys(S->shards[s].ds, ivf->shards[s], d_q, n, kk, n_probes, d_keys, st);
+    };
+    for (uint32_t q0 = 0; q0 < nq; q0 += SHARD_QUERY_CHUNK) {
+        FlatCallArgs a;
+        a.nq = std::min(SHARD_QUERY_CHUNK, nq - q0);
+        a.k = k;
+        a.h_queries = (const uint8_t*)queries + (size_t)q0 * rb;
+        a.h_ids = ids + (size_t)q0 * k;
+        a.h_dist = dist + (size_t)q0 * k;
+        a.h_counts = counts + q0;
+        sharded_flat_chunk(md, a, 1, &prod);
+    }
+}
+
+// ---- row-sharded PQ -------------------------------------------------------------------------------------
+vdb_pq* sharded_pq_create(const vdb_dataset* md, const void* h_codebooks, uint32_t m, uint32_t n_bits, const uint8_t* h_codes_in,
+                          uint8_t* h_codes_out) {
+    vdb_sharded_state* S = md->sharded;
+    auto pq = new vdb_pq();
+    pq->device = md->device;
+    pq->dim = md->dim;
+    pq->dtype = md->dtype;
+    pq->metric = md->metric;
+    pq->n = md->n;
+    pq->m = m;
+    pq->n_bits = n_bits;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    try {
+        for (auto& sh : S->shards) {
+            VDB_CUDA(cudaSetDevice(sh.device));
+            const size_t enc = n_bits == 4 ? (m + 1) / 2 : m;
+            pq->shards.push_back(pq_create(sh.ds, h_codebooks, m, n_bits, h_codes_in ? h_codes_in + sh.lo * enc : nullptr,
+                                           h_codes_out ? h_codes_out + sh.lo * enc : nullptr));
+            pq->enc = pq->shards.back()->enc;
+            pq->kc = pq->shards.back()->kc;
+        }
+    } catch (...) {
+        for (size_t i = 0; i < pq->shards.size(); ++i) {
+            cudaSetDevice(S->shards[i].device);
+            pq_destroy(pq->shards[i]);
+        }
+        cudaSetDevice(prev);
+        delete pq;
+        throw;
+    }
+    cudaSetDevice(prev);
+    return pq;
+}
+
+// IndexPQ::knn_pq for FlatIndex on the sharded set, identical to the unsharded call: (1) every shard's max(ef, k) best
+// codes by (ADC, global id) go to the queries' owners, (2) the owners merge them into the GLOBAL top-max(ef, k) and
+// peer-store their slice of it into every shard, (3) every shard reranks exactly the candidates it owns, (4) the [nq, k]
+// keys are merged on the owners.
+void sharded_pq_knn(const vdb_dataset* md, const vdb_pq* pq, const void* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                    uint64_t* ids, float* dist, uint32_t* counts) {
+    vdb_sharded_state* S = md->sharded;
+    if (nq == 0) return;
+    if (k == 0) {
+        memset(counts, 0, (size_t)nq * 4);
+        return;
+    }
+    VDB_REQUIRE(pq->shards.size() == S->shards.size(), "PQ table was not built on this sharded set");
+    VDB_REQUIRE(nq <= SHARD_QUERY_CHUNK, "sharded knn_pq: at most %u queries per call", SHARD_QUERY_CHUNK);
+    std::lock_guard<std::mutex> lk(S->call_mu);
+    const uint32_t G = (uint32_t)S->shards.size(), kk = std::max(ef, k);
+    const size_t rb = (size_t)md->dim * md->elem_size();
+    const uint32_t per = ceil_div(nq, G);
+    auto slice = [&](uint32_t h, uint32_t* lo, uint32_t* hi) {
+        *lo = std::min(nq, h * per);
+        *hi = std::min(nq, (h + 1) * per);
+    };
+    {
+        int prev = 0;
+        VDB_CUDA(cudaGetDevice(&prev));
+        for (uint32_t s = 0; s < G; ++s) {
+            Shard& sh = S->shards[s];
+            uint32_t lo, hi;
+            slice(s, &lo, &hi);
+            const uint32_t cnt = std::max(hi - lo, 1u);
+            VDB_CUDA(cudaSetDevice(sh.device));
+            sh.q_all.ensure((size_t)nq * rb);
+            sh.kin.ensure((size_t)G * cnt * kk * 8);
+            sh.jall.ensure((size_t)nq * kk * 8);          // the global candidate lists, written by the owners
+            sh.out_ids.ensure((size_t)cnt * k * 8);
+            sh.out_dist.ensure((size_t)cnt * k * 4);
+            sh.out_cnt.ensure((size_t)cnt * 4);
+        }
+        VDB_CUDA(cudaSetDevice(prev));
+    }
+    std::vector<DevBuf> keys(G), merged(G);
+    std::vector<std::function<void(uint32_t)>> ph;
+    ph.push_back([&](uint32_t s) {   // queries: every shard uploads the batch (knn_pq batches are small next to the code scan)
+        Shard& sh = S->shards[s];
+        VDB_CUDA(cudaMemcpyAsync(sh.q_all.p, queries, (size_t)nq * rb, cudaMemcpyHostToDevice, sh.st));
+        keys[s] = DevBuf((size_t)nq * kk * 8, sh.st);
+        pq_adc_keys(sh.ds, pq->shards[s], sh.q_all.p, nq, kk, keys[s].as<uint64_t>(), sh.st);
+        PtrList dk{}, df{};
+        for (uint32_t h = 0; h < G; ++h) {
+            uint32_t lo, hi;
+            slice(h, &lo, &hi);
+            dk.p[h] = (uint8_t*)S->shards[h].kin.p + (size_t)s * std::max(hi - lo, 1u) * kk * 8;
+        }
+        scatter_owner_kernel<<<nq, 128, 0, sh.st>>>(keys[s].as<uint64_t>(), nullptr, nq, kk, per, dk, df);
+        VDB_LAUNCHED();
+        VDB_CUDA(cudaEventRecord(sh.ev[EV_S], sh.st));
+    });
+    ph.push_back([&](uint32_t s) {   // owners: global top-kk of their queries, peer-stored into every shard
+        Shard& sh = S->shards[s];
+        wait_peers(S, s, EV_S);
+        uint32_t lo, hi;
+        slice(s, &lo, &hi);
+        const uint32_t cnt = hi - lo;
+        if (cnt) {
+            merged[s] = DevBuf((size_t)cnt * kk * 8, sh.st);
+            launch_merge_sorted((const uint64_t*)sh.kin.p, G, cnt, kk, kk, merged[s].as<uint64_t>(), nullptr, nullptr, nullptr, sh.st);
+            PtrList dst{};
+            for (uint32_t h = 0; h < G; ++h) dst.p[h] = (uint8_t*)S->shards[h].jall.p + (size_t)lo * kk * 8;
+            bcast(merged[s].p, (size_t)cnt * kk * 8, dst, G, sh.st);
+        }
+        VDB_CUDA(cudaEventRecord(sh.ev[EV_Q], sh.st));
+    });
+    ph.push_back([&](uint32_t s) {   // exact rerank of the candidates this shard owns
+        Shard& sh = S->shards[s];
+        wait_peers(S, s, EV_Q);
+        keys[s] = DevBuf((size_t)nq * k * 8, sh.st);
+        rerank_keys(sh.ds, sh.q_all.p, nq, (const uint64_t*)sh.jall.p, kk, k, keys[s].as<uint64_t>(), sh.st);
+        PtrList dk{}, df{};
+        for (uint32_t h = 0; h < G; ++h) {
+            uint32_t lo, hi;
+            slice(h, &lo, &hi);
+            dk.p[h] = (uint8_t*)S->shards[h].kin.p + (size_t)s * std::max(hi - lo, 1u) * k * 8;
+        }
+        // kin is reused for the second exchange: every shard has finished reading its first contents (it waited for
+        // EV_Q of all peers, which they record after their merge of phase 2)
+        scatter_owner_kernel<<<nq, 128, 0, sh.st>>>(keys[s].as<uint64_t>(), nullptr, nq, k, per, dk, df);
+        VDB_LAUNCHED();
+        VDB_CUDA(cudaEventRecord(sh.ev[EV_F], sh.st));
+    });
+    ph.push_back([&](uint32_t s) {
+        Shard& sh = S->shards[s];
+        wait_peers(S, s, EV_F);
+        uint32_t lo, hi;
+        slice(s, &lo, &hi);
+        const uint32_t cnt = hi - lo;
+        if (cnt) {
+            launch_merge_sorted((const uint64_t*)sh.kin.p, G, cnt, k, k, nullptr, (uint64_t*)sh.out_ids.p, (float*)sh.out_dist.p,
+                                (uint32_t*)sh.out_cnt.p, sh.st);
+            VDB_CUDA(cudaMemcpyAsync(ids + (size_t)lo * k, sh.out_ids.p, (size_t)cnt * k * 8, cudaMemcpyDeviceToHost, sh.st));
+            VDB_CUDA(cudaMemcpyAsync(dist + (size_t)lo * k, sh.out_dist.p, (size_t)cnt * k * 4, cudaMemcpyDeviceToHost, sh.st));
+            VDB_CUDA(cudaMemcpyAsync(counts + lo, sh.out_cnt.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sh.st));
+        }
+        keys[s] = DevBuf();
+        merged[s] = DevBuf();
+        VDB_CUDA(cudaStreamSynchronize(sh.st));
+    });
+    run_job(S, ph);
 }
 
 uint32_t sharded_count(const vdb_dataset* md) { return md->sharded ? (uint32_t)md->sharded->shards.size() : 0; }

@@ -31,11 +31,13 @@ DIST_TOML = {"L2Sqr": "l2sqr", "Cosine": "cosine"}
 # ---- raw vectors / fvecs --------------------------------------------------------------------------------------
 def load_raw(path, dim, dtype=np.float32, limit=None):
     """BinaryScalar::from_binary_file (scalar.rs:89-98) + VecDataConfig.limit (config.rs:31-52)."""
-    a = np.fromfile(path, dtype=np.dtype(dtype).newbyteorder("<"))
+    # the reference reads min(limit * dim, file scalars) SCALARS (file_size_limit, scalar.rs:78-82) and only then checks
+    # the row multiple (vec_set.rs:35-38): a trailing partial row beyond the limit is never looked at
+    count = -1 if limit is None else int(limit) * int(dim)
+    a = np.fromfile(path, dtype=np.dtype(dtype).newbyteorder("<"), count=count)
     if a.size % dim:
         raise ValueError("The length of the data is not a multiple of the dimension.")
-    a = a.reshape(-1, dim)
-    return np.ascontiguousarray(a[:limit] if limit is not None else a, dtype=dtype)
+    return np.ascontiguousarray(a.reshape(-1, dim), dtype=dtype)
 
 
 def save_raw(path, rows):

@@ -81,10 +81,10 @@ def assert_knn_parity(base, queries, metric, got, want, oracle, rtol=RTOL, atol=
 
 
 def have_gpu():
-    try:
-        import ctypes as C
-        from lab_1806_vec_db_b200 import _lib as L
-        n = C.c_int(0)
-        return L.lib().vdb_device_count(C.byref(n)) == 0 and n.value > 0
-    except Exception:
-        return False
+    """True when a CUDA device is visible. A missing or broken libvdb_b200.so (load failure, symbol mismatch) is NOT
+    "no GPU": it propagates, so a broken build fails the suite instead of skipping it."""
+    import ctypes as C
+    from lab_1806_vec_db_b200 import _lib as L
+    n = C.c_int(0)
+    rc = L.lib().vdb_device_count(C.byref(n))
+    return rc == 0 and n.value > 0

@@ -129,3 +129,18 @@ def test_hnsw_index_bincode_layout_known_answer():
     assert [a.tolist() for a in back.links_len] == [[1, 0], [1]]
     empty = F.load_hnsw_index(F.dump_hnsw_index(rec._replace(enter_level=None, enter_point=None)))
     assert empty.enter_level is None and empty.enter_point is None
+
+
+def test_load_raw_limit_ignores_a_trailing_partial_row(tmp_path):
+    """BinaryScalar::from_binary_file reads at most limit * dim scalars (scalar.rs:78-98): bytes beyond them - even a
+    partial row - are never examined; without a limit the same file is rejected (vec_set.rs:35-38)."""
+    from lab_1806_vec_db_b200 import formats as F
+    rows = np.arange(5 * 8, dtype=np.float32).reshape(5, 8)
+    p = tmp_path / "x.bin"
+    with open(p, "wb") as f:
+        f.write(rows.tobytes())
+        f.write(np.zeros(3, np.float32).tobytes())        # a trailing partial row
+    got = F.load_raw(p, 8, np.float32, limit=4)
+    assert got.shape == (4, 8) and (got == rows[:4]).all()
+    with pytest.raises(ValueError):
+        F.load_raw(p, 8, np.float32)

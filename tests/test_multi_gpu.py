@@ -185,3 +185,49 @@ def test_concurrent_calls_on_a_sharded_handle(vdb):
     for i, (a, b) in enumerate(outs):
         _same(a, want)
         _same(b, tuple(x[i:i + 1] for x in want))
+
+
+def test_sharded_ivf_and_pq_equal_the_unsharded_calls(vdb, oracle):
+    """vdb_ivf_create / vdb_ivf_knn and vdb_pq_create / vdb_pq_knn on a row-sharded set: assignment, lists,
+    codes and search results are bit-identical to the unsharded calls (and the oracle's on a query sample). Runs on
+    one GPU with three shards on device 0, and with one shard per GPU when more are visible."""
+    V = vdb
+    n, nq, dim = 200_000, 96, 96
+    base, q = _data(n, nq, dim, 7)
+    base[150_001] = base[5]
+    rng = np.random.default_rng(1)
+    cent = np.ascontiguousarray(base[rng.permutation(n)[:32]])
+    m = 24
+    books = np.concatenate([np.ascontiguousarray(base[100:116, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(dim, m)])
+    cfg = V.PQConfig(4, m, "l2sqr")
+    V.init_devices([])
+    full = V.FlatIndex.from_vec_set(base, "l2sqr")
+    ivf_full = V.IVFIndex(full.vec_set, cent)
+    pq_full = V.PQTable(full.vec_set, cfg, books)
+    want_ivf = {p: ivf_full.knn_with_ef_batch(q, 10, p) for p in (1, 4, 32)}
+    want_pq = {(k, ef): full.knn_pq_batch(q, k, ef, pq_full) for k, ef in ((10, 240), (10, 5), (3, 600))}
+    lists_full = ivf_full.clusters
+    for devs in _device_sets():
+        V.init_devices(devs)
+        vs = V.DeviceVecSet(base, "l2sqr")
+        ivf = V.IVFIndex(vs, cent)
+        assert (ivf.assignment == ivf_full.assignment).all()
+        for a, b in zip(ivf.clusters, lists_full):
+            assert (a == b).all()
+        for p, w in want_ivf.items():
+            _same(ivf.knn_with_ef_batch(q, 10, p), w)
+        _same(ivf.knn_with_ef_batch(q[:1], 10, 4), tuple(a[:1] for a in want_ivf[4]))
+        pq = V.PQTable(vs, cfg, books)
+        assert (pq.encoded_vec_set == pq_full.encoded_vec_set).all()
+        flat = V.FlatIndex(vs)
+        for (k, ef), w in want_pq.items():
+            _same(flat.knn_pq_batch(q, k, ef, pq), w)
+        lut_a, lut_b = pq.create_lookup(q[0]), pq_full.create_lookup(q[0])
+        assert all((np.asarray(x) == np.asarray(y)).all() for x, y in zip(lut_a, lut_b))
+        del ivf, pq, flat, vs
+    codes = pq_full.encoded_vec_set
+    off, mem = oracle.ivf_lists(ivf_full.assignment, 32)
+    oi = oracle.ivf_knn(base, cent, off, mem, q[:16], 10, 4, "l2sqr", nthreads=8)
+    assert_knn_parity(base, q[:16], "l2sqr", tuple(a[:16] for a in want_ivf[4]), oi, oracle)
+    op = oracle.flat_knn_pq(base, codes, books, m, 4, q[:16], 10, 240, "l2sqr", nthreads=8)
+    assert_knn_parity(base, q[:16], "l2sqr", tuple(a[:16] for a in want_pq[(10, 240)]), op, oracle)
