@@ -504,6 +504,13 @@ def run_ours_multi(args):
     q_host = q_pin[:nqs].numpy()
     qps_cpu, dt_cpu, ores = cpu_arm(base_host, q_host, args.k, cores, 1, 0)
     cpu = parity_fields(res, ores, q_host, base_host, nqs, args, cores, qps_cpu, dt_cpu)
+    other = None
+    if not args.no_other_configs:
+        try:
+            import bench_configs
+            other = bench_configs.sharded_legs(V, vs, base_host, q_pin.numpy(), res[0][:, :10], world)
+        except Exception as e:  # noqa: BLE001 - the headline line must not be lost to an auxiliary leg
+            other = {"error": repr(e)}
     del base_host
 
     line = {
@@ -524,6 +531,7 @@ def run_ours_multi(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "kernel_ms": {k_: {"ms": v[0], "launches": v[1]} for k_, v in prof.items()},
         "tensor_path": stats, "host_wall_ms_per_step": wall / args.steps * 1e3, "nccl_multiprocess": nccl,
+        "other_configs": other,
     }
     print(json.dumps(line), flush=True)
     dist.destroy_process_group()

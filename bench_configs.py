@@ -307,3 +307,69 @@ def run_all(V, L, lib, dev, peaks, base_flat, q_flat, synth_clustered, proto, n)
     cl["hnsw"] = legs.hnsw(pq, books)
     out["clustered_set"] = cl
     return out
+
+
+def sharded_legs(V, vs, base_host, q_host, gt10, n_gpus):
+    """configs[2] / configs[3] on the ROW-SHARDED set at N > 1 GPUs, through the host-pointer C calls a Rust host makes
+    (vdb_ivf_create / vdb_ivf_knn, vdb_pq_create / vdb_pq_knn on the sharded handle: csrc/multi.cu). 1000 queries, k = 10;
+    wall-clock QPS including the H2D of the queries and the D2H of the results, recall@10 against the exact Flat result
+    of the headline leg, and the oracle on a query sample in the same run (QPS, its recall, id equality)."""
+    import oracle as O
+    from lab_1806_vec_db_b200.index import train_codebooks
+    nq, k = min(1000, q_host.shape[0]), 10
+    q = np.ascontiguousarray(q_host[:nq])
+    gt = np.asarray(gt10)[:nq, :k].astype(np.int64)
+    cores = os.cpu_count() or 1
+    nc = min(16, nq)
+    rng = np.random.default_rng(42)
+    n = base_host.shape[0]
+    out = {"n_gpus": n_gpus, "nq": nq, "k": k, "api": "host pointers on the row-sharded handle (one C call per batch)"}
+
+    def wall(fn, reps=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        return (time.perf_counter() - t0) / reps, r
+
+    def row(param, secs, res, oi, cpu_s, what):
+        got = res[0].astype(np.int64)
+        return dict(param, **{"e2e_qps": nq / secs, "ms_per_batch": secs * 1e3, "recall@10": _recall(got, gt, k),
+                              "cpu_baseline": {"value": nc / cpu_s, "unit": "queries/s", "cores": cores, "kind": "port",
+                                               "sample": f"{nc} of the {nq} queries, {what}",
+                                               "recall@10": _recall(oi, gt[:nc], k),
+                                               "gpu_ids_equal_oracle_rate": float((got[:nc] == np.asarray(oi).astype(np.int64)).mean())}})
+
+    # ---- IVF ----
+    km = V.KMeans.from_vec_set(np.ascontiguousarray(base_host[rng.permutation(n)[:100_000]]),
+                               V.KMeansConfig(128, 20, 1e-6, "l2sqr"), rng)
+    t0 = time.perf_counter()
+    ivf = V.IVFIndex(vs, km.centroids)
+    t_build = time.perf_counter() - t0
+    off, mem = O.ivf_lists(ivf.assignment, 128)
+    rows = []
+    for nprobe in (8, 24):
+        secs, res = wall(lambda: ivf.knn_with_ef_batch(q, k, nprobe))
+        t0 = time.perf_counter()
+        oi, _, _ = O.ivf_knn(base_host, km.centroids, off, mem, q[:nc], k, nprobe, "l2sqr", nthreads=cores)
+        rows.append(row({"nprobe": nprobe}, secs, res, oi, time.perf_counter() - t0, "oracle ivf_knn"))
+    out["ivf"] = {"nlist": 128, "assign_and_lists_s": t_build, "search": rows}
+    ivf.close()
+    # ---- PQ ----
+    cfg = V.PQConfig(4, 240, "l2sqr", min(10_000, n), 20, 1e-6)
+    V.init_devices([])      # the training sample is a plain single-device set
+    train_dev = V.DeviceVecSet(np.ascontiguousarray(base_host[rng.permutation(n)[:10_000]]), "l2sqr")
+    books = train_codebooks(train_dev, cfg, rng)
+    train_dev.close()
+    t0 = time.perf_counter()
+    pq = V.PQTable(vs, cfg, books)
+    t_enc = time.perf_counter() - t0
+    flat = V.FlatIndex(vs)
+    rows = []
+    for ef in (240, 600):
+        secs, res = wall(lambda: flat.knn_pq_batch(q, k, ef, pq))
+        t0 = time.perf_counter()
+        oi, _, _ = O.flat_knn_pq(base_host, pq.encoded_vec_set, books, 240, 4, q[:nc], k, ef, "l2sqr", nthreads=cores)
+        rows.append(row({"ef": ef}, secs, res, oi, time.perf_counter() - t0, "oracle knn_pq"))
+    out["pq"] = {"m": 240, "n_bits": 4, "encode_s_incl_code_download": t_enc, "search": rows}
+    return out
