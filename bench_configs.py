@@ -357,7 +357,6 @@ def sharded_legs(V, vs, base_host, q_host, gt10, n_gpus):
     ivf.close()
     # ---- PQ ----
     cfg = V.PQConfig(4, 240, "l2sqr", min(10_000, n), 20, 1e-6)
-    V.init_devices([])      # the training sample is a plain single-device set
     train_dev = V.DeviceVecSet(np.ascontiguousarray(base_host[rng.permutation(n)[:10_000]]), "l2sqr")
     books = train_codebooks(train_dev, cfg, rng)
     train_dev.close()

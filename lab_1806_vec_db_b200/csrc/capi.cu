@@ -50,7 +50,7 @@ void prof_record(const char* name, cudaStream_t st, bool begin) {
 namespace vdb {
 // multi.cu
 std::vector<int> registered_devices();
-void init_devices(const int* devices, uint32_t n);
+void init_devices(const int* devices, uint32_t n, bool register_default);
 vdb_dataset* sharded_create(const std::vector<int>& devs, uint64_t n, uint32_t dim, int dtype, int metric, uint64_t id_base,
                             const std::vector<uint64_t>* counts,
                             const std::function<vdb_dataset*(uint32_t, int, uint64_t, uint64_t)>& make_shard);
@@ -284,7 +284,7 @@ static vdb_dataset* adopt_dataset_on(int device, const void* d_rows, uint64_t n,
 int vdb_init(const int* devices, uint32_t n) {
     return guarded([&] {
         VDB_REQUIRE(devices || n == 0, "devices is NULL");
-        vdb::init_devices(devices, n);
+        vdb::init_devices(devices, n, true);
         if (n == 1) {
             VDB_CUDA(cudaSetDevice(devices[0]));
             t_device = devices[0];
@@ -340,7 +340,7 @@ int vdb_dataset_create_sharded_dev(const void* const* d_rows, const uint64_t* co
         for (uint64_t c : cnt) n += c;
         VDB_REQUIRE(id_base + n < 0xFFFFFFFFull, "id_base + n must be < 2^32 - 1");
         std::vector<int> devs(devices, devices + nshards);
-        vdb::init_devices(devices, nshards);   // peer access between the shards' devices
+        vdb::init_devices(devices, nshards, false);   // peer access between the shards' devices (no global registration)
         *out = vdb::sharded_create(devs, n, dim, dtype, metric, id_base, &cnt,
                                    [&](uint32_t s, int device, uint64_t lo, uint64_t hi) {
                                        VDB_REQUIRE(d_rows[s] || hi == lo, "d_rows[%u] is NULL", s);

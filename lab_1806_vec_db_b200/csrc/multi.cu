@@ -62,13 +62,15 @@ static void enable_peers(const std::vector<int>& devs) {
     VDB_CUDA(cudaSetDevice(prev));
 }
 
-void init_devices(const int* devices, uint32_t n) {
+// peer access between the listed devices; `register_default`: vdb_dataset_create shards over them from now on
+void init_devices(const int* devices, uint32_t n, bool register_default) {
     std::vector<int> devs(devices, devices + n);
     int have = 0;
     VDB_CUDA(cudaGetDeviceCount(&have));
     for (int d : devs) VDB_REQUIRE(d >= 0 && d < have, "device %d out of range (have %d)", d, have);
     VDB_REQUIRE(n <= 64, "at most 64 shards");
     enable_peers(devs);
+    if (!register_default) return;
     std::lock_guard<std::mutex> lk(g_init_mu);
     g_devices = devs;
 }
