@@ -318,7 +318,8 @@ int vdb_hnsw_info(const vdb_hnsw* h, uint64_t* n, uint32_t* M, uint32_t* ef_cons
 /* level-0 adjacency as the reference stores it (level0_links :110-112, links_len): links0[n * 2M], len0[n]. */
 int vdb_hnsw_links0(const vdb_hnsw* h, uint32_t* links0, uint32_t* len0);
 /* Upper levels (other_links :113-119, links_len): for every node its level_i lists of M links, nodes in row order,
- * levels 1..level_i in order: ulinks[sum(levels) * M], ulen[sum(levels)]. levels[n] is filled when non-NULL. */
+ * levels 1..level_i in order: ulinks[sum(levels) * M], ulen[sum(levels)]. levels[n] is filled when non-NULL; a call
+ * with only `levels` (ulinks == ulen == NULL) returns the levels so that the caller can size the other two arrays. */
 int vdb_hnsw_upper(const vdb_hnsw* h, uint32_t* levels, uint32_t* ulinks, uint32_t* ulen);
 /* An index built elsewhere - e.g. deserialised from the reference's bincode file (IndexSerdeExternalVecSet
  * :641-668) - over the rows of `ds`: same layouts as vdb_hnsw_links0 / vdb_hnsw_upper. */

@@ -36,6 +36,39 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert L.lib().vdb_version() == 801
 
 
+def test_rust_shim_binds_only_declared_entry_points_with_matching_arity():
+    """rust_shim/vdb_b200.rs cannot be compiled here (no Rust toolchain), so its extern block is checked textually:
+    every bound function is declared in include/vdb_b200.h with the same number of arguments, and every call site in
+    the shim passes that many."""
+    hdr = open(os.path.join(ROOT, "include", "vdb_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    shim = open(os.path.join(ROOT, "rust_shim", "vdb_b200.rs")).read()
+    shim_nc = re.sub(r"//[^\n]*", "", shim)
+
+    def nargs(arglist):
+        arglist = arglist.strip()
+        return 0 if arglist in ("", "void") else arglist.count(",") + 1
+    c_decl = {m.group(1): nargs(m.group(2)) for m in re.finditer(r"\b(vdb_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr)}
+    rs_decl = {m.group(1): nargs(m.group(2)) for m in re.finditer(r"pub fn (vdb_[a-z0-9_]+)\(([^()]*)\)", shim_nc)}
+    assert len(rs_decl) >= 30
+    for name, n in rs_decl.items():
+        assert name in c_decl, f"{name} is bound by the shim but not declared in include/vdb_b200.h"
+        assert c_decl[name] == n, f"{name}: header has {c_decl[name]} arguments, shim declares {n}"
+    # call sites: `vdb_xxx(` inside `unsafe { ... }` with balanced parentheses
+    for m in re.finditer(r"unsafe \{ (vdb_[a-z0-9_]+)\(", shim_nc):
+        name, i, depth, commas = m.group(1), m.end(), 1, 0
+        empty = True
+        while depth:
+            ch = shim_nc[i]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            commas += ch == "," and depth == 1
+            empty &= ch.isspace() or depth == 0
+            i += 1
+        assert (0 if empty else commas + 1) == rs_decl[name], f"call of {name} passes {commas + 1} arguments"
+    assert "gpu_mirror" not in shim  # round-1 finding: the shim called a method that exists nowhere
+
+
 def test_no_cpu_fallback_on_a_box_without_gpu():
     """The product path must fail loudly, never compute on the CPU."""
     import lab_1806_vec_db_b200 as V
