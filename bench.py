@@ -763,6 +763,23 @@ def run_ours(args):
                                       "scan_kernel_ms": kern_ms, "achieved_gbs": gbs, "frac": gbs / peak_hbm,
                                       "frac_whole_call": n_local * DIM * 4 / (call_ms * 1e-3) / 1e9 / peak_hbm})
         L.check(lib.vdb_flat_set_path({"auto": 0, "scan": 1, "tensor": 2}[args.path]))
+        # the same small batches through the AUTO path (what a caller gets): from 3 queries up the library answers with
+        # one single-CTA tensor pass over the 2-byte operand copy (half the bytes of the f32 rows) + exact rerank
+        hbm_scan["auto_path"] = []
+        for nq1 in (2, 3, 4, 8, 32, 128):
+            qs = q_dev[:nq1].contiguous()
+            for _ in range(3):
+                idx.knn_batch_dev(qs, 10)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            a0.record()
+            for _ in range(reps):
+                idx.knn_batch_dev(qs, 10)
+            a1.record()
+            torch.cuda.synchronize()
+            call_ms = a0.elapsed_time(a1) / reps
+            hbm_scan["auto_path"].append({"nq": nq1, "qps": nq1 / (call_ms * 1e-3), "call_ms": call_ms,
+                                          "f32_row_bytes_per_call_over_peak": n_local * DIM * 4 / (call_ms * 1e-3) / 1e9 / peak_hbm})
 
     # ---- the reference's real call pattern: ONE query per knn call, host pointers, from 1 / 8 / 32 caller threads ----
     single = None

@@ -238,7 +238,7 @@ int vdb_ivf_knn_dev(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_que
 typedef struct vdb_tq vdb_tq;
 /* n, sample size, mean row norm and mean operand-error norm of this shard (builds the side arrays on first use). */
 int vdb_tq_info(const vdb_dataset* ds, uint64_t* n, uint32_t* sample_n, float* mean_norm, float* mean_ex);
-/* Smallest sample order statistic whose rank among n_total rows is >= k with probability > 1 - 2e-3. */
+/* Smallest sample order statistic whose rank among n_total rows is >= k with probability > 1 - 2e-5. */
 uint32_t vdb_tq_j0(uint32_t k, uint64_t sample_total, uint64_t n_total);
 int vdb_tq_begin_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, void* stream, vdb_tq** out);
 /* number of sampled rows to re-evaluate per query for the order statistic j0 (a few more than j0; at most sample_min,

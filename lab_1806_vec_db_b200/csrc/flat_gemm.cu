@@ -898,7 +898,7 @@ __global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t
 // Flat: the sample keys carry EXACT distances (the j best sampled rows by pruning score are re-evaluated in fp32), so
 // tau_q = d_(j0) - ||q||^2 (cosine: d_(j0)) needs no margin: every row x of the true top-k has S'(x) <= d(x) - ||q||^2
 // <= d_k - ||q||^2 <= d_(j0) - ||q||^2 whenever the j0-th sampled distance is not better than the k-th best of the set
-// (probability > 1 - 2e-3 by the choice of j0, verified per query by the check kernel). The slack keeps the check's
+// (probability > 1 - 2e-5 by the choice of j0, verified per query by the check kernel). The slack keeps the check's
 // strict comparison satisfiable when the j0-th sampled row IS the k-th best.
 __global__ void tau_exact_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, uint32_t j0,
                                  const float* __restrict__ qsq, float* __restrict__ tau) {
@@ -911,6 +911,119 @@ __global__ void tau_exact_kernel(const uint64_t* __restrict__ keys, uint32_t nq,
     }
     const float d = key_dist(kk), shift = qsq ? qsq[q] : 0.f;
     tau[q] = (d - shift) + 1e-4f * (fabsf(d) + shift) + 1e-30f;
+}
+// two-level sample selection: coarse threshold = the j1-th smallest sub-sample score, nudged up so that the strict
+// comparison of the filter keeps the row it came from (+inf when the sub-sample holds fewer than j1 rows)
+__global__ void tau_coarse_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j1, float* __restrict__ tau) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint64_t kk = keys[(size_t)q * j1 + (j1 - 1)];
+    const float s = key_dist(kk);
+    tau[q] = kk == KEY_NONE ? __uint_as_float(0x7f800000u) : s + 1e-6f * fabsf(s) + 1e-30f;
+}
+// filter-mode candidates (raw score bits << 32 | row of the B tensor) -> sortable keys, in place
+__global__ void cand_sortable_kernel(uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap) {
+    const uint32_t q = blockIdx.x, c = min(cnt[q], cap);
+    for (uint32_t j = threadIdx.x; j < c; j += blockDim.x) {
+        const uint64_t e = cand[(uint64_t)q * cap + j];
+        cand[(uint64_t)q * cap + j] = make_key(__uint_as_float((uint32_t)(e >> 32)), (uint32_t)e);
+    }
+}
+// ---- candidate pruning by score bounds -------------------------------------------------------------------------------
+// The filter keeps every row whose LOWER bound S' of the (shifted) distance is under tau_q; tau_q comes from a sample, so a
+// list holds several times k rows. The same contraction also gives an UPPER bound: the score without its error term lies
+// within +-B(q, x) of the exact value, so U = S' + 2 B (plus the rounding slack of the check kernel) >= d(q, x) - shift. At
+// least k rows of the list have a distance <= U_(k), the k-th smallest U, hence d_k - shift <= U_(k) and no row with
+// S' > U_(k) can be among the k best: it is dropped BEFORE the exact rerank (HBM gathers of whole rows). One CTA per
+// query: U of every candidate -> radix select of U_(k) in shared memory -> in-place compaction. Lists of <= k entries and
+// NaN scores (non-finite rows; the rerank decides) are kept whole.
+template <int METRIC>
+__global__ void __launch_bounds__(256) cand_prune_kernel(uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap,
+                                                         uint32_t k, const float* __restrict__ rnorm, const float* __restrict__ ex,
+                                                         const float* __restrict__ qab, const float* __restrict__ qb,
+                                                         const float* __restrict__ qsq, uint32_t* __restrict__ cnt_out) {
+    extern __shared__ uint32_t prune_u[];   // [min(cnt, cap)] order bits of U
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_bin, s_k, s_warp[8], s_base;
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const uint32_t c = min(cnt[q], cap);
+    if (c <= k) {
+        if (tid == 0) cnt_out[q] = c;
+        return;
+    }
+    uint64_t* list = cand + (uint64_t)q * cap;
+    const float a = qab[q], b = qb[q], shift = qsq ? qsq[q] : 0.f;
+    for (uint32_t j = tid; j < c; j += blockDim.x) {
+        const uint64_t e = list[j];
+        const uint32_t row = (uint32_t)e;
+        const float sp = __uint_as_float((uint32_t)(e >> 32));
+        const float bound = METRIC == VDB_L2SQR ? fmaf(a, ex[row], b * rnorm[row]) : (1.0f - b) + a * ex[row];
+        float up = sp + 2.0002f * bound;
+        up += 2e-5f * (fabsf(up) + shift) + 1e-30f;
+        // -inf marks a row that must be kept whatever its score (cosine: under the reference's norm clamp): no upper bound
+        prune_u[j] = fabsf(sp) <= 3.0e38f ? f32_order_bits(up) : 0xffffffffu;
+    }
+    // radix select: the k-th smallest (1-based) of prune_u[0, c), 8 bits per pass from the top
+    uint32_t prefix = 0, mask = 0, kk = k;
+    for (int sh = 24; sh >= 0; sh -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (uint32_t j = tid; j < c; j += blockDim.x) {
+            const uint32_t v = prune_u[j];
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> sh) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {   // warp 0: bin that holds the kk-th element (inclusive scan over 8 bins per lane)
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) loc[i] = hist[tid * 8 + i], sum += loc[i];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)tid >= o) incl += y;
+            }
+            const uint32_t before = incl - sum;
+            if (before < kk && kk <= incl) {   // exactly one lane
+                uint32_t run = before;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (run < kk && kk <= run + loc[i]) s_bin = tid * 8 + i, s_k = kk - run;
+                    run += loc[i];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= s_bin << sh;
+        mask |= 0xffu << sh;
+        kk = s_k;
+        __syncthreads();
+    }
+    const uint32_t thr = prefix;
+    // stable in-place compaction (a chunk is read completely before anything is written at or below it)
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t j0 = 0; j0 < c; j0 += blockDim.x) {
+        const uint32_t j = j0 + tid;
+        const uint64_t e = j < c ? list[j] : 0;
+        const float sp = __uint_as_float((uint32_t)(e >> 32));
+        const bool keep = j < c && (sp != sp || f32_order_bits(sp) <= thr);
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        const uint32_t lane = tid & 31, w = tid >> 5;
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        uint32_t off = s_base, total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < (int)w) off += s_warp[i];
+            total += s_warp[i];
+        }
+        if (keep) list[off + __popc(bal & ((1u << lane) - 1u))] = e;
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) cnt_out[q] = s_base;
 }
 // (query, source row) pairs of the j best sampled rows of every query; KEY_NONE entries are masked out
 __global__ void sample_pairs_kernel(const uint64_t* __restrict__ keys, uint64_t count, uint32_t j,
@@ -1102,7 +1215,7 @@ std::atomic<uint32_t> g_debug_force_redo{0};
 
 // ---- phases (also exported one by one for the row-sharded search, sharded.py) -------------------------------
 // j0: smallest order statistic of an `ns`-row uniform sample whose rank among the `n` rows is >= k with high
-// probability: P(rank < k) = P(Poisson(k*ns/n) >= j0) < 2e-3
+// probability: P(rank < k) = P(Poisson(k*ns/n) >= j0) < eps (2e-5 by default)
 uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps) {
     uint32_t j0 = 1;
     const double x = (double)k * (double)ns / (double)n;
@@ -1238,7 +1351,54 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     plan_gemm(ps, tq->ctas, stps);
     const uint64_t cnt = (uint64_t)tq->nq * j;
     DevBuf skeys(cnt * 8, st);
-    if (j <= (uint32_t)G_TOPJ) {
+    // Two-level selection (default): the register top-G_TOPJ epilogue (mode 2) runs at a fraction of the MMA rate (its
+    // insertions are warp-wide: 4 ms for 32768 sampled rows x 10 000 queries, a fifth of the whole step), and storing
+    // every sampled score (mode 0) is nq * ns * 8 bytes. Instead: (1) every SUB-th sample row is scored (~1024 rows) and
+    // the j1-th smallest score per query - j1 = the order statistic of the sub-sample whose rank in the sample is >= j
+    // with probability > 1 - 1e-5 - becomes a coarse threshold; (2) the whole sample is FILTERED against it at the full
+    // MMA rate (mode 1, ~j1 * SUB survivors per query); (3) the j smallest survivors are selected. A query that ends up
+    // with fewer than j survivors (or an overflowed list) only gets a looser tau: the completeness check of the search
+    // decides, as always.
+    // Batches of <= 128 queries (single CTAs, HBM-bound on the operand rows) keep the one-launch register epilogue.
+    static const bool two_level = !(getenv("VDB_GEMM_SAMPLE_2L") && !atoi(getenv("VDB_GEMM_SAMPLE_2L")));
+    const uint32_t SUB = (uint32_t)std::max<uint64_t>(2, ns / 1024);   // sub-sample of ~1024 rows
+    if (two_level && ns >= 2048 && (tq->ctas == 2 || j > (uint32_t)G_TOPJ)) {
+        const uint64_t ns1 = ns / SUB;
+        const uint32_t j1 = tensor_j0(j, ns1, ns, 1e-5);
+        const CUtensorMap m1 = make_op_map(tq->kind, ds->d_sample, ds->dim, ns1, op_row_bytes_of(ds) * SUB, GN / tq->ctas);
+        GemmParams p1 = ps;
+        p1.nrows = ns1;
+        p1.row_stride = SUB;
+        plan_gemm(p1, tq->ctas);
+        DevBuf k1((size_t)tq->nq * j1 * 8, st), tau1((size_t)tq->nq * 4, st);
+        if (j1 <= (uint32_t)G_TOPJ) {   // ~1024 rows: the register epilogue costs 1/32 of what it did on the whole sample
+            DevBuf part1((size_t)tq->nq * p1.nslabs * G_TOPJ * 8, st);
+            p1.out_keys = part1.as<uint64_t>();
+            launch_gemm(2, ds->metric, tq->kind, tq->mq, m1, p1, st, tq->ctas);
+            launch_merge_keys(part1.as<uint64_t>(), p1.nslabs, tq->nq, G_TOPJ, false, j1, k1.as<uint64_t>(), nullptr, nullptr, nullptr, st);
+        } else {
+            DevBuf all1((size_t)tq->nq * ns1 * 8, st);
+            p1.out_keys = all1.as<uint64_t>();
+            launch_gemm(0, ds->metric, tq->kind, tq->mq, m1, p1, st, tq->ctas);
+            launch_merge_keys(all1.as<uint64_t>(), 1, tq->nq, (uint32_t)ns1, false, j1, k1.as<uint64_t>(), nullptr, nullptr, nullptr, st);
+        }
+        tau_coarse_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(k1.as<uint64_t>(), tq->nq, j1, tau1.as<float>());
+        VDB_LAUNCHED();
+        const uint32_t cap2 = next_pow2(std::max<uint32_t>(256, 4 * j1 * SUB));
+        DevBuf cand2((size_t)tq->nq * cap2 * 8, st), cnt2((size_t)tq->nq * 4, st);
+        VDB_CUDA(cudaMemsetAsync(cnt2.p, 0, (size_t)tq->nq * 4, st));
+        GemmParams p2 = ps;
+        p2.tau = tau1.as<float>();
+        p2.cand_cnt = cnt2.as<uint32_t>();
+        p2.cand = cand2.as<uint64_t>();
+        p2.cap = cap2;
+        plan_gemm(p2, tq->ctas);
+        launch_gemm(1, ds->metric, tq->kind, tq->mq, ms, p2, st, tq->ctas);
+        cand_sortable_kernel<<<tq->nq, 128, 0, st>>>(cand2.as<uint64_t>(), cnt2.as<uint32_t>(), cap2);
+        VDB_LAUNCHED();
+        launch_merge_keys(cand2.as<uint64_t>(), 1, tq->nq, cap2, false, j, skeys.as<uint64_t>(), nullptr, nullptr, nullptr, st,
+                          nullptr, cnt2.as<uint32_t>());
+    } else if (j <= (uint32_t)G_TOPJ) {
         // the epilogue keeps each query's G_TOPJ smallest scores per slab in registers: nothing but
         // nq * nslabs * G_TOPJ keys ever reaches HBM
         DevBuf part((size_t)tq->nq * ps.nslabs * G_TOPJ * 8, st);
@@ -1369,8 +1529,15 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     // step is power-capped, so hiding the gathers slows the contraction by almost as much); a 125k-row shard with its
     // own thresholds 9.6 -> 8.0 ms; the same shard under the global thresholds of an 8-way split 4.87 -> 4.77 ms;
     // 8 parts cost more in launch tails than they hide
-    uint32_t parts = parts_env ? parts_env : (tile_units >= 8192 ? 3u : 1u);
+    // Round 2: with 2-byte operands the contraction runs at the L2 -> SM bandwidth, which the concurrent gathers
+    // compete for (1M x 960, 10k queries: 20.6 ms with 3 parts, 19.8 ms unsplit), and the bound-based pruning below cuts
+    // the rerank to a fraction, so the pass is NOT split by default any more (VDB_GEMM_PARTS=n brings the parts back,
+    // without pruning).
+    (void)tile_units;
+    uint32_t parts = parts_env ? parts_env : 1u;
     parts = std::max(1u, std::min(parts, total_slabs));
+    static const bool prune_on = !(getenv("VDB_GEMM_PRUNE") && !atoi(getenv("VDB_GEMM_PRUNE")));
+    const bool prune = prune_on && parts == 1 && (size_t)cap * 4 <= 96 * 1024;
     // part i covers a share proportional to ratio^i of the slabs: the rerank of the LAST part is the only one that is
     // not hidden under a contraction launch, so later parts are made smaller
     const char* ratio_s = getenv("VDB_GEMM_PART_RATIO");
@@ -1408,7 +1575,16 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         launch_gemm(1, ds->metric, tq->kind, tq->mq, mx, pp, st, tq->ctas);
         uint32_t* snap = snaps.as<uint32_t>() + (size_t)part * nq;
         const uint32_t* prev = part ? snap - nq : nullptr;
-        VDB_CUDA(cudaMemcpyAsync(snap, tq->cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToDevice, st));
+        if (prune) {   // snap = the pruned list lengths
+            auto kern = ds->metric == VDB_COSINE ? cand_prune_kernel<VDB_COSINE> : cand_prune_kernel<VDB_L2SQR>;
+            const size_t sm = (size_t)cap * 4;
+            if (sm > 48 * 1024) VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            kern<<<nq, 256, sm, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, k, ds->d_lo, ds->d_ex, tq->qab.as<float>(),
+                                      tq->qb.as<float>(), ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(), snap);
+            VDB_LAUNCHED();
+        } else {
+            VDB_CUDA(cudaMemcpyAsync(snap, tq->cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToDevice, st));
+        }
         if (parts > 1) {
             VDB_CUDA(cudaEventRecord(side.ev, st));
             VDB_CUDA(cudaStreamWaitEvent(rs, side.ev, 0));
@@ -1433,14 +1609,14 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     }
     drain.armed = false;   // from here on the main stream is ordered after the side stream
     // the k best exact keys of every query's list (its first min(cnt, cap) entries)
-    launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr,
-                      tq->cnt.as<uint32_t>());
+    const uint32_t* final_cnt = prune ? snaps.as<uint32_t>() : tq->cnt.as<uint32_t>();   // <= cap when pruned
+    launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr, final_cnt);
     if (d_overflow) {
         overflow_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), tq->qbad.as<uint32_t>(), nq, cap, d_overflow);
         VDB_LAUNCHED();
     }
     if (d_cand_total) {
-        cand_total_kernel<<<1, 1024, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, d_cand_total);
+        cand_total_kernel<<<1, 1024, 0, st>>>(final_cnt, nq, cap, d_cand_total);   // rows the exact rerank gathered
         VDB_LAUNCHED();
     }
 }

@@ -177,7 +177,7 @@ void flat_gemm_store(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
                      uint64_t* d_out_keys, cudaStream_t st);
 extern std::atomic<uint64_t> g_gemm_redo, g_gemm_cands, g_gemm_queries;
 extern std::atomic<uint32_t> g_debug_force_redo;
-uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps = 5e-4);
+uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps = 2e-5);
 vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, bool any_size = false);
 void operand_info(const vdb_dataset* ds, int* kind, float* scale, float* mean_norm, float* mean_ex, uint64_t* side_bytes);
 void tensor_end(vdb_tq* tq);
