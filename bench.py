@@ -415,7 +415,7 @@ def run_ours_multi(args):
         launches = int(lib.vdb_launch_count() - launches0)
         L.check(lib.vdb_prof_enable(0))
         clocks = sampler.stop()
-        for name in ("flat_scan", "flat_gemm", "rerank", "merge", "mg_queries", "mg_sample", "mg_filter", "mg_merge"):
+        for name in ("flat_scan", "flat_gemm", "flat_gemm_sample", "rerank", "merge", "mg_queries", "mg_sample", "mg_filter", "mg_merge"):
             t, c = C.c_double(0), C.c_uint64(0)
             L.check(lib.vdb_prof_read(name.encode(), C.byref(t), C.byref(c)))
             prof[name] = (t.value, int(c.value))
@@ -622,7 +622,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
 
     prof = {}
-    for name in ("flat_scan", "flat_gemm", "rerank", "merge"):
+    for name in ("flat_scan", "flat_gemm", "flat_gemm_sample", "rerank", "merge"):
         t, c = C.c_double(0), C.c_uint64(0)
         L.check(lib.vdb_prof_read(name.encode(), C.byref(t), C.byref(c)))
         prof[name] = (t.value, int(c.value))
@@ -631,7 +631,7 @@ def run_ours(args):
     # after it). In the timed region above the filter pass is cut into row parts and the rerank gathers of part i run
     # on a side stream under the launch of part i + 1: the step is shorter, each launch is longer.
     alone = None
-    if rank == 0 and world == 1 and args.path != "scan":
+    if rank == 0 and world == 1 and args.path != "scan" and int(os.environ.get("VDB_GEMM_PARTS", "1")) > 1:
         keep = os.environ.get("VDB_GEMM_PARTS")
         os.environ["VDB_GEMM_PARTS"] = "1"
         idx.knn_batch_dev(q_dev, args.k)
@@ -697,7 +697,8 @@ def run_ours(args):
                 "launches": c_dom, "avg_launch_ms": t_dom / max(c_dom, 1),
                 "algorithmic_bytes_per_launch": per_launch}
     else:
-        # dense contraction: 2*nq*n*dim FLOP per step (the sample pass adds ns/n ~ 3 % more, not counted), DESIGN.md K2
+        # dense contraction: 2*nq*n*dim FLOP per step = the filter launches; the sample passes (ns/n ~ 3 % more FLOP) are
+        # timed under their own name ("flat_gemm_sample" in kernel_ms) and counted in neither numerator nor denominator
         flops = 2.0 * args.nq * n_local * DIM * args.steps
         tstats = tensor_stats(lib, vs._h) or {}
         f16 = "fp16" in (tstats.get("operand") or {}).get("kind", "")

@@ -115,6 +115,7 @@ struct GemmParams {
     const GemmItem* items;  // nullptr -> the grid of plan_gemm
     uint32_t nitems;
     const uint32_t* qmap;   // table mode: row of the gathered query matrix -> query that owns the candidate list
+    uint32_t rare_per_score;  // 1: the filter's rare path reserves list slots one atomic per score (measurement switch)
 };
 
 template <int CTAS>
@@ -393,6 +394,29 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         for (int j = 0; j < 32; ++j) {
                             const uint64_t brow = tile_row0 + c0 + j;
                             if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(__uint_as_float(v[j]), (uint32_t)brow);
+                        }
+                    } else if (MODE == 1 && !p.rare_per_score && !(none[0] && none[1] && none[2] && none[3])) {
+                        // rare path of the filter: the passing (or NaN: the exact rerank decides) scores of the flagged groups
+                        // of 8 are collected in a bit mask and the thread reserves all their list slots with ONE atomic. (One
+                        // atomic per score serialises its ~700-cycle round trips in divergent code: the sample pass of the
+                        // two-level selection, where 0.6 % of the scores pass, ran at a third of the MMA rate.)
+                        uint32_t pass = 0;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (none[g]) continue;
+#pragma unroll
+                            for (int j = g * 8; j < g * 8 + 8; ++j) pass |= (__uint_as_float(v[j]) >= tau ? 0u : 1u) << j;
+                        }
+                        if (pass) {
+                            uint32_t pos = atomicAdd(&p.cand_cnt[oq], (uint32_t)__popc(pass));
+                            uint64_t* list = p.cand + (uint64_t)oq * p.cap;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if ((pass >> j) & 1u) {
+                                    if (pos < p.cap) list[pos] = ((uint64_t)v[j] << 32) | (uint32_t)(tile_row0 + c0 + j);
+                                    ++pos;
+                                }
+                            }
                         }
                     } else if (!(none[0] && none[1] && none[2] && none[3])) {
                         // rare path: only the groups of 8 in which this thread saw a passing (or NaN) score are walked again
@@ -688,7 +712,9 @@ static void ensure_side_arrays(const vdb_dataset* cds, cudaStream_t st, int kind
         }
     }
     // ~3 % of the shard, so the sample pass stays a small fixed fraction of the filter pass on every shard size
-    ds->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(G_SAMPLE, n / 2), std::max<uint64_t>(2048, n / 30));
+    static const uint32_t sample_env = getenv("VDB_GEMM_SAMPLE_N") ? (uint32_t)atoi(getenv("VDB_GEMM_SAMPLE_N")) : 0;
+    const uint64_t sample_max = sample_env ? sample_env : G_SAMPLE;
+    ds->sample_n = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(sample_max, n / 2), std::max<uint64_t>(2048, n / 30));
     const size_t op_row_bytes = ds->op_kind == KIND_F16 ? (size_t)ds->op_pitch * 2 : ds->pitch_bytes();
     VDB_CUDA(cudaMalloc(&ds->d_sample, (size_t)ds->sample_n * op_row_bytes));
     VDB_CUDA(cudaMalloc(&ds->d_sample_sq, (size_t)ds->sample_n * 4));
@@ -733,7 +759,7 @@ static int gemm_ctas() {
 }
 
 template <int MODE, int CTAS, int METRIC, int KIND>
-static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st) {
+static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st, const char* prof_name) {
     using Cfg = GemmCfg<CTAS, KIND>;
     auto kern = flat_gemm_kernel<MODE, CTAS, METRIC, KIND>;
     static std::atomic<size_t> configured[VDB_MAX_DEVICES];
@@ -755,33 +781,34 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
     DevBuf counter(4, st);
     VDB_CUDA(cudaMemsetAsync(counter.p, 0, 4, st));
     p.work_counter = counter.as<uint32_t>();
-    ProfScope prof("flat_gemm", st);
+    ProfScope prof(prof_name, st);
     VDB_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, p));
     VDB_LAUNCHED();
 }
 
 template <int MODE, int CTAS>
-static void launch_gemm_mk(int metric, int kind, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st) {
+static void launch_gemm_mk(int metric, int kind, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st,
+                           const char* prof_name) {
     if (metric == VDB_COSINE) {
-        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_F16>(mq, mx, p, st);
-        else launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_TF32>(mq, mx, p, st);
+        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_F16>(mq, mx, p, st, prof_name);
+        else launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_TF32>(mq, mx, p, st, prof_name);
     } else {
-        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_F16>(mq, mx, p, st);
-        else launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_TF32>(mq, mx, p, st);
+        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_F16>(mq, mx, p, st, prof_name);
+        else launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_TF32>(mq, mx, p, st, prof_name);
     }
 }
 
 // mode 0 = store every score, 1 = filter, 2 = per-slab smallest scores; `p` must have been planned (plan_gemm)
 static void launch_gemm(int mode, int metric, int kind, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p,
-                        cudaStream_t st, int ctas = 0) {
+                        cudaStream_t st, int ctas = 0, const char* prof_name = "flat_gemm") {
     const bool pair = (ctas ? ctas : gemm_ctas()) == 2;
     switch (mode * 2 + (pair ? 1 : 0)) {
-        case 0: launch_gemm_mk<0, 1>(metric, kind, mq, mx, p, st); break;
-        case 1: launch_gemm_mk<0, 2>(metric, kind, mq, mx, p, st); break;
-        case 2: launch_gemm_mk<1, 1>(metric, kind, mq, mx, p, st); break;
-        case 3: launch_gemm_mk<1, 2>(metric, kind, mq, mx, p, st); break;
-        case 4: launch_gemm_mk<2, 1>(metric, kind, mq, mx, p, st); break;
-        default: launch_gemm_mk<2, 2>(metric, kind, mq, mx, p, st); break;
+        case 0: launch_gemm_mk<0, 1>(metric, kind, mq, mx, p, st, prof_name); break;
+        case 1: launch_gemm_mk<0, 2>(metric, kind, mq, mx, p, st, prof_name); break;
+        case 2: launch_gemm_mk<1, 1>(metric, kind, mq, mx, p, st, prof_name); break;
+        case 3: launch_gemm_mk<1, 2>(metric, kind, mq, mx, p, st, prof_name); break;
+        case 4: launch_gemm_mk<2, 1>(metric, kind, mq, mx, p, st, prof_name); break;
+        default: launch_gemm_mk<2, 2>(metric, kind, mq, mx, p, st, prof_name); break;
     }
 }
 
@@ -1321,6 +1348,11 @@ static GemmParams base_params(const vdb_tq* tq) {
     p.qab = tq->qab.as<float>();
     p.qb = tq->qb.as<float>();
     p.qnorm = tq->ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr;
+    // The filter over the whole set passes ~0.05 % of its scores: there the per-score path is faster (A/B in one process,
+    // 1M x 960, 10k queries: 14.7 vs 16.6 ms per pass); the sample pass of the two-level selection passes ~0.6 % and
+    // takes the one-atomic path (1.25 vs 1.94 ms). VDB_GEMM_RARE_PER_SCORE overrides both (read per call).
+    const char* rare = getenv("VDB_GEMM_RARE_PER_SCORE");
+    p.rare_per_score = rare ? (atoi(rare) ? 1u : 0u) : 1u;
     return p;
 }
 
@@ -1361,7 +1393,8 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     // decides, as always.
     // Batches of <= 128 queries (single CTAs, HBM-bound on the operand rows) keep the one-launch register epilogue.
     static const bool two_level = !(getenv("VDB_GEMM_SAMPLE_2L") && !atoi(getenv("VDB_GEMM_SAMPLE_2L")));
-    const uint32_t SUB = (uint32_t)std::max<uint64_t>(2, ns / 1024);   // sub-sample of ~1024 rows
+    static const uint32_t sub_env = getenv("VDB_GEMM_SAMPLE_SUBN") ? (uint32_t)atoi(getenv("VDB_GEMM_SAMPLE_SUBN")) : 0;
+    const uint32_t SUB = (uint32_t)std::max<uint64_t>(2, ns / (sub_env ? sub_env : 1024));   // sub-sample of ~1024 rows
     if (two_level && ns >= 2048 && (tq->ctas == 2 || j > (uint32_t)G_TOPJ)) {
         const uint64_t ns1 = ns / SUB;
         const uint32_t j1 = tensor_j0(j, ns1, ns, 1e-5);
@@ -1374,12 +1407,12 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
         if (j1 <= (uint32_t)G_TOPJ) {   // ~1024 rows: the register epilogue costs 1/32 of what it did on the whole sample
             DevBuf part1((size_t)tq->nq * p1.nslabs * G_TOPJ * 8, st);
             p1.out_keys = part1.as<uint64_t>();
-            launch_gemm(2, ds->metric, tq->kind, tq->mq, m1, p1, st, tq->ctas);
+            launch_gemm(2, ds->metric, tq->kind, tq->mq, m1, p1, st, tq->ctas, "flat_gemm_sample");
             launch_merge_keys(part1.as<uint64_t>(), p1.nslabs, tq->nq, G_TOPJ, false, j1, k1.as<uint64_t>(), nullptr, nullptr, nullptr, st);
         } else {
             DevBuf all1((size_t)tq->nq * ns1 * 8, st);
             p1.out_keys = all1.as<uint64_t>();
-            launch_gemm(0, ds->metric, tq->kind, tq->mq, m1, p1, st, tq->ctas);
+            launch_gemm(0, ds->metric, tq->kind, tq->mq, m1, p1, st, tq->ctas, "flat_gemm_sample");
             launch_merge_keys(all1.as<uint64_t>(), 1, tq->nq, (uint32_t)ns1, false, j1, k1.as<uint64_t>(), nullptr, nullptr, nullptr, st);
         }
         tau_coarse_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(k1.as<uint64_t>(), tq->nq, j1, tau1.as<float>());
@@ -1392,8 +1425,9 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
         p2.cand_cnt = cnt2.as<uint32_t>();
         p2.cand = cand2.as<uint64_t>();
         p2.cap = cap2;
+        if (!getenv("VDB_GEMM_RARE_PER_SCORE")) p2.rare_per_score = 0;
         plan_gemm(p2, tq->ctas);
-        launch_gemm(1, ds->metric, tq->kind, tq->mq, ms, p2, st, tq->ctas);
+        launch_gemm(1, ds->metric, tq->kind, tq->mq, ms, p2, st, tq->ctas, "flat_gemm_sample");
         cand_sortable_kernel<<<tq->nq, 128, 0, st>>>(cand2.as<uint64_t>(), cnt2.as<uint32_t>(), cap2);
         VDB_LAUNCHED();
         launch_merge_keys(cand2.as<uint64_t>(), 1, tq->nq, cap2, false, j, skeys.as<uint64_t>(), nullptr, nullptr, nullptr, st,
@@ -1403,12 +1437,12 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
         // nq * nslabs * G_TOPJ keys ever reaches HBM
         DevBuf part((size_t)tq->nq * ps.nslabs * G_TOPJ * 8, st);
         ps.out_keys = part.as<uint64_t>();
-        launch_gemm(2, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas);
+        launch_gemm(2, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas, "flat_gemm_sample");
         launch_merge_keys(part.as<uint64_t>(), ps.nslabs, tq->nq, G_TOPJ, false, j, skeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
     } else {
         DevBuf all((size_t)tq->nq * ns * 8, st);
         ps.out_keys = all.as<uint64_t>();
-        launch_gemm(0, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas);
+        launch_gemm(0, ds->metric, tq->kind, tq->mq, ms, ps, st, tq->ctas, "flat_gemm_sample");
         launch_merge_keys(all.as<uint64_t>(), 1, tq->nq, (uint32_t)ns, false, j, skeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
     }
     // exact fp32 distances of those rows (the rerank's arithmetic), sorted ascending per query
