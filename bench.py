@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DIM = 960
-GEMM_PART_TRAFFIC = 1.413e9 + 26.7e6  # DRAM bytes of one filter launch (1/3 of the rows), see profiles/r01_flat_gemm_ncu.md
+GEMM_PASS_TRAFFIC = 1.954014e9 + 45.709e6  # dram__bytes_read.sum + dram__bytes_write.sum of ONE filter launch (the whole pass:
+#                                            1M x 960 FP16 operand rows, 10 000 queries), profiles/r02_flat_gemm_ncu.md
 CHUNK = 50_000  # rows per generator chunk (seeded per chunk so any sharding sees the same bits)
 
 
@@ -708,10 +709,11 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": achieved / peak,
                 "operand_kind": "f16 x f16 -> f32 (tcgen05.mma.kind::f16)" if f16 else "tf32 x tf32 -> f32 (tcgen05.mma.kind::tf32)",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one filter launch from the committed ncu capture
-                "traffic": (GEMM_PART_TRAFFIC if (n_local == 1_000_000 and args.nq == 10_000 and f16) else None),
-                "traffic_source": "ncu --set full capture, profiles/r02_flat_gemm_ncu.md (bytes per filter launch = "
-                                  "one of the 3 row parts of a step)",
-                "algorithmic_bytes_per_launch": n_local * DIM * (2 if f16 else 4) / 3 + args.nq * DIM * (2 if f16 else 4),
+                "traffic": (GEMM_PASS_TRAFFIC if (n_local == 1_000_000 and args.nq == 10_000 and f16 and
+                                                  int(os.environ.get("VDB_GEMM_PARTS", "1")) == 1) else None),
+                "traffic_source": "ncu --set full capture of this launch, profiles/r02_flat_gemm_ncu.md (a constant from that "
+                                  "capture, not measured in this run)",
+                "algorithmic_bytes_per_launch": n_local * (DIM * (2 if f16 else 4) + 12) + args.nq * DIM * (2 if f16 else 4),
                 "peak_source": peak_src,
                 "launches": c_dom, "avg_launch_ms": t_dom / max(c_dom, 1),
                 "flop_per_step": flops / args.steps}
