@@ -428,6 +428,8 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                 const float sc = __uint_as_float(v[j]);
                                 if (MODE == 2) {
                                     if (sc < best[MODE == 2 ? G_TOPJ - 1 : 0]) {  // bubble (sc, row) into place
+                                        // (measured: computing the rank with 16 independent compares and rewriting the slots
+                                        // independently executes ~50 % more instructions and is 15-20 % SLOWER than this chain)
                                         float w = sc;
                                         uint32_t wi = (uint32_t)(tile_row0 + c0 + j);
 #pragma unroll
@@ -1801,12 +1803,13 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
 // range the TMA can tile; the queries are gathered list by list into one matrix; the work items of the contraction
 // kernel are (list, tile of gathered queries, range of row tiles). Query tiles of <= 128 rows run on single CTAs
 // (M = 128), larger ones on CTA pairs (M = 256). Thresholds:
-//   k/16 small (j0 <= 16): a stratified 1/16 sample of every list (also kept in list order) is scored first, the
+//   k/64 small (j0 <= 16): a stratified 1/64 sample of every list (also kept in list order) is scored first, the
 //     j0-th smallest sampled S' over the probed lists (+ margin) is tau, as in the Flat path;
 //   else: tau = the k-th smallest EXACT distance over the first S rows of the visit sequence (complete by construction).
 // Candidates are reranked with the FP32 list scan's arithmetic; queries failing the completeness check or overflowing
 // their candidate list are redone by the FP32 list scan.
-constexpr uint32_t IVF_SAMPLE_RATE = 16;
+constexpr uint32_t IVF_SAMPLE_RATE = 64;   // round 2: 16 -> 64. The register top-16 epilogue pays per sampled row (594 us of a
+// 2.1 ms 1000-query batch at 1/16); a sparser sample loosens tau (more candidates), which the upper-bound pruning takes back
 
 __global__ void gather_op_rows_kernel(const uint4* __restrict__ op_rows, uint32_t row_u4, const float* __restrict__ colA,
                                       const float* __restrict__ rn, const float* __restrict__ ex,
@@ -2124,12 +2127,21 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
             pf.cap = cap;
             run_items(1, items, ivf->d_rows_lo, ds->n, pf);
         }
+        // ---- candidates that cannot be among the k best by their score bounds are dropped (cand_prune_kernel) ----
+        DevBuf pcnt((size_t)nq * 4, st);
+        {
+            auto kern = cosine ? cand_prune_kernel<VDB_COSINE> : cand_prune_kernel<VDB_L2SQR>;
+            kern<<<nq, 256, (size_t)cap * 4, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, k, ivf->d_rn_lo, ivf->d_ex_lo,
+                                                   tq->qab.as<float>(), tq->qb.as<float>(), cosine ? nullptr : tq->qsq.as<float>(),
+                                                   pcnt.as<uint32_t>());
+            VDB_LAUNCHED();
+        }
         // ---- exact rerank (the FP32 list scan's arithmetic) and top-k ----
         const uint64_t total = (uint64_t)nq * cap;
         DevBuf off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st), keys2(total * 8, st);
-        cand_offsets_kernel<<<1, 1024, 0, st>>>(tq->cnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
+        cand_offsets_kernel<<<1, 1024, 0, st>>>(pcnt.as<uint32_t>(), nq, cap, off.as<uint64_t>());
         VDB_LAUNCHED();
-        cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, off.as<uint64_t>(),
+        cand_to_pairs_kernel<<<nq, 256, 0, st>>>(cand.as<uint64_t>(), pcnt.as<uint32_t>(), cap, off.as<uint64_t>(),
                                                  ivf->d_members, qidx.as<uint32_t>(), rid.as<uint32_t>());
         VDB_LAUNCHED();
         const uint64_t* d_total = off.as<uint64_t>() + nq;

@@ -34,6 +34,8 @@ struct vdb_ivf {
     int dtype = VDB_F32, metric = VDB_L2SQR;
     uint64_t n = 0;
     void* d_centroids = nullptr;    // [nlist][dim] of dtype
+    float* d_centT = nullptr;       // [dim][nlist] f32: the probe-order kernel reads a centroid per lane, coalesced
+    float* d_cnorm = nullptr;       // [nlist] ||c|| (cosine), summed like assign_exact_kernel
     uint64_t* d_offsets = nullptr;  // [nlist+1]
     uint32_t* d_members = nullptr;  // [n] local row ids, ascending inside a list
     uint32_t max_list = 0;
@@ -43,7 +45,7 @@ struct vdb_ivf {
     float* d_colA_lo = nullptr;   // [n] ||x||^2 (L2Sqr) or 1/||x|| (cosine)
     float* d_rn_lo = nullptr;     // [n] ||x||
     float* d_ex_lo = nullptr;     // [n] operand error norm
-    // stratified 1/16 sample of every list, also in list order (threshold pass of the tensor-core probe scan)
+    // stratified 1/64 sample of every list, also in list order (threshold pass of the tensor-core probe scan)
     void* d_samp_rows = nullptr;
     float* d_samp_colA = nullptr, *d_samp_rn = nullptr, *d_samp_ex = nullptr;
     std::vector<uint64_t> h_samp_off;  // [nlist+1]

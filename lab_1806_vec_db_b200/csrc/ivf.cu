@@ -356,6 +356,79 @@ __global__ void probe_keys_kernel(const float* __restrict__ dist, uint64_t count
         keys[j] = make_key(dist[j], (uint32_t)(j % nlist));
 }
 
+// ---- exact query-centroid distances of a search batch (probe order = find_n_nearest, k_means.rs:174-191) -------------
+// kmeans_assign_exact is laid out for n >> k (a 32-centroid chunk staged per CTA, one launch per chunk): a 1000-query
+// batch paid 4 launches x 63 us for 0.4 GFLOP. Here the centroids are transposed once per index ([dim][nlist] f32, plus
+// ||c|| for cosine), one warp takes (query, 32 centroids) with lane = centroid and the query row in shared memory, and
+// every lane walks the same unfused sequential chain over the dimensions - the distances are bit-identical.
+template <typename T>
+__global__ void centroid_transpose_kernel(const T* __restrict__ cent, uint32_t nlist, uint32_t dim, float* __restrict__ centT,
+                                          float* __restrict__ cnorm) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nlist) return;
+    float s = 0.f;
+    for (uint32_t j = 0; j < dim; ++j) {
+        const float v = (float)cent[(size_t)c * dim + j];
+        centT[(size_t)j * nlist + c] = v;
+        s = __fadd_rn(s, __fmul_rn(v, v));
+    }
+    cnorm[c] = sqrtf(s);
+}
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(256) probe_dist_kernel(const T* __restrict__ queries, uint32_t nq, uint32_t dim,
+                                                         const float* __restrict__ centT, const float* __restrict__ cnorm,
+                                                         uint32_t nlist, float* __restrict__ out) {
+    extern __shared__ float probe_rows[];   // [8 warps][dim]
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t chunks = (nlist + 31) / 32;
+    const uint64_t w = (uint64_t)blockIdx.x * 8 + warp;
+    const uint32_t q = (uint32_t)(w / chunks), ch = (uint32_t)(w % chunks);
+    if (q >= nq) return;
+    float* x = probe_rows + (size_t)warp * dim;
+    for (uint32_t e = lane; e < dim; e += 32) x[e] = (float)queries[(size_t)q * dim + e];
+    __syncwarp();
+    const uint32_t c = ch * 32 + lane, cc = min(c, nlist - 1);
+    const float* col = centT + cc;
+    float s = 0.f, svv = 0.f;
+#pragma unroll 8
+    for (uint32_t j = 0; j < dim; ++j) {
+        const float xv = x[j], cv = col[(size_t)j * nlist];
+        if (METRIC == VDB_L2SQR) {
+            const float df = __fsub_rn(xv, cv);
+            s = __fadd_rn(s, __fmul_rn(df, df));
+        } else {
+            s = __fadd_rn(s, __fmul_rn(xv, cv));
+            svv = __fadd_rn(svv, __fmul_rn(xv, xv));
+        }
+    }
+    float dist = s;
+    if (METRIC == VDB_COSINE) {
+        const float den = fmaxf(__fmul_rn(sqrtf(svv), cnorm[cc]), 1e-10f);
+        dist = __fsub_rn(1.0f, __fdiv_rn(s, den));
+    }
+    if (c < nlist) out[(size_t)q * nlist + c] = dist;
+}
+static void probe_distances(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, float* d_out,
+                            cudaStream_t st) {
+    const uint32_t chunks = (ivf->nlist + 31) / 32;
+    const uint32_t grid = (uint32_t)ceil_div<uint64_t>((uint64_t)nq * chunks, 8);
+    const size_t smem = (size_t)8 * ds->dim * 4;
+    auto launch = [&](auto kern, auto* q) {
+        if (smem > 48 * 1024) VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope prof("kmeans_assign", st);
+        kern<<<grid, 256, smem, st>>>(q, nq, ds->dim, ivf->d_centT, ivf->d_cnorm, ivf->nlist, d_out);
+        VDB_LAUNCHED();
+    };
+    const bool l2 = ds->metric == VDB_L2SQR;
+    if (ds->dtype == VDB_F32) {
+        if (l2) launch(probe_dist_kernel<float, VDB_L2SQR>, (const float*)d_queries);
+        else launch(probe_dist_kernel<float, VDB_COSINE>, (const float*)d_queries);
+    } else {
+        if (l2) launch(probe_dist_kernel<uint8_t, VDB_L2SQR>, (const uint8_t*)d_queries);
+        else launch(probe_dist_kernel<uint8_t, VDB_COSINE>, (const uint8_t*)d_queries);
+    }
+}
+
 vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nlist, uint32_t* h_assign_out) {
     VDB_REQUIRE(nlist > 0, "The number of clusters should be greater than 0.");
     VDB_REQUIRE(h_centroids, "centroids is NULL");
@@ -374,6 +447,15 @@ vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nli
         VDB_CUDA(cudaMalloc(&ivf->d_offsets, (size_t)(nlist + 1) * 8));
         VDB_CUDA(cudaMalloc(&ivf->d_members, std::max<size_t>(4, ds->n * 4)));
         VDB_CUDA(cudaMemcpyAsync(ivf->d_centroids, h_centroids, cbytes, cudaMemcpyHostToDevice, st));
+        VDB_CUDA(cudaMalloc(&ivf->d_centT, (size_t)nlist * ds->dim * 4));
+        VDB_CUDA(cudaMalloc(&ivf->d_cnorm, (size_t)nlist * 4));
+        if (ds->dtype == VDB_F32)
+            centroid_transpose_kernel<float><<<ceil_div(nlist, 128u), 128, 0, st>>>((const float*)ivf->d_centroids, nlist, ds->dim,
+                                                                                   ivf->d_centT, ivf->d_cnorm);
+        else
+            centroid_transpose_kernel<uint8_t><<<ceil_div(nlist, 128u), 128, 0, st>>>((const uint8_t*)ivf->d_centroids, nlist, ds->dim,
+                                                                                     ivf->d_centT, ivf->d_cnorm);
+        VDB_LAUNCHED();
         {
             DevBuf best(ds->n * 8, st), assign(std::max<size_t>(4, ds->n * 4), st);
             kmeans_assign_exact(ds->d_rows, ds->n, ds->pitch, ds->dtype, ds->metric, 0, ds->dim, ivf->d_centroids,
@@ -399,6 +481,8 @@ vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nli
 void ivf_destroy(vdb_ivf* ivf) {
     if (!ivf) return;
     cudaFree(ivf->d_centroids);
+    cudaFree(ivf->d_centT);
+    cudaFree(ivf->d_cnorm);
     cudaFree(ivf->d_offsets);
     cudaFree(ivf->d_members);
     cudaFree(ivf->d_rows_lo);
@@ -547,10 +631,8 @@ void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queri
     }
     const uint32_t nprobe = std::min(n_probes, ivf->nlist);
     // 1. exact query-centroid distances, probe order = find_n_nearest (k_means.rs:174-191)
-    DevBuf cdist((size_t)nq * ivf->nlist * 4, st), best((size_t)nq * 8, st), ckeys((size_t)nq * ivf->nlist * 8, st),
-        probes((size_t)nq * nprobe * 8, st);
-    kmeans_assign_exact(d_queries, nq, ds->dim, ds->dtype, ds->metric, 0, ds->dim, ivf->d_centroids, ivf->nlist,
-                        best.as<uint64_t>(), nullptr, cdist.as<float>(), st);
+    DevBuf cdist((size_t)nq * ivf->nlist * 4, st), ckeys((size_t)nq * ivf->nlist * 8, st), probes((size_t)nq * nprobe * 8, st);
+    probe_distances(ds, ivf, d_queries, nq, cdist.as<float>(), st);
     const uint64_t cnt = (uint64_t)nq * ivf->nlist;
     probe_keys_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(cnt, 256), 4096), 256, 0, st>>>(
         cdist.as<float>(), cnt, ivf->nlist, ckeys.as<uint64_t>());
