@@ -54,6 +54,26 @@ extern std::atomic<uint64_t> g_launches;
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----
 void prof_record(const char* name, cudaStream_t st, bool begin);
 extern bool g_prof_on;
+// page-locked staging memory that grows and is reused (one per host thread and purpose: thread_local). Copies from / to
+// pageable vectors are staged by the driver and serialise with the host; small per-call tables go through this instead.
+struct PinnedStage {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* get(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            VDB_CUDA(cudaHostAlloc(&p, bytes * 2, cudaHostAllocPortable));
+            cap = bytes * 2;
+        }
+        return p;
+    }
+    ~PinnedStage() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
 struct ProfScope {
     const char* name;
     cudaStream_t st;

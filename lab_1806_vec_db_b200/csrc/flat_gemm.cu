@@ -1854,7 +1854,8 @@ __global__ void ivf_sample_gather_kernel(const uint4* __restrict__ rows_lo, uint
 }
 
 static std::mutex g_ivf_side_mu;
-static void ensure_ivf_side(const vdb_dataset* ds, const vdb_ivf* civf, const std::vector<uint64_t>& h_off, cudaStream_t st) {
+static void ensure_ivf_side(const vdb_dataset* ds, const vdb_ivf* civf, cudaStream_t st) {
+    const std::vector<uint64_t>& h_off = civf->h_off;
     vdb_ivf* ivf = const_cast<vdb_ivf*>(civf);
     std::lock_guard<std::mutex> lk(g_ivf_side_mu);
     ensure_side_arrays(ds, st);
@@ -1987,31 +1988,67 @@ __global__ void ivf_check_kernel(const uint64_t* __restrict__ keys, uint32_t nq,
 }
 
 bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
-                     const std::vector<uint64_t>& h_probes, const std::vector<uint64_t>& h_off, uint32_t nq, uint32_t nprobe,
-                     uint32_t k, uint64_t* d_keys, cudaStream_t st) {
+                     const uint64_t* h_probes, uint32_t nq, uint32_t nprobe, uint32_t k, uint64_t* d_keys, cudaStream_t st) {
     if (!flat_gemm_supported(ds, nq, k) || k > 512) return false;
-    ensure_ivf_side(ds, ivf, h_off, st);
-    // ---- host: group the (query, list) pairs by list, build the gathered query order and the work items ----
-    std::vector<std::vector<uint32_t>> by_list(ivf->nlist);   // entries: q * nprobe + j
-    for (uint32_t q = 0; q < nq; ++q)
-        for (uint32_t j = 0; j < nprobe; ++j) {
-            const uint64_t pk = h_probes[(size_t)q * nprobe + j];
-            if (pk != KEY_NONE) by_list[key_id(pk)].push_back(q * nprobe + j);
-        }
-    std::vector<uint32_t> qmap, gpos((size_t)nq * nprobe, 0xffffffffu);
-    std::vector<GemmItem> items[2], sitems[2];   // [0]: single CTAs (<= 128 gathered queries), [1]: CTA pairs
-    qmap.reserve((size_t)nq * nprobe);
+    ensure_ivf_side(ds, ivf, st);
+    const std::vector<uint64_t>& h_off = ivf->h_off;
+    // ---- host: group the (query, list) pairs by list (counting sort), build the gathered query order and the work
+    // items. Everything the device needs - qmap | gpos | the four item tables - is laid out in ONE page-locked staging
+    // block and uploaded with one copy (round 1: vectors of vectors and four pageable copies, ~0.4 ms per 1000 queries).
+    const size_t npairs = (size_t)nq * nprobe;
+    std::vector<uint32_t> lcount(ivf->nlist + 1, 0);
+    for (size_t e = 0; e < npairs; ++e) {
+        const uint64_t pk = h_probes[e];
+        if (pk != KEY_NONE) ++lcount[key_id(pk) + 1];
+    }
+    for (uint32_t l = 0; l < ivf->nlist; ++l) lcount[l + 1] += lcount[l];   // lcount[l] = first gathered row of list l
+    const uint32_t G = lcount[ivf->nlist];
     static const uint32_t force_ctas = getenv("VDB_IVF_CTAS") ? (uint32_t)atoi(getenv("VDB_IVF_CTAS")) : 0;
     const uint32_t tiles_per_item = 8;
+    // item counts first (the staging block is sized from them)
+    size_t n_items[2] = {0, 0}, n_sitems[2] = {0, 0};
     for (uint32_t l = 0; l < ivf->nlist; ++l) {
         const uint64_t r0 = h_off[l], r1 = h_off[l + 1];
-        if (r1 == r0 || by_list[l].empty()) continue;
-        const uint32_t g0 = (uint32_t)qmap.size();
-        for (uint32_t e : by_list[l]) {
-            gpos[e] = (uint32_t)qmap.size();
-            qmap.push_back(e / nprobe);
+        const uint32_t cnt = lcount[l + 1] - lcount[l];
+        if (r1 == r0 || cnt == 0) continue;
+        const uint64_t row_groups = ceil_div<uint64_t>(r1 - r0, (uint64_t)tiles_per_item * GN);
+        for (uint32_t g = 0; g < cnt;) {
+            const uint32_t left = cnt - g;
+            const uint32_t pair = force_ctas ? force_ctas - 1 : (left > GM ? 1u : 0u);
+            n_items[pair] += row_groups;
+            n_sitems[pair] += 1;
+            g += std::min(left, pair ? 2u * GM : (uint32_t)GM);
         }
-        const uint32_t g1 = (uint32_t)qmap.size();
+    }
+    static thread_local PinnedStage table_stage;
+    const size_t off_qmap = 0, off_gpos = off_qmap + round_up<size_t>((size_t)G * 4, 16);
+    size_t off_items[2], off_sitems[2], at = off_gpos + round_up<size_t>(npairs * 4, 16);
+    for (int t = 0; t < 2; ++t) off_items[t] = at, at += n_items[t] * sizeof(GemmItem);
+    for (int t = 0; t < 2; ++t) off_sitems[t] = at, at += n_sitems[t] * sizeof(GemmItem);
+    const size_t stage_bytes = std::max<size_t>(at, 16);
+    uint8_t* stage = (uint8_t*)table_stage.get(stage_bytes);
+    uint32_t* qmap = (uint32_t*)(stage + off_qmap);
+    uint32_t* gpos = (uint32_t*)(stage + off_gpos);
+    GemmItem* items[2] = {(GemmItem*)(stage + off_items[0]), (GemmItem*)(stage + off_items[1])};
+    GemmItem* sitems[2] = {(GemmItem*)(stage + off_sitems[0]), (GemmItem*)(stage + off_sitems[1])};
+    {
+        std::vector<uint32_t> fill(lcount.begin(), lcount.end() - 1);   // next free gathered row of every list
+        for (size_t e = 0; e < npairs; ++e) {
+            const uint64_t pk = h_probes[e];
+            if (pk == KEY_NONE) {
+                gpos[e] = 0xffffffffu;
+                continue;
+            }
+            const uint32_t pos = fill[key_id(pk)]++;
+            gpos[e] = pos;
+            qmap[pos] = (uint32_t)(e / nprobe);
+        }
+    }
+    size_t w_items[2] = {0, 0}, w_sitems[2] = {0, 0};
+    for (uint32_t l = 0; l < ivf->nlist; ++l) {
+        const uint64_t r0 = h_off[l], r1 = h_off[l + 1];
+        const uint32_t g0 = lcount[l], g1 = lcount[l + 1];
+        if (r1 == r0 || g1 == g0) continue;
         const uint64_t s0 = ivf->h_samp_off[l], s1 = ivf->h_samp_off[l + 1];
         // query tiles: 256 rows on a CTA pair, a remainder of <= 128 rows on a single CTA
         for (uint32_t g = g0; g < g1;) {
@@ -2019,27 +2056,32 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
             const uint32_t pair = force_ctas ? force_ctas - 1 : (left > GM ? 1u : 0u);
             const uint32_t len = std::min(left, pair ? 2u * GM : (uint32_t)GM);
             for (uint64_t r = r0; r < r1; r += (uint64_t)tiles_per_item * GN)
-                items[pair].push_back(GemmItem{g, g + len, r, std::min<uint64_t>(r1, r + (uint64_t)tiles_per_item * GN)});
-            sitems[pair].push_back(GemmItem{g, g + len, s0, s1});
+                items[pair][w_items[pair]++] = GemmItem{g, g + len, r, std::min<uint64_t>(r1, r + (uint64_t)tiles_per_item * GN)};
+            sitems[pair][w_sitems[pair]++] = GemmItem{g, g + len, s0, s1};
             g += len;
         }
     }
-    if (qmap.empty()) {
+    if (G == 0) {
         VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
         return true;
     }
-    const uint32_t G = (uint32_t)qmap.size();
     vdb_tq* tq = tensor_begin(ds, d_queries, nq, st);
     try {
         const bool cosine = ds->metric == VDB_COSINE;
         // ---- gathered query matrix, its per-row scalars, item tables ----
         const size_t q_rowb = (size_t)tq->op_pitch * (tq->kind == KIND_F16 ? 2 : 4);
-        DevBuf d_qmap((size_t)G * 4, st), qg((size_t)G * q_rowb, st), qd_g((size_t)G * 4, st), qab_g((size_t)G * 4, st),
+        DevBuf d_stage(stage_bytes, st), qg((size_t)G * q_rowb, st), qd_g((size_t)G * 4, st), qab_g((size_t)G * 4, st),
             qb_g((size_t)G * 4, st), qn_g((size_t)G * 4, st), tau_g((size_t)G * 4, st), tau((size_t)nq * 4, st);
-        VDB_CUDA(cudaMemcpyAsync(d_qmap.p, qmap.data(), (size_t)G * 4, cudaMemcpyHostToDevice, st));
+        VDB_CUDA(cudaMemcpyAsync(d_stage.p, stage, stage_bytes, cudaMemcpyHostToDevice, st));
+        const uint32_t* d_qmap = (const uint32_t*)((const uint8_t*)d_stage.p + off_qmap);
+        const uint32_t* d_gpos = (const uint32_t*)((const uint8_t*)d_stage.p + off_gpos);
+        const GemmItem* d_items[2] = {(const GemmItem*)((const uint8_t*)d_stage.p + off_items[0]),
+                                      (const GemmItem*)((const uint8_t*)d_stage.p + off_items[1])};
+        const GemmItem* d_sitems[2] = {(const GemmItem*)((const uint8_t*)d_stage.p + off_sitems[0]),
+                                       (const GemmItem*)((const uint8_t*)d_stage.p + off_sitems[1])};
         gather_query_side_kernel<<<G, 128, 0, st>>>((const uint4*)tq->qop.p, (uint32_t)(q_rowb / 16), tq->qd.as<float>(),
                                                     tq->qab.as<float>(), tq->qb.as<float>(),
-                                                    cosine ? tq->qtile.qcache.as<float>() : nullptr, d_qmap.as<uint32_t>(), G,
+                                                    cosine ? tq->qtile.qcache.as<float>() : nullptr, d_qmap, G,
                                                     (uint4*)qg.p, qd_g.as<float>(), qab_g.as<float>(), qb_g.as<float>(), qn_g.as<float>());
         VDB_LAUNCHED();
         const CUtensorMap mq = make_op_map(tq->kind, qg.p, ds->dim, G, q_rowb, GM);
@@ -2051,18 +2093,16 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
         base.qb = qb_g.as<float>();
         base.qnorm = cosine ? qn_g.as<float>() : nullptr;
         base.row_stride = 1;
-        base.qmap = d_qmap.as<uint32_t>();
+        base.qmap = d_qmap;
         base.nslabs = 1;
-        auto run_items = [&](int mode, const std::vector<GemmItem>* tabs, const void* rows, uint64_t nrows, GemmParams p) {
+        auto run_items = [&](int mode, const GemmItem* const* tabs, const size_t* counts, const void* rows, uint64_t nrows,
+                             GemmParams p) {
             for (uint32_t pair = 0; pair < 2; ++pair) {
-                if (tabs[pair].empty()) continue;
-                DevBuf d_items(tabs[pair].size() * sizeof(GemmItem), st);
-                VDB_CUDA(cudaMemcpyAsync(d_items.p, tabs[pair].data(), tabs[pair].size() * sizeof(GemmItem),
-                                         cudaMemcpyHostToDevice, st));
+                if (counts[pair] == 0) continue;
                 const CUtensorMap mx = make_op_map(tq->kind, rows, ds->dim, nrows, op_row_bytes_of(ds), GN / (pair + 1));
                 p.nrows = nrows;
-                p.items = d_items.as<GemmItem>();
-                p.nitems = (uint32_t)tabs[pair].size();
+                p.items = tabs[pair];
+                p.nitems = (uint32_t)counts[pair];
                 launch_gemm(mode, ds->metric, tq->kind, mq, mx, p, st, (int)pair + 1);
             }
         };
@@ -2071,17 +2111,15 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
         static const int force_subset = getenv("VDB_IVF_SUBSET") ? atoi(getenv("VDB_IVF_SUBSET")) : 0;
         const bool by_sample = j0 <= (uint32_t)G_TOPJ && ivf->samp_n > 0 && !force_subset;
         if (by_sample) {
-            DevBuf skeys((size_t)G * G_TOPJ * 8, st), d_gpos((size_t)nq * nprobe * 4, st),
-                ckeys((size_t)nq * nprobe * G_TOPJ * 8, st), jkeys((size_t)nq * j0 * 8, st);
+            DevBuf skeys((size_t)G * G_TOPJ * 8, st), ckeys((size_t)nq * nprobe * G_TOPJ * 8, st), jkeys((size_t)nq * j0 * 8, st);
             VDB_CUDA(cudaMemsetAsync(skeys.p, 0xff, (size_t)G * G_TOPJ * 8, st));
-            VDB_CUDA(cudaMemcpyAsync(d_gpos.p, gpos.data(), (size_t)nq * nprobe * 4, cudaMemcpyHostToDevice, st));
             GemmParams ps = base;
             ps.sqnorm = ivf->d_samp_colA;
             ps.rnorm = ivf->d_samp_rn;
             ps.ex = ivf->d_samp_ex;
             ps.out_keys = skeys.as<uint64_t>();
-            run_items(2, sitems, ivf->d_samp_rows, ivf->samp_n, ps);
-            ivf_collect_sample_kernel<<<nq, 128, 0, st>>>(skeys.as<uint64_t>(), d_gpos.as<uint32_t>(), nprobe, ckeys.as<uint64_t>());
+            run_items(2, d_sitems, n_sitems, ivf->d_samp_rows, ivf->samp_n, ps);
+            ivf_collect_sample_kernel<<<nq, 128, 0, st>>>(skeys.as<uint64_t>(), d_gpos, nprobe, ckeys.as<uint64_t>());
             VDB_LAUNCHED();
             launch_merge_keys(ckeys.as<uint64_t>(), 1, nq, nprobe * G_TOPJ, false, j0, jkeys.as<uint64_t>(), nullptr, nullptr,
                               nullptr, st);
@@ -2110,7 +2148,7 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
                                                               tau.as<float>());
             VDB_LAUNCHED();
         }
-        gather_f32_kernel<<<ceil_div(G, 256u), 256, 0, st>>>(tau.as<float>(), d_qmap.as<uint32_t>(), G, tau_g.as<float>());
+        gather_f32_kernel<<<ceil_div(G, 256u), 256, 0, st>>>(tau.as<float>(), d_qmap, G, tau_g.as<float>());
         VDB_LAUNCHED();
         // ---- filter pass over the probed (list, query tile) blocks ----
         const uint32_t cap = 8192;
@@ -2125,7 +2163,7 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
             pf.cand_cnt = tq->cnt.as<uint32_t>();
             pf.cand = cand.as<uint64_t>();
             pf.cap = cap;
-            run_items(1, items, ivf->d_rows_lo, ds->n, pf);
+            run_items(1, d_items, n_items, ivf->d_rows_lo, ds->n, pf);
         }
         // ---- candidates that cannot be among the k best by their score bounds are dropped (cand_prune_kernel) ----
         DevBuf pcnt((size_t)nq * 4, st);

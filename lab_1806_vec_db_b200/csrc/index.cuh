@@ -39,6 +39,7 @@ struct vdb_ivf {
     uint64_t* d_offsets = nullptr;  // [nlist+1]
     uint32_t* d_members = nullptr;  // [n] local row ids, ascending inside a list
     uint32_t max_list = 0;
+    std::vector<uint64_t> h_off;    // host copy of d_offsets (fixed after the build)
     // lazily built for the tensor-core probe scan: rows / norms permuted into list order (position p <-> members[p])
     void* d_rows_lo = nullptr;    // [n][op row bytes] operand rows of the dataset's kind (FP16 copy / fp32 rows)
     int op_kind = 0;
@@ -146,8 +147,7 @@ vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nli
 void ivf_destroy(vdb_ivf* ivf);
 // flat_gemm.cu: tensor-core probe scan for query batches (returns false when the shard / batch is not eligible)
 bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
-                     const std::vector<uint64_t>& h_probes, const std::vector<uint64_t>& h_off, uint32_t nq, uint32_t nprobe,
-                     uint32_t k, uint64_t* d_keys, cudaStream_t st);
+                     const uint64_t* h_probes, uint32_t nq, uint32_t nprobe, uint32_t k, uint64_t* d_keys, cudaStream_t st);
 void ivf_list_major_subset(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, const uint64_t* d_probes,
                            const uint32_t* h_sel, uint32_t nsel, uint32_t nprobe, uint32_t k, uint64_t* d_keys_sel,
                            cudaStream_t st);

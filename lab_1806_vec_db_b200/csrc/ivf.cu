@@ -465,7 +465,8 @@ vdb_ivf* ivf_create(const vdb_dataset* ds, const void* h_centroids, uint32_t nli
                 VDB_CUDA(cudaMemcpyAsync(h_assign_out, assign.p, ds->n * 4, cudaMemcpyDeviceToHost, st));
             VDB_CUDA(cudaStreamSynchronize(st));
         }
-        std::vector<uint64_t> off(nlist + 1);
+        std::vector<uint64_t>& off = ivf->h_off;
+        off.resize(nlist + 1);
         VDB_CUDA(cudaMemcpy(off.data(), ivf->d_offsets, off.size() * 8, cudaMemcpyDeviceToHost));
         for (uint32_t c = 0; c < nlist; ++c) ivf->max_list = std::max<uint32_t>(ivf->max_list, (uint32_t)(off[c + 1] - off[c]));
         VDB_CUDA(cudaStreamSynchronize(st));
@@ -496,7 +497,7 @@ void ivf_destroy(vdb_ivf* ivf) {
     delete ivf;
 }
 
-static void ivf_list_major(const vdb_dataset* ds, const vdb_ivf* ivf, const QueryTile& qt, const std::vector<uint64_t>& probes,
+static void ivf_list_major(const vdb_dataset* ds, const vdb_ivf* ivf, const QueryTile& qt, const uint64_t* probes,
                            const std::vector<uint64_t>& off, uint32_t nq, uint32_t nprobe, uint32_t k, uint64_t* d_keys,
                            cudaStream_t st) {
     std::vector<std::vector<uint32_t>> by_list(ivf->nlist);
@@ -608,12 +609,11 @@ void ivf_list_major_subset(const vdb_dataset* ds, const vdb_ivf* ivf, const void
     VDB_LAUNCHED();
     gather_bytes_rows_kernel<<<nsel, 64, 0, st>>>((const uint8_t*)d_probes, nprobe * 8, sel.as<uint32_t>(), nsel, pr.as<uint8_t>());
     VDB_LAUNCHED();
-    std::vector<uint64_t> h_probes((size_t)nsel * nprobe), h_off(ivf->nlist + 1);
+    std::vector<uint64_t> h_probes((size_t)nsel * nprobe);
     VDB_CUDA(cudaMemcpyAsync(h_probes.data(), pr.p, h_probes.size() * 8, cudaMemcpyDeviceToHost, st));
-    VDB_CUDA(cudaMemcpyAsync(h_off.data(), ivf->d_offsets, h_off.size() * 8, cudaMemcpyDeviceToHost, st));
     VDB_CUDA(cudaStreamSynchronize(st));
     QueryTile qt = prepare_queries(ds, q.p, nsel, st);
-    ivf_list_major(ds, ivf, qt, h_probes, h_off, nsel, nprobe, k, d_keys_sel, st);
+    ivf_list_major(ds, ivf, qt, h_probes.data(), ivf->h_off, nsel, nprobe, k, d_keys_sel, st);
 }
 
 void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queries, uint32_t nq, uint32_t k,
@@ -642,16 +642,16 @@ void ivf_knn_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_queri
     // 2. list scan
     if (nq >= 4) {
         // probe table to the host (nq * nprobe keys): the grouping by list is host work, the item tables go back
-        std::vector<uint64_t> h_probes((size_t)nq * nprobe), h_off(ivf->nlist + 1);
-        VDB_CUDA(cudaMemcpyAsync(h_probes.data(), probes.p, h_probes.size() * 8, cudaMemcpyDeviceToHost, st));
-        VDB_CUDA(cudaMemcpyAsync(h_off.data(), ivf->d_offsets, h_off.size() * 8, cudaMemcpyDeviceToHost, st));
+        static thread_local PinnedStage probe_stage;
+        const uint64_t* h_probes = (const uint64_t*)probe_stage.get((size_t)nq * nprobe * 8);
+        VDB_CUDA(cudaMemcpyAsync((void*)h_probes, probes.p, (size_t)nq * nprobe * 8, cudaMemcpyDeviceToHost, st));
         VDB_CUDA(cudaStreamSynchronize(st));
         static const int no_tensor = getenv("VDB_IVF_NO_TENSOR") ? atoi(getenv("VDB_IVF_NO_TENSOR")) : 0;
         if (!no_tensor && nq >= 16 &&
-            ivf_tensor_keys(ds, ivf, d_queries, probes.as<uint64_t>(), h_probes, h_off, nq, nprobe, k, d_keys, st))
+            ivf_tensor_keys(ds, ivf, d_queries, probes.as<uint64_t>(), h_probes, nq, nprobe, k, d_keys, st))
             return;
         QueryTile qt = prepare_queries(ds, d_queries, nq, st);
-        ivf_list_major(ds, ivf, qt, h_probes, h_off, nq, nprobe, k, d_keys, st);
+        ivf_list_major(ds, ivf, qt, h_probes, ivf->h_off, nq, nprobe, k, d_keys, st);
         return;
     }
     QueryTile qt = prepare_queries(ds, d_queries, nq, st);
