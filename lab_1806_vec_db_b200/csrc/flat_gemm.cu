@@ -2003,7 +2003,11 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
     }
     for (uint32_t l = 0; l < ivf->nlist; ++l) lcount[l + 1] += lcount[l];   // lcount[l] = first gathered row of list l
     const uint32_t G = lcount[ivf->nlist];
-    static const uint32_t force_ctas = getenv("VDB_IVF_CTAS") ? (uint32_t)atoi(getenv("VDB_IVF_CTAS")) : 0;
+    // Query tiles run on single CTAs (M = 128) by default: the probe scan of a batch is bound by streaming the lists
+    // and by per-item latency, not by the MMAs, and one launch per pass beats a single-CTA + a CTA-pair launch (measured,
+    // 1M x 960, nlist 128: 1000 queries nprobe 8 1.47 -> 1.27 ms, 10 000 queries nprobe 24 11.8 -> 11.7 ms).
+    // VDB_IVF_CTAS=0: 256-row tiles on CTA pairs with the remainder on single CTAs; =2: pairs only.
+    static const uint32_t force_ctas = getenv("VDB_IVF_CTAS") ? (uint32_t)atoi(getenv("VDB_IVF_CTAS")) : 1;
     const uint32_t tiles_per_item = 8;
     // item counts first (the staging block is sized from them)
     size_t n_items[2] = {0, 0}, n_sitems[2] = {0, 0};
