@@ -468,8 +468,9 @@ int vdb_flat_set_path(int path) {
     });
 }
 
-static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t nq, uint32_t k, uint64_t* d_keys,
-                               cudaStream_t st) {
+// returns true when `out` (optional) has already received the decoded results
+static bool flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t nq, uint32_t k, uint64_t* d_keys,
+                               cudaStream_t st, const vdb::ScanOut* out = nullptr) {
     const int path = ds->flat_path >= 0 ? ds->flat_path : vdb::g_flat_path.load();
     bool tensor = false;
     if (path == 2) {
@@ -482,8 +483,11 @@ static void flat_keys_dispatch(const vdb_dataset* ds, const void* d_q, uint32_t 
         // 0.59 ms for 1-2 queries (99 % of the HBM roofline of the fp32 rows), 0.70 ms for 3-4, 1.04 ms for 5-8
         tensor = nq >= 3 && vdb::flat_gemm_supported(ds, nq, k);
     }
-    if (tensor) vdb::flat_gemm_keys(ds, d_q, nq, k, d_keys, st);
-    else vdb::flat_scan_keys(ds, d_q, nq, k, d_keys, st);
+    if (tensor) {
+        vdb::flat_gemm_keys(ds, d_q, nq, k, d_keys, st);
+        return false;
+    }
+    return vdb::flat_scan_keys(ds, d_q, nq, k, d_keys, st, out);
 }
 
 
@@ -538,8 +542,9 @@ static void batcher_run(const vdb_dataset* ds, vdb_batcher* b, std::vector<vdb_b
     uint32_t* d_cnt = (uint32_t*)(b->d_stage + cnt_off);
     {
         vdb::DevBuf keys((size_t)nb * k * 8, st);
-        flat_keys_dispatch(ds, b->d_stage, nb, k, keys.as<uint64_t>(), st);
-        vdb::decode_keys(keys.as<uint64_t>(), nb, k, d_ids, d_dist, d_cnt, st);
+        const vdb::ScanOut so{d_ids, d_dist, d_cnt};
+        if (!flat_keys_dispatch(ds, b->d_stage, nb, k, keys.as<uint64_t>(), st, &so))
+            vdb::decode_keys(keys.as<uint64_t>(), nb, k, d_ids, d_dist, d_cnt, st);
     }
     VDB_CUDA(cudaMemcpyAsync(b->h_stage + ids_off, b->d_stage + ids_off, total - ids_off, cudaMemcpyDeviceToHost, st));
     VDB_CUDA(cudaStreamSynchronize(st));
@@ -627,8 +632,9 @@ int vdb_flat_knn_dev(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
         DeviceGuard g(dev_of(ds));
         cudaStream_t st = (cudaStream_t)stream;
         vdb::DevBuf keys((size_t)nq * k * 8, st);
-        flat_keys_dispatch(ds, d_queries, nq, k, keys.as<uint64_t>(), st);
-        vdb::decode_keys(keys.as<uint64_t>(), nq, k, d_ids, d_dist, d_counts, st);
+        const vdb::ScanOut so{d_ids, d_dist, d_counts};
+        if (!flat_keys_dispatch(ds, d_queries, nq, k, keys.as<uint64_t>(), st, &so))
+            vdb::decode_keys(keys.as<uint64_t>(), nq, k, d_ids, d_dist, d_counts, st);
     });
 }
 
@@ -649,8 +655,9 @@ int vdb_flat_knn(const vdb_dataset* ds, const void* queries, uint32_t nq, uint32
         host_search(dev_of(ds), queries, nq, (size_t)ds->dim * ds->elem_size(), k, ids, dist, counts,
                     [&](void* dq, uint64_t* dids, float* dd, uint32_t* dc, cudaStream_t st) {
                         vdb::DevBuf keys((size_t)nq * k * 8, st);
-                        flat_keys_dispatch(ds, dq, nq, k, keys.as<uint64_t>(), st);
-                        vdb::decode_keys(keys.as<uint64_t>(), nq, k, dids, dd, dc, st);
+                        const vdb::ScanOut so{dids, dd, dc};
+                        if (!flat_keys_dispatch(ds, dq, nq, k, keys.as<uint64_t>(), st, &so))
+                            vdb::decode_keys(keys.as<uint64_t>(), nq, k, dids, dd, dc, st);
                     });
     });
 }

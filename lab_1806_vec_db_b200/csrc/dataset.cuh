@@ -52,13 +52,22 @@ struct QueryTile {
     uint32_t qstride = 0;  // floats per query
     uint32_t nvec = 0, nit = 0;
 };
-QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st);
+QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st,
+                          uint32_t* d_zero_word = nullptr);   // d_zero_word: a counter the kernel clears on the way
 
 // ---- Flat exact scan (K1) ---------------------------------------------------------------------
 // keys out: [nq][k] ascending, KEY_NONE padded. If `d_members` != nullptr the scan visits only the
 // rows listed per query (IVF probe scan): see ivf.cu.
-void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
-                    uint64_t* d_keys, cudaStream_t st);
+// Decoded results of a search (the SoA arrays of the C ABI). flat_scan_keys writes them itself and returns true when the
+// whole batch is ONE scan launch (1-8 queries): the last CTA to finish merges the per-CTA lists and decodes, so a
+// single-query call is two launches (query tile + scan) instead of four. Otherwise it returns false: decode d_keys.
+struct ScanOut {
+    uint64_t* ids = nullptr;
+    float* dist = nullptr;
+    uint32_t* counts = nullptr;
+};
+bool flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_keys, cudaStream_t st,
+                    const ScanOut* out = nullptr);
 // decode [nq][k] keys into the SoA result arrays
 void decode_keys(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
                  uint32_t* d_counts, cudaStream_t st);

@@ -37,6 +37,12 @@ struct ScanParams {
     uint32_t id_base;
     uint32_t iters;        // row-group iterations per warp
     uint64_t* partial;     // [NQ][gridDim.x][K]
+    // fused tail (single-launch batches): the last CTA to finish merges the partial lists of every query
+    uint32_t* done;        // nullptr: off. Arrival counter, zero at launch (cleared by the query-tile kernel)
+    uint64_t* out_keys;    // [NQ][K]
+    uint64_t* out_ids;     // optional decoded results
+    float* out_dist;
+    uint32_t* out_counts;
 };
 
 // PL = 1: f32 rows (4 elements per 16-byte load); PL = 4: u8 rows (16 elements per load)
@@ -265,6 +271,45 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
         const uint32_t qi = i / p.K, j = i - qi * p.K;
         p.partial[((size_t)qi * gridDim.x + blockIdx.x) * p.K + j] = topk.seg(qi)[j];
     }
+    if (p.done == nullptr) return;
+    // ---- fused tail: last CTA done -> merge of the gridDim.x lists per query + decode (no further launches) ----
+    __shared__ uint32_t s_last, s_valid[8];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x < 8) s_valid[threadIdx.x] = 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    topk.init();
+    // at most `period` appends per segment between two flush tests (the contract of TopkSmem::push)
+    const uint32_t period = min((uint32_t)blockDim.x, p.P - p.K - p.limit);
+    const uint32_t total = gridDim.x * p.K;
+    for (uint32_t base = 0; base < total; base += period) {
+        const uint32_t i = base + threadIdx.x;
+        bool want = false;
+        if (threadIdx.x < period && i < total) {
+            for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
+                const uint64_t key = __ldcg(p.partial + (size_t)qi * total + i);   // written by other SMs: bypass L1
+                if (key < topk.tau(qi)) want |= topk.push(qi, key);
+            }
+        }
+        topk.maybe_flush(want);
+    }
+    topk.final_flush();
+    for (uint32_t i = threadIdx.x; i < p.nq_valid * p.K; i += blockDim.x) {
+        const uint32_t qi = i / p.K;
+        const uint64_t key = topk.seg(qi)[i - qi * p.K];
+        const bool ok = key != KEY_NONE;
+        p.out_keys[i] = key;
+        if (p.out_ids) {
+            p.out_ids[i] = ok ? (uint64_t)key_id(key) : KEY_NONE;
+            p.out_dist[i] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+        }
+        if (ok) atomicAdd(&s_valid[qi], 1u);
+    }
+    __syncthreads();
+    if (p.out_counts && threadIdx.x < p.nq_valid) p.out_counts[threadIdx.x] = s_valid[threadIdx.x];
 }
 
 // ---- merge of key lists ------------------------------------------------------------------------
@@ -470,8 +515,9 @@ void decode_keys(const uint64_t* d_keys, uint32_t nq, uint32_t k, uint64_t* d_id
 template <typename T>
 __global__ void prepare_queries_kernel(const T* __restrict__ src, uint32_t dim, uint32_t vec, uint32_t nit,
                                        uint32_t qstride, int metric, float* __restrict__ tile,
-                                       float* __restrict__ qcache) {
+                                       float* __restrict__ qcache, uint32_t* __restrict__ zero_word) {
     const uint32_t q = blockIdx.x;
+    if (zero_word && q == 0 && threadIdx.x == 0) *zero_word = 0u;
     const uint32_t plane = nit * 32 * 4;  // floats per plane
     float ss = 0.f;
     for (uint32_t i = threadIdx.x; i < qstride; i += blockDim.x) {
@@ -497,8 +543,10 @@ __global__ void prepare_queries_kernel(const T* __restrict__ src, uint32_t dim, 
 // u8 sets: the tile holds the queries' BYTES, zero padded to nit * 512 bytes per query (lane L of step it reads bytes
 // [(it*32 + L) * 16, +16), exactly the bytes it loads from a row), and the cache is computed in integers (exact)
 __global__ void prepare_queries_u8_kernel(const uint8_t* __restrict__ src, uint32_t dim, uint32_t qbytes, int metric,
-                                          uint8_t* __restrict__ tile, float* __restrict__ qcache) {
+                                          uint8_t* __restrict__ tile, float* __restrict__ qcache,
+                                          uint32_t* __restrict__ zero_word) {
     const uint32_t q = blockIdx.x;
+    if (zero_word && q == 0 && threadIdx.x == 0) *zero_word = 0u;
     __shared__ unsigned long long total;
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
@@ -513,7 +561,7 @@ __global__ void prepare_queries_u8_kernel(const uint8_t* __restrict__ src, uint3
     if (threadIdx.x == 0) qcache[q] = metric == VDB_COSINE ? sqrtf((float)total) : (float)total;
 }
 
-QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st) {
+QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, uint32_t* d_zero_word) {
     QueryTile t;
     const uint32_t vec = vec_elems(ds->dtype);
     t.nvec = ds->pitch / vec;
@@ -527,11 +575,11 @@ QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t
     if (ds->dtype == VDB_F32) {
         prepare_queries_kernel<float><<<nq, 256, 0, st>>>((const float*)d_queries, ds->dim, vec, t.nit,
                                                          t.qstride, ds->metric, t.q.as<float>(),
-                                                         t.qcache.as<float>());
+                                                         t.qcache.as<float>(), d_zero_word);
     } else {
         VDB_REQUIRE(ds->dim <= 65536, "u8 rows: dim %u too large for the 32-bit integer sums (max 65536)", ds->dim);
         prepare_queries_u8_kernel<<<nq, 256, 0, st>>>((const uint8_t*)d_queries, ds->dim, t.qstride * 4, ds->metric,
-                                                      t.q.as<uint8_t>(), t.qcache.as<float>());
+                                                      t.q.as<uint8_t>(), t.qcache.as<float>(), d_zero_word);
     }
     VDB_LAUNCHED();
     return t;
@@ -561,14 +609,16 @@ static int rows_per_group(int nqt) { return nqt <= 2 ? 8 : 4; }
 
 constexpr size_t SCAN_SMEM_MAX = 200 * 1024;
 
-void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
-                    uint64_t* d_keys, cudaStream_t st) {
-    if (nq == 0 || k == 0) return;
+bool flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, uint32_t k,
+                    uint64_t* d_keys, cudaStream_t st, const ScanOut* out) {
+    if (nq == 0 || k == 0) return false;
     if (ds->n == 0) {
         VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
-        return;
+        return false;
     }
-    QueryTile qt = prepare_queries(ds, d_queries, nq, st);
+    static const bool fuse_on = !(getenv("VDB_SCAN_FUSE") && !atoi(getenv("VDB_SCAN_FUSE")));
+    DevBuf done(fuse_on && nq <= 8 ? 4 : 0, st);   // arrival counter of the fused tail (cleared by the tile kernel)
+    QueryTile qt = prepare_queries(ds, d_queries, nq, st, done.as<uint32_t>());
 
     // queries per pass: as many as fit (<= 8) next to the top-k segments in shared memory.
     // The CTA-wide flush test (a barrier) runs every `sync_every` row groups: often enough that a query's segment
@@ -605,6 +655,7 @@ void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     uint32_t chunk = (uint32_t)std::max<size_t>(8, (size_t)(64u << 20) / partial_per_query);
     chunk = std::min(round_up(chunk, 8u), round_up(nq, 8u));
     DevBuf partial(partial_per_query * chunk, st);
+    bool fused = false;
 
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t qn = std::min(chunk, nq - q0);
@@ -626,6 +677,13 @@ void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
             p.qcache = qt.qcache.as<float>() + (q0 + qq);
             p.nq_valid = now;
             p.partial = partial.as<uint64_t>() + (size_t)qq * grid_used * k;
+            // the whole batch in this one launch: its last CTA merges and decodes
+            fused = done.p != nullptr && q0 == 0 && qq == 0 && now == nq;
+            p.done = fused ? done.as<uint32_t>() : nullptr;
+            p.out_keys = d_keys;
+            p.out_ids = fused && out ? out->ids : nullptr;
+            p.out_dist = fused && out ? out->dist : nullptr;
+            p.out_counts = fused && out ? out->counts : nullptr;
             const size_t smem = smem_for(t);
             if (ds->dtype == VDB_F32) {
                 if (ds->metric == VDB_L2SQR) dispatch_scan<VDB_L2SQR, 1>(t, p, grid_used, smem, st);
@@ -636,9 +694,11 @@ void flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
             }
             qq += now;
         }
-        launch_merge_keys(partial.as<uint64_t>(), grid_used, qn, k, false, k, d_keys + (size_t)q0 * k,
-                          nullptr, nullptr, nullptr, st);
+        if (!fused)
+            launch_merge_keys(partial.as<uint64_t>(), grid_used, qn, k, false, k, d_keys + (size_t)q0 * k,
+                              nullptr, nullptr, nullptr, st);
     }
+    return fused && out != nullptr;
 }
 
 }  // namespace vdb

@@ -32,14 +32,23 @@ for nq, k in cases:
     def run():
         L.check(lib.vdb_flat_knn_dev(ds._h, C.c_void_p(q.data_ptr()), nq, k, C.c_void_p(ids.data_ptr()),
                                      C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), C.c_void_p(stream)))
-    for _ in range(3): run()
+    for _ in range(int(os.environ.get("WARM", 3))): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
+    reps = int(os.environ.get("REPS", 10))
     e0.record()
     for _ in range(reps): run()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     passes = (nq + 7) // 8
     gbs = passes * n * dim * esz / ms / 1e6
-    print(f"nq={nq:3d} k={k:4d}: {ms:8.3f} ms/call  {nq/ms*1e3:9.1f} QPS  {gbs:7.1f} GB/s ({gbs/6551.4*100:5.1f}% of measured HBM peak)", flush=True)
+    extra = ""
+    if os.environ.get("PROF"):
+        L.check(lib.vdb_prof_reset()); L.check(lib.vdb_prof_enable(1))
+        for _ in range(50): run()
+        torch.cuda.synchronize()
+        L.check(lib.vdb_prof_enable(0))
+        t, c = C.c_double(0), C.c_uint64(0)
+        L.check(lib.vdb_prof_read(b"flat_scan", C.byref(t), C.byref(c)))
+        extra = f"  scan kernel {t.value / max(1, c.value) * 1e3:.1f} us x {c.value // 50} per call"
+    print(f"nq={nq:3d} k={k:4d}: {ms:8.3f} ms/call  {nq/ms*1e3:9.1f} QPS  {gbs:7.1f} GB/s ({gbs/6551.4*100:5.1f}% of measured HBM peak){extra}", flush=True)
