@@ -1394,7 +1394,8 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     // with fewer than j survivors (or an overflowed list) only gets a looser tau: the completeness check of the search
     // decides, as always.
     // Batches of <= 128 queries (single CTAs, HBM-bound on the operand rows) keep the one-launch register epilogue.
-    static const bool two_level = !(getenv("VDB_GEMM_SAMPLE_2L") && !atoi(getenv("VDB_GEMM_SAMPLE_2L")));
+    const char* two_level_s = getenv("VDB_GEMM_SAMPLE_2L");   // read per call: the tests toggle it in one process
+    const bool two_level = !(two_level_s && !atoi(two_level_s));
     static const uint32_t sub_env = getenv("VDB_GEMM_SAMPLE_SUBN") ? (uint32_t)atoi(getenv("VDB_GEMM_SAMPLE_SUBN")) : 0;
     const uint32_t SUB = (uint32_t)std::max<uint64_t>(2, ns / (sub_env ? sub_env : 1024));   // sub-sample of ~1024 rows
     if (two_level && ns >= 2048 && (tq->ctas == 2 || j > (uint32_t)G_TOPJ)) {
@@ -1572,7 +1573,8 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     (void)tile_units;
     uint32_t parts = parts_env ? parts_env : 1u;
     parts = std::max(1u, std::min(parts, total_slabs));
-    static const bool prune_on = !(getenv("VDB_GEMM_PRUNE") && !atoi(getenv("VDB_GEMM_PRUNE")));
+    const char* prune_s = getenv("VDB_GEMM_PRUNE");   // read per call: the tests toggle it in one process
+    const bool prune_on = !(prune_s && !atoi(prune_s));
     const bool prune = prune_on && parts == 1 && (size_t)cap * 4 <= 96 * 1024;
     // part i covers a share proportional to ratio^i of the slabs: the rerank of the LAST part is the only one that is
     // not hidden under a contraction launch, so later parts are made smaller

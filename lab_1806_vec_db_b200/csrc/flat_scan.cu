@@ -616,7 +616,8 @@ bool flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
         VDB_CUDA(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * k * 8, st));
         return false;
     }
-    static const bool fuse_on = !(getenv("VDB_SCAN_FUSE") && !atoi(getenv("VDB_SCAN_FUSE")));
+    const char* fuse_s = getenv("VDB_SCAN_FUSE");   // read per call: the tests toggle it in one process
+    const bool fuse_on = !(fuse_s && !atoi(fuse_s));
     DevBuf done(fuse_on && nq <= 8 ? 4 : 0, st);   // arrival counter of the fused tail (cleared by the tile kernel)
     QueryTile qt = prepare_queries(ds, d_queries, nq, st, done.as<uint32_t>());
 

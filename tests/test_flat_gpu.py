@@ -206,3 +206,36 @@ def test_u8_sums_beyond_2_pow_24_are_exact_where_the_reference_rounds(oracle):
     rel = np.abs(dd.astype(np.float64) - od.astype(np.float64)) / od
     assert rel.max() <= dim * 2.0 ** -25, float(rel.max())                       # the reference's own rounding, bounded
     assert rel.max() > 0                                                         # ... and really present on this input
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8])
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_fused_scan_tail_equals_the_separate_merge(metric, dtype, monkeypatch):
+    """Batches that are one scan launch (1-8 queries) are merged and decoded by the last CTA of that launch; the result
+    must equal the separate merge + decode kernels bit for bit, including the tail padding and the counts (k > n)."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(9)
+    L.check(L.lib().vdb_flat_set_path(1))   # the streaming scan for every batch size
+    try:
+        _fused_tail_cases(V, rng, metric, dtype, monkeypatch)
+    finally:
+        L.check(L.lib().vdb_flat_set_path(0))
+
+
+def _fused_tail_cases(V, rng, metric, dtype, monkeypatch):
+    for n, dim, k in ((5000, 96, 10), (300_000, 33, 100), (7, 16, 10)):
+        base = rng.random((n, dim), dtype=np.float32)
+        q = rng.random((8, dim), dtype=np.float32)
+        if dtype == np.uint8:
+            base, q = (base * 255).astype(np.uint8), (q * 255).astype(np.uint8)
+        idx = V.FlatIndex.from_vec_set(base, metric)
+        for nq in (1, 2, 3, 8):
+            monkeypatch.setenv("VDB_SCAN_FUSE", "0")
+            a = idx.knn_batch(q[:nq], k)
+            monkeypatch.setenv("VDB_SCAN_FUSE", "1")
+            b = idx.knn_batch(q[:nq], k)
+            monkeypatch.delenv("VDB_SCAN_FUSE")
+            assert (a[2] == b[2]).all() and (a[2] == min(k, n)).all()
+            assert (a[0] == b[0]).all()
+            assert (a[1].view(np.uint32) == b[1].view(np.uint32)).all()

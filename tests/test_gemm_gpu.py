@@ -308,3 +308,72 @@ def test_rows_of_wildly_different_magnitude_fall_back_to_tf32_operands():
         L.check(lib.vdb_flat_set_path(0))
     assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
     assert fallbacks < 32
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_round2_stages_do_not_change_a_bit(oracle, metric, monkeypatch):
+    """Upper-bound pruning of the candidate lists, the two-level sample selection, the filter's two rare paths and the row
+    parts only change how many rows reach the exact rerank: every combination returns the bits of the exact scan, the
+    pruned run gathers fewer rows, and nothing falls back to the scan on this set."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    n, nq, k = 150_000, 400, 50
+    base, q = _synthetic(n, nq)
+    idx = V.FlatIndex.from_vec_set(base, metric)
+    lib = L.lib()
+    stats = lambda: [x.value for x in _stats(lib)]  # noqa: E731
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, k)
+        L.check(lib.vdb_flat_set_path(2))
+        runs = {}
+        for name, env in (("default", {}), ("no_prune", {"VDB_GEMM_PRUNE": "0"}), ("one_level", {"VDB_GEMM_SAMPLE_2L": "0"}),
+                          ("rare_mask", {"VDB_GEMM_RARE_PER_SCORE": "0"}), ("rare_per_score", {"VDB_GEMM_RARE_PER_SCORE": "1"}),
+                          ("parts3", {"VDB_GEMM_PARTS": "3"})):
+            for key, val in env.items():
+                monkeypatch.setenv(key, val)
+            s0 = stats()
+            runs[name] = (idx.knn_batch(q, k), [b - a for a, b in zip(s0, stats())])
+            for key in env:
+                monkeypatch.delenv(key)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    for name, (res, (queries, cands, fallbacks)) in runs.items():
+        assert queries == nq, name
+        assert (res[0] == scan[0]).all(), name
+        assert (res[1].view(np.uint32) == scan[1].view(np.uint32)).all(), name
+        assert (res[2] == scan[2]).all(), name
+        assert fallbacks == 0, (name, fallbacks)
+    assert runs["default"][1][1] < runs["no_prune"][1][1], "pruning did not reduce the rows gathered by the rerank"
+    assert runs["default"][1][1] >= nq * k
+    want = oracle.flat_knn(base, q[:16], k, metric, 8)
+    assert_knn_parity(base, q[:16], metric, tuple(a[:16] for a in runs["default"][0]), want, oracle)
+
+
+def _stats(lib):
+    out = [C.c_uint64(0) for _ in range(3)]
+    lib.vdb_flat_gemm_stats(*[C.byref(x) for x in out])
+    return out
+
+
+def test_pruning_keeps_rows_under_the_cosine_norm_clamp(oracle):
+    """Rows whose norm product falls under the reference's 1e-10 clamp carry the score -inf ("always a candidate"); the
+    upper-bound pruning must not count them as rows with a known small distance, nor drop them."""
+    import lab_1806_vec_db_b200 as V
+    from lab_1806_vec_db_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    n, nq, k = 70_000, 200, 20
+    base = rng.random((n, 64), dtype=np.float32)
+    base[rng.choice(n, 300, replace=False)] = 0.0          # zero rows: cosine distance 1 - 0 / 1e-10 = 1
+    base[rng.choice(n, 300, replace=False)] *= 1e-12        # tiny rows: under the clamp for every query
+    q = rng.random((nq, 64), dtype=np.float32)
+    idx = V.FlatIndex.from_vec_set(base, "cosine")
+    lib = L.lib()
+    try:
+        L.check(lib.vdb_flat_set_path(1))
+        scan = idx.knn_batch(q, k)
+        L.check(lib.vdb_flat_set_path(2))
+        tens = idx.knn_batch(q, k)
+    finally:
+        L.check(lib.vdb_flat_set_path(0))
+    assert (tens[0] == scan[0]).all() and (tens[1].view(np.uint32) == scan[1].view(np.uint32)).all()
