@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvdb_b200.so")
+LIB_PATH = os.environ.get("VDB_LIB_PATH") or os.path.join(_HERE, "libvdb_b200.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4
 L2SQR, COSINE, DOT = 0, 1, 2
