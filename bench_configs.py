@@ -4,6 +4,7 @@
   configs[3]  PQ    m = 240 x 4 bits, k-means on 10k rows, Flat+PQ scan, ef in {240, 420, 600}  (config/bench_pq_240_hnsw.toml:7-23)
   configs[4]  HNSW  M = 16, ef_construction = 200, ef in {120, 200, 360}; HNSW+PQ ef in {240, 420, 600}  (config/bench_hnsw.toml:7-14)
   u8 rows     Flat L2Sqr on the byte-quantised set (the reference's second scalar type, src/scalar.rs:117-119)
+  cosine      Flat cosine on the headline set: single query and the 10 000-query batch (src/distance/mod.rs:60-69)
 
 1000 queries, k = 10, recall@10 against the exact Flat result (examples/bench.rs protocol, src/bin/gen_gnd.rs ground
 truth). Every search row carries
@@ -278,6 +279,63 @@ def u8_leg(V, L, lib, dev, peaks, base_f32, q_f32):
     return out
 
 
+def cosine_leg(V, L, lib, dev, peaks, base, q_f32):
+    """The headline batch (10 000 queries, k = 100) and the single-query call with the reference's other metric: cosine
+    distance (src/distance/mod.rs:60-69) through the same kernels, checked against the oracle on a query sample."""
+    import torch
+    import oracle as O
+    n = base.shape[0]
+    vs = V.DeviceVecSet.from_device(base.data_ptr(), n, DIM, DIM, np.float32, "cosine", keepalive=base)
+    flat = V.FlatIndex(vs)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    cores = os.cpu_count() or 1
+    out = {"metric": "cosine", "cases": []}
+    for nq, k, reps in ((1, 10, 30), (q_f32.shape[0], 100, 3)):
+        qq = q_f32[:nq].contiguous()
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+
+        def run():
+            L.check(lib.vdb_flat_knn_dev(vs._h, C.c_void_p(qq.data_ptr()), nq, k, C.c_void_p(ids.data_ptr()),
+                                         C.c_void_p(dd.data_ptr()), C.c_void_p(cnt.data_ptr()), st))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            run()
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / reps
+        case = {"nq": nq, "k": k, "qps": nq / ms * 1e3, "ms_per_call": ms}
+        if nq == 1:
+            case["roofline"] = {"bound": "hbm", "achieved": n * DIM * 4 / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                "frac": n * DIM * 4 / (ms * 1e-3) / 1e9 / hbm, "basis": "whole call, n dim 4 bytes"}
+        else:
+            nc = 8
+            q_host = qq[:nc].cpu().numpy()
+            t0 = time.perf_counter()
+            oi, od, _ = O.flat_knn(base.cpu().numpy(), q_host, k, "cosine", nthreads=cores)
+            cpu_s = time.perf_counter() - t0
+            gi, gd = ids[:nc].cpu().numpy(), dd[:nc].cpu().numpy()
+            # an id mismatch must be a tie: the ORACLE's distance of the returned row within 1e-5 (absolute: 1 - cos
+            # cancels, DESIGN.md section 2) of the oracle's distance at that rank
+            ties_ok = True
+            for qi, j in zip(*np.nonzero(gi != oi.astype(np.int64))):
+                d = O.distance(q_host[qi], base[int(gi[qi, j])].cpu().numpy(), "cosine")
+                ties_ok &= abs(d - od[qi, j]) <= 1e-5
+            case["cpu_baseline"] = {"value": nc / cpu_s, "unit": "queries/s", "cores": cores, "kind": "port",
+                                    "sample": f"{nc} of the {nq} queries",
+                                    "gpu_ids_equal_oracle_rate": float((gi == oi.astype(np.int64)).mean()),
+                                    "id_mismatches_are_ties_within_1e-5_abs": bool(ties_ok),
+                                    "gpu_max_abs_dist_err": float(np.abs(gd - od).max())}
+        out["cases"].append(case)
+    return out
+
+
 def run_all(V, L, lib, dev, peaks, base_flat, q_flat, synth_clustered, proto, n):
     """Both sets. The flat set is the headline's (already resident); the clustered one is generated here."""
     import torch
@@ -293,6 +351,10 @@ def run_all(V, L, lib, dev, peaks, base_flat, q_flat, synth_clustered, proto, n)
         out["u8"] = u8_leg(V, L, lib, dev, peaks, base_flat, q_flat)
     except Exception as e:  # noqa: BLE001
         out["u8"] = {"error": repr(e)}
+    try:
+        out["cosine"] = cosine_leg(V, L, lib, dev, peaks, base_flat, q_flat)
+    except Exception as e:  # noqa: BLE001
+        out["cosine"] = {"error": repr(e)}
     del legs, pq
     torch.cuda.empty_cache()
     base2 = synth_clustered(proto, 0, n, 42, dev)
