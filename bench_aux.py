@@ -204,6 +204,8 @@ def main():
             print(json.dumps({"config": "C5 HNSW build (CPU restatement, 1 thread)", "n": args.n,
                               "cpu_build_s": time.perf_counter() - t0}), flush=True)
         e0, e1, es = (int(x) for x in args.hnsw_ef.split(":"))
+        if os.environ.get("VDB_CUPROF"):   # ncu --profile-from-start off: capture the SEARCH launches, not the build's
+            torch.cuda.cudart().cudaProfilerStart()
         for ef in range(e0, e1 + 1, es):
             ids, dd, cnt = dev_out()
             if ref is not None:

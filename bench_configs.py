@@ -195,28 +195,47 @@ class Legs:
                                      "rows takes ~0.5 h on one thread): search parity on an identical graph",
                "search": [], "search_pq": []}
 
-        def roof(ms):
-            return {"bound": "hbm (dependent row gathers)", "achieved": None, "peak": self.hbm, "unit": "GB/s", "frac": None,
-                    "note": "latency-bound graph walk (SURVEY.md 8d): bytes = evaluations x (dim 4 + 4); the kernel does not "
-                            "count its evaluations, so only the time is reported", "ms_per_batch": ms}
+        def evals_of(fn):
+            """distance evaluations of ONE call (the library counts the rows its search_on_level loops gather)"""
+            n_ev = C.c_uint64(0)
+            L.check(lib.vdb_hnsw_evals(hn._h, C.byref(n_ev), 1))
+            fn()
+            self.torch.cuda.synchronize()
+            L.check(lib.vdb_hnsw_evals(hn._h, C.byref(n_ev), 1))
+            return int(n_ev.value)
+
+        def roof(ms, evals, unit_bytes, what):
+            gbs = evals * unit_bytes / (ms * 1e-3) / 1e9
+            return {"bound": "hbm (dependent gathers: latency, not bandwidth)", "achieved": gbs, "peak": self.hbm, "unit": "GB/s",
+                    "frac": gbs / self.hbm, "peak_source": self.peak_src, "evaluations_per_query": evals / self.nq,
+                    "algorithmic_bytes_per_batch": evals * unit_bytes,
+                    "basis": f"SURVEY.md 8d: evaluations x {what}, evaluations counted by the search kernel (vdb_hnsw_evals)",
+                    "ms_per_batch": ms}
         for ef in efs:
-            ms = self.timed(lambda: L.check(lib.vdb_hnsw_knn_dev(self.vs._h, hn._h, C.c_void_p(self.q.data_ptr()), self.nq, self.k,
-                                                                 ef, *self.out_ptrs(), self.st)))
+            call = lambda: L.check(lib.vdb_hnsw_knn_dev(self.vs._h, hn._h, C.c_void_p(self.q.data_ptr()), self.nq, self.k,  # noqa: E731
+                                                        ef, *self.out_ptrs(), self.st))
+            evals = evals_of(call)
+            ms = self.timed(call)
             e2e_s, _ = self.wall(lambda: hn.knn_with_ef_batch(self.q_host, self.k, ef))
             t0 = time.perf_counter()
             oi, _, _ = cpu.knn(self.q_host[:self.nc], self.k, ef, nthreads=self.cores)
             cpu_s = time.perf_counter() - t0
-            out["search"].append(self.row({"ef": ef}, ms, e2e_s, "vdb_hnsw_knn (host pointers)", roof(ms), oi, cpu_s,
+            out["search"].append(self.row({"ef": ef}, ms, e2e_s, "vdb_hnsw_knn (host pointers)",
+                                          roof(ms, evals, DIM * 4 + 4, "(dim 4 + 4) bytes per gathered row"), oi, cpu_s,
                                           "oracle knn_with_ef on the same graph, thread pool over queries"))
         if pq is not None:
             for ef in pq_efs:
-                ms = self.timed(lambda: L.check(lib.vdb_hnsw_knn_pq_dev(self.vs._h, hn._h, pq._h, C.c_void_p(self.q.data_ptr()),
-                                                                        self.nq, self.k, ef, *self.out_ptrs(), self.st)))
+                call = lambda: L.check(lib.vdb_hnsw_knn_pq_dev(self.vs._h, hn._h, pq._h, C.c_void_p(self.q.data_ptr()),  # noqa: E731
+                                                               self.nq, self.k, ef, *self.out_ptrs(), self.st))
+                evals = evals_of(call)
+                ms = self.timed(call)
                 e2e_s, _ = self.wall(lambda: hn.knn_pq_batch(self.q_host, self.k, ef, pq))
                 t0 = time.perf_counter()
                 oi, _, _ = cpu.knn_pq(self.q_host[:self.nc], self.k, ef, pq.encoded_vec_set, books, 240, 4, nthreads=self.cores)
                 cpu_s = time.perf_counter() - t0
-                out["search_pq"].append(self.row({"ef": ef}, ms, e2e_s, "vdb_hnsw_knn_pq (host pointers)", roof(ms), oi, cpu_s,
+                out["search_pq"].append(self.row({"ef": ef}, ms, e2e_s, "vdb_hnsw_knn_pq (host pointers)",
+                                                 roof(ms, evals, 120 + 4, "(120-byte code + 4) bytes per walked node; the exact "
+                                                      "rerank of max(ef, k) rows is not counted"), oi, cpu_s,
                                                  "oracle knn_pq on the same graph and codes, thread pool over queries"))
         return out
 

@@ -338,6 +338,9 @@ int vdb_hnsw_knn_dev(const vdb_dataset* ds, const vdb_hnsw* h, const void* d_que
  * cost recall, so it is never dropped silently: vdb_hnsw_build / _append / _knn / _knn_pq fail with VDB_EUNSUPPORTED;
  * after the asynchronous `_dev` searches the count since the last check is read with vdb_hnsw_overflow (must be 0). */
 int vdb_hnsw_overflow(const vdb_hnsw* h, uint32_t* count);
+/* Instrumentation: rows whose distance the search_on_level loops of this handle have evaluated (builds and searches) since
+ * the last reset - each is one dependent gather of a row (dim x sizeof(T) + 4 bytes: SURVEY.md section 8d's HNSW unit). */
+int vdb_hnsw_evals(const vdb_hnsw* h, uint64_t* count, int reset);
 
 /* IndexPQ::knn_pq on the graph (:672-697): the walk uses ADC distances of the 4-bit codes, all max(ef, k) results
  * are then re-scored exactly and the k best returned (ResultSet::pq_resort, candidate_pair.rs:102-108). */

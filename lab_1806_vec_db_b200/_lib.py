@@ -82,6 +82,7 @@ SIGNATURES = {
     "vdb_hnsw_info": (i32, [vp, vp, vp, vp, vp, vp]),
     "vdb_hnsw_links0": (i32, [vp, vp, vp]),
     "vdb_hnsw_overflow": (i32, [vp, vp]),
+    "vdb_hnsw_evals": (i32, [vp, vp, i32]),
     "vdb_hnsw_upper": (i32, [vp, vp, vp, vp]),
     "vdb_hnsw_create_from_graph": (i32, [vp, u32, u32, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, vp]),
     "vdb_hnsw_knn": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),

@@ -55,6 +55,10 @@ __device__ __forceinline__ const uint32_t* hn_links(const HnswGraph& g, uint32_t
 // dot product of a row in global memory with a vector held as zero-padded f32 in shared memory; every lane gets it
 template <typename T>
 __device__ __forceinline__ float warp_dot_row(const T* __restrict__ row, const float* __restrict__ qs, uint32_t pitch, int lane);
+// Every lane issues ALL its loads of a 1024-element chunk (8 x 16 bytes) before the first FMA: a walk is a chain of
+// dependent row gathers, and with the loads inside the FMA loop a 960-d row cost four HBM round trips instead of one
+// (ncu, round 2: the FFMAs of this function held most of the long-scoreboard stalls). The two accumulation chains and
+// their order (rounds 0, 2, 4, ... in s0, rounds 1, 3, 5, ... in s1) are unchanged, so the distances are bit-identical.
 template <>
 __device__ __forceinline__ float warp_dot_row<float>(const float* __restrict__ row, const float* __restrict__ qs, uint32_t pitch,
                                                      int lane) {
@@ -62,17 +66,24 @@ __device__ __forceinline__ float warp_dot_row<float>(const float* __restrict__ r
     const float4* q4 = reinterpret_cast<const float4*>(qs);
     float s0 = 0.f, s1 = 0.f;
     const uint32_t n4 = pitch >> 2;
-    uint32_t e = lane;
-    for (; e + 32 < n4; e += 64) {
-        const float4 a = __ldg(r4 + e), c = __ldg(r4 + e + 32);
-        const float4 b = q4[e], d = q4[e + 32];
-        s0 = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s0))));
-        s1 = fmaf(c.x, d.x, fmaf(c.y, d.y, fmaf(c.z, d.z, fmaf(c.w, d.w, s1))));
-    }
-    if (e < n4) {
-        const float4 a = __ldg(r4 + e);
-        const float4 b = q4[e];
-        s0 = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s0))));
+    for (uint32_t base = lane; base < n4; base += 256) {
+        float4 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t e = base + 32 * u;
+            // UNCONDITIONAL loads (index clamped into the row; the FMAs below skip the rounds past its end): ptxas hoists
+            // straight-line loads ahead of the arithmetic but keeps predicated ones next to their consumers
+            a[u] = __ldg(r4 + min(e, n4 - 1));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t e = base + 32 * u;
+            if (e < n4) {
+                const float4 b = q4[e];
+                if (u & 1) s1 = fmaf(a[u].x, b.x, fmaf(a[u].y, b.y, fmaf(a[u].z, b.z, fmaf(a[u].w, b.w, s1))));
+                else s0 = fmaf(a[u].x, b.x, fmaf(a[u].y, b.y, fmaf(a[u].z, b.z, fmaf(a[u].w, b.w, s0))));
+            }
+        }
     }
     float s = s0 + s1;
 #pragma unroll
@@ -86,15 +97,33 @@ __device__ __forceinline__ float warp_dot_row<uint8_t>(const uint8_t* __restrict
     const float4* q4 = reinterpret_cast<const float4*>(qs);
     float s = 0.f;
     const uint32_t n4 = pitch >> 2;
-    for (uint32_t e = lane; e < n4; e += 32) {
-        const uint32_t v = __ldg(r4 + e);
-        const float4 b = q4[e];
-        s = fmaf((float)(v & 0xffu), b.x, fmaf((float)((v >> 8) & 0xffu), b.y,
-                                               fmaf((float)((v >> 16) & 0xffu), b.z, fmaf((float)(v >> 24), b.w, s))));
+    for (uint32_t base = lane; base < n4; base += 256) {
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t e = base + 32 * u;
+            v[u] = __ldg(r4 + min(e, n4 - 1));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t e = base + 32 * u;
+            if (e < n4) {
+                const float4 b = q4[e];
+                s = fmaf((float)(v[u] & 0xffu), b.x, fmaf((float)((v[u] >> 8) & 0xffu), b.y,
+                                                          fmaf((float)((v[u] >> 16) & 0xffu), b.z, fmaf((float)(v[u] >> 24), b.w, s))));
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
+}
+// L2 prefetch of a whole row by one warp (lane = 128-byte line): the rows a warp evaluates AFTER its first one of an expansion
+// are then L2 hits, and so are the link lists of the entries most likely to be expanded next
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void warp_prefetch_bytes(const void* base, uint32_t bytes, int lane) {
+    const char* c = reinterpret_cast<const char*>(base);
+    for (uint32_t off = (uint32_t)lane * 128; off < bytes; off += 32 * 128) prefetch_l2(c + off);
 }
 // row -> zero-padded f32 vector in shared memory (all threads of the CTA)
 template <typename T>
@@ -159,6 +188,7 @@ struct HnswSearchParams {
     uint32_t nq, ef, hash_mask;
     uint32_t* ghash;           // visited sets in GLOBAL memory, one of hash_mask + 1 slots per CTA (large ef); nullptr: shared memory
     uint32_t* overflow;        // counts neighbours that could not be recorded because a visited set was 7/8 full
+    unsigned long long* evals; // distance evaluations of the search_on_level loops (instrumentation: bytes gathered)
     uint32_t enter_point, enter_level;
     int build;
     const uint64_t* out_off;   // build: first list of query i; its list of level l is out_off[i] + l
@@ -171,7 +201,7 @@ struct HnswSearchParams {
 };
 
 template <typename T, int METRIC, bool PQ>
-__global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearchParams p) {
+__global__ void __launch_bounds__(HN_THREADS, 4) hnsw_search_kernel(const HnswSearchParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     float* qs = reinterpret_cast<float*>(smem);                                  // [dimpad]: query, or LUT (+ dist_cache) in PQ mode
     uint64_t* resA = reinterpret_cast<uint64_t*>(qs + p.dimpad);                 // [ef]
@@ -323,6 +353,11 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearc
                 }
                 __syncthreads();
                 const uint32_t m_all = s_m;
+                // rows this warp evaluates after its first one: on their way to L2 while the first is being read
+                for (uint32_t j = warp + HN_THREADS / 32; j < m_all; j += HN_THREADS / 32) {
+                    if (PQ) prefetch_l2(p.codes + (size_t)nb[j] * p.enc);
+                    else warp_prefetch_bytes(rows + (size_t)nb[j] * p.pitch, p.dim * (uint32_t)sizeof(T), lane);
+                }
                 for (uint32_t m0 = 0; m0 < m_all; m0 += 32) {  // M0 <= 64: at most two rounds
                     const uint32_t m = min(32u, m_all - m0);
                     for (uint32_t j = warp; j < m; j += HN_THREADS / 32) {
@@ -336,7 +371,15 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearc
                     res = res2;
                     res2 = t;
                 }
+                // the next expansion takes the best unexpanded entry, almost always one of the first few: its link list
+                // (one dependent read at the head of every expansion) is sent to L2 now
+                if (lvl == 0 && threadIdx.x < 16 && threadIdx.x < rn && !(res[threadIdx.x] & 1ull)) {
+                    const uint32_t node = (uint32_t)(res[threadIdx.x] & 0xffffffffull) >> 1;
+                    prefetch_l2(p.g.links0 + (size_t)node * p.g.M0);
+                    prefetch_l2(p.g.len0 + node);
+                }
             }
+            if (threadIdx.x == 0 && p.evals) atomicAdd(p.evals, (unsigned long long)s_hcount);   // rows evaluated on this level
             cur = (uint32_t)(res[0] & 0xffffffffull) >> 1;  // nearest graph result = entry of the next level
             if (p.build) {
                 // brute force among the earlier nodes of the batch that live on this level (:431-437)
@@ -589,6 +632,7 @@ static void launch_search(const vdb_dataset* ds, const HnswSearchParams& p, uint
     HnswSearchParams q = p;
     q.ghash = ghash.as<uint32_t>();
     q.overflow = overflow;
+    q.evals = overflow ? reinterpret_cast<unsigned long long*>(overflow + 2) : nullptr;   // same 16-byte allocation
     if (pq) q.dimpad = (uint32_t)round_up(vec_floats, (size_t)4);  // the kernel's vector area holds the tables
     if (pq) {
         if (l2) launch_dyn(hnsw_search_kernel<uint8_t, VDB_L2SQR, true>, grid, smem, q, st);
@@ -671,8 +715,8 @@ static void hnsw_alloc(vdb_hnsw* h, const vdb_dataset* ds, uint32_t M, uint32_t 
     VDB_CUDA(cudaMalloc(&h->d_uoff, (n + 1) * 8));
     VDB_CUDA(cudaMalloc(&h->d_level, std::max<uint64_t>(n, 1) * 4));
     VDB_CUDA(cudaMalloc(&h->d_cache, std::max<uint64_t>(n, 1) * 4));
-    VDB_CUDA(cudaMalloc(&h->d_overflow, 4));
-    VDB_CUDA(cudaMemsetAsync(h->d_overflow, 0, 4, st));
+    VDB_CUDA(cudaMalloc(&h->d_overflow, 16));   // [0] overflow count, [2..3] u64 evaluation count
+    VDB_CUDA(cudaMemsetAsync(h->d_overflow, 0, 16, st));
     VDB_CUDA(cudaMemsetAsync(h->d_links0, 0, std::max<uint64_t>(n, 1) * h->M0 * 4, st));
     VDB_CUDA(cudaMemsetAsync(h->d_ulinks, 0, slots * M * 4, st));
     VDB_CUDA(cudaMemsetAsync(h->d_len0, 0, std::max<uint64_t>(n, 1) * 4, st));

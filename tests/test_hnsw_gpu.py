@@ -323,3 +323,25 @@ def test_append_leaves_the_index_intact_when_it_fails(V):
     V._lib.check(V.lib().vdb_hnsw_append(idx._h, vs._h, V._lib.ptr(good), 256))   # and a proper append still works
     V._lib.check(V.lib().vdb_hnsw_info(idx._h, V._lib.C.byref(n), None, None, None, None))
     assert n.value == 4000
+
+
+def test_evaluation_counter_counts_the_rows_a_search_gathers(V, fixtures):
+    """vdb_hnsw_evals (the roofline unit of the HNSW bench legs): more rows are evaluated for a larger ef, never more
+    than the graph holds per query, and the counter resets."""
+    import ctypes as C
+    from lab_1806_vec_db_b200 import _lib as L
+    base, test = fixtures["base"], fixtures["test"][:64]
+    vs = V.DeviceVecSet(base, "l2sqr")
+    idx = V.HNSWIndex(vs, V.HNSWConfig(0, 100, 8), rng=np.random.default_rng(3))
+    lib = L.lib()
+    n = C.c_uint64(0)
+    L.check(lib.vdb_hnsw_evals(idx._h, C.byref(n), 1))
+    assert n.value > len(base)            # the build's own searches
+    counts = []
+    for ef in (10, 80):
+        idx.knn_with_ef_batch(test, 10, ef)
+        L.check(lib.vdb_hnsw_evals(idx._h, C.byref(n), 1))
+        counts.append(n.value)
+    assert 64 * 10 <= counts[0] < counts[1] <= 64 * len(base)
+    L.check(lib.vdb_hnsw_evals(idx._h, C.byref(n), 0))
+    assert n.value == 0
