@@ -491,7 +491,7 @@ __device__ uint32_t heuristic_select(const T* rows, uint32_t pitch, uint32_t dim
 }
 
 template <typename T, int METRIC>
-__global__ void __launch_bounds__(HN_THREADS) hnsw_select_kernel(const HnswSelectParams p) {
+__global__ void __launch_bounds__(HN_THREADS, 4) hnsw_select_kernel(const HnswSelectParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem);
     __shared__ uint32_t kept[HN_MAX_M0 + 1];
@@ -528,7 +528,7 @@ struct HnswArrangeParams {
 };
 
 template <typename T, int METRIC>
-__global__ void __launch_bounds__(HN_THREADS) hnsw_arrange_kernel(const HnswArrangeParams p) {
+__global__ void __launch_bounds__(HN_THREADS, 4) hnsw_arrange_kernel(const HnswArrangeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     float* rs = reinterpret_cast<float*>(smem);  // row of the target
     float* xs = rs + p.dimpad;                   // one staging row per warp for the candidates under test
