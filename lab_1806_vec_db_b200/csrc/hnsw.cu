@@ -189,6 +189,7 @@ struct HnswSearchParams {
     uint32_t* ghash;           // visited sets in GLOBAL memory, one of hash_mask + 1 slots per CTA (large ef); nullptr: shared memory
     uint32_t* overflow;        // counts neighbours that could not be recorded because a visited set was 7/8 full
     unsigned long long* evals; // distance evaluations of the search_on_level loops (instrumentation: bytes gathered)
+    uint32_t* next_q;          // work queue: next query index to hand out (starts at gridDim.x); nullptr: static stride
     uint32_t enter_point, enter_level;
     int build;
     const uint64_t* out_off;   // build: first list of query i; its list of level l is out_off[i] + l
@@ -216,7 +217,10 @@ __global__ void __launch_bounds__(HN_THREADS, 4) hnsw_search_kernel(const HnswSe
     const T* rows = reinterpret_cast<const T*>(p.rows);
     const uint32_t hcap = p.hash_mask + 1, hlimit = hcap - (hcap >> 3);
 
-    for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {
+    // Queries are handed out dynamically: walks differ in length, and with a static stride a 1000-query batch on ~600
+    // resident CTAs takes two full rounds whatever the second round holds
+    __shared__ uint32_t s_next;
+    for (uint32_t q = blockIdx.x; q < p.nq;) {
         const uint32_t qrow = p.qrow_base + q;
         __syncthreads();
         if (PQ) {
@@ -412,6 +416,13 @@ __global__ void __launch_bounds__(HN_THREADS, 4) hnsw_search_kernel(const HnswSe
             for (uint32_t i = threadIdx.x; i < p.ef; i += blockDim.x)
                 out[i] = i < rn ? ((res[i] & 0xffffffff00000000ull) | ((res[i] & 0xffffffffull) >> 1)) : KEY_NONE;
             __syncthreads();
+        }
+        if (p.next_q) {
+            if (threadIdx.x == 0) s_next = atomicAdd(p.next_q, 1u);
+            __syncthreads();
+            q = s_next;
+        } else {
+            q += gridDim.x;
         }
     }
 }
@@ -627,10 +638,13 @@ static void launch_search(const vdb_dataset* ds, const HnswSearchParams& p, uint
         grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, (1ull << 30) / ((uint64_t)slots * 4)));
         ghash = DevBuf((size_t)grid * slots * 4, st);
     }
+    DevBuf next_q(4, st);
+    VDB_CUDA(cudaMemcpyAsync(next_q.p, &grid, 4, cudaMemcpyHostToDevice, st));   // the first `grid` queries are the CTAs' own
     ProfScope prof("hnsw_search", st);
     const bool l2 = ds->metric == VDB_L2SQR;
     HnswSearchParams q = p;
     q.ghash = ghash.as<uint32_t>();
+    q.next_q = next_q.as<uint32_t>();
     q.overflow = overflow;
     q.evals = overflow ? reinterpret_cast<unsigned long long*>(overflow + 2) : nullptr;   // same 16-byte allocation
     if (pq) q.dimpad = (uint32_t)round_up(vec_floats, (size_t)4);  // the kernel's vector area holds the tables
