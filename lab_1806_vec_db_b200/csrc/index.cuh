@@ -22,6 +22,12 @@ struct vdb_pq {
     uint32_t* d_sample_t = nullptr; // the same layout for a stratified random row sample (thresholds of the scan)
     uint8_t* d_sample = nullptr;    // the sampled code rows in the reference layout [sample_n][enc] (tensor-core sample pass)
     uint32_t sample_n = 0;
+    // decoded-operand contraction (pq_dec.cu), built lazily by the first batched search: FP16 codebooks scaled by a power
+    // of two, ||x^||^2 and ||x^|| of every code row and of every sampled row, the worst-case decode error norm
+    void* d_dec_cb16 = nullptr;
+    float* d_dec_r = nullptr, *d_dec_xn = nullptr, *d_dec_sr = nullptr, *d_dec_sxn = nullptr;
+    bool dec_ok = false;
+    float dec_scale = 1.0f, dec_ex = 0.f;
     std::vector<vdb_pq*> shards;    // row-sharded parent (multi.cu): one table per shard, the arrays above stay empty
 };
 
@@ -169,6 +175,18 @@ void pq_train_groups(const void* d_rows, uint64_t n, uint64_t pitch, int dtype, 
 
 // pq_gemm.cu
 bool pq_tensor_supported(const vdb_pq* pq, uint32_t nq);
+// pq_dec.cu: the same scan as a contraction over rows decoded on the fly (sub-vectors of 4 dimensions)
+bool pq_dec_supported(const vdb_pq* pq, uint32_t nq);
+void* pq_dec_begin(const vdb_pq* pq, const void* d_queries, uint32_t nq, cudaStream_t st);   // nullptr: not applicable
+void pq_dec_end(void* ctx);
+void pq_dec_sample(const vdb_pq* pq, void* ctx, uint32_t nq, float* d_all, cudaStream_t st);
+void pq_dec_filter(const vdb_pq* pq, void* ctx, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base,
+                   uint32_t* d_cnt, uint64_t* d_cand, uint32_t cap, cudaStream_t st);
+void pq_dec_destroy(vdb_pq* pq);
+// exact ADC (reference arithmetic) of coarse candidate rows; survivors with adc <= tau become keys (pq_gemm.cu)
+void pq_exact_candidates(const vdb_pq* pq, const float* d_lut, const float* d_tau, uint32_t nq, const uint32_t* d_ccnt,
+                         const uint32_t* d_ccand, uint32_t ccap, uint32_t id_base, uint32_t* d_cnt, uint64_t* d_cand,
+                         uint32_t cap, cudaStream_t st);
 void pq_tensor_lut(const vdb_pq* pq, const float* d_lut, uint32_t nq, DevBuf& lut16, cudaStream_t st);
 void pq_tensor_sample(const vdb_pq* pq, const DevBuf& lut16, uint32_t nq, float* d_all, cudaStream_t st);
 void pq_tensor_filter(const vdb_pq* pq, const DevBuf& lut16, const float* d_lut, uint32_t nq, const float* d_tau, uint32_t id_base,

@@ -688,8 +688,15 @@ static bool adc_global_supported(const vdb_pq* pq, uint32_t K) {
 }
 
 // top-K (adc, id) keys per query through the global-threshold scan; [nq][K]
-static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K,
-                            uint32_t id_base, uint64_t* d_keys, cudaStream_t st) {
+struct DecCtx {   // query context of the decoded contraction (pq_dec.cu), released on every exit
+    void* p = nullptr;
+    ~DecCtx() {
+        if (p) pq_dec_end(p);
+    }
+};
+
+static void adc_topk_global(const vdb_pq* pq, const void* d_queries, const float* d_lut, const float* d_qcache, uint32_t nq,
+                            uint32_t K, uint32_t id_base, uint64_t* d_keys, cudaStream_t st) {
     const uint32_t tab = pq->m * 16;
     const uint64_t ns = pq->sample_n;
     const uint32_t j0 = tensor_j0(K, ns, pq->n, 1e-5);
@@ -703,7 +710,11 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
     const uint32_t gq = (uint32_t)adc_gq();
     const bool tensor = pq_tensor_supported(pq, nq);
     DevBuf lut16;
-    if (tensor) {
+    DecCtx dec;   // sub-vectors of 4 dimensions: contraction over rows decoded on the fly (4x fewer MMAs than the one-hot form)
+    if (tensor && d_queries && pq_dec_supported(pq, nq)) dec.p = pq_dec_begin(pq, d_queries, nq, st);
+    if (dec.p) {
+        pq_dec_sample(pq, dec.p, nq, sall.as<float>(), st);
+    } else if (tensor) {
         pq_tensor_lut(pq, d_lut, nq, lut16, st);
         pq_tensor_sample(pq, lut16, nq, sall.as<float>(), st);
     } else
@@ -722,7 +733,9 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
     tau_from_jkeys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, tau.as<float>());
     VDB_LAUNCHED();
     // 2. filter scan over the shard (batches: bf16 one-hot contraction on the tensor cores + exact re-evaluation)
-    if (tensor)
+    if (dec.p)
+        pq_dec_filter(pq, dec.p, d_lut, nq, tau.as<float>(), id_base, cnt.as<uint32_t>(), cand.as<uint64_t>(), cap, st);
+    else if (tensor)
         pq_tensor_filter(pq, lut16, d_lut, nq, tau.as<float>(), id_base, cnt.as<uint32_t>(), cand.as<uint64_t>(), cap, st);
     else
     for (uint32_t q0 = 0; q0 < nq; q0 += gq) {
@@ -760,15 +773,16 @@ static void adc_topk_global(const vdb_pq* pq, const float* d_lut, const float* d
 }
 
 // top-K ADC keys: global-threshold scan for batches on large shards, per-CTA top-k otherwise
-static void adc_topk(const vdb_pq* pq, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K, uint32_t id_base,
-                     uint64_t* d_keys, cudaStream_t st) {
+static void adc_topk(const vdb_pq* pq, const void* d_queries, const float* d_lut, const float* d_qcache, uint32_t nq, uint32_t K,
+                     uint32_t id_base, uint64_t* d_keys, cudaStream_t st) {
     static const int force_old = getenv("VDB_ADC_OLD") ? atoi(getenv("VDB_ADC_OLD")) : 0;
     if (!force_old && nq >= 4 && adc_global_supported(pq, K)) {
         // chunks of 8192 queries bound the sample-score and candidate scratch (~1 GB + 8192 * cap * 12 B per chunk)
         const uint32_t tab = pq->m * pq->kc;
         for (uint32_t q0 = 0; q0 < nq; q0 += 8192) {
             const uint32_t cn = std::min(8192u, nq - q0);
-            adc_topk_global(pq, d_lut + (size_t)q0 * tab, d_qcache + q0, cn, K, id_base, d_keys + (size_t)q0 * K, st);
+            const void* dq = d_queries ? (const uint8_t*)d_queries + (size_t)q0 * pq->dim * (pq->dtype == VDB_F32 ? 4 : 1) : nullptr;
+            adc_topk_global(pq, dq, d_lut + (size_t)q0 * tab, d_qcache + q0, cn, K, id_base, d_keys + (size_t)q0 * K, st);
         }
     } else {
         adc_scan(pq, d_lut, d_qcache, nq, K, id_base, d_keys, nullptr, st);
@@ -919,6 +933,7 @@ void pq_destroy(vdb_pq* pq) {
     cudaFree(pq->d_codes_t);
     cudaFree(pq->d_sample_t);
     cudaFree(pq->d_sample);
+    pq_dec_destroy(pq);
     delete pq;
 }
 
@@ -1003,7 +1018,7 @@ void pq_adc_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries,
     const uint32_t tab = pq->m * pq->kc;
     DevBuf lut((size_t)nq * tab * 4, st), qcache((size_t)nq * 4, st);
     pq_lut(pq, d_queries, nq, lut.as<float>(), qcache.as<float>(), st);
-    adc_topk(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, d_keys, st);
+    adc_topk(pq, d_queries, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, d_keys, st);
 }
 
 void pq_knn_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries, uint32_t nq, uint32_t k,
@@ -1016,7 +1031,7 @@ void pq_knn_keys(const vdb_dataset* ds, const vdb_pq* pq, const void* d_queries,
     const uint32_t tab = pq->m * pq->kc;
     DevBuf lut((size_t)nq * tab * 4, st), qcache((size_t)nq * 4, st), cand((size_t)nq * kk * 8, st);
     pq_lut(pq, d_queries, nq, lut.as<float>(), qcache.as<float>(), st);
-    adc_topk(pq, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, cand.as<uint64_t>(), st);
+    adc_topk(pq, d_queries, lut.as<float>(), qcache.as<float>(), nq, kk, (uint32_t)ds->id_base, cand.as<uint64_t>(), st);
     rerank_keys(ds, d_queries, nq, cand.as<uint64_t>(), kk, k, d_keys, st);
 }
 

@@ -461,12 +461,18 @@ void pq_tensor_filter(const vdb_pq* pq, const DevBuf& lut16, const float* d_lut,
     p.ccand = ccand.as<uint32_t>();
     p.ccap = ccap;
     launch_pq_gemm<1>(pq, lut16, nq, pq->d_codes, pq->n, p, st);
-    {
-        ProfScope prof("pq_exact", st);
-        pq_exact_cands_kernel<<<nq, 256, (size_t)tab * 4, st>>>(pq->d_codes, pq->enc, pq->m, d_lut, d_tau, ccnt.as<uint32_t>(),
-                                                              ccand.as<uint32_t>(), ccap, id_base, d_cnt, d_cand, cap);
-        VDB_LAUNCHED();
-    }
+    (void)tab;
+    pq_exact_candidates(pq, d_lut, d_tau, nq, ccnt.as<uint32_t>(), ccand.as<uint32_t>(), ccap, id_base, d_cnt, d_cand, cap, st);
+}
+
+void pq_exact_candidates(const vdb_pq* pq, const float* d_lut, const float* d_tau, uint32_t nq, const uint32_t* d_ccnt,
+                         const uint32_t* d_ccand, uint32_t ccap, uint32_t id_base, uint32_t* d_cnt, uint64_t* d_cand,
+                         uint32_t cap, cudaStream_t st) {
+    const uint32_t tab = pq->m * 16;
+    ProfScope prof("pq_exact", st);
+    pq_exact_cands_kernel<<<nq, 256, (size_t)tab * 4, st>>>(pq->d_codes, pq->enc, pq->m, d_lut, d_tau, d_ccnt, d_ccand, ccap, id_base,
+                                                          d_cnt, d_cand, cap);
+    VDB_LAUNCHED();
 }
 
 }  // namespace vdb

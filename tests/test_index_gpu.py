@@ -379,6 +379,42 @@ def test_pq_tensor_filter_large_shard(V, oracle, m):
         assert (few[0] == got[0][:9]).all() and (few[1].view(np.uint32) == got[1][:9].view(np.uint32)).all()
 
 
+@pytest.mark.parametrize("dim,m,dtype", [(64, 16, np.float32), (960, 240, np.float32), (128, 32, np.uint8)])
+def test_pq_decoded_contraction_large_shard(V, oracle, dim, m, dtype, monkeypatch):
+    """Sub-vectors of 4 dimensions (m = dim / 4, the reference's bench setting): batches prune the ADC scan with the
+    contraction over rows DECODED on the fly (pq_dec.cu). Candidates, ids and distance bits must equal the one-hot
+    contraction's, the FP32 scan's and the oracle's, incl. exact ADC ties, a ragged last row tile, a ragged last query
+    tile and queries far outside the data."""
+    rng = np.random.default_rng(77 + m)
+    n = 70_001
+    scale = 255 if dtype == np.uint8 else 1
+    base = (rng.random((n, dim)) * scale).astype(dtype)
+    base[5000:5300] = base[17]                      # 300 identical rows: ADC ties decided by id
+    nq = 300 if dim <= 128 else 70
+    q = (rng.random((nq, dim)) * scale).astype(dtype)
+    q[0] = base[17]
+    if dtype == np.float32:
+        q[1] *= 40.0                                # a query far away: large norms, loose bounds
+        q[2] *= 1e-3
+    books = np.concatenate([np.ascontiguousarray(base[100:116, lo:hi]).reshape(-1) for lo, hi in V.pq_groups(dim, m)])
+    vs = V.DeviceVecSet(base, "l2sqr")
+    pq = V.PQTable(vs, V.PQConfig(4, m, "l2sqr"), books)
+    codes = oracle.pq_encode(base, books, m, 4, "l2sqr", nthreads=8)
+    assert (pq.encoded_vec_set == codes).all()
+    idx = V.FlatIndex(vs)
+    for k, ef in ((10, 50), (10, 300), (3, 1)):
+        got = idx.knn_pq_batch(q, k, ef, pq)
+        monkeypatch.setenv("VDB_PQ_NO_DECODE", "1")
+        onehot = idx.knn_pq_batch(q, k, ef, pq)
+        monkeypatch.delenv("VDB_PQ_NO_DECODE")
+        assert (onehot[0] == got[0]).all() and (onehot[1].view(np.uint32) == got[1].view(np.uint32)).all()
+        few = idx.knn_pq_batch(q[:9], k, ef, pq)     # < 32 queries: FP32 global-threshold scan
+        assert (few[0] == got[0][:9]).all() and (few[1].view(np.uint32) == got[1][:9].view(np.uint32)).all()
+        nchk = 24
+        want = oracle.flat_knn_pq(base, codes, books, m, 4, q[:nchk], k, ef, "l2sqr", nthreads=8)
+        assert_knn_parity(base, q[:nchk], "l2sqr", tuple(a[:nchk] for a in got), want, oracle)
+
+
 @pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
 @pytest.mark.parametrize("dtype", [np.float32, np.uint8])
 def test_batched_pq_training_bit_exact_vs_per_group(V, oracle, metric, dtype):
