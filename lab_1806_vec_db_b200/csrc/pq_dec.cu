@@ -70,6 +70,14 @@ struct PqDecParams {
     uint32_t ccap;
     uint32_t tiles_per_item, nrow_items, nqt;
     float* all_out;           // MODE 0: [nq][n] upper bounds of the exact ADC values (sample pass)
+    // MODE 1 output: one record per (row, chunk of 32 queries) with any passing score - the per-query candidate lists are
+    // filled from the records by pq_dec_expand_kernel. (Appending to the per-query lists from the epilogue costs one
+    // atomic round trip per passing score in divergent code: at 0.25 % passing scores the four epilogue warps needed
+    // twice the time of the tile's MMAs.)
+    uint64_t* rec;            // [rec_cap] row << 16 | chunk index (query = chunk * 32 + bit)
+    uint32_t* rec_mask;       // [rec_cap] passing queries of the chunk
+    uint32_t* rec_count;      // records written (may exceed rec_cap: then every list is declared overflowed)
+    uint32_t rec_cap;
 };
 
 // MODE 0: store an upper bound of every ADC value (sample pass), 1: filter
@@ -231,48 +239,106 @@ __global__ void __launch_bounds__(D_THREADS, 1) pq_dec_kernel(const __grid_const
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (lane_base << 16) + acc * DN;
+                constexpr int HC = DN / 64;   // chunks of 32 queries per half tile
+                auto flush = [&](const uint32_t (&msk)[HC], int half) {
+                    // records of this half tile: ONE atomic per warp reserves their slots
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int ci = 0; ci < HC; ++ci) cnt += msk[ci] != 0u;
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total == 0) return;
+                    uint32_t base = 0;
+                    if (lane == 31) base = atomicAdd(p.rec_count, total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    uint32_t idx = base + incl - cnt;
+#pragma unroll
+                    for (int ci = 0; ci < HC; ++ci) {
+                        if (msk[ci]) {
+                            if (idx < p.rec_cap) {
+                                p.rec[idx] = ((uint64_t)row << 16) | (uint64_t)(qt * (DN / 32) + half * HC + ci);
+                                p.rec_mask[idx] = msk[ci];
+                            }
+                            ++idx;
+                        }
+                    }
+                };
 #pragma unroll 1
-                for (int c0 = 0; c0 < DN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    if (row_ok) {
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t msk[HC];
 #pragma unroll
-                        for (int j4 = 0; j4 < 32; j4 += 4) {
-                            const float4 d4 = lds_f4(qd_a + (c0 + j4) * 4), b4 = lds_f4(qb_a + (c0 + j4) * 4),
-                                         t4 = lds_f4(qt_a + (c0 + j4) * 4);
-                            const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w},
-                                        tv[4] = {t4.x, t4.y, t4.z, t4.w};
+                    for (int ci = 0; ci < HC; ++ci) {
+                        msk[ci] = 0u;
+                        const int c0 = (half * HC + ci) * 32;
+                        uint32_t v[32];
+                        tmem_ld32(taddr + c0, v);
+                        if (row_ok) {
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = j4 + jj;
-                                const float dot = __uint_as_float(v[j]);
-                                const uint32_t q = q0 + c0 + j;
-                                if (MODE == 0) {
-                                    // upper bound of the reference's ADC value; a warp stores 32 consecutive rows of a query
-                                    const float up = (fmaf(dv[jj], dot, fmaf(bv[jj], xn, rr)) + tv[jj]) * 1.00005f + 1e-30f;
-                                    if (q < p.nq) p.all_out[(size_t)q * p.n + row] = up;
-                                } else {
-                                    const float s = fmaf(dv[jj], dot, fmaf(-bv[jj], xn, rr));
-                                    if (!(s > tv[jj])) {  // also keeps NaN (the exact re-evaluation decides)
-                                        const uint32_t pos = atomicAdd(&p.ccnt[q], 1u);
-                                        if (pos < p.ccap) p.ccand[(size_t)q * p.ccap + pos] = (uint32_t)row;
+                            for (int j4 = 0; j4 < 32; j4 += 4) {
+                                const float4 d4 = lds_f4(qd_a + (c0 + j4) * 4), b4 = lds_f4(qb_a + (c0 + j4) * 4),
+                                             t4 = lds_f4(qt_a + (c0 + j4) * 4);
+                                const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w},
+                                            tv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const int j = j4 + jj;
+                                    const float dot = __uint_as_float(v[j]);
+                                    if (MODE == 0) {
+                                        // upper bound of the reference's ADC value; a warp stores 32 consecutive rows of a query
+                                        const uint32_t q = q0 + c0 + j;
+                                        const float up = (fmaf(dv[jj], dot, fmaf(bv[jj], xn, rr)) + tv[jj]) * 1.00005f + 1e-30f;
+                                        if (q < p.nq) p.all_out[(size_t)q * p.n + row] = up;
+                                    } else {
+                                        const float sc = fmaf(dv[jj], dot, fmaf(-bv[jj], xn, rr));
+                                        msk[ci] |= (sc > tv[jj] ? 0u : 1u) << j;   // also keeps NaN (the exact re-evaluation decides)
                                     }
                                 }
                             }
                         }
                     }
+                    if (half == 1) {   // every TMEM load of the tile is done: hand the accumulator back (one arrive per warp)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        if (++acc == 2) acc = 0, acc_phase ^= 1;
+                    }
+                    if (MODE == 1) flush(msk, half);
                 }
-                // hand the accumulator back to the MMA issuer: one arrive per warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (++acc == 2) acc = 0, acc_phase ^= 1;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, D_TMEM_COLS);
+}
+
+// records (row, chunk of 32 queries, passing mask) -> per-query coarse candidate lists. One thread per record: the
+// atomics of a record are independent of every other thread's, so their latency is hidden by parallelism.
+__global__ void pq_dec_expand_kernel(const uint64_t* __restrict__ rec, const uint32_t* __restrict__ rec_mask,
+                                     const uint32_t* __restrict__ rec_count, uint32_t rec_cap, uint32_t nq,
+                                     uint32_t* __restrict__ ccnt, uint32_t* __restrict__ ccand, uint32_t ccap) {
+    const uint32_t total = *rec_count;
+    if (total > rec_cap) {   // the record buffer overflowed: every list counts as overflowed (exact fallback)
+        for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) ccnt[q] = ccap + 1;
+        return;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint64_t r = rec[i];
+        const uint32_t row = (uint32_t)(r >> 16), q0 = (uint32_t)(r & 0xffffu) * 32;
+        uint32_t m = rec_mask[i];
+        while (m) {
+            const uint32_t b = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t q = q0 + b;
+            const uint32_t pos = atomicAdd(&ccnt[q], 1u);
+            if (pos < ccap) ccand[(size_t)q * ccap + pos] = row;
+        }
+    }
 }
 
 // ---- per-table side data (lazily built by the first batched search) ---------------------------------------------
@@ -536,11 +602,24 @@ void pq_dec_filter(const vdb_pq* pq, void* ctx, const float* d_lut, uint32_t nq,
     VDB_CUDA(cudaMemsetAsync(ccnt.p, 0, (size_t)nq * 4, st));
     pq_dec_thresholds_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(d_tau, Q.qsq.as<float>(), Q.qab.as<float>(), nq, Q.qt.as<float>());
     VDB_LAUNCHED();
+    // one record per (row, 32-query chunk) with a passing score; at most one per candidate, so nq * ccap records hold
+    // every case in which no list overflows
+    const uint64_t rec_cap64 = std::min<uint64_t>((uint64_t)nq * ccap, 1ull << 28);
+    const uint32_t rec_cap = (uint32_t)rec_cap64;
+    DevBuf rec((size_t)rec_cap * 8, st), rec_mask((size_t)rec_cap * 4, st), rec_count(4, st);
+    VDB_CUDA(cudaMemsetAsync(rec_count.p, 0, 4, st));
     PqDecParams p{};
     p.ccnt = ccnt.as<uint32_t>();
     p.ccand = ccand.as<uint32_t>();
     p.ccap = ccap;
+    p.rec = rec.as<uint64_t>();
+    p.rec_mask = rec_mask.as<uint32_t>();
+    p.rec_count = rec_count.as<uint32_t>();
+    p.rec_cap = rec_cap;
     launch_dec(1, pq, Q, nq, pq->d_codes, pq->n, pq->d_dec_r, pq->d_dec_xn, p, st);
+    pq_dec_expand_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(rec.as<uint64_t>(), rec_mask.as<uint32_t>(), rec_count.as<uint32_t>(),
+                                                                  rec_cap, nq, ccnt.as<uint32_t>(), ccand.as<uint32_t>(), ccap);
+    VDB_LAUNCHED();
     pq_exact_candidates(pq, d_lut, d_tau, nq, ccnt.as<uint32_t>(), ccand.as<uint32_t>(), ccap, id_base, d_cnt, d_cand, cap, st);
 }
 
