@@ -540,6 +540,53 @@ __global__ void tau_from_jkeys_kernel(const uint64_t* __restrict__ jkeys, uint32
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) tau[q] = key_dist(jkeys[(size_t)q * j + (j - 1)]);
 }
+// tau[q] = the j-th smallest (1-based) of the ns sampled scores of query q: radix select over the order-preserving bit
+// pattern, 11 + 11 + 10 bits, one CTA per query. (Converting the scores to keys and running the sorting top-k merge over
+// 32768 of them per query cost 83 + 247 us per 1000 queries.)
+__global__ void __launch_bounds__(256) select_jth_kernel(const float* __restrict__ v, uint32_t ns, uint32_t j, float* __restrict__ tau) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t s_bin, s_k;
+    const float* x = v + (size_t)blockIdx.x * ns;
+    uint32_t prefix = 0, mask = 0, kk = j;
+    const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        const int sh = shifts[pass];
+        const uint32_t nb = 1u << widths[pass];
+        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
+            const uint32_t o = f32_order_bits(x[i]);
+            if ((o & mask) == prefix) atomicAdd(&hist[(o >> sh) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {   // warp 0: the bin that holds the kk-th element
+            const uint32_t per = nb / 32;
+            uint32_t sum = 0;
+            for (uint32_t i = 0; i < per; ++i) sum += hist[threadIdx.x * per + i];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += y;
+            }
+            const uint32_t before = incl - sum;
+            if (before < kk && kk <= incl) {   // exactly one lane
+                uint32_t run = before;
+                for (uint32_t i = 0; i < per; ++i) {
+                    const uint32_t c = hist[threadIdx.x * per + i];
+                    if (run < kk && kk <= run + c) s_bin = threadIdx.x * per + i, s_k = kk - run;
+                    run += c;
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= s_bin << sh;
+        mask |= (nb - 1) << sh;
+        kk = s_k;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tau[blockIdx.x] = f32_from_order_bits(prefix);
+}
 // queries whose candidate list is too short (the threshold was too tight) or overflowed must be redone
 __global__ void adc_check_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t need, uint32_t cap,
                                  uint32_t* __restrict__ redo, uint32_t* __restrict__ nredo) {
@@ -701,7 +748,7 @@ static void adc_topk_global(const vdb_pq* pq, const void* d_queries, const float
     const uint64_t ns = pq->sample_n;
     const uint32_t j0 = tensor_j0(K, ns, pq->n, 1e-5);
     const uint32_t cap = next_pow2((uint32_t)std::min<uint64_t>(pq->n, std::max<uint64_t>(4ull * j0 * (pq->n / ns), 4096)));
-    DevBuf sall((size_t)nq * ns * 4, st), skeys((size_t)nq * ns * 8, st), jkeys((size_t)nq * j0 * 8, st), tau((size_t)nq * 4, st),
+    DevBuf sall((size_t)nq * ns * 4, st), skeys, jkeys, tau((size_t)nq * 4, st),
         cnt((size_t)nq * 4, st), cand((size_t)nq * cap * 8, st), redo((size_t)nq * 4, st), nredo(4, st);
     VDB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nq * 4, st));
     VDB_CUDA(cudaMemsetAsync(cand.p, 0xff, (size_t)nq * cap * 8, st));
@@ -726,12 +773,20 @@ static void adc_topk_global(const vdb_pq* pq, const void* d_queries, const float
         p.all_out = sall.as<float>() + (size_t)q0 * ns;
         launch_adc_global<0>(pq, p, pq->d_sample_t, ns, st);
     }
-    floats_to_keys_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>((uint64_t)nq * ns, 256), 8192), 256, 0, st>>>(
-        sall.as<float>(), (uint64_t)nq * ns, ns, skeys.as<uint64_t>());
-    VDB_LAUNCHED();
-    launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j0, jkeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
-    tau_from_jkeys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, tau.as<float>());
-    VDB_LAUNCHED();
+    static const bool old_select = getenv("VDB_PQ_SELECT_OLD") && atoi(getenv("VDB_PQ_SELECT_OLD"));
+    if (!old_select && j0 <= ns) {
+        select_jth_kernel<<<nq, 256, 0, st>>>(sall.as<float>(), (uint32_t)ns, j0, tau.as<float>());
+        VDB_LAUNCHED();
+    } else {
+        skeys = DevBuf((size_t)nq * ns * 8, st);
+        jkeys = DevBuf((size_t)nq * j0 * 8, st);
+        floats_to_keys_kernel<<<(uint32_t)std::min<uint64_t>(ceil_div<uint64_t>((uint64_t)nq * ns, 256), 8192), 256, 0, st>>>(
+            sall.as<float>(), (uint64_t)nq * ns, ns, skeys.as<uint64_t>());
+        VDB_LAUNCHED();
+        launch_merge_keys(skeys.as<uint64_t>(), 1, nq, (uint32_t)ns, false, j0, jkeys.as<uint64_t>(), nullptr, nullptr, nullptr, st);
+        tau_from_jkeys_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(jkeys.as<uint64_t>(), nq, j0, tau.as<float>());
+        VDB_LAUNCHED();
+    }
     // 2. filter scan over the shard (batches: bf16 one-hot contraction on the tensor cores + exact re-evaluation)
     if (dec.p)
         pq_dec_filter(pq, dec.p, d_lut, nq, tau.as<float>(), id_base, cnt.as<uint32_t>(), cand.as<uint64_t>(), cap, st);
