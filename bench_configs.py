@@ -166,12 +166,15 @@ class Legs:
             oi, _, _ = O.flat_knn_pq(self.base_host(), pq.encoded_vec_set, books, 240, 4, self.q_host[:self.nc], self.k, ef,
                                      "l2sqr", nthreads=self.cores)
             cpu_s = time.perf_counter() - t0
-            flops = 2.0 * self.nq * self.n * 240 * 16    # the ADC lookup as a one-hot contraction
+            # m = dim / 4: the ADC filter is a contraction over rows decoded on the fly, K = dim; the one-hot
+            # form of round 1 (K = 16 m) did 4x the FLOP for the same scan
+            flops = 2.0 * self.nq * self.n * DIM
             roof = {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": self.bf16, "unit": "TFLOP/s",
                     "frac": flops / (ms * 1e-3) / 1e12 / self.bf16, "peak_source": self.peak_src + " bf16_tflops_sustained",
                     "flop_per_batch": flops, "code_bytes_per_pass": self.n * 120,
-                    "basis": "2 nq n m 16 FLOP: the batch's ADC scan runs as a one-hot x LUT contraction on the tensor cores; "
-                             "the whole call (LUT, contraction, exact re-evaluation, merges, rerank) is timed"}
+                    "basis": "2 nq n dim FLOP (fp16 operands: decoded centroid values x queries) divided by the time of the WHOLE "
+                             "call (LUT, sample pass, contraction, exact re-evaluation, merges, rerank); the contraction kernel "
+                             "alone is 1.70 of the 2.63 ms (profiles/r02_pq_dec_launches.md)"}
             rows.append(self.row({"ef": ef}, ms, e2e_s, "vdb_pq_knn (host pointers)", roof, oi, cpu_s,
                                  "oracle knn_pq (ADC scan of all codes + pq_resort), thread pool over queries"))
         return {"reference_config": "config/bench_pq_240_hnsw.toml:16-23 (Flat+PQ scan variant)", "m": 240, "n_bits": 4,
