@@ -51,6 +51,10 @@ template <int KIND> struct KindCfg {
     static constexpr int GKE = GKB / ELEM;                      // elements per k-block: 32 (tf32) / 64 (f16)
     static constexpr uint32_t FMT = KIND == KIND_F16 ? 0u : 2u;  // UMMA a/b format: F16 = 0, TF32 = 2
 };
+// filter (mode 1): passing scores are staged per epilogue warp in shared memory (list owner + key) and their list slots
+// reserved by ALL lanes at once when the buffer fills, so the ~700-cycle atomic round trip is paid once per G_STG_CAP
+// candidates instead of once per 32-score chunk with a hit
+constexpr int G_STG_CAP = 256;
 constexpr int G_THREADS = 192;       // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
 constexpr int G_TMEM_COLS = 512;     // 2 accumulators x 256 columns
 constexpr int G_MAX_STAGES = 6;
@@ -61,7 +65,8 @@ template <int CTAS, int KIND = KIND_TF32> struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * GKB;
     static constexpr int STAGE_BYTES = G_A_BYTES + B_BYTES;     // 48 KB / 32 KB
     static constexpr int STAGES = CTAS == 1 ? 4 : 6;            // 192 KB either way
-    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 3 * GN * 4 /*row-scalar tiles*/ + 512 /*barriers*/;
+    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 3 * GN * 4 /*row-scalar tiles*/ + 512 /*barriers*/ +
+                                     4 * G_STG_CAP * 12 /*candidate staging of the 4 epilogue warps*/;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32 or F16, both K-major, N>>3, M>>4
     static constexpr uint32_t IDESC = (1u << 4) | (KindCfg<KIND>::FMT << 7) | (KindCfg<KIND>::FMT << 10) |
                                       ((uint32_t)(GN >> 3) << 17) | ((uint32_t)((GM * CTAS) >> 4) << 24);
@@ -115,7 +120,7 @@ struct GemmParams {
     const GemmItem* items;  // nullptr -> the grid of plan_gemm
     uint32_t nitems;
     const uint32_t* qmap;   // table mode: row of the gathered query matrix -> query that owns the candidate list
-    uint32_t rare_per_score;  // 1: the filter's rare path reserves list slots one atomic per score (measurement switch)
+    uint32_t rare_per_score;  // filter's rare path: 0 one atomic per thread and 32-score chunk, 1 one per score, 2 staged per warp
 };
 
 template <int CTAS>
@@ -159,6 +164,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t* iq_empty = iq_full + G_ITEMQ;          // [G_ITEMQ] (leader's copy is live): every reader took it
     uint32_t* item_ring = reinterpret_cast<uint32_t*>(iq_empty + G_ITEMQ);  // [G_ITEMQ]
     uint32_t* tmem_slot = item_ring + G_ITEMQ;
+    uint8_t* stg_base = reinterpret_cast<uint8_t*>(bars) + 512;   // [4 warps][G_STG_CAP] keys (8 B), then owners (4 B)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
@@ -292,6 +298,25 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== epilogue: warps 0-3, thread = query (TMEM lane), registers = database rows =====
         uint32_t acc = 0, acc_phase = 0;
         const uint32_t lane_base = (uint32_t)warp * 32;
+        uint64_t* stg_key = reinterpret_cast<uint64_t*>(stg_base) + warp * G_STG_CAP;
+        uint32_t* stg_own = reinterpret_cast<uint32_t*>(stg_base + 4 * G_STG_CAP * 8) + warp * G_STG_CAP;
+        uint32_t stg_fill = 0;   // warp-uniform
+        auto stg_flush = [&]() {
+            __syncwarp();
+            uint32_t pos[G_STG_CAP / 32];
+#pragma unroll
+            for (int u = 0; u < G_STG_CAP / 32; ++u) {   // every round trip of the buffer is in flight at once
+                const uint32_t e = u * 32 + lane;
+                pos[u] = e < stg_fill ? atomicAdd(&p.cand_cnt[stg_own[e]], 1u) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < G_STG_CAP / 32; ++u) {
+                const uint32_t e = u * 32 + lane;
+                if (e < stg_fill && pos[u] < p.cap) p.cand[(uint64_t)stg_own[e] * p.cap + pos[u]] = stg_key[e];
+            }
+            __syncwarp();
+            stg_fill = 0;
+        };
         for (uint32_t n = 0;; ++n) {
             uint32_t item = 0;
             if (lane == 0) item = take_item(n);
@@ -362,7 +387,8 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tmem_ld_wait(va);
                 // scores of the 32 columns in v[]: 3 FMAs + one predicate-chained compare per score, a flag per group of 8
                 auto score = [&](uint32_t (&v)[32], int c0) {
-                    if (!qok) return;
+                    const bool staged = MODE == 1 && p.rare_per_score == 2;   // warp-uniform: every lane takes part
+                    if (!qok && !staged) return;
                     const float thr = MODE == 1 ? tau : (MODE == 2 ? best[MODE == 2 ? G_TOPJ - 1 : 0] : 0.f);
                     bool none[4] = {true, true, true, true};
 #pragma unroll
@@ -394,6 +420,59 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         for (int j = 0; j < 32; ++j) {
                             const uint64_t brow = tile_row0 + c0 + j;
                             if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(__uint_as_float(v[j]), (uint32_t)brow);
+                        }
+                    } else if (staged) {
+                        const bool mine = qok && !(none[0] && none[1] && none[2] && none[3]);
+                        if (__any_sync(0xffffffffu, mine)) {
+                            uint32_t pass = 0;
+                            if (mine) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    if (none[g]) continue;
+#pragma unroll
+                                    for (int j = g * 8; j < g * 8 + 8; ++j) pass |= (__uint_as_float(v[j]) >= tau ? 0u : 1u) << j;
+                                }
+                            }
+                            const uint32_t cnt = (uint32_t)__popc(pass);
+                            uint32_t inc = cnt;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
+                                if (lane >= d) inc += up;
+                            }
+                            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                            if (total) {
+                                if (stg_fill + total > (uint32_t)G_STG_CAP) stg_flush();
+                                if (total > (uint32_t)G_STG_CAP) {
+                                    // denser than the buffer (a threshold of +inf): slots reserved per thread
+                                    if (pass) {
+                                        uint32_t pos = atomicAdd(&p.cand_cnt[oq], cnt);
+                                        uint64_t* list = p.cand + (uint64_t)oq * p.cap;
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) {
+                                            if ((pass >> j) & 1u) {
+                                                if (pos < p.cap) list[pos] = ((uint64_t)v[j] << 32) | (uint32_t)(tile_row0 + c0 + j);
+                                                ++pos;
+                                            }
+                                        }
+                                    }
+                                } else {
+                                    uint32_t e = stg_fill + inc - cnt;
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g) {
+                                        if (((pass >> (g * 8)) & 0xffu) == 0u) continue;
+#pragma unroll
+                                        for (int j = g * 8; j < g * 8 + 8; ++j) {
+                                            if ((pass >> j) & 1u) {
+                                                stg_key[e] = ((uint64_t)v[j] << 32) | (uint32_t)(tile_row0 + c0 + j);
+                                                stg_own[e] = oq;
+                                                ++e;
+                                            }
+                                        }
+                                    }
+                                    stg_fill += total;
+                                }
+                            }
                         }
                     } else if (MODE == 1 && !p.rare_per_score && !(none[0] && none[1] && none[2] && none[3])) {
                         // rare path of the filter: the passing (or NaN: the exact rerank decides) scores of the flagged groups
@@ -477,6 +556,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         bidx[i] == 0xffffffffu ? KEY_NONE : make_key(best[i], bidx[i]);
             }
         }
+        if (MODE == 1 && stg_fill) stg_flush();
     }
     tc_fence_before();
     __syncthreads();
@@ -1350,11 +1430,12 @@ static GemmParams base_params(const vdb_tq* tq) {
     p.qab = tq->qab.as<float>();
     p.qb = tq->qb.as<float>();
     p.qnorm = tq->ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr;
-    // The filter over the whole set passes ~0.05 % of its scores: there the per-score path is faster (A/B in one process,
-    // 1M x 960, 10k queries: 14.7 vs 16.6 ms per pass); the sample pass of the two-level selection passes ~0.6 % and
-    // takes the one-atomic path (1.25 vs 1.94 ms). VDB_GEMM_RARE_PER_SCORE overrides both (read per call).
+    // The filter over the whole set passes ~0.05 % of its scores: there the per-score path (1) is faster (A/B in one process,
+    // 1M x 960, 10k queries: 14.7 vs 16.6 ms per pass with the per-thread mask path 0, 16.4 vs 16.9 with the staged path 2);
+    // the sample pass of the two-level selection passes ~0.6 % and takes the staged path. At 0.34 % (a 125k-row shard under
+    // its LOCAL threshold) staged is 2.9 vs 4.0-4.6 ms. VDB_GEMM_RARE_PER_SCORE = 0 / 1 / 2 overrides both (read per call).
     const char* rare = getenv("VDB_GEMM_RARE_PER_SCORE");
-    p.rare_per_score = rare ? (atoi(rare) ? 1u : 0u) : 1u;
+    p.rare_per_score = rare ? (uint32_t)std::min(2, std::max(0, atoi(rare))) : 1u;
     return p;
 }
 
@@ -1428,7 +1509,9 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
         p2.cand_cnt = cnt2.as<uint32_t>();
         p2.cand = cand2.as<uint64_t>();
         p2.cap = cap2;
-        if (!getenv("VDB_GEMM_RARE_PER_SCORE")) p2.rare_per_score = 0;
+        // ~0.6-1.6 % of the sample's scores pass the coarse threshold: staged slots (A/B on one box, 10k queries: 1.39 ->
+        // 1.25 ms for the 33k-row sample; the per-thread mask path 0 and the per-score path 1 stay selectable)
+        if (!getenv("VDB_GEMM_RARE_PER_SCORE")) p2.rare_per_score = 2;
         plan_gemm(p2, tq->ctas);
         launch_gemm(1, ds->metric, tq->kind, tq->mq, ms, p2, st, tq->ctas, "flat_gemm_sample");
         cand_sortable_kernel<<<tq->nq, 128, 0, st>>>(cand2.as<uint64_t>(), cnt2.as<uint32_t>(), cap2);

@@ -282,19 +282,42 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     if (!s_last) return;
     __threadfence();
     topk.init();
+    // Every per-CTA list is ascending, so the smallest of their K-th keys bounds the K-th key of the union: only keys up
+    // to it are pushed (a few more than K instead of gridDim.x * K), and the keys of a batch are loaded before any of them
+    // is tested - the L2 round trips of the tail overlap instead of lining up one per round.
+    __shared__ unsigned long long s_bound[8];
+    if (threadIdx.x < 8) s_bound[threadIdx.x] = KEY_NONE;
+    __syncthreads();
+    const uint32_t total = gridDim.x * p.K;
+    for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
+        unsigned long long b = KEY_NONE;
+        for (uint32_t l = threadIdx.x; l < gridDim.x; l += blockDim.x)
+            b = min(b, (unsigned long long)__ldcg(p.partial + (size_t)qi * total + (size_t)l * p.K + (p.K - 1)));   // other SMs wrote it: bypass L1
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, d));
+        if ((threadIdx.x & 31) == 0 && b != KEY_NONE) atomicMin(&s_bound[qi], b);   // 64-bit shared atomics are CAS loops: one per warp
+    }
+    __syncthreads();
     // at most `period` appends per segment between two flush tests (the contract of TopkSmem::push)
     const uint32_t period = min((uint32_t)blockDim.x, p.P - p.K - p.limit);
-    const uint32_t total = gridDim.x * p.K;
-    for (uint32_t base = 0; base < total; base += period) {
-        const uint32_t i = base + threadIdx.x;
-        bool want = false;
-        if (threadIdx.x < period && i < total) {
-            for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
-                const uint64_t key = __ldcg(p.partial + (size_t)qi * total + i);   // written by other SMs: bypass L1
-                if (key < topk.tau(qi)) want |= topk.push(qi, key);
+    constexpr int TAIL_U = 8;
+    for (uint32_t base = 0; base < total; base += TAIL_U * period) {
+        for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
+            const uint64_t bound = s_bound[qi];
+            uint64_t kk[TAIL_U];
+#pragma unroll
+            for (int u = 0; u < TAIL_U; ++u) {
+                const uint32_t i = base + u * period + threadIdx.x;
+                kk[u] = (threadIdx.x < period && i < total) ? __ldcg(p.partial + (size_t)qi * total + i) : KEY_NONE;
+            }
+#pragma unroll
+            for (int u = 0; u < TAIL_U; ++u) {
+                if (base + u * period >= total) break;   // CTA-uniform
+                bool want = false;
+                if (kk[u] <= bound && kk[u] < topk.tau(qi)) want = topk.push(qi, kk[u]);
+                topk.maybe_flush(want);
             }
         }
-        topk.maybe_flush(want);
     }
     topk.final_flush();
     for (uint32_t i = threadIdx.x; i < p.nq_valid * p.K; i += blockDim.x) {
@@ -550,13 +573,14 @@ __global__ void prepare_queries_u8_kernel(const uint8_t* __restrict__ src, uint3
     __shared__ unsigned long long total;
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
-    unsigned long long ss = 0;
+    uint32_t ss = 0;   // <= 64 bytes per thread (dim <= 65536, 1024 threads): 64 * 255^2 fits
     for (uint32_t i = threadIdx.x; i < qbytes; i += blockDim.x) {
         const uint32_t v = i < dim ? src[(size_t)q * dim + i] : 0u;
         tile[(size_t)q * qbytes + i] = (uint8_t)v;
         ss += v * v;
     }
-    atomicAdd(&total, ss);
+    ss = __reduce_add_sync(0xffffffffu, ss);
+    if ((threadIdx.x & 31) == 0 && ss) atomicAdd(&total, (unsigned long long)ss);
     __syncthreads();
     if (threadIdx.x == 0) qcache[q] = metric == VDB_COSINE ? sqrtf((float)total) : (float)total;
 }
@@ -578,7 +602,8 @@ QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t
                                                          t.qcache.as<float>(), d_zero_word);
     } else {
         VDB_REQUIRE(ds->dim <= 65536, "u8 rows: dim %u too large for the 32-bit integer sums (max 65536)", ds->dim);
-        prepare_queries_u8_kernel<<<nq, 256, 0, st>>>((const uint8_t*)d_queries, ds->dim, t.qstride * 4, ds->metric,
+        // one byte per thread and pass when the query is short: the loads of a query are all in flight at once
+        prepare_queries_u8_kernel<<<nq, 1024, 0, st>>>((const uint8_t*)d_queries, ds->dim, t.qstride * 4, ds->metric,
                                                       t.q.as<uint8_t>(), t.qcache.as<float>(), d_zero_word);
     }
     VDB_LAUNCHED();

@@ -52,9 +52,22 @@ struct TopkSmem {
         for (uint32_t i = threadIdx.x; i < nseg; i += blockDim.x) ncand[i] = 0;
         __syncthreads();
     }
+    // Everything past slot K + ncand is KEY_NONE (the maximum), so sorting the smallest power-of-two prefix that holds the
+    // best and the pending candidates of every segment equals sorting the whole segment - at a fraction of the
+    // log^2(P) barrier stages when few candidates are pending (the usual state at the end of a scan or a merge).
     __device__ __forceinline__ void final_flush() {
         __syncthreads();
-        flush_nosync_entry();
+        uint32_t m = 0;
+        for (uint32_t s = 0; s < nseg; ++s) m = max(m, ncand[s]);   // CTA-uniform
+        const uint32_t need = K + m;
+        const uint32_t n = need <= 2 ? 2u : min(P, 1u << (32 - __clz(need - 1)));
+        cta_bitonic_sort(keys, n, nseg, P);  // ends with __syncthreads()
+        for (uint32_t i = threadIdx.x; i < nseg * (n - min(n, K)); i += blockDim.x) {
+            const uint32_t w = n - K, s = i / w, j = i - s * w;
+            seg(s)[K + j] = KEY_NONE;
+        }
+        for (uint32_t i = threadIdx.x; i < nseg; i += blockDim.x) ncand[i] = 0;
+        __syncthreads();
     }
     static __host__ __device__ size_t bytes(uint32_t nseg, uint32_t P) {
         return (size_t)nseg * P * 8 + (size_t)nseg * 4;

@@ -329,6 +329,7 @@ def test_round2_stages_do_not_change_a_bit(oracle, metric, monkeypatch):
         runs = {}
         for name, env in (("default", {}), ("no_prune", {"VDB_GEMM_PRUNE": "0"}), ("one_level", {"VDB_GEMM_SAMPLE_2L": "0"}),
                           ("rare_mask", {"VDB_GEMM_RARE_PER_SCORE": "0"}), ("rare_per_score", {"VDB_GEMM_RARE_PER_SCORE": "1"}),
+                          ("rare_staged", {"VDB_GEMM_RARE_PER_SCORE": "2"}),
                           ("parts3", {"VDB_GEMM_PARTS": "3"})):
             for key, val in env.items():
                 monkeypatch.setenv(key, val)
