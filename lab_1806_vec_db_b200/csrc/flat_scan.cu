@@ -30,6 +30,8 @@ struct ScanParams {
     uint64_t pitch_bytes;
     uint32_t nvec, nit;
     const float* q;        // query tile (see prepare_queries), first query of this pass
+    const uint8_t* raw_q;  // u8 rows, L2Sqr, one launch: the caller's query bytes (dim per query); the CTA pads them itself
+    uint32_t raw_dim;
     uint32_t qstride;      // floats per query
     const float* qcache;   // per query ||q|| (cosine)
     uint32_t nq_valid;
@@ -61,8 +63,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem + (size_t)NQ * p.qstride * 4);
     TopkSmem topk{tk, reinterpret_cast<uint32_t*>(tk + (size_t)NQ * p.P), p.K, p.P, NQ, p.limit};
 
-    for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x)
-        qs[i] = (i / qs4 < p.nq_valid) ? reinterpret_cast<const float4*>(p.q)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (PL == 4 && p.raw_q) {
+        // no tile kernel in front of this launch: the tile is the queries' bytes, zero padded to qstride * 4 per query
+        const uint32_t qbytes = p.qstride * 4;
+        for (uint32_t i = threadIdx.x; i < NQ * qbytes; i += blockDim.x) {
+            const uint32_t qi = i / qbytes, off = i - qi * qbytes;
+            smem[i] = (qi < p.nq_valid && off < p.raw_dim) ? p.raw_q[(size_t)qi * p.raw_dim + off] : (uint8_t)0;
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < NQ * qs4; i += blockDim.x)
+            qs[i] = (i / qs4 < p.nq_valid) ? reinterpret_cast<const float4*>(p.q)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     topk.init();
 
     const int pidx = lane >> SH;
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
 // ---- merge of key lists ------------------------------------------------------------------------
 constexpr int MERGE_THREADS = 256;
 constexpr int MERGE_UNROLL = 1;
-__global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
+__global__ void __launch_bounds__(MERGE_THREADS, 8) merge_keys_kernel(
     const uint64_t* __restrict__ keys, uint32_t nlists, uint32_t nq, uint32_t len, int list_major,
     const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ seg_cnt, uint32_t K, uint32_t P, uint32_t limit,
     uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids, float* __restrict__ dist, uint32_t* __restrict__ counts) {
@@ -371,13 +382,25 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(
                                      : (list_major ? ((l * nq + q) * len + j) : (((uint64_t)q * nlists + l) * len + j));
         return keys[src];
     };
-    uint64_t next = rounds ? load_key(0) : KEY_NONE;
-    for (uint64_t r = 0; r < rounds; ++r) {
-        const uint64_t key = next;
-        if (r + 1 < rounds) next = load_key(r + 1);
-        bool want = false;
-        if (key < topk.tau(0)) want = topk.push(0, key);
-        topk.maybe_flush(want);
+    if (total + K <= P) {
+        // everything fits next to the K best: four rounds of loads in flight at a time, no flush test, one sort
+        for (uint64_t r0 = 0; r0 < rounds; r0 += 4) {
+            uint64_t kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kk[u] = r0 + u < rounds ? load_key(r0 + u) : KEY_NONE;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (kk[u] != KEY_NONE) topk.push(0, kk[u]);
+        }
+    } else {
+        uint64_t next = rounds ? load_key(0) : KEY_NONE;
+        for (uint64_t r = 0; r < rounds; ++r) {
+            const uint64_t key = next;
+            if (r + 1 < rounds) next = load_key(r + 1);
+            bool want = false;
+            if (key < topk.tau(0)) want = topk.push(0, key);
+            topk.maybe_flush(want);
+        }
     }
     topk.final_flush();
     uint32_t valid = 0;
@@ -417,8 +440,12 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     if (smem > 48 * 1024)
         VDB_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
+    // short inputs (the sample lists of the tensor path: 16-300 keys per query, 10 000 queries): a CTA of one or two warps
+    // per query instead of eight - four times as many queries resident per SM and nearly free barriers
+    uint32_t threads = MERGE_THREADS;
+    if (total_max + k <= 1024) threads = P <= 128 ? 32u : (P <= 256 ? 64u : (P <= 512 ? 128u : 256u));
     ProfScope prof("merge", stream);
-    merge_keys_kernel<<<nq, MERGE_THREADS, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off, d_seg_cnt,
+    merge_keys_kernel<<<nq, threads, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off, d_seg_cnt,
                                                            k, P, limit, d_out_keys, d_ids,
                                                            d_dist, d_counts);
     VDB_LAUNCHED();
@@ -585,7 +612,8 @@ __global__ void prepare_queries_u8_kernel(const uint8_t* __restrict__ src, uint3
     if (threadIdx.x == 0) qcache[q] = metric == VDB_COSINE ? sqrtf((float)total) : (float)total;
 }
 
-QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, uint32_t* d_zero_word) {
+// geometry of the tile only (no buffers, no launch)
+static QueryTile query_tile_shape(const vdb_dataset* ds) {
     QueryTile t;
     const uint32_t vec = vec_elems(ds->dtype);
     t.nvec = ds->pitch / vec;
@@ -593,6 +621,12 @@ QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t
     // floats per query for f32 sets; for u8 sets the same count of 4-byte words (= nit * 512 bytes of query bytes), so
     // qstride * 4 is the tile's size in bytes per query for both
     t.qstride = ds->dtype == VDB_F32 ? t.nit * 32 * vec : t.nit * 32 * 4;
+    return t;
+}
+
+QueryTile prepare_queries(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, uint32_t* d_zero_word) {
+    QueryTile t = query_tile_shape(ds);
+    const uint32_t vec = vec_elems(ds->dtype);
     t.q = DevBuf((size_t)nq * t.qstride * 4, st);
     t.qcache = DevBuf((size_t)nq * 4, st);
     if (nq == 0) return t;
@@ -644,7 +678,17 @@ bool flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
     const char* fuse_s = getenv("VDB_SCAN_FUSE");   // read per call: the tests toggle it in one process
     const bool fuse_on = !(fuse_s && !atoi(fuse_s));
     DevBuf done(fuse_on && nq <= 8 ? 4 : 0, st);   // arrival counter of the fused tail (cleared by the tile kernel)
-    QueryTile qt = prepare_queries(ds, d_queries, nq, st, done.as<uint32_t>());
+    // u8 rows under L2Sqr in one launch (the trait's single-query call): the scan CTAs read the caller's query bytes
+    // themselves and the counter is cleared by a 4-byte memset - no tile kernel in front of the scan
+    const bool raw_q = ds->dtype == VDB_U8 && ds->metric == VDB_L2SQR && nq <= 8 && done.p != nullptr;
+    QueryTile qt;
+    if (raw_q) {
+        qt = query_tile_shape(ds);
+        VDB_REQUIRE(ds->dim <= 65536, "u8 rows: dim %u too large for the 32-bit integer sums (max 65536)", ds->dim);
+        VDB_CUDA(cudaMemsetAsync(done.p, 0, 4, st));
+    } else {
+        qt = prepare_queries(ds, d_queries, nq, st, done.as<uint32_t>());
+    }
 
     // queries per pass: as many as fit (<= 8) next to the top-k segments in shared memory.
     // The CTA-wide flush test (a barrier) runs every `sync_every` row groups: often enough that a query's segment
@@ -699,8 +743,10 @@ bool flat_scan_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
             if (grid_used == 0) grid_used = grid;
             p.iters = (uint32_t)ceil_div<uint64_t>(ngroups, (uint64_t)grid_used * SCAN_WARPS);
             p.sync_every = sync_for((uint32_t)R);
-            p.q = qt.q.as<float>() + (size_t)(q0 + qq) * qt.qstride;
-            p.qcache = qt.qcache.as<float>() + (q0 + qq);
+            p.q = raw_q ? nullptr : qt.q.as<float>() + (size_t)(q0 + qq) * qt.qstride;
+            p.qcache = raw_q ? nullptr : qt.qcache.as<float>() + (q0 + qq);
+            p.raw_q = raw_q ? (const uint8_t*)d_queries + (size_t)(q0 + qq) * ds->dim : nullptr;
+            p.raw_dim = ds->dim;
             p.nq_valid = now;
             p.partial = partial.as<uint64_t>() + (size_t)qq * grid_used * k;
             // the whole batch in this one launch: its last CTA merges and decodes
