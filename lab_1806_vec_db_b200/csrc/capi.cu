@@ -747,7 +747,7 @@ int vdb_tq_tau_dev(vdb_tq* tq, const uint64_t* d_keys_lists, uint32_t nlists, ui
 int vdb_tq_filter_dev(vdb_tq* tq, uint32_t k, const float* d_tau, uint64_t* d_keys, uint32_t* d_overflow) {
     return guarded([&] {
         VDB_REQUIRE(tq && d_tau && d_keys && d_overflow && k > 0, "NULL argument");
-        vdb::tensor_filter_keys(tq, k, 0, d_tau, d_keys, d_overflow, nullptr);
+        vdb::tensor_filter_keys(tq, k, 0, d_tau, d_keys, d_overflow);
     });
 }
 int vdb_tq_check_dev(vdb_tq* tq, const uint64_t* d_merged_keys, uint32_t k, uint64_t n_total, const float* d_tau,

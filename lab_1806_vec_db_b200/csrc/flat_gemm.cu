@@ -1263,11 +1263,6 @@ __global__ void rekey_dev_count_kernel(const float* __restrict__ dist, const uin
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
         keys[j] = make_key(dist[j], ids[j] + id_base);
 }
-__global__ void overflow_kernel(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ qbad, uint32_t nq, uint32_t cap,
-                                uint32_t* __restrict__ flag) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) flag[q] = (cnt[q] > cap || qbad[q]) ? 1u : 0u;   // non-finite queries go to the exact scan
-}
 // completeness check; failing queries are appended to redo[]
 // keys / overflow are indexed by the LOCAL query i of the checked range [q0, q0 + cnt) (a row-sharded search checks
 // only the slice of queries a GPU owns); tau / qsq by the batch index q0 + i, which is also what redo[] receives.
@@ -1355,6 +1350,15 @@ struct vdb_tq {
 };
 
 namespace vdb {
+// tq->cnt: [nq] candidate-list lengths, then (8-byte aligned) the number of reranked candidates (u64) and the number of
+// queries that failed the completeness check (u32). The filter clears all of it with one memset.
+static size_t tq_cnt_bytes(uint32_t nq) { return ((size_t)round_up(nq, 2u) + 4) * 4; }
+uint64_t* tensor_cand_total_ptr(const vdb_tq* tq) { return reinterpret_cast<uint64_t*>(tq->cnt.as<uint32_t>() + round_up(tq->nq, 2u)); }
+uint32_t* tensor_nredo_ptr(const vdb_tq* tq) { return tq->cnt.as<uint32_t>() + round_up(tq->nq, 2u) + 2; }
+
+}  // namespace vdb
+
+namespace vdb {
 
 vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, bool any_size) {
     VDB_REQUIRE(any_size || flat_gemm_supported(ds, nq, 1), "tensor-core Flat path: unsupported dataset");
@@ -1372,8 +1376,9 @@ vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, 
         tq->op_pitch = tq->kind == KIND_F16 ? round_up(dim, 8u) : tq->qpitch;
         tq->qcopy = DevBuf((size_t)nq * tq->qpitch * 4, st);
         tq->qop = DevBuf((size_t)nq * tq->op_pitch * (tq->kind == KIND_F16 ? 2 : 4), st);
-        for (DevBuf* b : {&tq->qsq, &tq->qerr, &tq->qscale, &tq->qbad, &tq->qd, &tq->qab, &tq->qb, &tq->cnt})
+        for (DevBuf* b : {&tq->qsq, &tq->qerr, &tq->qscale, &tq->qbad, &tq->qd, &tq->qab, &tq->qb})
             *b = DevBuf((size_t)nq * 4, st);
+        tq->cnt = DevBuf(tq_cnt_bytes(nq), st);   // list lengths + the call's two counters, cleared by one memset
         const bool l2 = ds->metric == VDB_L2SQR;
         const uint32_t pgrid = ceil_div(nq, 8u);   // 8 warps per CTA, one query each
         auto prep = [&](auto kern, auto* src) {
@@ -1597,23 +1602,10 @@ struct SideDrain {
         if (armed) cudaStreamSynchronize(s);
     }
 };
-// sum of min(cnt, cap) over the queries (instrumentation: candidates reranked)
-__global__ void __launch_bounds__(1024) cand_total_kernel(const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t cap,
-                                                          uint64_t* __restrict__ out) {
-    __shared__ unsigned long long sum;
-    if (threadIdx.x == 0) sum = 0;
-    __syncthreads();
-    unsigned long long mine = 0;
-    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) mine += min(cnt[q], cap);
-    atomicAdd(&sum, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) *out = sum;
-}
-
 // FILTER + RERANK: rows with S' < tau_q -> exact distances -> this shard's k best keys per query.
 // d_overflow[q] = 1 when the candidate list of q overflowed (its result is then incomplete).
 void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
-                        uint32_t* d_overflow, uint64_t* d_cand_total) {
+                        uint32_t* d_overflow, const TensorCheck* check) {
     const vdb_dataset* ds = tq->ds;
     cudaStream_t st = tq->st;
     const uint32_t nq = tq->nq, dim = ds->dim;
@@ -1622,7 +1614,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         ds->n, std::max<uint64_t>(8ull * std::max(j0_local_hint, 1u) * (ds->n / ns), 8192)));
     tq->cap = cap;
     DevBuf cand((size_t)nq * cap * 8, st);
-    VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, (size_t)nq * 4, st));
+    VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, tq_cnt_bytes(nq), st));
     const CUtensorMap mx = make_op_map(tq->kind, op_rows_of(ds), dim, ds->n, op_row_bytes_of(ds), GN / tq->ctas);
     GemmParams pf = base_params(tq);
     pf.sqnorm = ds->d_sqnorm;
@@ -1731,15 +1723,23 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
     drain.armed = false;   // from here on the main stream is ordered after the side stream
     // the k best exact keys of every query's list (its first min(cnt, cap) entries)
     const uint32_t* final_cnt = prune ? snaps.as<uint32_t>() : tq->cnt.as<uint32_t>();   // <= cap when pruned
-    launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr, final_cnt);
-    if (d_overflow) {
-        overflow_kernel<<<ceil_div(nq, 256u), 256, 0, st>>>(tq->cnt.as<uint32_t>(), tq->qbad.as<uint32_t>(), nq, cap, d_overflow);
-        VDB_LAUNCHED();
+    // the merge's CTA of a query also sets its overflow flag, counts its reranked rows and (single-GPU calls) runs the
+    // completeness check on the keys it still holds: overflow_kernel + cand_total_kernel + check_kernel + a memset less
+    MergeFinish fin;
+    fin.cnt_raw = tq->cnt.as<uint32_t>();
+    fin.qbad = tq->qbad.as<uint32_t>();
+    fin.cap = cap;
+    fin.overflow = d_overflow;
+    fin.cand_total = reinterpret_cast<unsigned long long*>(tensor_cand_total_ptr(tq));
+    if (check) {
+        fin.tau = d_tau;
+        fin.qsq = ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>();
+        fin.n_total = check->n_total;
+        fin.force_mod = g_debug_force_redo.load();
+        fin.redo = check->d_redo;
+        fin.nredo = tensor_nredo_ptr(tq);
     }
-    if (d_cand_total) {
-        cand_total_kernel<<<1, 1024, 0, st>>>(final_cnt, nq, cap, d_cand_total);   // rows the exact rerank gathered
-        VDB_LAUNCHED();
-    }
+    launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr, final_cnt, &fin);
 }
 
 // CHECK: the (merged) result of q is provably exact iff no shard overflowed and d_k - ||q||^2 < tau_q
@@ -1762,7 +1762,7 @@ void tensor_check_range(vdb_tq* tq, uint32_t q0, uint32_t cnt, const uint64_t* d
 // One chunk of the batch, enqueued WITHOUT a host synchronisation: sample -> tau -> filter -> rerank -> check.
 struct ChunkState {
     vdb_tq* tq = nullptr;
-    DevBuf redo, nredo, ctotal;
+    DevBuf redo;
     const void* d_queries = nullptr;
     uint64_t* d_keys = nullptr;
     uint32_t nq = 0;
@@ -1777,15 +1777,12 @@ static void chunk_enqueue(const vdb_dataset* ds, const void* d_queries, uint32_t
     cs.nq = nq;
     cs.tq = tensor_begin(ds, d_queries, nq, st);
     const uint32_t j0 = tensor_j0(k, ds->sample_n, ds->n), j = tensor_sample_j(j0, ds->sample_n);
-    DevBuf jkeys((size_t)nq * j * 8, st), tau((size_t)nq * 4, st), overflow((size_t)nq * 4, st);
+    DevBuf jkeys((size_t)nq * j * 8, st), tau((size_t)nq * 4, st);
     cs.redo = DevBuf((size_t)nq * 4, st);
-    cs.nredo = DevBuf(4, st);
-    cs.ctotal = DevBuf(8, st);
     tensor_sample_keys(cs.tq, j, jkeys.as<uint64_t>());
     tensor_tau(cs.tq, jkeys.as<uint64_t>(), 1, j, std::min(j0, j), tau.as<float>());
-    tensor_filter_keys(cs.tq, k, j0, tau.as<float>(), d_keys, overflow.as<uint32_t>(), cs.ctotal.as<uint64_t>());
-    tensor_check(cs.tq, d_keys, k, ds->n, tau.as<float>(), overflow.as<uint32_t>(), cs.redo.as<uint32_t>(),
-                 cs.nredo.as<uint32_t>());
+    const TensorCheck chk{ds->n, cs.redo.as<uint32_t>()};
+    tensor_filter_keys(cs.tq, k, j0, tau.as<float>(), d_keys, nullptr, &chk);   // check fused into the final merge
 }
 
 // worker streams of the chunk pipeline (per host thread and device)
@@ -1855,8 +1852,8 @@ void flat_gemm_keys(const vdb_dataset* ds, const void* d_queries, uint32_t nq, u
                 VDB_CUDA(cudaStreamWaitEvent(st, ws.join[i], 0));
             }
         for (auto& c : cs) {
-            VDB_CUDA(cudaMemcpyAsync(&c.h_redo, c.nredo.p, 4, cudaMemcpyDeviceToHost, st));
-            VDB_CUDA(cudaMemcpyAsync(&c.h_cands, c.ctotal.p, 8, cudaMemcpyDeviceToHost, st));
+            VDB_CUDA(cudaMemcpyAsync(&c.h_redo, tensor_nredo_ptr(c.tq), 4, cudaMemcpyDeviceToHost, st));
+            VDB_CUDA(cudaMemcpyAsync(&c.h_cands, tensor_cand_total_ptr(c.tq), 8, cudaMemcpyDeviceToHost, st));
         }
         VDB_CUDA(cudaStreamSynchronize(st));
         for (auto& c : cs) {

@@ -352,7 +352,8 @@ constexpr int MERGE_UNROLL = 1;
 __global__ void __launch_bounds__(MERGE_THREADS, 8) merge_keys_kernel(
     const uint64_t* __restrict__ keys, uint32_t nlists, uint32_t nq, uint32_t len, int list_major,
     const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ seg_cnt, uint32_t K, uint32_t P, uint32_t limit,
-    uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids, float* __restrict__ dist, uint32_t* __restrict__ counts) {
+    uint64_t* __restrict__ out_keys, uint64_t* __restrict__ ids, float* __restrict__ dist, uint32_t* __restrict__ counts,
+    const MergeFinish fin) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* tk = reinterpret_cast<uint64_t*>(smem);
     const uint32_t q = blockIdx.x;
@@ -418,11 +419,34 @@ __global__ void __launch_bounds__(MERGE_THREADS, 8) merge_keys_kernel(
     if (valid) atomicAdd(&total_valid, valid);
     __syncthreads();
     if (threadIdx.x == 0 && counts) counts[q] = total_valid;
+    if (fin.cnt_raw && threadIdx.x == 0) {
+        // the same tests as overflow_kernel / check_kernel (flat_gemm.cu), on the keys still in shared memory
+        const bool ovf = fin.cnt_raw[q] > fin.cap || (fin.qbad && fin.qbad[q]);
+        if (fin.overflow) fin.overflow[q] = ovf ? 1u : 0u;
+        if (fin.cand_total) atomicAdd(fin.cand_total, (unsigned long long)min((uint64_t)fin.cap, total));
+        if (fin.redo) {
+            const uint32_t need = (uint32_t)((uint64_t)K < fin.n_total ? (uint64_t)K : fin.n_total);
+            bool ok = !ovf;
+            if (ok && need) {
+                const uint64_t kk = topk.seg(0)[need - 1];
+                ok = kk != KEY_NONE;
+                if (ok) {
+                    const float dk = key_dist(kk);
+                    const float shift = fin.qsq ? fin.qsq[q] : 0.f;
+                    const float slack = 2e-5f * (fabsf(dk) + shift + fabsf(fin.tau[q]));
+                    ok = (dk - shift) < fin.tau[q] - slack;
+                }
+            }
+            if (fin.force_mod && q % fin.force_mod == 0) ok = false;
+            if (!ok) fin.redo[atomicAdd(fin.nredo, 1u)] = q;
+        }
+    }
 }
 
 void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
-                       uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off, const uint32_t* d_seg_cnt) {
+                       uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off, const uint32_t* d_seg_cnt,
+                       const MergeFinish* finish) {
     if (nq == 0 || k == 0) return;
     // segment size: small inputs (K + all keys of a query fit in 1024 slots) are loaded completely and sorted once
     // in the smallest power-of-two segment; larger inputs stream through a K + 2 * 256 slot segment
@@ -447,7 +471,7 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     ProfScope prof("merge", stream);
     merge_keys_kernel<<<nq, threads, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off, d_seg_cnt,
                                                            k, P, limit, d_out_keys, d_ids,
-                                                           d_dist, d_counts);
+                                                           d_dist, d_counts, finish ? *finish : MergeFinish{});
     VDB_LAUNCHED();
 }
 

@@ -204,8 +204,16 @@ void tensor_end(vdb_tq* tq);
 void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys);
 void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float* d_tau);
 uint32_t tensor_sample_j(uint32_t j0, uint64_t sample_n);
+// check != nullptr: the completeness check runs inside the filter's final merge (queries that fail go to d_redo, their
+// number to *tensor_nredo_ptr(tq)); the number of reranked candidates is always left in *tensor_cand_total_ptr(tq)
+struct TensorCheck {
+    uint64_t n_total;
+    uint32_t* d_redo;
+};
 void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
-                        uint32_t* d_overflow, uint64_t* d_cand_total);
+                        uint32_t* d_overflow, const TensorCheck* check = nullptr);
+uint64_t* tensor_cand_total_ptr(const vdb_tq* tq);
+uint32_t* tensor_nredo_ptr(const vdb_tq* tq);
 void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,
                   const uint32_t* d_overflow, uint32_t* d_redo, uint32_t* d_nredo);
 void tensor_check_range(vdb_tq* tq, uint32_t q0, uint32_t cnt, const uint64_t* d_keys, uint32_t k, uint64_t n_total,

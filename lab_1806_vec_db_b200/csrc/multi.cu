@@ -219,7 +219,10 @@ static void worker_main(vdb_sharded_state* S, uint32_t s) {
         }
         seen = S->gen.load(std::memory_order_acquire);
         const auto& phases = *S->phases;
+        static const bool trace = getenv("VDB_MG_TRACE") != nullptr;   // host time each phase takes to enqueue (diagnostic)
+        double host_us[8] = {};
         for (size_t p = 0; p < phases.size(); ++p) {
+            const auto t0 = std::chrono::steady_clock::now();
             if (!S->failed.load(std::memory_order_acquire)) {
                 try {
                     phases[p](s);
@@ -231,8 +234,12 @@ static void worker_main(vdb_sharded_state* S, uint32_t s) {
                     if (!S->failed.exchange(true)) S->err = e.what(), S->err_code = VDB_ECUDA;
                 }
             }
+            if (trace && p < 8) host_us[p] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
             if (p + 1 < phases.size()) S->barrier.wait();
         }
+        if (trace && s == 0)
+            fprintf(stderr, "[vdb mg] shard 0 host us per phase: %.0f %.0f %.0f %.0f %.0f\n", host_us[0], host_us[1], host_us[2], host_us[3],
+                    host_us[4]);
         if (S->failed.load()) cudaStreamSynchronize(S->shards[s].st);   // nothing of the call may outlive it
         if (S->done.fetch_add(1, std::memory_order_acq_rel) + 1 == S->shards.size()) {
             std::lock_guard<std::mutex> lk(S->mu);
@@ -480,7 +487,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
     std::vector<vdb_tq*> tqs(G, nullptr);
     std::vector<const void*> qptr(G, nullptr);
     struct Local {
-        DevBuf jkeys, tau, keys, ovf, merged, ovm, redo, nredo, ctotal;
+        DevBuf jkeys, tau, keys, ovf, merged, ovm, redo, nredo;
     };
     std::vector<Local> loc(G);
 
@@ -531,7 +538,10 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
         tensor_sample_keys(tqs[s], j, loc[s].jkeys.as<uint64_t>());
         PtrList dst{};
         for (uint32_t h = 0; h < G; ++h) dst.p[h] = (uint8_t*)S->shards[h].jall.p + (size_t)s * nq * j * 8;
-        bcast(loc[s].jkeys.p, (size_t)nq * j * 8, dst, G, sh.st);
+        {
+            PhaseProf pb(s == 0, "mg_bcast", sh.st);
+            bcast(loc[s].jkeys.p, (size_t)nq * j * 8, dst, G, sh.st);
+        }
         VDB_CUDA(cudaEventRecord(sh.ev[EV_S], sh.st));
     });
     // P2: thresholds + filter + rerank (tensor) / exact scan; rows of the owned slices go to their owners
@@ -544,12 +554,10 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
             wait_peers(S, s, EV_S);
             L.tau = DevBuf((size_t)nq * 4, sh.st);
             L.ovf = DevBuf((size_t)nq * 4, sh.st);
-            L.ctotal = DevBuf(8, sh.st);
             tensor_tau(tqs[s], (const uint64_t*)sh.jall.p, G, j, (uint32_t)std::min<uint64_t>(j0, (uint64_t)j * G),
                        L.tau.as<float>());
-            tensor_filter_keys(tqs[s], k, 0, L.tau.as<float>(), L.keys.as<uint64_t>(), L.ovf.as<uint32_t>(),
-                               L.ctotal.as<uint64_t>());
-            VDB_CUDA(cudaMemcpyAsync(sh.h_stat, L.ctotal.p, 8, cudaMemcpyDeviceToHost, sh.st));
+            tensor_filter_keys(tqs[s], k, 0, L.tau.as<float>(), L.keys.as<uint64_t>(), L.ovf.as<uint32_t>());
+            VDB_CUDA(cudaMemcpyAsync(sh.h_stat, tensor_cand_total_ptr(tqs[s]), 8, cudaMemcpyDeviceToHost, sh.st));
         } else if (producer) {
             (*producer)(s, qptr[s], nq, k, L.keys.as<uint64_t>(), sh.st);
         } else {
@@ -563,9 +571,12 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
             dk.p[h] = (uint8_t*)S->shards[h].kin.p + (size_t)s * cnt * k * 8;
             df.p[h] = (uint8_t*)S->shards[h].ovin.p + (size_t)s * cnt * 4;
         }
-        scatter_owner_kernel<<<nq, 128, 0, sh.st>>>(L.keys.as<uint64_t>(), tensor ? L.ovf.as<uint32_t>() : nullptr, nq, k, per,
-                                                    dk, df);
-        VDB_LAUNCHED();
+        {
+            PhaseProf ps(s == 0, "mg_scatter", sh.st);
+            scatter_owner_kernel<<<nq, 128, 0, sh.st>>>(L.keys.as<uint64_t>(), tensor ? L.ovf.as<uint32_t>() : nullptr, nq, k, per,
+                                                        dk, df);
+            VDB_LAUNCHED();
+        }
         VDB_CUDA(cudaEventRecord(sh.ev[EV_F], sh.st));
     });
     // P3: merge of the owned slice, completeness check, result slice

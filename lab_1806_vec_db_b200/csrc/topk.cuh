@@ -81,9 +81,26 @@ inline uint32_t topk_segment_size(uint32_t K, uint32_t period) { return next_pow
 // in: keys[list][query][len] when list_major, else keys[query][list][len].
 void launch_merge_sorted(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, uint32_t k, uint64_t* d_out_keys,
                          uint64_t* d_ids, float* d_dist, uint32_t* d_counts, cudaStream_t stream);
+// Optional tail of launch_merge_keys for the tensor path's final merge (one CTA per query is already there): the list's
+// overflow flag, the instrumentation count and the completeness check of the merged result - four launches folded into
+// the merge. cnt_raw == nullptr: off.
+struct MergeFinish {
+    const uint32_t* cnt_raw = nullptr;   // [nq] candidates the filter produced (before pruning): > cap = overflowed list
+    const uint32_t* qbad = nullptr;      // [nq] non-finite queries (always redone)
+    uint32_t cap = 0;
+    uint32_t* overflow = nullptr;        // [nq] out, optional
+    unsigned long long* cand_total = nullptr;   // += min(list length, cap); zeroed by the caller
+    // completeness check (redo == nullptr: off): the result of q is exact iff d_need - shift < tau_q - slack
+    const float* tau = nullptr;
+    const float* qsq = nullptr;          // nullptr: cosine
+    uint64_t n_total = 0;
+    uint32_t force_mod = 0;
+    uint32_t* redo = nullptr;
+    uint32_t* nredo = nullptr;           // zeroed by the caller
+};
 void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uint32_t len, bool list_major,
                        uint32_t k, uint64_t* d_out_keys, uint64_t* d_ids, float* d_dist,
                        uint32_t* d_counts, cudaStream_t stream, const uint64_t* d_seg_off = nullptr,
-                       const uint32_t* d_seg_cnt = nullptr);
+                       const uint32_t* d_seg_cnt = nullptr, const MergeFinish* finish = nullptr);
 
 }  // namespace vdb

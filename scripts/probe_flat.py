@@ -18,7 +18,7 @@ if u8:
 esz = 1 if u8 else 4
 ds = V.DeviceVecSet.from_device(base.data_ptr(), n, dim, dim, np.uint8 if u8 else np.float32, os.environ.get("METRIC", "l2sqr"), keepalive=base)
 lib = L.lib()
-L.check(lib.vdb_flat_set_path(1))
+L.check(lib.vdb_flat_set_path(int(os.environ.get("FLATPATH", 1))))
 stream = torch.cuda.current_stream().cuda_stream
 cases = [(1, 10), (2, 10), (4, 10), (8, 10), (8, 100), (1, 100), (16, 10), (64, 100)]
 if os.environ.get("CASES"):  # e.g. CASES=8:10,4:10
