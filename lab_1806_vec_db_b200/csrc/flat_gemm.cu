@@ -1009,17 +1009,37 @@ __global__ void tau_from_keys_kernel(const uint64_t* __restrict__ keys, uint32_t
 // <= d_k - ||q||^2 <= d_(j0) - ||q||^2 whenever the j0-th sampled distance is not better than the k-th best of the set
 // (probability > 1 - 2e-5 by the choice of j0, verified per query by the check kernel). The slack keeps the check's
 // strict comparison satisfiable when the j0-th sampled row IS the k-th best.
+__device__ __forceinline__ float tau_of_key(uint64_t kk, float shift) {
+    if (kk == KEY_NONE) return __uint_as_float(0x7f800000u);   // fewer than j0 sampled rows: keep everything
+    const float d = key_dist(kk);
+    return (d - shift) + 1e-4f * (fabsf(d) + shift) + 1e-30f;
+}
 __global__ void tau_exact_kernel(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t j, uint32_t j0,
                                  const float* __restrict__ qsq, float* __restrict__ tau) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    const uint64_t kk = keys[(size_t)q * j + (j0 - 1)];
-    if (kk == KEY_NONE) {
-        tau[q] = __uint_as_float(0x7f800000u);   // fewer than j0 sampled rows: keep everything
-        return;
+    tau[q] = tau_of_key(keys[(size_t)q * j + (j0 - 1)], qsq ? qsq[q] : 0.f);
+}
+// Tail of the sample phase for j <= 32, one warp per query: exact distances of the j best sampled rows -> keys -> ascending
+// (rank by counting, ties cannot occur: the ids differ) -> optionally tau_q from the j0-th. Replaces a re-keying launch, a
+// one-CTA-per-query merge and the tau launch.
+__global__ void __launch_bounds__(256) sample_finish_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ rid,
+                                                            const uint8_t* __restrict__ valid, uint32_t id_base, uint32_t nq,
+                                                            uint32_t j, uint64_t* __restrict__ jkeys, uint32_t j0,
+                                                            const float* __restrict__ qsq, float* __restrict__ tau) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;   // warp-uniform
+    const size_t i = (size_t)q * j + lane;
+    const uint64_t mine = (lane < j && valid[i]) ? make_key(dist[i], id_base + rid[i]) : KEY_NONE;
+    uint32_t rank = 0;
+    for (uint32_t m = 0; m < j; ++m) {
+        const uint64_t other = __shfl_sync(0xffffffffu, mine, m);
+        rank += (other < mine || (other == mine && m < lane)) ? 1u : 0u;
     }
-    const float d = key_dist(kk), shift = qsq ? qsq[q] : 0.f;
-    tau[q] = (d - shift) + 1e-4f * (fabsf(d) + shift) + 1e-30f;
+    if (lane < j) {
+        jkeys[(size_t)q * j + rank] = mine;
+        if (tau && rank == j0 - 1) tau[q] = tau_of_key(mine, qsq ? qsq[q] : 0.f);
+    }
 }
 // two-level sample selection: coarse threshold = the j1-th smallest sub-sample score, nudged up so that the strict
 // comparison of the filter keeps the row it came from (+inf when the sub-sample holds fewer than j1 rows)
@@ -1050,17 +1070,37 @@ template <int METRIC>
 __global__ void __launch_bounds__(256) cand_prune_kernel(uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap,
                                                          uint32_t k, const float* __restrict__ rnorm, const float* __restrict__ ex,
                                                          const float* __restrict__ qab, const float* __restrict__ qb,
-                                                         const float* __restrict__ qsq, uint32_t* __restrict__ cnt_out) {
+                                                         const float* __restrict__ qsq, uint32_t* __restrict__ cnt_out,
+                                                         uint64_t* __restrict__ off, unsigned long long* __restrict__ pair_total,
+                                                         uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid) {
     extern __shared__ uint32_t prune_u[];   // [min(cnt, cap)] order bits of U
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_bin, s_k, s_warp[8], s_base;
+    __shared__ unsigned long long s_off;
     const uint32_t q = blockIdx.x, tid = threadIdx.x;
     const uint32_t c = min(cnt[q], cap);
+    uint64_t* list = cand + (uint64_t)q * cap;
+    // off != nullptr: the surviving (query, row) pairs go straight to the rerank's input arrays, at a range claimed with
+    // one atomic per query (the order of the ranges does not matter: every pair carries its query) - no separate
+    // prefix-sum and pair-building launches
+    auto emit_pairs = [&](uint32_t count) {
+        if (!off) return;
+        if (tid == 0) {
+            s_off = atomicAdd(pair_total, (unsigned long long)count);
+            off[q] = s_off;
+        }
+        __syncthreads();
+        const unsigned long long o = s_off;
+        for (uint32_t j = tid; j < count; j += blockDim.x) {
+            qidx[o + j] = q;
+            rid[o + j] = (uint32_t)list[j];
+        }
+    };
     if (c <= k) {
         if (tid == 0) cnt_out[q] = c;
+        emit_pairs(c);
         return;
     }
-    uint64_t* list = cand + (uint64_t)q * cap;
     const float a = qab[q], b = qb[q], shift = qsq ? qsq[q] : 0.f;
     for (uint32_t j = tid; j < c; j += blockDim.x) {
         const uint64_t e = list[j];
@@ -1133,6 +1173,7 @@ __global__ void __launch_bounds__(256) cand_prune_kernel(uint64_t* __restrict__ 
         __syncthreads();
     }
     if (tid == 0) cnt_out[q] = s_base;
+    emit_pairs(s_base);   // the loop's last barrier ordered the compacted list
 }
 // (query, source row) pairs of the j best sampled rows of every query; KEY_NONE entries are masked out
 __global__ void sample_pairs_kernel(const uint64_t* __restrict__ keys, uint64_t count, uint32_t j,
@@ -1236,8 +1277,8 @@ __global__ void part_to_pairs_kernel(const uint64_t* __restrict__ cand, const ui
 __global__ void part_rekey_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ qidx,
                                   const uint32_t* __restrict__ rid, const uint64_t* __restrict__ off, uint32_t nq,
                                   const uint32_t* __restrict__ prev, uint32_t cap, uint32_t id_base,
-                                  uint64_t* __restrict__ cand) {
-    const uint64_t n = off[nq];
+                                  uint64_t* __restrict__ cand, const uint64_t* __restrict__ n_ptr) {
+    const uint64_t n = n_ptr ? *n_ptr : off[nq];
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t q = qidx[i];
         const uint32_t j = (prev ? min(prev[q], cap) : 0u) + (uint32_t)(i - off[q]);
@@ -1352,7 +1393,9 @@ struct vdb_tq {
 namespace vdb {
 // tq->cnt: [nq] candidate-list lengths, then (8-byte aligned) the number of reranked candidates (u64) and the number of
 // queries that failed the completeness check (u32). The filter clears all of it with one memset.
-static size_t tq_cnt_bytes(uint32_t nq) { return ((size_t)round_up(nq, 2u) + 4) * 4; }
+static size_t tq_cnt_bytes(uint32_t nq) { return ((size_t)round_up(nq, 2u) + 6) * 4; }
+// ... and the number of (query, row) pairs the pruning kernel handed to the rerank (u64)
+static uint64_t* tq_pairs_ptr(const vdb_tq* tq) { return reinterpret_cast<uint64_t*>(tq->cnt.as<uint32_t>() + round_up(tq->nq, 2u) + 4); }
 uint64_t* tensor_cand_total_ptr(const vdb_tq* tq) { return reinterpret_cast<uint64_t*>(tq->cnt.as<uint32_t>() + round_up(tq->nq, 2u)); }
 uint32_t* tensor_nredo_ptr(const vdb_tq* tq) { return tq->cnt.as<uint32_t>() + round_up(tq->nq, 2u) + 2; }
 
@@ -1446,7 +1489,7 @@ static GemmParams base_params(const vdb_tq* tq) {
 
 // SAMPLE: the j best sampled rows of every query by pruning score, re-evaluated exactly: d_jkeys [nq][j] = keys
 // (exact distance, global row id), ascending, KEY_NONE padded
-void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
+void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys, float* d_tau, uint32_t j0) {
     const vdb_dataset* ds = tq->ds;
     cudaStream_t st = tq->st;
     const uint64_t ns = ds->sample_n;
@@ -1543,8 +1586,20 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys) {
     VDB_LAUNCHED();
     exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), valid.as<uint8_t>(), cnt,
                                 dist.as<float>(), st, nullptr, ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr);
+    const float* qsq = ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>();
+    if (j <= 32) {
+        VDB_REQUIRE(!d_tau || (j0 >= 1 && j0 <= j), "j0 out of range");
+        sample_finish_kernel<<<ceil_div(tq->nq, 8u), 256, 0, st>>>(dist.as<float>(), rid.as<uint32_t>(), valid.as<uint8_t>(),
+                                                                  (uint32_t)ds->id_base, tq->nq, j, d_jkeys, j0, qsq, d_tau);
+        VDB_LAUNCHED();
+        return;
+    }
     rekey_based(dist.as<float>(), rid.as<uint32_t>(), (uint32_t)ds->id_base, valid.as<uint8_t>(), cnt, ekeys.as<uint64_t>(), st);
     launch_merge_keys(ekeys.as<uint64_t>(), 1, tq->nq, j, false, j, d_jkeys, nullptr, nullptr, nullptr, st);
+    if (d_tau) {
+        tau_exact_kernel<<<ceil_div(tq->nq, 256u), 256, 0, st>>>(d_jkeys, tq->nq, j, j0, qsq, d_tau);
+        VDB_LAUNCHED();
+    }
 }
 
 // TAU: merge `nlists` shards' [nq][j] exact sample keys (list-major) and set tau_q from the j0-th smallest
@@ -1693,7 +1748,9 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
             const size_t sm = (size_t)cap * 4;
             if (sm > 48 * 1024) VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             kern<<<nq, 256, sm, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, k, ds->d_lo, ds->d_ex, tq->qab.as<float>(),
-                                      tq->qb.as<float>(), ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(), snap);
+                                      tq->qb.as<float>(), ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(), snap,
+                                      off.as<uint64_t>(), reinterpret_cast<unsigned long long*>(tq_pairs_ptr(tq)),
+                                      qidx.as<uint32_t>(), rid.as<uint32_t>());
             VDB_LAUNCHED();
         } else {
             VDB_CUDA(cudaMemcpyAsync(snap, tq->cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToDevice, st));
@@ -1703,17 +1760,20 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
             VDB_CUDA(cudaStreamWaitEvent(rs, side.ev, 0));
         }
         // exact rerank of the part's candidates (compacted: only the valid pairs are touched)
-        part_offsets_kernel<<<1, 1024, 0, rs>>>(prev, snap, nq, cap, off.as<uint64_t>());
-        VDB_LAUNCHED();
-        part_to_pairs_kernel<<<nq, 256, 0, rs>>>(cand.as<uint64_t>(), prev, snap, cap, off.as<uint64_t>(), qidx.as<uint32_t>(),
-                                                 rid.as<uint32_t>());
-        VDB_LAUNCHED();
+        const uint64_t* n_pairs = prune ? tq_pairs_ptr(tq) : off.as<uint64_t>() + nq;   // pruned: pairs came with the pruning
+        if (!prune) {
+            part_offsets_kernel<<<1, 1024, 0, rs>>>(prev, snap, nq, cap, off.as<uint64_t>());
+            VDB_LAUNCHED();
+            part_to_pairs_kernel<<<nq, 256, 0, rs>>>(cand.as<uint64_t>(), prev, snap, cap, off.as<uint64_t>(), qidx.as<uint32_t>(),
+                                                     rid.as<uint32_t>());
+            VDB_LAUNCHED();
+        }
         exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total,
-                                    dist.as<float>(), rs, off.as<uint64_t>() + nq,
+                                    dist.as<float>(), rs, n_pairs,
                                     ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr);
         part_rekey_kernel<<<(uint32_t)sm_count() * 8, 256, 0, rs>>>(dist.as<float>(), qidx.as<uint32_t>(), rid.as<uint32_t>(),
                                                                    off.as<uint64_t>(), nq, prev, cap, (uint32_t)ds->id_base,
-                                                                   cand.as<uint64_t>());
+                                                                   cand.as<uint64_t>(), prune ? n_pairs : nullptr);
         VDB_LAUNCHED();
     }
     if (parts > 1) {
@@ -1779,8 +1839,7 @@ static void chunk_enqueue(const vdb_dataset* ds, const void* d_queries, uint32_t
     const uint32_t j0 = tensor_j0(k, ds->sample_n, ds->n), j = tensor_sample_j(j0, ds->sample_n);
     DevBuf jkeys((size_t)nq * j * 8, st), tau((size_t)nq * 4, st);
     cs.redo = DevBuf((size_t)nq * 4, st);
-    tensor_sample_keys(cs.tq, j, jkeys.as<uint64_t>());
-    tensor_tau(cs.tq, jkeys.as<uint64_t>(), 1, j, std::min(j0, j), tau.as<float>());
+    tensor_sample_keys(cs.tq, j, jkeys.as<uint64_t>(), tau.as<float>(), std::min(j0, j));   // tau from the same launch
     const TensorCheck chk{ds->n, cs.redo.as<uint32_t>()};
     tensor_filter_keys(cs.tq, k, j0, tau.as<float>(), d_keys, nullptr, &chk);   // check fused into the final merge
 }
@@ -2257,7 +2316,7 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
             auto kern = cosine ? cand_prune_kernel<VDB_COSINE> : cand_prune_kernel<VDB_L2SQR>;
             kern<<<nq, 256, (size_t)cap * 4, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, k, ivf->d_rn_lo, ivf->d_ex_lo,
                                                    tq->qab.as<float>(), tq->qb.as<float>(), cosine ? nullptr : tq->qsq.as<float>(),
-                                                   pcnt.as<uint32_t>());
+                                                   pcnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
             VDB_LAUNCHED();
         }
         // ---- exact rerank (the FP32 list scan's arithmetic) and top-k ----

@@ -201,7 +201,8 @@ uint32_t tensor_j0(uint32_t k, uint64_t ns, uint64_t n, double eps = 2e-5);
 vdb_tq* tensor_begin(const vdb_dataset* ds, const void* d_queries, uint32_t nq, cudaStream_t st, bool any_size = false);
 void operand_info(const vdb_dataset* ds, int* kind, float* scale, float* mean_norm, float* mean_ex, uint64_t* side_bytes);
 void tensor_end(vdb_tq* tq);
-void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys);
+// d_tau != nullptr: also tau_q from the j0-th smallest exact sample distance (single-shard calls: no exchange in between)
+void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys, float* d_tau = nullptr, uint32_t j0 = 0);
 void tensor_tau(vdb_tq* tq, const uint64_t* d_lists, uint32_t nlists, uint32_t j, uint32_t j0, float* d_tau);
 uint32_t tensor_sample_j(uint32_t j0, uint64_t sample_n);
 // check != nullptr: the completeness check runs inside the filter's final merge (queries that fail go to d_redo, their
