@@ -120,8 +120,9 @@ class Legs:
             ms = self.timed(lambda: L.check(lib.vdb_ivf_knn_dev(self.vs._h, ivf._h, C.c_void_p(self.q.data_ptr()), self.nq, self.k,
                                                                 nprobe, *self.out_ptrs(), self.st)))
             e2e_s, _ = self.wall(lambda: ivf.knn_with_ef_batch(self.q_host, self.k, nprobe))
+            bh = self.base_host()   # the host copy of the rows is made outside the timed call
             t0 = time.perf_counter()
-            oi, _, _ = O.ivf_knn(self.base_host(), km.centroids, off, mem, self.q_host[:self.nc], self.k, nprobe, "l2sqr",
+            oi, _, _ = O.ivf_knn(bh, km.centroids, off, mem, self.q_host[:self.nc], self.k, nprobe, "l2sqr",
                                  nthreads=self.cores)
             cpu_s = time.perf_counter() - t0
             # a 1000-query batch probes every list: each list's rows are streamed once (FP16 operand copy in list order)
@@ -162,8 +163,9 @@ class Legs:
             ms = self.timed(lambda: L.check(lib.vdb_pq_knn_dev(self.vs._h, pq._h, C.c_void_p(self.q.data_ptr()), self.nq, self.k,
                                                                ef, *self.out_ptrs(), self.st)))
             e2e_s, _ = self.wall(lambda: self.flat.knn_pq_batch(self.q_host, self.k, ef, pq))
+            bh = self.base_host()
             t0 = time.perf_counter()
-            oi, _, _ = O.flat_knn_pq(self.base_host(), pq.encoded_vec_set, books, 240, 4, self.q_host[:self.nc], self.k, ef,
+            oi, _, _ = O.flat_knn_pq(bh, pq.encoded_vec_set, books, 240, 4, self.q_host[:self.nc], self.k, ef,
                                      "l2sqr", nthreads=self.cores)
             cpu_s = time.perf_counter() - t0
             # m = dim / 4: the ADC filter is a contraction over rows decoded on the fly, K = dim; the one-hot

@@ -65,8 +65,8 @@ template <int CTAS, int KIND = KIND_TF32> struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * GKB;
     static constexpr int STAGE_BYTES = G_A_BYTES + B_BYTES;     // 48 KB / 32 KB
     static constexpr int STAGES = CTAS == 1 ? 4 : 6;            // 192 KB either way
-    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 3 * GN * 4 /*row-scalar tiles*/ + 512 /*barriers*/ +
-                                     4 * G_STG_CAP * 12 /*candidate staging of the 4 epilogue warps*/;
+    static constexpr uint32_t SMEM = 1024 /*align*/ + STAGES * STAGE_BYTES + 2 * 3 * GN * 4 /*row-scalar tiles*/ + 512 /*barriers*/;
+    static constexpr uint32_t SMEM_STAGED = SMEM + 4 * G_STG_CAP * 12;   // + candidate staging of the 4 epilogue warps
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32 or F16, both K-major, N>>3, M>>4
     static constexpr uint32_t IDESC = (1u << 4) | (KindCfg<KIND>::FMT << 7) | (KindCfg<KIND>::FMT << 10) |
                                       ((uint32_t)(GN >> 3) << 17) | ((uint32_t)((GM * CTAS) >> 4) << 24);
@@ -145,7 +145,10 @@ __device__ __forceinline__ ItemView decode_item(const GemmParams& p, uint32_t it
     return v;
 }
 
-template <int MODE, int CTAS, int METRIC, int KIND>
+// STAGED (filter only): passing scores go through the per-warp staging buffer (G_STG_CAP). A separate instantiation: as
+// a run-time switch inside the one kernel it cost the sparse full pass ~7 % (194 instead of 168 registers, 12 % more
+// executed instructions, tensor pipe 73 -> 66 %: round-2 re-capture), so the full pass keeps its own code.
+template <int MODE, int CTAS, int METRIC, int KIND, bool STAGED = false>
 __global__ void __launch_bounds__(G_THREADS, 1)
 flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
     using Cfg = GemmCfg<CTAS, KIND>;
@@ -298,6 +301,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== epilogue: warps 0-3, thread = query (TMEM lane), registers = database rows =====
         uint32_t acc = 0, acc_phase = 0;
         const uint32_t lane_base = (uint32_t)warp * 32;
+        // (dead code unless STAGED: the flush lambda and the buffer pointers are only used by that instantiation)
         uint64_t* stg_key = reinterpret_cast<uint64_t*>(stg_base) + warp * G_STG_CAP;
         uint32_t* stg_own = reinterpret_cast<uint32_t*>(stg_base + 4 * G_STG_CAP * 8) + warp * G_STG_CAP;
         uint32_t stg_fill = 0;   // warp-uniform
@@ -387,7 +391,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tmem_ld_wait(va);
                 // scores of the 32 columns in v[]: 3 FMAs + one predicate-chained compare per score, a flag per group of 8
                 auto score = [&](uint32_t (&v)[32], int c0) {
-                    const bool staged = MODE == 1 && p.rare_per_score == 2;   // warp-uniform: every lane takes part
+                    constexpr bool staged = MODE == 1 && STAGED;   // every lane of the warp takes part
                     if (!qok && !staged) return;
                     const float thr = MODE == 1 ? tau : (MODE == 2 ? best[MODE == 2 ? G_TOPJ - 1 : 0] : 0.f);
                     bool none[4] = {true, true, true, true};
@@ -421,7 +425,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                             const uint64_t brow = tile_row0 + c0 + j;
                             if (brow < iv.r_end) p.out_keys[(uint64_t)q * p.nrows + brow] = make_key(__uint_as_float(v[j]), (uint32_t)brow);
                         }
-                    } else if (staged) {
+                    } else if constexpr (staged) {
                         const bool mine = qok && !(none[0] && none[1] && none[2] && none[3]);
                         if (__any_sync(0xffffffffu, mine)) {
                             uint32_t pass = 0;
@@ -556,7 +560,7 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         bidx[i] == 0xffffffffu ? KEY_NONE : make_key(best[i], bidx[i]);
             }
         }
-        if (MODE == 1 && stg_fill) stg_flush();
+        if (MODE == 1 && STAGED && stg_fill) stg_flush();
     }
     tc_fence_before();
     __syncthreads();
@@ -840,18 +844,19 @@ static int gemm_ctas() {
     return v == 1 ? 1 : 2;
 }
 
-template <int MODE, int CTAS, int METRIC, int KIND>
+template <int MODE, int CTAS, int METRIC, int KIND, bool STAGED = false>
 static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p, cudaStream_t st, const char* prof_name) {
     using Cfg = GemmCfg<CTAS, KIND>;
-    auto kern = flat_gemm_kernel<MODE, CTAS, METRIC, KIND>;
+    auto kern = flat_gemm_kernel<MODE, CTAS, METRIC, KIND, STAGED>;
     static std::atomic<size_t> configured[VDB_MAX_DEVICES];
-    ensure_dyn_smem(kern, Cfg::SMEM, configured);
+    constexpr uint32_t SMEM = STAGED ? Cfg::SMEM_STAGED : Cfg::SMEM;
+    ensure_dyn_smem(kern, SMEM, configured);
     const uint32_t sms = (uint32_t)sm_count();
     const uint32_t units = std::min(sms / CTAS, p.items ? p.nitems : p.nqt * p.nslabs);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units * CTAS);
     cfg.blockDim = dim3(G_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -868,15 +873,15 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
     VDB_LAUNCHED();
 }
 
-template <int MODE, int CTAS>
+template <int MODE, int CTAS, bool STAGED = false>
 static void launch_gemm_mk(int metric, int kind, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st,
                            const char* prof_name) {
     if (metric == VDB_COSINE) {
-        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_F16>(mq, mx, p, st, prof_name);
-        else launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_TF32>(mq, mx, p, st, prof_name);
+        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_F16, STAGED>(mq, mx, p, st, prof_name);
+        else launch_gemm_t<MODE, CTAS, VDB_COSINE, KIND_TF32, STAGED>(mq, mx, p, st, prof_name);
     } else {
-        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_F16>(mq, mx, p, st, prof_name);
-        else launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_TF32>(mq, mx, p, st, prof_name);
+        if (kind == KIND_F16) launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_F16, STAGED>(mq, mx, p, st, prof_name);
+        else launch_gemm_t<MODE, CTAS, VDB_L2SQR, KIND_TF32, STAGED>(mq, mx, p, st, prof_name);
     }
 }
 
@@ -884,6 +889,11 @@ static void launch_gemm_mk(int metric, int kind, const CUtensorMap& mq, const CU
 static void launch_gemm(int mode, int metric, int kind, const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p,
                         cudaStream_t st, int ctas = 0, const char* prof_name = "flat_gemm") {
     const bool pair = (ctas ? ctas : gemm_ctas()) == 2;
+    if (mode == 1 && p.rare_per_score == 2) {   // filter with staged candidate slots (its own instantiation)
+        if (pair) launch_gemm_mk<1, 2, true>(metric, kind, mq, mx, p, st, prof_name);
+        else launch_gemm_mk<1, 1, true>(metric, kind, mq, mx, p, st, prof_name);
+        return;
+    }
     switch (mode * 2 + (pair ? 1 : 0)) {
         case 0: launch_gemm_mk<0, 1>(metric, kind, mq, mx, p, st, prof_name); break;
         case 1: launch_gemm_mk<0, 2>(metric, kind, mq, mx, p, st, prof_name); break;
