@@ -118,6 +118,21 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def wait_ready(self, timeout=5.0):
+        """Blocks until the first sample is out: nvidia-smi's start-up (NVML initialisation, ~0.3 s) can stall the CUDA
+        driver calls of this process for tens of milliseconds and must not overlap the timed steps (seen once as a 85 ms
+        gap in a 1-step run)."""
+        if self.p is None:
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout and self.p.poll() is None:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
@@ -396,6 +411,7 @@ def run_ours_multi(args):
     prof = {}
     if rank == 0:
         sampler = ClockSampler(0)
+        sampler.wait_ready()
         for _ in range(args.warmup):
             dev_call()
         sync_all()
@@ -604,6 +620,8 @@ def run_ours(args):
     # ---- device-resident timing (value) -----------------------------------------------------------
     res = None
     sampler = ClockSampler(local) if rank == 0 else None  # started early: nvidia-smi needs ~0.3 s to emit samples
+    if sampler:
+        sampler.wait_ready()
     for _ in range(args.warmup):
         res = idx.knn_batch_dev(q_dev, args.k)
     barrier()
