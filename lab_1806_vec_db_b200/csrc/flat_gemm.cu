@@ -501,7 +501,43 @@ flat_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                 }
                             }
                         }
-                    } else if (!(none[0] && none[1] && none[2] && none[3])) {
+                    } else if (MODE == 2 && !(none[0] && none[1] && none[2] && none[3])) {
+                        // Top-G_TOPJ epilogue: the flagged scores go to this thread's private row of a shared-memory scratch and
+                        // are inserted from there in column order. Walking the 32 columns in unrolled code made the WARP pay an
+                        // insertion chain for every column in which ANY lane had a new best (nearly every row of a tile's first
+                        // slabs); the per-thread loop makes it pay max-over-lanes(insertions) chains per chunk instead.
+                        float* row = reinterpret_cast<float*>(stg_base) + threadIdx.x * 33;
+                        const float last = best[MODE == 2 ? G_TOPJ - 1 : 0];
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (none[g]) continue;
+#pragma unroll
+                            for (int j = g * 8; j < g * 8 + 8; ++j) {
+                                const float sc = __uint_as_float(v[j]);
+                                row[j] = sc;
+                                mask |= (sc < last ? 1u : 0u) << j;
+                            }
+                        }
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float sc = row[j];
+                            if (sc < best[MODE == 2 ? G_TOPJ - 1 : 0]) {  // bubble (sc, row) into place
+                                // (measured: computing the rank with 16 independent compares and rewriting the slots
+                                // independently executes ~50 % more instructions and is 15-20 % SLOWER than this chain)
+                                float w = sc;
+                                uint32_t wi = (uint32_t)(tile_row0 + c0 + j);
+#pragma unroll
+                                for (int i = 0; i < (MODE == 2 ? G_TOPJ : 1); ++i) {
+                                    const bool lt = w < best[i];
+                                    const float lo = lt ? w : best[i], hi = lt ? best[i] : w;
+                                    const uint32_t loi = lt ? wi : bidx[i], hii = lt ? bidx[i] : wi;
+                                    best[i] = lo, bidx[i] = loi, w = hi, wi = hii;
+                                }
+                            }
+                        }
+                    } else if (MODE != 2 && !(none[0] && none[1] && none[2] && none[3])) {
                         // rare path: only the groups of 8 in which this thread saw a passing (or NaN) score are walked again
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -849,7 +885,8 @@ static void launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, GemmPara
     using Cfg = GemmCfg<CTAS, KIND>;
     auto kern = flat_gemm_kernel<MODE, CTAS, METRIC, KIND, STAGED>;
     static std::atomic<size_t> configured[VDB_MAX_DEVICES];
-    constexpr uint32_t SMEM = STAGED ? Cfg::SMEM_STAGED : Cfg::SMEM;
+    // + the staging buffers (STAGED filter) or the top-G_TOPJ epilogue's per-thread score rows (mode 2: 128 x 33 floats)
+    constexpr uint32_t SMEM = (STAGED ? Cfg::SMEM_STAGED : Cfg::SMEM) + (MODE == 2 ? 128 * 33 * 4 : 0);
     ensure_dyn_smem(kern, SMEM, configured);
     const uint32_t sms = (uint32_t)sm_count();
     const uint32_t units = std::min(sms / CTAS, p.items ? p.nitems : p.nqt * p.nslabs);
