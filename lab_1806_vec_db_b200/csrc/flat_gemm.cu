@@ -1570,8 +1570,13 @@ void tensor_sample_keys(vdb_tq* tq, uint32_t j, uint64_t* d_jkeys, float* d_tau,
     // with fewer than j survivors (or an overflowed list) only gets a looser tau: the completeness check of the search
     // decides, as always.
     // Batches of <= 128 queries (single CTAs, HBM-bound on the operand rows) keep the one-launch register epilogue.
+    // End of round 2: with the per-thread insertion loop of the top-G_TOPJ epilogue (mode 2) ONE launch over the whole sample
+    // beats the two levels whenever j fits the registers (10k queries x 33k sampled rows: 0.87 + 0.22 ms against 1.11 + 0.35
+    // for gemms + merges; a 125k-row shard 0.33 against 0.46 ms per sample phase), so the two levels are now only the way
+    // to handle j > G_TOPJ (k beyond ~200). VDB_GEMM_SAMPLE_2L=1 forces them as before, =0 forbids them.
     const char* two_level_s = getenv("VDB_GEMM_SAMPLE_2L");   // read per call: the tests toggle it in one process
-    const bool two_level = !(two_level_s && !atoi(two_level_s));
+    const bool two_level_forced = two_level_s && atoi(two_level_s);
+    const bool two_level = two_level_s ? two_level_forced : j > (uint32_t)G_TOPJ;
     static const uint32_t sub_env = getenv("VDB_GEMM_SAMPLE_SUBN") ? (uint32_t)atoi(getenv("VDB_GEMM_SAMPLE_SUBN")) : 0;
     const uint32_t SUB = (uint32_t)std::max<uint64_t>(2, ns / (sub_env ? sub_env : 1024));   // sub-sample of ~1024 rows
     if (two_level && ns >= 2048 && (tq->ctas == 2 || j > (uint32_t)G_TOPJ)) {

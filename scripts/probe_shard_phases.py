@@ -17,7 +17,7 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 nn, ns, mn = C.c_uint64(0), C.c_uint32(0), C.c_float(0)
 me = C.c_float(0)
 L.check(lib.vdb_tq_info(vs._h, C.byref(nn), C.byref(ns), C.byref(mn), C.byref(me)))
-j0 = int(os.environ.get("J0", 0)) or int(lib.vdb_tq_j0(k, ns.value, nn.value)); j = j0  # J0=2 on a 125k shard ~ the global threshold of an 8-way split
+j0 = int(os.environ.get("J0", 0)) or int(lib.vdb_tq_j0(k, ns.value, nn.value)); j = int(os.environ.get("J", 0)) or j0  # J0=2 on a 125k shard ~ the global threshold of an 8-way split
 print("n", nn.value, "sample", ns.value, "j0", j0)
 names = ["begin", "sample", "tau", "filter", "check", "decode"]
 def once(record):

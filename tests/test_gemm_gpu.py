@@ -327,7 +327,7 @@ def test_round2_stages_do_not_change_a_bit(oracle, metric, monkeypatch):
         scan = idx.knn_batch(q, k)
         L.check(lib.vdb_flat_set_path(2))
         runs = {}
-        for name, env in (("default", {}), ("no_prune", {"VDB_GEMM_PRUNE": "0"}), ("one_level", {"VDB_GEMM_SAMPLE_2L": "0"}),
+        for name, env in (("default", {}), ("no_prune", {"VDB_GEMM_PRUNE": "0"}), ("one_level", {"VDB_GEMM_SAMPLE_2L": "0"}), ("two_level", {"VDB_GEMM_SAMPLE_2L": "1"}),
                           ("rare_mask", {"VDB_GEMM_RARE_PER_SCORE": "0"}), ("rare_per_score", {"VDB_GEMM_RARE_PER_SCORE": "1"}),
                           ("rare_staged", {"VDB_GEMM_RARE_PER_SCORE": "2"}),
                           ("parts3", {"VDB_GEMM_PARTS": "3"})):
