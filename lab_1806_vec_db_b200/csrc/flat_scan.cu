@@ -468,6 +468,10 @@ void launch_merge_keys(const uint64_t* d_keys, uint32_t nlists, uint32_t nq, uin
     // per query instead of eight - four times as many queries resident per SM and nearly free barriers
     uint32_t threads = MERGE_THREADS;
     if (total_max + k <= 1024) threads = P <= 128 ? 32u : (P <= 256 ? 64u : (P <= 512 ? 128u : 256u));
+    // counted lists (the tensor path's final selection: ~1.3 k live keys of a cap-sized list per query): the sort is over
+    // <= 256 slots for k <= 128, so 4 warps do it as fast as 8 and twice as many queries are resident (a shorter period
+    // than the limit assumes is always safe)
+    else if (d_seg_cnt && k <= 128) threads = 128;
     ProfScope prof("merge", stream);
     merge_keys_kernel<<<nq, threads, smem, stream>>>(d_keys, nlists, nq, len, list_major ? 1 : 0, d_seg_off, d_seg_cnt,
                                                            k, P, limit, d_out_keys, d_ids,
