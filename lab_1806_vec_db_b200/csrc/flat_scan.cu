@@ -47,6 +47,73 @@ struct ScanParams {
     uint32_t* out_counts;
 };
 
+// Tail of a single-launch batch, run by the last CTA to finish: merge of the gridDim.x per-CTA lists of every query + decode.
+// Kept out of line: inlined into the scan kernel it perturbed the register allocation of the main loop (the 4-query f32
+// variant, 128 registers with three load buffers, went from 0.75 to 0.85 ms per pass).
+struct ScanTailArgs {   // by value: a reference to the kernel's parameter block would force a copy of it onto the stack
+    const uint64_t* partial;
+    uint32_t nq_valid, K, P, limit;
+    uint64_t* out_keys;
+    uint64_t* out_ids;
+    float* out_dist;
+    uint32_t* out_counts;
+};
+static __device__ __noinline__ void scan_tail(const ScanTailArgs p, TopkSmem topk, uint32_t* s_valid) {
+    __threadfence();
+    topk.init();
+    // Every per-CTA list is ascending, so the smallest of their K-th keys bounds the K-th key of the union: only keys up
+    // to it are pushed (a few more than K instead of gridDim.x * K), and the keys of a batch are loaded before any of them
+    // is tested - the L2 round trips of the tail overlap instead of lining up one per round.
+    __shared__ unsigned long long s_bound[8];
+    if (threadIdx.x < 8) s_bound[threadIdx.x] = KEY_NONE;
+    __syncthreads();
+    const uint32_t total = gridDim.x * p.K;
+    for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
+        unsigned long long b = KEY_NONE;
+        for (uint32_t l = threadIdx.x; l < gridDim.x; l += blockDim.x)
+            b = min(b, (unsigned long long)__ldcg(p.partial + (size_t)qi * total + (size_t)l * p.K + (p.K - 1)));   // other SMs wrote it: bypass L1
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, d));
+        if ((threadIdx.x & 31) == 0 && b != KEY_NONE) atomicMin(&s_bound[qi], b);   // 64-bit shared atomics are CAS loops: one per warp
+    }
+    __syncthreads();
+    // at most `period` appends per segment between two flush tests (the contract of TopkSmem::push)
+    const uint32_t period = min((uint32_t)blockDim.x, p.P - p.K - p.limit);
+    constexpr int TAIL_U = 8;
+    for (uint32_t base = 0; base < total; base += TAIL_U * period) {
+        for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
+            const uint64_t bound = s_bound[qi];
+            uint64_t kk[TAIL_U];
+#pragma unroll
+            for (int u = 0; u < TAIL_U; ++u) {
+                const uint32_t i = base + u * period + threadIdx.x;
+                kk[u] = (threadIdx.x < period && i < total) ? __ldcg(p.partial + (size_t)qi * total + i) : KEY_NONE;
+            }
+#pragma unroll
+            for (int u = 0; u < TAIL_U; ++u) {
+                if (base + u * period >= total) break;   // CTA-uniform
+                bool want = false;
+                if (kk[u] <= bound && kk[u] < topk.tau(qi)) want = topk.push(qi, kk[u]);
+                topk.maybe_flush(want);
+            }
+        }
+    }
+    topk.final_flush();
+    for (uint32_t i = threadIdx.x; i < p.nq_valid * p.K; i += blockDim.x) {
+        const uint32_t qi = i / p.K;
+        const uint64_t key = topk.seg(qi)[i - qi * p.K];
+        const bool ok = key != KEY_NONE;
+        p.out_keys[i] = key;
+        if (p.out_ids) {
+            p.out_ids[i] = ok ? (uint64_t)key_id(key) : KEY_NONE;
+            p.out_dist[i] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+        }
+        if (ok) atomicAdd(&s_valid[qi], 1u);
+    }
+    __syncthreads();
+    if (p.out_counts && threadIdx.x < p.nq_valid) p.out_counts[threadIdx.x] = s_valid[threadIdx.x];
+}
+
 // PL = 1: f32 rows (4 elements per 16-byte load); PL = 4: u8 rows (16 elements per load)
 template <int NQ, int R, int METRIC, int PL>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanParams p) {
@@ -291,59 +358,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) flat_scan_kernel(const ScanPa
     if (threadIdx.x < 8) s_valid[threadIdx.x] = 0;
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
-    topk.init();
-    // Every per-CTA list is ascending, so the smallest of their K-th keys bounds the K-th key of the union: only keys up
-    // to it are pushed (a few more than K instead of gridDim.x * K), and the keys of a batch are loaded before any of them
-    // is tested - the L2 round trips of the tail overlap instead of lining up one per round.
-    __shared__ unsigned long long s_bound[8];
-    if (threadIdx.x < 8) s_bound[threadIdx.x] = KEY_NONE;
-    __syncthreads();
-    const uint32_t total = gridDim.x * p.K;
-    for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
-        unsigned long long b = KEY_NONE;
-        for (uint32_t l = threadIdx.x; l < gridDim.x; l += blockDim.x)
-            b = min(b, (unsigned long long)__ldcg(p.partial + (size_t)qi * total + (size_t)l * p.K + (p.K - 1)));   // other SMs wrote it: bypass L1
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, d));
-        if ((threadIdx.x & 31) == 0 && b != KEY_NONE) atomicMin(&s_bound[qi], b);   // 64-bit shared atomics are CAS loops: one per warp
-    }
-    __syncthreads();
-    // at most `period` appends per segment between two flush tests (the contract of TopkSmem::push)
-    const uint32_t period = min((uint32_t)blockDim.x, p.P - p.K - p.limit);
-    constexpr int TAIL_U = 8;
-    for (uint32_t base = 0; base < total; base += TAIL_U * period) {
-        for (uint32_t qi = 0; qi < p.nq_valid; ++qi) {
-            const uint64_t bound = s_bound[qi];
-            uint64_t kk[TAIL_U];
-#pragma unroll
-            for (int u = 0; u < TAIL_U; ++u) {
-                const uint32_t i = base + u * period + threadIdx.x;
-                kk[u] = (threadIdx.x < period && i < total) ? __ldcg(p.partial + (size_t)qi * total + i) : KEY_NONE;
-            }
-#pragma unroll
-            for (int u = 0; u < TAIL_U; ++u) {
-                if (base + u * period >= total) break;   // CTA-uniform
-                bool want = false;
-                if (kk[u] <= bound && kk[u] < topk.tau(qi)) want = topk.push(qi, kk[u]);
-                topk.maybe_flush(want);
-            }
-        }
-    }
-    topk.final_flush();
-    for (uint32_t i = threadIdx.x; i < p.nq_valid * p.K; i += blockDim.x) {
-        const uint32_t qi = i / p.K;
-        const uint64_t key = topk.seg(qi)[i - qi * p.K];
-        const bool ok = key != KEY_NONE;
-        p.out_keys[i] = key;
-        if (p.out_ids) {
-            p.out_ids[i] = ok ? (uint64_t)key_id(key) : KEY_NONE;
-            p.out_dist[i] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
-        }
-        if (ok) atomicAdd(&s_valid[qi], 1u);
-    }
-    __syncthreads();
-    if (p.out_counts && threadIdx.x < p.nq_valid) p.out_counts[threadIdx.x] = s_valid[threadIdx.x];
+    scan_tail(ScanTailArgs{p.partial, p.nq_valid, p.K, p.P, p.limit, p.out_keys, p.out_ids, p.out_dist, p.out_counts}, topk, s_valid);
 }
 
 // ---- merge of key lists ------------------------------------------------------------------------
