@@ -432,7 +432,7 @@ def run_ours_multi(args):
         launches = int(lib.vdb_launch_count() - launches0)
         L.check(lib.vdb_prof_enable(0))
         clocks = sampler.stop()
-        for name in ("flat_scan", "flat_gemm", "flat_gemm_sample", "rerank", "merge", "mg_queries", "mg_sample", "mg_bcast", "mg_filter", "mg_scatter", "mg_merge"):
+        for name in ("flat_scan", "flat_gemm", "flat_gemm_sample", "rerank", "merge", "mg_queries", "mg_sample", "mg_bcast", "mg_filter", "mg_finish", "mg_scatter", "mg_merge"):
             t, c = C.c_double(0), C.c_uint64(0)
             L.check(lib.vdb_prof_read(name.encode(), C.byref(t), C.byref(c)))
             prof[name] = (t.value, int(c.value))

@@ -1113,13 +1113,64 @@ __global__ void cand_sortable_kernel(uint64_t* __restrict__ cand, const uint32_t
 // S' > U_(k) can be among the k best: it is dropped BEFORE the exact rerank (HBM gathers of whole rows). One CTA per
 // query: U of every candidate -> radix select of U_(k) in shared memory -> in-place compaction. Lists of <= k entries and
 // NaN scores (non-finite rows; the rerank decides) are kept whole.
+// order bits of the upper bound U of a candidate's shifted distance (see above); rows that must be kept whatever their
+// score (NaN / -inf: cosine rows under the reference's norm clamp) get the largest value: no upper bound
+template <int METRIC>
+__device__ __forceinline__ uint32_t cand_upper_bits(uint64_t e, float a, float b, float shift, const float* __restrict__ rnorm,
+                                                    const float* __restrict__ ex) {
+    const uint32_t row = (uint32_t)e;
+    const float sp = __uint_as_float((uint32_t)(e >> 32));
+    const float bound = METRIC == VDB_L2SQR ? fmaf(a, ex[row], b * rnorm[row]) : (1.0f - b) + a * ex[row];
+    float up = sp + 2.0002f * bound;
+    up += 2e-5f * (fabsf(up) + shift) + 1e-30f;
+    return fabsf(sp) <= 3.0e38f ? f32_order_bits(up) : 0xffffffffu;
+}
+// Row-sharded search, first half of the global pruning: per query the upper bounds of ranks m, 2m, ..., T m of this shard's
+// candidate list, ascending (order bits; 0xffffffff where the list is shorter, and everywhere for lists too long to sort
+// here - they only weaken the bound). One CTA per query, bitonic sort of the list's U in shared memory.
+constexpr uint32_t PRUNE_SORT_MAX = 2048;
+template <int METRIC>
+__global__ void __launch_bounds__(256) prune_stats_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+                                                          uint32_t cap, uint32_t m, uint32_t T, const float* __restrict__ rnorm,
+                                                          const float* __restrict__ ex, const float* __restrict__ qab,
+                                                          const float* __restrict__ qb, const float* __restrict__ qsq,
+                                                          uint32_t* __restrict__ stats) {
+    __shared__ uint32_t u[PRUNE_SORT_MAX];
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const uint32_t c = min(cnt[q], cap);
+    uint32_t* out = stats + (size_t)q * T;
+    if (c > PRUNE_SORT_MAX || c == 0) {
+        for (uint32_t i = tid; i < T; i += blockDim.x) out[i] = 0xffffffffu;
+        return;
+    }
+    const uint32_t n = c <= 32 ? 32u : (1u << (32 - __clz(c - 1)));
+    const uint64_t* list = cand + (uint64_t)q * cap;
+    const float a = qab[q], b = qb[q], shift = qsq ? qsq[q] : 0.f;
+    for (uint32_t j = tid; j < n; j += blockDim.x) u[j] = j < c ? cand_upper_bits<METRIC>(list[j], a, b, shift, rnorm, ex) : 0xffffffffu;
+    __syncthreads();
+    for (uint32_t size = 2; size <= n; size <<= 1)
+        for (uint32_t st = size >> 1; st > 0; st >>= 1) {
+            for (uint32_t t = tid; t < (n >> 1); t += blockDim.x) {
+                const uint32_t i = ((t & ~(st - 1)) << 1) | (t & (st - 1)), l = i | st;
+                const uint32_t x = u[i], y = u[l];
+                if ((x > y) == ((i & size) == 0)) u[i] = y, u[l] = x;
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = tid; i < T; i += blockDim.x) {
+        const uint32_t r = (i + 1) * m - 1;
+        out[i] = r < c ? u[r] : 0xffffffffu;
+    }
+}
 template <int METRIC>
 __global__ void __launch_bounds__(256) cand_prune_kernel(uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap,
                                                          uint32_t k, const float* __restrict__ rnorm, const float* __restrict__ ex,
                                                          const float* __restrict__ qab, const float* __restrict__ qb,
                                                          const float* __restrict__ qsq, uint32_t* __restrict__ cnt_out,
                                                          uint64_t* __restrict__ off, unsigned long long* __restrict__ pair_total,
-                                                         uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid) {
+                                                         uint32_t* __restrict__ qidx, uint32_t* __restrict__ rid,
+                                                         const uint32_t* __restrict__ gstats, uint32_t gshards, uint32_t gT,
+                                                         uint32_t gnq) {
     extern __shared__ uint32_t prune_u[];   // [min(cnt, cap)] order bits of U
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_bin, s_k, s_warp[8], s_base;
@@ -1143,22 +1194,40 @@ __global__ void __launch_bounds__(256) cand_prune_kernel(uint64_t* __restrict__ 
             rid[o + j] = (uint32_t)list[j];
         }
     };
-    if (c <= k) {
+    if (c <= k && !gstats) {
         if (tid == 0) cnt_out[q] = c;
         emit_pairs(c);
         return;
     }
+    uint32_t thr;
+    if (gstats) {
+        // Row-sharded search: every shard sent the upper bounds U of ranks m, 2m, ..., T m of ITS list (order bits, ascending,
+        // padded with the largest value; prune_stats_kernel). The i-th entry of a shard's row certifies (i + 1) m rows with
+        // d - shift <= that value, so the T-th smallest of all G T entries certifies >= T m >= k rows of the WHOLE set: no row
+        // with S' above it can be among the k best - the local list is cut against the global bound, not the shard's own.
+        const uint32_t GT = gshards * gT;
+        for (uint32_t i = tid; i < GT; i += blockDim.x) {
+            const uint32_t sh = i / gT, t = i - sh * gT;
+            prune_u[i] = gstats[((size_t)sh * gnq + q) * gT + t];
+        }
+        __syncthreads();
+        if (tid == 0) s_bin = 0xffffffffu;
+        __syncthreads();
+        for (uint32_t i = tid; i < GT; i += blockDim.x) {
+            const uint32_t v = prune_u[i];
+            uint32_t r = 0;
+            for (uint32_t j = 0; j < GT; ++j) {
+                const uint32_t w = prune_u[j];
+                r += (w < v || (w == v && j < i)) ? 1u : 0u;
+            }
+            if (r == gT - 1) s_bin = v;   // exactly one entry has this rank
+        }
+        __syncthreads();
+        thr = s_bin;
+        __syncthreads();
+    } else {
     const float a = qab[q], b = qb[q], shift = qsq ? qsq[q] : 0.f;
-    for (uint32_t j = tid; j < c; j += blockDim.x) {
-        const uint64_t e = list[j];
-        const uint32_t row = (uint32_t)e;
-        const float sp = __uint_as_float((uint32_t)(e >> 32));
-        const float bound = METRIC == VDB_L2SQR ? fmaf(a, ex[row], b * rnorm[row]) : (1.0f - b) + a * ex[row];
-        float up = sp + 2.0002f * bound;
-        up += 2e-5f * (fabsf(up) + shift) + 1e-30f;
-        // -inf marks a row that must be kept whatever its score (cosine: under the reference's norm clamp): no upper bound
-        prune_u[j] = fabsf(sp) <= 3.0e38f ? f32_order_bits(up) : 0xffffffffu;
-    }
+    for (uint32_t j = tid; j < c; j += blockDim.x) prune_u[j] = cand_upper_bits<METRIC>(list[j], a, b, shift, rnorm, ex);
     // radix select: the k-th smallest (1-based) of prune_u[0, c), 8 bits per pass from the top
     uint32_t prefix = 0, mask = 0, kk = k;
     for (int sh = 24; sh >= 0; sh -= 8) {
@@ -1195,7 +1264,8 @@ __global__ void __launch_bounds__(256) cand_prune_kernel(uint64_t* __restrict__ 
         kk = s_k;
         __syncthreads();
     }
-    const uint32_t thr = prefix;
+    thr = prefix;
+    }
     // stable in-place compaction (a chunk is read completely before anything is written at or below it)
     if (tid == 0) s_base = 0;
     __syncthreads();
@@ -1435,6 +1505,11 @@ struct vdb_tq {
     CUtensorMap mq;
     uint32_t cap = 0;
     int ctas = 2;   // CTAs per work unit: pairs (M = 256 queries), single CTAs (M = 128) for batches of <= 128 queries
+    // row-sharded search with the global pruning bound: the filter is split around one peer exchange
+    // (tensor_filter_begin / tensor_filter_finish); these live from the one to the other
+    vdb::DevBuf f_cand, f_stats;
+    uint32_t f_k = 0, f_m = 0, f_T = 0;
+    const float* f_tau = nullptr;
 };
 
 namespace vdb {
@@ -1804,7 +1879,7 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
             kern<<<nq, 256, sm, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, k, ds->d_lo, ds->d_ex, tq->qab.as<float>(),
                                       tq->qb.as<float>(), ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(), snap,
                                       off.as<uint64_t>(), reinterpret_cast<unsigned long long*>(tq_pairs_ptr(tq)),
-                                      qidx.as<uint32_t>(), rid.as<uint32_t>());
+                                      qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, 0u, 0u, 0u);
             VDB_LAUNCHED();
         } else {
             VDB_CUDA(cudaMemcpyAsync(snap, tq->cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToDevice, st));
@@ -1854,6 +1929,94 @@ void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const fl
         fin.nredo = tensor_nredo_ptr(tq);
     }
     launch_merge_keys(cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr, final_cnt, &fin);
+}
+
+// ---- the filter, split around ONE peer exchange (row-sharded search) -----------------------------------------------------
+// A shard can only prune its candidate list against ITS k-th upper bound, and holds fewer than k candidates per query once
+// the set is split 4 or 8 ways: nothing is pruned and the shards together gather ~4x the rows the unsharded call gathers
+// (8 x B200, 10k queries, k = 100: 533 rows per query against 129). tensor_filter_begin runs the contraction and leaves T
+// order statistics of the list's upper bounds per query (ranks m, 2m, ..., T m >= k; prune_stats_kernel); the caller makes
+// every shard's [nq][T] block visible to every shard; tensor_filter_finish cuts the list against the bound they certify
+// together (cand_prune_kernel, gstats branch) and reranks what is left. Results are the bits of the unsplit call: only rows
+// that provably are not among the k best of the WHOLE set are dropped.
+constexpr uint32_t GPRUNE_M = 4;
+bool tensor_filter_split_supported(const vdb_tq* tq, uint32_t k) {
+    const char* e = getenv("VDB_MG_GLOBAL_PRUNE");   // read per call: the tests toggle it in one process
+    if (e && !atoi(e)) return false;
+    const char* parts_s = getenv("VDB_GEMM_PARTS");
+    const char* prune_s = getenv("VDB_GEMM_PRUNE");
+    if ((parts_s && atoi(parts_s) > 1) || (prune_s && !atoi(prune_s))) return false;
+    return k >= 1 && k <= 256 && tq->nq > 0;
+}
+const uint32_t* tensor_filter_begin(vdb_tq* tq, uint32_t k, const float* d_tau, uint32_t* T_out) {
+    const vdb_dataset* ds = tq->ds;
+    cudaStream_t st = tq->st;
+    const uint32_t nq = tq->nq;
+    const uint32_t cap = (uint32_t)next_pow2((uint32_t)std::min<uint64_t>(ds->n, 8192));   // as tensor_filter_keys with hint 0
+    tq->cap = cap;
+    tq->f_k = k;
+    tq->f_m = GPRUNE_M;
+    tq->f_T = ceil_div(k, GPRUNE_M);
+    tq->f_tau = d_tau;
+    tq->f_cand = DevBuf((size_t)nq * cap * 8, st);
+    tq->f_stats = DevBuf((size_t)nq * tq->f_T * 4, st);
+    VDB_CUDA(cudaMemsetAsync(tq->cnt.p, 0, tq_cnt_bytes(nq), st));
+    const CUtensorMap mx = make_op_map(tq->kind, op_rows_of(ds), ds->dim, ds->n, op_row_bytes_of(ds), GN / tq->ctas);
+    GemmParams pf = base_params(tq);
+    pf.sqnorm = ds->d_sqnorm;
+    pf.rnorm = ds->d_lo;
+    pf.ex = ds->d_ex;
+    pf.nrows = ds->n;
+    pf.row_stride = 1;
+    pf.tau = d_tau;
+    pf.cand_cnt = tq->cnt.as<uint32_t>();
+    pf.cand = tq->f_cand.as<uint64_t>();
+    pf.cap = cap;
+    plan_gemm(pf, tq->ctas);
+    launch_gemm(1, ds->metric, tq->kind, tq->mq, mx, pf, st, tq->ctas);
+    auto kern = ds->metric == VDB_COSINE ? prune_stats_kernel<VDB_COSINE> : prune_stats_kernel<VDB_L2SQR>;
+    kern<<<nq, 256, 0, st>>>(tq->f_cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, tq->f_m, tq->f_T, ds->d_lo, ds->d_ex,
+                             tq->qab.as<float>(), tq->qb.as<float>(), ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(),
+                             tq->f_stats.as<uint32_t>());
+    VDB_LAUNCHED();
+    *T_out = tq->f_T;
+    return tq->f_stats.as<uint32_t>();
+}
+// d_stats_all: [shards][nq][T] (every shard's block, this one's included)
+void tensor_filter_finish(vdb_tq* tq, const uint32_t* d_stats_all, uint32_t shards, uint64_t* d_keys, uint32_t* d_overflow) {
+    const vdb_dataset* ds = tq->ds;
+    cudaStream_t st = tq->st;
+    const uint32_t nq = tq->nq, cap = tq->cap, k = tq->f_k;
+    VDB_REQUIRE(tq->f_cand.p && shards >= 1 && (size_t)shards * tq->f_T * 4 <= (size_t)cap * 4, "tensor_filter_finish without begin");
+    const uint64_t total = (uint64_t)nq * cap;
+    DevBuf snap((size_t)nq * 4, st), off((size_t)(nq + 1) * 8, st), qidx(total * 4, st), rid(total * 4, st), dist(total * 4, st);
+    {
+        auto kern = ds->metric == VDB_COSINE ? cand_prune_kernel<VDB_COSINE> : cand_prune_kernel<VDB_L2SQR>;
+        const size_t sm = (size_t)cap * 4;
+        if (sm > 48 * 1024) VDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        kern<<<nq, 256, sm, st>>>(tq->f_cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, k, ds->d_lo, ds->d_ex, tq->qab.as<float>(),
+                                  tq->qb.as<float>(), ds->metric == VDB_COSINE ? nullptr : tq->qsq.as<float>(), snap.as<uint32_t>(),
+                                  off.as<uint64_t>(), reinterpret_cast<unsigned long long*>(tq_pairs_ptr(tq)), qidx.as<uint32_t>(),
+                                  rid.as<uint32_t>(), d_stats_all, shards, tq->f_T, nq);
+        VDB_LAUNCHED();
+    }
+    const uint64_t* n_pairs = tq_pairs_ptr(tq);
+    exact_pair_distances_masked(ds, tq->qcopy.p, tq->qpitch, qidx.as<uint32_t>(), rid.as<uint32_t>(), nullptr, total, dist.as<float>(),
+                                st, n_pairs, ds->metric == VDB_COSINE ? tq->qtile.qcache.as<float>() : nullptr);
+    part_rekey_kernel<<<(uint32_t)sm_count() * 8, 256, 0, st>>>(dist.as<float>(), qidx.as<uint32_t>(), rid.as<uint32_t>(),
+                                                               off.as<uint64_t>(), nq, nullptr, cap, (uint32_t)ds->id_base,
+                                                               tq->f_cand.as<uint64_t>(), n_pairs);
+    VDB_LAUNCHED();
+    MergeFinish fin;
+    fin.cnt_raw = tq->cnt.as<uint32_t>();
+    fin.qbad = tq->qbad.as<uint32_t>();
+    fin.cap = cap;
+    fin.overflow = d_overflow;
+    fin.cand_total = reinterpret_cast<unsigned long long*>(tensor_cand_total_ptr(tq));
+    launch_merge_keys(tq->f_cand.as<uint64_t>(), 1, nq, cap, false, k, d_keys, nullptr, nullptr, nullptr, st, nullptr,
+                      snap.as<uint32_t>(), &fin);
+    tq->f_cand = DevBuf();   // stream-ordered frees
+    tq->f_stats = DevBuf();
 }
 
 // CHECK: the (merged) result of q is provably exact iff no shard overflowed and d_k - ||q||^2 < tau_q
@@ -2370,7 +2533,7 @@ bool ivf_tensor_keys(const vdb_dataset* ds, const vdb_ivf* ivf, const void* d_qu
             auto kern = cosine ? cand_prune_kernel<VDB_COSINE> : cand_prune_kernel<VDB_L2SQR>;
             kern<<<nq, 256, (size_t)cap * 4, st>>>(cand.as<uint64_t>(), tq->cnt.as<uint32_t>(), cap, k, ivf->d_rn_lo, ivf->d_ex_lo,
                                                    tq->qab.as<float>(), tq->qb.as<float>(), cosine ? nullptr : tq->qsq.as<float>(),
-                                                   pcnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
+                                                   pcnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, 0u, 0u, 0u);
             VDB_LAUNCHED();
         }
         // ---- exact rerank (the FP32 list scan's arithmetic) and top-k ----

@@ -213,6 +213,10 @@ struct TensorCheck {
 };
 void tensor_filter_keys(vdb_tq* tq, uint32_t k, uint32_t j0_local_hint, const float* d_tau, uint64_t* d_keys,
                         uint32_t* d_overflow, const TensorCheck* check = nullptr);
+// the same filter split around one peer exchange of pruning statistics (row-sharded search, see flat_gemm.cu)
+bool tensor_filter_split_supported(const vdb_tq* tq, uint32_t k);
+const uint32_t* tensor_filter_begin(vdb_tq* tq, uint32_t k, const float* d_tau, uint32_t* T_out);   // -> [nq][T] statistics
+void tensor_filter_finish(vdb_tq* tq, const uint32_t* d_stats_all, uint32_t shards, uint64_t* d_keys, uint32_t* d_overflow);
 uint64_t* tensor_cand_total_ptr(const vdb_tq* tq);
 uint32_t* tensor_nredo_ptr(const vdb_tq* tq);
 void tensor_check(vdb_tq* tq, const uint64_t* d_keys, uint32_t k, uint64_t n_total, const float* d_tau,

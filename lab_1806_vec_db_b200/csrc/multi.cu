@@ -157,7 +157,7 @@ struct PeerBuf {
     }
 };
 
-enum { EV_Q = 0, EV_S, EV_F, EV_R, EV_COUNT };
+enum { EV_Q = 0, EV_S, EV_P, EV_F, EV_R, EV_COUNT };
 
 struct Shard {
     int device = 0;
@@ -165,7 +165,7 @@ struct Shard {
     uint64_t lo = 0, hi = 0;          // global row block
     cudaStream_t st = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
-    PeerBuf q_all, jall, kin, ovin;   // written by the peers
+    PeerBuf q_all, jall, ustat, kin, ovin;   // written by the peers
     PeerBuf out_ids, out_dist, out_cnt;   // host calls: this shard's slice of the result before the D2H
     uint32_t* h_redo = nullptr;       // pinned: [0] = count, [1..] = flagged batch indices of the owned slice
     size_t h_redo_cap = 0;
@@ -311,7 +311,7 @@ void sharded_destroy(vdb_dataset* md) {
         for (auto& sh : S->shards) {
             cudaSetDevice(sh.device);
             if (sh.st) cudaStreamSynchronize(sh.st);
-            for (PeerBuf* b : {&sh.q_all, &sh.jall, &sh.kin, &sh.ovin, &sh.out_ids, &sh.out_dist, &sh.out_cnt}) b->release();
+            for (PeerBuf* b : {&sh.q_all, &sh.jall, &sh.ustat, &sh.kin, &sh.ovin, &sh.out_ids, &sh.out_dist, &sh.out_cnt}) b->release();
             if (sh.h_redo) cudaFreeHost(sh.h_redo);
             if (sh.h_stat) cudaFreeHost(sh.h_stat);
             for (auto& e : sh.ev)
@@ -464,6 +464,7 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
             VDB_CUDA(cudaSetDevice(sh.device));
             if (host) sh.q_all.ensure((size_t)nq * rb);
             if (tensor) sh.jall.ensure((size_t)G * nq * j * 8);
+            if (tensor) sh.ustat.ensure((size_t)G * nq * ((k + 3) / 4) * 4);   // global pruning statistics (GPRUNE_M = 4)
             sh.kin.ensure((size_t)G * std::max(cnt, 1u) * k * 8);
             sh.ovin.ensure((size_t)G * std::max(cnt, 1u) * 4);
             if (host) {
@@ -544,13 +545,36 @@ static void sharded_flat_chunk(const vdb_dataset* md, const FlatCallArgs& a, int
         }
         VDB_CUDA(cudaEventRecord(sh.ev[EV_S], sh.st));
     });
+    // P2a (tensor path with the global pruning bound): thresholds + contraction + this shard's pruning statistics to every shard
+    bool gprune = false;   // decided by shard 0 in P1 (same answer on every shard: it depends on k and the environment only)
+    ph.push_back([&](uint32_t s) {
+        if (!tensor || G < 2 || !tensor_filter_split_supported(tqs[s], k)) return;
+        if (s == 0) gprune = true;
+        Shard& sh = S->shards[s];
+        Local& L = loc[s];
+        PhaseProf pp(s == 0, "mg_filter", sh.st);
+        wait_peers(S, s, EV_S);
+        L.tau = DevBuf((size_t)nq * 4, sh.st);
+        L.ovf = DevBuf((size_t)nq * 4, sh.st);
+        tensor_tau(tqs[s], (const uint64_t*)sh.jall.p, G, j, (uint32_t)std::min<uint64_t>(j0, (uint64_t)j * G), L.tau.as<float>());
+        uint32_t T = 0;
+        const uint32_t* stats = tensor_filter_begin(tqs[s], k, L.tau.as<float>(), &T);
+        PtrList dst{};
+        for (uint32_t h = 0; h < G; ++h) dst.p[h] = (uint8_t*)S->shards[h].ustat.p + (size_t)s * nq * T * 4;
+        bcast(stats, (size_t)nq * T * 4, dst, G, sh.st);
+        VDB_CUDA(cudaEventRecord(sh.ev[EV_P], sh.st));
+    });
     // P2: thresholds + filter + rerank (tensor) / exact scan; rows of the owned slices go to their owners
     ph.push_back([&](uint32_t s) {
         Shard& sh = S->shards[s];
         Local& L = loc[s];
-        PhaseProf pp(s == 0, "mg_filter", sh.st);
+        PhaseProf pp(s == 0, gprune ? "mg_finish" : "mg_filter", sh.st);
         L.keys = DevBuf((size_t)nq * k * 8, sh.st);
-        if (tensor) {
+        if (tensor && gprune) {
+            wait_peers(S, s, EV_P);
+            tensor_filter_finish(tqs[s], (const uint32_t*)sh.ustat.p, G, L.keys.as<uint64_t>(), L.ovf.as<uint32_t>());
+            VDB_CUDA(cudaMemcpyAsync(sh.h_stat, tensor_cand_total_ptr(tqs[s]), 8, cudaMemcpyDeviceToHost, sh.st));
+        } else if (tensor) {
             wait_peers(S, s, EV_S);
             L.tau = DevBuf((size_t)nq * 4, sh.st);
             L.ovf = DevBuf((size_t)nq * 4, sh.st);

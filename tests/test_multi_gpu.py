@@ -231,3 +231,42 @@ def test_sharded_ivf_and_pq_equal_the_unsharded_calls(vdb, oracle):
     assert_knn_parity(base, q[:16], "l2sqr", tuple(a[:16] for a in want_ivf[4]), oi, oracle)
     op = oracle.flat_knn_pq(base, codes, books, m, 4, q[:16], 10, 240, "l2sqr", nthreads=8)
     assert_knn_parity(base, q[:16], "l2sqr", tuple(a[:16] for a in want_pq[(10, 240)]), op, oracle)
+
+
+@pytest.mark.parametrize("metric", ["l2sqr", "cosine"])
+def test_global_pruning_bound_changes_no_bit_and_gathers_fewer_rows(vdb, metric, monkeypatch):
+    """Between the contraction and the rerank the shards exchange order statistics of their candidates' upper bounds and cut
+    their lists against the bound these certify TOGETHER (csrc/flat_gemm.cu: tensor_filter_begin / _finish). A shard alone
+    can only prune against its own k-th upper bound and holds fewer than k candidates once the set is split: with the
+    exchange the same bits come back and fewer rows reach the exact rerank."""
+    V = vdb
+    n, nq, dim, k = 400_000, 500, 128, 100
+    base, q = _data(n, nq, dim, 5)
+    V.init_devices([])
+    full = V.FlatIndex.from_vec_set(base, metric)
+    full.vec_set.set_flat_path("scan")
+    want = full.knn_batch(q, k)
+    V.init_devices([0, 0, 0, 0])
+    idx = V.FlatIndex.from_vec_set(base, metric)
+    lib = V.lib()
+
+    def cands():
+        out = [C.c_uint64(0) for _ in range(3)]
+        lib.vdb_flat_gemm_stats(*[C.byref(x) for x in out])
+        return out[1].value, out[2].value
+
+    gathered = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VDB_MG_GLOBAL_PRUNE", flag)
+        c0, f0 = cands()
+        _same(idx.knn_batch(q, k), want)
+        c1, f1 = cands()
+        gathered[flag] = c1 - c0
+        assert f1 - f0 == 0, "no query may fall back to the exact scan on this set"
+    monkeypatch.delenv("VDB_MG_GLOBAL_PRUNE")
+    assert gathered["1"] < gathered["0"], gathered
+    assert gathered["1"] >= nq * k
+    # forced re-scans go through the same phases
+    V._lib.check(lib.vdb_debug_force_redo(5))
+    _same(idx.knn_batch(q, k), want)
+    V._lib.check(lib.vdb_debug_force_redo(0))
