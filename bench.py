@@ -27,8 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DIM = 960
-GEMM_PASS_TRAFFIC = 1.954014e9 + 45.709e6  # dram__bytes_read.sum + dram__bytes_write.sum of ONE filter launch (the whole pass:
-#                                            1M x 960 FP16 operand rows, 10 000 queries), profiles/r02_flat_gemm_ncu.md
+GEMM_PASS_TRAFFIC = 1.952671e9 + 45.116e6  # dram__bytes_read.sum + dram__bytes_write.sum of ONE filter launch (the whole pass:
+#                                            1M x 960 FP16 operand rows, 10 000 queries): end-of-round re-capture of the
+#                                            shipped kernel, profiles/r02_flat_gemm_ncu.md (first capture: 1.954014e9 + 45.709e6)
 CHUNK = 50_000  # rows per generator chunk (seeded per chunk so any sharding sees the same bits)
 
 
