@@ -258,10 +258,45 @@ def _as_device_rows(rows, dist):
     return DeviceVecSet(np.ascontiguousarray(rows), dist)
 
 
+def sample_indices(rng, n, k):
+    """Row indices of VecSet::random_sample (vec_set.rs:154-163): the first k entries of the shuffled index vector. A
+    `rand_compat.StdRng` follows the reference's Fisher-Yates draws, a numpy Generator its own permutation."""
+    from .rand_compat import StdRng
+    if isinstance(rng, StdRng):
+        return rng.shuffle(n)[:k]
+    return rng.permutation(n)[:k]
+
+
+def k_means_init_reference_stream(rows_host, config: KMeansConfig, rng):
+    """k-means++ (k_means.rs:61-87) under the reference's OWN random stream (`rand_compat.StdRng`: rand 0.8.5 restated,
+    parity with the crate unpinned - see that module): gen_range for the first pick, per round the f32 WeightedIndex over
+    the weights the GPU updates (`vdb_kmeans_pp_weights`: w[i] = min(w[i], d(c, v_i)) with the reference's sequential f32
+    distance) and the eagerly drawn fallback. Rows stay on the host (the weights call stages them)."""
+    from .rand_compat import k_means_init_indices
+    rows = np.ascontiguousarray(rows_host)
+    n, dim = rows.shape
+    lo, hi = config.selected if config.selected is not None else (0, dim)
+    w = np.full(n, np.inf, np.float32)
+
+    def update(idx):
+        c = np.ascontiguousarray(rows[idx, lo:hi])
+        L.check(L.lib().vdb_kmeans_pp_weights(L.ptr(rows), n, dim, L.dtype_code(rows), L.metric_code(config.dist), L.ptr(c),
+                                              lo, hi, L.ptr(w)))
+        return w
+
+    chosen = k_means_init_indices(update, n, config.k, rng)
+    return np.ascontiguousarray(rows[chosen, lo:hi])
+
+
 def k_means_init(rows, config: KMeansConfig, rng):
-    """k-means++ (k_means.rs:61-87). The draws consume the CALLER's rng (numpy Generator here; the reference's
-    ChaCha12 stream cannot be reproduced): 2k-1 uniforms drive the first pick, the weighted picks and the eagerly
-    drawn fallbacks; the weight updates run on the GPU over device-resident rows."""
+    """k-means++ (k_means.rs:61-87). The draws consume the CALLER's rng: with a numpy Generator 2k-1 uniforms drive the
+    first pick, the weighted picks and the eagerly drawn fallbacks and everything runs on the GPU over device-resident
+    rows; with a `rand_compat.StdRng` the reference's draw sequence is followed (k_means_init_reference_stream)."""
+    from .rand_compat import StdRng
+    if isinstance(rng, StdRng):
+        if isinstance(rows, DeviceVecSet):
+            raise TypeError("the reference-stream k-means++ needs the training rows on the host (pass the numpy array)")
+        return k_means_init_reference_stream(rows, config, rng)
     vs = _as_device_rows(rows, config.dist)
     lo, hi = config.selected if config.selected is not None else (0, vs.dim)
     u = np.ascontiguousarray(rng.random(2 * config.k - 1), dtype=np.float64)
@@ -282,6 +317,9 @@ class KMeans:
         """KMeans::from_vec_set (k_means.rs:95-162). `rows` may be a host array or a DeviceVecSet."""
         if config.k <= 0:
             raise ValueError("The number of clusters should be greater than 0.")
+        from .rand_compat import StdRng
+        if init_centroids is None and isinstance(rng, StdRng):
+            init_centroids = k_means_init(rows, config, rng)   # the reference's stream: host rows (see k_means_init)
         vs = _as_device_rows(rows, config.dist)
         dim = vs.dim
         lo, hi = config.selected if config.selected is not None else (0, dim)
@@ -387,11 +425,21 @@ class PQTable:
         rows_host = np.ascontiguousarray(rows_host)
         train = rows_host
         if config.k_means_size is not None:
-            perm = rng.permutation(len(rows_host))[:config.k_means_size]  # VecSet::random_sample (vec_set.rs:154-163)
+            perm = sample_indices(rng, len(rows_host), config.k_means_size)  # VecSet::random_sample (vec_set.rs:154-163)
             train = np.ascontiguousarray(rows_host[perm])
         train_dev = DeviceVecSet(train, config.dist)  # the sample is uploaded once for all m groups
         try:
-            books = train_codebooks(train_dev, config, rng)
+            from .rand_compat import StdRng
+            init = None
+            if isinstance(rng, StdRng):
+                # the reference trains the groups one after the other on one stream (pq_table.rs:154-172); only the
+                # k-means++ of each group draws, so the initial centroids are fixed here in group order and Lloyd runs
+                # for all groups at once (bit-identical to the per-group runs given the same start)
+                k = 1 << config.n_bits
+                init = np.concatenate([
+                    k_means_init(train, KMeansConfig(k, config.k_means_max_iter, config.k_means_tol, config.dist, (lo, hi)),
+                                 rng).reshape(-1) for lo, hi in pq_groups(train.shape[1], config.m)])
+            books = train_codebooks(train_dev, config, rng, init)
         finally:
             train_dev.close()
         return cls(vec_set, config, books)
@@ -478,7 +526,7 @@ class IVFIndex:
         rows_host = np.ascontiguousarray(rows_host)
         train = rows_host
         if config.k_means_size is not None:
-            train = np.ascontiguousarray(rows_host[rng.permutation(len(rows_host))[:config.k_means_size]])
+            train = np.ascontiguousarray(rows_host[sample_indices(rng, len(rows_host), config.k_means_size)])
         km = KMeans.from_vec_set(train, KMeansConfig(config.k, config.k_means_max_iter, config.k_means_tol, dist), rng)
         if not isinstance(vec_set, DeviceVecSet):
             vec_set = DeviceVecSet(rows_host, dist)
@@ -537,7 +585,8 @@ class HNSWConfig(NamedTuple):
 
 def hnsw_rand_levels(n, M, rng):
     """rand_level (hnsw_index.rs:145-149) for n rows in row order: floor(-ln(u) / ln(M)), u uniform f32 in [0, 1)."""
-    u = rng.random(n, dtype=np.float32)
+    from .rand_compat import StdRng
+    u = rng.gen_unit_f32_array(n) if isinstance(rng, StdRng) else rng.random(n, dtype=np.float32)
     u = np.maximum(u, np.float32(2.0 ** -24))  # the reference would overflow usize on u == 0
     inv_log_m = np.float32(1.0) / np.log(np.float32(M))
     return np.floor(-np.log(u) * inv_log_m).astype(np.uint32)

@@ -178,3 +178,78 @@ def test_bench_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     other = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+# ---- rand_compat: the reference's random stream restated (rand 0.8.5 StdRng = ChaCha12) -------------------------------
+def test_chacha_core_matches_the_published_keystreams():
+    """Zero key, zero nonce, block 0: the keystream vectors published for ChaCha8 / ChaCha12 / ChaCha20 (the eSTREAM /
+    IETF test vectors for the original 64-bit-counter layout, which rand_chacha uses). This pins the block function and
+    the word order; the seeding and sampling layers above it are restated but cannot be pinned without the crates."""
+    from lab_1806_vec_db_b200.rand_compat import chacha_blocks
+    want = {
+        8: "3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e984ce172b9216f419f445367456d5619"
+           "314a42a3da86b001387bfdb80e0cfe42",
+        12: "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f0564f879d27ae3c02ce82834acfa8c79"
+            "3a629f2ca0de6919610be82f411326be",
+        20: "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7da41597c5157488d7724e03fb8d84a37"
+            "6a43b8f41518a11cc387b669b2ee6586",
+    }
+    for rounds, hexes in want.items():
+        got = chacha_blocks([0] * 8, 0, 1, rounds).astype("<u4").tobytes().hex()
+        assert got == hexes, rounds
+    # blocks are consecutive counters: block 1 of a 2-block call = a 1-block call at counter 1
+    two = chacha_blocks(list(range(1, 9)), 5, 2, 12)
+    assert (two[16:] == chacha_blocks(list(range(1, 9)), 6, 1, 12)).all()
+    assert not (two[:16] == two[16:]).all()
+
+
+def test_stdrng_draws_follow_the_restated_rand_algorithms():
+    from lab_1806_vec_db_b200.rand_compat import StdRng, k_means_init_indices
+    a, b = StdRng.seed_from_u64(42), StdRng.seed_from_u64(42)
+    w = [a.next_u32() for _ in range(6)]
+    assert b.next_u64() == w[0] | (w[1] << 32) and b.next_u32() == w[2]        # u64 = two consecutive words, low first
+    assert StdRng.seed_from_u64(43).next_u32() != w[0]
+    # gen_range: in range, one draw unless rejected, hi word of the widening multiply
+    r, s = StdRng.seed_from_u64(7), StdRng.seed_from_u64(7)
+    for n in (1, 2, 3, 1000, 10**6, 2**31 + 5, 1 << 20):
+        v = r.gen_range_usize(n)
+        while True:                                      # accept iff the low half of the product is inside the zone
+            x = s.next_u64()
+            lo, hi = (x * n) & (2**64 - 1), (x * n) >> 64
+            if lo <= ((n << (64 - n.bit_length())) & (2**64 - 1)) - 1:
+                break
+        assert 0 <= v < n and v == hi
+    assert r.next_u32() == s.next_u32()                  # both consumed the same number of words
+    draws = [StdRng.seed_from_u64(i).gen_range_u32(10) for i in range(400)]
+    assert min(draws) == 0 and max(draws) == 9 and 20 < draws.count(3) < 65
+    # shuffle: a permutation, n - 1 draws through the u32 path
+    r, s = StdRng.seed_from_u64(1), StdRng.seed_from_u64(1)
+    p = r.shuffle(100)
+    assert sorted(p.tolist()) == list(range(100)) and p.tolist() != list(range(100))
+    for i in range(99, 0, -1):
+        s.gen_range_u32(i + 1)
+    assert r.next_u32() == s.next_u32()
+    # WeightedIndex<f32>: zero weights are never picked, errors are None, the first index above the sample wins
+    r = StdRng.seed_from_u64(3)
+    picks = [r.weighted_index_f32(np.array([0, 1, 0, 3, 0], np.float32)) for _ in range(300)]
+    assert set(picks) == {1, 3} and 40 < picks.count(1) < 120
+    assert r.weighted_index_f32(np.zeros(4, np.float32)) is None
+    assert r.weighted_index_f32(np.array([1, -1], np.float32)) is None
+    assert r.weighted_index_f32(np.array([1, np.nan], np.float32)) is None
+    assert StdRng._uniform_f32_scale(0.0, 1.0) == np.float32(1.0)
+    u = StdRng.seed_from_u64(9).gen_unit_f32_array(1000)
+    assert u.dtype == np.float32 and (u >= 0).all() and (u < 1).all() and ((u * 2.0**23) % 1 == 0).all()
+    # k-means++ (k_means.rs:61-87): one usize draw, then per round a weighted sample (one word, skipped when
+    # WeightedIndex::new fails) AND the eagerly evaluated fallback draw (always)
+    n, k = 50, 5
+    r, s = StdRng.seed_from_u64(11), StdRng.seed_from_u64(11)
+    got = k_means_init_indices(lambda idx: np.zeros(n, np.float32), n, k, r)
+    assert got == [s.gen_range_usize(n) for _ in range(k)]                       # all-zero weights: the fallback wins
+    r, s = StdRng.seed_from_u64(12), StdRng.seed_from_u64(12)
+    wts = np.linspace(0, 1, n, dtype=np.float32)
+    got = k_means_init_indices(lambda idx: wts, n, k, r)
+    want = [s.gen_range_usize(n)]
+    for _ in range(1, k):
+        want.append(s.weighted_index_f32(wts))
+        s.gen_range_usize(n)                                                     # drawn and dropped
+    assert got == want and r.next_u32() == s.next_u32()

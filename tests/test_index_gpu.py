@@ -497,3 +497,41 @@ def test_pq_tensor_filter_m320(V, oracle):
         got = idx.knn_pq_batch(q, k, ef, pq)
         want = oracle.flat_knn_pq(base, codes, books, m, 4, q, k, ef, "l2sqr", nthreads=8)
         assert_knn_parity(base, q, "l2sqr", got, want, oracle)
+
+
+# ---- the reference's random stream (rand_compat.StdRng) driving the training entry points ------------------------------
+def test_kmeans_pp_under_the_restated_reference_stream(V):
+    """k-means++ (k_means.rs:61-87) with the reference's draw sequence: the GPU's weight updates (`vdb_kmeans_pp_weights`)
+    must be the bits of the sequential-f32 emulation, so the same stream picks the same rows; the training entry points
+    accept the stream in place of a numpy Generator (random_sample = the restated Fisher-Yates shuffle)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import np_emul as E
+    from lab_1806_vec_db_b200.index import k_means_init, sample_indices
+    from lab_1806_vec_db_b200.rand_compat import StdRng, k_means_init_indices
+    rng = np.random.default_rng(5)
+    rows = rng.random((600, 40), dtype=np.float32)
+    k = 12
+    for sel in (None, (8, 24)):
+        lo, hi = sel if sel else (0, rows.shape[1])
+        w = np.full(len(rows), np.inf, np.float32)
+
+        def update(idx):
+            np.minimum(w, E.l2sqr(np.broadcast_to(rows[idx, lo:hi], (len(rows), hi - lo)), rows[:, lo:hi]), out=w)
+            return w
+
+        want = k_means_init_indices(update, len(rows), k, StdRng.seed_from_u64(42))
+        cfg = V.KMeansConfig(k, 5, 1e-6, "l2sqr", sel)
+        got = k_means_init(rows, cfg, StdRng.seed_from_u64(42))
+        assert (bits(got) == bits(rows[want, lo:hi])).all()
+        km = V.KMeans.from_vec_set(rows, cfg, StdRng.seed_from_u64(42))
+        assert km.centroids.shape == (k, hi - lo)
+    # random_sample: the first entries of the shuffled index vector
+    assert (sample_indices(StdRng.seed_from_u64(1), 600, 100) == StdRng.seed_from_u64(1).shuffle(600)[:100]).all()
+    vs = V.DeviceVecSet(rows, "l2sqr")
+    pq = V.PQTable.from_vec_set(vs, rows, V.PQConfig(4, 10, "l2sqr", 200, 5, 1e-6), StdRng.seed_from_u64(42))
+    pq2 = V.PQTable.from_vec_set(vs, rows, V.PQConfig(4, 10, "l2sqr", 200, 5, 1e-6), StdRng.seed_from_u64(42))
+    assert (bits(pq.codebooks) == bits(pq2.codebooks)).all() and (pq.encoded_vec_set == pq2.encoded_vec_set).all()
+    ivf = V.IVFIndex.from_vec_set(vs, rows, "l2sqr", V.IVFConfig(8, 300, 5, 1e-6), StdRng.seed_from_u64(42))
+    assert ivf.centroids.shape == (8, rows.shape[1])
